@@ -1,0 +1,375 @@
+// Integer half of the hot path: game_logic.State on the GPU.
+//   K1 legal_mask      game_logic.py:103-357
+//   K2 build_graph     derived from game_logic.py:145-167 (edges) and 56-93 (features)
+//   K9 state_next      game_logic.py:43-54, 359-391
+// plus row68 <-> AqState packing and the ordered action list.
+#include <cstdio>
+#include <cstring>
+#include "aq_common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing (thread-local, no global mutable state shared between host threads)
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[256] = "ok";
+
+int aq_set_error(int code, const char *what) {
+    if (code > 0)
+        snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString((cudaError_t)code));
+    else
+        snprintf(g_err, sizeof g_err, "%s: invalid argument", what);
+    return code;
+}
+
+int aq_check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return aq_set_error((int)e, what);
+    return 0;
+}
+
+extern "C" int aq_version(void) { return 100; }
+extern "C" const char *aq_last_error_string(void) { return g_err; }
+
+using namespace aq;
+
+// ------------------------------------------------------------------------------------------
+// pack / unpack
+// ------------------------------------------------------------------------------------------
+__global__ void pack_states_kernel(const uint8_t *__restrict__ rows, const int16_t *__restrict__ plies, int64_t B,
+                                   AqState *__restrict__ out) {
+    // one warp per state: lanes 0..63 hold the wall entries (two per lane), ballot builds the bitboards
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const uint8_t *r = rows + 68 * b;
+    const uint8_t w0 = r[4 + lane], w1 = r[4 + 32 + lane];
+    const unsigned h0 = __ballot_sync(0xffffffffu, w0 == 1), h1 = __ballot_sync(0xffffffffu, w1 == 1);
+    const unsigned v0 = __ballot_sync(0xffffffffu, w0 == 2), v1 = __ballot_sync(0xffffffffu, w1 == 2);
+    if (lane == 0) {
+        uint4 a;
+        a.x = h0; a.y = h1; a.z = v0; a.w = v1;
+        uint4 c;
+        c.x = (unsigned)r[0] | ((unsigned)r[1] << 8) | ((unsigned)r[2] << 16) | ((unsigned)r[3] << 24);
+        c.y = plies ? (unsigned)(uint16_t)plies[b] : 0u;
+        c.z = 0; c.w = 0;
+        uint4 *o = reinterpret_cast<uint4 *>(out + b);
+        o[0] = a;
+        o[1] = c;
+    }
+}
+
+__global__ void unpack_states_kernel(const AqState *__restrict__ states, int64_t B, uint8_t *__restrict__ rows,
+                                     int16_t *__restrict__ plies) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const AqState s = load_state(states + b);
+    uint8_t *r = rows + 68 * b;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int slot = lane + 32 * k;
+        r[4 + slot] = (uint8_t)(((s.hwalls >> slot) & 1) | (((s.vwalls >> slot) & 1) << 1));
+    }
+    if (lane == 0) {
+        r[0] = s.ppos; r[1] = s.pwalls; r[2] = s.epos; r[3] = s.ewalls;
+        if (plies) plies[b] = (int16_t)s.plies;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 legal_mask: one warp per state.
+//   all lanes: open-direction bitboards, can_place + gate for all 128 candidates (bit-parallel)
+//   candidates whose gate fires are compacted into a per-warp list and dealt round-robin to the
+//   lanes; each lane runs the two flood fills for its candidates in registers.
+// ------------------------------------------------------------------------------------------
+constexpr int kLegalWarps = 4;
+
+__global__ void __launch_bounds__(kLegalWarps * 32)
+legal_mask_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__restrict__ mask,
+                  uint8_t *__restrict__ pawn) {
+    __shared__ uint8_t cand[kLegalWarps][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * kLegalWarps + warp;
+    if (b >= B) return;
+    const AqState s = load_state(states + b);
+    const Open base = open_from_walls(s.hwalls, s.vwalls);
+    const int me = s.ppos, en = 80 - (int)s.epos;  // enemy square in the mover's frame, game_logic.py:136
+
+    u64 legalH = 0, legalV = 0;
+    if (s.pwalls > 0) {  // game_logic.py:113
+        const WallSets ws = wall_sets(s.hwalls, s.vwalls);
+        legalH = ws.freeH;
+        legalV = ws.freeV;
+        // compact the candidates that need the search; order is irrelevant
+        const int nH = __popcll(ws.needH), total = nH + __popcll(ws.needV);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int slot = lane + 32 * k;
+            if ((ws.needH >> slot) & 1) cand[warp][__popcll(ws.needH & ((1ull << slot) - 1))] = (uint8_t)slot;
+            if ((ws.needV >> slot) & 1) cand[warp][nH + __popcll(ws.needV & ((1ull << slot) - 1))] = (uint8_t)(64 | slot);
+        }
+        __syncwarp();
+        u64 okH = 0, okV = 0;
+        for (int j = lane; j < total; j += 32) {
+            const int code = cand[warp][j];
+            const int slot = code & 63, orient = (code >> 6) + 1;
+            Open o = base;
+            add_wall(o, orient, slot);
+            // mover: start me, obstacle en, goal row 0; opponent (un-rotated frame): start en,
+            // obstacle me, goal row 8  (game_logic.py:332-348)
+            const bool ok = reaches(o, me, en, kRow0) && reaches(o, en, me, kRow8);
+            if (ok) {
+                if (orient == 1) okH |= 1ull << slot; else okV |= 1ull << slot;
+            }
+        }
+        // OR-reduce the per-lane results
+        unsigned a0 = __reduce_or_sync(0xffffffffu, (unsigned)okH), a1 = __reduce_or_sync(0xffffffffu, (unsigned)(okH >> 32));
+        unsigned c0 = __reduce_or_sync(0xffffffffu, (unsigned)okV), c1 = __reduce_or_sync(0xffffffffu, (unsigned)(okV >> 32));
+        legalH |= ((u64)a1 << 32) | a0;
+        legalV |= ((u64)c1 << 32) | c0;
+    }
+    if (lane == 0) {
+        uint8_t pm[8] = {0, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0, 0};
+        const int n = pawn_moves(base, me, en, pm + 1);
+        pm[0] = (uint8_t)n;
+        u128 lo = 0;
+        for (int k = 0; k < n; ++k) lo |= bit81(pm[1 + k]);
+        lo |= (u128)legalH << 81;                                  // H wall actions 81..144
+        const u128 hi = (u128)(legalH >> 47) | ((u128)legalV << 17);  // V wall actions 145..208
+        uint4 *m = reinterpret_cast<uint4 *>(mask + 8 * b);
+        uint4 w;
+        w.x = (unsigned)lo; w.y = (unsigned)(lo >> 32); w.z = (unsigned)(lo >> 64); w.w = (unsigned)(lo >> 96);
+        m[0] = w;
+        w.x = (unsigned)hi; w.y = (unsigned)(hi >> 32); w.z = (unsigned)(hi >> 64); w.w = (unsigned)(hi >> 96);
+        m[1] = w;
+        uint2 p;
+        p.x = pm[0] | (pm[1] << 8) | (pm[2] << 16) | ((unsigned)pm[3] << 24);
+        p.y = pm[4] | (pm[5] << 8);
+        *reinterpret_cast<uint2 *>(pawn + 8 * b) = p;
+    }
+}
+
+// ordered action list (State.legal_actions() order): pawn list, then per slot H before V
+__global__ void legal_list_kernel(const uint32_t *__restrict__ mask, const uint8_t *__restrict__ pawn, int64_t B,
+                                  int16_t *__restrict__ actions, int16_t *__restrict__ n_actions) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const uint32_t *m = mask + 8 * b;
+    int16_t *out = actions + (int64_t)AQ_MAX_LEGAL * b;
+    const int np = pawn[8 * b];
+    // interleaved candidate index c = 2*slot + (0 H | 1 V); lane handles c = lane + 32*k, k<4
+    int base = np;
+    for (int k = 0; k < 4; ++k) {
+        const int c = lane + 32 * k;
+        const int slot = c >> 1;
+        const int a = (c & 1) ? (AQ_SQUARES + AQ_SLOTS + slot) : (AQ_SQUARES + slot);
+        const bool on = (m[a >> 5] >> (a & 31)) & 1;
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (on) out[base + __popc(bal & ((1u << lane) - 1))] = (int16_t)a;
+        base += __popc(bal);
+    }
+    for (int k = lane; k < AQ_MAX_LEGAL; k += 32) {
+        if (k < np) out[k] = pawn[8 * b + 1 + k];
+        else if (k >= base) out[k] = -1;
+    }
+    if (lane == 0 && n_actions) n_actions[b] = (int16_t)base;
+}
+
+// ------------------------------------------------------------------------------------------
+// K9 state_next
+// ------------------------------------------------------------------------------------------
+__global__ void state_next_kernel(const AqState *__restrict__ states, const int16_t *__restrict__ actions, int64_t B,
+                                  AqState *__restrict__ out, uint8_t *__restrict__ terminal) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    AqState s = load_state(states + b);
+    const int a = actions[b];
+    int ppos = s.ppos, pwalls = s.pwalls;
+    if (a < AQ_SQUARES) {
+        ppos = a;
+    } else if (a < AQ_SQUARES + AQ_SLOTS) {
+        s.hwalls |= 1ull << (a - AQ_SQUARES);
+        pwalls -= 1;
+    } else {
+        s.vwalls |= 1ull << (a - AQ_SQUARES - AQ_SLOTS);
+        pwalls -= 1;
+    }
+    const u64 h = __brevll(s.hwalls), v = __brevll(s.vwalls);  // rotate_walls: walls'[i] = walls[63-i]
+    const unsigned plies = s.plies + 1u;
+    uint4 x, y;
+    x.x = (unsigned)h; x.y = (unsigned)(h >> 32); x.z = (unsigned)v; x.w = (unsigned)(v >> 32);
+    // swap players: the successor's player is the old enemy
+    y.x = (unsigned)s.epos | ((unsigned)s.ewalls << 8) | ((unsigned)(ppos & 0xFF) << 16) | ((unsigned)(pwalls & 0xFF) << 24);
+    y.y = plies & 0xFFFFu;
+    y.z = 0; y.w = 0;
+    uint4 *o = reinterpret_cast<uint4 *>(out + b);
+    o[0] = x;
+    o[1] = y;
+    if (terminal) {
+        const int lose = (ppos / AQ_N) == 0;  // successor.enemy[0] // N == 0, game_logic.py:43-46
+        const int draw = plies >= AQ_PLIES_FOR_DRAW;
+        terminal[b] = (uint8_t)(lose | (draw << 1));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 build_graph: one warp per board
+// ------------------------------------------------------------------------------------------
+__device__ __constant__ float kDinv[6] = {0.f, 1.0f, 0.70710678118654752f, 0.57735026918962576f, 0.5f,
+                                          0.44721359549995794f};
+
+__global__ void build_graph_kernel(const AqState *__restrict__ states, int64_t B, uint8_t *__restrict__ open_mask,
+                                   float *__restrict__ dinv, float *__restrict__ x, int32_t *__restrict__ edge_count) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const AqState s = load_state(states + b);
+    const Open o = open_from_walls(s.hwalls, s.vwalls);
+    const u128 eh = expand8to9(s.hwalls), ev = expand8to9(s.vwalls);
+    int edges = 0;
+    for (int v = lane; v < AQ_SQUARES; v += 32) {
+        const int m = (int)has(o.up, v) | ((int)has(o.down, v) << 1) | ((int)has(o.left, v) << 2) | ((int)has(o.right, v) << 3);
+        edges += __popc(m);
+        if (open_mask) open_mask[b * AQ_SQUARES + v] = (uint8_t)m;
+        if (dinv) dinv[b * AQ_SQUARES + v] = kDinv[1 + __popc(m)];
+        if (x) {
+            float2 *px = reinterpret_cast<float2 *>(x + (b * AQ_SQUARES + v) * AQ_FEATURES);
+            px[0] = make_float2(v == s.ppos ? 1.f : 0.f, (float)s.pwalls);
+            px[1] = make_float2(v == s.epos ? 1.f : 0.f, (float)s.ewalls);  // enemy's own frame, quirk KA11
+            px[2] = make_float2(has(eh, v) ? 1.f : 0.f, has(ev, v) ? 1.f : 0.f);
+        }
+    }
+    if (edge_count) {
+        edges = __reduce_add_sync(0xffffffffu, edges);
+        if (lane == 0) edge_count[b] = edges;
+    }
+}
+
+__global__ void build_edge_index_kernel(const uint8_t *__restrict__ open_mask, const int64_t *__restrict__ edge_offset,
+                                        int64_t B, int64_t *__restrict__ src, int64_t *__restrict__ dst) {
+    // one warp per board; canonical order: node ascending, directions U,D,L,R
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    int64_t base = edge_offset[b];
+    const int delta[4] = {-9, 9, -1, 1};
+    for (int v0 = 0; v0 < 96; v0 += 32) {
+        const int v = v0 + lane;
+        const int m = v < AQ_SQUARES ? open_mask[b * AQ_SQUARES + v] : 0;
+        const int cnt = __popc(m);
+        // exclusive prefix over lanes
+        int pre = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, pre, d);
+            if (lane >= d) pre += t;
+        }
+        const int tot = __shfl_sync(0xffffffffu, pre, 31);
+        int64_t at = base + pre - cnt;
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            if ((m >> d) & 1) {
+                src[at] = b * AQ_SQUARES + v;
+                dst[at] = b * AQ_SQUARES + v + delta[d];
+                ++at;
+            }
+        base += tot;
+    }
+}
+
+__global__ void edges_to_open_mask_kernel(const int64_t *__restrict__ src, const int64_t *__restrict__ dst, int64_t E,
+                                          int64_t B, unsigned *__restrict__ open_words, int32_t *__restrict__ bad) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const int64_t s = src[e], t = dst[e];
+    if (s == t) return;  // self loops are dropped by gcn_norm and re-added
+    const int64_t b = s / AQ_SQUARES;
+    const int v = (int)(s - b * AQ_SQUARES), u = (int)(t - b * AQ_SQUARES);
+    int d = -1;
+    if (s >= 0 && b < B && t / AQ_SQUARES == b && t >= 0) {
+        const int diff = u - v;
+        if (diff == -9) d = 0;
+        else if (diff == 9) d = 1;
+        else if (diff == -1 && v % AQ_N != 0) d = 2;
+        else if (diff == 1 && v % AQ_N != AQ_N - 1) d = 3;
+    }
+    if (d < 0) { atomicExch(bad, 1); return; }
+    // byte v of board b inside a word array (4 bytes per word)
+    const int64_t byte = b * AQ_SQUARES + v;
+    atomicOr(open_words + (byte >> 2), (1u << d) << (8 * (int)(byte & 3)));
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+static inline cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+extern "C" int aq_pack_states(const uint8_t *rows68, const int16_t *plies, int64_t B, AqState *out, void *stream) {
+    if (B < 0 || (B > 0 && (!rows68 || !out))) return aq_set_error(AQ_ERR_ARG, "aq_pack_states");
+    if (B == 0) return 0;
+    pack_states_kernel<<<blocks_for(B, 8), 256, 0, S(stream)>>>(rows68, plies, B, out);
+    return aq_check_launch("aq_pack_states");
+}
+
+extern "C" int aq_unpack_states(const AqState *states, int64_t B, uint8_t *rows68, int16_t *plies, void *stream) {
+    if (B < 0 || (B > 0 && (!rows68 || !states))) return aq_set_error(AQ_ERR_ARG, "aq_unpack_states");
+    if (B == 0) return 0;
+    unpack_states_kernel<<<blocks_for(B, 8), 256, 0, S(stream)>>>(states, B, rows68, plies);
+    return aq_check_launch("aq_unpack_states");
+}
+
+extern "C" int aq_legal_mask(const AqState *states, int64_t B, uint32_t *mask, uint8_t *pawn, void *stream) {
+    if (B < 0 || (B > 0 && (!states || !mask || !pawn))) return aq_set_error(AQ_ERR_ARG, "aq_legal_mask");
+    if (B == 0) return 0;
+    legal_mask_kernel<<<blocks_for(B, kLegalWarps), kLegalWarps * 32, 0, S(stream)>>>(states, B, mask, pawn);
+    return aq_check_launch("aq_legal_mask");
+}
+
+extern "C" int aq_legal_actions_list(const uint32_t *mask, const uint8_t *pawn, int64_t B, int16_t *actions,
+                                     int16_t *n_actions, void *stream) {
+    if (B < 0 || (B > 0 && (!mask || !pawn || !actions))) return aq_set_error(AQ_ERR_ARG, "aq_legal_actions_list");
+    if (B == 0) return 0;
+    legal_list_kernel<<<blocks_for(B, 8), 256, 0, S(stream)>>>(mask, pawn, B, actions, n_actions);
+    return aq_check_launch("aq_legal_actions_list");
+}
+
+extern "C" int aq_state_next(const AqState *states, const int16_t *actions, int64_t B, AqState *out, uint8_t *terminal,
+                             void *stream) {
+    if (B < 0 || (B > 0 && (!states || !actions || !out))) return aq_set_error(AQ_ERR_ARG, "aq_state_next");
+    if (B == 0) return 0;
+    state_next_kernel<<<blocks_for(B, 256), 256, 0, S(stream)>>>(states, actions, B, out, terminal);
+    return aq_check_launch("aq_state_next");
+}
+
+extern "C" int aq_build_graph(const AqState *states, int64_t B, uint8_t *open_mask, float *dinv, float *x,
+                              int32_t *edge_count, void *stream) {
+    if (B < 0 || (B > 0 && !states)) return aq_set_error(AQ_ERR_ARG, "aq_build_graph");
+    if (B == 0) return 0;
+    build_graph_kernel<<<blocks_for(B, 8), 256, 0, S(stream)>>>(states, B, open_mask, dinv, x, edge_count);
+    return aq_check_launch("aq_build_graph");
+}
+
+extern "C" int aq_build_edge_index(const uint8_t *open_mask, const int64_t *edge_offset, int64_t B, int64_t *src,
+                                   int64_t *dst, void *stream) {
+    if (B < 0 || (B > 0 && (!open_mask || !edge_offset || !src || !dst)))
+        return aq_set_error(AQ_ERR_ARG, "aq_build_edge_index");
+    if (B == 0) return 0;
+    build_edge_index_kernel<<<blocks_for(B, 8), 256, 0, S(stream)>>>(open_mask, edge_offset, B, src, dst);
+    return aq_check_launch("aq_build_edge_index");
+}
+
+extern "C" int aq_edges_to_open_mask(const int64_t *src, const int64_t *dst, int64_t E, int64_t B, uint8_t *open_mask,
+                                     int32_t *bad, void *stream) {
+    if (B < 0 || E < 0 || !open_mask || !bad || (E > 0 && (!src || !dst)))
+        return aq_set_error(AQ_ERR_ARG, "aq_edges_to_open_mask");
+    // open_mask must be 4-byte aligned and padded to a multiple of 4 bytes (caller allocates B*81 rounded up)
+    if ((reinterpret_cast<uintptr_t>(open_mask) & 3) != 0) return aq_set_error(AQ_ERR_ARG, "aq_edges_to_open_mask(align)");
+    cudaError_t e = cudaMemsetAsync(open_mask, 0, (size_t)((B * AQ_SQUARES + 3) / 4 * 4), S(stream));
+    if (e != cudaSuccess) return aq_set_error((int)e, "aq_edges_to_open_mask");
+    e = cudaMemsetAsync(bad, 0, sizeof(int32_t), S(stream));
+    if (e != cudaSuccess) return aq_set_error((int)e, "aq_edges_to_open_mask");
+    if (E == 0) return 0;
+    edges_to_open_mask_kernel<<<blocks_for(E, 256), 256, 0, S(stream)>>>(src, dst, E, B, reinterpret_cast<unsigned *>(open_mask), bad);
+    return aq_check_launch("aq_edges_to_open_mask");
+}

@@ -1,0 +1,147 @@
+/*
+ * aqgnn.h -- C ABI of libaqgnn.so, the sm_100a CUDA implementation of the AlphaQuoridorGNN
+ * hot path (game_logic legal moves / wall legality, board-graph construction, the
+ * pv_network_gnn GCN forward/backward, batched leaf evaluation and lock-step PV-MCTS).
+ *
+ * The reference (ApproximateCaesar/AlphaQuoridorGNN) is pure Python and has no FFI; the
+ * boundary it exposes is the duck-typed BaseNetwork object (BaseNetwork.py:9-54) plus
+ * game_logic.State (game_logic.py:15-395).  Each entry point below names the reference
+ * function it replaces.  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates
+ *     nothing persistent, and keeps no global mutable state (re-entrant per stream);
+ *   - return value: 0 = ok, >0 = cudaError_t of the launch, <0 = argument error
+ *     (AQ_ERR_*); aq_last_error_string() describes the last failure on this host thread;
+ *   - board is 9x9: 81 squares, 64 wall slots, 209 actions (game_logic.py:105-108).
+ */
+#ifndef AQGNN_H
+#define AQGNN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AQ_N 9
+#define AQ_SQUARES 81
+#define AQ_SLOTS 64
+#define AQ_ACTIONS 209
+#define AQ_MASK_WORDS 8      /* 256-bit legal mask, bit a = action a */
+#define AQ_MAX_LEGAL 136     /* 5 pawn moves + 128 wall actions, rounded up */
+#define AQ_FEATURES 6        /* pv_network_gnn.py:17 */
+#define AQ_HIDDEN 128        /* pv_network_gnn.py:18 */
+#define AQ_HEAD_HIDDEN 64    /* hidden_dim // 2, pv_network_gnn.py:39,47 */
+#define AQ_PLIES_FOR_DRAW 116 /* constants.py:20 */
+
+#define AQ_ERR_ARG (-1)
+#define AQ_ERR_UNSUPPORTED (-2)
+
+/* Packed game state, 32 bytes.  Mirrors game_logic.State (game_logic.py:15-40):
+ *   hwalls bit s  <=> walls[s] == 1,  vwalls bit s <=> walls[s] == 2   (s = 8*row + col)
+ *   ppos/pwalls = State.player, epos/ewalls = State.enemy (epos in the ENEMY's own frame),
+ *   plies = State.plies_played.  rotate_walls() (game_logic.py:359-364) is a 64-bit
+ *   bit reversal in this layout. */
+typedef struct AqState {
+    uint64_t hwalls;
+    uint64_t vwalls;
+    uint8_t ppos, pwalls, epos, ewalls;
+    uint16_t plies;
+    uint16_t flags;    /* reserved, 0 */
+    uint64_t reserved; /* reserved, 0 */
+} AqState;
+
+int aq_version(void);
+const char *aq_last_error_string(void);
+
+/* State.to_array() rows ("row68": uint8[68] = player[2], enemy[2], walls[64]) <-> AqState.
+ * Replaces the python list handling of game_logic.py:96-100. */
+int aq_pack_states(const uint8_t *rows68, const int16_t *plies, int64_t B, AqState *out, void *stream);
+int aq_unpack_states(const AqState *states, int64_t B, uint8_t *rows68, int16_t *plies, void *stream);
+
+/* State.legal_actions() (game_logic.py:103-117) for B states: legal_actions_pos (120-192),
+ * can_place_wall (199-223), the touch-count gate (227-307,327-328) and both path-existence
+ * searches (309-348), bit-exact.
+ *   mask [B,8] uint32 : bit a set iff action a is legal
+ *   pawn [B,8] uint8  : [n_pawn, p0..p4 in the reference's U,D,L,R/jump order (0xFF pad), 0, 0]
+ * The ordered action list is pawn[1..n] followed by the wall bits of `mask` in ascending
+ * slot order, H before V per slot (game_logic.py:352-355); aq_legal_actions_list emits it. */
+int aq_legal_mask(const AqState *states, int64_t B, uint32_t *mask, uint8_t *pawn, void *stream);
+int aq_legal_actions_list(const uint32_t *mask, const uint8_t *pawn, int64_t B, int16_t *actions /*[B,136], -1 pad*/,
+                          int16_t *n_actions /*[B]*/, void *stream);
+
+/* State.next() + is_lose()/is_draw() of the successor (game_logic.py:43-54, 359-391).
+ * terminal[b] bit0 = successor.is_lose(), bit1 = successor.is_draw(). terminal may be NULL. */
+int aq_state_next(const AqState *states, const int16_t *actions, int64_t B, AqState *out, uint8_t *terminal,
+                  void *stream);
+
+/* Board graph + node features (derived from game_logic.py:145-167 and 56-93; the reference has
+ * no graph builder -- SURVEY.md section 8a A6).
+ *   open_mask [B,81] uint8 : bit k = direction k of MOVEMENT_DIRECTIONS (U,D,L,R) is an edge
+ *   dinv      [B,81] f32   : (1 + popcount(open))^-1/2   (gcn_norm with self loops)
+ *   x         [B*81,6] f32 : the 6 planes of State.pieces_array read at each square
+ *   edge_count[B] int32    : directed edges of board b (may be NULL) */
+int aq_build_graph(const AqState *states, int64_t B, uint8_t *open_mask, float *dinv, float *x, int32_t *edge_count,
+                   void *stream);
+/* PyG-style edge_index for GraphPolicyValueNetwork.forward(x, edge_index, batch)
+ * (pv_network_gnn.py:53): edge_offset[B] = exclusive scan of edge_count; src/dst int64[E]. */
+int aq_build_edge_index(const uint8_t *open_mask, const int64_t *edge_offset, int64_t B, int64_t *src, int64_t *dst,
+                        void *stream);
+/* Inverse, for callers that hand us (x, edge_index, batch): rebuild open masks; bad[0] is set
+ * non-zero if an edge does not join 4-neighbours of one 9x9 board. */
+int aq_edges_to_open_mask(const int64_t *src, const int64_t *dst, int64_t E, int64_t B, uint8_t *open_mask,
+                          int32_t *bad, void *stream);
+
+/* GraphPolicyValueNetwork.forward (pv_network_gnn.py:53-64 + PyG GCNConv/global_mean_pool).
+ * params: flat f32[64082] in state_dict order (see aq_param_count / DESIGN.md).
+ * Inputs are either `states` (graph built in-kernel) or (x, open_mask) when states == NULL.
+ *   policy [B,209] softmax probabilities, value [B] tanh.
+ *   saved  NULL for inference, else workspace of aq_gnn_saved_floats(B) floats kept for backward.
+ *   precision 0 = fp32 FFMA path, 1 = bf16 tcgen05 tensor-core path (inference only). */
+int64_t aq_param_count(void);
+int64_t aq_gnn_saved_floats(int64_t B);
+int aq_gnn_forward(const float *params, const AqState *states, const float *x, const uint8_t *open_mask, int64_t B,
+                   float *policy, float *value, float *saved, int precision, void *stream);
+
+/* Backward of the above (autograd of train_network.py:93).  dpolicy [B,209], dvalue [B] are the
+ * loss gradients w.r.t. the softmax / tanh outputs; grads f32[64082] is OVERWRITTEN with the
+ * parameter gradients (flat, same order as params); workspace of aq_gnn_backward_ws_floats(B). */
+int64_t aq_gnn_backward_ws_floats(int64_t B);
+int aq_gnn_backward(const float *params, const float *saved, const float *dpolicy, const float *dvalue, int64_t B,
+                    float *grads, float *workspace, void *stream);
+
+/* Loss of train_network.py:54-55,85-89: CrossEntropyLoss applied to the softmax OUTPUT (so a
+ * second log_softmax; kept literally) + MSELoss, both 'mean' over B_total (= global batch under
+ * data parallelism).  Writes loss[0] = policy loss sum over this shard / B_total, loss[1] = value
+ * part, and the gradients dpolicy [B,209], dvalue [B]. */
+int aq_loss_grad(const float *policy, const float *value, const float *policy_target, const float *value_target,
+                 int64_t B, int64_t B_total, float *loss, float *dpolicy, float *dvalue, void *stream);
+
+/* torch.optim.Adam step (train_network.py:56,94; default betas/eps, no weight decay) on the flat
+ * buffers. step is the 1-based step count; lr already includes the LambdaLR factor. */
+int aq_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, int64_t step,
+                 float lr, float beta1, float beta2, float eps, float grad_scale, void *stream);
+
+/* Batched BaseNetwork.predict (BaseNetwork.py:36-40; behaviour pv_network_cnn.py:117-137):
+ * legal mask + graph + forward + restriction to legal actions + renormalisation, for B leaves.
+ *   priors [B,209]: p[a]/sum_legal p for legal a, 0 elsewhere (sum==0 -> left unnormalised, as
+ *                   `policy /= sum if sum else 1`)
+ *   value  [B], mask [B,8], pawn [B,8] as in aq_legal_mask. */
+int aq_leaf_eval(const float *params, const AqState *states, int64_t B, float *priors, float *value, uint32_t *mask,
+                 uint8_t *pawn, float *workspace /* aq_leaf_eval_ws_floats(B) */, int precision, void *stream);
+int64_t aq_leaf_eval_ws_floats(int64_t B);
+
+/* Same through HOST buffers (pinned or pageable): copies states H2D, runs, copies priors/value/
+ * mask/pawn D2H on `stream`, then synchronises the stream.  dev_ws is a device workspace of
+ * aq_leaf_eval_host_ws_bytes(B) bytes. */
+int64_t aq_leaf_eval_host_ws_bytes(int64_t B);
+int aq_leaf_eval_host(const float *params, const AqState *states_host, int64_t B, float *priors_host,
+                      float *value_host, uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision,
+                      void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AQGNN_H */
