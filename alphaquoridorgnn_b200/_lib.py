@@ -1,0 +1,87 @@
+"""ctypes loader for libaqgnn.so (the C ABI of include/aqgnn.h).
+
+There is no CPU fallback: if the shared library is missing or a kernel launch fails this raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libaqgnn.so")
+
+# name -> (restype, argtypes); must list every symbol declared in include/aqgnn.h
+_vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
+SYMBOLS = {
+    "aq_version": (_i32, []),
+    "aq_last_error_string": (ctypes.c_char_p, []),
+    "aq_pack_states": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "aq_unpack_states": (_i32, [_vp, _i64, _vp, _vp, _vp]),
+    "aq_legal_mask": (_i32, [_vp, _i64, _vp, _vp, _vp]),
+    "aq_legal_actions_list": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "aq_state_next": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "aq_build_graph": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "aq_build_edge_index": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "aq_edges_to_open_mask": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "aq_param_count": (_i64, []),
+    "aq_gnn_saved_floats": (_i64, [_i64]),
+    "aq_gnn_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
+    "aq_gcn_trunk_forward": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp]),
+    "aq_heads_forward": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "aq_gnn_backward_ws_floats": (_i64, [_i64]),
+    "aq_gnn_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "aq_loss_grad": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "aq_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "aq_leaf_eval": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "aq_leaf_eval_ws_floats": (_i64, [_i64]),
+    "aq_leaf_eval_host_ws_bytes": (_i64, [_i64]),
+    "aq_leaf_eval_host": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+}
+
+_lib = None
+
+
+class AqError(RuntimeError):
+    pass
+
+
+def load(build_if_missing=True):
+    """Load libaqgnn.so, building it with nvcc if it is absent. Raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise AqError(f"{LIB_PATH} is missing; run `python -m alphaquoridorgnn_b200.build`")
+        from . import build as _build
+        _build.build()
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().aq_last_error_string().decode()
+        raise AqError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / None."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "libaqgnn expects contiguous tensors"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise AqError(f"{name} must be a CUDA tensor: the AlphaQuoridorGNN hot path has no CPU fallback")

@@ -1,0 +1,448 @@
+// Backward of GraphPolicyValueNetwork (autograd of train_network.py:93) -- fp32, atomic-free and
+// deterministic.  A_hat is symmetric (is_wall_blocking is symmetric, game_logic.py:145-167), so the
+// transposed-CSR scatter of the backward pass is the same 5-point gather as the forward.
+//   heads_backward_kernel : softmax/tanh/MLP backward per board -> dz, dhp, dhv, du, dg
+//   gcn_backward_kernel   : per board dY_l, dZ_l = A_hat dY_l, dX_{l-1} = dZ_l W_l ; bias partials
+//   atb_jobs_kernel       : all weight gradients dW = A^T B as split-row partial GEMMs (one launch)
+//   reduce_partials_kernel: grads[i] = sum over slots of partial[slot][i]
+// plus the loss gradient of train_network.py:54-55,85-89 and the Adam step.
+#include "gnn_fp32.cuh"
+
+using namespace aq;
+
+constexpr int kSlots = 148;  // partial-gradient slots (one per persistent CTA / row chunk)
+
+struct BwdWs {
+    int64_t B;
+    __host__ __device__ int64_t dz3() const { return 0; }
+    __host__ __device__ int64_t dz2() const { return B * kV * kH; }
+    __host__ __device__ int64_t dy1() const { return 2 * B * kV * kH; }
+    __host__ __device__ int64_t dg() const { return 3 * B * kV * kH; }
+    __host__ __device__ int64_t dhp() const { return dg() + B * kH; }
+    __host__ __device__ int64_t dhv() const { return dhp() + B * kHH; }
+    __host__ __device__ int64_t dz() const { return dhv() + B * kHH; }
+    __host__ __device__ int64_t du() const { return dz() + B * kP; }
+    __host__ __device__ int64_t partial() const { return (du() + B + 3) / 4 * 4; }
+    __host__ __device__ int64_t total() const { return partial() + (int64_t)kSlots * kNumParams; }
+};
+
+// ------------------------------------------------------------------------------------------
+// heads backward: one warp per board
+// ------------------------------------------------------------------------------------------
+constexpr int kHbThreads = 256;
+struct HeadBwdSmem {
+    float wp2[kP * kHH];  // [a][j]
+    float wp0[kHH * kH];  // [j][k]
+    float wv0[kHH * kH];
+    float wv2[kHH];
+    float dz[kHbThreads / 32][224];
+    float dh[kHbThreads / 32][2 * kHH];  // dhp | dhv
+};
+
+__global__ void __launch_bounds__(kHbThreads, 1)
+heads_backward_kernel(const float *__restrict__ params, const float *__restrict__ saved,
+                      const float *__restrict__ dpolicy, const float *__restrict__ dvalue, int64_t B,
+                      float *__restrict__ ws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HeadBwdSmem &sm = *reinterpret_cast<HeadBwdSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < kP * kHH; i += kHbThreads) sm.wp2[i] = __ldg(params + kOffWP2 + i);
+    for (int i = tid; i < kHH * kH; i += kHbThreads) {
+        sm.wp0[i] = __ldg(params + kOffWP0 + i);
+        sm.wv0[i] = __ldg(params + kOffWV0 + i);
+    }
+    if (tid < kHH) sm.wv2[tid] = __ldg(params + kOffWV2 + tid);
+    __syncthreads();
+    const SavedLayout L{B};
+    const BwdWs W{B};
+    const int nwarps = kHbThreads / 32;
+    for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
+        __syncwarp();
+        // softmax backward: dz = p * (dp - sum_j dp_j p_j)
+        float p[7], dp[7], s = 0.f;
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            const int a = lane + 32 * t;
+            p[t] = a < kP ? saved[L.policy() + b * kP + a] : 0.f;
+            dp[t] = a < kP ? __ldg(dpolicy + b * kP + a) : 0.f;
+            s = fmaf(dp[t], p[t], s);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            const int a = lane + 32 * t;
+            const float dz = p[t] * (dp[t] - s);
+            sm.dz[warp][a] = dz;
+            if (a < kP) ws[W.dz() + b * kP + a] = dz;
+        }
+        __syncwarp();
+        // dhp = (Wp2^T dz) * (hp > 0); outputs j = lane, lane+32
+        float h0 = 0.f, h1 = 0.f;
+#pragma unroll 4
+        for (int a = 0; a < kP; ++a) {
+            const float dz = sm.dz[warp][a];
+            h0 = fmaf(dz, sm.wp2[a * kHH + lane], h0);
+            h1 = fmaf(dz, sm.wp2[a * kHH + lane + 32], h1);
+        }
+        const float hp0 = saved[L.hp() + b * kHH + lane], hp1 = saved[L.hp() + b * kHH + lane + 32];
+        h0 = hp0 > 0.f ? h0 : 0.f;
+        h1 = hp1 > 0.f ? h1 : 0.f;
+        // value head: v = tanh(u); du = dv * (1 - v^2); dhv = du * wv2 * (hv > 0)
+        const float v = saved[L.value() + b];
+        const float du = __ldg(dvalue + b) * (1.f - v * v);
+        const float hv0 = saved[L.hv() + b * kHH + lane], hv1 = saved[L.hv() + b * kHH + lane + 32];
+        const float g0 = hv0 > 0.f ? du * sm.wv2[lane] : 0.f;
+        const float g1 = hv1 > 0.f ? du * sm.wv2[lane + 32] : 0.f;
+        sm.dh[warp][lane] = h0; sm.dh[warp][lane + 32] = h1;
+        sm.dh[warp][kHH + lane] = g0; sm.dh[warp][kHH + lane + 32] = g1;
+        ws[W.dhp() + b * kHH + lane] = h0; ws[W.dhp() + b * kHH + lane + 32] = h1;
+        ws[W.dhv() + b * kHH + lane] = g0; ws[W.dhv() + b * kHH + lane + 32] = g1;
+        if (lane == 0) ws[W.du() + b] = du;
+        __syncwarp();
+        // dg = Wp0^T dhp + Wv0^T dhv ; outputs k = lane + 32 t
+        float dg[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int j = 0; j < kHH; ++j) {
+            const float a = sm.dh[warp][j], c = sm.dh[warp][kHH + j];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                dg[t] = fmaf(a, sm.wp0[j * kH + lane + 32 * t], dg[t]);
+                dg[t] = fmaf(c, sm.wv0[j * kH + lane + 32 * t], dg[t]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) ws[W.dg() + b * kH + lane + 32 * t] = dg[t];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// GCN backward: one board per CTA iteration
+// ------------------------------------------------------------------------------------------
+struct GcnBwdSmem {
+    float w2[kH * kH];  // natural [n][k]: dX = dZ W reduces over n
+    float w3[kH * kH];
+    float bufa[kV * kH];
+    float bufb[kV * kH];
+    float pad[7 * kH];  // GEMM over-read of bufb rows 81..87
+    float coef[kV * 5 + 3];
+    float dg[kH];
+    float red[256];
+};
+static_assert(sizeof(GcnBwdSmem) <= 227 * 1024, "GcnBwdSmem too large");
+
+__device__ __forceinline__ void colsum_accumulate(const float *buf, float &acc, int tid) {
+    const int n = tid & (kH - 1);
+    float s = 0.f;
+    for (int v = tid >> 7; v < kV; v += 2) s += buf[v * kH + n];
+    acc += s;
+}
+
+__global__ void __launch_bounds__(kGcnThreads, 1)
+gcn_backward_kernel(const float *__restrict__ params, const float *__restrict__ saved, int64_t B,
+                    float *__restrict__ ws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GcnBwdSmem &sm = *reinterpret_cast<GcnBwdSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const SavedLayout L{B};
+    const BwdWs W{B};
+    float db1 = 0.f, db2 = 0.f, db3 = 0.f;  // per-thread partial column sums (column tid & 127)
+    if ((int64_t)blockIdx.x < B) {
+        load_weight_natural(sm.w2, params + kOffW2, tid);
+        load_weight_natural(sm.w3, params + kOffW3, tid);
+    }
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int i = tid; i < kV * 5; i += kGcnThreads) sm.coef[i] = saved[L.coef() + b * kV * 5 + i];
+        if (tid < kH) sm.dg[tid] = ws[W.dg() + b * kH + tid] / (float)kV;  // d mean / d x_v
+        __syncthreads();
+        // dY3 = (X3 > 0) * dg/81
+        {
+            const float4 *x3 = reinterpret_cast<const float4 *>(saved + L.x(2) + b * kV * kH);
+            const float4 d = reinterpret_cast<const float4 *>(sm.dg)[lane];
+            for (int i = tid; i < kV * kH / 4; i += kGcnThreads) {  // i & 31 == lane
+                const float4 x = x3[i];
+                reinterpret_cast<float4 *>(sm.bufa)[i] = make_float4(x.x > 0.f ? d.x : 0.f, x.y > 0.f ? d.y : 0.f,
+                                                                     x.z > 0.f ? d.z : 0.f, x.w > 0.f ? d.w : 0.f);
+            }
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int layer = 2; layer >= 1; --layer) {
+            // bufa = dY_{layer+1}; bias gradient and dZ = A_hat dY
+            colsum_accumulate(sm.bufa, layer == 2 ? db3 : db2, tid);
+            aggregate<false>(sm.bufa, sm.bufb, sm.coef, nullptr, warp, lane);
+            __syncthreads();
+            {
+                float4 *dst = reinterpret_cast<float4 *>(ws + (layer == 2 ? W.dz3() : W.dz2()) + b * kV * kH);
+                const float4 *src = reinterpret_cast<const float4 *>(sm.bufb);
+                for (int i = tid; i < kV * kH / 4; i += kGcnThreads) dst[i] = src[i];
+            }
+            // dX_layer = dZ W ; dY_layer = (X_layer > 0) * dX_layer
+            float acc[kRowsPerWarp][4];
+            gemm_rows(sm.bufb, layer == 2 ? sm.w3 : sm.w2, warp, lane, acc);
+            const float4 *xl = reinterpret_cast<const float4 *>(saved + L.x(layer - 1) + b * kV * kH);
+#pragma unroll
+            for (int i = 0; i < kRowsPerWarp; ++i) {
+                const int r = warp * kRowsPerWarp + i;
+                if (r < kV) {
+                    const float4 x = xl[r * 32 + lane];
+                    reinterpret_cast<float4 *>(sm.bufa)[r * 32 + lane] =
+                        make_float4(x.x > 0.f ? acc[i][0] : 0.f, x.y > 0.f ? acc[i][1] : 0.f,
+                                    x.z > 0.f ? acc[i][2] : 0.f, x.w > 0.f ? acc[i][3] : 0.f);
+                }
+            }
+            __syncthreads();
+        }
+        // bufa = dY1: bias gradient, and keep it for dW1 = dY1^T (A_hat X0)
+        colsum_accumulate(sm.bufa, db1, tid);
+        {
+            float4 *dst = reinterpret_cast<float4 *>(ws + W.dy1() + b * kV * kH);
+            const float4 *src = reinterpret_cast<const float4 *>(sm.bufa);
+            for (int i = tid; i < kV * kH / 4; i += kGcnThreads) dst[i] = src[i];
+        }
+    }
+    // bias partials of this CTA (zeros when it had no board): combine the two row halves
+    float *slot = ws + W.partial() + (int64_t)blockIdx.x * kNumParams;
+    const int n = tid & (kH - 1);
+    float vals[3] = {db1, db2, db3};
+    const int offs[3] = {kOffB1, kOffB2, kOffB3};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        __syncthreads();
+        sm.red[tid] = vals[q];
+        __syncthreads();
+        if (tid < kH) slot[offs[q] + n] = sm.red[tid] + sm.red[tid + kH];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradients: out[m][n] = sum_r A[r][m] * Bm[r][n], rows split over kSlots chunks.
+// One launch for all jobs: grid = (kSlots, kMaxMTiles, njobs).
+// ------------------------------------------------------------------------------------------
+struct AtbJob {
+    const float *A; int lda; int M;
+    const float *Bm; int ldb; int N;  // Bm == nullptr: implicit ones, N = 1 (column sums of A)
+    int64_t R;
+    int out_off;                      // offset inside a partial slot, row-major [M][N]
+};
+constexpr int kMaxJobs = 12;
+struct AtbJobs { AtbJob job[kMaxJobs]; int n; };
+constexpr int kAtbMT = 64, kAtbKT = 32, kMaxMTiles = 4;
+
+__global__ void __launch_bounds__(256)
+atb_jobs_kernel(const AtbJobs jobs, float *__restrict__ partial) {
+    const AtbJob J = jobs.job[blockIdx.z];
+    const int m0 = blockIdx.y * kAtbMT;
+    if (m0 >= J.M) return;
+    __shared__ __align__(16) float As[kAtbKT][kAtbMT];
+    __shared__ __align__(16) float Bs[kAtbKT][kH];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // tx -> 8 columns, ty -> 4 rows of the tile
+    const int64_t per = (J.R + kSlots - 1) / kSlots;
+    const int64_t r_begin = (int64_t)blockIdx.x * per;
+    const int64_t r_end = r_begin + per < J.R ? r_begin + per : J.R;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += kAtbKT) {
+        __syncthreads();
+        for (int i = tid; i < kAtbKT * kAtbMT; i += 256) {
+            const int k = i / kAtbMT, m = i % kAtbMT;
+            const int64_t r = r0 + k;
+            As[k][m] = (r < r_end && m0 + m < J.M) ? __ldg(J.A + r * J.lda + m0 + m) : 0.f;
+        }
+        for (int i = tid; i < kAtbKT * kH; i += 256) {
+            const int k = i / kH, n = i % kH;
+            const int64_t r = r0 + k;
+            float v = 0.f;
+            if (r < r_end && n < J.N) v = J.Bm ? __ldg(J.Bm + r * J.ldb + n) : 1.f;
+            Bs[k][n] = v;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < kAtbKT; ++k) {
+            const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 8]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 8 + 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+    }
+    float *slot = partial + (int64_t)blockIdx.x * kNumParams + J.out_off;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= J.M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = tx * 8 + j;
+            if (n < J.N) slot[m * J.N + n] = acc[i][j];
+        }
+    }
+}
+
+__global__ void reduce_partials_kernel(const float *__restrict__ partial, float *__restrict__ grads) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kNumParams) return;
+    float s = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < kSlots; ++k) s += partial[(int64_t)k * kNumParams + i];  // fixed order: deterministic
+    grads[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// loss gradient (train_network.py:54-55,85-89) and Adam (train_network.py:56,94)
+// ------------------------------------------------------------------------------------------
+__global__ void loss_grad_kernel(const float *__restrict__ policy, const float *__restrict__ value,
+                                 const float *__restrict__ ptarget, const float *__restrict__ vtarget, int64_t B,
+                                 float inv_total, float *__restrict__ loss, float *__restrict__ dpolicy,
+                                 float *__restrict__ dvalue) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    float lp = 0.f, lv = 0.f;
+    for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
+        // CrossEntropyLoss(input = softmax probabilities, target = probabilities):
+        //   -sum_a t_a * log_softmax(p)_a   -- the second softmax is the reference's behaviour
+        float p[7], t[7], mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int a = lane + 32 * k;
+            p[k] = a < kP ? __ldg(policy + b * kP + a) : -INFINITY;
+            t[k] = a < kP ? __ldg(ptarget + b * kP + a) : 0.f;
+            mx = fmaxf(mx, p[k]);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        float se = 0.f, tsum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            if (lane + 32 * k < kP) se += expf(p[k] - mx);
+            tsum += t[k];
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, d);
+            tsum += __shfl_xor_sync(0xffffffffu, tsum, d);
+        }
+        const float lse = mx + logf(se);
+        float l = 0.f;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int a = lane + 32 * k;
+            if (a < kP) {
+                const float ls = p[k] - lse;
+                l -= t[k] * ls;
+                dpolicy[b * kP + a] = (expf(ls) * tsum - t[k]) * inv_total;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) l += __shfl_xor_sync(0xffffffffu, l, d);
+        if (lane == 0) {
+            const float dv = __ldg(value + b) - __ldg(vtarget + b);
+            lp += l;
+            lv += dv * dv;
+            dvalue[b] = 2.f * dv * inv_total;
+        }
+    }
+    if (lane == 0 && loss) {  // monitoring scalars only; gradients above do not depend on them
+        atomicAdd(loss + 0, lp * inv_total);
+        atomicAdd(loss + 1, lv * inv_total);
+    }
+}
+
+__global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                            float *__restrict__ v, int64_t n, float step_size, float bc2_sqrt, float beta1,
+                            float beta2, float eps, float grad_scale) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i] * grad_scale;
+    const float mi = m[i] + (1.f - beta1) * (gi - m[i]);        // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;          // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+    p[i] = p[i] - step_size * (mi / denom);
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" int64_t aq_gnn_backward_ws_floats(int64_t B) { return BwdWs{B}.total(); }
+
+extern "C" int aq_gnn_backward(const float *params, const float *saved, const float *dpolicy, const float *dvalue,
+                               int64_t B, float *grads, float *workspace, void *stream) {
+    if (B <= 0 || !params || !saved || !dpolicy || !dvalue || !grads || !workspace)
+        return aq_set_error(AQ_ERR_ARG, "aq_gnn_backward");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const SavedLayout L{B};
+    const BwdWs W{B};
+    cudaError_t e;
+    e = cudaFuncSetAttribute(heads_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadBwdSmem));
+    if (e != cudaSuccess) return aq_set_error((int)e, "heads_backward smem");
+    e = cudaFuncSetAttribute(gcn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GcnBwdSmem));
+    if (e != cudaSuccess) return aq_set_error((int)e, "gcn_backward smem");
+    const int64_t hb = (B + 7) / 8;
+    heads_backward_kernel<<<(unsigned)(hb < kSlots ? hb : kSlots), kHbThreads, sizeof(HeadBwdSmem), st>>>(
+        params, saved, dpolicy, dvalue, B, workspace);
+    int rc = aq_check_launch("heads_backward_kernel");
+    if (rc) return rc;
+    gcn_backward_kernel<<<kSlots, kGcnThreads, sizeof(GcnBwdSmem), st>>>(params, saved, B, workspace);
+    if ((rc = aq_check_launch("gcn_backward_kernel"))) return rc;
+
+    AtbJobs jobs;
+    int nj = 0;
+    auto add = [&](const float *A, int lda, int M, const float *Bm, int ldb, int N, int64_t R, int off) {
+        jobs.job[nj++] = AtbJob{A, lda, M, Bm, ldb, N, R, off};
+    };
+    const int64_t RN = B * kV;
+    add(workspace + W.dy1(), kH, kH, saved + L.ax0(), kF, kF, RN, kOffW1);    // dW1 = dY1^T (A_hat X0)
+    add(workspace + W.dz2(), kH, kH, saved + L.x(0), kH, kH, RN, kOffW2);     // dW2 = dZ2^T X1
+    add(workspace + W.dz3(), kH, kH, saved + L.x(1), kH, kH, RN, kOffW3);     // dW3 = dZ3^T X2
+    add(workspace + W.dhp(), kHH, kHH, saved + L.pooled(), kH, kH, B, kOffWP0);
+    add(workspace + W.dhp(), kHH, kHH, nullptr, 0, 1, B, kOffBP0);
+    add(workspace + W.dz(), kP, kP, saved + L.hp(), kHH, kHH, B, kOffWP2);
+    add(workspace + W.dz(), kP, kP, nullptr, 0, 1, B, kOffBP2);
+    add(workspace + W.dhv(), kHH, kHH, saved + L.pooled(), kH, kH, B, kOffWV0);
+    add(workspace + W.dhv(), kHH, kHH, nullptr, 0, 1, B, kOffBV0);
+    add(workspace + W.du(), 1, 1, saved + L.hv(), kHH, kHH, B, kOffWV2);
+    add(workspace + W.du(), 1, 1, nullptr, 0, 1, B, kOffBV2);
+    jobs.n = nj;
+    atb_jobs_kernel<<<dim3(kSlots, kMaxMTiles, nj), 256, 0, st>>>(jobs, workspace + W.partial());
+    if ((rc = aq_check_launch("atb_jobs_kernel"))) return rc;
+    reduce_partials_kernel<<<(kNumParams + 255) / 256, 256, 0, st>>>(workspace + W.partial(), grads);
+    return aq_check_launch("reduce_partials_kernel");
+}
+
+extern "C" int aq_loss_grad(const float *policy, const float *value, const float *policy_target,
+                            const float *value_target, int64_t B, int64_t B_total, float *loss, float *dpolicy,
+                            float *dvalue, void *stream) {
+    if (B <= 0 || B_total <= 0 || !policy || !value || !policy_target || !value_target || !dpolicy || !dvalue)
+        return aq_set_error(AQ_ERR_ARG, "aq_loss_grad");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (loss) {
+        cudaError_t e = cudaMemsetAsync(loss, 0, 2 * sizeof(float), st);
+        if (e != cudaSuccess) return aq_set_error((int)e, "aq_loss_grad(memset)");
+    }
+    const int64_t nb = (B + 7) / 8;
+    loss_grad_kernel<<<(unsigned)(nb < 1184 ? nb : 1184), 256, 0, st>>>(policy, value, policy_target, value_target, B,
+                                                                       1.0f / (float)B_total, loss, dpolicy, dvalue);
+    return aq_check_launch("loss_grad_kernel");
+}
+
+extern "C" int aq_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n,
+                            int64_t step, float lr, float beta1, float beta2, float eps, float grad_scale,
+                            void *stream) {
+    if (n <= 0 || step <= 0 || !params || !grads || !exp_avg || !exp_avg_sq) return aq_set_error(AQ_ERR_ARG, "aq_adam_step");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    const float step_size = (float)((double)lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        params, grads, exp_avg, exp_avg_sq, n, step_size, bc2_sqrt, beta1, beta2, eps, grad_scale);
+    return aq_check_launch("adam_kernel");
+}

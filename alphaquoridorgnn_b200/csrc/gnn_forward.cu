@@ -1,0 +1,416 @@
+// GraphPolicyValueNetwork.forward (pv_network_gnn.py:53-64) -- fp32 FFMA path.
+//   gcn_forward_fp32_kernel : graph build + 3 GCN layers + global_mean_pool, one board per CTA
+//                             iteration, all activations resident in shared memory
+//   heads_forward_kernel    : policy / value MLPs, softmax, tanh, optional legal-action
+//                             renormalisation (BaseNetwork.predict semantics)
+#include "gnn_fp32.cuh"
+
+using namespace aq;
+
+// ------------------------------------------------------------------------------------------
+// shared memory map of the GCN kernel (bytes): two weight tiles, two activation buffers
+// (bufx's GEMM over-read of rows 81..87 lands in bufz / the small arrays, results discarded)
+// ------------------------------------------------------------------------------------------
+struct GcnSmem {
+    float w2[kH * kH];
+    float w3[kH * kH];
+    float bufx[kV * kH];
+    float bufz[kV * kH];
+    float w1t[kF * kH];  // [f][n]   (w1t + b1..b3 = 1152 floats >= the 7x128 GEMM over-read of bufz)
+    float b1[kH], b2[kH], b3[kH];
+    float coef[kV * 5 + 3];
+    float x0[kV * kF + 2];
+    float ax0[kV * kF + 2];
+    float red[256];
+    uint8_t open_s[96];
+};
+static_assert(sizeof(GcnSmem) <= 227 * 1024, "GcnSmem exceeds the 227 KB shared memory limit");
+
+template <bool kSave>
+__global__ void __launch_bounds__(kGcnThreads, 1)
+gcn_forward_fp32_kernel(const float *__restrict__ params, const AqState *__restrict__ states,
+                        const float *__restrict__ x_in, const uint8_t *__restrict__ open_in, int64_t B,
+                        float *__restrict__ pooled_out, float *__restrict__ saved) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GcnSmem &sm = *reinterpret_cast<GcnSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // weights: W^T tiles so that the GEMM reads rows of the reduction index
+    load_weight_transposed(sm.w2, params + kOffW2, tid);
+    load_weight_transposed(sm.w3, params + kOffW3, tid);
+    for (int i = tid; i < kF * kH; i += kGcnThreads) {
+        const int n = i / kF, f = i % kF;
+        sm.w1t[f * kH + n] = __ldg(params + kOffW1 + i);
+    }
+    if (tid < kH) {
+        sm.b1[tid] = __ldg(params + kOffB1 + tid);
+        sm.b2[tid] = __ldg(params + kOffB2 + tid);
+        sm.b3[tid] = __ldg(params + kOffB3 + tid);
+    }
+    const SavedLayout L{B};
+
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();  // previous board fully consumed (also covers the weight fill)
+        // ---- inputs: node features + open-direction masks --------------------------------
+        if (states) {
+            const AqState s = load_state(states + b);
+            board_inputs_from_state(s, sm.x0, sm.open_s, tid);
+        } else {
+            for (int i = tid; i < kV * kF; i += kGcnThreads) sm.x0[i] = __ldg(x_in + b * kV * kF + i);
+            if (tid < kV) sm.open_s[tid] = __ldg(open_in + b * kV + tid);
+        }
+        __syncthreads();
+        board_coefficients(sm.open_s, sm.coef, tid);
+        __syncthreads();
+        // ---- layer 1: (A_hat X0) W1^T + b1, ReLU  (aggregate the 6-wide input first) -------
+        for (int i = tid; i < kV * kF; i += kGcnThreads) {
+            const int v = i / kF, f = i % kF;
+            const float *c = sm.coef + v * 5;
+            float s = c[0] * sm.x0[i];
+            if (c[1] != 0.f) s = fmaf(c[1], sm.x0[(v - 9) * kF + f], s);
+            if (c[2] != 0.f) s = fmaf(c[2], sm.x0[(v + 9) * kF + f], s);
+            if (c[3] != 0.f) s = fmaf(c[3], sm.x0[(v - 1) * kF + f], s);
+            if (c[4] != 0.f) s = fmaf(c[4], sm.x0[(v + 1) * kF + f], s);
+            sm.ax0[i] = s;
+        }
+        __syncthreads();
+        {
+            const int n = tid & (kH - 1);
+            float w[kF];
+#pragma unroll
+            for (int f = 0; f < kF; ++f) w[f] = sm.w1t[f * kH + n];
+            const float bias = sm.b1[n];
+            for (int v = tid >> 7; v < kV; v += 2) {
+                float s = bias;
+#pragma unroll
+                for (int f = 0; f < kF; ++f) s = fmaf(sm.ax0[v * kF + f], w[f], s);
+                sm.bufx[v * kH + n] = fmaxf(s, 0.f);
+            }
+        }
+        __syncthreads();
+        if (kSave) {
+            float4 *dst = reinterpret_cast<float4 *>(saved + L.x(0) + b * kV * kH);
+            const float4 *src = reinterpret_cast<const float4 *>(sm.bufx);
+            for (int i = tid; i < kV * kH / 4; i += kGcnThreads) dst[i] = src[i];
+            for (int i = tid; i < kV * 5; i += kGcnThreads) saved[L.coef() + b * kV * 5 + i] = sm.coef[i];
+            for (int i = tid; i < kV * kF; i += kGcnThreads) saved[L.ax0() + b * kV * kF + i] = sm.ax0[i];
+        }
+        // ---- layers 2, 3: Z = X W^T ; X' = relu(A_hat Z + b) ----------------------------------
+#pragma unroll 1
+        for (int layer = 1; layer < kLayers; ++layer) {
+            const float *wt = layer == 1 ? sm.w2 : sm.w3;
+            const float *bias = layer == 1 ? sm.b2 : sm.b3;
+            float acc[kRowsPerWarp][4];
+            gemm_rows(sm.bufx, wt, warp, lane, acc);
+#pragma unroll
+            for (int i = 0; i < kRowsPerWarp; ++i) {
+                const int r = warp * kRowsPerWarp + i;
+                if (r < kV)
+                    reinterpret_cast<float4 *>(sm.bufz)[r * 32 + lane] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            }
+            __syncthreads();
+            aggregate<true>(sm.bufz, sm.bufx, sm.coef, bias, warp, lane);
+            __syncthreads();
+            if (kSave) {
+                float4 *dst = reinterpret_cast<float4 *>(saved + L.x(layer) + b * kV * kH);
+                const float4 *src = reinterpret_cast<const float4 *>(sm.bufx);
+                for (int i = tid; i < kV * kH / 4; i += kGcnThreads) dst[i] = src[i];
+            }
+        }
+        // ---- global_mean_pool: every graph has exactly 81 nodes --------------------------------
+        {
+            const int n = tid & (kH - 1), half = tid >> 7;
+            float s = 0.f;
+            for (int v = half; v < kV; v += 2) s += sm.bufx[v * kH + n];
+            sm.red[tid] = s;
+        }
+        __syncthreads();
+        if (tid < kH) {
+            const float g = (sm.red[tid] + sm.red[tid + kH]) / (float)kV;
+            pooled_out[b * kH + tid] = g;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// heads: one warp per board; weights transposed in shared memory ([k][j], j fastest)
+// ------------------------------------------------------------------------------------------
+constexpr int kHeadThreads = 256;
+constexpr int kPPad = 224;  // 209 logits -> 7 per lane
+
+struct HeadSmem {
+    float wp0t[kH * kHH];     // [k][j]
+    float wv0t[kH * kHH];
+    float wp2t[kHH * kPPad];  // [j][a]
+    float bp0[kHH], bv0[kHH], wv2[kHH];
+    float bp2[kPPad];
+    float g[kHeadThreads / 32][kH];
+    float hp[kHeadThreads / 32][kHH];
+    float hv[kHeadThreads / 32][kHH];
+};
+static_assert(sizeof(HeadSmem) <= 227 * 1024, "HeadSmem too large");
+
+// mode 0: policy/value outputs (network forward). mode 1: predict semantics -- restrict to the
+// legal mask and renormalise (pv_network_cnn.py:129-132).
+template <bool kSave, bool kLegal>
+__global__ void __launch_bounds__(kHeadThreads, 1)
+heads_forward_kernel(const float *__restrict__ params, const float *__restrict__ pooled, int64_t B,
+                     float *__restrict__ policy, float *__restrict__ value, const uint32_t *__restrict__ mask,
+                     float *__restrict__ saved) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HeadSmem &sm = *reinterpret_cast<HeadSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < kHH * kH; i += kHeadThreads) {
+        const int j = i >> 7, k = i & 127;
+        sm.wp0t[k * kHH + j] = __ldg(params + kOffWP0 + i);
+        sm.wv0t[k * kHH + j] = __ldg(params + kOffWV0 + i);
+    }
+    for (int i = tid; i < kHH * kPPad; i += kHeadThreads) {
+        const int j = i / kPPad, a = i % kPPad;
+        sm.wp2t[i] = a < kP ? __ldg(params + kOffWP2 + a * kHH + j) : 0.f;
+    }
+    if (tid < kHH) {
+        sm.bp0[tid] = __ldg(params + kOffBP0 + tid);
+        sm.bv0[tid] = __ldg(params + kOffBV0 + tid);
+        sm.wv2[tid] = __ldg(params + kOffWV2 + tid);
+    }
+    if (tid < kPPad) sm.bp2[tid] = tid < kP ? __ldg(params + kOffBP2 + tid) : 0.f;
+    const float bv2 = __ldg(params + kOffBV2);
+    __syncthreads();
+    const SavedLayout L{B};
+    const int nwarps = kHeadThreads / 32;
+
+    for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
+        __syncwarp();
+        reinterpret_cast<float4 *>(sm.g[warp])[lane] = __ldg(reinterpret_cast<const float4 *>(pooled + b * kH) + lane);
+        __syncwarp();
+        // hidden layers of both heads: outputs j = lane, lane+32
+        float p0 = sm.bp0[lane], p1 = sm.bp0[lane + 32], v0 = sm.bv0[lane], v1 = sm.bv0[lane + 32];
+#pragma unroll 4
+        for (int k = 0; k < kH; ++k) {
+            const float gk = sm.g[warp][k];
+            p0 = fmaf(gk, sm.wp0t[k * kHH + lane], p0);
+            p1 = fmaf(gk, sm.wp0t[k * kHH + lane + 32], p1);
+            v0 = fmaf(gk, sm.wv0t[k * kHH + lane], v0);
+            v1 = fmaf(gk, sm.wv0t[k * kHH + lane + 32], v1);
+        }
+        p0 = fmaxf(p0, 0.f); p1 = fmaxf(p1, 0.f); v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f);
+        sm.hp[warp][lane] = p0; sm.hp[warp][lane + 32] = p1;
+        sm.hv[warp][lane] = v0; sm.hv[warp][lane + 32] = v1;
+        if (kSave) {
+            saved[L.hp() + b * kHH + lane] = p0; saved[L.hp() + b * kHH + lane + 32] = p1;
+            saved[L.hv() + b * kHH + lane] = v0; saved[L.hv() + b * kHH + lane + 32] = v1;
+        }
+        __syncwarp();
+        // value: Linear(64 -> 1) + tanh
+        float u = v0 * sm.wv2[lane] + v1 * sm.wv2[lane + 32];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) u += __shfl_xor_sync(0xffffffffu, u, d);
+        const float val = tanhf(u + bv2);
+        // policy logits a = lane + 32 t
+        float z[7];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) z[t] = sm.bp2[lane + 32 * t];
+#pragma unroll 2
+        for (int j = 0; j < kHH; ++j) {
+            const float h = sm.hp[warp][j];
+#pragma unroll
+            for (int t = 0; t < 7; ++t) z[t] = fmaf(h, sm.wp2t[j * kPPad + lane + 32 * t], z[t]);
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < 7; ++t) if (lane + 32 * t < kP) mx = fmaxf(mx, z[t]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        float sum = 0.f;
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            z[t] = (lane + 32 * t < kP) ? expf(z[t] - mx) : 0.f;
+            sum += z[t];
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+#pragma unroll
+        for (int t = 0; t < 7; ++t) z[t] = z[t] / sum;  // softmax probabilities
+        if (kSave) {
+#pragma unroll
+            for (int t = 0; t < 7; ++t) if (lane + 32 * t < kP) saved[L.policy() + b * kP + lane + 32 * t] = z[t];
+            if (lane == 0) saved[L.value() + b] = val;
+        }
+        if (kLegal) {
+            // policy = policy[legal]; policy /= sum(policy) if sum(policy) else 1
+            float ls = 0.f;
+#pragma unroll
+            for (int t = 0; t < 7; ++t) {
+                const bool legal = (__ldg(mask + b * 8 + t) >> lane) & 1;  // word t holds actions 32t..32t+31
+                z[t] = legal ? z[t] : 0.f;
+                ls += z[t];
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, d);
+            if (ls != 0.f) {
+#pragma unroll
+                for (int t = 0; t < 7; ++t) z[t] = z[t] / ls;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 7; ++t) if (lane + 32 * t < kP) policy[b * kP + lane + 32 * t] = z[t];
+        if (lane == 0) value[b] = val;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+int aq_gcn_forward_tc(const float *params, const AqState *states, int64_t B, float *pooled, cudaStream_t st);  // gnn_tc.cu
+
+static int launch_trunk(const float *params, const AqState *states, const float *x, const uint8_t *open_mask, int64_t B,
+                        float *pooled, float *saved, int precision, cudaStream_t st) {
+    if (precision == 1) {
+        if (saved || !states) return aq_set_error(AQ_ERR_UNSUPPORTED, "aq_gnn_forward(bf16 path is inference-from-states only)");
+        return aq_gcn_forward_tc(params, states, B, pooled, st);
+    }
+    const unsigned grid = (unsigned)(B < num_sms() ? B : num_sms());
+    int rc;
+    if (saved) {
+        if ((rc = set_smem(gcn_forward_fp32_kernel<true>, sizeof(GcnSmem)))) return aq_set_error(rc, "gcn_forward smem");
+        gcn_forward_fp32_kernel<true><<<grid, kGcnThreads, sizeof(GcnSmem), st>>>(params, states, x, open_mask, B, pooled, saved);
+    } else {
+        if ((rc = set_smem(gcn_forward_fp32_kernel<false>, sizeof(GcnSmem)))) return aq_set_error(rc, "gcn_forward smem");
+        gcn_forward_fp32_kernel<false><<<grid, kGcnThreads, sizeof(GcnSmem), st>>>(params, states, x, open_mask, B, pooled, nullptr);
+    }
+    return aq_check_launch("gcn_forward_fp32_kernel");
+}
+
+static int launch_heads(const float *params, const float *pooled, int64_t B, float *policy, float *value,
+                        const uint32_t *legal_mask, float *saved, cudaStream_t st) {
+    const int64_t hb = (B + 7) / 8;
+    const unsigned hgrid = (unsigned)(hb < num_sms() ? hb : num_sms());
+    int rc;
+    if (legal_mask) {
+        if ((rc = set_smem(heads_forward_kernel<false, true>, sizeof(HeadSmem)))) return aq_set_error(rc, "heads smem");
+        heads_forward_kernel<false, true><<<hgrid, kHeadThreads, sizeof(HeadSmem), st>>>(params, pooled, B, policy, value, legal_mask, nullptr);
+    } else if (saved) {
+        if ((rc = set_smem(heads_forward_kernel<true, false>, sizeof(HeadSmem)))) return aq_set_error(rc, "heads smem");
+        heads_forward_kernel<true, false><<<hgrid, kHeadThreads, sizeof(HeadSmem), st>>>(params, pooled, B, policy, value, nullptr, saved);
+    } else {
+        if ((rc = set_smem(heads_forward_kernel<false, false>, sizeof(HeadSmem)))) return aq_set_error(rc, "heads smem");
+        heads_forward_kernel<false, false><<<hgrid, kHeadThreads, sizeof(HeadSmem), st>>>(params, pooled, B, policy, value, nullptr, nullptr);
+    }
+    return aq_check_launch("heads_forward_kernel");
+}
+
+extern "C" int aq_gcn_trunk_forward(const float *params, const AqState *states, int64_t B, float *pooled, int precision,
+                                    void *stream) {
+    if (B < 0 || !params || (B > 0 && (!states || !pooled))) return aq_set_error(AQ_ERR_ARG, "aq_gcn_trunk_forward");
+    if (B == 0) return 0;
+    return launch_trunk(params, states, nullptr, nullptr, B, pooled, nullptr, precision, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int aq_heads_forward(const float *params, const float *pooled, int64_t B, float *policy, float *value,
+                                const uint32_t *legal_mask, void *stream) {
+    if (B < 0 || !params || (B > 0 && (!pooled || !policy || !value))) return aq_set_error(AQ_ERR_ARG, "aq_heads_forward");
+    if (B == 0) return 0;
+    return launch_heads(params, pooled, B, policy, value, legal_mask, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// pooled [B,128] scratch must be provided by the caller when saved == NULL (inference); with a
+// saved workspace the pooled section of `saved` is used.
+int aq_gnn_forward_impl(const float *params, const AqState *states, const float *x, const uint8_t *open_mask,
+                        int64_t B, float *policy, float *value, float *saved, float *pooled_scratch,
+                        const uint32_t *legal_mask, int precision, cudaStream_t st) {
+    if (B == 0) return 0;
+    const SavedLayout L{B};
+    float *pooled = saved ? saved + L.pooled() : pooled_scratch;
+    if (!pooled) return aq_set_error(AQ_ERR_ARG, "aq_gnn_forward(pooled scratch)");
+    int rc = launch_trunk(params, states, x, open_mask, B, pooled, saved, precision, st);
+    if (rc) return rc;
+    return launch_heads(params, pooled, B, policy, value, legal_mask, saved, st);
+}
+
+extern "C" int64_t aq_param_count(void) { return kNumParams; }
+extern "C" int64_t aq_gnn_saved_floats(int64_t B) { return SavedLayout{B}.total(); }
+
+extern "C" int aq_gnn_forward(const float *params, const AqState *states, const float *x, const uint8_t *open_mask,
+                              int64_t B, float *policy, float *value, float *saved, int precision, void *stream) {
+    if (B < 0 || !params || (B > 0 && (!policy || !value)) || (B > 0 && !states && (!x || !open_mask)))
+        return aq_set_error(AQ_ERR_ARG, "aq_gnn_forward");
+    if (B == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // inference without a saved workspace: the pooled [B,128] vector needs scratch; take it from the
+    // stream-ordered pool (no persistent allocation, freed on the same stream)
+    float *scratch = nullptr;
+    if (!saved) {
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&scratch), (size_t)B * kH * sizeof(float), st);
+        if (e != cudaSuccess) return aq_set_error((int)e, "aq_gnn_forward(cudaMallocAsync)");
+    }
+    int rc = aq_gnn_forward_impl(params, states, x, open_mask, B, policy, value, saved, scratch, nullptr, precision, st);
+    if (scratch) cudaFreeAsync(scratch, st);
+    return rc;
+}
+
+extern "C" int64_t aq_leaf_eval_ws_floats(int64_t B) { return B * kH; }
+
+extern "C" int aq_leaf_eval(const float *params, const AqState *states, int64_t B, float *priors, float *value,
+                            uint32_t *mask, uint8_t *pawn, float *workspace, int precision, void *stream) {
+    if (B < 0 || !params || (B > 0 && (!states || !priors || !value || !mask || !pawn || !workspace)))
+        return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval");
+    if (B == 0) return 0;
+    int rc = aq_legal_mask(states, B, mask, pawn, stream);
+    if (rc) return rc;
+    return aq_gnn_forward_impl(params, states, nullptr, nullptr, B, priors, value, nullptr, workspace, mask, precision,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- host-buffer variant ----------------------------------------------------------------------
+// device workspace layout: states | priors | value | mask | pawn | pooled
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int64_t aq_leaf_eval_host_ws_bytes(int64_t B) {
+    return (int64_t)(align256((size_t)B * sizeof(AqState)) + align256((size_t)B * kP * 4) + align256((size_t)B * 4) +
+                     align256((size_t)B * 32) + align256((size_t)B * 8) + align256((size_t)B * kH * 4));
+}
+
+extern "C" int aq_leaf_eval_host(const float *params, const AqState *states_host, int64_t B, float *priors_host,
+                                 float *value_host, uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws,
+                                 int precision, void *stream) {
+    if (B < 0 || !params || (B > 0 && (!states_host || !priors_host || !value_host || !dev_ws)))
+        return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host");
+    if (B == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char *p = reinterpret_cast<unsigned char *>(dev_ws);
+    AqState *d_states = reinterpret_cast<AqState *>(p); p += align256((size_t)B * sizeof(AqState));
+    float *d_priors = reinterpret_cast<float *>(p);     p += align256((size_t)B * kP * 4);
+    float *d_value = reinterpret_cast<float *>(p);      p += align256((size_t)B * 4);
+    uint32_t *d_mask = reinterpret_cast<uint32_t *>(p); p += align256((size_t)B * 32);
+    uint8_t *d_pawn = reinterpret_cast<uint8_t *>(p);   p += align256((size_t)B * 8);
+    float *d_pooled = reinterpret_cast<float *>(p);
+    cudaError_t e = cudaMemcpyAsync(d_states, states_host, (size_t)B * sizeof(AqState), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(H2D)");
+    int rc = aq_leaf_eval(params, d_states, B, d_priors, d_value, d_mask, d_pawn, d_pooled, precision, stream);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(priors_host, d_priors, (size_t)B * kP * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(value_host, d_value, (size_t)B * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && mask_host) e = cudaMemcpyAsync(mask_host, d_mask, (size_t)B * 32, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && pawn_host) e = cudaMemcpyAsync(pawn_host, d_pawn, (size_t)B * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(D2H)");
+    return 0;
+}

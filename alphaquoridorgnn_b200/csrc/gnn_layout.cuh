@@ -1,0 +1,46 @@
+// Flat parameter / saved-activation layouts shared by the forward, backward and optimiser
+// kernels.  Parameter order = state_dict order of GraphPolicyValueNetwork
+// (pv_network_gnn.py:24-51): gcn_layers.{0,1,2}.{lin.weight,bias}, policy_head.{0,2}, value_head.{0,2}.
+#pragma once
+#include <cstdint>
+
+namespace aq {
+
+constexpr int kV = 81;     // nodes per board
+constexpr int kF = 6;      // NUM_FEATURES
+constexpr int kH = 128;    // HIDDEN_DIM
+constexpr int kHH = 64;    // HIDDEN_DIM // 2
+constexpr int kP = 209;    // POLICY_OUTPUT_SIZE
+constexpr int kLayers = 3; // NUM_GCN_LAYERS
+
+constexpr int kOffW1 = 0;                       // [128][6]
+constexpr int kOffB1 = kOffW1 + kH * kF;        // 768
+constexpr int kOffW2 = kOffB1 + kH;             // 896   [128][128]
+constexpr int kOffB2 = kOffW2 + kH * kH;        // 17280
+constexpr int kOffW3 = kOffB2 + kH;             // 17408
+constexpr int kOffB3 = kOffW3 + kH * kH;        // 33792
+constexpr int kOffWP0 = kOffB3 + kH;            // 33920 [64][128]
+constexpr int kOffBP0 = kOffWP0 + kHH * kH;     // 42112
+constexpr int kOffWP2 = kOffBP0 + kHH;          // 42176 [209][64]
+constexpr int kOffBP2 = kOffWP2 + kP * kHH;     // 55552
+constexpr int kOffWV0 = kOffBP2 + kP;           // 55761 [64][128]
+constexpr int kOffBV0 = kOffWV0 + kHH * kH;     // 63953
+constexpr int kOffWV2 = kOffBV0 + kHH;          // 64017 [1][64]
+constexpr int kOffBV2 = kOffWV2 + kHH;          // 64081
+constexpr int kNumParams = kOffBV2 + 1;         // 64082
+
+// Saved activations for backward, struct-of-arrays over the batch (all float32).
+struct SavedLayout {
+    int64_t B;
+    __host__ __device__ int64_t x(int layer) const { return (int64_t)layer * B * kV * kH; }  // X1,X2,X3 [B][81][128]
+    __host__ __device__ int64_t pooled() const { return 3 * B * kV * kH; }                   // [B][128]
+    __host__ __device__ int64_t hp() const { return pooled() + B * kH; }                     // [B][64]
+    __host__ __device__ int64_t hv() const { return hp() + B * kHH; }                        // [B][64]
+    __host__ __device__ int64_t policy() const { return hv() + B * kHH; }                    // [B][209]
+    __host__ __device__ int64_t value() const { return policy() + B * kP; }                  // [B]
+    __host__ __device__ int64_t coef() const { return value() + B; }                         // [B][81][5] self,U,D,L,R
+    __host__ __device__ int64_t ax0() const { return coef() + B * kV * 5; }                  // [B][81][6]  A_hat X0
+    __host__ __device__ int64_t total() const { return ax0() + B * kV * kF; }
+};
+
+}  // namespace aq

@@ -1,0 +1,306 @@
+"""Policy-Value network with a GNN architecture -- drop-in for reference pv_network_gnn.py.
+
+Same module-level names (NUM_FEATURES, HIDDEN_DIM, NUM_GCN_LAYERS, POLICY_OUTPUT_SIZE,
+GraphPolicyValueNetwork, create_network) and the same state_dict keys as the reference
+(pv_network_gnn.py:17-80), plus ``GNNNetwork``: the BaseNetwork API (BaseNetwork.py:9-54: name,
+prep_for_inference, predict, train_model, preprocess_input) with the behaviour the reference
+defines in its only concrete network (pv_network_cnn.py:88-140).
+
+All arithmetic runs in libaqgnn.so (hand-written sm_100a kernels); torch is the tensor/autograd
+shell.  There is no CPU fallback: calling the network without a CUDA device raises.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import game_logic as gl
+from .constants import BOARD_SIZE
+
+# Parameters (pv_network_gnn.py:17-20)
+NUM_FEATURES = 6  # Node feature size (similar to input channels in CNN)
+HIDDEN_DIM = 128  # Hidden dimension for GCN layers
+NUM_GCN_LAYERS = 3  # Number of GCN layers
+POLICY_OUTPUT_SIZE = BOARD_SIZE ** 2 + 2 * (BOARD_SIZE - 1) ** 2  # Number of possible actions
+
+PRECISIONS = {"fp32": 0, "bf16": 1}
+
+
+class _GlorotLinear(nn.Module):
+    """Weight holder of GCNConv.lin (PyG Linear(bias=False, weight_initializer='glorot'))."""
+
+    def __init__(self, n_in, n_out):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(n_out, n_in))
+        a = math.sqrt(6.0 / (n_in + n_out))
+        nn.init.uniform_(self.weight, -a, a)
+
+
+class GCNConv(nn.Module):
+    """Parameter holder with the key names of torch_geometric.nn.GCNConv (lin.weight, bias)."""
+
+    def __init__(self, n_in, n_out):
+        super().__init__()
+        self.lin = _GlorotLinear(n_in, n_out)
+        self.bias = nn.Parameter(torch.zeros(n_out))
+
+
+class _GnnFunction(torch.autograd.Function):
+    """forward = aq_gnn_forward with a saved-activation workspace, backward = aq_gnn_backward."""
+
+    @staticmethod
+    def forward(ctx, flat, packed, x, open_mask, *params):
+        L = _lib.load()
+        dev = flat.device
+        B = packed.shape[0] if packed is not None else open_mask.shape[0]
+        policy = torch.empty((B, POLICY_OUTPUT_SIZE), dtype=torch.float32, device=dev)
+        value = torch.empty((B,), dtype=torch.float32, device=dev)
+        saved = torch.empty((L.aq_gnn_saved_floats(B),), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.aq_gnn_forward(_lib.ptr(flat), _lib.ptr(packed), _lib.ptr(x), _lib.ptr(open_mask), B,
+                                        _lib.ptr(policy), _lib.ptr(value), _lib.ptr(saved), 0, _lib.stream_ptr(dev)),
+                       "aq_gnn_forward")
+        ctx.save_for_backward(flat, saved)
+        ctx.B = B
+        ctx.shapes = [p.shape for p in params]
+        return policy, value.unsqueeze(1)
+
+    @staticmethod
+    def backward(ctx, dpolicy, dvalue):
+        L = _lib.load()
+        flat, saved = ctx.saved_tensors
+        dev, B = flat.device, ctx.B
+        dpolicy = dpolicy.contiguous().float()
+        dvalue = dvalue.reshape(B).contiguous().float()
+        grads = torch.empty_like(flat)
+        ws = torch.empty((L.aq_gnn_backward_ws_floats(B),), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.aq_gnn_backward(_lib.ptr(flat), _lib.ptr(saved), _lib.ptr(dpolicy), _lib.ptr(dvalue), B,
+                                         _lib.ptr(grads), _lib.ptr(ws), _lib.stream_ptr(dev)), "aq_gnn_backward")
+        out, off = [], 0
+        for shp in ctx.shapes:
+            n = int(np.prod(shp))
+            out.append(grads[off:off + n].view(shp))
+            off += n
+        return (None, None, None, None, *out)
+
+
+# Graph-based Policy-Value Network
+class GraphPolicyValueNetwork(nn.Module):
+    def __init__(self, num_features, hidden_dim, num_gcn_layers, policy_output_size):
+        super(GraphPolicyValueNetwork, self).__init__()
+        if (num_features, hidden_dim, num_gcn_layers, policy_output_size) != (
+                NUM_FEATURES, HIDDEN_DIM, NUM_GCN_LAYERS, POLICY_OUTPUT_SIZE):
+            raise ValueError("libaqgnn.so is compiled for num_features=6, hidden_dim=128, num_gcn_layers=3, "
+                             "policy_output_size=209 (the reference's constants, pv_network_gnn.py:17-20)")
+        self.num_features = num_features
+        self.hidden_dim = hidden_dim
+        self.num_gcn_layers = num_gcn_layers
+        self.policy_output_size = policy_output_size
+
+        # GCN layers
+        self.gcn_layers = nn.ModuleList()
+        self.gcn_layers.append(GCNConv(num_features, hidden_dim))
+        for _ in range(num_gcn_layers - 1):
+            self.gcn_layers.append(GCNConv(hidden_dim, hidden_dim))
+
+        # Policy head (containers for the parameters; Softmax/Tanh are applied inside the kernel)
+        self.policy_head = nn.Sequential(
+            nn.Linear(hidden_dim, hidden_dim // 2),
+            nn.ReLU(),
+            nn.Linear(hidden_dim // 2, policy_output_size),
+            nn.Softmax(dim=1)
+        )
+
+        # Value head
+        self.value_head = nn.Sequential(
+            nn.Linear(hidden_dim, hidden_dim // 2),
+            nn.ReLU(),
+            nn.Linear(hidden_dim // 2, 1),
+            nn.Tanh()
+        )
+        self.precision = "fp32"  # inference arithmetic: "fp32" (FFMA) or "bf16" (tcgen05 tensor cores)
+        self._flat = None
+
+    # ---- flat parameter buffer: every parameter is a view into one f32[64082] tensor ------------
+    def flat_parameters(self):
+        """The flat parameter buffer the kernels read (state_dict order).  Parameters are re-pointed
+        into it lazily, e.g. after .to(device)."""
+        params = list(self.parameters())
+        dev = params[0].device
+        flat = self._flat
+        ok = flat is not None and flat.device == dev
+        if ok:
+            off = 0
+            for p in params:
+                ok = ok and p.data_ptr() == flat.data_ptr() + 4 * off and p.dtype == torch.float32
+                off += p.numel()
+        if not ok:
+            total = sum(p.numel() for p in params)
+            assert total == _lib.load().aq_param_count(), "parameter count does not match libaqgnn.so"
+            flat = torch.empty((total,), dtype=torch.float32, device=dev)
+            off = 0
+            for p in params:
+                n = p.numel()
+                flat[off:off + n].copy_(p.data.reshape(-1))
+                p.data = flat[off:off + n].view(p.shape)
+                off += n
+            self._flat = flat
+        return flat
+
+    def _prepare(self, x, edge_index, batch):
+        """-> (packed, x, open_mask): either packed states or explicit graph inputs on the device."""
+        flat = self.flat_parameters()
+        _lib.require_cuda(flat, "model parameters")
+        dev = flat.device
+        if edge_index is None:
+            # states: packed uint8[B,32], or State.to_array() rows [B,68] of any numeric dtype
+            s = torch.as_tensor(x)
+            if s.dim() != 2 or s.shape[1] not in (gl.STATE_BYTES, 68):
+                raise ValueError("expected packed states [B,32] or row68 states [B,68]")
+            if s.shape[1] == 68:
+                packed = gl.pack_rows(s.to(torch.uint8), None, dev)
+            else:
+                packed = s.to(device=dev, dtype=torch.uint8).contiguous()
+            return flat, packed, None, None
+        x = x.to(device=dev, dtype=torch.float32).contiguous()
+        if x.dim() != 2 or x.shape[1] != NUM_FEATURES or x.shape[0] % gl.NUM_SQUARES != 0:
+            raise ValueError("x must be [B*81, 6]")
+        B = x.shape[0] // gl.NUM_SQUARES
+        if batch is not None:
+            expect = torch.arange(B, device=batch.device).repeat_interleave(gl.NUM_SQUARES)
+            if batch.shape[0] != x.shape[0] or not torch.equal(batch.to(torch.int64), expect):
+                raise ValueError("batch must assign 81 consecutive nodes to each graph")
+        open_mask = gl.open_mask_from_edge_index(edge_index.to(dev), B)
+        return flat, None, x, open_mask
+
+    def forward(self, x, edge_index=None, batch=None):
+        """forward(x, edge_index, batch) as in the reference (pv_network_gnn.py:53-64), or
+        forward(states) with packed / row68 states (graph built inside the kernel).
+        Returns (policy [B,209] softmax probabilities, value [B,1])."""
+        flat, packed, xx, open_mask = self._prepare(x, edge_index, batch)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return _GnnFunction.apply(flat, packed, xx, open_mask, *self.parameters())
+        L = _lib.load()
+        dev = flat.device
+        B = packed.shape[0] if packed is not None else open_mask.shape[0]
+        policy = torch.empty((B, POLICY_OUTPUT_SIZE), dtype=torch.float32, device=dev)
+        value = torch.empty((B,), dtype=torch.float32, device=dev)
+        prec = PRECISIONS[self.precision] if packed is not None else 0
+        with torch.cuda.device(dev):
+            _lib.check(L.aq_gnn_forward(_lib.ptr(flat), _lib.ptr(packed), _lib.ptr(xx), _lib.ptr(open_mask), B,
+                                        _lib.ptr(policy), _lib.ptr(value), None, prec, _lib.stream_ptr(dev)),
+                       "aq_gnn_forward")
+        return policy, value.unsqueeze(1)
+
+
+class GNNNetwork(GraphPolicyValueNetwork):
+    """BaseNetwork API (BaseNetwork.py:9-54) for the GNN; 0-argument constructor like CNNNetwork."""
+
+    def __init__(self):
+        super().__init__(NUM_FEATURES, HIDDEN_DIM, NUM_GCN_LAYERS, POLICY_OUTPUT_SIZE)
+        self._name = 'GNN'
+        self.optimised_model = None  # BaseNetwork.py:13; the CUDA kernels are the optimised model
+
+    @property
+    def name(self):
+        return self._name
+
+    def prep_for_inference(self, model_path):
+        """Loads state_dict of parameters located at model_path and prepares the model for
+        inference (BaseNetwork.py:21-32; TensorRT compilation is replaced by libaqgnn)."""
+        if not torch.cuda.is_available():
+            raise _lib.AqError("prep_for_inference needs a CUDA device (no CPU fallback)")
+        self.load_state_dict(torch.load(model_path, map_location='cuda'))
+        self.eval()
+        self.to('cuda')
+        self.flat_parameters()
+        self.optimised_model = self
+
+    def preprocess_input(self, game_state_arrays):
+        """list of State.to_array() triples -> uint8[M,68] rows, the form ``forward`` accepts
+        (BaseNetwork.py:49-54; the CNN's version builds 6 planes, pv_network_cnn.py:88-114 -- here
+        the planes and the graph are built on the GPU from these rows)."""
+        return gl.rows_from_arrays(game_state_arrays)
+
+    @torch.no_grad()
+    def predict_batch(self, states, plies=None):
+        """Batched predict for B leaves.  states: list of State objects, row68 array/tensor [B,68], or
+        packed CUDA tensor [B,32].  Returns dict(priors f32[B,209] legal-masked and renormalised,
+        value f32[B], mask int32[B,8], pawn uint8[B,8]) on the device."""
+        flat = self.flat_parameters()
+        _lib.require_cuda(flat, "model parameters")
+        dev = flat.device
+        if isinstance(states, (list, tuple)):
+            rows, plies = gl.rows_from_states(states)
+            packed = gl.pack_rows(rows, plies, dev)
+        else:
+            s = torch.as_tensor(states)
+            packed = gl.pack_rows(s, plies, dev) if s.shape[1] == 68 else s.to(dev).contiguous()
+        B = packed.shape[0]
+        L = _lib.load()
+        priors = torch.empty((B, POLICY_OUTPUT_SIZE), dtype=torch.float32, device=dev)
+        value = torch.empty((B,), dtype=torch.float32, device=dev)
+        mask = torch.empty((B, 8), dtype=torch.int32, device=dev)
+        pawn = torch.empty((B, 8), dtype=torch.uint8, device=dev)
+        ws = torch.empty((max(1, L.aq_leaf_eval_ws_floats(B)),), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.aq_leaf_eval(_lib.ptr(flat), _lib.ptr(packed), B, _lib.ptr(priors), _lib.ptr(value),
+                                      _lib.ptr(mask), _lib.ptr(pawn), _lib.ptr(ws), PRECISIONS[self.precision],
+                                      _lib.stream_ptr(dev)), "aq_leaf_eval")
+        return {"priors": priors, "value": value, "mask": mask, "pawn": pawn, "packed": packed}
+
+    def predict(self, state, device=None):
+        """Predict the policy and value for a game state given a State object.
+        :returns: policy, value, where policy is a normalised PMF over all legal actions (1D numpy
+        array in state.legal_actions() order) and value is a float between -1 and 1
+        (BaseNetwork.py:36-40; pv_network_cnn.py:117-137)."""
+        out = self.predict_batch([state])
+        actions, n = gl.legal_actions_batch(out["packed"], out["mask"], out["pawn"])
+        idx = actions[0, : int(n[0])].to(torch.int64)
+        policy = out["priors"][0][idx].cpu().numpy()
+        return policy, out["value"][0].item()
+
+    def train_model(self, data_loader, optimizer, loss_fn=None, device='cuda', num_epochs=10):
+        """Performs model training (BaseNetwork.py:42-45).  Batches are (states, policy_target,
+        value_target) as produced by train_network.py:42-49; the default loss is the reference's
+        CrossEntropyLoss-on-softmax + MSELoss (train_network.py:54-55,85-89)."""
+        if loss_fn is None:
+            ce, mse = nn.CrossEntropyLoss(), nn.MSELoss()
+            loss_fn = lambda pp, vp, pt, vt: ce(pp, pt) + mse(vp.squeeze(), vt)  # noqa: E731
+        self.to(device)
+        history = []
+        for _ in range(num_epochs):
+            self.train()
+            total = 0.0
+            for state, policy_target, value_target in data_loader:
+                policy_pred, value_pred = self(state.to(device))
+                loss = loss_fn(policy_pred, value_pred, policy_target.to(device), value_target.to(device))
+                optimizer.zero_grad()
+                loss.backward()
+                optimizer.step()
+                total += loss.item()
+            history.append(total)
+        return history
+
+
+# Function to create the dual network
+def create_network(model_path='model/best.pth'):
+    # Do nothing if the model is already created (pv_network_gnn.py:68-80)
+    if os.path.exists(model_path):
+        return
+
+    # Initialize the model
+    model = GraphPolicyValueNetwork(NUM_FEATURES, HIDDEN_DIM, NUM_GCN_LAYERS, POLICY_OUTPUT_SIZE)
+
+    # Save the model
+    os.makedirs(os.path.dirname(model_path) or '.', exist_ok=True)
+    torch.save(model.state_dict(), model_path)
+
+
+# Running the function
+if __name__ == '__main__':
+    create_network()

@@ -105,6 +105,15 @@ int64_t aq_gnn_saved_floats(int64_t B);
 int aq_gnn_forward(const float *params, const AqState *states, const float *x, const uint8_t *open_mask, int64_t B,
                    float *policy, float *value, float *saved, int precision, void *stream);
 
+/* The two stages of aq_gnn_forward, exposed separately for profiling and tests:
+ *   aq_gcn_trunk_forward: graph build + 3 GCN layers + global_mean_pool -> pooled [B,128]
+ *   aq_heads_forward:     policy/value MLPs on pooled; legal_mask (may be NULL) applies the
+ *                         predict() restriction + renormalisation */
+int aq_gcn_trunk_forward(const float *params, const AqState *states, int64_t B, float *pooled, int precision,
+                         void *stream);
+int aq_heads_forward(const float *params, const float *pooled, int64_t B, float *policy, float *value,
+                     const uint32_t *legal_mask, void *stream);
+
 /* Backward of the above (autograd of train_network.py:93).  dpolicy [B,209], dvalue [B] are the
  * loss gradients w.r.t. the softmax / tanh outputs; grads f32[64082] is OVERWRITTEN with the
  * parameter gradients (flat, same order as params); workspace of aq_gnn_backward_ws_floats(B). */

@@ -1,0 +1,232 @@
+"""GPU parity tests of the floating-point path: GNN forward / backward / loss / Adam / predict
+through the C ABI against the CPU oracle restatement (oracle/gnn_oracle.py).
+
+Tolerances (stated per SURVEY.md section 8d; fp32 FFMA path):
+  policy, value        abs <= 2e-5 vs the fp32 oracle, <= 2e-5 vs the fp64 dense restatement
+  gradients            rel-L2 <= 1e-4 vs the fp64 oracle (per parameter tensor)
+  bf16 tensor path     policy abs <= 2e-3, value abs <= 5e-3 (when built)
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from alphaquoridorgnn_b200 import _lib
+from alphaquoridorgnn_b200 import game_logic as gl
+from alphaquoridorgnn_b200.pv_network_gnn import (GNNNetwork, GraphPolicyValueNetwork, NUM_FEATURES, HIDDEN_DIM,
+                                                  NUM_GCN_LAYERS, POLICY_OUTPUT_SIZE)
+from oracle import gnn_oracle, quoridor_oracle as qo
+
+pytestmark = pytest.mark.gpu
+TOL_OUT = 2e-5
+TOL_GRAD = 1e-4
+
+
+def _sample_rows(traj, n, seed=0):
+    rng = np.random.default_rng(seed)
+    idx = rng.choice(len(traj["rows"]), n, replace=False)
+    return traj["rows"][idx], traj["plies"][idx]
+
+
+def _models(seed=0):
+    torch.manual_seed(seed)
+    ref = gnn_oracle.GraphPolicyValueNetworkOracle()
+    with torch.no_grad():  # non-zero GCN biases so the bias path is exercised
+        for layer in ref.gcn_layers:
+            layer.bias.uniform_(-0.1, 0.1)
+    net = GNNNetwork()
+    net.load_state_dict(ref.state_dict())
+    return ref, net.cuda()
+
+
+def test_state_dict_keys_match_reference_names():
+    net = GraphPolicyValueNetwork(NUM_FEATURES, HIDDEN_DIM, NUM_GCN_LAYERS, POLICY_OUTPUT_SIZE)
+    want = []
+    for i in range(3):
+        want += [f"gcn_layers.{i}.bias", f"gcn_layers.{i}.lin.weight"]
+    want += [f"{h}.{i}.{p}" for h in ("policy_head", "value_head") for i in (0, 2) for p in ("weight", "bias")]
+    assert sorted(net.state_dict().keys()) == sorted(want)
+    assert sum(p.numel() for p in net.parameters()) == 64082
+    assert [tuple(p.shape) for p in net.parameters()][:2] in ([(128,), (128, 6)], [(128, 6), (128,)])
+
+
+def test_forward_matches_oracle(traj):
+    rows, plies = _sample_rows(traj, 256)
+    ref, net = _models()
+    x, ei, batch = gnn_oracle.graph_inputs_from_rows(rows)
+    with torch.no_grad():
+        p_ref, v_ref = ref(x, ei, batch)
+        p64, v64 = gnn_oracle.dense_forward_fp64(ref.state_dict(), rows[:32])
+        net.eval()
+        p, v = net(torch.from_numpy(rows))
+    assert p.shape == (256, 209) and v.shape == (256, 1)
+    assert (p.cpu() - p_ref).abs().max().item() <= TOL_OUT
+    assert (v.cpu() - v_ref).abs().max().item() <= TOL_OUT
+    assert np.abs(p[:32].cpu().numpy() - p64).max() <= TOL_OUT
+    assert np.abs(v[:32].cpu().numpy() - v64).max() <= TOL_OUT
+    assert torch.allclose(p.sum(1), torch.ones(256, device="cuda"), atol=1e-5)
+    # the reference signature forward(x, edge_index, batch) gives the same numbers
+    with torch.no_grad():
+        p2, v2 = net(x.cuda(), ei.cuda(), batch.cuda())
+    assert torch.equal(p, p2) and torch.equal(v, v2)
+    # packed states too
+    with torch.no_grad():
+        p3, _ = net(gl.pack_rows(rows, plies))
+    assert torch.equal(p, p3)
+
+
+@pytest.mark.parametrize("B", [1, 2, 7, 150, 300])
+def test_forward_ragged_batches(traj, B):
+    rows, _ = _sample_rows(traj, B, seed=B)
+    ref, net = _models(1)
+    x, ei, batch = gnn_oracle.graph_inputs_from_rows(rows)
+    with torch.no_grad():
+        p_ref, v_ref = ref(x, ei, batch)
+        p, v = net(torch.from_numpy(rows))
+    assert (p.cpu() - p_ref).abs().max().item() <= TOL_OUT and (v.cpu() - v_ref).abs().max().item() <= TOL_OUT
+
+
+def _rel_l2(a, b):
+    return (a.double() - b.double()).norm().item() / max(b.double().norm().item(), 1e-30)
+
+
+def test_backward_matches_oracle_autograd(traj):
+    B = 256
+    rows, _ = _sample_rows(traj, B, seed=3)
+    ref, net = _models(2)
+    ref64 = copy.deepcopy(ref).double()
+    x, ei, batch = gnn_oracle.graph_inputs_from_rows(rows, dtype=torch.float64)
+    torch.manual_seed(5)
+    pt = torch.softmax(torch.randn(B, 209), dim=1)
+    vt = torch.randint(-1, 2, (B,)).float()
+    p64, v64 = ref64(x, ei, batch)
+    loss64, _, _ = gnn_oracle.training_loss(p64, v64, pt.double(), vt.double())
+    loss64.backward()
+    net.train()
+    p, v = net(torch.from_numpy(rows))
+    loss = torch.nn.CrossEntropyLoss()(p, pt.cuda()) + torch.nn.MSELoss()(v.squeeze(), vt.cuda())
+    loss.backward()
+    assert abs(loss.item() - loss64.item()) <= 1e-5
+    g_ref = dict(ref64.named_parameters())
+    for name, prm in net.named_parameters():
+        assert prm.grad is not None, name
+        err = _rel_l2(prm.grad.cpu(), g_ref[name].grad)
+        assert err <= TOL_GRAD, (name, err)
+
+
+def test_fused_loss_grad_and_adam_match_torch(traj):
+    B = 128
+    rows, _ = _sample_rows(traj, B, seed=4)
+    ref, net = _models(3)
+    L = _lib.load()
+    torch.manual_seed(6)
+    pt = torch.softmax(torch.randn(B, 209), dim=1).cuda()
+    vt = torch.randint(-1, 2, (B,)).float().cuda()
+    # loss + gradient w.r.t. the network outputs vs autograd
+    with torch.no_grad():
+        p, v = net(torch.from_numpy(rows))
+    p_t = p.clone().requires_grad_(True)
+    v_t = v.clone().requires_grad_(True)
+    loss_t = torch.nn.CrossEntropyLoss()(p_t, pt) + torch.nn.MSELoss()(v_t.squeeze(), vt)
+    loss_t.backward()
+    loss = torch.zeros(2, device="cuda")
+    dp = torch.empty_like(p)
+    dv = torch.empty(B, device="cuda")
+    _lib.check(L.aq_loss_grad(_lib.ptr(p), _lib.ptr(v.reshape(B).contiguous()), _lib.ptr(pt), _lib.ptr(vt), B, B,
+                              _lib.ptr(loss), _lib.ptr(dp), _lib.ptr(dv), _lib.stream_ptr()), "aq_loss_grad")
+    assert abs(loss.sum().item() - loss_t.item()) <= 1e-5
+    assert (dp - p_t.grad).abs().max().item() <= 1e-8 + 1e-5 * p_t.grad.abs().max().item()
+    assert (dv - v_t.grad.reshape(B)).abs().max().item() <= 1e-8
+    # Adam: 5 steps of aq_adam_step vs torch.optim.Adam on the same gradients
+    torch.manual_seed(7)
+    w = torch.randn(64082, device="cuda")
+    w_ref = w.clone().requires_grad_(True)
+    opt = torch.optim.Adam([w_ref], lr=1e-3)
+    m = torch.zeros_like(w)
+    s = torch.zeros_like(w)
+    for step in range(1, 6):
+        g = torch.randn(64082, device="cuda") * 0.1
+        w_ref.grad = g.clone()
+        opt.step()
+        _lib.check(L.aq_adam_step(_lib.ptr(w), _lib.ptr(g), _lib.ptr(m), _lib.ptr(s), 64082, step, 1e-3, 0.9, 0.999, 1e-8,
+                                  1.0, _lib.stream_ptr()), "aq_adam_step")
+    assert (w - w_ref.detach()).abs().max().item() <= 2e-6
+
+
+def test_predict_matches_reference_semantics(traj, ka):
+    ref, net = _models(4)
+    net.eval()
+    # single-state predict: priors over state.legal_actions() in order, normalised; value float
+    for name in ("KA1", "KA3", "KA13", "G1"):
+        v = ka[name]
+        s = gl.State(player=v["row"][0:2], enemy=v["row"][2:4], walls=v["row"][4:], plies_played=v["plies"])
+        policy, value = net.predict(s, "cuda")
+        assert isinstance(policy, np.ndarray) and policy.dtype == np.float32 and isinstance(value, float)
+        assert policy.shape == (len(v["legal_actions"]),)
+        x, ei, batch = gnn_oracle.graph_inputs_from_rows(np.array([v["row"]], np.uint8))
+        with torch.no_grad():
+            p_ref, v_ref = ref(x, ei, batch)
+        want = p_ref[0][v["legal_actions"]]
+        want = want / (want.sum() if want.sum() else 1)
+        assert np.abs(policy - want.numpy()).max() <= 5e-5
+        assert abs(value - v_ref.item()) <= TOL_OUT and -1.0 <= value <= 1.0
+        assert abs(policy.sum() - 1.0) <= 1e-5
+    # batched leaf evaluation = the same thing for many states at once
+    rows, plies = _sample_rows(traj, 512, seed=9)
+    out = net.predict_batch(torch.from_numpy(rows), torch.from_numpy(plies))
+    legal = qo.legal_actions_batch(rows, plies)
+    assert np.array_equal(out["mask"].cpu().numpy().view(np.uint32), legal["mask"])
+    x, ei, batch = gnn_oracle.graph_inputs_from_rows(rows)
+    with torch.no_grad():
+        p_ref, v_ref = ref(x, ei, batch)
+    dense = torch.from_numpy(np.unpackbits(legal["mask"].view(np.uint8), axis=1, bitorder="little")[:, :209].astype(bool))
+    want = torch.where(dense, p_ref, torch.zeros_like(p_ref))
+    ssum = want.sum(1, keepdim=True)
+    want = want / torch.where(ssum == 0, torch.ones_like(ssum), ssum)
+    assert (out["priors"].cpu() - want).abs().max().item() <= 5e-5
+    assert (out["value"].cpu() - v_ref.squeeze(1)).abs().max().item() <= TOL_OUT
+
+
+def test_leaf_eval_host_buffers_equal_device_path(traj):
+    rows, plies = _sample_rows(traj, 1000, seed=11)
+    _, net = _models(5)
+    L = _lib.load()
+    out = net.predict_batch(torch.from_numpy(rows), torch.from_numpy(plies))
+    B = 1000
+    st = torch.from_numpy(gl.pack_rows_host(rows, plies)).pin_memory()
+    pri = torch.empty((B, 209), dtype=torch.float32).pin_memory()
+    val = torch.empty((B,), dtype=torch.float32).pin_memory()
+    msk = torch.empty((B, 8), dtype=torch.int32).pin_memory()
+    pwn = torch.empty((B, 8), dtype=torch.uint8).pin_memory()
+    ws = torch.empty((L.aq_leaf_eval_host_ws_bytes(B),), dtype=torch.uint8, device="cuda")
+    _lib.check(L.aq_leaf_eval_host(_lib.ptr(net.flat_parameters()), _lib.ptr(st), B, _lib.ptr(pri), _lib.ptr(val),
+                                   _lib.ptr(msk), _lib.ptr(pwn), _lib.ptr(ws), 0, _lib.stream_ptr()), "aq_leaf_eval_host")
+    assert torch.equal(pri, out["priors"].cpu()) and torch.equal(val, out["value"].cpu())
+    assert torch.equal(msk, out["mask"].cpu()) and torch.equal(pwn, out["pawn"].cpu())
+
+
+def test_checkpoint_interchange_and_training_step(tmp_path, traj):
+    """state_dict written by the product loads into the oracle model and vice versa; one
+    train_model epoch with torch.optim.Adam changes the weights and lowers the loss."""
+    ref, net = _models(6)
+    path = tmp_path / "best.pth"
+    torch.save(net.state_dict(), path)
+    ref2 = gnn_oracle.GraphPolicyValueNetworkOracle()
+    ref2.load_state_dict(torch.load(path, map_location="cpu"))
+    net2 = GNNNetwork()
+    net2.prep_for_inference(str(path))
+    rows, _ = _sample_rows(traj, 64, seed=12)
+    with torch.no_grad():
+        a, _ = net(torch.from_numpy(rows))
+        b, _ = net2(torch.from_numpy(rows))
+    assert torch.equal(a, b)
+    torch.manual_seed(8)
+    pt = torch.softmax(3 * torch.randn(64, 209), dim=1)
+    vt = torch.randint(-1, 2, (64,)).float()
+    ds = torch.utils.data.TensorDataset(torch.from_numpy(net.preprocess_input(
+        [[r[0:2].tolist(), r[2:4].tolist(), r[4:].tolist()] for r in rows])).float(), pt, vt)
+    loader = torch.utils.data.DataLoader(ds, batch_size=32, shuffle=False)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    hist = net.train_model(loader, opt, None, "cuda", num_epochs=8)
+    assert hist[-1] < hist[0]
