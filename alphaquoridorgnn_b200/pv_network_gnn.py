@@ -28,6 +28,13 @@ POLICY_OUTPUT_SIZE = BOARD_SIZE ** 2 + 2 * (BOARD_SIZE - 1) ** 2  # Number of po
 
 PRECISIONS = {"fp32": 0, "bf16": 1}
 
+# Order of the flat f32[64082] parameter buffer the kernels read (csrc/gnn_layout.cuh).  Fixed by
+# NAME: nn.Module.parameters() yields a GCNConv's own `bias` before its child `lin.weight`.
+FLAT_PARAM_ORDER = (
+    [n for i in range(NUM_GCN_LAYERS) for n in (f"gcn_layers.{i}.lin.weight", f"gcn_layers.{i}.bias")]
+    + ["policy_head.0.weight", "policy_head.0.bias", "policy_head.2.weight", "policy_head.2.bias",
+       "value_head.0.weight", "value_head.0.bias", "value_head.2.weight", "value_head.2.bias"])
+
 
 class _GlorotLinear(nn.Module):
     """Weight holder of GCNConv.lin (PyG Linear(bias=False, weight_initializer='glorot'))."""
@@ -125,11 +132,15 @@ class GraphPolicyValueNetwork(nn.Module):
         self.precision = "fp32"  # inference arithmetic: "fp32" (FFMA) or "bf16" (tcgen05 tensor cores)
         self._flat = None
 
+    def ordered_parameters(self):
+        named = dict(self.named_parameters())
+        return [named[n] for n in FLAT_PARAM_ORDER]
+
     # ---- flat parameter buffer: every parameter is a view into one f32[64082] tensor ------------
     def flat_parameters(self):
         """The flat parameter buffer the kernels read (state_dict order).  Parameters are re-pointed
         into it lazily, e.g. after .to(device)."""
-        params = list(self.parameters())
+        params = self.ordered_parameters()
         dev = params[0].device
         flat = self._flat
         ok = flat is not None and flat.device == dev
@@ -183,7 +194,7 @@ class GraphPolicyValueNetwork(nn.Module):
         Returns (policy [B,209] softmax probabilities, value [B,1])."""
         flat, packed, xx, open_mask = self._prepare(x, edge_index, batch)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            return _GnnFunction.apply(flat, packed, xx, open_mask, *self.parameters())
+            return _GnnFunction.apply(flat, packed, xx, open_mask, *self.ordered_parameters())
         L = _lib.load()
         dev = flat.device
         B = packed.shape[0] if packed is not None else open_mask.shape[0]

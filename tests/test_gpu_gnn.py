@@ -48,7 +48,7 @@ def test_state_dict_keys_match_reference_names():
     want += [f"{h}.{i}.{p}" for h in ("policy_head", "value_head") for i in (0, 2) for p in ("weight", "bias")]
     assert sorted(net.state_dict().keys()) == sorted(want)
     assert sum(p.numel() for p in net.parameters()) == 64082
-    assert [tuple(p.shape) for p in net.parameters()][:2] in ([(128,), (128, 6)], [(128, 6), (128,)])
+    assert [tuple(p.shape) for p in net.ordered_parameters()][:4] == [(128, 6), (128,), (128, 128), (128,)]
 
 
 def test_forward_matches_oracle(traj):
