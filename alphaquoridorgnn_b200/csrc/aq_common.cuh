@@ -199,4 +199,43 @@ __device__ __forceinline__ AqState load_state(const AqState *p) {
     return s;
 }
 
+// State.next() (game_logic.py:366-391): apply the action, rotate the board 180 degrees
+// (rotate_walls = 64-bit bit reversal of each wall bitboard), swap the players, plies + 1.
+__device__ __forceinline__ AqState state_after(AqState s, int a) {
+    int ppos = s.ppos, pwalls = s.pwalls;
+    if (a < AQ_SQUARES) {
+        ppos = a;
+    } else if (a < AQ_SQUARES + AQ_SLOTS) {
+        s.hwalls |= 1ull << (a - AQ_SQUARES);
+        pwalls -= 1;
+    } else {
+        s.vwalls |= 1ull << (a - AQ_SQUARES - AQ_SLOTS);
+        pwalls -= 1;
+    }
+    AqState t;
+    t.hwalls = __brevll(s.hwalls);
+    t.vwalls = __brevll(s.vwalls);
+    t.ppos = s.epos;
+    t.pwalls = s.ewalls;
+    t.epos = (uint8_t)ppos;
+    t.ewalls = (uint8_t)pwalls;
+    t.plies = (uint16_t)(s.plies + 1);
+    t.flags = 0;
+    t.reserved = 0;
+    return t;
+}
+// is_lose (game_logic.py:43-46) | is_draw << 1 (game_logic.py:49-50)
+__device__ __forceinline__ int terminal_flags(const AqState &s) {
+    return (int)((s.epos / AQ_N) == 0) | ((int)(s.plies >= AQ_PLIES_FOR_DRAW) << 1);
+}
+__device__ __forceinline__ void store_state(AqState *p, const AqState &s) {
+    uint4 x, y;
+    x.x = (unsigned)s.hwalls; x.y = (unsigned)(s.hwalls >> 32); x.z = (unsigned)s.vwalls; x.w = (unsigned)(s.vwalls >> 32);
+    y.x = (unsigned)s.ppos | ((unsigned)s.pwalls << 8) | ((unsigned)s.epos << 16) | ((unsigned)s.ewalls << 24);
+    y.y = (unsigned)s.plies;
+    y.z = 0; y.w = 0;
+    reinterpret_cast<uint4 *>(p)[0] = x;
+    reinterpret_cast<uint4 *>(p)[1] = y;
+}
+
 }  // namespace aq

@@ -182,34 +182,9 @@ __global__ void state_next_kernel(const AqState *__restrict__ states, const int1
                                   AqState *__restrict__ out, uint8_t *__restrict__ terminal) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    AqState s = load_state(states + b);
-    const int a = actions[b];
-    int ppos = s.ppos, pwalls = s.pwalls;
-    if (a < AQ_SQUARES) {
-        ppos = a;
-    } else if (a < AQ_SQUARES + AQ_SLOTS) {
-        s.hwalls |= 1ull << (a - AQ_SQUARES);
-        pwalls -= 1;
-    } else {
-        s.vwalls |= 1ull << (a - AQ_SQUARES - AQ_SLOTS);
-        pwalls -= 1;
-    }
-    const u64 h = __brevll(s.hwalls), v = __brevll(s.vwalls);  // rotate_walls: walls'[i] = walls[63-i]
-    const unsigned plies = s.plies + 1u;
-    uint4 x, y;
-    x.x = (unsigned)h; x.y = (unsigned)(h >> 32); x.z = (unsigned)v; x.w = (unsigned)(v >> 32);
-    // swap players: the successor's player is the old enemy
-    y.x = (unsigned)s.epos | ((unsigned)s.ewalls << 8) | ((unsigned)(ppos & 0xFF) << 16) | ((unsigned)(pwalls & 0xFF) << 24);
-    y.y = plies & 0xFFFFu;
-    y.z = 0; y.w = 0;
-    uint4 *o = reinterpret_cast<uint4 *>(out + b);
-    o[0] = x;
-    o[1] = y;
-    if (terminal) {
-        const int lose = (ppos / AQ_N) == 0;  // successor.enemy[0] // N == 0, game_logic.py:43-46
-        const int draw = plies >= AQ_PLIES_FOR_DRAW;
-        terminal[b] = (uint8_t)(lose | (draw << 1));
-    }
+    const AqState t = state_after(load_state(states + b), actions[b]);
+    store_state(out + b, t);
+    if (terminal) terminal[b] = (uint8_t)terminal_flags(t);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,248 @@
+// GPU-resident lock-step PV-MCTS (reference pv_mcts.py:20-95).  G independent games each own a node
+// arena; every simulation is three steps shared by all games:
+//   aq_mcts_select         descend from the root with PUCT (pv_mcts.py:69-78) to a leaf, rebuilding
+//                          the leaf's state by applying the actions on the path (lazy State.next)
+//   (leaf evaluation)      aq_leaf_eval on the G leaf states = batched model.predict (pv_mcts.py:47)
+//   aq_mcts_expand_backup  create the children in legal_actions() order with their priors
+//                          (pv_mcts.py:53-56) and back the value up with alternating sign (:60-66)
+// The reference has no virtual loss, no Dirichlet noise and no tree reuse, so batching ACROSS games
+// leaves every game's search unchanged.
+//
+// Arithmetic is kept as the reference computes it under NumPy >= 2 (requirements.txt pins
+// numpy~=2.0.2, NEP 50 promotion): w accumulates in float64; the PUCT score is
+//   float32(-w/n computed in float64) + ((float32(1.25) * p) * float32(sqrt(t))) / float32(1 + n)
+// all in float32, and np.argmax takes the FIRST maximum.
+#include "aq_common.cuh"
+
+using namespace aq;
+
+struct __align__(16) MctsNode {
+    double w;           // cumulative value
+    float prior;        // p
+    int n;              // visit count
+    int first_child;    // -1 = not expanded
+    int parent;         // -1 = root
+    short n_children;
+    short action;       // action that leads here from the parent
+    int pad;
+};
+static_assert(sizeof(MctsNode) == 32, "MctsNode must be 32 bytes");
+
+struct __align__(16) MctsGame {
+    AqState root;
+    int node_count;
+    int leaf;       // node selected by the last aq_mcts_select
+    int leaf_kind;  // 0 = evaluate with the network, 1 = terminal loss (-1), 2 = terminal draw (0)
+    int overflow;   // arena exhausted (caller error: max_nodes too small)
+    int pad[4];
+};
+static_assert(sizeof(MctsGame) == 64, "MctsGame must be 64 bytes");
+
+static inline size_t mcts_nodes_offset(int64_t G) { return ((size_t)G * sizeof(MctsGame) + 255) & ~(size_t)255; }
+
+__global__ void mcts_reset_kernel(MctsGame *games, MctsNode *nodes, const AqState *__restrict__ roots, int64_t G,
+                                  int64_t max_nodes) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    MctsGame gm;
+    gm.root = load_state(roots + g);
+    gm.node_count = 1;
+    gm.leaf = 0;
+    gm.leaf_kind = 0;
+    gm.overflow = 0;
+    gm.pad[0] = gm.pad[1] = gm.pad[2] = gm.pad[3] = 0;
+    games[g] = gm;
+    MctsNode r;
+    r.w = 0.0; r.prior = 0.f; r.n = 0; r.first_child = -1; r.parent = -1; r.n_children = 0; r.action = -1; r.pad = 0;
+    nodes[g * max_nodes] = r;  // root node: Node(state, 0), pv_mcts.py:81
+}
+
+// one warp per game
+__global__ void __launch_bounds__(128)
+mcts_select_kernel(MctsGame *games, const MctsNode *__restrict__ nodes_all, int64_t G, int64_t max_nodes, float c_puct,
+                   AqState *__restrict__ leaf_states, int32_t *__restrict__ leaf_kind) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= G) return;
+    const MctsNode *nodes = nodes_all + g * max_nodes;
+    AqState s = games[g].root;
+    int node = 0, kind = 0;
+    while (true) {
+        const int tf = terminal_flags(s);  // pv_mcts.py:35-42: terminal test comes first
+        if (tf) { kind = (tf & 1) ? 1 : 2; break; }
+        const int first = nodes[node].first_child, nc = nodes[node].n_children;
+        if (first < 0 || nc <= 0) { kind = 0; break; }  // `not self.child_nodes` (None or empty)
+        // t = sum(child.n)
+        int t = 0;
+        for (int c = lane; c < nc; c += 32) t += nodes[first + c].n;
+        t = __reduce_add_sync(0xffffffffu, t);
+        const float sq = (float)sqrt((double)t);
+        float best = -INFINITY;
+        int best_c = 0x7fffffff;
+        for (int c = lane; c < nc; c += 32) {
+            const MctsNode ch = nodes[first + c];
+            const float q = ch.n ? (float)(-ch.w / (double)ch.n) : 0.0f;
+            const float u = __fdiv_rn(__fmul_rn(__fmul_rn(c_puct, ch.prior), sq), (float)(1 + ch.n));
+            const float sc = __fadd_rn(q, u);
+            if (sc > best || (sc == best && c < best_c) || best_c == 0x7fffffff) { best = sc; best_c = c; }
+        }
+        // warp arg-max, lowest index among equal maxima (np.argmax)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+            const int oc = __shfl_xor_sync(0xffffffffu, best_c, d);
+            const bool take = (oc != 0x7fffffff) && (best_c == 0x7fffffff || ob > best || (ob == best && oc < best_c));
+            if (take) { best = ob; best_c = oc; }
+        }
+        node = first + best_c;
+        s = state_after(s, nodes[node].action);  // lazy State.next along the path
+    }
+    if (lane == 0) {
+        games[g].leaf = node;
+        games[g].leaf_kind = kind;
+        store_state(leaf_states + g, s);
+        leaf_kind[g] = kind;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+mcts_expand_backup_kernel(MctsGame *games, MctsNode *nodes_all, int64_t G, int64_t max_nodes,
+                          const float *__restrict__ priors, const float *__restrict__ values,
+                          const uint32_t *__restrict__ mask, const uint8_t *__restrict__ pawn) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= G) return;
+    MctsNode *nodes = nodes_all + g * max_nodes;
+    const int leaf = games[g].leaf, kind = games[g].leaf_kind;
+    double value;
+    if (kind == 0) {
+        value = (double)values[g];  // value.item(): float32 -> python float
+        // children in State.legal_actions() order: ordered pawn moves, then per slot H before V
+        const uint32_t *m = mask + 8 * g;
+        const float *pr = priors + (int64_t)AQ_ACTIONS * g;
+        const int np = pawn[8 * g];
+        const int first = games[g].node_count;
+        int total = np;
+        // wall actions = mask bits >= 81 (word 2 holds actions 64..95); counted first to bound-check the arena
+        int wl = 0;
+        if (lane >= 2 && lane < 8) {
+            uint32_t w = m[lane];
+            if (lane == 2) w >>= 17;
+            wl = __popc(w);
+        }
+        wl = __reduce_add_sync(0xffffffffu, wl);
+        total += wl;
+        bool fits = (int64_t)first + total <= max_nodes;
+        if (!fits) {
+            if (lane == 0) games[g].overflow = 1;
+            total = 0;
+        }
+        if (fits) {
+            MctsNode ch;
+            ch.w = 0.0; ch.n = 0; ch.first_child = -1; ch.parent = leaf; ch.n_children = 0; ch.pad = 0;
+            if (lane < np) {
+                const int a = pawn[8 * g + 1 + lane];
+                ch.action = (short)a;
+                ch.prior = pr[a];
+                nodes[first + lane] = ch;
+            }
+            int base = first + np;
+            for (int k = 0; k < 4; ++k) {
+                const int c = lane + 32 * k;  // interleaved candidate index: 2*slot + (0 = H, 1 = V)
+                const int slot = c >> 1;
+                const int a = (c & 1) ? (AQ_SQUARES + AQ_SLOTS + slot) : (AQ_SQUARES + slot);
+                const bool on = (m[a >> 5] >> (a & 31)) & 1;
+                const unsigned bal = __ballot_sync(0xffffffffu, on);
+                if (on) {
+                    ch.action = (short)a;
+                    ch.prior = pr[a];
+                    nodes[base + __popc(bal & ((1u << lane) - 1))] = ch;
+                }
+                base += __popc(bal);
+            }
+        }
+        if (lane == 0) {
+            nodes[leaf].first_child = first;
+            nodes[leaf].n_children = (short)total;
+            games[g].node_count = first + total;
+        }
+    } else {
+        value = kind == 1 ? -1.0 : 0.0;  // pv_mcts.py:39
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int node = leaf;
+        while (node >= 0) {  // pv_mcts.py:50-51, 63-65: w += value; n += 1; parent gets -value
+            nodes[node].w += value;
+            nodes[node].n += 1;
+            value = -value;
+            node = nodes[node].parent;
+        }
+    }
+}
+
+__global__ void mcts_root_counts_kernel(const MctsGame *__restrict__ games, const MctsNode *__restrict__ nodes_all,
+                                        int64_t G, int64_t max_nodes, int32_t *__restrict__ counts,
+                                        int16_t *__restrict__ actions, int16_t *__restrict__ n_out,
+                                        int32_t *__restrict__ overflow) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= G) return;
+    const MctsNode *nodes = nodes_all + g * max_nodes;
+    const int first = nodes[0].first_child;
+    const int nc = first < 0 ? 0 : nodes[0].n_children;
+    for (int c = lane; c < AQ_MAX_LEGAL; c += 32) {
+        counts[g * AQ_MAX_LEGAL + c] = c < nc ? nodes[first + c].n : 0;
+        actions[g * AQ_MAX_LEGAL + c] = c < nc ? nodes[first + c].action : (int16_t)-1;
+    }
+    if (lane == 0) {
+        n_out[g] = (int16_t)nc;
+        if (overflow && games[g].overflow) atomicExch(overflow, 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" int64_t aq_mcts_ws_bytes(int64_t G, int64_t max_nodes) {
+    return (int64_t)(mcts_nodes_offset(G) + (size_t)G * (size_t)max_nodes * sizeof(MctsNode));
+}
+
+static inline MctsGame *games_of(void *ws) { return reinterpret_cast<MctsGame *>(ws); }
+static inline MctsNode *nodes_of(void *ws, int64_t G) {
+    return reinterpret_cast<MctsNode *>(reinterpret_cast<unsigned char *>(ws) + mcts_nodes_offset(G));
+}
+
+extern "C" int aq_mcts_reset(void *ws, const AqState *roots, int64_t G, int64_t max_nodes, void *stream) {
+    if (G <= 0 || max_nodes < 1 || !ws || !roots) return aq_set_error(AQ_ERR_ARG, "aq_mcts_reset");
+    mcts_reset_kernel<<<(unsigned)((G + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        games_of(ws), nodes_of(ws, G), roots, G, max_nodes);
+    return aq_check_launch("aq_mcts_reset");
+}
+
+extern "C" int aq_mcts_select(void *ws, int64_t G, int64_t max_nodes, float c_puct, AqState *leaf_states,
+                              int32_t *leaf_kind, void *stream) {
+    if (G <= 0 || !ws || !leaf_states || !leaf_kind) return aq_set_error(AQ_ERR_ARG, "aq_mcts_select");
+    mcts_select_kernel<<<(unsigned)((G + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        games_of(ws), nodes_of(ws, G), G, max_nodes, c_puct, leaf_states, leaf_kind);
+    return aq_check_launch("aq_mcts_select");
+}
+
+extern "C" int aq_mcts_expand_backup(void *ws, int64_t G, int64_t max_nodes, const float *priors, const float *values,
+                                     const uint32_t *mask, const uint8_t *pawn, void *stream) {
+    if (G <= 0 || !ws || !priors || !values || !mask || !pawn) return aq_set_error(AQ_ERR_ARG, "aq_mcts_expand_backup");
+    mcts_expand_backup_kernel<<<(unsigned)((G + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        games_of(ws), nodes_of(ws, G), G, max_nodes, priors, values, mask, pawn);
+    return aq_check_launch("aq_mcts_expand_backup");
+}
+
+extern "C" int aq_mcts_root_counts(void *ws, int64_t G, int64_t max_nodes, int32_t *counts, int16_t *actions,
+                                   int16_t *n_children, int32_t *overflow, void *stream) {
+    if (G <= 0 || !ws || !counts || !actions || !n_children) return aq_set_error(AQ_ERR_ARG, "aq_mcts_root_counts");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (overflow) {
+        cudaError_t e = cudaMemsetAsync(overflow, 0, sizeof(int32_t), st);
+        if (e != cudaSuccess) return aq_set_error((int)e, "aq_mcts_root_counts");
+    }
+    mcts_root_counts_kernel<<<(unsigned)((G + 3) / 4), 128, 0, st>>>(games_of(ws), nodes_of(ws, G), G, max_nodes, counts,
+                                                                     actions, n_children, overflow);
+    return aq_check_launch("aq_mcts_root_counts");
+}

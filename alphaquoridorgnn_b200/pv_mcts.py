@@ -1,0 +1,157 @@
+"""Policy-Value Monte Carlo Tree Search -- drop-in for reference pv_mcts.py, batched over games.
+
+Same public names (PV_EVALUATE_COUNT, pv_mcts_policy, pv_mcts_action, boltzman).  The tree lives on
+the GPU (csrc/mcts.cu): G games are searched in lock-step, so the leaf of every game at simulation k
+forms one batch for the network (batched leaf evaluation = model.predict for G states at once,
+pv_mcts.py:47).  The reference has no virtual loss, no Dirichlet noise and no tree reuse
+(pv_mcts.py:81 builds a fresh root per move), so each game's search is exactly the reference's.
+"""
+from copy import deepcopy
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import game_logic as gl
+
+# Prepare parameters
+PV_EVALUATE_COUNT = 50  # Number of simulations per inference (pv_mcts.py:18)
+C_PUCT = 1.25           # pv_mcts.py:71
+MAX_CHILDREN = 133      # 5 pawn moves + 128 wall placements
+
+
+def network_evaluator(model):
+    """Evaluator protocol: packed states uint8[G,32] -> dict(priors f32[G,209] (legal-masked,
+    renormalised), value f32[G], mask int32[G,8], pawn uint8[G,8])."""
+    return lambda packed: model.predict_batch(packed)
+
+
+class BatchedMCTS:
+    """Lock-step PV-MCTS over G independent root states."""
+
+    def __init__(self, evaluator, sims=None, c_puct=C_PUCT, device=None):
+        self.evaluator = evaluator
+        self.sims = sims
+        self.c_puct = float(c_puct)
+        self.device = gl._dev(device)
+        self._ws = None
+        self._cap = (0, 0)
+
+    def _workspace(self, G, max_nodes):
+        L = _lib.load()
+        need = L.aq_mcts_ws_bytes(G, max_nodes)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    @torch.no_grad()
+    def search(self, roots, sims=None):
+        """roots: packed uint8[G,32] (non-terminal states).  Runs `sims` simulations per game
+        (pv_mcts.py:84) and returns (counts int32[G,136], actions int16[G,136], n_children int16[G]):
+        visit counts of the root's children in State.legal_actions() order (pv_mcts.py:88)."""
+        sims = sims or self.sims or PV_EVALUATE_COUNT
+        L = _lib.load()
+        dev = self.device
+        roots = roots.to(dev).contiguous()
+        G = roots.shape[0]
+        max_nodes = 1 + sims * MAX_CHILDREN
+        ws = self._workspace(G, max_nodes)
+        leaf = torch.empty((G, gl.STATE_BYTES), dtype=torch.uint8, device=dev)
+        kind = torch.empty((G,), dtype=torch.int32, device=dev)
+        P = _lib.ptr
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            _lib.check(L.aq_mcts_reset(P(ws), P(roots), G, max_nodes, st), "aq_mcts_reset")
+            for _ in range(sims):
+                _lib.check(L.aq_mcts_select(P(ws), G, max_nodes, self.c_puct, P(leaf), P(kind), st), "aq_mcts_select")
+                out = self.evaluator(leaf)  # terminal leaves are evaluated too and ignored by the backup
+                _lib.check(L.aq_mcts_expand_backup(P(ws), G, max_nodes, P(out["priors"]), P(out["value"]), P(out["mask"]),
+                                                   P(out["pawn"]), st), "aq_mcts_expand_backup")
+            counts = torch.empty((G, gl.MAX_LEGAL), dtype=torch.int32, device=dev)
+            actions = torch.empty((G, gl.MAX_LEGAL), dtype=torch.int16, device=dev)
+            n = torch.empty((G,), dtype=torch.int16, device=dev)
+            ovf = torch.zeros((1,), dtype=torch.int32, device=dev)
+            _lib.check(L.aq_mcts_root_counts(P(ws), G, max_nodes, P(counts), P(actions), P(n), P(ovf), st),
+                       "aq_mcts_root_counts")
+        if int(ovf.item()):
+            raise _lib.AqError("MCTS node arena overflow")
+        return counts, actions, n
+
+
+def policy_from_counts(counts, temperature):
+    """pv_mcts.py:88-95 for a batch: counts [G,136] -> float64 probabilities [G,136] (0 beyond the
+    root's children)."""
+    c = counts.to(torch.float64)
+    if temperature == 0:  # most-visited child, first maximum (np.argmax)
+        pol = torch.zeros_like(c)
+        pol[torch.arange(c.shape[0], device=c.device), torch.argmax(counts, dim=1)] = 1.0
+        return pol
+    x = c ** (1.0 / temperature)
+    return x / x.sum(dim=1, keepdim=True)
+
+
+def _as_evaluator(model):
+    return model if callable(model) and not hasattr(model, "predict_batch") else network_evaluator(model)
+
+
+def pv_mcts_policy_batch(model, packed_roots, temperature, sims=None, device=None):
+    """Batched pv_mcts_policy: -> (policy float64[G,136], actions int16[G,136], n_children int16[G])."""
+    mcts = BatchedMCTS(_as_evaluator(model), sims or PV_EVALUATE_COUNT, device=device)
+    counts, actions, n = mcts.search(packed_roots)
+    return policy_from_counts(counts, temperature), actions, n
+
+
+def pv_mcts_policy(model, state, temperature, device=None):
+    """Use PUCT-based Monte Carlo Tree Search to return an improved policy (distribution over legal
+    actions), compared to the prior policy provided by the neural network (pv_mcts.py:20-95)."""
+    rows, plies = gl.rows_from_states([state])
+    packed = gl.pack_rows(rows, plies, device)
+    pol, _, n = pv_mcts_policy_batch(model, packed, temperature, PV_EVALUATE_COUNT, device)
+    k = int(n[0])
+    out = pol[0, :k].cpu().numpy()
+    return out if temperature == 0 else out.tolist()
+
+
+# Action selection with Monte Carlo Tree Search
+def pv_mcts_action(model, temperature=0, device=None):
+    """Returns a function of the game state that selects an action based on PV-MCTS (pv_mcts.py:98-103)."""
+    def pv_mcts_action(state):
+        policy = pv_mcts_policy(model, deepcopy(state), temperature, device)
+        return np.random.choice(state.legal_actions(), p=policy)
+    return pv_mcts_action
+
+
+# Boltzmann distribution
+def boltzman(xs, temperature):
+    """Boltzmann distribution (pv_mcts.py:106-109)"""
+    xs = [x ** (1 / temperature) for x in xs]
+    return [x / sum(xs) for x in xs]
+
+
+def bench_sims_per_sec(net, dev, world, timed_barrier, games=4096, sims=200, moves=2):
+    """MCTS simulations/s for bench.py (BASELINE configs[3] shape: `games` concurrent games x `sims`
+    simulations per move, `moves` moves from the start position, T=1 sampling)."""
+    import time
+    from . import positions
+    import torch.distributed as dist
+    mcts = BatchedMCTS(network_evaluator(net), sims, device=dev)
+    roots = positions.start_states(games, dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)
+    mcts.search(roots[:64], sims=4)  # warm-up
+    timed_barrier()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(moves):
+        counts, actions, n = mcts.search(roots)
+        pol = policy_from_counts(counts, 1.0)
+        pick = torch.multinomial(pol.float(), 1, generator=gen)
+        act = torch.gather(actions, 1, pick).squeeze(1)
+        roots, term = gl.next_batch(roots, act)
+        done += roots.shape[0] * sims
+        roots = roots[term == 0].contiguous()
+    timed_barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    return {"mcts_sims_per_sec": world * done / float(dt.item()), "mcts_config": f"{games} games x {sims} sims x {moves} moves per GPU"}

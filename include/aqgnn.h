@@ -150,6 +150,21 @@ int aq_leaf_eval_host(const float *params, const AqState *states_host, int64_t B
                       float *value_host, uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision,
                       void *stream);
 
+/* Lock-step PV-MCTS over G independent games (pv_mcts.py:20-95: Node.evaluate / next_child_node).
+ * ws: device workspace of aq_mcts_ws_bytes(G, max_nodes); max_nodes >= 1 + sims * 133 never overflows.
+ * One simulation = aq_mcts_select -> aq_leaf_eval on leaf_states -> aq_mcts_expand_backup.
+ *   leaf_kind[g]: 0 = leaf needs the network, 1 = terminal loss (value -1), 2 = terminal draw (0)
+ *   aq_mcts_root_counts: visit counts / actions of the root's children in legal_actions() order
+ *   (pv_mcts.py:88), n_children[g]; overflow[0] != 0 if any arena was exhausted. */
+int64_t aq_mcts_ws_bytes(int64_t G, int64_t max_nodes);
+int aq_mcts_reset(void *ws, const AqState *roots, int64_t G, int64_t max_nodes, void *stream);
+int aq_mcts_select(void *ws, int64_t G, int64_t max_nodes, float c_puct, AqState *leaf_states, int32_t *leaf_kind,
+                   void *stream);
+int aq_mcts_expand_backup(void *ws, int64_t G, int64_t max_nodes, const float *priors, const float *values,
+                          const uint32_t *mask, const uint8_t *pawn, void *stream);
+int aq_mcts_root_counts(void *ws, int64_t G, int64_t max_nodes, int32_t *counts /*[G,136]*/,
+                        int16_t *actions /*[G,136]*/, int16_t *n_children /*[G]*/, int32_t *overflow, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
