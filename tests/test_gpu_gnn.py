@@ -230,3 +230,33 @@ def test_checkpoint_interchange_and_training_step(tmp_path, traj):
     opt = torch.optim.Adam(net.parameters(), lr=1e-3)
     hist = net.train_model(loader, opt, None, "cuda", num_epochs=8)
     assert hist[-1] < hist[0]
+
+
+def test_bf16_tensor_core_path_within_tolerance(traj):
+    """tcgen05 (bf16 operands, fp32 accumulate) inference path vs the fp32 oracle.  Stated tolerance:
+    policy abs <= 2e-3, value abs <= 5e-3; the measured error is printed."""
+    rows, plies = _sample_rows(traj, 600, seed=21)
+    ref, net = _models(7)
+    x, ei, batch = gnn_oracle.graph_inputs_from_rows(rows)
+    with torch.no_grad():
+        p_ref, v_ref = ref(x, ei, batch)
+        net.eval()
+        p32, v32 = net(torch.from_numpy(rows))
+        net.precision = "bf16"
+        p16, v16 = net(torch.from_numpy(rows))
+        out = net.predict_batch(torch.from_numpy(rows), torch.from_numpy(plies))
+    ep = (p16.cpu() - p_ref).abs().max().item()
+    ev = (v16.cpu() - v_ref).abs().max().item()
+    print(f"bf16 path: max |dp| = {ep:.3e}, max |dv| = {ev:.3e}; fp32 path: {(p32.cpu() - p_ref).abs().max().item():.3e}")
+    assert ep <= 2e-3 and ev <= 5e-3, (ep, ev)
+    assert torch.allclose(p16.sum(1), torch.ones(600, device="cuda"), atol=1e-5)
+    # repeated launches are deterministic, ragged batch sizes work
+    with torch.no_grad():
+        p16b, _ = net(torch.from_numpy(rows))
+        p3, v3 = net(torch.from_numpy(rows[:3]))
+    assert torch.equal(p16, p16b)
+    assert torch.equal(p3, p16[:3]) and torch.equal(v3, v16[:3])
+    # leaf evaluation through the bf16 path keeps the exact legal mask and stays within tolerance
+    legal = qo.legal_actions_batch(rows, plies)
+    assert np.array_equal(out["mask"].cpu().numpy().view(np.uint32), legal["mask"])
+    assert (out["value"].cpu() - v_ref.squeeze(1)).abs().max().item() <= 5e-3
