@@ -1,8 +1,9 @@
 // bf16 tensor-core path of the GCN trunk (inference): graph build + 3 GCN layers + mean pool with
 // the two 128x128 node transforms on the 5th-gen tensor cores.
 //
-//   * one CTA (256 threads) per SM, persistent over boards; W2, W3 live in shared memory as bf16 in
-//     the canonical UMMA K-major SWIZZLE_128B layout for the whole kernel;
+//   * one CTA per SM, persistent over boards, two 8-warp groups each owning one board at a time;
+//     W2, W3 live in shared memory as bf16 in the canonical UMMA K-major SWIZZLE_128B layout for
+//     the whole kernel and are shared by both groups;
 //   * per board and layer: the activations X (81 rows, padded to the M=128 tile) are written as bf16
 //     into the swizzled A tile, ONE thread issues 8 x tcgen05.mma (M128 N128 K16, kind::f16, fp32
 //     accumulate in TMEM), tcgen05.commit arrives on an mbarrier, the 8 warps read the accumulator
@@ -19,32 +20,53 @@ using namespace aq;
 
 namespace {
 
-constexpr int kTcThreads = 256;
+// Two independent 8-warp groups per CTA, each working on its own board (own A tile, Z buffer, TMEM
+// accumulator and mbarrier) and sharing the bf16 weight tiles: while one group waits for its MMAs
+// the other runs its CUDA-core phases, and the SM holds 16 warps to hide shared-memory latency.
+constexpr int kGroups = 2;
+constexpr int kGroupThreads = 256;
+constexpr int kTcThreads = kGroups * kGroupThreads;
 constexpr int kZStride = 132;                // fp32 Z rows padded: conflict-free per-row float4 stores
 constexpr uint32_t kTileBytes = 128 * 256;   // 128 rows x 128 bf16 = two K-blocks of 128 rows x 128 B
 constexpr uint32_t kKBlockBytes = 128 * 128;
-constexpr uint32_t kTmemCols = 128;
+constexpr uint32_t kTmemCols = 128 * kGroups;
 
 // tcgen05 instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1),
 // both K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
+// Rows 81..127 of each K-block of the A tile are read by the tensor core but their accumulator rows
+// are never used, so those 47 x 128 B = 6016 B per K-block hold the group's small per-board arrays.
+constexpr uint32_t kGap0 = kV * 128;                        // K-block 0 gap: coef | x0 | ax0 | open
+constexpr uint32_t kOffCoef = kGap0;                        // 408 floats
+constexpr uint32_t kOffX0 = kOffCoef + 1632;                // 488 floats
+constexpr uint32_t kOffAx0 = kOffX0 + 1952;                 // 488 floats
+constexpr uint32_t kOffOpen = kOffAx0 + 1952;               // 96 bytes
+static_assert(kOffOpen + 96 <= kKBlockBytes, "K-block 0 gap overflow");
+constexpr uint32_t kOffRed = kKBlockBytes + kGap0;          // K-block 1 gap: pool partials 8 x 128 floats
+static_assert(kOffRed + 8 * kH * 4 <= 2 * kKBlockBytes, "K-block 1 gap overflow");
+
+struct TcGroupSmem {
+    unsigned char a[kTileBytes];  // 1024-byte aligned (SWIZZLE_128B atoms are 8 rows x 128 B)
+    float z[kV * kZStride];
+    unsigned char pad[1024 - (kV * kZStride * 4) % 1024];
+};
+static_assert(sizeof(TcGroupSmem) % 1024 == 0, "group smem must keep 1024-byte alignment");
+
 struct TcSmem {
-    // 1024-byte aligned (SWIZZLE_128B atoms are 8 rows x 128 B)
     unsigned char w2[kTileBytes];
     unsigned char w3[kTileBytes];
-    unsigned char a[kTileBytes];
-    float z[kV * kZStride];
+    TcGroupSmem g[kGroups];
     float w1t[kF * kH];
-    float b1[kH], b2[kH], b3[kH];
-    float coef[kV * 5 + 3];
-    float x0[kV * kF + 2];
-    float ax0[kV * kF + 2];
-    float red[8 * kH];
-    unsigned long long mbar;
+    float b1[kH];
+    unsigned long long mbar[kGroups];
     uint32_t tmem_base;
-    uint8_t open_s[96];
 };
+static_assert(sizeof(TcSmem) + 1024 <= 227 * 1024, "TcSmem exceeds shared memory");
+
+__device__ __forceinline__ void group_sync(int grp) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(grp + 1), "r"(kGroupThreads) : "memory");
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -102,93 +124,103 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t *>(&t);
 }
 
-// fp32 [128][128] row-major weight in global memory -> bf16 swizzled K-major tile (row = n, col = k)
-__device__ __forceinline__ void load_weight_bf16(unsigned char *tile, const float *__restrict__ W, int tid) {
-    for (int c = tid; c < 128 * 16; c += kTcThreads) {
-        const int n = c >> 4, j = c & 15;
+__global__ void __launch_bounds__(kTcThreads, 1)
+gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restrict__ states, int64_t B,
+                      float *__restrict__ pooled_out) {
+    extern __shared__ unsigned char smem_raw[];
+    TcSmem &sm = *reinterpret_cast<TcSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const int gtid = threadIdx.x;
+    const int grp = gtid / kGroupThreads, tid = gtid % kGroupThreads, lane = tid & 31, warp = tid >> 5;
+
+    for (int c = gtid; c < 2 * 128 * 16; c += kTcThreads) {  // both weight tiles, 16-byte chunks
+        const int which = c >> 11, cc = c & 2047;
+        const int n = cc >> 4, j = cc & 15;
+        const float *W = params + (which ? kOffW3 : kOffW2);
         const float4 lo = __ldg(reinterpret_cast<const float4 *>(W + n * kH + j * 8));
         const float4 hi = __ldg(reinterpret_cast<const float4 *>(W + n * kH + j * 8) + 1);
         uint4 v;
         v.x = pack_bf16(lo.x, lo.y); v.y = pack_bf16(lo.z, lo.w);
         v.z = pack_bf16(hi.x, hi.y); v.w = pack_bf16(hi.z, hi.w);
-        *reinterpret_cast<uint4 *>(tile + sw128_chunk(n, j)) = v;
+        *reinterpret_cast<uint4 *>((which ? sm.w3 : sm.w2) + sw128_chunk(n, j)) = v;
     }
-}
-
-__global__ void __launch_bounds__(kTcThreads, 1)
-gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restrict__ states, int64_t B,
-                      float *__restrict__ pooled_out) {
-    extern __shared__ unsigned char smem_raw[];
-    // SWIZZLE_128B tiles need 1024-byte alignment
-    TcSmem &sm = *reinterpret_cast<TcSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    load_weight_bf16(sm.w2, params + kOffW2, tid);
-    load_weight_bf16(sm.w3, params + kOffW3, tid);
-    for (int i = tid; i < kF * kH; i += kTcThreads) {
+    for (int i = gtid; i < kF * kH; i += kTcThreads) {
         const int n = i / kF, f = i % kF;
         sm.w1t[f * kH + n] = __ldg(params + kOffW1 + i);
     }
-    if (tid < kH) {
-        sm.b1[tid] = __ldg(params + kOffB1 + tid);
-        sm.b2[tid] = __ldg(params + kOffB2 + tid);
-        sm.b3[tid] = __ldg(params + kOffB3 + tid);
-    }
-    const uint32_t bar = smem_u32(&sm.mbar);
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
+    if (gtid < kH) sm.b1[gtid] = __ldg(params + kOffB1 + gtid);
+    if (gtid < kGroups) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&sm.mbar[gtid])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (warp == 0) {  // TMEM accumulator: 128 lanes x 128 fp32 columns
+    if (gtid < 32) {  // TMEM: 128 lanes x (128 fp32 columns per group)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const uint32_t tmem = sm.tmem_base;
-    const uint32_t a_addr = smem_u32(sm.a), w2_addr = smem_u32(sm.w2), w3_addr = smem_u32(sm.w3);
+
+    TcGroupSmem &gs = sm.g[grp];
+    float *coef = reinterpret_cast<float *>(gs.a + kOffCoef);
+    float *x0 = reinterpret_cast<float *>(gs.a + kOffX0);
+    float *ax0 = reinterpret_cast<float *>(gs.a + kOffAx0);
+    uint8_t *open_s = gs.a + kOffOpen;
+    float *red = reinterpret_cast<float *>(gs.a + kOffRed);
+    const uint32_t tmem = sm.tmem_base + (uint32_t)grp * 128u;  // this group's accumulator columns
+    const uint32_t bar = smem_u32(&sm.mbar[grp]);
+    const uint32_t a_addr = smem_u32(gs.a), w2_addr = smem_u32(sm.w2), w3_addr = smem_u32(sm.w3);
+    const float4 bias2 = __ldg(reinterpret_cast<const float4 *>(params + kOffB2) + lane);
+    const float4 bias3 = __ldg(reinterpret_cast<const float4 *>(params + kOffB3) + lane);
     uint32_t phase = 0;
 
-    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int64_t b = (int64_t)blockIdx.x * kGroups + grp; b < B; b += (int64_t)gridDim.x * kGroups) {
         // ---- inputs ---------------------------------------------------------------------------
         {
             const AqState s = load_state(states + b);
-            board_inputs_from_state(s, sm.x0, sm.open_s, tid);
+            board_inputs_from_state(s, x0, open_s, tid);
         }
-        __syncthreads();
-        board_coefficients(sm.open_s, sm.coef, tid);
-        __syncthreads();
-        for (int i = tid; i < kV * kF; i += kTcThreads) {
+        group_sync(grp);
+        board_coefficients(open_s, coef, tid);
+        group_sync(grp);
+        for (int i = tid; i < kV * kF; i += kGroupThreads) {
             const int v = i / kF, f = i % kF;
-            const float *c = sm.coef + v * 5;
-            float s = c[0] * sm.x0[i];
-            if (c[1] != 0.f) s = fmaf(c[1], sm.x0[(v - 9) * kF + f], s);
-            if (c[2] != 0.f) s = fmaf(c[2], sm.x0[(v + 9) * kF + f], s);
-            if (c[3] != 0.f) s = fmaf(c[3], sm.x0[(v - 1) * kF + f], s);
-            if (c[4] != 0.f) s = fmaf(c[4], sm.x0[(v + 1) * kF + f], s);
-            sm.ax0[i] = s;
+            const float *c = coef + v * 5;
+            float s = c[0] * x0[i];
+            if (c[1] != 0.f) s = fmaf(c[1], x0[(v - 9) * kF + f], s);
+            if (c[2] != 0.f) s = fmaf(c[2], x0[(v + 9) * kF + f], s);
+            if (c[3] != 0.f) s = fmaf(c[3], x0[(v - 1) * kF + f], s);
+            if (c[4] != 0.f) s = fmaf(c[4], x0[(v + 1) * kF + f], s);
+            ax0[i] = s;
         }
-        __syncthreads();
-        // ---- layer 1 on the CUDA cores, written straight into the swizzled bf16 A tile ----------
-        for (int c = tid; c < kV * 16; c += kTcThreads) {
-            const int v = c >> 4, j = c & 15;
-            float a6[kF];
-#pragma unroll
-            for (int f = 0; f < kF; ++f) a6[f] = sm.ax0[v * kF + f];
-            float o[8];
+        group_sync(grp);
+        // ---- layer 1 on the CUDA cores, written straight into the swizzled bf16 A tile: thread owns
+        //      the 8 output columns of chunk j for rows v0, v0+16, ... (weights reused from registers)
+        {
+            const int j = tid & 15, v0 = tid >> 4;
+            float w[kF][8], bb[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int n = j * 8 + e;
-                float s = sm.b1[n];
+                bb[e] = sm.b1[j * 8 + e];
 #pragma unroll
-                for (int f = 0; f < kF; ++f) s = fmaf(a6[f], sm.w1t[f * kH + n], s);
-                o[e] = fmaxf(s, 0.f);
+                for (int f = 0; f < kF; ++f) w[f][e] = sm.w1t[f * kH + j * 8 + e];
             }
-            uint4 pk;
-            pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]);
-            pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
-            *reinterpret_cast<uint4 *>(sm.a + sw128_chunk(v, j)) = pk;
+            for (int v = v0; v < kV; v += 16) {
+                float a6[kF];
+#pragma unroll
+                for (int f = 0; f < kF; ++f) a6[f] = ax0[v * kF + f];
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float s = bb[e];
+#pragma unroll
+                    for (int f = 0; f < kF; ++f) s = fmaf(a6[f], w[f][e], s);
+                    o[e] = fmaxf(s, 0.f);
+                }
+                uint4 pk;
+                pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]);
+                pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
+                *reinterpret_cast<uint4 *>(gs.a + sw128_chunk(v, j)) = pk;
+            }
         }
         float4 pool = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
@@ -196,7 +228,7 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
             // make the generic-proxy writes of the A tile visible to the tensor core (async proxy)
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            __syncthreads();
+            group_sync(grp);
             if (tid == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint32_t w_addr = layer == 1 ? w2_addr : w3_addr;
@@ -215,32 +247,40 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
             {
                 const int q = warp & 3, half = warp >> 2;
                 const int r = q * 32 + lane;
+                if (q * 32 < kV) {  // quadrant 3 (rows 96..127) holds no board rows
 #pragma unroll
-                for (int cb = 0; cb < 2; ++cb) {
-                    const int col0 = half * 64 + cb * 32;
-                    float v[32];
-                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
-                    if (r < kV) {
-                        float4 *dst = reinterpret_cast<float4 *>(sm.z + r * kZStride + col0);
+                    for (int cb = 0; cb < 2; ++cb) {
+                        const int col0 = half * 64 + cb * 32;
+                        float v[32];
+                        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+                        if (r < kV) {
+                            float4 *dst = reinterpret_cast<float4 *>(gs.z + r * kZStride + col0);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        }
                     }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            __syncthreads();
-            // ---- aggregation + bias + ReLU, warp per node --------------------------------------------
+            group_sync(grp);
+            // ---- aggregation + bias + ReLU, warp per node; all five rows are loaded unconditionally
+            //      (closed directions re-read the node's own row with coefficient 0) for load-level ILP
             {
-                const float4 bb = reinterpret_cast<const float4 *>(layer == 1 ? sm.b2 : sm.b3)[lane];
-                for (int v = warp; v < kV; v += kTcThreads / 32) {
-                    const float *c = sm.coef + v * 5;
+                const float4 bb = layer == 1 ? bias2 : bias3;
+#pragma unroll 2
+                for (int v = warp; v < kV; v += kGroupThreads / 32) {
+                    const float *c = coef + v * 5;
                     const float c0 = c[0], cu = c[1], cd = c[2], cl = c[3], cr = c[4];
-                    float4 a = *reinterpret_cast<const float4 *>(sm.z + v * kZStride + lane * 4);
-                    float4 s = make_float4(c0 * a.x, c0 * a.y, c0 * a.z, c0 * a.w);
-                    if (cu != 0.f) { a = *reinterpret_cast<const float4 *>(sm.z + (v - 9) * kZStride + lane * 4); s.x = fmaf(cu, a.x, s.x); s.y = fmaf(cu, a.y, s.y); s.z = fmaf(cu, a.z, s.z); s.w = fmaf(cu, a.w, s.w); }
-                    if (cd != 0.f) { a = *reinterpret_cast<const float4 *>(sm.z + (v + 9) * kZStride + lane * 4); s.x = fmaf(cd, a.x, s.x); s.y = fmaf(cd, a.y, s.y); s.z = fmaf(cd, a.z, s.z); s.w = fmaf(cd, a.w, s.w); }
-                    if (cl != 0.f) { a = *reinterpret_cast<const float4 *>(sm.z + (v - 1) * kZStride + lane * 4); s.x = fmaf(cl, a.x, s.x); s.y = fmaf(cl, a.y, s.y); s.z = fmaf(cl, a.z, s.z); s.w = fmaf(cl, a.w, s.w); }
-                    if (cr != 0.f) { a = *reinterpret_cast<const float4 *>(sm.z + (v + 1) * kZStride + lane * 4); s.x = fmaf(cr, a.x, s.x); s.y = fmaf(cr, a.y, s.y); s.z = fmaf(cr, a.z, s.z); s.w = fmaf(cr, a.w, s.w); }
+                    const float4 a0 = *reinterpret_cast<const float4 *>(gs.z + v * kZStride + lane * 4);
+                    const float4 au = *reinterpret_cast<const float4 *>(gs.z + (cu != 0.f ? v - 9 : v) * kZStride + lane * 4);
+                    const float4 ad = *reinterpret_cast<const float4 *>(gs.z + (cd != 0.f ? v + 9 : v) * kZStride + lane * 4);
+                    const float4 al = *reinterpret_cast<const float4 *>(gs.z + (cl != 0.f ? v - 1 : v) * kZStride + lane * 4);
+                    const float4 ar = *reinterpret_cast<const float4 *>(gs.z + (cr != 0.f ? v + 1 : v) * kZStride + lane * 4);
+                    float4 s;
+                    s.x = fmaf(cr, ar.x, fmaf(cl, al.x, fmaf(cd, ad.x, fmaf(cu, au.x, c0 * a0.x))));
+                    s.y = fmaf(cr, ar.y, fmaf(cl, al.y, fmaf(cd, ad.y, fmaf(cu, au.y, c0 * a0.y))));
+                    s.z = fmaf(cr, ar.z, fmaf(cl, al.z, fmaf(cd, ad.z, fmaf(cu, au.z, c0 * a0.z))));
+                    s.w = fmaf(cr, ar.w, fmaf(cl, al.w, fmaf(cd, ad.w, fmaf(cu, au.w, c0 * a0.w))));
                     s.x = fmaxf(s.x + bb.x, 0.f); s.y = fmaxf(s.y + bb.y, 0.f);
                     s.z = fmaxf(s.z + bb.z, 0.f); s.w = fmaxf(s.w + bb.w, 0.f);
                     if (layer + 1 < kLayers) {
@@ -248,7 +288,7 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
                         uint2 pk;
                         pk.x = pack_bf16(s.x, s.y);
                         pk.y = pack_bf16(s.z, s.w);
-                        *reinterpret_cast<uint2 *>(sm.a + sw128_chunk(v, lane >> 1) + (lane & 1) * 8) = pk;
+                        *reinterpret_cast<uint2 *>(gs.a + sw128_chunk(v, lane >> 1) + (lane & 1) * 8) = pk;
                     } else {
                         pool.x += s.x; pool.y += s.y; pool.z += s.z; pool.w += s.w;
                     }
@@ -256,21 +296,21 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
             }
         }
         // ---- global_mean_pool -----------------------------------------------------------------------
-        reinterpret_cast<float4 *>(sm.red + warp * kH)[lane] = pool;
-        __syncthreads();
+        reinterpret_cast<float4 *>(red + warp * kH)[lane] = pool;
+        group_sync(grp);
         if (tid < kH) {
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) s += sm.red[w * kH + tid];
+            for (int w = 0; w < 8; ++w) s += red[w * kH + tid];
             pooled_out[b * kH + tid] = s / (float)kV;
         }
-        __syncthreads();
+        group_sync(grp);
     }
     // ---- teardown ------------------------------------------------------------------------------------
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    if (gtid < 32) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(sm.tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -287,7 +327,8 @@ int aq_gcn_forward_tc(const float *params, const AqState *states, int64_t B, flo
     const size_t smem = sizeof(TcSmem) + 1024;
     cudaError_t e = cudaFuncSetAttribute(gcn_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return aq_set_error((int)e, "gcn_forward_tc smem");
-    const unsigned grid = (unsigned)(B < sms ? B : sms);
+    const int64_t want = (B + kGroups - 1) / kGroups;
+    const unsigned grid = (unsigned)(want < sms ? want : sms);
     gcn_forward_tc_kernel<<<grid, kTcThreads, smem, st>>>(params, states, B, pooled);
     return aq_check_launch("gcn_forward_tc_kernel");
 }
