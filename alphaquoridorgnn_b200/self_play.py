@@ -1,0 +1,124 @@
+"""Self-play -- drop-in for reference self_play.py, with all games of a run played in lock-step on
+the GPU (game-level sharding across ranks needs no communication).
+
+History format is the reference's (self_play.py:51-54,63-66): a list of
+``[[player, enemy, walls], policy (209 floats), value]`` pickled to ``./data/<timestamp>.history``."""
+import os
+import pickle
+from datetime import datetime
+
+import numpy as np
+import torch
+
+from . import game_logic as gl
+from . import pv_mcts
+from .constants import PV_NETWORK_PATH
+from .pv_network_gnn import GNNNetwork, POLICY_OUTPUT_SIZE
+from .positions import start_states
+
+# Parameters
+SP_GAME_COUNT = 50  # Number of games for self-play (self_play.py:19)
+SP_TEMPERATURE = 1.0  # Temperature parameter for Boltzmann distribution (self_play.py:20)
+
+
+def first_player_value(ended_state):
+    """1: First player wins, -1: First player loses, 0: Draw (self_play.py:22-27)."""
+    if ended_state.is_lose():
+        return -1 if ended_state.is_first_player() else 1
+    return 0
+
+
+def write_data(history, directory='./data/'):
+    """Save training data to a file (self_play.py:30-37)."""
+    now = datetime.now()
+    os.makedirs(directory, exist_ok=True)
+    path = os.path.join(directory, '{:04}{:02}{:02}{:02}{:02}{:02}.history'.format(
+        now.year, now.month, now.day, now.hour, now.minute, now.second))
+    with open(path, mode='wb') as f:
+        pickle.dump(history, f)
+    return path
+
+
+@torch.no_grad()
+def play_batch(model, num_games, device=None, sims=None, temperature=SP_TEMPERATURE, seed=None, max_plies=None):
+    """Execute `num_games` self-play games in lock-step (self_play.py:40-68 per game).
+    Returns (history in the reference format, dict with per-game results)."""
+    dev = gl._dev(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed) if seed is not None else int(torch.seed() % (2 ** 31)))
+    mcts = pv_mcts.BatchedMCTS(pv_mcts._as_evaluator(model), sims or pv_mcts.PV_EVALUATE_COUNT, device=dev)
+    states = start_states(num_games, dev)
+    game_id = torch.arange(num_games, device=dev)
+    rec_state, rec_policy, rec_game = [], [], []
+    final_flags = torch.zeros(num_games, dtype=torch.uint8, device=dev)
+    final_plies = torch.zeros(num_games, dtype=torch.int64, device=dev)
+    ply = 0
+    while states.shape[0] > 0 and (max_plies is None or ply < max_plies):
+        counts, actions, n = mcts.search(states)
+        pol = pv_mcts.policy_from_counts(counts, temperature)            # [G,136] over legal actions
+        dense = torch.zeros((states.shape[0], POLICY_OUTPUT_SIZE), dtype=torch.float64, device=dev)
+        valid = actions >= 0
+        dense.scatter_(1, actions.clamp(min=0).to(torch.int64), torch.where(valid, pol, torch.zeros_like(pol)))
+        rec_state.append(states)
+        rec_policy.append(dense)
+        rec_game.append(game_id)
+        pick = torch.multinomial(pol.float(), 1, generator=gen)          # np.random.choice(legal, p=scores)
+        act = torch.gather(actions, 1, pick).squeeze(1)
+        states, term = gl.next_batch(states, act)
+        ply += 1
+        done = term != 0
+        final_flags[game_id[done]] = term[done]
+        final_plies[game_id[done]] = ply
+        states, game_id = states[~done].contiguous(), game_id[~done]
+    # ---- host side: the reference's list-of-lists with back-filled values (self_play.py:63-66) ----
+    all_states = torch.cat(rec_state)
+    rows, _ = gl.unpack_rows(all_states)
+    rows = rows.cpu().numpy()
+    pols = torch.cat(rec_policy).cpu().numpy()
+    gids = torch.cat(rec_game).cpu().numpy()
+    flags, plies = final_flags.cpu().numpy(), final_plies.cpu().numpy()
+    order = np.argsort(gids, kind='stable')                              # plies stay in order within a game
+    history, seen = [], {}
+    for i in order:
+        g = int(gids[i])
+        k = seen.get(g, 0)                                               # ply index inside game g
+        seen[g] = k + 1
+        # first_player_value of the ended state (self_play.py:22-27): the player to move there has lost
+        fpv = (-1 if plies[g] % 2 == 0 else 1) if (flags[g] & 1) else 0
+        value = fpv if k % 2 == 0 else -fpv                              # alternating sign, self_play.py:63-66
+        r = rows[i]
+        history.append([[r[0:2].tolist(), r[2:4].tolist(), r[4:].tolist()], pols[i].tolist(), value])
+    return history, {"flags": flags, "plies": plies}
+
+
+def play(model, device=None):
+    """Execute one self-play game (self_play.py:40-68)."""
+    history, _ = play_batch(model, 1, device)
+    return history
+
+
+def self_play(game_count=None, model_path=None, data_dir='./data/', rank=0, world_size=1, sims=None, seed=None):
+    """Perform self-play games and save the training data (self_play.py:71-98).  With
+    world_size > 1 each rank plays its share of the games on its own GPU and rank 0 writes the file."""
+    game_count = SP_GAME_COUNT if game_count is None else game_count
+    model = GNNNetwork()
+    model.prep_for_inference(model_path=model_path or (PV_NETWORK_PATH + 'best.pth'))
+    mine = game_count // world_size + (1 if rank < game_count % world_size else 0)
+    history, _ = play_batch(model, mine, sims=sims, seed=None if seed is None else seed + rank) if mine else ([], None)
+    if world_size > 1:
+        import torch.distributed as dist
+        gathered = [None] * world_size if rank == 0 else None
+        dist.gather_object(history, gathered, dst=0)
+        if rank == 0:
+            history = [h for part in gathered for h in part]
+    path = None
+    if rank == 0:
+        path = write_data(history, data_dir)
+        print(f'Self-play: {game_count} games, {len(history)} positions -> {path}')
+    del model
+    torch.cuda.empty_cache()
+    return path
+
+
+if __name__ == '__main__':
+    self_play()

@@ -184,6 +184,7 @@ def run_ours(args, rank, world, local_rank):
 
     torch.manual_seed(0)
     net = GNNNetwork().to(dev).eval()
+    net.precision = args.precision
     flat = net.flat_parameters()
     nb = 4
     allpos = positions.random_positions(nb * B, seed=1 + rank, games=8192, device=dev)
@@ -364,7 +365,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16384)
-    ap.add_argument("--precision", default=os.environ.get("AQ_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("AQ_PRECISION", "bf16"), choices=["fp32", "bf16"],
+                    help="GNN inference arithmetic: bf16 = tcgen05 tensor cores (default), fp32 = FFMA")
     ap.add_argument("--skip-extra", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()

@@ -1,0 +1,123 @@
+"""GPU tests of the callers either side of the hot path: self-play history, training loop (flat-buffer
+trainer vs torch autograd + torch.optim.Adam), arena evaluation and one tiny train cycle."""
+import copy
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from alphaquoridorgnn_b200 import game_logic as gl
+from alphaquoridorgnn_b200 import evaluate_network, pv_mcts, self_play, train_network
+from alphaquoridorgnn_b200.pv_network_gnn import GNNNetwork, create_network
+from oracle import quoridor_oracle as qo
+
+pytestmark = pytest.mark.gpu
+
+
+def _net(seed=0):
+    torch.manual_seed(seed)
+    return GNNNetwork().cuda().eval()
+
+
+def test_self_play_history_format_and_semantics():
+    net = _net()
+    history, info = self_play.play_batch(net, 6, sims=8, seed=1)
+    assert len(history) == int(info["plies"].sum())
+    # reference format: [[player, enemy, walls], policy[209], value]
+    k = 0
+    for g in range(6):
+        n = int(info["plies"][g])
+        game = history[k:k + n]
+        k += n
+        state = qo.PyOracleState()
+        for i, (s, policy, value) in enumerate(game):
+            assert s == state.to_array()                                   # trajectory is a legal game
+            la = state.legal_actions()
+            pol = np.array(policy)
+            assert len(policy) == 209 and abs(pol.sum() - 1.0) < 1e-9
+            assert set(np.nonzero(pol)[0].tolist()) <= set(la)            # mass only on legal actions
+            assert value == game[0][2] * (1 if i % 2 == 0 else -1)        # alternating sign
+            # the move actually played is not stored; recover it from the next state
+            if i + 1 < n:
+                nxt = game[i + 1][0]
+                cand = [a for a in la if state.next(a).to_array() == nxt]
+                assert cand, "next position is not a successor"
+                state = state.next(cand[0])
+        assert game[0][2] in (-1, 0, 1)
+        lose, draw = info["flags"][g] & 1, info["flags"][g] & 2
+        assert lose or draw
+        if lose:   # the player to move in the final state lost: first player iff plies even
+            assert game[0][2] == (-1 if n % 2 == 0 else 1)
+        else:
+            assert game[0][2] == 0 and n == 116
+
+
+def test_flat_trainer_matches_torch_autograd_and_adam(traj):
+    rng = np.random.default_rng(0)
+    idx = rng.choice(len(traj["rows"]), 96, replace=False)
+    rows = traj["rows"][idx]
+    torch.manual_seed(3)
+    pt = torch.softmax(2 * torch.randn(96, 209), 1).cuda()
+    vt = torch.randint(-1, 2, (96,)).float().cuda()
+    a = _net(1).train()
+    b = copy.deepcopy(a)
+    packed = gl.pack_rows(rows)
+    trainer = train_network.FlatTrainer(a, lr=1e-3)
+    opt = torch.optim.Adam(b.parameters(), lr=1e-3)
+    ce, mse = torch.nn.CrossEntropyLoss(), torch.nn.MSELoss()
+    for step in range(4):
+        loss_flat = trainer.step(packed, pt, vt, 96).sum().item()
+        p, v = b(packed)
+        loss = ce(p, pt) + mse(v.squeeze(), vt)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        assert abs(loss_flat - loss.item()) <= 2e-5
+    pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+    for n in pa:
+        assert (pa[n] - pb[n]).abs().max().item() <= 2e-6, n
+
+
+def test_train_on_history_and_sharded_steps_equal_full_batch(traj):
+    """Two half-batch steps whose gradients are summed (what the all-reduce does) give the same
+    update as one full-batch step: data-parallel exactness on a single GPU."""
+    rng = np.random.default_rng(1)
+    idx = rng.choice(len(traj["rows"]), 64, replace=False)
+    packed = gl.pack_rows(traj["rows"][idx])
+    torch.manual_seed(4)
+    pt = torch.softmax(torch.randn(64, 209), 1).cuda()
+    vt = torch.randint(-1, 2, (64,)).float().cuda()
+    full = train_network.FlatTrainer(_net(2).train())
+    full.step(packed, pt, vt, 64)
+    g_full = full.grads.clone()
+    parts = []
+    for rank in range(2):
+        lo, hi = train_network.shard_bounds(64, rank, 2)
+        t = train_network.FlatTrainer(_net(2).train())
+        t.step(packed[lo:hi].contiguous(), pt[lo:hi].contiguous(), vt[lo:hi].contiguous(), 64)
+        parts.append(t.grads.clone())
+    assert (parts[0] + parts[1] - g_full).abs().max().item() <= 1e-6 * max(1.0, g_full.abs().max().item())
+    # the full loop lowers the loss on a fixed history
+    history = [[[r[0:2].tolist(), r[2:4].tolist(), r[4:].tolist()], pt[i].tolist(), float(vt[i])]
+               for i, r in enumerate(traj["rows"][idx])]
+    losses = train_network.train_on_history(_net(5), history, num_epochs=6, batch_size=32, verbose=False)
+    assert sum(losses[-1]) < sum(losses[0])
+
+
+def test_arena_and_tiny_train_cycle(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    model_dir = str(tmp_path / "models") + os.sep
+    create_network(model_dir + "best.pth")
+    assert os.path.exists(model_dir + "best.pth")
+    monkeypatch.setattr(pv_mcts, "PV_EVALUATE_COUNT", 6)
+    path = self_play.self_play(game_count=4, model_path=model_dir + "best.pth", data_dir=str(tmp_path / "data"), seed=3)
+    hist = pickle.load(open(path, "rb"))
+    assert len(hist) > 8 and len(hist[0]) == 3 and len(hist[0][1]) == 209
+    train_network.train_network(data_dir=str(tmp_path / "data"), model_dir=model_dir, num_epochs=2)
+    assert os.path.exists(model_dir + "latest.pth")
+    promoted = evaluate_network.evaluate_network(model_dir=model_dir, num_games=4, sims=6)
+    assert promoted in (True, False)
+    pts = evaluate_network.play_matches(_net(0), _net(0), num_games=4, sims=6, seed=1)
+    assert 0.0 <= pts <= 4.0
