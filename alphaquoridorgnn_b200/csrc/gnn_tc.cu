@@ -37,11 +37,10 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) <<
 
 // Rows 81..127 of each K-block of the A tile are read by the tensor core but their accumulator rows
 // are never used, so those 47 x 128 B = 6016 B per K-block hold the group's small per-board arrays.
-constexpr uint32_t kGap0 = kV * 128;                        // K-block 0 gap: coef | x0 | ax0 | open
-constexpr uint32_t kOffCoef = kGap0;                        // 408 floats
-constexpr uint32_t kOffX0 = kOffCoef + 1632;                // 488 floats
-constexpr uint32_t kOffAx0 = kOffX0 + 1952;                 // 488 floats
-constexpr uint32_t kOffOpen = kOffAx0 + 1952;               // 96 bytes
+constexpr uint32_t kGap0 = kV * 128;                        // K-block 0 gap: node records | x0 | open
+constexpr uint32_t kOffRec = kGap0;                         // 81 x 32 B: {c0,cu,cd,cl | cr, packed neighbour rows, -, -}
+constexpr uint32_t kOffX0 = kOffRec + kV * 32;              // 488 floats
+constexpr uint32_t kOffOpen = kOffX0 + 1952;                // 96 bytes
 static_assert(kOffOpen + 96 <= kKBlockBytes, "K-block 0 gap overflow");
 constexpr uint32_t kOffRed = kKBlockBytes + kGap0;          // K-block 1 gap: pool partials 8 x 128 floats
 static_assert(kOffRed + 8 * kH * 4 <= 2 * kKBlockBytes, "K-block 1 gap overflow");
@@ -57,8 +56,7 @@ struct TcSmem {
     unsigned char w2[kTileBytes];
     unsigned char w3[kTileBytes];
     TcGroupSmem g[kGroups];
-    float w1t[kF * kH];
-    float b1[kH];
+    unsigned char w1[128 * 32];   // layer-1 B operand: bf16 [128 n][16 k], K-major SWIZZLE_32B
     unsigned long long mbar[kGroups];
     uint32_t tmem_base;
 };
@@ -79,6 +77,15 @@ __device__ __forceinline__ uint32_t sw128_chunk(int row, int j) {
 // version 1 (Blackwell), layout type 2 = SWIZZLE_128B
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// K-major SWIZZLE_32B operand (rows of 32 B, 8-row atoms of 256 B): chunk c of row r sits at
+// r*32 + ((c ^ ((r >> 2) & 1)) << 4)  (Swizzle<1,4,3>: address bit 7 XORed into bit 4); layout type 6, SBO = 256 B
+__device__ __forceinline__ uint32_t sw32_chunk(int row, int c) {
+    return (uint32_t)row * 32u + (uint32_t)((c ^ ((row >> 2) & 1)) << 4);
+}
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
 }
 
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -124,6 +131,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t *>(&t);
 }
 
+// relu on a packed bf16x2 word
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t x) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162 *>(&x);
+    v = __hmax2(v, __floats2bfloat162_rn(0.f, 0.f));
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1)
 gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restrict__ states, int64_t B,
                       float *__restrict__ pooled_out) {
@@ -132,7 +146,7 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
     const int gtid = threadIdx.x;
     const int grp = gtid / kGroupThreads, tid = gtid % kGroupThreads, lane = tid & 31, warp = tid >> 5;
 
-    for (int c = gtid; c < 2 * 128 * 16; c += kTcThreads) {  // both weight tiles, 16-byte chunks
+    for (int c = gtid; c < 2 * 128 * 16; c += kTcThreads) {  // both 128x128 weight tiles, 16-byte chunks
         const int which = c >> 11, cc = c & 2047;
         const int n = cc >> 4, j = cc & 15;
         const float *W = params + (which ? kOffW3 : kOffW2);
@@ -143,11 +157,22 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
         v.z = pack_bf16(hi.x, hi.y); v.w = pack_bf16(hi.z, hi.w);
         *reinterpret_cast<uint4 *>((which ? sm.w3 : sm.w2) + sw128_chunk(n, j)) = v;
     }
-    for (int i = gtid; i < kF * kH; i += kTcThreads) {
-        const int n = i / kF, f = i % kF;
-        sm.w1t[f * kH + n] = __ldg(params + kOffW1 + i);
+    // Layer-1 B operand, K = 16: columns [W1 (6) | W1 (6) | b1_hi | b1_lo | 0 | 0].  The A operand
+    // carries [hi(A_hat x0) (6) | lo(A_hat x0) (6) | 1 | 1 | 0 | 0], so the product is
+    // (hi + lo) . bf16(W1) + b1: the input keeps ~16 mantissa bits and the bias comes for free.
+    if (gtid < kH) {
+        const int n = gtid;
+        float w[kF];
+#pragma unroll
+        for (int f = 0; f < kF; ++f) w[f] = __ldg(params + kOffW1 + n * kF + f);
+        const float bias = __ldg(params + kOffB1 + n);
+        const float bias_hi = __bfloat162float(__float2bfloat16_rn(bias));
+        uint4 c0, c1;
+        c0.x = pack_bf16(w[0], w[1]); c0.y = pack_bf16(w[2], w[3]); c0.z = pack_bf16(w[4], w[5]); c0.w = pack_bf16(w[0], w[1]);
+        c1.x = pack_bf16(w[2], w[3]); c1.y = pack_bf16(w[4], w[5]); c1.z = pack_bf16(bias_hi, bias - bias_hi); c1.w = 0u;
+        *reinterpret_cast<uint4 *>(sm.w1 + sw32_chunk(n, 0)) = c0;
+        *reinterpret_cast<uint4 *>(sm.w1 + sw32_chunk(n, 1)) = c1;
     }
-    if (gtid < kH) sm.b1[gtid] = __ldg(params + kOffB1 + gtid);
     if (gtid < kGroups) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&sm.mbar[gtid])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -156,73 +181,105 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 
     TcGroupSmem &gs = sm.g[grp];
-    float *coef = reinterpret_cast<float *>(gs.a + kOffCoef);
+    float4 *rec = reinterpret_cast<float4 *>(gs.a + kOffRec);
     float *x0 = reinterpret_cast<float *>(gs.a + kOffX0);
-    float *ax0 = reinterpret_cast<float *>(gs.a + kOffAx0);
     uint8_t *open_s = gs.a + kOffOpen;
     float *red = reinterpret_cast<float *>(gs.a + kOffRed);
     const uint32_t tmem = sm.tmem_base + (uint32_t)grp * 128u;  // this group's accumulator columns
     const uint32_t bar = smem_u32(&sm.mbar[grp]);
-    const uint32_t a_addr = smem_u32(gs.a), w2_addr = smem_u32(sm.w2), w3_addr = smem_u32(sm.w3);
-    const float4 bias2 = __ldg(reinterpret_cast<const float4 *>(params + kOffB2) + lane);
-    const float4 bias3 = __ldg(reinterpret_cast<const float4 *>(params + kOffB3) + lane);
+    const uint32_t a_addr = smem_u32(gs.a), w1_addr = smem_u32(sm.w1), w2_addr = smem_u32(sm.w2), w3_addr = smem_u32(sm.w3);
+    // aggregation mapping: half-warp per node, lane owns float4 columns l16 and l16 + 16
+    const int sub = lane >> 4, l16 = lane & 15;
+    const float4 b2a = __ldg(reinterpret_cast<const float4 *>(params + kOffB2) + l16);
+    const float4 b2b = __ldg(reinterpret_cast<const float4 *>(params + kOffB2) + 16 + l16);
+    const float4 b3a = __ldg(reinterpret_cast<const float4 *>(params + kOffB3) + l16);
+    const float4 b3b = __ldg(reinterpret_cast<const float4 *>(params + kOffB3) + 16 + l16);
+    const int q = warp & 3, half = warp >> 2, erow = q * 32 + lane;  // epilogue: TMEM lane quadrant / column half / row
     uint32_t phase = 0;
 
     for (int64_t b = (int64_t)blockIdx.x * kGroups + grp; b < B; b += (int64_t)gridDim.x * kGroups) {
-        // ---- inputs ---------------------------------------------------------------------------
+        // ---- inputs: node features + open-direction masks ------------------------------------------
         {
             const AqState s = load_state(states + b);
             board_inputs_from_state(s, x0, open_s, tid);
         }
         group_sync(grp);
-        board_coefficients(open_s, coef, tid);
-        group_sync(grp);
-        for (int i = tid; i < kV * kF; i += kGroupThreads) {
-            const int v = i / kF, f = i % kF;
-            const float *c = coef + v * 5;
-            float s = c[0] * x0[i];
-            if (c[1] != 0.f) s = fmaf(c[1], x0[(v - 9) * kF + f], s);
-            if (c[2] != 0.f) s = fmaf(c[2], x0[(v + 9) * kF + f], s);
-            if (c[3] != 0.f) s = fmaf(c[3], x0[(v - 1) * kF + f], s);
-            if (c[4] != 0.f) s = fmaf(c[4], x0[(v + 1) * kF + f], s);
-            ax0[i] = s;
+        // ---- per-node record: A_hat coefficients and neighbour rows (a closed direction points at
+        //      the node itself with coefficient 0) ------------------------------------------------------
+        if (tid < kV) {
+            const int v = tid, m = open_s[v];
+            const float dv = dinv_of(m);
+            const int iu = (m & 1) ? v - 9 : v, id = (m & 2) ? v + 9 : v, il = (m & 4) ? v - 1 : v, ir = (m & 8) ? v + 1 : v;
+            const float cu = (m & 1) ? dv * dinv_of(open_s[iu]) : 0.f, cd = (m & 2) ? dv * dinv_of(open_s[id]) : 0.f;
+            const float cl = (m & 4) ? dv * dinv_of(open_s[il]) : 0.f, cr = (m & 8) ? dv * dinv_of(open_s[ir]) : 0.f;
+            rec[2 * v] = make_float4(dv * dv, cu, cd, cl);
+            rec[2 * v + 1] = make_float4(cr, __int_as_float(iu | (id << 8) | (il << 16) | (ir << 24)), 0.f, 0.f);
         }
         group_sync(grp);
-        // ---- layer 1 on the CUDA cores, written straight into the swizzled bf16 A tile: thread owns
-        //      the 8 output columns of chunk j for rows v0, v0+16, ... (weights reused from registers)
-        {
-            const int j = tid & 15, v0 = tid >> 4;
-            float w[kF][8], bb[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                bb[e] = sm.b1[j * 8 + e];
-#pragma unroll
-                for (int f = 0; f < kF; ++f) w[f][e] = sm.w1t[f * kH + j * 8 + e];
+        // ---- layer 1 A operand: row v = [hi(A_hat x0) | lo(A_hat x0) | 1 | 1 | 0 | 0] as bf16 ----------
+        for (int i = tid; i < kV * 8; i += kGroupThreads) {
+            const int v = i >> 3, f = i & 7;
+            unsigned short hi_bits, lo_bits;
+            if (f < kF) {
+                const float4 r0 = rec[2 * v], r1 = rec[2 * v + 1];
+                const int nb = __float_as_int(r1.y);
+                float s = r0.x * x0[v * kF + f];
+                s = fmaf(r0.y, x0[(nb & 0xFF) * kF + f], s);
+                s = fmaf(r0.z, x0[((nb >> 8) & 0xFF) * kF + f], s);
+                s = fmaf(r0.w, x0[((nb >> 16) & 0xFF) * kF + f], s);
+                s = fmaf(r1.x, x0[((nb >> 24) & 0xFF) * kF + f], s);
+                const __nv_bfloat16 h = __float2bfloat16_rn(s);
+                const __nv_bfloat16 l = __float2bfloat16_rn(s - __bfloat162float(h));
+                hi_bits = *reinterpret_cast<const unsigned short *>(&h);
+                lo_bits = *reinterpret_cast<const unsigned short *>(&l);
+                // columns f (chunk 0) and 6 + f (chunk 0 for f < 2, chunk 1 otherwise)
+                *reinterpret_cast<unsigned short *>(gs.a + sw128_chunk(v, 0) + f * 2) = hi_bits;
+                const int c = 6 + f;
+                *reinterpret_cast<unsigned short *>(gs.a + sw128_chunk(v, c >> 3) + (c & 7) * 2) = lo_bits;
+            } else if (f == 6) {  // columns 12..15 = 1, 1, 0, 0
+                *reinterpret_cast<uint2 *>(gs.a + sw128_chunk(v, 1) + 8) = make_uint2(0x3F803F80u, 0u);
             }
-            for (int v = v0; v < kV; v += 16) {
-                float a6[kF];
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        group_sync(grp);
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            mma_bf16(tmem, umma_desc(a_addr), umma_desc_sw32(w1_addr), kIdesc, 0u);  // one K = 16 step
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        // ---- layer 1 epilogue: ReLU, bf16, straight into the layer-2 A tile ------------------------------
+        if (q * 32 < kV) {
 #pragma unroll
-                for (int f = 0; f < kF; ++f) a6[f] = ax0[v * kF + f];
-                float o[8];
+            for (int cb = 0; cb < 2; ++cb) {
+                const int col0 = half * 64 + cb * 32;
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+                if (erow < kV) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    float s = bb[e];
-#pragma unroll
-                    for (int f = 0; f < kF; ++f) s = fmaf(a6[f], w[f][e], s);
-                    o[e] = fmaxf(s, 0.f);
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 pk;
+                        pk.x = relu_bf16x2(pack_bf16(v[8 * i + 0], v[8 * i + 1]));
+                        pk.y = relu_bf16x2(pack_bf16(v[8 * i + 2], v[8 * i + 3]));
+                        pk.z = relu_bf16x2(pack_bf16(v[8 * i + 4], v[8 * i + 5]));
+                        pk.w = relu_bf16x2(pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+                        *reinterpret_cast<uint4 *>(gs.a + sw128_chunk(erow, (col0 >> 3) + i)) = pk;
+                    }
                 }
-                uint4 pk;
-                pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]);
-                pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
-                *reinterpret_cast<uint4 *>(gs.a + sw128_chunk(v, j)) = pk;
             }
         }
-        float4 pool = make_float4(0.f, 0.f, 0.f, 0.f);
+        float pool[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pool[i] = 0.f;
 #pragma unroll 1
         for (int layer = 1; layer < kLayers; ++layer) {
             // make the generic-proxy writes of the A tile visible to the tensor core (async proxy)
@@ -237,66 +294,76 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
                     const uint32_t off = (uint32_t)(k >> 2) * kKBlockBytes + (uint32_t)(k & 3) * 32u;
                     mma_bf16(tmem, umma_desc(a_addr + off), umma_desc(w_addr + off), kIdesc, k > 0 ? 1u : 0u);
                 }
-                // arrives on the mbarrier once all MMAs above have completed
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
             }
             mbar_wait(bar, phase);
             phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             // ---- epilogue: TMEM -> registers -> fp32 Z (row = TMEM lane) ---------------------------
-            {
-                const int q = warp & 3, half = warp >> 2;
-                const int r = q * 32 + lane;
-                if (q * 32 < kV) {  // quadrant 3 (rows 96..127) holds no board rows
+            if (q * 32 < kV) {  // quadrant 3 (rows 96..127) holds no board rows
 #pragma unroll
-                    for (int cb = 0; cb < 2; ++cb) {
-                        const int col0 = half * 64 + cb * 32;
-                        float v[32];
-                        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
-                        if (r < kV) {
-                            float4 *dst = reinterpret_cast<float4 *>(gs.z + r * kZStride + col0);
+                for (int cb = 0; cb < 2; ++cb) {
+                    const int col0 = half * 64 + cb * 32;
+                    float v[32];
+                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+                    if (erow < kV) {
+                        float4 *dst = reinterpret_cast<float4 *>(gs.z + erow * kZStride + col0);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                        }
+                        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             group_sync(grp);
-            // ---- aggregation + bias + ReLU, warp per node; all five rows are loaded unconditionally
-            //      (closed directions re-read the node's own row with coefficient 0) for load-level ILP
+            // ---- aggregation + bias + ReLU: half-warp per node (two nodes per warp instruction), lane owns
+            //      float4 columns l16 and l16+16; all five rows are loaded unconditionally --------------------
             {
-                const float4 bb = layer == 1 ? bias2 : bias3;
-#pragma unroll 2
-                for (int v = warp; v < kV; v += kGroupThreads / 32) {
-                    const float *c = coef + v * 5;
-                    const float c0 = c[0], cu = c[1], cd = c[2], cl = c[3], cr = c[4];
-                    const float4 a0 = *reinterpret_cast<const float4 *>(gs.z + v * kZStride + lane * 4);
-                    const float4 au = *reinterpret_cast<const float4 *>(gs.z + (cu != 0.f ? v - 9 : v) * kZStride + lane * 4);
-                    const float4 ad = *reinterpret_cast<const float4 *>(gs.z + (cd != 0.f ? v + 9 : v) * kZStride + lane * 4);
-                    const float4 al = *reinterpret_cast<const float4 *>(gs.z + (cl != 0.f ? v - 1 : v) * kZStride + lane * 4);
-                    const float4 ar = *reinterpret_cast<const float4 *>(gs.z + (cr != 0.f ? v + 1 : v) * kZStride + lane * 4);
-                    float4 s;
-                    s.x = fmaf(cr, ar.x, fmaf(cl, al.x, fmaf(cd, ad.x, fmaf(cu, au.x, c0 * a0.x))));
-                    s.y = fmaf(cr, ar.y, fmaf(cl, al.y, fmaf(cd, ad.y, fmaf(cu, au.y, c0 * a0.y))));
-                    s.z = fmaf(cr, ar.z, fmaf(cl, al.z, fmaf(cd, ad.z, fmaf(cu, au.z, c0 * a0.z))));
-                    s.w = fmaf(cr, ar.w, fmaf(cl, al.w, fmaf(cd, ad.w, fmaf(cu, au.w, c0 * a0.w))));
-                    s.x = fmaxf(s.x + bb.x, 0.f); s.y = fmaxf(s.y + bb.y, 0.f);
-                    s.z = fmaxf(s.z + bb.z, 0.f); s.w = fmaxf(s.w + bb.w, 0.f);
-                    if (layer + 1 < kLayers) {
-                        // next layer's A tile: columns 4*lane..4*lane+3 = half of 16-byte chunk lane/2
-                        uint2 pk;
-                        pk.x = pack_bf16(s.x, s.y);
-                        pk.y = pack_bf16(s.z, s.w);
-                        *reinterpret_cast<uint2 *>(gs.a + sw128_chunk(v, lane >> 1) + (lane & 1) * 8) = pk;
+                const float4 ba = layer == 1 ? b2a : b3a, bb = layer == 1 ? b2b : b3b;
+                const bool last = layer + 1 == kLayers;
+                for (int v = 2 * warp + sub; v < kV; v += 2 * (kGroupThreads / 32)) {
+                    const float4 r0 = rec[2 * v], r1 = rec[2 * v + 1];
+                    const int nb = __float_as_int(r1.y);
+                    const float *z0 = gs.z + v * kZStride + l16 * 4;
+                    const float *zu = gs.z + (nb & 0xFF) * kZStride + l16 * 4;
+                    const float *zd = gs.z + ((nb >> 8) & 0xFF) * kZStride + l16 * 4;
+                    const float *zl = gs.z + ((nb >> 16) & 0xFF) * kZStride + l16 * 4;
+                    const float *zr = gs.z + ((nb >> 24) & 0xFF) * kZStride + l16 * 4;
+                    const float4 a0 = *reinterpret_cast<const float4 *>(z0), e0 = *reinterpret_cast<const float4 *>(z0 + 64);
+                    const float4 au = *reinterpret_cast<const float4 *>(zu), eu = *reinterpret_cast<const float4 *>(zu + 64);
+                    const float4 ad = *reinterpret_cast<const float4 *>(zd), ed = *reinterpret_cast<const float4 *>(zd + 64);
+                    const float4 al = *reinterpret_cast<const float4 *>(zl), el = *reinterpret_cast<const float4 *>(zl + 64);
+                    const float4 ar = *reinterpret_cast<const float4 *>(zr), er = *reinterpret_cast<const float4 *>(zr + 64);
+                    const float c0 = r0.x, cu = r0.y, cd = r0.z, cl = r0.w, cr = r1.x;
+                    float s[8];
+                    s[0] = fmaf(cr, ar.x, fmaf(cl, al.x, fmaf(cd, ad.x, fmaf(cu, au.x, fmaf(c0, a0.x, ba.x)))));
+                    s[1] = fmaf(cr, ar.y, fmaf(cl, al.y, fmaf(cd, ad.y, fmaf(cu, au.y, fmaf(c0, a0.y, ba.y)))));
+                    s[2] = fmaf(cr, ar.z, fmaf(cl, al.z, fmaf(cd, ad.z, fmaf(cu, au.z, fmaf(c0, a0.z, ba.z)))));
+                    s[3] = fmaf(cr, ar.w, fmaf(cl, al.w, fmaf(cd, ad.w, fmaf(cu, au.w, fmaf(c0, a0.w, ba.w)))));
+                    s[4] = fmaf(cr, er.x, fmaf(cl, el.x, fmaf(cd, ed.x, fmaf(cu, eu.x, fmaf(c0, e0.x, bb.x)))));
+                    s[5] = fmaf(cr, er.y, fmaf(cl, el.y, fmaf(cd, ed.y, fmaf(cu, eu.y, fmaf(c0, e0.y, bb.y)))));
+                    s[6] = fmaf(cr, er.z, fmaf(cl, el.z, fmaf(cd, ed.z, fmaf(cu, eu.z, fmaf(c0, e0.z, bb.z)))));
+                    s[7] = fmaf(cr, er.w, fmaf(cl, el.w, fmaf(cd, ed.w, fmaf(cu, eu.w, fmaf(c0, e0.w, bb.w)))));
+                    if (!last) {
+                        // next layer's A tile: columns 4*l16..+3 = half (l16 & 1) of chunk l16/2, and the same 64 columns on
+                        uint2 p0, p1;
+                        p0.x = relu_bf16x2(pack_bf16(s[0], s[1])); p0.y = relu_bf16x2(pack_bf16(s[2], s[3]));
+                        p1.x = relu_bf16x2(pack_bf16(s[4], s[5])); p1.y = relu_bf16x2(pack_bf16(s[6], s[7]));
+                        *reinterpret_cast<uint2 *>(gs.a + sw128_chunk(v, l16 >> 1) + (l16 & 1) * 8) = p0;
+                        *reinterpret_cast<uint2 *>(gs.a + sw128_chunk(v, 8 + (l16 >> 1)) + (l16 & 1) * 8) = p1;
                     } else {
-                        pool.x += s.x; pool.y += s.y; pool.z += s.z; pool.w += s.w;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) pool[i] += fmaxf(s[i], 0.f);
                     }
                 }
             }
         }
-        // ---- global_mean_pool -----------------------------------------------------------------------
-        reinterpret_cast<float4 *>(red + warp * kH)[lane] = pool;
+        // ---- global_mean_pool: combine the two half-warps, then the eight warps ---------------------------
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pool[i] += __shfl_xor_sync(0xffffffffu, pool[i], 16);
+        if (sub == 0) {
+            reinterpret_cast<float4 *>(red + warp * kH)[l16] = make_float4(pool[0], pool[1], pool[2], pool[3]);
+            reinterpret_cast<float4 *>(red + warp * kH)[16 + l16] = make_float4(pool[4], pool[5], pool[6], pool[7]);
+        }
         group_sync(grp);
         if (tid < kH) {
             float s = 0.f;
