@@ -280,6 +280,8 @@ static int set_smem(K kernel, size_t bytes) {
 }
 
 int aq_gcn_forward_tc(const float *params, const AqState *states, int64_t B, float *pooled, cudaStream_t st);  // gnn_tc.cu
+int aq_heads_forward_tc(const float *params, const float *pooled, int64_t B, float *policy, float *value,
+                        const uint32_t *legal_mask, cudaStream_t st);  // heads_tc.cu
 
 static int launch_trunk(const float *params, const AqState *states, const float *x, const uint8_t *open_mask, int64_t B,
                         float *pooled, float *saved, int precision, cudaStream_t st) {
@@ -300,7 +302,8 @@ static int launch_trunk(const float *params, const AqState *states, const float 
 }
 
 static int launch_heads(const float *params, const float *pooled, int64_t B, float *policy, float *value,
-                        const uint32_t *legal_mask, float *saved, cudaStream_t st) {
+                        const uint32_t *legal_mask, float *saved, int precision, cudaStream_t st) {
+    if (precision == 1 && !saved) return aq_heads_forward_tc(params, pooled, B, policy, value, legal_mask, st);
     const int64_t hb = (B + 7) / 8;
     const unsigned hgrid = (unsigned)(hb < num_sms() ? hb : num_sms());
     int rc;
@@ -325,10 +328,10 @@ extern "C" int aq_gcn_trunk_forward(const float *params, const AqState *states, 
 }
 
 extern "C" int aq_heads_forward(const float *params, const float *pooled, int64_t B, float *policy, float *value,
-                                const uint32_t *legal_mask, void *stream) {
+                                const uint32_t *legal_mask, int precision, void *stream) {
     if (B < 0 || !params || (B > 0 && (!pooled || !policy || !value))) return aq_set_error(AQ_ERR_ARG, "aq_heads_forward");
     if (B == 0) return 0;
-    return launch_heads(params, pooled, B, policy, value, legal_mask, nullptr, reinterpret_cast<cudaStream_t>(stream));
+    return launch_heads(params, pooled, B, policy, value, legal_mask, nullptr, precision, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // pooled [B,128] scratch must be provided by the caller when saved == NULL (inference); with a
@@ -342,7 +345,7 @@ int aq_gnn_forward_impl(const float *params, const AqState *states, const float 
     if (!pooled) return aq_set_error(AQ_ERR_ARG, "aq_gnn_forward(pooled scratch)");
     int rc = launch_trunk(params, states, x, open_mask, B, pooled, saved, precision, st);
     if (rc) return rc;
-    return launch_heads(params, pooled, B, policy, value, legal_mask, saved, st);
+    return launch_heads(params, pooled, B, policy, value, legal_mask, saved, precision, st);
 }
 
 extern "C" int64_t aq_param_count(void) { return kNumParams; }

@@ -239,7 +239,7 @@ def run_ours(args, rank, world, local_rank):
         _lib.check(L.aq_gcn_trunk_forward(P(flat), P(batches[i % nb]), B, P(pooled), prec, st), "aq_gcn_trunk_forward")
 
     def k_heads(i):
-        _lib.check(L.aq_heads_forward(P(flat), P(pooled), B, P(priors), P(value), P(mask), st), "aq_heads_forward")
+        _lib.check(L.aq_heads_forward(P(flat), P(pooled), B, P(priors), P(value), P(mask), prec, st), "aq_heads_forward")
 
     kms = {"legal_mask_kernel": timed(k_legal, K, 2), "gcn_forward_kernel": timed(k_trunk, K, 2),
            "heads_forward_kernel": timed(k_heads, K, 2)}

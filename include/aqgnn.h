@@ -112,7 +112,7 @@ int aq_gnn_forward(const float *params, const AqState *states, const float *x, c
 int aq_gcn_trunk_forward(const float *params, const AqState *states, int64_t B, float *pooled, int precision,
                          void *stream);
 int aq_heads_forward(const float *params, const float *pooled, int64_t B, float *policy, float *value,
-                     const uint32_t *legal_mask, void *stream);
+                     const uint32_t *legal_mask, int precision, void *stream);
 
 /* Backward of the above (autograd of train_network.py:93).  dpolicy [B,209], dvalue [B] are the
  * loss gradients w.r.t. the softmax / tanh outputs; grads f32[64082] is OVERWRITTEN with the
