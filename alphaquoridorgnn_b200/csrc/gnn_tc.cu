@@ -20,6 +20,7 @@
 //   * rows 81..95 of the X tile are never written: accumulator column n depends only on X row n, and
 //     columns >= 81 are never read (the stencil is unrolled, out-of-board neighbours do not exist in
 //     the code).
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include "gnn_fp32.cuh"
 
@@ -27,12 +28,7 @@ using namespace aq;
 
 namespace {
 
-#ifndef AQ_TC_GROUPS
-#define AQ_TC_GROUPS 4
-#endif
-constexpr int kGroups = AQ_TC_GROUPS;
 constexpr int kGroupThreads = 128;
-constexpr int kTcThreads = kGroups * kGroupThreads;
 constexpr int kNodesPad = 96;                              // MMA N: 81 nodes padded to a multiple of 16
 constexpr uint32_t kWKBlock = 128 * 128;                   // weight tile: 128 rows x 128 B per K-block
 constexpr uint32_t kXKBlock = kNodesPad * 128;             // node tile: 96 rows x 128 B per K-block
@@ -51,6 +47,7 @@ struct TcGroupSmem {
 };
 static_assert(sizeof(TcGroupSmem) % 1024 == 0, "group smem must keep 1024-byte alignment");
 
+template <int kGroups>
 struct TcSmem {
     unsigned char w2[2 * kWKBlock];
     unsigned char w3[2 * kWKBlock];
@@ -59,8 +56,8 @@ struct TcSmem {
     unsigned long long mbar[kGroups];
     uint32_t tmem_base;
 };
-static_assert(sizeof(TcSmem) + 1024 <= 227 * 1024, "TcSmem exceeds shared memory");
-static_assert(kGroups * kNodesPad <= (int)kTmemCols, "TMEM columns");
+static_assert(sizeof(TcSmem<5>) + 1024 <= 227 * 1024, "TcSmem exceeds shared memory");
+static_assert(5 * kNodesPad <= (int)kTmemCols, "TMEM columns");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -132,11 +129,13 @@ __device__ __forceinline__ unsigned short bf16_bits(float x) {
 // Accumulator column c of the current layer: columns 0..31 / 64..95 live in za (reloaded once), 32..63 in zb.
 #define AQ_Z(c) ((c) < 32 ? za[(c)] : ((c) < 64 ? zb[(c) - 32] : za[(c) - 64]))
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int kGroups>
+__global__ void __launch_bounds__(kGroups * kGroupThreads, 1)
 gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restrict__ states, int64_t B,
                       float *__restrict__ pooled_out) {
+    constexpr int kTcThreads = kGroups * kGroupThreads;
     extern __shared__ unsigned char smem_raw[];
-    TcSmem &sm = *reinterpret_cast<TcSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    TcSmem<kGroups> &sm = *reinterpret_cast<TcSmem<kGroups> *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int gtid = threadIdx.x;
     const int grp = gtid / kGroupThreads, tid = gtid % kGroupThreads;  // tid = feature = TMEM lane
 
@@ -314,19 +313,28 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
 
 }  // namespace
 
+template <int kGroups>
+static int launch_tc(const float *params, const AqState *states, int64_t B, float *pooled, int sms, cudaStream_t st) {
+    const size_t smem = sizeof(TcSmem<kGroups>) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(gcn_forward_tc_kernel<kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return aq_set_error((int)e, "gcn_forward_tc smem");
+    const int64_t want = (B + kGroups - 1) / kGroups;
+    const unsigned grid = (unsigned)(want < sms ? want : sms);
+    gcn_forward_tc_kernel<kGroups><<<grid, kGroups * kGroupThreads, smem, st>>>(params, states, B, pooled);
+    return aq_check_launch("gcn_forward_tc_kernel");
+}
+
 int aq_gcn_forward_tc(const float *params, const AqState *states, int64_t B, float *pooled, cudaStream_t st) {
-    static int sms = 0;
+    static int sms = 0, groups = 0;
     if (sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
+        const char *env = getenv("AQ_TC_GROUPS");  // tuning knob: boards in flight per SM (3, 4 or 5)
+        groups = env ? atoi(env) : 5;
     }
-    const size_t smem = sizeof(TcSmem) + 1024;
-    cudaError_t e = cudaFuncSetAttribute(gcn_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return aq_set_error((int)e, "gcn_forward_tc smem");
-    const int64_t want = (B + kGroups - 1) / kGroups;
-    const unsigned grid = (unsigned)(want < sms ? want : sms);
-    gcn_forward_tc_kernel<<<grid, kTcThreads, smem, st>>>(params, states, B, pooled);
-    return aq_check_launch("gcn_forward_tc_kernel");
+    if (groups == 3) return launch_tc<3>(params, states, B, pooled, sms, st);
+    if (groups == 4) return launch_tc<4>(params, states, B, pooled, sms, st);
+    return launch_tc<5>(params, states, B, pooled, sms, st);
 }
