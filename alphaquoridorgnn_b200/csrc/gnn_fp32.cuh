@@ -109,13 +109,25 @@ __device__ __forceinline__ void aggregate(const float *__restrict__ in, float *_
     }
 }
 
+// Open-direction mask of one square straight from the wall bitboards (is_wall_blocking,
+// game_logic.py:145-167): an H wall in slot (x,y) blocks the vertical moves between rows x,x+1 in
+// columns y,y+1; a V wall blocks the horizontal moves between columns y,y+1 in rows x,x+1.
+__device__ __forceinline__ int node_open_mask(u64 h, u64 vw, int r, int c) {
+    // pair of wall slots whose wall touches column c (slots c-1 and c) / row r (slots r-1 and r)
+    const u64 colpair = (c < 8 ? 1ull << c : 0ull) | (c > 0 ? 1ull << (c - 1) : 0ull);
+    const u64 rowpair = (r < 8 ? 1ull << (8 * r) : 0ull) | (r > 0 ? 1ull << (8 * (r - 1)) : 0ull);
+    const bool up = r > 0 && ((h >> (8 * (r - 1))) & colpair) == 0;
+    const bool down = r < 8 && ((h >> (8 * r)) & colpair & 0xFFull) == 0;
+    const bool left = c > 0 && ((vw >> (c - 1)) & rowpair) == 0;
+    const bool right = c < 8 && ((vw >> c) & rowpair) == 0;
+    return (int)up | ((int)down << 1) | ((int)left << 2) | ((int)right << 3);
+}
+
 // Node features of one board into x0[81][6] and open masks into open_s[81], from a packed state.
 __device__ __forceinline__ void board_inputs_from_state(const AqState &s, float *x0, uint8_t *open_s, int tid) {
     if (tid < kV) {
-        const Open o = open_from_walls(s.hwalls, s.vwalls);
         const int v = tid;
-        open_s[v] = (uint8_t)((int)has(o.up, v) | ((int)has(o.down, v) << 1) | ((int)has(o.left, v) << 2) |
-                              ((int)has(o.right, v) << 3));
+        open_s[v] = (uint8_t)node_open_mask(s.hwalls, s.vwalls, v / 9, v % 9);
         // the six planes of pieces_array (game_logic.py:56-93); wall planes sit on the slot's top-left tile
         const int r = v / 9, c = v % 9;
         const bool slot_ok = r < 8 && c < 8;

@@ -96,9 +96,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!ok) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");  // suspend-time hint (ns): sleep, do not spin
     }
 }
 // 32 accumulator columns of this thread's TMEM lane
@@ -120,6 +120,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&t);
+}
+// relu(x) -> bf16 -> 16-bit shared store (cvt.rn.relu folds the ReLU into the conversion)
+__device__ __forceinline__ void st_relu_bf16(uint32_t saddr, float x) {
+    asm volatile("{\n\t.reg .b16 t;\n\tcvt.rn.relu.bf16.f32 t, %1;\n\tst.shared.b16 [%0], t;\n\t}\n" ::"r"(saddr), "f"(x) : "memory");
 }
 __device__ __forceinline__ unsigned short bf16_bits(float x) {
     const __nv_bfloat16 h = __float2bfloat16_rn(x);
@@ -183,11 +187,11 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
     const uint32_t x_addr = smem_u32(gs.x), w1_addr = smem_u32(sm.w1), w2_addr = smem_u32(sm.w2), w3_addr = smem_u32(sm.w3);
     const float bias2 = __ldg(params + kOffB2 + tid), bias3 = __ldg(params + kOffB3 + tid);
     // store addresses of this thread's feature column inside the node tile, one per (row & 7) swizzle phase
-    unsigned char *xs[8];
+    uint32_t xs[8];
     {
         const int j = tid >> 3;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) xs[t] = gs.x + (uint32_t)(j >> 3) * kXKBlock + (uint32_t)(((j & 7) ^ t) << 4) + (tid & 7) * 2;
+        for (int t = 0; t < 8; ++t) xs[t] = x_addr + (uint32_t)(j >> 3) * kXKBlock + (uint32_t)(((j & 7) ^ t) << 4) + (tid & 7) * 2;
     }
     uint32_t phase = 0;
 
@@ -249,7 +253,7 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const int v = cb * 32 + i;
-                    if (v < kV) *reinterpret_cast<unsigned short *>(xs[v & 7] + v * 128) = bf16_bits(fmaxf(za[i], 0.f));
+                    if (v < kV) st_relu_bf16(xs[v & 7] + v * 128, za[i]);
                 }
             }
         }
@@ -276,9 +280,7 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             // ---- aggregation + bias + ReLU, thread-local: this thread holds feature `tid` of all 81 nodes.
             //      The stencil is fully unrolled; neighbours that fall off the board are absent from the code.
-            {
-                const float bias = layer == 1 ? bias2 : bias3;
-                const bool last = layer + 1 == kLayers;
+            if (layer + 1 < kLayers) {
                 float za[32], zb[32];
                 tmem_ld32(tmem_me, za);
                 tmem_ld32(tmem_me + 32, zb);
@@ -287,14 +289,28 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
                     if (v == 41) tmem_ld32(tmem_me + 64, za);  // columns 0..31 are dead after node 40
                     const float4 r0 = gs.rec[2 * v];
                     const float cr = gs.rec[2 * v + 1].x;
-                    float s = fmaf(r0.x, AQ_Z(v), bias);
+                    float s = fmaf(r0.x, AQ_Z(v), bias2);
                     if (v >= 9) s = fmaf(r0.y, AQ_Z(v - 9), s);
                     if (v < kV - 9) s = fmaf(r0.z, AQ_Z(v + 9), s);
                     if (v % 9 != 0) s = fmaf(r0.w, AQ_Z(v - 1), s);
                     if (v % 9 != 8) s = fmaf(cr, AQ_Z(v + 1), s);
-                    s = fmaxf(s, 0.f);
-                    if (!last) *reinterpret_cast<unsigned short *>(xs[v & 7] + v * 128) = bf16_bits(s);
-                    else pool += s;
+                    st_relu_bf16(xs[v & 7] + v * 128, s);  // next layer's node operand
+                }
+            } else {
+                float za[32], zb[32];
+                tmem_ld32(tmem_me, za);
+                tmem_ld32(tmem_me + 32, zb);
+#pragma unroll
+                for (int v = 0; v < kV; ++v) {
+                    if (v == 41) tmem_ld32(tmem_me + 64, za);
+                    const float4 r0 = gs.rec[2 * v];
+                    const float cr = gs.rec[2 * v + 1].x;
+                    float s = fmaf(r0.x, AQ_Z(v), bias3);
+                    if (v >= 9) s = fmaf(r0.y, AQ_Z(v - 9), s);
+                    if (v < kV - 9) s = fmaf(r0.z, AQ_Z(v + 9), s);
+                    if (v % 9 != 0) s = fmaf(r0.w, AQ_Z(v - 1), s);
+                    if (v % 9 != 8) s = fmaf(cr, AQ_Z(v + 1), s);
+                    pool += fmaxf(s, 0.f);  // last layer feeds only the mean pool
                 }
             }
         }
