@@ -125,6 +125,88 @@ AQ_DEV bool reaches(const Open &o, int start, int ob, u128 goal) {
     }
 }
 
+// ---- path witness --------------------------------------------------------------------------------
+// One concrete path start -> goal (with the pawn rules) found by the same flood fill, returned as the
+// set of wall slots whose H / V wall would sever one of the unit edges the path uses.  A candidate
+// wall outside these sets leaves the path intact, so the goal stays reachable and no search is needed:
+// walls only ADD blocks, every "edge open" condition the path relies on stays true unless that edge is
+// severed, and every "straight jump blocked" condition stays true.  (The converse is not used: a
+// candidate that cuts the witness gets a real search.  If no path exists without the candidate, all
+// candidates are searched -- a wall behind the other pawn can create diagonal jumps.)
+struct PathCuts {
+    u64 cutH, cutV;
+    int exists;
+};
+
+AQ_DEV int lowest_bit(u128 b) {
+    const u64 lo = (u64)b, hi = (u64)(b >> 64);
+#ifdef __CUDA_ARCH__
+    return lo ? __ffsll((long long)lo) - 1 : 64 + __ffsll((long long)hi) - 1;
+#else
+    return lo ? __builtin_ctzll(lo) : 64 + __builtin_ctzll(hi);
+#endif
+}
+
+// unit edge between adjacent squares a and b -> slots whose wall severs it
+AQ_DEV void add_edge_cut(PathCuts &pc, int a, int b) {
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    const int r = lo / 9, c = lo % 9;
+    if (hi - lo == 9) {  // vertical edge (r,c)-(r+1,c): H walls in slots (r,c) and (r,c-1)
+        if (c < 8) pc.cutH |= 1ull << (8 * r + c);
+        if (c > 0) pc.cutH |= 1ull << (8 * r + c - 1);
+    } else {             // horizontal edge (r,c)-(r,c+1): V walls in slots (r,c) and (r-1,c)
+        if (r < 8) pc.cutV |= 1ull << (8 * r + c);
+        if (r > 0) pc.cutV |= 1ull << (8 * (r - 1) + c);
+    }
+}
+
+AQ_DEV PathCuts find_path_cuts(const Open &o, int start, int ob, u128 goal) {
+    const u128 srcU = has(o.down, ob) ? bit81(ob + 9) : (u128)0;
+    const u128 srcD = has(o.up, ob) ? bit81(ob - 9) : (u128)0;
+    const u128 srcL = has(o.right, ob) ? bit81(ob + 1) : (u128)0;
+    const u128 srcR = has(o.left, ob) ? bit81(ob - 1) : (u128)0;
+    const u128 jU = jump_targets(o, ob, 0), jD = jump_targets(o, ob, 1);
+    const u128 jL = jump_targets(o, ob, 2), jR = jump_targets(o, ob, 3);
+    const u128 notob = ~bit81(ob);
+    u128 reach = bit81(start);
+    // squares first reached by a plain move in direction U/D/L/R, or by a jump approached in that direction
+    u128 byU = 0, byD = 0, byL = 0, byR = 0, jbU = 0, jbD = 0, jbL = 0, jbR = 0;
+    PathCuts pc;
+    pc.cutH = 0; pc.cutV = 0; pc.exists = 0;
+    while (!(reach & goal)) {
+        u128 acc = reach, n;
+        n = ((reach & o.up) >> 9) & notob & ~acc;    byU |= n; acc |= n;
+        n = ((reach & o.down) << 9) & notob & ~acc;  byD |= n; acc |= n;
+        n = ((reach & o.left) >> 1) & notob & ~acc;  byL |= n; acc |= n;
+        n = ((reach & o.right) << 1) & notob & ~acc; byR |= n; acc |= n;
+        if (reach & srcU) { n = jU & ~acc; jbU |= n; acc |= n; }
+        if (reach & srcD) { n = jD & ~acc; jbD |= n; acc |= n; }
+        if (reach & srcL) { n = jL & ~acc; jbL |= n; acc |= n; }
+        if (reach & srcR) { n = jR & ~acc; jbR |= n; acc |= n; }
+        if (acc == reach) return pc;  // goal unreachable even without a candidate
+        reach = acc;
+    }
+    pc.exists = 1;
+    int cur = lowest_bit(reach & goal);
+    while (cur != start) {
+        int prev;
+        if (has(byU, cur)) prev = cur + 9;
+        else if (has(byD, cur)) prev = cur - 9;
+        else if (has(byL, cur)) prev = cur + 1;
+        else if (has(byR, cur)) prev = cur - 1;
+        else {  // jump over the pawn on ob: two unit edges, src-ob and ob-cur
+            prev = has(jbU, cur) ? ob + 9 : has(jbD, cur) ? ob - 9 : has(jbL, cur) ? ob + 1 : ob - 1;
+            add_edge_cut(pc, prev, ob);
+            add_edge_cut(pc, ob, cur);
+            cur = prev;
+            continue;
+        }
+        add_edge_cut(pc, prev, cur);
+        cur = prev;
+    }
+    return pc;
+}
+
 // legal_actions_pos (game_logic.py:120-192) from square p with the enemy pawn on e (mover's
 // frame); writes up to 5 squares in the reference order, returns the count.
 AQ_DEV int pawn_moves(const Open &o, int p, int e, uint8_t *out) {

@@ -76,20 +76,28 @@ __global__ void unpack_states_kernel(const AqState *__restrict__ states, int64_t
 }
 
 // ------------------------------------------------------------------------------------------
-// K1 legal_mask: one warp per state.
-//   all lanes: open-direction bitboards, can_place + gate for all 128 candidates (bit-parallel)
-//   candidates whose gate fires are compacted into a per-warp list and dealt round-robin to the
-//   lanes; each lane runs the two flood fills for its candidates in registers.
+// K1 legal_mask: eight lanes per state (four states per warp).
+//   every lane: open-direction bitboards, can_place + gate for all 128 candidates (bit-parallel);
+//   sub-lanes 0/1: one witness path for the mover / the opponent on the board WITHOUT a candidate,
+//   as the sets of slots that would cut it (find_path_cuts);
+//   a gated candidate needs a real search only for the player whose witness it cuts: those
+//   (candidate, player) tasks are compacted into a per-state list and dealt round-robin to the
+//   state's eight lanes; each lane runs its flood fills in registers.
 // ------------------------------------------------------------------------------------------
 constexpr int kLegalWarps = 4;
+constexpr int kLanesPerState = 8;
+constexpr int kStatesPerWarp = 32 / kLanesPerState;
 
 __global__ void __launch_bounds__(kLegalWarps * 32)
 legal_mask_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__restrict__ mask,
                   uint8_t *__restrict__ pawn) {
-    __shared__ uint8_t cand[kLegalWarps][128];
+    __shared__ uint8_t task[kLegalWarps * kStatesPerWarp][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t b = (int64_t)blockIdx.x * kLegalWarps + warp;
-    if (b >= B) return;
+    const int sub = lane & (kLanesPerState - 1), grp = lane / kLanesPerState;
+    const unsigned gmask = ((1u << kLanesPerState) - 1u) << (grp * kLanesPerState);
+    const int64_t b = ((int64_t)blockIdx.x * kLegalWarps + warp) * kStatesPerWarp + grp;
+    if (b >= B) return;  // whole 8-lane group leaves together
+    uint8_t *tl = task[warp * kStatesPerWarp + grp];
     const AqState s = load_state(states + b);
     const Open base = open_from_walls(s.hwalls, s.vwalls);
     const int me = s.ppos, en = 80 - (int)s.epos;  // enemy square in the mover's frame, game_logic.py:136
@@ -99,35 +107,53 @@ legal_mask_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__res
         const WallSets ws = wall_sets(s.hwalls, s.vwalls);
         legalH = ws.freeH;
         legalV = ws.freeV;
-        // compact the candidates that need the search; order is irrelevant
-        const int nH = __popcll(ws.needH), total = nH + __popcll(ws.needV);
+        if (ws.needH | ws.needV) {
+            // witness paths: mover (start me, obstacle en, goal row 0) on sub-lane 0, opponent in the
+            // un-rotated frame (start en, obstacle me, goal row 8) on sub-lane 1  (game_logic.py:332-348)
+            PathCuts pc;
+            pc.cutH = 0; pc.cutV = 0; pc.exists = 0;
+            if (sub < 2) pc = find_path_cuts(base, sub == 0 ? me : en, sub == 0 ? en : me, sub == 0 ? kRow0 : kRow8);
+            __syncwarp(gmask);
+            u64 set[4];  // tasks: [mover H, mover V, opponent H, opponent V]
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int slot = lane + 32 * k;
-            if ((ws.needH >> slot) & 1) cand[warp][__popcll(ws.needH & ((1ull << slot) - 1))] = (uint8_t)slot;
-            if ((ws.needV >> slot) & 1) cand[warp][nH + __popcll(ws.needV & ((1ull << slot) - 1))] = (uint8_t)(64 | slot);
-        }
-        __syncwarp();
-        u64 okH = 0, okV = 0;
-        for (int j = lane; j < total; j += 32) {
-            const int code = cand[warp][j];
-            const int slot = code & 63, orient = (code >> 6) + 1;
-            Open o = base;
-            add_wall(o, orient, slot);
-            // mover: start me, obstacle en, goal row 0; opponent (un-rotated frame): start en,
-            // obstacle me, goal row 8  (game_logic.py:332-348)
-            const bool ok = reaches(o, me, en, kRow0) && reaches(o, en, me, kRow8);
-            if (ok) {
-                if (orient == 1) okH |= 1ull << slot; else okV |= 1ull << slot;
+            for (int p = 0; p < 2; ++p) {
+                const int ex = __shfl_sync(gmask, pc.exists, p, kLanesPerState);
+                const u64 ch = ((u64)__shfl_sync(gmask, (unsigned)(pc.cutH >> 32), p, kLanesPerState) << 32) |
+                               __shfl_sync(gmask, (unsigned)pc.cutH, p, kLanesPerState);
+                const u64 cv = ((u64)__shfl_sync(gmask, (unsigned)(pc.cutV >> 32), p, kLanesPerState) << 32) |
+                               __shfl_sync(gmask, (unsigned)pc.cutV, p, kLanesPerState);
+                set[2 * p + 0] = ws.needH & (ex ? ch : ~0ull);
+                set[2 * p + 1] = ws.needV & (ex ? cv : ~0ull);
             }
+            int offs[5];
+            offs[0] = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) offs[q + 1] = offs[q] + __popcll(set[q]);
+            const int total = offs[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                for (int slot = sub; slot < 64; slot += kLanesPerState)
+                    if ((set[q] >> slot) & 1) tl[offs[q] + __popcll(set[q] & ((1ull << slot) - 1))] = (uint8_t)(slot | (q << 6));
+            __syncwarp(gmask);
+            u64 failH = 0, failV = 0;
+            for (int j = sub; j < total; j += kLanesPerState) {
+                const int code = tl[j];
+                const int slot = code & 63, orient = ((code >> 6) & 1) + 1, opp = code >> 7;
+                Open o = base;
+                add_wall(o, orient, slot);
+                const bool ok = opp ? reaches(o, en, me, kRow8) : reaches(o, me, en, kRow0);
+                if (!ok) {
+                    if (orient == 1) failH |= 1ull << slot; else failV |= 1ull << slot;
+                }
+            }
+            __syncwarp(gmask);
+            const unsigned a0 = __reduce_or_sync(gmask, (unsigned)failH), a1 = __reduce_or_sync(gmask, (unsigned)(failH >> 32));
+            const unsigned c0 = __reduce_or_sync(gmask, (unsigned)failV), c1 = __reduce_or_sync(gmask, (unsigned)(failV >> 32));
+            legalH |= ws.needH & ~(((u64)a1 << 32) | a0);
+            legalV |= ws.needV & ~(((u64)c1 << 32) | c0);
         }
-        // OR-reduce the per-lane results
-        unsigned a0 = __reduce_or_sync(0xffffffffu, (unsigned)okH), a1 = __reduce_or_sync(0xffffffffu, (unsigned)(okH >> 32));
-        unsigned c0 = __reduce_or_sync(0xffffffffu, (unsigned)okV), c1 = __reduce_or_sync(0xffffffffu, (unsigned)(okV >> 32));
-        legalH |= ((u64)a1 << 32) | a0;
-        legalV |= ((u64)c1 << 32) | c0;
     }
-    if (lane == 0) {
+    if (sub == 0) {
         uint8_t pm[8] = {0, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0, 0};
         const int n = pawn_moves(base, me, en, pm + 1);
         pm[0] = (uint8_t)n;
@@ -297,7 +323,7 @@ extern "C" int aq_unpack_states(const AqState *states, int64_t B, uint8_t *rows6
 extern "C" int aq_legal_mask(const AqState *states, int64_t B, uint32_t *mask, uint8_t *pawn, void *stream) {
     if (B < 0 || (B > 0 && (!states || !mask || !pawn))) return aq_set_error(AQ_ERR_ARG, "aq_legal_mask");
     if (B == 0) return 0;
-    legal_mask_kernel<<<blocks_for(B, kLegalWarps), kLegalWarps * 32, 0, S(stream)>>>(states, B, mask, pawn);
+    legal_mask_kernel<<<blocks_for(B, kLegalWarps * kStatesPerWarp), kLegalWarps * 32, 0, S(stream)>>>(states, B, mask, pawn);
     return aq_check_launch("aq_legal_mask");
 }
 

@@ -30,13 +30,21 @@ extern "C" void emul_legal_mask(const AqState *states, long long B, uint32_t *ma
             const WallSets ws = wall_sets(s.hwalls, s.vwalls);
             legalH = ws.freeH;
             legalV = ws.freeV;
+            // same decision structure as legal_mask_kernel: witness paths first, a real search only for the
+            // player whose witness the candidate cuts
+            const PathCuts pm_ = find_path_cuts(base, me, en, kRow0);
+            const PathCuts pe_ = find_path_cuts(base, en, me, kRow8);
             for (int slot = 0; slot < 64; ++slot)
                 for (int orient = 1; orient <= 2; ++orient) {
                     const u64 need = orient == 1 ? ws.needH : ws.needV;
                     if (!((need >> slot) & 1)) continue;
+                    const u64 cm = orient == 1 ? pm_.cutH : pm_.cutV, ce = orient == 1 ? pe_.cutH : pe_.cutV;
                     Open o = base;
                     add_wall(o, orient, slot);
-                    if (reaches(o, me, en, kRow0) && reaches(o, en, me, kRow8)) {
+                    bool ok = true;
+                    if (!pm_.exists || ((cm >> slot) & 1)) ok = ok && reaches(o, me, en, kRow0);
+                    if (!pe_.exists || ((ce >> slot) & 1)) ok = ok && reaches(o, en, me, kRow8);
+                    if (ok) {
                         if (orient == 1) legalH |= 1ull << slot; else legalV |= 1ull << slot;
                     }
                 }
