@@ -85,7 +85,7 @@ __global__ void unpack_states_kernel(const AqState *__restrict__ states, int64_t
 //   state's eight lanes; each lane runs its flood fills in registers.
 // ------------------------------------------------------------------------------------------
 constexpr int kLegalWarps = 4;
-constexpr int kLanesPerState = 8;
+constexpr int kLanesPerState = 2;
 constexpr int kStatesPerWarp = 32 / kLanesPerState;
 
 __global__ void __launch_bounds__(kLegalWarps * 32)
