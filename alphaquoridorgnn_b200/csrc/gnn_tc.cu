@@ -40,10 +40,10 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNo
 
 struct TcGroupSmem {
     unsigned char x[2 * kXKBlock];   // 24 KB, 1024-byte aligned (SWIZZLE_128B atoms are 8 rows x 128 B)
-    float4 rec[2 * kV];              // per node {c0,cu,cd,cl | cr,-,-,-}: A_hat coefficients (0 = closed)
+    float4 rec[kV + 3];              // per node {c0,cu,cd,cl}: A_hat coefficients (0 = closed); c_right(v) = c_left(v+1)
     float x0[kV * kF + 2];
     uint8_t open_s[96];
-    unsigned char pad[1024 - (2 * kV * 16 + (kV * kF + 2) * 4 + 96) % 1024];
+    unsigned char pad[1024 - ((kV + 3) * 16 + (kV * kF + 2) * 4 + 96) % 1024];
 };
 static_assert(sizeof(TcGroupSmem) % 1024 == 0, "group smem must keep 1024-byte alignment");
 
@@ -211,8 +211,7 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
             const float c0 = dv * dv;
             const float cu = (m & 1) ? dv * dinv_of(gs.open_s[iu]) : 0.f, cd = (m & 2) ? dv * dinv_of(gs.open_s[id]) : 0.f;
             const float cl = (m & 4) ? dv * dinv_of(gs.open_s[il]) : 0.f, cr = (m & 8) ? dv * dinv_of(gs.open_s[ir]) : 0.f;
-            gs.rec[2 * v] = make_float4(c0, cu, cd, cl);
-            gs.rec[2 * v + 1] = make_float4(cr, 0.f, 0.f, 0.f);
+            gs.rec[v] = make_float4(c0, cu, cd, cl);
             unsigned short hi[kF], lo[kF];
 #pragma unroll
             for (int f = 0; f < kF; ++f) {
@@ -284,11 +283,13 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
                 float za[32], zb[32];
                 tmem_ld32(tmem_me, za);
                 tmem_ld32(tmem_me + 32, zb);
+                float4 rn = gs.rec[0];
 #pragma unroll
                 for (int v = 0; v < kV; ++v) {
                     if (v == 41) tmem_ld32(tmem_me + 64, za);  // columns 0..31 are dead after node 40
-                    const float4 r0 = gs.rec[2 * v];
-                    const float cr = gs.rec[2 * v + 1].x;
+                    const float4 r0 = rn;
+                    if (v + 1 < kV) rn = gs.rec[v + 1];
+                    const float cr = rn.w;  // c_right(v) = c_left(v + 1): A_hat is symmetric
                     float s = fmaf(r0.x, AQ_Z(v), bias2);
                     if (v >= 9) s = fmaf(r0.y, AQ_Z(v - 9), s);
                     if (v < kV - 9) s = fmaf(r0.z, AQ_Z(v + 9), s);
@@ -300,11 +301,13 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
                 float za[32], zb[32];
                 tmem_ld32(tmem_me, za);
                 tmem_ld32(tmem_me + 32, zb);
+                float4 rn = gs.rec[0];
 #pragma unroll
                 for (int v = 0; v < kV; ++v) {
                     if (v == 41) tmem_ld32(tmem_me + 64, za);
-                    const float4 r0 = gs.rec[2 * v];
-                    const float cr = gs.rec[2 * v + 1].x;
+                    const float4 r0 = rn;
+                    if (v + 1 < kV) rn = gs.rec[v + 1];
+                    const float cr = rn.w;  // c_right(v) = c_left(v + 1): A_hat is symmetric
                     float s = fmaf(r0.x, AQ_Z(v), bias3);
                     if (v >= 9) s = fmaf(r0.y, AQ_Z(v - 9), s);
                     if (v < kV - 9) s = fmaf(r0.z, AQ_Z(v + 9), s);

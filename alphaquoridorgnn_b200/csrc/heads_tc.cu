@@ -1,7 +1,7 @@
 // Policy / value heads on the tensor cores (bf16 operands, fp32 accumulate in TMEM) -- the
 // inference path that follows gcn_forward_tc_kernel.  pv_network_gnn.py:38-51,62-63:
 //   policy = Softmax(Linear(64->209)(ReLU(Linear(128->64)(g))));  value = Tanh(Linear(64->1)(ReLU(Linear(128->64)(g))))
-// One CTA of 128 threads per tile of 128 boards (thread = board = TMEM lane):
+// One CTA of 256 threads per tile of 128 boards (thread pair = board = TMEM lane, one thread per column half):
 //   GEMM 1  [128 boards x 128] x [Wp0 ; Wv0]^T  -> 64 policy-hidden + 64 value-hidden columns
 //   epilogue 1: bias + ReLU; policy hidden -> bf16 A tile of GEMM 2; value head finished in fp32
 //   GEMM 2  [128 boards x 64] x Wp2^T (209 rows padded to 224) -> logits in TMEM
@@ -15,7 +15,7 @@ using namespace aq;
 
 namespace {
 
-constexpr int kHtThreads = 128;
+constexpr int kHtThreads = 256;                // two threads per board row (column halves)
 constexpr int kTile = 128;                   // boards per CTA
 constexpr int kNPad = 224;                   // 209 logits padded to a multiple of 16
 constexpr uint32_t kKBlock = 128 * 128;      // one 128-row K-block of 64 bf16
@@ -28,6 +28,7 @@ struct HtSmem {
     float bp0[kHH], bv0[kHH], wv2[kHH];
     float bp2[kNPad];
     float bv2;
+    float xch[3][2][kTile];                  // row-wise exchange between the two column halves
     unsigned long long mbar;
     uint32_t tmem_base;
 };
@@ -91,22 +92,34 @@ heads_forward_tc_kernel(const float *__restrict__ params, const float *__restric
     extern __shared__ unsigned char smem_raw[];
     HtSmem &sm = *reinterpret_cast<HtSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (kTile - 1), hf = tid >> 7;  // board of this thread inside the tile / column half it handles
     const int64_t b0 = (int64_t)blockIdx.x * kTile;
 
     // ---- operands -> bf16 swizzled tiles ---------------------------------------------------------
     for (int c = tid; c < 128 * 16; c += kHtThreads) {  // B1 rows 0..63 = Wp0, 64..127 = Wv0 (each [64][128])
         const int n = c >> 4, j = c & 15;
-        const float *W = params + (n < kHH ? kOffWP0 + n * kH : kOffWV0 + (n - kHH) * kH) + j * 8;
         float f[8];
+        if (n < kHH) {
+            const float4 lo = __ldg(reinterpret_cast<const float4 *>(params + kOffWP0 + n * kH + j * 8));
+            const float4 hi = __ldg(reinterpret_cast<const float4 *>(params + kOffWP0 + n * kH + j * 8) + 1);
+            f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+        } else {  // kOffWV0 is not 16-byte aligned: scalar loads
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = __ldg(W + e);  // kOffWV0 is not 16-byte aligned: scalar loads
+            for (int e = 0; e < 8; ++e) f[e] = __ldg(params + kOffWV0 + (n - kHH) * kH + j * 8 + e);
+        }
         *reinterpret_cast<uint4 *>(sm.b1 + sw128(n, j)) = pack8(f);
     }
     for (int c = tid; c < kNPad * 8; c += kHtThreads) {  // B2 = Wp2 [209][64], rows >= 209 are zero
         const int n = c >> 3, j = c & 7;
         float f[8];
+        if (n < kP) {
+            const float4 lo = __ldg(reinterpret_cast<const float4 *>(params + kOffWP2 + n * kHH + j * 8));
+            const float4 hi = __ldg(reinterpret_cast<const float4 *>(params + kOffWP2 + n * kHH + j * 8) + 1);
+            f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+        } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = n < kP ? __ldg(params + kOffWP2 + n * kHH + j * 8 + e) : 0.f;
+            for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        }
         *reinterpret_cast<uint4 *>(sm.b2 + sw128(n, j)) = pack8(f);
     }
     for (int c = tid; c < kTile * 16; c += kHtThreads) {  // A1 = pooled rows of this tile (zeros past B)
@@ -144,8 +157,7 @@ heads_forward_tc_kernel(const float *__restrict__ params, const float *__restric
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = sm.tmem_base;
     const uint32_t a_addr = smem_u32(sm.a), b1_addr = smem_u32(sm.b1), b2_addr = smem_u32(sm.b2);
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's TMEM lane quadrant
-    const int row = tid;                                               // board of this thread inside the tile
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's TMEM lane quadrant
     const bool valid = b0 + row < B;
 
     // ---- GEMM 1: hidden layers of both heads -------------------------------------------------------
@@ -160,28 +172,29 @@ heads_forward_tc_kernel(const float *__restrict__ params, const float *__restric
     }
     wait(bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    // ---- epilogue 1 ------------------------------------------------------------------------------------
-    float val;
+    // ---- epilogue 1: half 0 = policy hidden -> bf16 A2; half 1 = value head in fp32 ------------------------
     {
         float v[32];
+        if (hf == 0) {
 #pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {  // policy hidden: bias + ReLU -> bf16 A2 (K-block 0 of the A region)
-            ld32(lane_base + cb * 32, v);
+            for (int cb = 0; cb < 2; ++cb) {  // bias + ReLU -> bf16 A2 (K-block 0 of the A region; GEMM 1 is done with it)
+                ld32(lane_base + cb * 32, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + sm.bp0[cb * 32 + i], 0.f);
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + sm.bp0[cb * 32 + i], 0.f);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4 *>(sm.a + sw128(row, cb * 4 + i)) = pack8(v + 8 * i);
+                for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4 *>(sm.a + sw128(row, cb * 4 + i)) = pack8(v + 8 * i);
+            }
+        } else {
+            float u = sm.bv2;
+#pragma unroll
+            for (int cb = 0; cb < 2; ++cb) {  // Linear(64 -> 1) on relu(hidden) in fp32, then tanh
+                ld32(lane_base + 64 + cb * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) u = fmaf(fmaxf(v[i] + sm.bv0[cb * 32 + i], 0.f), sm.wv2[cb * 32 + i], u);
+            }
+            if (valid) value[b0 + row] = tanhf(u);
         }
-        float u = sm.bv2;
-#pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {  // value head: Linear(64 -> 1) on relu(hidden) in fp32, then tanh
-            ld32(lane_base + 64 + cb * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) u = fmaf(fmaxf(v[i] + sm.bv0[cb * 32 + i], 0.f), sm.wv2[cb * 32 + i], u);
-        }
-        val = tanhf(u);
     }
-    if (valid) value[b0 + row] = val;
     // ---- GEMM 2: logits ------------------------------------------------------------------------------------
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -196,24 +209,29 @@ heads_forward_tc_kernel(const float *__restrict__ params, const float *__restric
     }
     wait(bar, 1);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    // ---- epilogue 2: softmax of the thread's row (+ legal restriction), three passes over TMEM ------------------
+    // ---- epilogue 2: softmax of the row (+ legal restriction); the two halves of a row exchange their
+    //      partial max / sums through shared memory; three passes over the thread's TMEM columns ------------
+    const int cb0 = hf == 0 ? 0 : 4, cb1 = hf == 0 ? 4 : 7;  // column blocks of 32: half 0 -> 0..127, half 1 -> 128..223
     const uint32_t *lmask = mask + (kLegal && valid ? (b0 + row) * 8 : 0);  // 8 words per board, L1-resident
     float mx = -INFINITY;
     {
         float v[32];
 #pragma unroll 1
-        for (int cb = 0; cb < 7; ++cb) {
+        for (int cb = cb0; cb < cb1; ++cb) {
             ld32(lane_base + cb * 32, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i)
                 if (cb * 32 + i < kP) mx = fmaxf(mx, v[i] + sm.bp2[cb * 32 + i]);
         }
     }
+    sm.xch[0][hf][row] = mx;
+    __syncthreads();
+    mx = fmaxf(mx, sm.xch[0][hf ^ 1][row]);
     float sum_all = 0.f, sum_legal = 0.f;
     {
         float v[32];
 #pragma unroll 1
-        for (int cb = 0; cb < 7; ++cb) {
+        for (int cb = cb0; cb < cb1; ++cb) {
             ld32(lane_base + cb * 32, v);
             const uint32_t bits = (kLegal && valid) ? __ldg(lmask + cb) : 0xFFFFFFFFu;
 #pragma unroll
@@ -226,6 +244,11 @@ heads_forward_tc_kernel(const float *__restrict__ params, const float *__restric
             }
         }
     }
+    sm.xch[1][hf][row] = sum_all;
+    sm.xch[2][hf][row] = sum_legal;
+    __syncthreads();
+    sum_all += sm.xch[1][hf ^ 1][row];
+    sum_legal += sm.xch[2][hf ^ 1][row];
     // softmax then `policy /= sum(policy) if sum(policy) else 1` over the legal entries
     // (pv_network_cnn.py:129-132): p_a / sum_legal p = e_a / sum_legal e
     float inv;
@@ -235,7 +258,7 @@ heads_forward_tc_kernel(const float *__restrict__ params, const float *__restric
         float v[32];
         float *out = policy + (b0 + row) * kP;
 #pragma unroll 1
-        for (int cb = 0; cb < 7; ++cb) {
+        for (int cb = cb0; cb < cb1; ++cb) {
             ld32(lane_base + cb * 32, v);  // executed by every lane: tcgen05.ld is warp-convergent
             if (valid) {
                 const uint32_t bits = kLegal ? __ldg(lmask + cb) : 0xFFFFFFFFu;
