@@ -35,7 +35,9 @@ SYMBOLS = {
     "aq_leaf_eval": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "aq_leaf_eval_ws_floats": (_i64, [_i64]),
     "aq_leaf_eval_host_ws_bytes": (_i64, [_i64]),
-    "aq_leaf_eval_host": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "aq_host_ctx_create": (_i32, [ctypes.POINTER(ctypes.c_void_p)]),
+    "aq_host_ctx_destroy": (_i32, [_vp]),
+    "aq_leaf_eval_host": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "aq_mcts_ws_bytes": (_i64, [_i64, _i64]),
     "aq_mcts_reset": (_i32, [_vp, _vp, _i64, _i64, _vp]),
     "aq_mcts_select": (_i32, [_vp, _i64, _i64, _f32, _vp, _vp, _vp]),

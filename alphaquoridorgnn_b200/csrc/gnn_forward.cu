@@ -391,9 +391,37 @@ extern "C" int64_t aq_leaf_eval_host_ws_bytes(int64_t B) {
                      align256((size_t)B * 32) + align256((size_t)B * 8) + align256((size_t)B * kH * 4));
 }
 
+// Host-side context for the pipelined host-buffer path: two worker streams and their events.  Owned by
+// the caller (aq_host_ctx_create / aq_host_ctx_destroy); no global state.
+struct AqHostCtx {
+    cudaStream_t s[2];
+    cudaEvent_t ready, done[2];
+};
+
+extern "C" int aq_host_ctx_create(void **ctx) {
+    if (!ctx) return aq_set_error(AQ_ERR_ARG, "aq_host_ctx_create");
+    AqHostCtx *c = new AqHostCtx();
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&c->s[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) { delete c; return aq_set_error((int)e, "aq_host_ctx_create"); }
+    *ctx = c;
+    return 0;
+}
+
+extern "C" int aq_host_ctx_destroy(void *ctx) {
+    if (!ctx) return 0;
+    AqHostCtx *c = reinterpret_cast<AqHostCtx *>(ctx);
+    for (int i = 0; i < 2; ++i) { cudaStreamDestroy(c->s[i]); cudaEventDestroy(c->done[i]); }
+    cudaEventDestroy(c->ready);
+    delete c;
+    return 0;
+}
+
 extern "C" int aq_leaf_eval_host(const float *params, const AqState *states_host, int64_t B, float *priors_host,
                                  float *value_host, uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws,
-                                 int precision, void *stream) {
+                                 int precision, void *host_ctx, void *stream) {
     if (B < 0 || !params || (B > 0 && (!states_host || !priors_host || !value_host || !dev_ws)))
         return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host");
     if (B == 0) return 0;
@@ -405,15 +433,39 @@ extern "C" int aq_leaf_eval_host(const float *params, const AqState *states_host
     uint32_t *d_mask = reinterpret_cast<uint32_t *>(p); p += align256((size_t)B * 32);
     uint8_t *d_pawn = reinterpret_cast<uint8_t *>(p);   p += align256((size_t)B * 8);
     float *d_pooled = reinterpret_cast<float *>(p);
-    cudaError_t e = cudaMemcpyAsync(d_states, states_host, (size_t)B * sizeof(AqState), cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(H2D)");
-    int rc = aq_leaf_eval(params, d_states, B, d_priors, d_value, d_mask, d_pawn, d_pooled, precision, stream);
-    if (rc) return rc;
-    e = cudaMemcpyAsync(priors_host, d_priors, (size_t)B * kP * 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(value_host, d_value, (size_t)B * 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && mask_host) e = cudaMemcpyAsync(mask_host, d_mask, (size_t)B * 32, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && pawn_host) e = cudaMemcpyAsync(pawn_host, d_pawn, (size_t)B * 8, cudaMemcpyDeviceToHost, st);
+    AqHostCtx *ctx = reinterpret_cast<AqHostCtx *>(host_ctx);
+    // chunked so that the D2H of chunk c overlaps the H2D + kernels of chunk c+1 (two worker streams);
+    // without a context (or for small batches) everything runs in order on `stream`
+    const int nchunk = (ctx && B >= 4096) ? 4 : 1;
+    cudaError_t e = cudaSuccess;
+    if (nchunk > 1) {
+        e = cudaEventRecord(ctx->ready, st);
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(ctx->s[i], ctx->ready, 0);
+        if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(fork)");
+    }
+    const int64_t per = (B + nchunk - 1) / nchunk;
+    for (int c = 0; c < nchunk; ++c) {
+        const int64_t lo = (int64_t)c * per, n = (lo + per <= B ? per : B - lo);
+        if (n <= 0) break;
+        cudaStream_t cs = nchunk > 1 ? ctx->s[c & 1] : st;
+        e = cudaMemcpyAsync(d_states + lo, states_host + lo, (size_t)n * sizeof(AqState), cudaMemcpyHostToDevice, cs);
+        if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(H2D)");
+        int rc = aq_leaf_eval(params, d_states + lo, n, d_priors + lo * kP, d_value + lo, d_mask + lo * 8, d_pawn + lo * 8,
+                              d_pooled + lo * kH, precision, cs);
+        if (rc) return rc;
+        e = cudaMemcpyAsync(priors_host + lo * kP, d_priors + lo * kP, (size_t)n * kP * 4, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(value_host + lo, d_value + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess && mask_host) e = cudaMemcpyAsync(mask_host + lo * 8, d_mask + lo * 8, (size_t)n * 32, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess && pawn_host) e = cudaMemcpyAsync(pawn_host + lo * 8, d_pawn + lo * 8, (size_t)n * 8, cudaMemcpyDeviceToHost, cs);
+        if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(D2H)");
+    }
+    if (nchunk > 1) {
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = cudaEventRecord(ctx->done[i], ctx->s[i]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ctx->done[i], 0);
+        }
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(D2H)");
+    if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(sync)");
     return 0;
 }

@@ -27,22 +27,53 @@ def network_evaluator(model):
 
 
 class BatchedMCTS:
-    """Lock-step PV-MCTS over G independent root states."""
+    """Lock-step PV-MCTS over G independent root states.
 
-    def __init__(self, evaluator, sims=None, c_puct=C_PUCT, device=None):
-        self.evaluator = evaluator
+    `evaluator` is either a GNNNetwork (leaf evaluation = aq_leaf_eval into preallocated buffers, and the
+    whole simulation step -- select, legal mask, GNN trunk, heads, expand+backup -- is captured once in a
+    CUDA graph and replayed `sims` times) or any callable following the evaluator protocol (eager loop)."""
+
+    def __init__(self, evaluator, sims=None, c_puct=C_PUCT, device=None, use_graph=True):
+        self.model = evaluator if hasattr(evaluator, "flat_parameters") else None
+        self.evaluator = network_evaluator(evaluator) if hasattr(evaluator, "predict_batch") else evaluator
         self.sims = sims
         self.c_puct = float(c_puct)
         self.device = gl._dev(device)
+        self.use_graph = use_graph
         self._ws = None
-        self._cap = (0, 0)
+        self._buf = {}
+        self._graphs = {}
 
     def _workspace(self, G, max_nodes):
         L = _lib.load()
         need = L.aq_mcts_ws_bytes(G, max_nodes)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
+            self._graphs.clear()  # graphs hold raw pointers into the old workspace
         return self._ws
+
+    def _buffers(self, G):
+        if G not in self._buf:
+            dev = self.device
+            self._buf[G] = {
+                "leaf": torch.empty((G, gl.STATE_BYTES), dtype=torch.uint8, device=dev),
+                "kind": torch.empty((G,), dtype=torch.int32, device=dev),
+                "priors": torch.empty((G, gl.NUM_ACTIONS), dtype=torch.float32, device=dev),
+                "value": torch.empty((G,), dtype=torch.float32, device=dev),
+                "mask": torch.empty((G, 8), dtype=torch.int32, device=dev),
+                "pawn": torch.empty((G, 8), dtype=torch.uint8, device=dev),
+                "pooled": torch.empty((G, 128), dtype=torch.float32, device=dev),
+            }
+        return self._buf[G]
+
+    def _step_network(self, ws, G, max_nodes, buf, flat, prec, st):
+        """One simulation for all games with the network evaluator: three library calls, five kernels."""
+        L, P = _lib.load(), _lib.ptr
+        _lib.check(L.aq_mcts_select(P(ws), G, max_nodes, self.c_puct, P(buf["leaf"]), P(buf["kind"]), st), "aq_mcts_select")
+        _lib.check(L.aq_leaf_eval(P(flat), P(buf["leaf"]), G, P(buf["priors"]), P(buf["value"]), P(buf["mask"]), P(buf["pawn"]),
+                                  P(buf["pooled"]), prec, st), "aq_leaf_eval")
+        _lib.check(L.aq_mcts_expand_backup(P(ws), G, max_nodes, P(buf["priors"]), P(buf["value"]), P(buf["mask"]),
+                                           P(buf["pawn"]), st), "aq_mcts_expand_backup")
 
     @torch.no_grad()
     def search(self, roots, sims=None):
@@ -50,23 +81,49 @@ class BatchedMCTS:
         (pv_mcts.py:84) and returns (counts int32[G,136], actions int16[G,136], n_children int16[G]):
         visit counts of the root's children in State.legal_actions() order (pv_mcts.py:88)."""
         sims = sims or self.sims or PV_EVALUATE_COUNT
-        L = _lib.load()
+        L, P = _lib.load(), _lib.ptr
         dev = self.device
         roots = roots.to(dev).contiguous()
         G = roots.shape[0]
         max_nodes = 1 + sims * MAX_CHILDREN
         ws = self._workspace(G, max_nodes)
-        leaf = torch.empty((G, gl.STATE_BYTES), dtype=torch.uint8, device=dev)
-        kind = torch.empty((G,), dtype=torch.int32, device=dev)
-        P = _lib.ptr
+        buf = self._buffers(G)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             _lib.check(L.aq_mcts_reset(P(ws), P(roots), G, max_nodes, st), "aq_mcts_reset")
-            for _ in range(sims):
-                _lib.check(L.aq_mcts_select(P(ws), G, max_nodes, self.c_puct, P(leaf), P(kind), st), "aq_mcts_select")
-                out = self.evaluator(leaf)  # terminal leaves are evaluated too and ignored by the backup
-                _lib.check(L.aq_mcts_expand_backup(P(ws), G, max_nodes, P(out["priors"]), P(out["value"]), P(out["mask"]),
-                                                   P(out["pawn"]), st), "aq_mcts_expand_backup")
+            if self.model is not None:
+                from .pv_network_gnn import PRECISIONS
+                flat = self.model.flat_parameters()
+                prec = PRECISIONS[self.model.precision]
+                key = (G, max_nodes, flat.data_ptr(), prec)
+                graph = self._graphs.get(key) if self.use_graph else None
+                if self.use_graph and graph is None:
+                    try:
+                        self._step_network(ws, G, max_nodes, buf, flat, prec, st)  # warm-up outside capture (= simulation 1)
+                        done = 1
+                        torch.cuda.synchronize(dev)
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            self._step_network(ws, G, max_nodes, buf, flat, prec, _lib.stream_ptr(dev))
+                        if len(self._graphs) >= 16:  # self-play shrinks G as games end: keep the cache bounded
+                            self._graphs.clear()
+                        self._graphs[key] = graph = g
+                    except Exception:  # capture unsupported: stay eager
+                        self.use_graph, graph, done = False, None, 1
+                        torch.cuda.synchronize(dev)
+                else:
+                    done = 0
+                for _ in range(sims - done):
+                    if graph is not None:
+                        graph.replay()
+                    else:
+                        self._step_network(ws, G, max_nodes, buf, flat, prec, st)
+            else:
+                for _ in range(sims):
+                    _lib.check(L.aq_mcts_select(P(ws), G, max_nodes, self.c_puct, P(buf["leaf"]), P(buf["kind"]), st), "aq_mcts_select")
+                    out = self.evaluator(buf["leaf"])  # terminal leaves are evaluated too and ignored by the backup
+                    _lib.check(L.aq_mcts_expand_backup(P(ws), G, max_nodes, P(out["priors"]), P(out["value"]), P(out["mask"]),
+                                                       P(out["pawn"]), st), "aq_mcts_expand_backup")
             counts = torch.empty((G, gl.MAX_LEGAL), dtype=torch.int32, device=dev)
             actions = torch.empty((G, gl.MAX_LEGAL), dtype=torch.int16, device=dev)
             n = torch.empty((G,), dtype=torch.int16, device=dev)
@@ -91,7 +148,8 @@ def policy_from_counts(counts, temperature):
 
 
 def _as_evaluator(model):
-    return model if callable(model) and not hasattr(model, "predict_batch") else network_evaluator(model)
+    """BatchedMCTS accepts a network or an evaluator callable directly."""
+    return model
 
 
 def pv_mcts_policy_batch(model, packed_roots, temperature, sims=None, device=None):
@@ -134,7 +192,7 @@ def bench_sims_per_sec(net, dev, world, timed_barrier, games=4096, sims=200, mov
     import time
     from . import positions
     import torch.distributed as dist
-    mcts = BatchedMCTS(network_evaluator(net), sims, device=dev)
+    mcts = BatchedMCTS(net, sims, device=dev)
     roots = positions.start_states(games, dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(5)

@@ -271,8 +271,12 @@ def run_ours(args, rank, world, local_rank):
     h_pwn = torch.empty((B, 8), dtype=torch.uint8).pin_memory()
     ws = torch.empty((L.aq_leaf_eval_host_ws_bytes(B),), dtype=torch.uint8, device=dev)
 
+    import ctypes
+    hctx = ctypes.c_void_p()
+    _lib.check(L.aq_host_ctx_create(ctypes.byref(hctx)), "aq_host_ctx_create")
+
     def e2e_step(i):
-        _lib.check(L.aq_leaf_eval_host(P(flat), P(hst[i % nb]), B, P(h_pri), P(h_val), P(h_msk), P(h_pwn), P(ws), prec, st),
+        _lib.check(L.aq_leaf_eval_host(P(flat), P(hst[i % nb]), B, P(h_pri), P(h_val), P(h_msk), P(h_pwn), P(ws), prec, hctx, st),
                    "aq_leaf_eval_host")
 
     for i in range(3):

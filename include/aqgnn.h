@@ -146,9 +146,13 @@ int64_t aq_leaf_eval_ws_floats(int64_t B);
  * mask/pawn D2H on `stream`, then synchronises the stream.  dev_ws is a device workspace of
  * aq_leaf_eval_host_ws_bytes(B) bytes. */
 int64_t aq_leaf_eval_host_ws_bytes(int64_t B);
+/* host_ctx (optional, may be NULL): context from aq_host_ctx_create; with it, batches >= 4096 are
+ * processed in 4 chunks on two worker streams so that the D2H of one chunk overlaps the next chunk. */
+int aq_host_ctx_create(void **ctx);
+int aq_host_ctx_destroy(void *ctx);
 int aq_leaf_eval_host(const float *params, const AqState *states_host, int64_t B, float *priors_host,
                       float *value_host, uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision,
-                      void *stream);
+                      void *host_ctx, void *stream);
 
 /* Lock-step PV-MCTS over G independent games (pv_mcts.py:20-95: Node.evaluate / next_child_node).
  * ws: device workspace of aq_mcts_ws_bytes(G, max_nodes); max_nodes >= 1 + sims * 133 never overflows.

@@ -201,9 +201,27 @@ def test_leaf_eval_host_buffers_equal_device_path(traj):
     pwn = torch.empty((B, 8), dtype=torch.uint8).pin_memory()
     ws = torch.empty((L.aq_leaf_eval_host_ws_bytes(B),), dtype=torch.uint8, device="cuda")
     _lib.check(L.aq_leaf_eval_host(_lib.ptr(net.flat_parameters()), _lib.ptr(st), B, _lib.ptr(pri), _lib.ptr(val),
-                                   _lib.ptr(msk), _lib.ptr(pwn), _lib.ptr(ws), 0, _lib.stream_ptr()), "aq_leaf_eval_host")
+                                   _lib.ptr(msk), _lib.ptr(pwn), _lib.ptr(ws), 0, None, _lib.stream_ptr()), "aq_leaf_eval_host")
     assert torch.equal(pri, out["priors"].cpu()) and torch.equal(val, out["value"].cpu())
     assert torch.equal(msk, out["mask"].cpu()) and torch.equal(pwn, out["pawn"].cpu())
+    # pipelined variant (host context, 4 chunks on two worker streams) gives the same bytes
+    import ctypes
+    B2 = 6000
+    rows2, plies2 = _sample_rows(traj, B2, seed=13)
+    ref2 = net.predict_batch(torch.from_numpy(rows2), torch.from_numpy(plies2))
+    st2 = torch.from_numpy(gl.pack_rows_host(rows2, plies2)).pin_memory()
+    pri2 = torch.empty((B2, 209), dtype=torch.float32).pin_memory()
+    val2 = torch.empty((B2,), dtype=torch.float32).pin_memory()
+    msk2 = torch.empty((B2, 8), dtype=torch.int32).pin_memory()
+    pwn2 = torch.empty((B2, 8), dtype=torch.uint8).pin_memory()
+    ws2 = torch.empty((L.aq_leaf_eval_host_ws_bytes(B2),), dtype=torch.uint8, device="cuda")
+    ctx = ctypes.c_void_p()
+    _lib.check(L.aq_host_ctx_create(ctypes.byref(ctx)), "aq_host_ctx_create")
+    _lib.check(L.aq_leaf_eval_host(_lib.ptr(net.flat_parameters()), _lib.ptr(st2), B2, _lib.ptr(pri2), _lib.ptr(val2),
+                                   _lib.ptr(msk2), _lib.ptr(pwn2), _lib.ptr(ws2), 0, ctx, _lib.stream_ptr()), "aq_leaf_eval_host")
+    _lib.check(L.aq_host_ctx_destroy(ctx), "aq_host_ctx_destroy")
+    assert torch.equal(pri2, ref2["priors"].cpu()) and torch.equal(val2, ref2["value"].cpu())
+    assert torch.equal(msk2, ref2["mask"].cpu()) and torch.equal(pwn2, ref2["pawn"].cpu())
 
 
 def test_checkpoint_interchange_and_training_step(tmp_path, traj):

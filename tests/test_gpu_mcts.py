@@ -93,3 +93,21 @@ def test_policy_api_shapes_with_the_real_network():
     assert pv_mcts.boltzman([1, 2, 1], 1.0) == [0.25, 0.5, 0.25]
     act = pv_mcts.pv_mcts_action(net, 0)(s)
     assert act in s.legal_actions()
+
+
+def test_cuda_graph_replay_equals_eager_search(mcts_golden):
+    """The network path replays one captured simulation step; it must give the same tree as the eager loop."""
+    torch.manual_seed(1)
+    net = GNNNetwork().cuda().eval()
+    cases = [r for r in mcts_golden["roots"] if r["sims"] == 50 and r["evaluator"] == "hash"]
+    packed = gl.pack_rows(np.array([c["row"] for c in cases], np.uint8), np.array([c["plies"] for c in cases], np.int16))
+    for prec in ("fp32", "bf16"):
+        net.precision = prec
+        graph = pv_mcts.BatchedMCTS(net, 40, use_graph=True)
+        eager = pv_mcts.BatchedMCTS(net, 40, use_graph=False)
+        c1, a1, n1 = graph.search(packed)
+        c2, a2, n2 = eager.search(packed)
+        c3, _, _ = graph.search(packed)  # second call replays the cached graph from simulation 1
+        assert graph.use_graph and len(graph._graphs) == 1
+        assert torch.equal(c1, c2) and torch.equal(a1, a2) and torch.equal(n1, n2) and torch.equal(c1, c3)
+        assert int(c1.sum(1).min()) == 39
