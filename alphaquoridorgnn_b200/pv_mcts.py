@@ -196,7 +196,7 @@ def bench_sims_per_sec(net, dev, world, timed_barrier, games=4096, sims=200, mov
     roots = positions.start_states(games, dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(5)
-    mcts.search(roots[:64], sims=4)  # warm-up
+    mcts.search(roots, sims=sims)  # warm-up with the same shape: the simulation-step CUDA graph is captured here
     timed_barrier()
     t0 = time.perf_counter()
     done = 0

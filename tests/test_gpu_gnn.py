@@ -278,3 +278,24 @@ def test_bf16_tensor_core_path_within_tolerance(traj):
     legal = qo.legal_actions_batch(rows, plies)
     assert np.array_equal(out["mask"].cpu().numpy().view(np.uint32), legal["mask"])
     assert (out["value"].cpu() - v_ref.squeeze(1)).abs().max().item() <= 5e-3
+
+
+def test_empty_and_tiny_batches_through_every_entry_point():
+    _, net = _models(8)
+    L = _lib.load()
+    for prec in ("fp32", "bf16"):
+        net.precision = prec
+        for B in (0, 1, 2):
+            rows = np.zeros((B, 68), np.uint8)
+            rows[:, [0, 2]] = 76
+            rows[:, [1, 3]] = 10
+            out = net.predict_batch(torch.from_numpy(rows), torch.zeros(B, dtype=torch.int16))
+            assert out["priors"].shape == (B, 209) and out["value"].shape == (B,)
+            if B:
+                assert torch.allclose(out["priors"].sum(1), torch.ones(B, device="cuda"), atol=1e-5)
+                assert int(gl.mask_to_dense(out["mask"]).sum(1)[0]) == 131
+            with torch.no_grad():
+                p, v = net(torch.from_numpy(rows))
+            assert p.shape == (B, 209) and v.shape == (B, 1)
+    assert L.aq_gnn_backward(None, None, None, None, 0, None, None, None) != 0  # argument errors are reported, not crashes
+    assert b"aq_gnn_backward" in L.aq_last_error_string()

@@ -111,3 +111,16 @@ def test_cuda_graph_replay_equals_eager_search(mcts_golden):
         assert graph.use_graph and len(graph._graphs) == 1
         assert torch.equal(c1, c2) and torch.equal(a1, a2) and torch.equal(n1, n2) and torch.equal(c1, c3)
         assert int(c1.sum(1).min()) == 39
+
+
+def test_search_on_a_state_without_legal_actions_is_defined(ka):
+    """KA13-like position with no walls in hand: legal_actions() == [] (the reference would spin / crash at
+    np.argmax([])).  Here the root is re-evaluated every simulation and has no children."""
+    v = ka["KA13"]
+    row = list(v["row"])
+    row[1] = 0  # no walls in hand -> no wall actions either
+    packed = gl.pack_rows(np.array([row], np.uint8), np.array([v["plies"]], np.int16))
+    actions, n = gl.legal_actions_batch(packed)
+    assert int(n[0]) == 0
+    counts, acts, nc = pv_mcts.BatchedMCTS(uniform_evaluator, 8).search(packed)
+    assert int(nc[0]) == 0 and int(counts.sum()) == 0 and int((acts >= 0).sum()) == 0
