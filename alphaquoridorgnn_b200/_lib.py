@@ -29,7 +29,7 @@ SYMBOLS = {
     "aq_gcn_trunk_forward": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp]),
     "aq_heads_forward": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
     "aq_gnn_backward_ws_floats": (_i64, [_i64]),
-    "aq_gnn_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "aq_gnn_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     "aq_loss_grad": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "aq_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _vp]),
     "aq_leaf_eval": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),

@@ -374,8 +374,10 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
 // ------------------------------------------------------------------------------------------
 extern "C" int64_t aq_gnn_backward_ws_floats(int64_t B) { return BwdWs{B}.total(); }
 
+int aq_gcn_backward_tc(const float *params, float *saved, const float *dg, int64_t B, float *partial, cudaStream_t st);  // gnn_tc_bwd.cu
+
 extern "C" int aq_gnn_backward(const float *params, const float *saved, const float *dpolicy, const float *dvalue,
-                               int64_t B, float *grads, float *workspace, void *stream) {
+                               int64_t B, float *grads, float *workspace, int precision, void *stream) {
     if (B <= 0 || !params || !saved || !dpolicy || !dvalue || !grads || !workspace)
         return aq_set_error(AQ_ERR_ARG, "aq_gnn_backward");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -391,8 +393,12 @@ extern "C" int aq_gnn_backward(const float *params, const float *saved, const fl
         params, saved, dpolicy, dvalue, B, workspace);
     int rc = aq_check_launch("heads_backward_kernel");
     if (rc) return rc;
-    gcn_backward_kernel<<<kSlots, kGcnThreads, sizeof(GcnBwdSmem), st>>>(params, saved, B, workspace);
-    if ((rc = aq_check_launch("gcn_backward_kernel"))) return rc;
+    if (precision == 1) {  // tensor-core trunk backward: fills the GCN ranges of every partial slot itself
+        if ((rc = aq_gcn_backward_tc(params, const_cast<float *>(saved), workspace + W.dg(), B, workspace + W.partial(), st))) return rc;
+    } else {
+        gcn_backward_kernel<<<kSlots, kGcnThreads, sizeof(GcnBwdSmem), st>>>(params, saved, B, workspace);
+        if ((rc = aq_check_launch("gcn_backward_kernel"))) return rc;
+    }
 
     AtbJobs jobs;
     int nj = 0;
@@ -400,9 +406,11 @@ extern "C" int aq_gnn_backward(const float *params, const float *saved, const fl
         jobs.job[nj++] = AtbJob{A, lda, M, Bm, ldb, N, R, off};
     };
     const int64_t RN = B * kV;
-    add(workspace + W.dy1(), kH, kH, saved + L.ax0(), kF, kF, RN, kOffW1);    // dW1 = dY1^T (A_hat X0)
-    add(workspace + W.dz2(), kH, kH, saved + L.x(0), kH, kH, RN, kOffW2);     // dW2 = dZ2^T X1
-    add(workspace + W.dz3(), kH, kH, saved + L.x(1), kH, kH, RN, kOffW3);     // dW3 = dZ3^T X2
+    if (precision != 1) {
+        add(workspace + W.dy1(), kH, kH, saved + L.ax0(), kF, kF, RN, kOffW1);    // dW1 = dY1^T (A_hat X0)
+        add(workspace + W.dz2(), kH, kH, saved + L.x(0), kH, kH, RN, kOffW2);     // dW2 = dZ2^T X1
+        add(workspace + W.dz3(), kH, kH, saved + L.x(1), kH, kH, RN, kOffW3);     // dW3 = dZ3^T X2
+    }
     add(workspace + W.dhp(), kHH, kHH, saved + L.pooled(), kH, kH, B, kOffWP0);
     add(workspace + W.dhp(), kHH, kHH, nullptr, 0, 1, B, kOffBP0);
     add(workspace + W.dz(), kP, kP, saved + L.hp(), kHH, kHH, B, kOffWP2);

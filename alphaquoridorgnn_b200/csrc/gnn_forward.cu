@@ -279,15 +279,15 @@ static int set_smem(K kernel, size_t bytes) {
     return e == cudaSuccess ? 0 : (int)e;
 }
 
-int aq_gcn_forward_tc(const float *params, const AqState *states, int64_t B, float *pooled, cudaStream_t st);  // gnn_tc.cu
+int aq_gcn_forward_tc(const float *params, const AqState *states, int64_t B, float *pooled, float *saved, cudaStream_t st);  // gnn_tc.cu
 int aq_heads_forward_tc(const float *params, const float *pooled, int64_t B, float *policy, float *value,
                         const uint32_t *legal_mask, cudaStream_t st);  // heads_tc.cu
 
 static int launch_trunk(const float *params, const AqState *states, const float *x, const uint8_t *open_mask, int64_t B,
                         float *pooled, float *saved, int precision, cudaStream_t st) {
     if (precision == 1) {
-        if (saved || !states) return aq_set_error(AQ_ERR_UNSUPPORTED, "aq_gnn_forward(bf16 path is inference-from-states only)");
-        return aq_gcn_forward_tc(params, states, B, pooled, st);
+        if (!states) return aq_set_error(AQ_ERR_UNSUPPORTED, "aq_gnn_forward(bf16 path needs packed states)");
+        return aq_gcn_forward_tc(params, states, B, pooled, saved, st);
     }
     const unsigned grid = (unsigned)(B < num_sms() ? B : num_sms());
     int rc;

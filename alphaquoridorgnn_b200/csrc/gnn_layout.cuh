@@ -43,4 +43,16 @@ struct SavedLayout {
     __host__ __device__ int64_t total() const { return ax0() + B * kV * kF; }
 };
 
+// Tensor-core training path (precision 1): the x(l) regions of SavedLayout hold bf16 data instead of fp32 --
+//   tc_xfm(l): post-ReLU activations of layer l+1, FEATURE-major bf16 [B][128][96] (zero beyond node 80);
+//   tc_a1t:    the layer-1 node operand transposed, bf16 [B][16][96], stored behind tc_xfm(0) inside x(0);
+//   coef():    A_hat coefficients as [B][81][4] floats {c0, cu, cd, cl}.
+// x(l) has room for B*81*128 floats = B*41,472 bytes; the two views need B*(24,576 + 3,072) bytes.
+__host__ __device__ inline unsigned short *tc_xfm(float *saved, int64_t B, int layer) {
+    return reinterpret_cast<unsigned short *>(saved + SavedLayout{B}.x(layer));
+}
+__host__ __device__ inline unsigned short *tc_a1t(float *saved, int64_t B) {
+    return reinterpret_cast<unsigned short *>(saved + SavedLayout{B}.x(0)) + B * kH * 96;
+}
+
 }  // namespace aq

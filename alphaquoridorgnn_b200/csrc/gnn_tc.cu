@@ -23,12 +23,13 @@
 #include <cstdlib>
 #include <cuda_bf16.h>
 #include "gnn_fp32.cuh"
+#include "tc_common.cuh"
 
 using namespace aq;
+using namespace aqtc;
 
 namespace {
 
-constexpr int kGroupThreads = 128;
 constexpr int kNodesPad = 96;                              // MMA N: 81 nodes padded to a multiple of 16
 constexpr uint32_t kWKBlock = 128 * 128;                   // weight tile: 128 rows x 128 B per K-block
 constexpr uint32_t kXKBlock = kNodesPad * 128;             // node tile: 96 rows x 128 B per K-block
@@ -59,84 +60,17 @@ struct TcSmem {
 static_assert(sizeof(TcSmem<5>) + 1024 <= 227 * 1024, "TcSmem exceeds shared memory");
 static_assert(5 * kNodesPad <= (int)kTmemCols, "TMEM columns");
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void group_sync(int grp) {
-    asm volatile("bar.sync %0, %1;\n" ::"r"(grp + 1), "r"(kGroupThreads) : "memory");
-}
-
-// byte offset of 16-byte chunk j (0..15) of `row` inside a K-major SWIZZLE_128B tile with the given K-block size
-__device__ __forceinline__ uint32_t sw128_chunk(int row, int j, uint32_t kblock) {
-    return (uint32_t)(j >> 3) * kblock + (uint32_t)row * 128u + (uint32_t)(((j & 7) ^ (row & 7)) << 4);
-}
-// shared-memory matrix descriptors: start>>4, LBO=1 (unused for swizzled K-major), SBO, version 1, layout type
-__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {  // SBO = 1024 B, type 2 = SWIZZLE_128B
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// K-major SWIZZLE_32B (rows of 32 B, 8-row atoms of 256 B): chunk c of row r at r*32 + ((c ^ ((r>>2)&1)) << 4)
-__device__ __forceinline__ uint32_t sw32_chunk(int row, int c) {
-    return (uint32_t)row * 32u + (uint32_t)((c ^ ((row >> 2) & 1)) << 4);
-}
-__device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr) {   // SBO = 256 B, type 6 = SWIZZLE_32B
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
-}
-
-__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");  // suspend-time hint (ns): sleep, do not spin
-    }
-}
-// 32 accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t *>(&t);
-}
-// relu(x) -> bf16 -> 16-bit shared store (cvt.rn.relu folds the ReLU into the conversion)
-__device__ __forceinline__ void st_relu_bf16(uint32_t saddr, float x) {
-    asm volatile("{\n\t.reg .b16 t;\n\tcvt.rn.relu.bf16.f32 t, %1;\n\tst.shared.b16 [%0], t;\n\t}\n" ::"r"(saddr), "f"(x) : "memory");
-}
-__device__ __forceinline__ unsigned short bf16_bits(float x) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    return *reinterpret_cast<const unsigned short *>(&h);
-}
-
 // Accumulator column c of the current layer: columns 0..31 / 64..95 live in za (reloaded once), 32..63 in zb.
 #define AQ_Z(c) ((c) < 32 ? za[(c)] : ((c) < 64 ? zb[(c) - 32] : za[(c) - 64]))
 
-template <int kGroups>
+// kSave (training forward): additionally writes what the tensor-core backward needs into the SavedLayout
+// regions (gnn_layout.cuh) -- the post-ReLU activations of the three layers FEATURE-major as bf16
+// [B][128][96] (zero beyond node 80) inside the x(l) regions, the layer-1 node operand transposed
+// [B][16][96] behind them, and the A_hat coefficients [B][81][4] in the coef region.
+template <int kGroups, bool kSave>
 __global__ void __launch_bounds__(kGroups * kGroupThreads, 1)
 gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restrict__ states, int64_t B,
-                      float *__restrict__ pooled_out) {
+                      float *__restrict__ pooled_out, float *__restrict__ saved) {
     constexpr int kTcThreads = kGroups * kGroupThreads;
     extern __shared__ unsigned char smem_raw[];
     TcSmem<kGroups> &sm = *reinterpret_cast<TcSmem<kGroups> *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -231,6 +165,19 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
             c1v.z = 0x3F803F80u; c1v.w = 0u;  // 1, 1, 0, 0
             *reinterpret_cast<uint4 *>(gs.x + sw128_chunk(v, 0, kXKBlock)) = c0v;
             *reinterpret_cast<uint4 *>(gs.x + sw128_chunk(v, 1, kXKBlock)) = c1v;
+            if (kSave) {
+                const SavedLayout L{B};
+                float *rs = saved + L.coef() + (b * kV + v) * 4;
+                rs[0] = c0; rs[1] = cu; rs[2] = cd; rs[3] = cl;
+                unsigned short *at = tc_a1t(saved, B) + b * 16 * kNodesPad + v;
+                const uint32_t wds[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+#pragma unroll
+                for (int k = 0; k < 16; ++k) at[k * kNodesPad] = (unsigned short)(wds[k >> 1] >> (16 * (k & 1)));
+            }
+        } else if (kSave && tid < kNodesPad) {  // K padding of the transposed layer-1 operand must be zero
+            unsigned short *at = tc_a1t(saved, B) + b * 16 * kNodesPad + tid;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) at[k * kNodesPad] = 0;
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -253,6 +200,16 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
                 for (int i = 0; i < 32; ++i) {
                     const int v = cb * 32 + i;
                     if (v < kV) st_relu_bf16(xs[v & 7] + v * 128, za[i]);
+                }
+                if (kSave) {
+                    uint4 *row = reinterpret_cast<uint4 *>(tc_xfm(saved, B, 0) + (b * kH + tid) * kNodesPad) + cb * 4;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float h[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) h[e] = (cb * 32 + i * 8 + e < kV) ? fmaxf(za[i * 8 + e], 0.f) : 0.f;
+                        row[i] = pack8_bf16(h);
+                    }
                 }
             }
         }
@@ -284,6 +241,8 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
                 tmem_ld32(tmem_me, za);
                 tmem_ld32(tmem_me + 32, zb);
                 float4 rn = gs.rec[0];
+                float hold[8];
+                uint4 *srow = kSave ? reinterpret_cast<uint4 *>(tc_xfm(saved, B, 1) + (b * kH + tid) * kNodesPad) : nullptr;
 #pragma unroll
                 for (int v = 0; v < kV; ++v) {
                     if (v == 41) tmem_ld32(tmem_me + 64, za);  // columns 0..31 are dead after node 40
@@ -296,12 +255,23 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
                     if (v % 9 != 0) s = fmaf(r0.w, AQ_Z(v - 1), s);
                     if (v % 9 != 8) s = fmaf(cr, AQ_Z(v + 1), s);
                     st_relu_bf16(xs[v & 7] + v * 128, s);  // next layer's node operand
+                    if (kSave) {
+                        hold[v & 7] = fmaxf(s, 0.f);
+                        if ((v & 7) == 7) srow[v >> 3] = pack8_bf16(hold);
+                    }
+                }
+                if (kSave) {  // node 80 and the zero K padding (columns 81..95)
+                    const float t[8] = {hold[0], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    srow[10] = pack8_bf16(t);
+                    srow[11] = make_uint4(0u, 0u, 0u, 0u);
                 }
             } else {
                 float za[32], zb[32];
                 tmem_ld32(tmem_me, za);
                 tmem_ld32(tmem_me + 32, zb);
                 float4 rn = gs.rec[0];
+                float hold[8];
+                uint4 *srow = kSave ? reinterpret_cast<uint4 *>(tc_xfm(saved, B, 2) + (b * kH + tid) * kNodesPad) : nullptr;
 #pragma unroll
                 for (int v = 0; v < kV; ++v) {
                     if (v == 41) tmem_ld32(tmem_me + 64, za);
@@ -314,6 +284,15 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
                     if (v % 9 != 0) s = fmaf(r0.w, AQ_Z(v - 1), s);
                     if (v % 9 != 8) s = fmaf(cr, AQ_Z(v + 1), s);
                     pool += fmaxf(s, 0.f);  // last layer feeds only the mean pool
+                    if (kSave) {
+                        hold[v & 7] = fmaxf(s, 0.f);
+                        if ((v & 7) == 7) srow[v >> 3] = pack8_bf16(hold);
+                    }
+                }
+                if (kSave) {
+                    const float t[8] = {hold[0], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    srow[10] = pack8_bf16(t);
+                    srow[11] = make_uint4(0u, 0u, 0u, 0u);
                 }
             }
         }
@@ -333,17 +312,26 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
 }  // namespace
 
 template <int kGroups>
-static int launch_tc(const float *params, const AqState *states, int64_t B, float *pooled, int sms, cudaStream_t st) {
+static int launch_tc(const float *params, const AqState *states, int64_t B, float *pooled, float *saved, int sms,
+                     cudaStream_t st) {
     const size_t smem = sizeof(TcSmem<kGroups>) + 1024;
-    cudaError_t e = cudaFuncSetAttribute(gcn_forward_tc_kernel<kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return aq_set_error((int)e, "gcn_forward_tc smem");
     const int64_t want = (B + kGroups - 1) / kGroups;
     const unsigned grid = (unsigned)(want < sms ? want : sms);
-    gcn_forward_tc_kernel<kGroups><<<grid, kGroups * kGroupThreads, smem, st>>>(params, states, B, pooled);
+    cudaError_t e;
+    if (saved) {
+        e = cudaFuncSetAttribute(gcn_forward_tc_kernel<kGroups, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return aq_set_error((int)e, "gcn_forward_tc smem");
+        gcn_forward_tc_kernel<kGroups, true><<<grid, kGroups * kGroupThreads, smem, st>>>(params, states, B, pooled, saved);
+    } else {
+        e = cudaFuncSetAttribute(gcn_forward_tc_kernel<kGroups, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return aq_set_error((int)e, "gcn_forward_tc smem");
+        gcn_forward_tc_kernel<kGroups, false><<<grid, kGroups * kGroupThreads, smem, st>>>(params, states, B, pooled, nullptr);
+    }
     return aq_check_launch("gcn_forward_tc_kernel");
 }
 
-int aq_gcn_forward_tc(const float *params, const AqState *states, int64_t B, float *pooled, cudaStream_t st) {
+// saved == nullptr: inference.  saved != nullptr: training forward (activations kept for aq_gnn_backward, precision 1).
+int aq_gcn_forward_tc(const float *params, const AqState *states, int64_t B, float *pooled, float *saved, cudaStream_t st) {
     static int sms = 0, groups = 0;
     if (sms == 0) {
         int dev = 0;
@@ -353,7 +341,7 @@ int aq_gcn_forward_tc(const float *params, const AqState *states, int64_t B, flo
         const char *env = getenv("AQ_TC_GROUPS");  // tuning knob: boards in flight per SM (3, 4 or 5)
         groups = env ? atoi(env) : 5;
     }
-    if (groups == 3) return launch_tc<3>(params, states, B, pooled, sms, st);
-    if (groups == 4) return launch_tc<4>(params, states, B, pooled, sms, st);
-    return launch_tc<5>(params, states, B, pooled, sms, st);
+    if (saved || groups == 3) return launch_tc<3>(params, states, B, pooled, saved, sms, st);  // the save variant needs the registers
+    if (groups == 4) return launch_tc<4>(params, states, B, pooled, saved, sms, st);
+    return launch_tc<5>(params, states, B, pooled, saved, sms, st);
 }

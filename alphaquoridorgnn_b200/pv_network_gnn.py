@@ -59,7 +59,7 @@ class _GnnFunction(torch.autograd.Function):
     """forward = aq_gnn_forward with a saved-activation workspace, backward = aq_gnn_backward."""
 
     @staticmethod
-    def forward(ctx, flat, packed, x, open_mask, *params):
+    def forward(ctx, flat, packed, x, open_mask, prec, *params):
         L = _lib.load()
         dev = flat.device
         B = packed.shape[0] if packed is not None else open_mask.shape[0]
@@ -68,10 +68,11 @@ class _GnnFunction(torch.autograd.Function):
         saved = torch.empty((L.aq_gnn_saved_floats(B),), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(L.aq_gnn_forward(_lib.ptr(flat), _lib.ptr(packed), _lib.ptr(x), _lib.ptr(open_mask), B,
-                                        _lib.ptr(policy), _lib.ptr(value), _lib.ptr(saved), 0, _lib.stream_ptr(dev)),
+                                        _lib.ptr(policy), _lib.ptr(value), _lib.ptr(saved), prec, _lib.stream_ptr(dev)),
                        "aq_gnn_forward")
         ctx.save_for_backward(flat, saved)
         ctx.B = B
+        ctx.prec = prec
         ctx.shapes = [p.shape for p in params]
         return policy, value.unsqueeze(1)
 
@@ -86,13 +87,13 @@ class _GnnFunction(torch.autograd.Function):
         ws = torch.empty((L.aq_gnn_backward_ws_floats(B),), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(L.aq_gnn_backward(_lib.ptr(flat), _lib.ptr(saved), _lib.ptr(dpolicy), _lib.ptr(dvalue), B,
-                                         _lib.ptr(grads), _lib.ptr(ws), _lib.stream_ptr(dev)), "aq_gnn_backward")
+                                         _lib.ptr(grads), _lib.ptr(ws), ctx.prec, _lib.stream_ptr(dev)), "aq_gnn_backward")
         out, off = [], 0
         for shp in ctx.shapes:
             n = int(np.prod(shp))
             out.append(grads[off:off + n].view(shp))
             off += n
-        return (None, None, None, None, *out)
+        return (None, None, None, None, None, *out)
 
 
 # Graph-based Policy-Value Network
@@ -130,6 +131,7 @@ class GraphPolicyValueNetwork(nn.Module):
             nn.Tanh()
         )
         self.precision = "fp32"  # inference arithmetic: "fp32" (FFMA) or "bf16" (tcgen05 tensor cores)
+        self.train_precision = "fp32"  # forward+backward under autograd: "fp32", or "bf16" (tcgen05 trunk, fp32 accumulate)
         self._flat = None
 
     def ordered_parameters(self):
@@ -194,7 +196,8 @@ class GraphPolicyValueNetwork(nn.Module):
         Returns (policy [B,209] softmax probabilities, value [B,1])."""
         flat, packed, xx, open_mask = self._prepare(x, edge_index, batch)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            return _GnnFunction.apply(flat, packed, xx, open_mask, *self.ordered_parameters())
+            prec = PRECISIONS[self.train_precision] if packed is not None else 0
+            return _GnnFunction.apply(flat, packed, xx, open_mask, prec, *self.ordered_parameters())
         L = _lib.load()
         dev = flat.device
         B = packed.shape[0] if packed is not None else open_mask.shape[0]

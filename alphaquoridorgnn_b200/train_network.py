@@ -48,8 +48,10 @@ def shard_bounds(n, rank, world_size):
 class FlatTrainer:
     """One model replica + Adam state on flat buffers; step() = forward/loss/backward/all-reduce/Adam."""
 
-    def __init__(self, model, lr=0.001, betas=(0.9, 0.999), eps=1e-8, rank=0, world_size=1):
+    def __init__(self, model, lr=0.001, betas=(0.9, 0.999), eps=1e-8, rank=0, world_size=1, precision=None):
+        from .pv_network_gnn import PRECISIONS
         self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
+        self.prec = PRECISIONS[precision if precision is not None else model.train_precision]
         self.rank, self.world = rank, world_size
         self.flat = model.flat_parameters()
         _lib.require_cuda(self.flat, "model parameters")
@@ -74,10 +76,10 @@ class FlatTrainer:
                 saved = torch.empty((L.aq_gnn_saved_floats(b),), dtype=torch.float32, device=dev)
                 ws = torch.empty((L.aq_gnn_backward_ws_floats(b),), dtype=torch.float32, device=dev)
                 dp, dv = torch.empty_like(policy), torch.empty_like(value)
-                _lib.check(L.aq_gnn_forward(P(self.flat), P(packed), None, None, b, P(policy), P(value), P(saved), 0, st), "aq_gnn_forward")
+                _lib.check(L.aq_gnn_forward(P(self.flat), P(packed), None, None, b, P(policy), P(value), P(saved), self.prec, st), "aq_gnn_forward")
                 _lib.check(L.aq_loss_grad(P(policy), P(value), P(policy_target), P(value_target), b, global_batch, P(self.loss),
                                           P(dp), P(dv), st), "aq_loss_grad")
-                _lib.check(L.aq_gnn_backward(P(self.flat), P(saved), P(dp), P(dv), b, P(self.grads), P(ws), st), "aq_gnn_backward")
+                _lib.check(L.aq_gnn_backward(P(self.flat), P(saved), P(dp), P(dv), b, P(self.grads), P(ws), self.prec, st), "aq_gnn_backward")
             else:
                 self.grads.zero_()
                 self.loss.zero_()

@@ -323,12 +323,13 @@ def run_ours(args, rank, world, local_rank):
         grads, m1, m2 = torch.empty_like(tflat), torch.zeros_like(tflat), torch.zeros_like(tflat)
         loss = torch.zeros(2, device=dev)
         stepno = [0]
+        tprec = prec  # training arithmetic follows --precision (bf16 = tcgen05 trunk forward/backward, fp32 accumulate)
 
         def train_step(i):
             stepno[0] += 1
-            _lib.check(L.aq_gnn_forward(P(tflat), P(tb), None, None, TB, P(tp), P(tv), P(saved), 0, st), "fwd")
+            _lib.check(L.aq_gnn_forward(P(tflat), P(tb), None, None, TB, P(tp), P(tv), P(saved), tprec, st), "fwd")
             _lib.check(L.aq_loss_grad(P(tp), P(tv), P(pt), P(vt), TB, TB * world, P(loss), P(dp), P(dv), st), "loss")
-            _lib.check(L.aq_gnn_backward(P(tflat), P(saved), P(dp), P(dv), TB, P(grads), P(bws), st), "bwd")
+            _lib.check(L.aq_gnn_backward(P(tflat), P(saved), P(dp), P(dv), TB, P(grads), P(bws), tprec, st), "bwd")
             if world > 1:
                 dist.all_reduce(grads)
             _lib.check(L.aq_adam_step(P(tflat), P(grads), P(m1), P(m2), tflat.numel(), stepno[0], 1e-3, 0.9, 0.999, 1e-8,

@@ -99,7 +99,7 @@ int aq_edges_to_open_mask(const int64_t *src, const int64_t *dst, int64_t E, int
  * Inputs are either `states` (graph built in-kernel) or (x, open_mask) when states == NULL.
  *   policy [B,209] softmax probabilities, value [B] tanh.
  *   saved  NULL for inference, else workspace of aq_gnn_saved_floats(B) floats kept for backward.
- *   precision 0 = fp32 FFMA path, 1 = bf16 tcgen05 tensor-core path (inference only). */
+ *   precision 0 = fp32 FFMA path, 1 = bf16 tcgen05 tensor-core path (needs packed states). */
 int64_t aq_param_count(void);
 int64_t aq_gnn_saved_floats(int64_t B);
 int aq_gnn_forward(const float *params, const AqState *states, const float *x, const uint8_t *open_mask, int64_t B,
@@ -116,10 +116,12 @@ int aq_heads_forward(const float *params, const float *pooled, int64_t B, float 
 
 /* Backward of the above (autograd of train_network.py:93).  dpolicy [B,209], dvalue [B] are the
  * loss gradients w.r.t. the softmax / tanh outputs; grads f32[64082] is OVERWRITTEN with the
- * parameter gradients (flat, same order as params); workspace of aq_gnn_backward_ws_floats(B). */
+ * parameter gradients (flat, same order as params); workspace of aq_gnn_backward_ws_floats(B).
+ * precision must equal the precision of the aq_gnn_forward call that filled `saved` (0 = fp32 FFMA,
+ * 1 = bf16 tcgen05 trunk forward/backward with fp32 accumulation; heads, loss and Adam stay fp32). */
 int64_t aq_gnn_backward_ws_floats(int64_t B);
 int aq_gnn_backward(const float *params, const float *saved, const float *dpolicy, const float *dvalue, int64_t B,
-                    float *grads, float *workspace, void *stream);
+                    float *grads, float *workspace, int precision, void *stream);
 
 /* Loss of train_network.py:54-55,85-89: CrossEntropyLoss applied to the softmax OUTPUT (so a
  * second log_softmax; kept literally) + MSELoss, both 'mean' over B_total (= global batch under

@@ -297,5 +297,50 @@ def test_empty_and_tiny_batches_through_every_entry_point():
             with torch.no_grad():
                 p, v = net(torch.from_numpy(rows))
             assert p.shape == (B, 209) and v.shape == (B, 1)
-    assert L.aq_gnn_backward(None, None, None, None, 0, None, None, None) != 0  # argument errors are reported, not crashes
+    assert L.aq_gnn_backward(None, None, None, None, 0, None, None, 0, None) != 0  # argument errors are reported, not crashes
     assert b"aq_gnn_backward" in L.aq_last_error_string()
+
+
+def test_bf16_tensor_core_training_gradients(traj):
+    """Training forward + backward with the tcgen05 trunk (bf16 operands, fp32 accumulation; heads, loss and
+    Adam in fp32) against fp64 oracle autograd.  Stated tolerance: every parameter gradient rel-L2 <= 2e-2
+    (SURVEY.md section 8d); the measured errors are printed."""
+    B = 300
+    rows, _ = _sample_rows(traj, B, seed=31)
+    ref, net = _models(9)
+    ref64 = copy.deepcopy(ref).double()
+    x, ei, batch = gnn_oracle.graph_inputs_from_rows(rows, dtype=torch.float64)
+    torch.manual_seed(5)
+    pt = torch.softmax(2 * torch.randn(B, 209), dim=1)
+    vt = torch.randint(-1, 2, (B,)).float()
+    p64, v64 = ref64(x, ei, batch)
+    loss64, _, _ = gnn_oracle.training_loss(p64, v64, pt.double(), vt.double())
+    loss64.backward()
+    net.train()
+    net.train_precision = "bf16"
+    p, v = net(torch.from_numpy(rows))
+    loss = torch.nn.CrossEntropyLoss()(p, pt.cuda()) + torch.nn.MSELoss()(v.squeeze(), vt.cuda())
+    loss.backward()
+    assert (p.detach().cpu() - p64.float()).abs().max().item() <= 2e-3
+    assert (v.detach().cpu() - v64.float()).abs().max().item() <= 5e-3
+    assert abs(loss.item() - loss64.item()) <= 2e-3
+    g_ref = dict(ref64.named_parameters())
+    worst = {}
+    for name, prm in net.named_parameters():
+        assert prm.grad is not None and torch.isfinite(prm.grad).all(), name
+        worst[name] = _rel_l2(prm.grad.cpu(), g_ref[name].grad)
+    print("bf16 training grads rel-L2:", {k: f"{e:.2e}" for k, e in worst.items()})
+    assert max(worst.values()) <= 2e-2, worst
+    # deterministic: a second backward gives bit-identical gradients
+    g1 = {n: q.grad.clone() for n, q in net.named_parameters()}
+    net.zero_grad()
+    p, v = net(torch.from_numpy(rows))
+    (torch.nn.CrossEntropyLoss()(p, pt.cuda()) + torch.nn.MSELoss()(v.squeeze(), vt.cuda())).backward()
+    for n, q in net.named_parameters():
+        assert torch.equal(q.grad, g1[n]), n
+    # small and ragged batches
+    for b in (1, 3, 149):
+        net.zero_grad()
+        p, v = net(torch.from_numpy(rows[:b]))
+        (p.square().sum() + v.sum()).backward()
+        assert all(torch.isfinite(q.grad).all() for q in net.parameters())
