@@ -308,37 +308,44 @@ def run_ours(args, rank, world, local_rank):
         extra["legal_mask_ms_per_1M"] = ms
         extra["legal_mask_hbm_frac"] = BYTES_PER_POSITION_LEGAL * M / (ms * 1e-3) / 1e9 / pk["hbm"]
         del big, bmask, bpawn
-        # training step, BASELINE configs[0] shape on the GPU: B=256 forward + loss + backward + Adam
-        TB = 256
-        tb = batches[0][:TB].contiguous()
-        torch.manual_seed(1)
-        pt = torch.softmax(torch.randn(TB, 209, device=dev), 1)
-        vt = torch.randint(-1, 2, (TB,), device=dev).float()
-        tflat = flat.clone()
-        saved = torch.empty((L.aq_gnn_saved_floats(TB),), dtype=torch.float32, device=dev)
-        bws = torch.empty((L.aq_gnn_backward_ws_floats(TB),), dtype=torch.float32, device=dev)
-        tp = torch.empty((TB, 209), dtype=torch.float32, device=dev)
-        tv = torch.empty((TB,), dtype=torch.float32, device=dev)
-        dp, dv = torch.empty_like(tp), torch.empty_like(tv)
-        grads, m1, m2 = torch.empty_like(tflat), torch.zeros_like(tflat), torch.zeros_like(tflat)
-        loss = torch.zeros(2, device=dev)
-        stepno = [0]
-        tprec = prec  # training arithmetic follows --precision (bf16 = tcgen05 trunk forward/backward, fp32 accumulate)
+        # training step (forward + loss + backward + gradient all-reduce + Adam), random targets:
+        #   B=256  -- BASELINE configs[0] shape (what one optimizer step of the reference looks like)
+        #   B=4096 -- the same step at a throughput-sized per-GPU batch
+        def train_bench(TB):
+            tb = allpos[:TB].contiguous()
+            torch.manual_seed(1)
+            pt = torch.softmax(torch.randn(TB, 209, device=dev), 1)
+            vt = torch.randint(-1, 2, (TB,), device=dev).float()
+            tflat = flat.clone()
+            saved = torch.empty((L.aq_gnn_saved_floats(TB),), dtype=torch.float32, device=dev)
+            bws = torch.empty((L.aq_gnn_backward_ws_floats(TB),), dtype=torch.float32, device=dev)
+            tp = torch.empty((TB, 209), dtype=torch.float32, device=dev)
+            tv = torch.empty((TB,), dtype=torch.float32, device=dev)
+            dp, dv = torch.empty_like(tp), torch.empty_like(tv)
+            grads, m1, m2 = torch.empty_like(tflat), torch.zeros_like(tflat), torch.zeros_like(tflat)
+            loss = torch.zeros(2, device=dev)
+            stepno = [0]
+            tprec = prec  # training arithmetic follows --precision (bf16 = tcgen05 trunk forward/backward, fp32 accumulate)
 
-        def train_step(i):
-            stepno[0] += 1
-            _lib.check(L.aq_gnn_forward(P(tflat), P(tb), None, None, TB, P(tp), P(tv), P(saved), tprec, st), "fwd")
-            _lib.check(L.aq_loss_grad(P(tp), P(tv), P(pt), P(vt), TB, TB * world, P(loss), P(dp), P(dv), st), "loss")
-            _lib.check(L.aq_gnn_backward(P(tflat), P(saved), P(dp), P(dv), TB, P(grads), P(bws), tprec, st), "bwd")
-            if world > 1:
-                dist.all_reduce(grads)
-            _lib.check(L.aq_adam_step(P(tflat), P(grads), P(m1), P(m2), tflat.numel(), stepno[0], 1e-3, 0.9, 0.999, 1e-8,
-                                      1.0, st), "adam")
+            def train_step(i):
+                stepno[0] += 1
+                _lib.check(L.aq_gnn_forward(P(tflat), P(tb), None, None, TB, P(tp), P(tv), P(saved), tprec, st), "fwd")
+                _lib.check(L.aq_loss_grad(P(tp), P(tv), P(pt), P(vt), TB, TB * world, P(loss), P(dp), P(dv), st), "loss")
+                _lib.check(L.aq_gnn_backward(P(tflat), P(saved), P(dp), P(dv), TB, P(grads), P(bws), tprec, st), "bwd")
+                if world > 1:
+                    dist.all_reduce(grads)
+                _lib.check(L.aq_adam_step(P(tflat), P(grads), P(m1), P(m2), tflat.numel(), stepno[0], 1e-3, 0.9, 0.999, 1e-8,
+                                          1.0, st), "adam")
 
-        ms = timed(train_step, 20, 5)
-        extra["train_samples_per_sec"] = world * TB / (ms * 1e-3)
+            return timed(train_step, 20, 5)
+
+        ms = train_bench(256)
+        extra["train_samples_per_sec"] = world * 256 / (ms * 1e-3)
         extra["train_ms_per_step_B256"] = ms
-        extra["train_tensor_frac"] = FLOP_PER_BOARD_FWDBWD * TB / (ms * 1e-3) / 1e12 / pk["tensor"]
+        ms = train_bench(4096)
+        extra["train_samples_per_sec_B4096"] = world * 4096 / (ms * 1e-3)
+        extra["train_ms_per_step_B4096"] = ms
+        extra["train_tensor_frac_B4096"] = FLOP_PER_BOARD_FWDBWD * 4096 / (ms * 1e-3) / 1e12 / pk["tensor"]
         try:
             from alphaquoridorgnn_b200 import pv_mcts
             extra.update(pv_mcts.bench_sims_per_sec(net, dev, world, timed_barrier=barrier))
