@@ -26,18 +26,20 @@ SYMBOLS = {
     "aq_param_count": (_i64, []),
     "aq_gnn_saved_floats": (_i64, [_i64]),
     "aq_gnn_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
-    "aq_gcn_trunk_forward": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp]),
-    "aq_heads_forward": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
+    "aq_gcn_trunk_forward": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _vp]),
+    "aq_heads_forward": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
+    "aq_prepared_bytes": (_i64, []),
+    "aq_prepare_inference": (_i32, [_vp, _vp, _vp]),
     "aq_gnn_backward_ws_floats": (_i64, [_i64]),
     "aq_gnn_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     "aq_loss_grad": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "aq_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _vp]),
-    "aq_leaf_eval": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "aq_leaf_eval": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "aq_leaf_eval_ws_floats": (_i64, [_i64]),
     "aq_leaf_eval_host_ws_bytes": (_i64, [_i64]),
     "aq_host_ctx_create": (_i32, [ctypes.POINTER(ctypes.c_void_p)]),
     "aq_host_ctx_destroy": (_i32, [_vp]),
-    "aq_leaf_eval_host": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "aq_leaf_eval_host": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "aq_mcts_ws_bytes": (_i64, [_i64, _i64]),
     "aq_mcts_reset": (_i32, [_vp, _vp, _i64, _i64, _vp]),
     "aq_mcts_select": (_i32, [_vp, _i64, _i64, _f32, _vp, _vp, _vp]),

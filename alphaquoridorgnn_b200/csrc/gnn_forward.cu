@@ -279,15 +279,16 @@ static int set_smem(K kernel, size_t bytes) {
     return e == cudaSuccess ? 0 : (int)e;
 }
 
-int aq_gcn_forward_tc(const float *params, const AqState *states, int64_t B, float *pooled, float *saved, cudaStream_t st);  // gnn_tc.cu
-int aq_heads_forward_tc(const float *params, const float *pooled, int64_t B, float *policy, float *value,
+int aq_gcn_forward_tc(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, float *saved,
+                      cudaStream_t st);  // gnn_tc.cu
+int aq_heads_forward_tc(const float *params, const void *prepared, const float *pooled, int64_t B, float *policy, float *value,
                         const uint32_t *legal_mask, cudaStream_t st);  // heads_tc.cu
 
-static int launch_trunk(const float *params, const AqState *states, const float *x, const uint8_t *open_mask, int64_t B,
-                        float *pooled, float *saved, int precision, cudaStream_t st) {
+static int launch_trunk(const float *params, const void *prepared, const AqState *states, const float *x,
+                        const uint8_t *open_mask, int64_t B, float *pooled, float *saved, int precision, cudaStream_t st) {
     if (precision == 1) {
         if (!states) return aq_set_error(AQ_ERR_UNSUPPORTED, "aq_gnn_forward(bf16 path needs packed states)");
-        return aq_gcn_forward_tc(params, states, B, pooled, saved, st);
+        return aq_gcn_forward_tc(params, prepared, states, B, pooled, saved, st);
     }
     const unsigned grid = (unsigned)(B < num_sms() ? B : num_sms());
     int rc;
@@ -301,9 +302,9 @@ static int launch_trunk(const float *params, const AqState *states, const float 
     return aq_check_launch("gcn_forward_fp32_kernel");
 }
 
-static int launch_heads(const float *params, const float *pooled, int64_t B, float *policy, float *value,
-                        const uint32_t *legal_mask, float *saved, int precision, cudaStream_t st) {
-    if (precision == 1 && !saved) return aq_heads_forward_tc(params, pooled, B, policy, value, legal_mask, st);
+static int launch_heads(const float *params, const void *prepared, const float *pooled, int64_t B, float *policy,
+                        float *value, const uint32_t *legal_mask, float *saved, int precision, cudaStream_t st) {
+    if (precision == 1 && !saved) return aq_heads_forward_tc(params, prepared, pooled, B, policy, value, legal_mask, st);
     const int64_t hb = (B + 7) / 8;
     const unsigned hgrid = (unsigned)(hb < num_sms() ? hb : num_sms());
     int rc;
@@ -320,32 +321,32 @@ static int launch_heads(const float *params, const float *pooled, int64_t B, flo
     return aq_check_launch("heads_forward_kernel");
 }
 
-extern "C" int aq_gcn_trunk_forward(const float *params, const AqState *states, int64_t B, float *pooled, int precision,
-                                    void *stream) {
+extern "C" int aq_gcn_trunk_forward(const float *params, const void *prepared, const AqState *states, int64_t B,
+                                    float *pooled, int precision, void *stream) {
     if (B < 0 || !params || (B > 0 && (!states || !pooled))) return aq_set_error(AQ_ERR_ARG, "aq_gcn_trunk_forward");
     if (B == 0) return 0;
-    return launch_trunk(params, states, nullptr, nullptr, B, pooled, nullptr, precision, reinterpret_cast<cudaStream_t>(stream));
+    return launch_trunk(params, prepared, states, nullptr, nullptr, B, pooled, nullptr, precision, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int aq_heads_forward(const float *params, const float *pooled, int64_t B, float *policy, float *value,
-                                const uint32_t *legal_mask, int precision, void *stream) {
+extern "C" int aq_heads_forward(const float *params, const void *prepared, const float *pooled, int64_t B, float *policy,
+                                float *value, const uint32_t *legal_mask, int precision, void *stream) {
     if (B < 0 || !params || (B > 0 && (!pooled || !policy || !value))) return aq_set_error(AQ_ERR_ARG, "aq_heads_forward");
     if (B == 0) return 0;
-    return launch_heads(params, pooled, B, policy, value, legal_mask, nullptr, precision, reinterpret_cast<cudaStream_t>(stream));
+    return launch_heads(params, prepared, pooled, B, policy, value, legal_mask, nullptr, precision, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // pooled [B,128] scratch must be provided by the caller when saved == NULL (inference); with a
 // saved workspace the pooled section of `saved` is used.
-int aq_gnn_forward_impl(const float *params, const AqState *states, const float *x, const uint8_t *open_mask,
-                        int64_t B, float *policy, float *value, float *saved, float *pooled_scratch,
+int aq_gnn_forward_impl(const float *params, const void *prepared, const AqState *states, const float *x,
+                        const uint8_t *open_mask, int64_t B, float *policy, float *value, float *saved, float *pooled_scratch,
                         const uint32_t *legal_mask, int precision, cudaStream_t st) {
     if (B == 0) return 0;
     const SavedLayout L{B};
     float *pooled = saved ? saved + L.pooled() : pooled_scratch;
     if (!pooled) return aq_set_error(AQ_ERR_ARG, "aq_gnn_forward(pooled scratch)");
-    int rc = launch_trunk(params, states, x, open_mask, B, pooled, saved, precision, st);
+    int rc = launch_trunk(params, prepared, states, x, open_mask, B, pooled, saved, precision, st);
     if (rc) return rc;
-    return launch_heads(params, pooled, B, policy, value, legal_mask, saved, precision, st);
+    return launch_heads(params, prepared, pooled, B, policy, value, legal_mask, saved, precision, st);
 }
 
 extern "C" int64_t aq_param_count(void) { return kNumParams; }
@@ -364,21 +365,21 @@ extern "C" int aq_gnn_forward(const float *params, const AqState *states, const 
         cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&scratch), (size_t)B * kH * sizeof(float), st);
         if (e != cudaSuccess) return aq_set_error((int)e, "aq_gnn_forward(cudaMallocAsync)");
     }
-    int rc = aq_gnn_forward_impl(params, states, x, open_mask, B, policy, value, saved, scratch, nullptr, precision, st);
+    int rc = aq_gnn_forward_impl(params, nullptr, states, x, open_mask, B, policy, value, saved, scratch, nullptr, precision, st);
     if (scratch) cudaFreeAsync(scratch, st);
     return rc;
 }
 
 extern "C" int64_t aq_leaf_eval_ws_floats(int64_t B) { return B * kH; }
 
-extern "C" int aq_leaf_eval(const float *params, const AqState *states, int64_t B, float *priors, float *value,
-                            uint32_t *mask, uint8_t *pawn, float *workspace, int precision, void *stream) {
+extern "C" int aq_leaf_eval(const float *params, const void *prepared, const AqState *states, int64_t B, float *priors,
+                            float *value, uint32_t *mask, uint8_t *pawn, float *workspace, int precision, void *stream) {
     if (B < 0 || !params || (B > 0 && (!states || !priors || !value || !mask || !pawn || !workspace)))
         return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval");
     if (B == 0) return 0;
     int rc = aq_legal_mask(states, B, mask, pawn, stream);
     if (rc) return rc;
-    return aq_gnn_forward_impl(params, states, nullptr, nullptr, B, priors, value, nullptr, workspace, mask, precision,
+    return aq_gnn_forward_impl(params, prepared, states, nullptr, nullptr, B, priors, value, nullptr, workspace, mask, precision,
                                reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -419,7 +420,7 @@ extern "C" int aq_host_ctx_destroy(void *ctx) {
     return 0;
 }
 
-extern "C" int aq_leaf_eval_host(const float *params, const AqState *states_host, int64_t B, float *priors_host,
+extern "C" int aq_leaf_eval_host(const float *params, const void *prepared, const AqState *states_host, int64_t B, float *priors_host,
                                  float *value_host, uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws,
                                  int precision, void *host_ctx, void *stream) {
     if (B < 0 || !params || (B > 0 && (!states_host || !priors_host || !value_host || !dev_ws)))
@@ -450,7 +451,7 @@ extern "C" int aq_leaf_eval_host(const float *params, const AqState *states_host
         cudaStream_t cs = nchunk > 1 ? ctx->s[c & 1] : st;
         e = cudaMemcpyAsync(d_states + lo, states_host + lo, (size_t)n * sizeof(AqState), cudaMemcpyHostToDevice, cs);
         if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(H2D)");
-        int rc = aq_leaf_eval(params, d_states + lo, n, d_priors + lo * kP, d_value + lo, d_mask + lo * 8, d_pawn + lo * 8,
+        int rc = aq_leaf_eval(params, prepared, d_states + lo, n, d_priors + lo * kP, d_value + lo, d_mask + lo * 8, d_pawn + lo * 8,
                               d_pooled + lo * kH, precision, cs);
         if (rc) return rc;
         e = cudaMemcpyAsync(priors_host + lo * kP, d_priors + lo * kP, (size_t)n * kP * 4, cudaMemcpyDeviceToHost, cs);

@@ -20,6 +20,7 @@
 //   * rows 81..95 of the X tile are never written: accumulator column n depends only on X row n, and
 //     columns >= 81 are never read (the stencil is unrolled, out-of-board neighbours do not exist in
 //     the code).
+#include <cstddef>
 #include <cstdlib>
 #include <cuda_bf16.h>
 #include "gnn_fp32.cuh"
@@ -58,6 +59,7 @@ struct TcSmem {
     uint32_t tmem_base;
 };
 static_assert(sizeof(TcSmem<5>) + 1024 <= 227 * 1024, "TcSmem exceeds shared memory");
+static_assert(offsetof(TcSmem<5>, w3) == kPrepW3 && offsetof(TcSmem<5>, w1) == kPrepW1, "prepared layout must match the shared-memory layout");
 static_assert(5 * kNodesPad <= (int)kTmemCols, "TMEM columns");
 
 // Accumulator column c of the current layer: columns 0..31 / 64..95 live in za (reloaded once), 32..63 in zb.
@@ -69,37 +71,44 @@ static_assert(5 * kNodesPad <= (int)kTmemCols, "TMEM columns");
 // [B][16][96] behind them, and the A_hat coefficients [B][81][4] in the coef region.
 template <int kGroups, bool kSave>
 __global__ void __launch_bounds__(kGroups * kGroupThreads, 1)
-gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restrict__ states, int64_t B,
-                      float *__restrict__ pooled_out, float *__restrict__ saved) {
+gcn_forward_tc_kernel(const float *__restrict__ params, const unsigned char *__restrict__ prepared,
+                      const AqState *__restrict__ states, int64_t B, float *__restrict__ pooled_out,
+                      float *__restrict__ saved) {
     constexpr int kTcThreads = kGroups * kGroupThreads;
     extern __shared__ unsigned char smem_raw[];
     TcSmem<kGroups> &sm = *reinterpret_cast<TcSmem<kGroups> *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int gtid = threadIdx.x;
     const int grp = gtid / kGroupThreads, tid = gtid % kGroupThreads;  // tid = feature = TMEM lane
 
-    for (int c = gtid; c < 2 * 128 * 16; c += kTcThreads) {  // both 128x128 weight tiles, 16-byte chunks
-        const int which = c >> 11, cc = c & 2047;
-        const int n = cc >> 4, j = cc & 15;
-        const float *W = params + (which ? kOffW3 : kOffW2);
-        const float4 lo = __ldg(reinterpret_cast<const float4 *>(W + n * kH + j * 8));
-        const float4 hi = __ldg(reinterpret_cast<const float4 *>(W + n * kH + j * 8) + 1);
-        uint4 v;
-        v.x = pack_bf16(lo.x, lo.y); v.y = pack_bf16(lo.z, lo.w);
-        v.z = pack_bf16(hi.x, hi.y); v.w = pack_bf16(hi.z, hi.w);
-        *reinterpret_cast<uint4 *>((which ? sm.w3 : sm.w2) + sw128_chunk(n, j, kWKBlock)) = v;
-    }
-    if (gtid < kH) {  // layer-1 weight operand: [W1 (6) | W1 (6) | b1_hi | b1_lo | 0 | 0]
-        const int n = gtid;
-        float w[kF];
-#pragma unroll
-        for (int f = 0; f < kF; ++f) w[f] = __ldg(params + kOffW1 + n * kF + f);
-        const float bias = __ldg(params + kOffB1 + n);
-        const float bias_hi = __bfloat162float(__float2bfloat16_rn(bias));
-        uint4 c0, c1;
-        c0.x = pack_bf16(w[0], w[1]); c0.y = pack_bf16(w[2], w[3]); c0.z = pack_bf16(w[4], w[5]); c0.w = pack_bf16(w[0], w[1]);
-        c1.x = pack_bf16(w[2], w[3]); c1.y = pack_bf16(w[4], w[5]); c1.z = pack_bf16(bias_hi, bias - bias_hi); c1.w = 0u;
-        *reinterpret_cast<uint4 *>(sm.w1 + sw32_chunk(n, 0)) = c0;
-        *reinterpret_cast<uint4 *>(sm.w1 + sw32_chunk(n, 1)) = c1;
+    if (prepared) {  // operand tiles were built once by aq_prepare_inference: w2 | w3 | w1 are contiguous in both places
+        const uint4 *src = reinterpret_cast<const uint4 *>(prepared);
+        uint4 *dst = reinterpret_cast<uint4 *>(sm.w2);
+        for (int c = gtid; c < (int)(kPrepHeadB1 / 16); c += kTcThreads) dst[c] = __ldg(src + c);
+    } else {
+        for (int c = gtid; c < 2 * 128 * 16; c += kTcThreads) {  // both 128x128 weight tiles, 16-byte chunks
+            const int which = c >> 11, cc = c & 2047;
+            const int n = cc >> 4, j = cc & 15;
+            const float *W = params + (which ? kOffW3 : kOffW2);
+            const float4 lo = __ldg(reinterpret_cast<const float4 *>(W + n * kH + j * 8));
+            const float4 hi = __ldg(reinterpret_cast<const float4 *>(W + n * kH + j * 8) + 1);
+            uint4 v;
+            v.x = pack_bf16(lo.x, lo.y); v.y = pack_bf16(lo.z, lo.w);
+            v.z = pack_bf16(hi.x, hi.y); v.w = pack_bf16(hi.z, hi.w);
+            *reinterpret_cast<uint4 *>((which ? sm.w3 : sm.w2) + sw128_chunk(n, j, kWKBlock)) = v;
+        }
+        if (gtid < kH) {  // layer-1 weight operand: [W1 (6) | W1 (6) | b1_hi | b1_lo | 0 | 0]
+            const int n = gtid;
+            float w[kF];
+    #pragma unroll
+            for (int f = 0; f < kF; ++f) w[f] = __ldg(params + kOffW1 + n * kF + f);
+            const float bias = __ldg(params + kOffB1 + n);
+            const float bias_hi = __bfloat162float(__float2bfloat16_rn(bias));
+            uint4 c0, c1;
+            c0.x = pack_bf16(w[0], w[1]); c0.y = pack_bf16(w[2], w[3]); c0.z = pack_bf16(w[4], w[5]); c0.w = pack_bf16(w[0], w[1]);
+            c1.x = pack_bf16(w[2], w[3]); c1.y = pack_bf16(w[4], w[5]); c1.z = pack_bf16(bias_hi, bias - bias_hi); c1.w = 0u;
+            *reinterpret_cast<uint4 *>(sm.w1 + sw32_chunk(n, 0)) = c0;
+            *reinterpret_cast<uint4 *>(sm.w1 + sw32_chunk(n, 1)) = c1;
+        }
     }
     if (gtid < kGroups) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&sm.mbar[gtid])) : "memory");
@@ -312,8 +321,8 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const AqState *__restric
 }  // namespace
 
 template <int kGroups>
-static int launch_tc(const float *params, const AqState *states, int64_t B, float *pooled, float *saved, int sms,
-                     cudaStream_t st) {
+static int launch_tc(const float *params, const unsigned char *prepared, const AqState *states, int64_t B, float *pooled,
+                     float *saved, int sms, cudaStream_t st) {
     const size_t smem = sizeof(TcSmem<kGroups>) + 1024;
     const int64_t want = (B + kGroups - 1) / kGroups;
     const unsigned grid = (unsigned)(want < sms ? want : sms);
@@ -321,17 +330,19 @@ static int launch_tc(const float *params, const AqState *states, int64_t B, floa
     if (saved) {
         e = cudaFuncSetAttribute(gcn_forward_tc_kernel<kGroups, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return aq_set_error((int)e, "gcn_forward_tc smem");
-        gcn_forward_tc_kernel<kGroups, true><<<grid, kGroups * kGroupThreads, smem, st>>>(params, states, B, pooled, saved);
+        gcn_forward_tc_kernel<kGroups, true><<<grid, kGroups * kGroupThreads, smem, st>>>(params, prepared, states, B, pooled, saved);
     } else {
         e = cudaFuncSetAttribute(gcn_forward_tc_kernel<kGroups, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return aq_set_error((int)e, "gcn_forward_tc smem");
-        gcn_forward_tc_kernel<kGroups, false><<<grid, kGroups * kGroupThreads, smem, st>>>(params, states, B, pooled, nullptr);
+        gcn_forward_tc_kernel<kGroups, false><<<grid, kGroups * kGroupThreads, smem, st>>>(params, prepared, states, B, pooled, nullptr);
     }
     return aq_check_launch("gcn_forward_tc_kernel");
 }
 
 // saved == nullptr: inference.  saved != nullptr: training forward (activations kept for aq_gnn_backward, precision 1).
-int aq_gcn_forward_tc(const float *params, const AqState *states, int64_t B, float *pooled, float *saved, cudaStream_t st) {
+int aq_gcn_forward_tc(const float *params, const void *prepared_v, const AqState *states, int64_t B, float *pooled, float *saved,
+                      cudaStream_t st) {
+    const unsigned char *prepared = reinterpret_cast<const unsigned char *>(prepared_v);
     static int sms = 0, groups = 0;
     if (sms == 0) {
         int dev = 0;
@@ -341,7 +352,64 @@ int aq_gcn_forward_tc(const float *params, const AqState *states, int64_t B, flo
         const char *env = getenv("AQ_TC_GROUPS");  // tuning knob: boards in flight per SM (3, 4 or 5)
         groups = env ? atoi(env) : 5;
     }
-    if (saved || groups == 3) return launch_tc<3>(params, states, B, pooled, saved, sms, st);  // the save variant needs the registers
-    if (groups == 4) return launch_tc<4>(params, states, B, pooled, saved, sms, st);
-    return launch_tc<5>(params, states, B, pooled, saved, sms, st);
+    if (saved || groups == 3) return launch_tc<3>(params, prepared, states, B, pooled, saved, sms, st);  // the save variant needs the registers
+    if (groups == 4) return launch_tc<4>(params, prepared, states, B, pooled, saved, sms, st);
+    return launch_tc<5>(params, prepared, states, B, pooled, saved, sms, st);
+}
+
+// ---- aq_prepare_inference: fp32 parameters -> the bf16 operand tiles of the inference kernels ---------------------
+namespace {
+__global__ void prepare_inference_kernel(const float *__restrict__ params, unsigned char *__restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte output chunk per thread
+    auto load8 = [&](const float *p, bool aligned, float *f) {
+        if (aligned) {
+            const float4 lo = __ldg(reinterpret_cast<const float4 *>(p)), hi = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+            f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __ldg(p + e);
+        }
+    };
+    float f[8];
+    if (c < 4096) {  // trunk W2 / W3
+        const int which = c >> 11, cc = c & 2047, n = cc >> 4, j = cc & 15;
+        load8(params + (which ? kOffW3 : kOffW2) + n * kH + j * 8, true, f);
+        *reinterpret_cast<uint4 *>(out + (which ? kPrepW3 : kPrepW2) + sw128_chunk(n, j, kWKBlock)) = pack8_bf16(f);
+    } else if (c < 4096 + 128) {  // trunk layer-1 operand [W1 | W1 | b1_hi | b1_lo | 0 | 0]
+        const int n = c - 4096;
+        float w[kF];
+#pragma unroll
+        for (int k = 0; k < kF; ++k) w[k] = __ldg(params + kOffW1 + n * kF + k);
+        const float bias = __ldg(params + kOffB1 + n);
+        const float bias_hi = __bfloat162float(__float2bfloat16_rn(bias));
+        uint4 c0, c1;
+        c0.x = pack_bf16(w[0], w[1]); c0.y = pack_bf16(w[2], w[3]); c0.z = pack_bf16(w[4], w[5]); c0.w = pack_bf16(w[0], w[1]);
+        c1.x = pack_bf16(w[2], w[3]); c1.y = pack_bf16(w[4], w[5]); c1.z = pack_bf16(bias_hi, bias - bias_hi); c1.w = 0u;
+        *reinterpret_cast<uint4 *>(out + kPrepW1 + sw32_chunk(n, 0)) = c0;
+        *reinterpret_cast<uint4 *>(out + kPrepW1 + sw32_chunk(n, 1)) = c1;
+    } else if (c < 4096 + 128 + 2048) {  // heads B1: rows 0..63 = Wp0, 64..127 = Wv0 (Wv0 is not 16-byte aligned)
+        const int cc = c - (4096 + 128), n = cc >> 4, j = cc & 15;
+        if (n < kHH) load8(params + kOffWP0 + n * kH + j * 8, true, f);
+        else load8(params + kOffWV0 + (n - kHH) * kH + j * 8, false, f);
+        *reinterpret_cast<uint4 *>(out + kPrepHeadB1 + sw128_chunk(n, j, kWKBlock)) = pack8_bf16(f);
+    } else if (c < 4096 + 128 + 2048 + 224 * 8) {  // heads B2 = Wp2 [209][64] padded to 224 rows
+        const int cc = c - (4096 + 128 + 2048), n = cc >> 3, j = cc & 7;
+        if (n < kP) load8(params + kOffWP2 + n * kHH + j * 8, true, f);
+        else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        }
+        *reinterpret_cast<uint4 *>(out + kPrepHeadB2 + sw128_chunk(n, j, kWKBlock)) = pack8_bf16(f);
+    }
+}
+}  // namespace
+
+extern "C" int64_t aq_prepared_bytes(void) { return kPrepBytes; }
+
+extern "C" int aq_prepare_inference(const float *params, void *prepared, void *stream) {
+    if (!params || !prepared) return aq_set_error(AQ_ERR_ARG, "aq_prepare_inference");
+    const int chunks = 4096 + 128 + 2048 + 224 * 8;
+    prepare_inference_kernel<<<(chunks + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        params, reinterpret_cast<unsigned char *>(prepared));
+    return aq_check_launch("prepare_inference_kernel");
 }

@@ -7,9 +7,11 @@
 //   GEMM 2  [128 boards x 64] x Wp2^T (209 rows padded to 224) -> logits in TMEM
 //   epilogue 2: softmax over the thread's own row straight from TMEM (three passes over 7 column
 //   blocks), optionally restricted to the legal mask and renormalised (BaseNetwork.predict).
+#include <cstddef>
 #include <cuda_bf16.h>
 #include "aq_common.cuh"
 #include "gnn_layout.cuh"
+#include "tc_common.cuh"
 
 using namespace aq;
 
@@ -32,6 +34,9 @@ struct HtSmem {
     unsigned long long mbar;
     uint32_t tmem_base;
 };
+static_assert(aqtc::kPrepHeadB2 - aqtc::kPrepHeadB1 == sizeof(HtSmem::b1) && aqtc::kPrepBytes - aqtc::kPrepHeadB2 == sizeof(HtSmem::b2) &&
+                  offsetof(HtSmem, b2) == sizeof(HtSmem::b1),
+              "prepared layout must match the shared-memory layout");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t sw128(int row, int j) {  // 16-byte chunk j (0..15) of row
@@ -87,8 +92,9 @@ __device__ __forceinline__ uint4 pack8(const float *f) {
 
 template <bool kLegal>
 __global__ void __launch_bounds__(kHtThreads)
-heads_forward_tc_kernel(const float *__restrict__ params, const float *__restrict__ pooled, int64_t B,
-                        float *__restrict__ policy, float *__restrict__ value, const uint32_t *__restrict__ mask) {
+heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *__restrict__ prepared,
+                        const float *__restrict__ pooled, int64_t B, float *__restrict__ policy,
+                        float *__restrict__ value, const uint32_t *__restrict__ mask) {
     extern __shared__ unsigned char smem_raw[];
     HtSmem &sm = *reinterpret_cast<HtSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -96,31 +102,37 @@ heads_forward_tc_kernel(const float *__restrict__ params, const float *__restric
     const int64_t b0 = (int64_t)blockIdx.x * kTile;
 
     // ---- operands -> bf16 swizzled tiles ---------------------------------------------------------
-    for (int c = tid; c < 128 * 16; c += kHtThreads) {  // B1 rows 0..63 = Wp0, 64..127 = Wv0 (each [64][128])
-        const int n = c >> 4, j = c & 15;
-        float f[8];
-        if (n < kHH) {
-            const float4 lo = __ldg(reinterpret_cast<const float4 *>(params + kOffWP0 + n * kH + j * 8));
-            const float4 hi = __ldg(reinterpret_cast<const float4 *>(params + kOffWP0 + n * kH + j * 8) + 1);
-            f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
-        } else {  // kOffWV0 is not 16-byte aligned: scalar loads
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __ldg(params + kOffWV0 + (n - kHH) * kH + j * 8 + e);
+    if (prepared) {  // b1 | b2 are contiguous here and in the prepared buffer (aq_prepare_inference)
+        const uint4 *src = reinterpret_cast<const uint4 *>(prepared + aqtc::kPrepHeadB1);
+        uint4 *dst = reinterpret_cast<uint4 *>(sm.b1);
+        for (int c = tid; c < (int)((2 * kKBlock + kNPad * 128) / 16); c += kHtThreads) dst[c] = __ldg(src + c);
+    } else {
+        for (int c = tid; c < 128 * 16; c += kHtThreads) {  // B1 rows 0..63 = Wp0, 64..127 = Wv0 (each [64][128])
+            const int n = c >> 4, j = c & 15;
+            float f[8];
+            if (n < kHH) {
+                const float4 lo = __ldg(reinterpret_cast<const float4 *>(params + kOffWP0 + n * kH + j * 8));
+                const float4 hi = __ldg(reinterpret_cast<const float4 *>(params + kOffWP0 + n * kH + j * 8) + 1);
+                f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+            } else {  // kOffWV0 is not 16-byte aligned: scalar loads
+    #pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = __ldg(params + kOffWV0 + (n - kHH) * kH + j * 8 + e);
+            }
+            *reinterpret_cast<uint4 *>(sm.b1 + sw128(n, j)) = pack8(f);
         }
-        *reinterpret_cast<uint4 *>(sm.b1 + sw128(n, j)) = pack8(f);
-    }
-    for (int c = tid; c < kNPad * 8; c += kHtThreads) {  // B2 = Wp2 [209][64], rows >= 209 are zero
-        const int n = c >> 3, j = c & 7;
-        float f[8];
-        if (n < kP) {
-            const float4 lo = __ldg(reinterpret_cast<const float4 *>(params + kOffWP2 + n * kHH + j * 8));
-            const float4 hi = __ldg(reinterpret_cast<const float4 *>(params + kOffWP2 + n * kHH + j * 8) + 1);
-            f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        for (int c = tid; c < kNPad * 8; c += kHtThreads) {  // B2 = Wp2 [209][64], rows >= 209 are zero
+            const int n = c >> 3, j = c & 7;
+            float f[8];
+            if (n < kP) {
+                const float4 lo = __ldg(reinterpret_cast<const float4 *>(params + kOffWP2 + n * kHH + j * 8));
+                const float4 hi = __ldg(reinterpret_cast<const float4 *>(params + kOffWP2 + n * kHH + j * 8) + 1);
+                f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+            } else {
+    #pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = 0.f;
+            }
+            *reinterpret_cast<uint4 *>(sm.b2 + sw128(n, j)) = pack8(f);
         }
-        *reinterpret_cast<uint4 *>(sm.b2 + sw128(n, j)) = pack8(f);
     }
     for (int c = tid; c < kTile * 16; c += kHtThreads) {  // A1 = pooled rows of this tile (zeros past B)
         const int r = c >> 4, j = c & 15;
@@ -280,19 +292,20 @@ heads_forward_tc_kernel(const float *__restrict__ params, const float *__restric
 
 }  // namespace
 
-int aq_heads_forward_tc(const float *params, const float *pooled, int64_t B, float *policy, float *value,
-                        const uint32_t *legal_mask, cudaStream_t st) {
+int aq_heads_forward_tc(const float *params, const void *prepared_v, const float *pooled, int64_t B, float *policy,
+                        float *value, const uint32_t *legal_mask, cudaStream_t st) {
+    const unsigned char *prepared = reinterpret_cast<const unsigned char *>(prepared_v);
     const size_t smem = sizeof(HtSmem) + 1024;
     const unsigned grid = (unsigned)((B + kTile - 1) / kTile);
     cudaError_t e;
     if (legal_mask) {
         e = cudaFuncSetAttribute(heads_forward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return aq_set_error((int)e, "heads_forward_tc smem");
-        heads_forward_tc_kernel<true><<<grid, kHtThreads, smem, st>>>(params, pooled, B, policy, value, legal_mask);
+        heads_forward_tc_kernel<true><<<grid, kHtThreads, smem, st>>>(params, prepared, pooled, B, policy, value, legal_mask);
     } else {
         e = cudaFuncSetAttribute(heads_forward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return aq_set_error((int)e, "heads_forward_tc smem");
-        heads_forward_tc_kernel<false><<<grid, kHtThreads, smem, st>>>(params, pooled, B, policy, value, nullptr);
+        heads_forward_tc_kernel<false><<<grid, kHtThreads, smem, st>>>(params, prepared, pooled, B, policy, value, nullptr);
     }
     return aq_check_launch("heads_forward_tc_kernel");
 }

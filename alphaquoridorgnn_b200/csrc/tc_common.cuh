@@ -86,4 +86,13 @@ __device__ __forceinline__ uint4 pack8_bf16(const float *f) {
     return v;
 }
 
+// "Prepared" inference weights: the bf16 operand tiles exactly as the kernels keep them in shared memory, built
+// once by aq_prepare_inference so that every CTA only copies them (no per-CTA fp32 -> bf16 conversion).
+constexpr uint32_t kPrepW2 = 0;                    // trunk W2 tile  [128][128] K-major SWIZZLE_128B   (32 KB)
+constexpr uint32_t kPrepW3 = 32768;                // trunk W3 tile                                    (32 KB)
+constexpr uint32_t kPrepW1 = 65536;                // trunk layer-1 operand [128][16] SWIZZLE_32B      ( 4 KB)
+constexpr uint32_t kPrepHeadB1 = 69632;            // heads [Wp0 ; Wv0] tile [128][128]                (32 KB)
+constexpr uint32_t kPrepHeadB2 = 102400;           // heads Wp2 tile [224][64]                         (28 KB)
+constexpr uint32_t kPrepBytes = 131072;
+
 }  // namespace aqtc

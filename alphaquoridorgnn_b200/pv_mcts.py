@@ -66,11 +66,11 @@ class BatchedMCTS:
             }
         return self._buf[G]
 
-    def _step_network(self, ws, G, max_nodes, buf, flat, prec, st):
+    def _step_network(self, ws, G, max_nodes, buf, flat, prep, prec, st):
         """One simulation for all games with the network evaluator: three library calls, five kernels."""
         L, P = _lib.load(), _lib.ptr
         _lib.check(L.aq_mcts_select(P(ws), G, max_nodes, self.c_puct, P(buf["leaf"]), P(buf["kind"]), st), "aq_mcts_select")
-        _lib.check(L.aq_leaf_eval(P(flat), P(buf["leaf"]), G, P(buf["priors"]), P(buf["value"]), P(buf["mask"]), P(buf["pawn"]),
+        _lib.check(L.aq_leaf_eval(P(flat), P(prep), P(buf["leaf"]), G, P(buf["priors"]), P(buf["value"]), P(buf["mask"]), P(buf["pawn"]),
                                   P(buf["pooled"]), prec, st), "aq_leaf_eval")
         _lib.check(L.aq_mcts_expand_backup(P(ws), G, max_nodes, P(buf["priors"]), P(buf["value"]), P(buf["mask"]),
                                            P(buf["pawn"]), st), "aq_mcts_expand_backup")
@@ -95,16 +95,18 @@ class BatchedMCTS:
                 from .pv_network_gnn import PRECISIONS
                 flat = self.model.flat_parameters()
                 prec = PRECISIONS[self.model.precision]
-                key = (G, max_nodes, flat.data_ptr(), prec)
+                # bf16 operand tiles, refreshed in place if the parameters changed since the last search
+                prep = self.model.prepared_weights() if prec == 1 else None
+                key = (G, max_nodes, flat.data_ptr(), prep.data_ptr() if prep is not None else 0, prec)
                 graph = self._graphs.get(key) if self.use_graph else None
                 if self.use_graph and graph is None:
                     try:
-                        self._step_network(ws, G, max_nodes, buf, flat, prec, st)  # warm-up outside capture (= simulation 1)
+                        self._step_network(ws, G, max_nodes, buf, flat, prep, prec, st)  # warm-up outside capture (= simulation 1)
                         done = 1
                         torch.cuda.synchronize(dev)
                         g = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g):
-                            self._step_network(ws, G, max_nodes, buf, flat, prec, _lib.stream_ptr(dev))
+                            self._step_network(ws, G, max_nodes, buf, flat, prep, prec, _lib.stream_ptr(dev))
                         if len(self._graphs) >= 16:  # self-play shrinks G as games end: keep the cache bounded
                             self._graphs.clear()
                         self._graphs[key] = graph = g
@@ -117,7 +119,7 @@ class BatchedMCTS:
                     if graph is not None:
                         graph.replay()
                     else:
-                        self._step_network(ws, G, max_nodes, buf, flat, prec, st)
+                        self._step_network(ws, G, max_nodes, buf, flat, prep, prec, st)
             else:
                 for _ in range(sims):
                     _lib.check(L.aq_mcts_select(P(ws), G, max_nodes, self.c_puct, P(buf["leaf"]), P(buf["kind"]), st), "aq_mcts_select")

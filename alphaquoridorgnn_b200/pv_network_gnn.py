@@ -133,6 +133,9 @@ class GraphPolicyValueNetwork(nn.Module):
         self.precision = "fp32"  # inference arithmetic: "fp32" (FFMA) or "bf16" (tcgen05 tensor cores)
         self.train_precision = "fp32"  # forward+backward under autograd: "fp32", or "bf16" (tcgen05 trunk, fp32 accumulate)
         self._flat = None
+        self._prepared = None      # bf16 operand tiles of the tensor-core inference kernels (aq_prepare_inference)
+        self._prepared_key = None
+        self._weights_epoch = 0    # bumped by writers that update the flat buffer through raw pointers (FlatTrainer)
 
     def ordered_parameters(self):
         named = dict(self.named_parameters())
@@ -163,6 +166,27 @@ class GraphPolicyValueNetwork(nn.Module):
                 off += n
             self._flat = flat
         return flat
+
+    def mark_weights_changed(self):
+        """Tell the network its flat buffer was modified behind torch's back (raw-pointer Adam step)."""
+        self._weights_epoch += 1
+
+    def prepared_weights(self):
+        """Device buffer with the inference weights in the layout the tensor-core kernels keep in shared
+        memory, rebuilt (one small kernel) whenever the parameters changed.  The counterpart of the
+        reference's one-time inference preparation (BaseNetwork.py:22-32)."""
+        flat = self.flat_parameters()
+        _lib.require_cuda(flat, "model parameters")
+        key = (flat.data_ptr(), flat._version, self._weights_epoch, tuple(p._version for p in self.ordered_parameters()))
+        if self._prepared is None or self._prepared.device != flat.device or key != self._prepared_key:
+            L = _lib.load()
+            if self._prepared is None or self._prepared.device != flat.device:
+                self._prepared = torch.empty((L.aq_prepared_bytes(),), dtype=torch.uint8, device=flat.device)
+            with torch.cuda.device(flat.device):
+                _lib.check(L.aq_prepare_inference(_lib.ptr(flat), _lib.ptr(self._prepared), _lib.stream_ptr(flat.device)),
+                           "aq_prepare_inference")
+            self._prepared_key = key
+        return self._prepared
 
     def _prepare(self, x, edge_index, batch):
         """-> (packed, x, open_mask): either packed states or explicit graph inputs on the device."""
@@ -232,6 +256,7 @@ class GNNNetwork(GraphPolicyValueNetwork):
         self.eval()
         self.to('cuda')
         self.flat_parameters()
+        self.prepared_weights()
         self.optimised_model = self
 
     def preprocess_input(self, game_state_arrays):
@@ -261,8 +286,9 @@ class GNNNetwork(GraphPolicyValueNetwork):
         mask = torch.empty((B, 8), dtype=torch.int32, device=dev)
         pawn = torch.empty((B, 8), dtype=torch.uint8, device=dev)
         ws = torch.empty((max(1, L.aq_leaf_eval_ws_floats(B)),), dtype=torch.float32, device=dev)
+        prep = self.prepared_weights() if self.precision == "bf16" else None
         with torch.cuda.device(dev):
-            _lib.check(L.aq_leaf_eval(_lib.ptr(flat), _lib.ptr(packed), B, _lib.ptr(priors), _lib.ptr(value),
+            _lib.check(L.aq_leaf_eval(_lib.ptr(flat), _lib.ptr(prep), _lib.ptr(packed), B, _lib.ptr(priors), _lib.ptr(value),
                                       _lib.ptr(mask), _lib.ptr(pawn), _lib.ptr(ws), PRECISIONS[self.precision],
                                       _lib.stream_ptr(dev)), "aq_leaf_eval")
         return {"priors": priors, "value": value, "mask": mask, "pawn": pawn, "packed": packed}

@@ -90,6 +90,8 @@ class FlatTrainer:
             _lib.check(L.aq_adam_step(P(self.flat), P(self.grads), P(self.exp_avg), P(self.exp_avg_sq), self.flat.numel(),
                                       self.step_count, self.lr * lr_scale, self.betas[0], self.betas[1], self.eps, 1.0, st),
                        "aq_adam_step")
+        if hasattr(self.model, "mark_weights_changed"):
+            self.model.mark_weights_changed()  # the flat buffer was written through a raw pointer
         return self.loss
 
 

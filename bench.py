@@ -188,6 +188,8 @@ def run_ours(args, rank, world, local_rank):
     net = GNNNetwork().to(dev).eval()
     net.precision = args.precision
     flat = net.flat_parameters()
+    # inference weights prepared once, as prep_for_inference does (the weights do not change between evaluations)
+    prep = net.prepared_weights() if prec == 1 else None
     nb = 4
     allpos = positions.random_positions(nb * B, seed=1 + rank, games=8192, device=dev)
     batches = [allpos[i * B:(i + 1) * B].contiguous() for i in range(nb)]
@@ -206,7 +208,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     def step(i):
-        _lib.check(L.aq_leaf_eval(P(flat), P(batches[i % nb]), B, P(priors), P(value), P(mask), P(pawn), P(pooled), prec, st),
+        _lib.check(L.aq_leaf_eval(P(flat), P(prep), P(batches[i % nb]), B, P(priors), P(value), P(mask), P(pawn), P(pooled), prec, st),
                    "aq_leaf_eval")
 
     def timed(fn, n, warm):
@@ -237,10 +239,10 @@ def run_ours(args, rank, world, local_rank):
         _lib.check(L.aq_legal_mask(P(batches[i % nb]), B, P(mask), P(pawn), st), "aq_legal_mask")
 
     def k_trunk(i):
-        _lib.check(L.aq_gcn_trunk_forward(P(flat), P(batches[i % nb]), B, P(pooled), prec, st), "aq_gcn_trunk_forward")
+        _lib.check(L.aq_gcn_trunk_forward(P(flat), P(prep), P(batches[i % nb]), B, P(pooled), prec, st), "aq_gcn_trunk_forward")
 
     def k_heads(i):
-        _lib.check(L.aq_heads_forward(P(flat), P(pooled), B, P(priors), P(value), P(mask), prec, st), "aq_heads_forward")
+        _lib.check(L.aq_heads_forward(P(flat), P(prep), P(pooled), B, P(priors), P(value), P(mask), prec, st), "aq_heads_forward")
 
     kms = {"legal_mask_kernel": timed(k_legal, K, 2), "gcn_forward_kernel": timed(k_trunk, K, 2),
            "heads_forward_kernel": timed(k_heads, K, 2)}
@@ -280,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
     _lib.check(L.aq_host_ctx_create(ctypes.byref(hctx)), "aq_host_ctx_create")
 
     def e2e_step(i):
-        _lib.check(L.aq_leaf_eval_host(P(flat), P(hst[i % nb]), B, P(h_pri), P(h_val), P(h_msk), P(h_pwn), P(ws), prec, hctx, st),
+        _lib.check(L.aq_leaf_eval_host(P(flat), P(prep), P(hst[i % nb]), B, P(h_pri), P(h_val), P(h_msk), P(h_pwn), P(ws), prec, hctx, st),
                    "aq_leaf_eval_host")
 
     for i in range(3):

@@ -109,10 +109,19 @@ int aq_gnn_forward(const float *params, const AqState *states, const float *x, c
  *   aq_gcn_trunk_forward: graph build + 3 GCN layers + global_mean_pool -> pooled [B,128]
  *   aq_heads_forward:     policy/value MLPs on pooled; legal_mask (may be NULL) applies the
  *                         predict() restriction + renormalisation */
-int aq_gcn_trunk_forward(const float *params, const AqState *states, int64_t B, float *pooled, int precision,
-                         void *stream);
-int aq_heads_forward(const float *params, const float *pooled, int64_t B, float *policy, float *value,
-                     const uint32_t *legal_mask, int precision, void *stream);
+int aq_gcn_trunk_forward(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled,
+                         int precision, void *stream);
+int aq_heads_forward(const float *params, const void *prepared, const float *pooled, int64_t B, float *policy,
+                     float *value, const uint32_t *legal_mask, int precision, void *stream);
+
+/* Inference weights prepared once per parameter update (the counterpart of the reference's one-time
+ * model.eval() / TensorRT compile in BaseNetwork.py:22-32): the bf16 operand tiles of the tensor-core
+ * kernels (trunk W1/W2/W3, heads Wp0/Wv0/Wp2) in their shared-memory layout, aq_prepared_bytes() bytes.
+ * Every inference entry point takes `prepared` (may be NULL: each CTA then converts the fp32 parameters
+ * itself; ignored at precision 0).  The caller must call aq_prepare_inference again after changing
+ * params.  Biases and the fp32 value head are always read from params. */
+int64_t aq_prepared_bytes(void);
+int aq_prepare_inference(const float *params, void *prepared, void *stream);
 
 /* Backward of the above (autograd of train_network.py:93).  dpolicy [B,209], dvalue [B] are the
  * loss gradients w.r.t. the softmax / tanh outputs; grads f32[64082] is OVERWRITTEN with the
@@ -140,8 +149,9 @@ int aq_adam_step(float *params, const float *grads, float *exp_avg, float *exp_a
  *   priors [B,209]: p[a]/sum_legal p for legal a, 0 elsewhere (sum==0 -> left unnormalised, as
  *                   `policy /= sum if sum else 1`)
  *   value  [B], mask [B,8], pawn [B,8] as in aq_legal_mask. */
-int aq_leaf_eval(const float *params, const AqState *states, int64_t B, float *priors, float *value, uint32_t *mask,
-                 uint8_t *pawn, float *workspace /* aq_leaf_eval_ws_floats(B) */, int precision, void *stream);
+int aq_leaf_eval(const float *params, const void *prepared /* or NULL */, const AqState *states, int64_t B, float *priors,
+                 float *value, uint32_t *mask, uint8_t *pawn, float *workspace /* aq_leaf_eval_ws_floats(B) */,
+                 int precision, void *stream);
 int64_t aq_leaf_eval_ws_floats(int64_t B);
 
 /* Same through HOST buffers (pinned or pageable): copies states H2D, runs, copies priors/value/
@@ -152,9 +162,9 @@ int64_t aq_leaf_eval_host_ws_bytes(int64_t B);
  * processed in 4 chunks on two worker streams so that the D2H of one chunk overlaps the next chunk. */
 int aq_host_ctx_create(void **ctx);
 int aq_host_ctx_destroy(void *ctx);
-int aq_leaf_eval_host(const float *params, const AqState *states_host, int64_t B, float *priors_host,
-                      float *value_host, uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision,
-                      void *host_ctx, void *stream);
+int aq_leaf_eval_host(const float *params, const void *prepared /* or NULL */, const AqState *states_host, int64_t B,
+                      float *priors_host, float *value_host, uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws,
+                      int precision, void *host_ctx, void *stream);
 
 /* Lock-step PV-MCTS over G independent games (pv_mcts.py:20-95: Node.evaluate / next_child_node).
  * ws: device workspace of aq_mcts_ws_bytes(G, max_nodes); max_nodes >= 1 + sims * 133 never overflows.

@@ -200,7 +200,7 @@ def test_leaf_eval_host_buffers_equal_device_path(traj):
     msk = torch.empty((B, 8), dtype=torch.int32).pin_memory()
     pwn = torch.empty((B, 8), dtype=torch.uint8).pin_memory()
     ws = torch.empty((L.aq_leaf_eval_host_ws_bytes(B),), dtype=torch.uint8, device="cuda")
-    _lib.check(L.aq_leaf_eval_host(_lib.ptr(net.flat_parameters()), _lib.ptr(st), B, _lib.ptr(pri), _lib.ptr(val),
+    _lib.check(L.aq_leaf_eval_host(_lib.ptr(net.flat_parameters()), None, _lib.ptr(st), B, _lib.ptr(pri), _lib.ptr(val),
                                    _lib.ptr(msk), _lib.ptr(pwn), _lib.ptr(ws), 0, None, _lib.stream_ptr()), "aq_leaf_eval_host")
     assert torch.equal(pri, out["priors"].cpu()) and torch.equal(val, out["value"].cpu())
     assert torch.equal(msk, out["mask"].cpu()) and torch.equal(pwn, out["pawn"].cpu())
@@ -217,7 +217,7 @@ def test_leaf_eval_host_buffers_equal_device_path(traj):
     ws2 = torch.empty((L.aq_leaf_eval_host_ws_bytes(B2),), dtype=torch.uint8, device="cuda")
     ctx = ctypes.c_void_p()
     _lib.check(L.aq_host_ctx_create(ctypes.byref(ctx)), "aq_host_ctx_create")
-    _lib.check(L.aq_leaf_eval_host(_lib.ptr(net.flat_parameters()), _lib.ptr(st2), B2, _lib.ptr(pri2), _lib.ptr(val2),
+    _lib.check(L.aq_leaf_eval_host(_lib.ptr(net.flat_parameters()), None, _lib.ptr(st2), B2, _lib.ptr(pri2), _lib.ptr(val2),
                                    _lib.ptr(msk2), _lib.ptr(pwn2), _lib.ptr(ws2), 0, ctx, _lib.stream_ptr()), "aq_leaf_eval_host")
     _lib.check(L.aq_host_ctx_destroy(ctx), "aq_host_ctx_destroy")
     assert torch.equal(pri2, ref2["priors"].cpu()) and torch.equal(val2, ref2["value"].cpu())
@@ -278,6 +278,51 @@ def test_bf16_tensor_core_path_within_tolerance(traj):
     legal = qo.legal_actions_batch(rows, plies)
     assert np.array_equal(out["mask"].cpu().numpy().view(np.uint32), legal["mask"])
     assert (out["value"].cpu() - v_ref.squeeze(1)).abs().max().item() <= 5e-3
+
+
+def test_prepared_inference_weights_are_bit_identical_and_refresh(traj):
+    """aq_prepare_inference builds the same bf16 operand tiles every CTA would build itself: outputs with and
+    without `prepared` are bit-identical, and GNNNetwork refreshes the tiles after any parameter update."""
+    rows, plies = _sample_rows(traj, 700, seed=33)
+    _, net = _models(11)
+    net.eval()
+    net.precision = "bf16"
+    L, P = _lib.load(), _lib.ptr
+    packed = gl.pack_rows(torch.from_numpy(rows), torch.from_numpy(plies), "cuda")
+    B = packed.shape[0]
+    flat = net.flat_parameters()
+
+    def leaf(prep):
+        pri = torch.empty((B, 209), device="cuda"); val = torch.empty((B,), device="cuda")
+        msk = torch.empty((B, 8), dtype=torch.int32, device="cuda"); pwn = torch.empty((B, 8), dtype=torch.uint8, device="cuda")
+        ws = torch.empty((L.aq_leaf_eval_ws_floats(B),), device="cuda")
+        _lib.check(L.aq_leaf_eval(P(flat), P(prep), P(packed), B, P(pri), P(val), P(msk), P(pwn), P(ws), 1, _lib.stream_ptr()),
+                   "aq_leaf_eval")
+        return pri, val
+
+    prep = net.prepared_weights()
+    assert prep.numel() == L.aq_prepared_bytes()
+    p0, v0 = leaf(None)
+    p1, v1 = leaf(prep)
+    assert torch.equal(p0, p1) and torch.equal(v0, v1)
+    out = net.predict_batch(packed)
+    assert torch.equal(out["priors"], p0) and torch.equal(out["value"], v0)
+    # parameter update through torch (version counters) -> tiles rebuilt
+    with torch.no_grad():
+        net.gcn_layers[1].lin.weight.mul_(1.5)
+    out2 = net.predict_batch(packed)
+    p2, v2 = leaf(None)
+    assert not torch.equal(p2, p0)
+    assert torch.equal(out2["priors"], p2) and torch.equal(out2["value"], v2)
+    # raw-pointer update (FlatTrainer's Adam step) -> mark_weights_changed
+    from alphaquoridorgnn_b200.train_network import FlatTrainer
+    tr = FlatTrainer(net, lr=0.01)
+    pt = torch.full((B, 209), 1.0 / 209, device="cuda"); vt = torch.zeros((B,), device="cuda")
+    tr.step(packed, pt, vt, B)
+    out3 = net.predict_batch(packed)
+    p3, v3 = leaf(None)
+    assert not torch.equal(p3, p2)
+    assert torch.equal(out3["priors"], p3) and torch.equal(out3["value"], v3)
 
 
 def test_empty_and_tiny_batches_through_every_entry_point():
