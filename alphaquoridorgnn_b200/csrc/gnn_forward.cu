@@ -3,6 +3,7 @@
 //                             iteration, all activations resident in shared memory
 //   heads_forward_kernel    : policy / value MLPs, softmax, tanh, optional legal-action
 //                             renormalisation (BaseNetwork.predict semantics)
+#include <cstdlib>
 #include "gnn_fp32.cuh"
 
 using namespace aq;
@@ -392,16 +393,34 @@ extern "C" int64_t aq_leaf_eval_host_ws_bytes(int64_t B) {
                      align256((size_t)B * 32) + align256((size_t)B * 8) + align256((size_t)B * kH * 4));
 }
 
-// Host-side context for the pipelined host-buffer path: two worker streams and their events.  Owned by
-// the caller (aq_host_ctx_create / aq_host_ctx_destroy); no global state.
+// Host-side context for the pipelined host-buffer path: worker streams, their events, and a small cache of
+// instantiated CUDA graphs (one per distinct argument tuple).  Owned by the caller (aq_host_ctx_create /
+// aq_host_ctx_destroy); no global state.
+struct AqHostKey {
+    const void *params, *prepared, *states_host, *priors_host, *value_host, *mask_host, *pawn_host, *dev_ws;
+    int64_t B;
+    int precision;
+    bool operator==(const AqHostKey &o) const {
+        return params == o.params && prepared == o.prepared && states_host == o.states_host && priors_host == o.priors_host &&
+               value_host == o.value_host && mask_host == o.mask_host && pawn_host == o.pawn_host && dev_ws == o.dev_ws &&
+               B == o.B && precision == o.precision;
+    }
+};
+constexpr int kHostGraphSlots = 8;
 struct AqHostCtx {
     cudaStream_t s[2];
     cudaEvent_t ready, done[2];
+    AqHostKey key[kHostGraphSlots];
+    cudaGraphExec_t exec[kHostGraphSlots];
+    int n_graphs, next_slot;
+    bool graphs_ok;
 };
 
 extern "C" int aq_host_ctx_create(void **ctx) {
     if (!ctx) return aq_set_error(AQ_ERR_ARG, "aq_host_ctx_create");
     AqHostCtx *c = new AqHostCtx();
+    c->n_graphs = c->next_slot = 0;
+    c->graphs_ok = getenv("AQ_HOST_GRAPH") ? atoi(getenv("AQ_HOST_GRAPH")) != 0 : true;
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&c->s[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);
@@ -414,45 +433,46 @@ extern "C" int aq_host_ctx_create(void **ctx) {
 extern "C" int aq_host_ctx_destroy(void *ctx) {
     if (!ctx) return 0;
     AqHostCtx *c = reinterpret_cast<AqHostCtx *>(ctx);
+    for (int i = 0; i < c->n_graphs; ++i) cudaGraphExecDestroy(c->exec[i]);
     for (int i = 0; i < 2; ++i) { cudaStreamDestroy(c->s[i]); cudaEventDestroy(c->done[i]); }
     cudaEventDestroy(c->ready);
     delete c;
     return 0;
 }
 
-extern "C" int aq_leaf_eval_host(const float *params, const void *prepared, const AqState *states_host, int64_t B, float *priors_host,
-                                 float *value_host, uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws,
-                                 int precision, void *host_ctx, void *stream) {
-    if (B < 0 || !params || (B > 0 && (!states_host || !priors_host || !value_host || !dev_ws)))
-        return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host");
-    if (B == 0) return 0;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    unsigned char *p = reinterpret_cast<unsigned char *>(dev_ws);
+// Enqueues H2D -> leaf evaluation -> D2H for B states in `nchunk` chunks.  nchunk == 1: everything in order on
+// `origin`.  nchunk > 1: chunks alternate between the two worker streams (forked from / joined back into
+// `origin`), so the D2H of one chunk overlaps the kernels of the next.  Works eagerly and under stream capture.
+static int enqueue_host_pipeline(AqHostCtx *ctx, cudaStream_t origin, int nchunk, const AqHostKey &k) {
+    const int64_t B = k.B;
+    unsigned char *p = reinterpret_cast<unsigned char *>(const_cast<void *>(k.dev_ws));
     AqState *d_states = reinterpret_cast<AqState *>(p); p += align256((size_t)B * sizeof(AqState));
     float *d_priors = reinterpret_cast<float *>(p);     p += align256((size_t)B * kP * 4);
     float *d_value = reinterpret_cast<float *>(p);      p += align256((size_t)B * 4);
     uint32_t *d_mask = reinterpret_cast<uint32_t *>(p); p += align256((size_t)B * 32);
     uint8_t *d_pawn = reinterpret_cast<uint8_t *>(p);   p += align256((size_t)B * 8);
     float *d_pooled = reinterpret_cast<float *>(p);
-    AqHostCtx *ctx = reinterpret_cast<AqHostCtx *>(host_ctx);
-    // chunked so that the D2H of chunk c overlaps the H2D + kernels of chunk c+1 (two worker streams);
-    // without a context (or for small batches) everything runs in order on `stream`
-    const int nchunk = (ctx && B >= 4096) ? 4 : 1;
+    const AqState *states_host = reinterpret_cast<const AqState *>(k.states_host);
+    float *priors_host = reinterpret_cast<float *>(const_cast<void *>(k.priors_host));
+    float *value_host = reinterpret_cast<float *>(const_cast<void *>(k.value_host));
+    uint32_t *mask_host = reinterpret_cast<uint32_t *>(const_cast<void *>(k.mask_host));
+    uint8_t *pawn_host = reinterpret_cast<uint8_t *>(const_cast<void *>(k.pawn_host));
     cudaError_t e = cudaSuccess;
     if (nchunk > 1) {
-        e = cudaEventRecord(ctx->ready, st);
+        e = cudaEventRecord(ctx->ready, origin);
         for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(ctx->s[i], ctx->ready, 0);
         if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(fork)");
     }
-    const int64_t per = (B + nchunk - 1) / nchunk;
+    // chunk boundaries are multiples of 128 boards (the heads kernel works on tiles of 128)
+    const int64_t per = ((B + nchunk - 1) / nchunk + 127) / 128 * 128;
     for (int c = 0; c < nchunk; ++c) {
         const int64_t lo = (int64_t)c * per, n = (lo + per <= B ? per : B - lo);
         if (n <= 0) break;
-        cudaStream_t cs = nchunk > 1 ? ctx->s[c & 1] : st;
+        cudaStream_t cs = nchunk > 1 ? ctx->s[c & 1] : origin;
         e = cudaMemcpyAsync(d_states + lo, states_host + lo, (size_t)n * sizeof(AqState), cudaMemcpyHostToDevice, cs);
         if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(H2D)");
-        int rc = aq_leaf_eval(params, prepared, d_states + lo, n, d_priors + lo * kP, d_value + lo, d_mask + lo * 8, d_pawn + lo * 8,
-                              d_pooled + lo * kH, precision, cs);
+        int rc = aq_leaf_eval(reinterpret_cast<const float *>(k.params), k.prepared, d_states + lo, n, d_priors + lo * kP,
+                              d_value + lo, d_mask + lo * 8, d_pawn + lo * 8, d_pooled + lo * kH, k.precision, cs);
         if (rc) return rc;
         e = cudaMemcpyAsync(priors_host + lo * kP, d_priors + lo * kP, (size_t)n * kP * 4, cudaMemcpyDeviceToHost, cs);
         if (e == cudaSuccess) e = cudaMemcpyAsync(value_host + lo, d_value + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, cs);
@@ -463,10 +483,69 @@ extern "C" int aq_leaf_eval_host(const float *params, const void *prepared, cons
     if (nchunk > 1) {
         for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
             e = cudaEventRecord(ctx->done[i], ctx->s[i]);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ctx->done[i], 0);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(origin, ctx->done[i], 0);
         }
+        if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(join)");
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return 0;
+}
+
+static bool is_pinned_host(const void *ptr) {
+    if (!ptr) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Looks up / builds the instantiated graph of the pipeline for this argument tuple.  The pipeline is captured on
+// the context's own stream (the caller's stream may be the legacy default stream, which cannot be captured).
+static cudaGraphExec_t host_graph_for(AqHostCtx *ctx, int nchunk, const AqHostKey &k) {
+    for (int i = 0; i < ctx->n_graphs; ++i)
+        if (ctx->key[i] == k) return ctx->exec[i];
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    if (cudaStreamBeginCapture(ctx->s[0], cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    // inside the capture s[0] is the origin and also one of the two workers: the fork/join events keep the order
+    const int rc = enqueue_host_pipeline(ctx, ctx->s[0], nchunk, k);
+    const cudaError_t e = cudaStreamEndCapture(ctx->s[0], &graph);
+    if (rc != 0 || e != cudaSuccess || !graph) { cudaGetLastError(); if (graph) cudaGraphDestroy(graph); return nullptr; }
+    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGetLastError(); exec = nullptr; }
+    cudaGraphDestroy(graph);
+    if (!exec) return nullptr;
+    int slot;
+    if (ctx->n_graphs < kHostGraphSlots) slot = ctx->n_graphs++;
+    else { slot = ctx->next_slot; ctx->next_slot = (ctx->next_slot + 1) % kHostGraphSlots; cudaGraphExecDestroy(ctx->exec[slot]); }
+    ctx->key[slot] = k;
+    ctx->exec[slot] = exec;
+    return exec;
+}
+
+extern "C" int aq_leaf_eval_host(const float *params, const void *prepared, const AqState *states_host, int64_t B, float *priors_host,
+                                 float *value_host, uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws,
+                                 int precision, void *host_ctx, void *stream) {
+    if (B < 0 || !params || (B > 0 && (!states_host || !priors_host || !value_host || !dev_ws)))
+        return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host");
+    if (B == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    AqHostCtx *ctx = reinterpret_cast<AqHostCtx *>(host_ctx);
+    const AqHostKey k{params, prepared, states_host, priors_host, value_host, mask_host, pawn_host, dev_ws, B, precision};
+    // with a context, batches >= 4096 are chunked so that the D2H of chunk c overlaps the kernels of chunk c+1; when all
+    // host buffers are pinned the whole pipeline is one CUDA graph per argument tuple (~40 API calls -> one launch)
+    static const int env_chunks = getenv("AQ_HOST_CHUNKS") ? atoi(getenv("AQ_HOST_CHUNKS")) : 0;
+    const int nchunk = (ctx && B >= 4096) ? (env_chunks > 0 ? env_chunks : 4) : 1;
+    cudaError_t e = cudaSuccess;
+    cudaGraphExec_t exec = nullptr;
+    if (ctx && ctx->graphs_ok && is_pinned_host(states_host) && is_pinned_host(priors_host) && is_pinned_host(value_host) &&
+        is_pinned_host(mask_host) && is_pinned_host(pawn_host))
+        exec = host_graph_for(ctx, nchunk, k);
+    if (exec) {
+        e = cudaGraphLaunch(exec, st);
+        if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(graph launch)");
+    } else {
+        const int rc = enqueue_host_pipeline(ctx, st, nchunk, k);
+        if (rc) return rc;
+    }
+    e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(sync)");
     return 0;
 }

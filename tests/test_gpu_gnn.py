@@ -219,9 +219,22 @@ def test_leaf_eval_host_buffers_equal_device_path(traj):
     _lib.check(L.aq_host_ctx_create(ctypes.byref(ctx)), "aq_host_ctx_create")
     _lib.check(L.aq_leaf_eval_host(_lib.ptr(net.flat_parameters()), None, _lib.ptr(st2), B2, _lib.ptr(pri2), _lib.ptr(val2),
                                    _lib.ptr(msk2), _lib.ptr(pwn2), _lib.ptr(ws2), 0, ctx, _lib.stream_ptr()), "aq_leaf_eval_host")
-    _lib.check(L.aq_host_ctx_destroy(ctx), "aq_host_ctx_destroy")
     assert torch.equal(pri2, ref2["priors"].cpu()) and torch.equal(val2, ref2["value"].cpu())
     assert torch.equal(msk2, ref2["mask"].cpu()) and torch.equal(pwn2, ref2["pawn"].cpu())
+    # second call with the same buffers replays the cached CUDA graph of the pipeline: new contents, new results
+    st2.copy_(st2.flip(0).clone())
+    pri2.zero_(); val2.zero_(); msk2.zero_(); pwn2.zero_()
+    _lib.check(L.aq_leaf_eval_host(_lib.ptr(net.flat_parameters()), None, _lib.ptr(st2), B2, _lib.ptr(pri2), _lib.ptr(val2),
+                                   _lib.ptr(msk2), _lib.ptr(pwn2), _lib.ptr(ws2), 0, ctx, _lib.stream_ptr()), "aq_leaf_eval_host")
+    assert torch.equal(pri2, ref2["priors"].cpu().flip(0)) and torch.equal(val2, ref2["value"].cpu().flip(0))
+    assert torch.equal(msk2, ref2["mask"].cpu().flip(0)) and torch.equal(pwn2, ref2["pawn"].cpu().flip(0))
+    # pageable host buffers with a context take the eager pipeline (no graph) and give the same bytes
+    st3 = st2.clone()
+    pri3, val3 = torch.zeros((B2, 209), dtype=torch.float32), torch.zeros((B2,), dtype=torch.float32)
+    _lib.check(L.aq_leaf_eval_host(_lib.ptr(net.flat_parameters()), None, _lib.ptr(st3), B2, _lib.ptr(pri3), _lib.ptr(val3),
+                                   None, None, _lib.ptr(ws2), 0, ctx, _lib.stream_ptr()), "aq_leaf_eval_host")
+    assert torch.equal(pri3, pri2) and torch.equal(val3, val2)
+    _lib.check(L.aq_host_ctx_destroy(ctx), "aq_host_ctx_destroy")
 
 
 def test_checkpoint_interchange_and_training_step(tmp_path, traj):
