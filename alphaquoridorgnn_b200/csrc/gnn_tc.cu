@@ -339,12 +339,16 @@ static int launch_tc(const float *params, const unsigned char *prepared, const A
     return aq_check_launch("gcn_forward_tc_kernel");
 }
 
+int aq_gcn_forward_tc2(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, cudaStream_t st);  // gnn_tc2.cu
+
 // saved == nullptr: inference.  saved != nullptr: training forward (activations kept for aq_gnn_backward, precision 1).
 int aq_gcn_forward_tc(const float *params, const void *prepared_v, const AqState *states, int64_t B, float *pooled, float *saved,
                       cudaStream_t st) {
     const unsigned char *prepared = reinterpret_cast<const unsigned char *>(prepared_v);
-    static int sms = 0, groups = 0;
+    static int sms = 0, groups = 0, version = 2;
     if (sms == 0) {
+        const char *ver = getenv("AQ_TC_VERSION");  // 1 = CUDA-core stencil aggregation (this file), 2 = tensor-core aggregation (gnn_tc2.cu)
+        if (ver) version = atoi(ver);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -352,6 +356,7 @@ int aq_gcn_forward_tc(const float *params, const void *prepared_v, const AqState
         const char *env = getenv("AQ_TC_GROUPS");  // tuning knob: boards in flight per SM (3, 4 or 5)
         groups = env ? atoi(env) : 5;
     }
+    if (!saved && version == 2) return aq_gcn_forward_tc2(params, prepared_v, states, B, pooled, st);
     if (saved || groups == 3) return launch_tc<3>(params, prepared, states, B, pooled, saved, sms, st);  // the save variant needs the registers
     if (groups == 4) return launch_tc<4>(params, prepared, states, B, pooled, saved, sms, st);
     return launch_tc<5>(params, prepared, states, B, pooled, saved, sms, st);

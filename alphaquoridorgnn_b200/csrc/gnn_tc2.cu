@@ -1,0 +1,410 @@
+// bf16 tensor-core GCN trunk, version 2 (inference): the node transform AND the A_hat aggregation both run
+// on the 5th-gen tensor cores; the CUDA cores only convert accumulators to bf16 and build the per-board
+// operands.  Per board  X_{l+1} = ReLU(A_hat (X_l W_l^T) + b_l)  is evaluated feature-major:
+//
+//   transform   Z^T = W X^T        A = W   [128 out][128 in]  bf16 resident in TENSOR MEMORY (TS form of tcgen05.mma)
+//                                  B = X^T [K = 128 feat][N = 96 nodes]  MN-major SWIZZLE_64B in shared memory
+//                                  D = Z^T [128 lanes = features][96 columns = nodes]  fp32 in TMEM
+//   aggregate   Y^T = Z^T A_hat^T  A = Z^T [M = 128 feat][K = 96 nodes]  K-major SWIZZLE_64B -- byte for byte the same
+//               + b 1^T               "feature-major" tile as the transform's B operand, so one 24 KB buffer per board serves both
+//                                  B = A_hat, banded: two blocks of [48 out nodes][64 in nodes] K-major SWIZZLE_128B (a 5-point
+//                                      stencil on a 9x9 board reaches at most 9 nodes away: out nodes 0..47 need in nodes 0..63,
+//                                      out nodes 48..80 need 32..95)
+//                                  the aggregation runs in FP16 (A and B must share a format): the coefficients dinv_i dinv_j
+//                                  lie in [0.2, 1] and keep 11 mantissa bits, Z is converted with saturation (|z| <= 65504)
+//                                  one extra K = 16 step adds the bias: A = [b_hi b_lo 0..], B = [1 1 0..]
+//                                  D = Y^T [128 lanes][96 columns]
+//
+// A thread owns one feature (TMEM lane) of its board; every epilogue is "tcgen05.ld 32 columns -> cvt.bf16x2 ->
+// four 16-byte shared stores into the thread's own tile row": no scattered stores, no stencil arithmetic.  Only the 5
+// non-zero positions per adjacency row are rewritten per board (the tiles are zeroed once per kernel).
+//
+// One persistent CTA per SM, 4 independent 4-warp groups (one board each in flight).  TMEM: 4 x 96 accumulator columns +
+// 2 x 64 columns holding W2 and W3 = 512.  Shared memory: 4 x 50 KB group state + 14 KB shared operands.
+// Layer 1 (K = 6) keeps the fp32 aggregation of the 6-wide input by the node threads and one K = 16 MMA
+// (hi/lo split input, bias folded), as in version 1 (gnn_tc.cu).
+#include <cstddef>
+#include <cstdlib>
+#include <cuda_bf16.h>
+#include "gnn_fp32.cuh"
+#include "tc_common.cuh"
+
+using namespace aq;
+using namespace aqtc;
+
+namespace {
+
+constexpr int kG = 4;                                // groups (boards in flight) per CTA
+constexpr int kNodesPad = 96;
+constexpr uint32_t kFmBlock = 16 * 512;              // feature-major tile: [3 node blocks of 32][16 atoms of 8 features][8][64 B]
+constexpr uint32_t kAdjBlock = 48 * 128;             // adjacency block: 48 out-node rows x 64 in-nodes (128 B)
+constexpr uint32_t kWKBlock = 128 * 128;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemW2 = kG * kNodesPad, kTmemW3 = kTmemW2 + 64;
+static_assert(kTmemW3 + 64 <= kTmemCols, "TMEM columns");
+
+// instruction descriptors (kind::f16): D = f32, A = B = bf16, M = 128
+constexpr uint32_t kIdescBase = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+constexpr uint32_t kIdescL1 = kIdescBase | ((uint32_t)(kNodesPad >> 3) << 17);                 // K-major A and B, N = 96
+constexpr uint32_t kIdescT = kIdescBase | (1u << 16) | ((uint32_t)(kNodesPad >> 3) << 17);     // B MN-major, N = 96
+constexpr uint32_t kIdescA = (1u << 4) | ((128u >> 4) << 24) | ((uint32_t)(48 >> 3) << 17);    // A = B = f16, K-major, N = 48
+
+struct Tc2Group {
+    unsigned char fm[3 * kFmBlock];          // 24 KB: X^T (B operand, MN-major) / Z^T (A operand, K-major); layer-1 node operand aliases it
+    unsigned char adj[2][kAdjBlock];         // 12 KB: A_hat (fp16) [block 0 | 1]
+    float x0[kV * kF + 2];
+    uint8_t open_s[96];
+};
+static_assert(sizeof(Tc2Group) % 1024 == 0, "group state must keep 1024-byte alignment");
+
+struct Tc2Smem {
+    unsigned char w1[128 * 32];              // layer-1 weight operand [128][16] K-major SWIZZLE_32B: [W1 | W1 | b1_hi | b1_lo | 0 | 0]
+    unsigned char bt[2][128 * 32];           // bias operands of layers 2, 3: fp16 [128][16]: [b_hi | b_lo | 0 ...]
+    unsigned char ones[2048];                // fp16 [48][16]: [1 | 1 | 0 ...]   (1536 B used)
+    Tc2Group g[kG];
+    unsigned long long mbar[kG];
+    uint32_t tmem_base;
+};
+static_assert(offsetof(Tc2Smem, g) % 1024 == 0, "group state must be 1024-byte aligned");
+static_assert(sizeof(Tc2Smem) + 1024 <= 227 * 1024, "Tc2Smem exceeds shared memory");
+
+__device__ __forceinline__ uint64_t desc_fm_mn(uint32_t saddr) {  // MN-major SWIZZLE_64B: LBO = node-block stride, SBO = 8-feature atom stride
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(kFmBlock >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ uint64_t desc_fm_k(uint32_t saddr) {   // K-major SWIZZLE_64B: SBO = 512 B (8 rows x 64 B)
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+                 ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                   "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+                   "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+                   "r"(r[30]), "r"(r[31]) : "memory");
+}
+// two floats -> packed bf16x2 (a in the low half), optionally through ReLU
+template <bool kRelu>
+__device__ __forceinline__ uint32_t cvt2(float a, float b) {
+    uint32_t d;
+    if (kRelu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(b), "f"(a));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+__device__ __forceinline__ uint32_t cvt2_f16(float a, float b) {  // packed f16x2 (a in the low half), saturating
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+__device__ __forceinline__ unsigned short f16_bits(float x) { return (unsigned short)(cvt2_f16(x, 0.f) & 0xFFFFu); }
+__device__ __forceinline__ float f16_value(unsigned short h) {
+    float f;
+    asm("cvt.f32.f16 %0, %1;\n" : "=f"(f) : "h"(h));
+    return f;
+}
+// mbarrier wait: hint_ns == 0 spins on try_wait, otherwise passes the suspend-time hint
+__device__ __forceinline__ void mbar_wait2(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok = 0;
+    if (hint_ns == 0) {
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } else {
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(ok) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
+    }
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t saddr, unsigned short v) {
+    asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(saddr), "h"(v) : "memory");
+}
+
+// Accumulator columns [32 cb, 32 cb + 32) of this thread's lane -> bf16 -> node block cb of the thread's feature row.
+// Nodes >= 81 are written as zero (they are K padding of the aggregation's A operand: 0 x garbage must not be NaN).
+enum { kToBf16 = 0, kToBf16Relu = 1, kToF16 = 2 };
+template <int kMode>
+__device__ __forceinline__ uint32_t cvt_pair(float a, float b) {
+    return kMode == kToF16 ? cvt2_f16(a, b) : cvt2<kMode == kToBf16Relu>(a, b);
+}
+template <int kMode>
+__device__ __forceinline__ void store_block(uint32_t row_addr, int swz, int cb, const float *z) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint4 v;
+        if (cb == 2 && q == 3) v = make_uint4(0u, 0u, 0u, 0u);                                   // nodes 88..95
+        else if (cb == 2 && q == 2) v = make_uint4(cvt_pair<kMode>(z[16], 0.f), 0u, 0u, 0u);     // node 80, then padding
+        else {
+            v.x = cvt_pair<kMode>(z[q * 8 + 0], z[q * 8 + 1]); v.y = cvt_pair<kMode>(z[q * 8 + 2], z[q * 8 + 3]);
+            v.z = cvt_pair<kMode>(z[q * 8 + 4], z[q * 8 + 5]); v.w = cvt_pair<kMode>(z[q * 8 + 6], z[q * 8 + 7]);
+        }
+        sts128(row_addr + (uint32_t)cb * kFmBlock + (uint32_t)((q ^ swz) << 4), v);
+    }
+}
+
+__global__ void __launch_bounds__(kG * kGroupThreads, 1)
+gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__restrict__ prepared,
+                       const AqState *__restrict__ states, int64_t B, float *__restrict__ pooled_out, uint32_t wait_ns) {
+    constexpr int kThreads = kG * kGroupThreads;
+    extern __shared__ unsigned char smem_raw[];
+    Tc2Smem &sm = *reinterpret_cast<Tc2Smem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const int gtid = threadIdx.x;
+    const int grp = gtid / kGroupThreads, tid = gtid % kGroupThreads;  // tid = feature = TMEM lane
+    Tc2Group &gs = sm.g[grp];
+
+    // ---- one-time setup ---------------------------------------------------------------------------------------
+    {
+        uint4 *adj = reinterpret_cast<uint4 *>(&gs.adj[0][0]);  // adjacency tiles start as zero; only the stencil positions change
+        for (int c = tid; c < (int)(2 * kAdjBlock / 16); c += kGroupThreads) adj[c] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (gtid < kH) {
+        const int n = gtid;
+        uint4 c0, c1;
+        if (prepared) {  // layer-1 operand as built by aq_prepare_inference
+            c0 = __ldg(reinterpret_cast<const uint4 *>(prepared + kPrepW1 + sw32_chunk(n, 0)));
+            c1 = __ldg(reinterpret_cast<const uint4 *>(prepared + kPrepW1 + sw32_chunk(n, 1)));
+        } else {
+            float w[kF];
+#pragma unroll
+            for (int f = 0; f < kF; ++f) w[f] = __ldg(params + kOffW1 + n * kF + f);
+            const float bias = __ldg(params + kOffB1 + n);
+            const float bias_hi = __bfloat162float(__float2bfloat16_rn(bias));
+            c0.x = pack_bf16(w[0], w[1]); c0.y = pack_bf16(w[2], w[3]); c0.z = pack_bf16(w[4], w[5]); c0.w = pack_bf16(w[0], w[1]);
+            c1.x = pack_bf16(w[2], w[3]); c1.y = pack_bf16(w[4], w[5]); c1.z = pack_bf16(bias_hi, bias - bias_hi); c1.w = 0u;
+        }
+        *reinterpret_cast<uint4 *>(sm.w1 + sw32_chunk(n, 0)) = c0;
+        *reinterpret_cast<uint4 *>(sm.w1 + sw32_chunk(n, 1)) = c1;
+    } else if (gtid < 3 * kH) {  // bias operands of layers 2 and 3
+        const int which = gtid / kH - 1, n = gtid % kH;
+        const float bias = __ldg(params + (which ? kOffB3 : kOffB2) + n);
+        const unsigned short hb = f16_bits(bias);
+        *reinterpret_cast<uint4 *>(sm.bt[which] + sw32_chunk(n, 0)) =
+            make_uint4((uint32_t)hb | ((uint32_t)f16_bits(bias - f16_value(hb)) << 16), 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(sm.bt[which] + sw32_chunk(n, 1)) = make_uint4(0u, 0u, 0u, 0u);
+    } else if (gtid < 3 * kH + 48) {
+        const int n = gtid - 3 * kH;
+        *reinterpret_cast<uint4 *>(sm.ones + sw32_chunk(n, 0)) = make_uint4(0x3C003C00u, 0u, 0u, 0u);  // fp16 1, 1
+        *reinterpret_cast<uint4 *>(sm.ones + sw32_chunk(n, 1)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (gtid < kG) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&sm.mbar[gtid])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (gtid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_base = sm.tmem_base;
+    const uint32_t lane_off = (uint32_t)((tid >> 5) * 32) << 16;  // this warp's TMEM lane quadrant
+    if (grp < 2) {  // W2 (group 0) / W3 (group 1): row `tid` -> 64 TMEM columns, two bf16 per column (k = 2c, 2c + 1)
+        const uint32_t dst = tmem_base + lane_off + (grp ? kTmemW3 : kTmemW2);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            if (prepared) {
+                const unsigned char *src = prepared + (grp ? kPrepW3 : kPrepW2);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + sw128_chunk(tid, half * 8 + j, kWKBlock)));
+                    r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+                }
+            } else {
+                const float4 *W = reinterpret_cast<const float4 *>(params + (grp ? kOffW3 : kOffW2) + tid * kH + half * 64);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float4 v = __ldg(W + j);
+                    r[2 * j] = pack_bf16(v.x, v.y); r[2 * j + 1] = pack_bf16(v.z, v.w);
+                }
+            }
+            tmem_st32(dst + half * 32, r);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+
+    const uint32_t tmem_d = tmem_base + (uint32_t)(grp * kNodesPad);   // the group's accumulator columns
+    const uint32_t tmem_me = tmem_d + lane_off;
+    const uint32_t bar = smem_u32(&sm.mbar[grp]);
+    const uint32_t fm_addr = smem_u32(gs.fm), adj_addr = smem_u32(&gs.adj[0][0]);
+    const uint32_t w1_addr = smem_u32(sm.w1), ones_addr = smem_u32(sm.ones);
+    const uint32_t row_addr = fm_addr + (uint32_t)(tid >> 3) * 512u + (uint32_t)(tid & 7) * 64u;  // this thread's feature row
+    const int swz = (tid & 7) >> 1;
+    uint32_t phase = 0;
+
+    for (int64_t b = (int64_t)blockIdx.x * kG + grp; b < B; b += (int64_t)gridDim.x * kG) {
+        // ---- inputs: node features + open-direction masks ------------------------------------------------------
+        {
+            const AqState s = load_state(states + b);
+            board_inputs_from_state(s, gs.x0, gs.open_s, tid);
+        }
+        group_sync(grp);
+        // ---- node threads: A_hat coefficients -> adjacency tiles (hi/lo), and the layer-1 node operand row
+        //      [hi(A_hat x0) (6) | lo(A_hat x0) (6) | 1 | 1 | 0 | 0] ------------------------------------------------
+        if (tid < kV) {
+            const int v = tid, m = gs.open_s[v];
+            const float dv = dinv_of(m);
+            const int iu = (m & 1) ? v - 9 : v, id = (m & 2) ? v + 9 : v, il = (m & 4) ? v - 1 : v, ir = (m & 8) ? v + 1 : v;
+            const float c0 = dv * dv;
+            const float cu = (m & 1) ? dv * dinv_of(gs.open_s[iu]) : 0.f, cd = (m & 2) ? dv * dinv_of(gs.open_s[id]) : 0.f;
+            const float cl = (m & 4) ? dv * dinv_of(gs.open_s[il]) : 0.f, cr = (m & 8) ? dv * dinv_of(gs.open_s[ir]) : 0.f;
+            {
+                const int blk = v >= 48 ? 1 : 0, r = v - 48 * blk, kl0 = v - 32 * blk;  // row and self position inside the block's window
+                const uint32_t hi_row = adj_addr + (uint32_t)blk * kAdjBlock + (uint32_t)r * 128u;
+                auto put = [&](int kl, float c) {
+                    sts16(hi_row + (uint32_t)(((kl >> 3) ^ (r & 7)) << 4) + (uint32_t)(kl & 7) * 2u, f16_bits(c));
+                };
+                put(kl0, c0);
+                if (v >= 9) put(kl0 - 9, cu);
+                if (v < kV - 9) put(kl0 + 9, cd);
+                if (v % 9 != 0) put(kl0 - 1, cl);
+                if (v % 9 != 8) put(kl0 + 1, cr);
+            }
+            unsigned short hi[kF], lo[kF];
+#pragma unroll
+            for (int f = 0; f < kF; ++f) {
+                float s = c0 * gs.x0[v * kF + f];
+                s = fmaf(cu, gs.x0[iu * kF + f], s);
+                s = fmaf(cd, gs.x0[id * kF + f], s);
+                s = fmaf(cl, gs.x0[il * kF + f], s);
+                s = fmaf(cr, gs.x0[ir * kF + f], s);
+                const float h = __bfloat162float(__float2bfloat16_rn(s));
+                hi[f] = bf16_bits(s);
+                lo[f] = bf16_bits(s - h);
+            }
+            uint4 c0v, c1v;
+            c0v.x = hi[0] | ((uint32_t)hi[1] << 16); c0v.y = hi[2] | ((uint32_t)hi[3] << 16);
+            c0v.z = hi[4] | ((uint32_t)hi[5] << 16); c0v.w = lo[0] | ((uint32_t)lo[1] << 16);
+            c1v.x = lo[2] | ((uint32_t)lo[3] << 16); c1v.y = lo[4] | ((uint32_t)lo[5] << 16);
+            c1v.z = 0x3F803F80u; c1v.w = 0u;  // 1, 1, 0, 0
+            sts128(fm_addr + (uint32_t)v * 128u + (uint32_t)((0 ^ (v & 7)) << 4), c0v);   // K-major SWIZZLE_128B rows of 128 B, K = 16 used
+            sts128(fm_addr + (uint32_t)v * 128u + (uint32_t)((1 ^ (v & 7)) << 4), c1v);
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        group_sync(grp);
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            mma_bf16(tmem_d, desc_sw32(w1_addr), desc_sw128(fm_addr), kIdescL1, 0u);  // one K = 16 step
+            mma_commit(bar);
+        }
+        mbar_wait2(bar, phase, wait_ns);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        // ---- layer 1 epilogue: ReLU -> bf16 -> X1^T row ---------------------------------------------------------------
+#pragma unroll
+        for (int cb = 0; cb < 3; ++cb) {
+            float z[32];
+            tmem_ld32(tmem_me + cb * 32, z);
+            store_block<kToBf16Relu>(row_addr, swz, cb, z);
+        }
+        float pool = 0.f;
+#pragma unroll 1
+        for (int layer = 1; layer < kLayers; ++layer) {
+            // ---- transform: Z^T = W X^T (A = W in TMEM, B = X^T tile) -------------------------------------------
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            group_sync(grp);
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint32_t w_tmem = tmem_base + (layer == 1 ? kTmemW2 : kTmemW3);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)  // K = 128 features = 8 x 16: 8 TMEM columns of A, two 8-feature atoms of B per step
+                    mma_ts(tmem_d, w_tmem + k * 8, desc_fm_mn(fm_addr + k * 1024), kIdescT, k > 0 ? 1u : 0u);
+                mma_commit(bar);
+            }
+            mbar_wait2(bar, phase, wait_ns);
+            phase ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            // ---- Z^T -> bf16 -> the same tile, now the aggregation's A operand -------------------------------------
+#pragma unroll
+            for (int cb = 0; cb < 3; ++cb) {
+                float z[32];
+                tmem_ld32(tmem_me + cb * 32, z);
+                store_block<kToF16>(row_addr, swz, cb, z);
+            }
+            // ---- aggregate: Y^T = Z^T A_hat^T + b 1^T --------------------------------------------------------------
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            group_sync(grp);
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint64_t bias_desc = desc_sw32(smem_u32(sm.bt[layer - 1])), ones_desc = desc_sw32(ones_addr);
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                    const uint32_t d = tmem_d + blk * 48;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {  // 64 in-nodes = 4 K steps; A: two 32-node blocks, 2 steps of 32 B each
+                        const uint64_t a = desc_fm_k(fm_addr + (uint32_t)(blk + (s >> 1)) * kFmBlock + (uint32_t)(s & 1) * 32u);
+                        const uint64_t bd = desc_sw128(adj_addr + (uint32_t)blk * kAdjBlock + (uint32_t)s * 32u);
+                        mma_bf16(d, a, bd, kIdescA, s ? 1u : 0u);
+                    }
+                    mma_bf16(d, bias_desc, ones_desc, kIdescA, 1u);
+                }
+                mma_commit(bar);
+            }
+            mbar_wait2(bar, phase, wait_ns);
+            phase ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (layer + 1 < kLayers) {  // ReLU -> bf16 -> X^T row of the next layer
+#pragma unroll
+                for (int cb = 0; cb < 3; ++cb) {
+                    float z[32];
+                    tmem_ld32(tmem_me + cb * 32, z);
+                    store_block<kToBf16Relu>(row_addr, swz, cb, z);
+                }
+            } else {                    // last layer feeds only the mean pool
+#pragma unroll
+                for (int cb = 0; cb < 3; ++cb) {
+                    float z[32];
+                    tmem_ld32(tmem_me + cb * 32, z);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (cb * 32 + i < kV) pool += fmaxf(z[i], 0.f);
+                }
+            }
+        }
+        pooled_out[b * kH + tid] = pool / (float)kV;
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        group_sync(grp);  // the next board overwrites x0 / open_s / the tiles
+    }
+    // ---- teardown ---------------------------------------------------------------------------------------------------
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (gtid < 32) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+}  // namespace
+
+// Inference trunk, version 2.  Same contract as aq_gcn_forward_tc(saved == nullptr).
+int aq_gcn_forward_tc2(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, cudaStream_t st) {
+    static int sms = 0;
+    static uint32_t wait_ns = 0;
+    if (sms == 0) {
+        const char *env = getenv("AQ_TC_WAIT_NS");  // tuning knob: suspend-time hint of the mbarrier waits (0 = spin)
+        if (env) wait_ns = (uint32_t)atoi(env);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const size_t smem = sizeof(Tc2Smem) + 1024;
+    const int64_t want = (B + kG - 1) / kG;
+    const unsigned grid = (unsigned)(want < sms ? want : sms);
+    cudaError_t e = cudaFuncSetAttribute(gcn_forward_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return aq_set_error((int)e, "gcn_forward_tc2 smem");
+    gcn_forward_tc2_kernel<<<grid, kG * kGroupThreads, smem, st>>>(params, reinterpret_cast<const unsigned char *>(prepared), states, B, pooled, wait_ns);
+    return aq_check_launch("gcn_forward_tc2_kernel");
+}
