@@ -8,7 +8,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libaqgnn.so")
+LIB_PATH = os.environ.get("AQ_LIB_PATH") or os.path.join(_PKG, "libaqgnn.so")  # AQ_LIB_PATH: kernel-variant builds (scripts/build_variant.py)
 
 # name -> (restype, argtypes); must list every symbol declared in include/aqgnn.h
 _vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float

@@ -32,6 +32,29 @@
 using namespace aq;
 using namespace aqtc;
 
+#ifndef TC2_PREFETCH
+#define TC2_PREFETCH 1   // 1: fetch the next board's state one board ahead
+#endif
+#ifndef TC2_BIAS
+#define TC2_BIAS 0       // 0: extra MMA step with a ones column, 1: accumulator initialised by tcgen05.st, 2: added in the epilogue
+#endif
+
+#ifndef TC2_TIMING
+#define TC2_TIMING 0     // 1: per-phase clock64 accounting by thread 0 of group 0 of CTA 0 (debug variant)
+#endif
+#if TC2_TIMING
+__device__ long long g_tc2_timing[16];
+#define TC2_T(slot) do { if (blockIdx.x == 0 && gtid == 0) { const long long t_ = clock64(); g_tc2_timing[slot] += t_ - t_last; t_last = t_; } } while (0)
+extern "C" int aq_debug_tc2_timing(long long *out) {
+    cudaMemcpyFromSymbol(out, g_tc2_timing, sizeof(long long) * 16);
+    long long z[16] = {0};
+    cudaMemcpyToSymbol(g_tc2_timing, z, sizeof(z));
+    return 0;
+}
+#else
+#define TC2_T(slot) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kG = 4;                                // groups (boards in flight) per CTA
@@ -49,11 +72,20 @@ constexpr uint32_t kIdescL1 = kIdescBase | ((uint32_t)(kNodesPad >> 3) << 17);  
 constexpr uint32_t kIdescT = kIdescBase | (1u << 16) | ((uint32_t)(kNodesPad >> 3) << 17);     // B MN-major, N = 96
 constexpr uint32_t kIdescA = (1u << 4) | ((128u >> 4) << 24) | ((uint32_t)(48 >> 3) << 17);    // A = B = f16, K-major, N = 48
 
+// Loop-invariant facts about node v = (r, c), built once per CTA.  Wall slots are read through an 18-bit window of the
+// H / V bitboards that starts at slot 8 r + c - 9: bit 0 = slot (r-1, c-1), 1 = (r-1, c), 8 = (r, c-1), 9 = (r, c),
+// 10 = (r, c+1), 17 = (r+1, c).  Bit 31 of a blocking mask stands for "this direction does not exist".
+struct NodeConst {
+    uint32_t upm, dnm, lfm, rtm;             // slots whose wall closes the move up / down (H board) and left / right (V board)
+    uint32_t pv, sh, adj01, adj23;           // valid wall-plane bits {self 9, up 1, down 17, left 8, right 10}; window shift; tile offsets
+    uint32_t adj4, row_off, pad0, pad1;      // ... of the stencil positions self|up, down|left, right (0xFFFF = absent); layer-1 operand row offset
+};
+
 struct Tc2Group {
     unsigned char fm[3 * kFmBlock];          // 24 KB: X^T (B operand, MN-major) / Z^T (A operand, K-major); layer-1 node operand aliases it
     unsigned char adj[2][kAdjBlock];         // 12 KB: A_hat (fp16) [block 0 | 1]
-    float x0[kV * kF + 2];
-    uint8_t open_s[96];
+    uint8_t deg[128];                        // degree (1 + open directions) of node v at [16 + v]; neighbours are read at 16 + v +- 1 / 9
+    unsigned char pad[1024 - 128];
 };
 static_assert(sizeof(Tc2Group) % 1024 == 0, "group state must keep 1024-byte alignment");
 
@@ -62,6 +94,8 @@ struct Tc2Smem {
     unsigned char bt[2][128 * 32];           // bias operands of layers 2, 3: fp16 [128][16]: [b_hi | b_lo | 0 ...]
     unsigned char ones[2048];                // fp16 [48][16]: [1 | 1 | 0 ...]   (1536 B used)
     Tc2Group g[kG];
+    NodeConst nc[kV];                        // loop-invariant per-node constants
+    float2 lut[64];                          // [deg_v * 8 + deg_u] -> {dinv_v * dinv_u as float, the same as fp16 bits}; entry 0 = closed edge
     unsigned long long mbar[kG];
     uint32_t tmem_base;
 };
@@ -104,6 +138,16 @@ __device__ __forceinline__ float f16_value(unsigned short h) {
     float f;
     asm("cvt.f32.f16 %0, %1;\n" : "=f"(f) : "h"(h));
     return f;
+}
+// (1 + popcount(open directions))^-1/2 without branches
+__device__ __forceinline__ float dinv_sel(int open_mask) {
+    const int deg = 1 + __popc(open_mask & 15);
+    float d = 1.0f;
+    d = deg == 2 ? 0.70710678118654752f : d;
+    d = deg == 3 ? 0.57735026918962576f : d;
+    d = deg == 4 ? 0.5f : d;
+    d = deg == 5 ? 0.44721359549995794f : d;
+    return d;
 }
 // mbarrier wait: hint_ns == 0 spins on try_wait, otherwise passes the suspend-time hint
 __device__ __forceinline__ void mbar_wait2(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
@@ -162,6 +206,35 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         uint4 *adj = reinterpret_cast<uint4 *>(&gs.adj[0][0]);  // adjacency tiles start as zero; only the stencil positions change
         for (int c = tid; c < (int)(2 * kAdjBlock / 16); c += kGroupThreads) adj[c] = make_uint4(0u, 0u, 0u, 0u);
     }
+    if (gtid < kV) {
+        const int v = gtid, r = v / 9, c = v - 9 * r;
+        NodeConst k;
+        const uint32_t none = 0x80000000u;
+        k.upm = r >= 1 ? ((c >= 1 ? 1u : 0u) | (c <= 7 ? 2u : 0u)) : none;                 // H slots (r-1, c-1), (r-1, c)
+        k.dnm = r <= 7 ? ((c >= 1 ? 1u << 8 : 0u) | (c <= 7 ? 1u << 9 : 0u)) : none;       // H slots (r, c-1), (r, c)
+        k.lfm = c >= 1 ? ((r >= 1 ? 1u : 0u) | (r <= 7 ? 1u << 8 : 0u)) : none;            // V slots (r-1, c-1), (r, c-1)
+        k.rtm = c <= 7 ? ((r >= 1 ? 2u : 0u) | (r <= 7 ? 1u << 9 : 0u)) : none;            // V slots (r-1, c), (r, c)
+        k.pv = ((r <= 7 && c <= 7) ? 1u << 9 : 0u) | ((r >= 1 && c <= 7) ? 2u : 0u) | ((r <= 6 && c <= 7) ? 1u << 17 : 0u) |
+               ((r <= 7 && c >= 1) ? 1u << 8 : 0u) | ((r <= 7 && c <= 6) ? 1u << 10 : 0u);
+        k.sh = (uint32_t)(8 * r + c);
+        const int blk = v >= 48 ? 1 : 0, row = v - 48 * blk, kl0 = v - 32 * blk;  // row and self position inside the block's window
+        auto off = [&](int kl, bool exists) -> uint32_t {
+            return exists ? (uint32_t)blk * kAdjBlock + (uint32_t)row * 128u + (uint32_t)(((kl >> 3) ^ (row & 7)) << 4) + (uint32_t)(kl & 7) * 2u
+                          : 0xFFFFu;
+        };
+        k.adj01 = off(kl0, true) | (off(kl0 - 9, r >= 1) << 16);
+        k.adj23 = off(kl0 + 9, r <= 7) | (off(kl0 - 1, c >= 1) << 16);
+        k.adj4 = off(kl0 + 1, c <= 7);
+        k.row_off = (uint32_t)v * 128u + (uint32_t)((v & 7) << 4);  // chunk 0 of row v in the K-major SWIZZLE_128B layer-1 operand; chunk 1 = ^ 16
+        k.pad0 = k.pad1 = 0u;
+        sm.nc[v] = k;
+    } else if (gtid >= 128 && gtid < 192) {
+        const int i = gtid - 128, a = i >> 3, b2 = i & 7;
+        float cf = 0.f;
+        if (a >= 1 && a <= 5 && b2 >= 1 && b2 <= 5) cf = dinv_sel((1 << (a - 1)) - 1) * dinv_sel((1 << (b2 - 1)) - 1);  // popcount(2^k - 1) = k
+        sm.lut[i] = make_float2(cf, __uint_as_float((uint32_t)f16_bits(cf)));
+    }
+    if (tid < 32) reinterpret_cast<uint32_t *>(gs.deg)[tid] = 0x01010101u;
     if (gtid < kH) {
         const int n = gtid;
         uint4 c0, c1;
@@ -241,58 +314,101 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
     const uint32_t row_addr = fm_addr + (uint32_t)(tid >> 3) * 512u + (uint32_t)(tid & 7) * 64u;  // this thread's feature row
     const int swz = (tid & 7) >> 1;
     uint32_t phase = 0;
+#if TC2_BIAS != 0
+    const float bias2 = __ldg(params + kOffB2 + tid), bias3 = __ldg(params + kOffB3 + tid);
+#endif
 
-    for (int64_t b = (int64_t)blockIdx.x * kG + grp; b < B; b += (int64_t)gridDim.x * kG) {
-        // ---- inputs: node features + open-direction masks ------------------------------------------------------
-        {
-            const AqState s = load_state(states + b);
-            board_inputs_from_state(s, gs.x0, gs.open_s, tid);
+    const int64_t stride = (int64_t)gridDim.x * kG;
+#if TC2_PREFETCH
+    uint4 pre_a = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t pre_b = 0u;
+    if ((int64_t)blockIdx.x * kG + grp < B && tid < kV) {
+        pre_a = __ldg(reinterpret_cast<const uint4 *>(states + (int64_t)blockIdx.x * kG + grp));
+        pre_b = __ldg(reinterpret_cast<const uint32_t *>(states + (int64_t)blockIdx.x * kG + grp) + 4);
+    }
+#endif
+#if TC2_TIMING
+    long long t_last = clock64();
+#endif
+    for (int64_t b = (int64_t)blockIdx.x * kG + grp; b < B; b += stride) {
+        // ---- node threads, part 1: open directions of node v from two bitboard windows; degree -> shared memory ----------
+        uint32_t wH = 0u, wV = 0u, meta = 0u;
+        int m = 0, dv = 1;
+        if (tid < kV) {
+#if TC2_PREFETCH
+            const u64 h = ((u64)pre_a.y << 32) | pre_a.x, vw = ((u64)pre_a.w << 32) | pre_a.z;
+            meta = pre_b;
+            if (b + stride < B) {
+                pre_a = __ldg(reinterpret_cast<const uint4 *>(states + b + stride));
+                pre_b = __ldg(reinterpret_cast<const uint32_t *>(states + b + stride) + 4);
+            }
+#else
+            const uint4 sa = __ldg(reinterpret_cast<const uint4 *>(states + b));
+            meta = __ldg(reinterpret_cast<const uint32_t *>(states + b) + 4);
+            const u64 h = ((u64)sa.y << 32) | sa.x, vw = ((u64)sa.w << 32) | sa.z;
+#endif
+            const uint4 k0 = *reinterpret_cast<const uint4 *>(&sm.nc[tid].upm);
+            const uint32_t sh = sm.nc[tid].sh;
+            wH = (uint32_t)((((unsigned __int128)h) << 9) >> sh);
+            wV = (uint32_t)((((unsigned __int128)vw) << 9) >> sh);
+            const uint32_t eH = wH | 0x80000000u, eV = wV | 0x80000000u;
+            m = ((eH & k0.x) == 0u ? 1 : 0) | ((eH & k0.y) == 0u ? 2 : 0) | ((eV & k0.z) == 0u ? 4 : 0) | ((eV & k0.w) == 0u ? 8 : 0);
+            dv = 1 + __popc(m);
+            gs.deg[16 + tid] = (uint8_t)dv;
         }
         group_sync(grp);
-        // ---- node threads: A_hat coefficients -> adjacency tiles (hi/lo), and the layer-1 node operand row
-        //      [hi(A_hat x0) (6) | lo(A_hat x0) (6) | 1 | 1 | 0 | 0] ------------------------------------------------
+        // ---- part 2: A_hat row of v -> adjacency tile (fp16 bits straight from a table), and the layer-1 node operand row
+        //      [hi(A_hat x0) (6) | lo(A_hat x0) (6) | 1 | 1 | 0 | 0]; the six planes of pieces_array (game_logic.py:56-93) at v and
+        //      its neighbours are read from the same windows -------------------------------------------------------------------
         if (tid < kV) {
-            const int v = tid, m = gs.open_s[v];
-            const float dv = dinv_of(m);
-            const int iu = (m & 1) ? v - 9 : v, id = (m & 2) ? v + 9 : v, il = (m & 4) ? v - 1 : v, ir = (m & 8) ? v + 1 : v;
-            const float c0 = dv * dv;
-            const float cu = (m & 1) ? dv * dinv_of(gs.open_s[iu]) : 0.f, cd = (m & 2) ? dv * dinv_of(gs.open_s[id]) : 0.f;
-            const float cl = (m & 4) ? dv * dinv_of(gs.open_s[il]) : 0.f, cr = (m & 8) ? dv * dinv_of(gs.open_s[ir]) : 0.f;
+            const int v = tid;
+            const uint4 k1 = *reinterpret_cast<const uint4 *>(&sm.nc[tid].pv);
+            const uint2 k2 = *reinterpret_cast<const uint2 *>(&sm.nc[tid].adj4);
+            const int du = gs.deg[16 + v - 9], dd = gs.deg[16 + v + 9], dl = gs.deg[16 + v - 1], dr = gs.deg[16 + v + 1];
+            const float2 e0 = sm.lut[dv * 9];
+            const float2 eu = sm.lut[(m & 1) ? dv * 8 + du : 0], ed = sm.lut[(m & 2) ? dv * 8 + dd : 0];
+            const float2 el = sm.lut[(m & 4) ? dv * 8 + dl : 0], er = sm.lut[(m & 8) ? dv * 8 + dr : 0];
+            const float c0 = e0.x, cu = eu.x, cd = ed.x, cl = el.x, cr = er.x;
             {
-                const int blk = v >= 48 ? 1 : 0, r = v - 48 * blk, kl0 = v - 32 * blk;  // row and self position inside the block's window
-                const uint32_t hi_row = adj_addr + (uint32_t)blk * kAdjBlock + (uint32_t)r * 128u;
-                auto put = [&](int kl, float c) {
-                    sts16(hi_row + (uint32_t)(((kl >> 3) ^ (r & 7)) << 4) + (uint32_t)(kl & 7) * 2u, f16_bits(c));
-                };
-                put(kl0, c0);
-                if (v >= 9) put(kl0 - 9, cu);
-                if (v < kV - 9) put(kl0 + 9, cd);
-                if (v % 9 != 0) put(kl0 - 1, cl);
-                if (v % 9 != 8) put(kl0 + 1, cr);
+                const uint32_t o0 = k1.z & 0xFFFFu, o1 = k1.z >> 16, o2 = k1.w & 0xFFFFu, o3 = k1.w >> 16, o4 = k2.x;
+                sts16(adj_addr + o0, (unsigned short)__float_as_uint(e0.y));
+                if (o1 != 0xFFFFu) sts16(adj_addr + o1, (unsigned short)__float_as_uint(eu.y));
+                if (o2 != 0xFFFFu) sts16(adj_addr + o2, (unsigned short)__float_as_uint(ed.y));
+                if (o3 != 0xFFFFu) sts16(adj_addr + o3, (unsigned short)__float_as_uint(el.y));
+                if (o4 != 0xFFFFu) sts16(adj_addr + o4, (unsigned short)__float_as_uint(er.y));
             }
-            unsigned short hi[kF], lo[kF];
-#pragma unroll
-            for (int f = 0; f < kF; ++f) {
-                float s = c0 * gs.x0[v * kF + f];
-                s = fmaf(cu, gs.x0[iu * kF + f], s);
-                s = fmaf(cd, gs.x0[id * kF + f], s);
-                s = fmaf(cl, gs.x0[il * kF + f], s);
-                s = fmaf(cr, gs.x0[ir * kF + f], s);
-                const float h = __bfloat162float(__float2bfloat16_rn(s));
-                hi[f] = bf16_bits(s);
-                lo[f] = bf16_bits(s - h);
+            float s[kF];
+            {
+                const int dp = (int)(meta & 0xFF) - v, de = (int)((meta >> 16) & 0xFF) - v;
+                const float pw = (float)((meta >> 8) & 0xFF), ew = (float)(meta >> 24);
+                const uint32_t pH = wH & k1.x, pV = wV & k1.x;
+                auto onehot = [&](int d) {  // same summation order as a fused multiply-add chain over {self, up, down, left, right}
+                    float t = d == 0 ? c0 : 0.f;
+                    t += d == -9 ? cu : 0.f; t += d == 9 ? cd : 0.f; t += d == -1 ? cl : 0.f; t += d == 1 ? cr : 0.f;
+                    return t;
+                };
+                auto plane = [&](uint32_t w) {
+                    float t = (w & (1u << 9)) ? c0 : 0.f;
+                    t += (w & 2u) ? cu : 0.f; t += (w & (1u << 17)) ? cd : 0.f; t += (w & (1u << 8)) ? cl : 0.f; t += (w & (1u << 10)) ? cr : 0.f;
+                    return t;
+                };
+                auto scaled = [&](float x) { return fmaf(cr, x, fmaf(cl, x, fmaf(cd, x, fmaf(cu, x, c0 * x)))); };
+                s[0] = onehot(dp); s[1] = scaled(pw); s[2] = onehot(de); s[3] = scaled(ew); s[4] = plane(pH); s[5] = plane(pV);
             }
             uint4 c0v, c1v;
-            c0v.x = hi[0] | ((uint32_t)hi[1] << 16); c0v.y = hi[2] | ((uint32_t)hi[3] << 16);
-            c0v.z = hi[4] | ((uint32_t)hi[5] << 16); c0v.w = lo[0] | ((uint32_t)lo[1] << 16);
-            c1v.x = lo[2] | ((uint32_t)lo[3] << 16); c1v.y = lo[4] | ((uint32_t)lo[5] << 16);
+            c0v.x = cvt2<false>(s[0], s[1]); c0v.y = cvt2<false>(s[2], s[3]); c0v.z = cvt2<false>(s[4], s[5]);
+            c0v.w = cvt2<false>(s[0] - __uint_as_float(c0v.x << 16), s[1] - __uint_as_float(c0v.x & 0xFFFF0000u));
+            c1v.x = cvt2<false>(s[2] - __uint_as_float(c0v.y << 16), s[3] - __uint_as_float(c0v.y & 0xFFFF0000u));
+            c1v.y = cvt2<false>(s[4] - __uint_as_float(c0v.z << 16), s[5] - __uint_as_float(c0v.z & 0xFFFF0000u));
             c1v.z = 0x3F803F80u; c1v.w = 0u;  // 1, 1, 0, 0
-            sts128(fm_addr + (uint32_t)v * 128u + (uint32_t)((0 ^ (v & 7)) << 4), c0v);   // K-major SWIZZLE_128B rows of 128 B, K = 16 used
-            sts128(fm_addr + (uint32_t)v * 128u + (uint32_t)((1 ^ (v & 7)) << 4), c1v);
+            sts128(fm_addr + k2.y, c0v);          // K-major SWIZZLE_128B rows of 128 B, K = 16 used
+            sts128(fm_addr + (k2.y ^ 16u), c1v);
         }
+        TC2_T(2);
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         group_sync(grp);
+        TC2_T(3);
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             mma_bf16(tmem_d, desc_sw32(w1_addr), desc_sw128(fm_addr), kIdescL1, 0u);  // one K = 16 step
@@ -300,6 +416,7 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         }
         mbar_wait2(bar, phase, wait_ns);
         phase ^= 1u;
+        TC2_T(4);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         // ---- layer 1 epilogue: ReLU -> bf16 -> X1^T row ---------------------------------------------------------------
 #pragma unroll
@@ -315,6 +432,7 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             group_sync(grp);
+        TC2_T(5);
             if (tid == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint32_t w_tmem = tmem_base + (layer == 1 ? kTmemW2 : kTmemW3);
@@ -325,6 +443,7 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
             }
             mbar_wait2(bar, phase, wait_ns);
             phase ^= 1u;
+        TC2_T(6);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             // ---- Z^T -> bf16 -> the same tile, now the aggregation's A operand -------------------------------------
 #pragma unroll
@@ -332,11 +451,24 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
                 float z[32];
                 tmem_ld32(tmem_me + cb * 32, z);
                 store_block<kToF16>(row_addr, swz, cb, z);
+#if TC2_BIAS == 1
+                {
+                    const uint32_t bias_bits = __float_as_uint(layer == 1 ? bias2 : bias3);
+                    uint32_t bb[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) bb[i] = bias_bits;
+                    tmem_st32(tmem_me + cb * 32, bb);
+                }
+#endif
             }
+#if TC2_BIAS == 1
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+#endif
             // ---- aggregate: Y^T = Z^T A_hat^T + b 1^T --------------------------------------------------------------
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             group_sync(grp);
+        TC2_T(7);
             if (tid == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint64_t bias_desc = desc_sw32(smem_u32(sm.bt[layer - 1])), ones_desc = desc_sw32(ones_addr);
@@ -347,20 +479,27 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
                     for (int s = 0; s < 4; ++s) {  // 64 in-nodes = 4 K steps; A: two 32-node blocks, 2 steps of 32 B each
                         const uint64_t a = desc_fm_k(fm_addr + (uint32_t)(blk + (s >> 1)) * kFmBlock + (uint32_t)(s & 1) * 32u);
                         const uint64_t bd = desc_sw128(adj_addr + (uint32_t)blk * kAdjBlock + (uint32_t)s * 32u);
-                        mma_bf16(d, a, bd, kIdescA, s ? 1u : 0u);
+                        mma_bf16(d, a, bd, kIdescA, (s || TC2_BIAS == 1) ? 1u : 0u);
                     }
+#if TC2_BIAS == 0
                     mma_bf16(d, bias_desc, ones_desc, kIdescA, 1u);
+#endif
                 }
                 mma_commit(bar);
             }
             mbar_wait2(bar, phase, wait_ns);
             phase ^= 1u;
+        TC2_T(8);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             if (layer + 1 < kLayers) {  // ReLU -> bf16 -> X^T row of the next layer
 #pragma unroll
                 for (int cb = 0; cb < 3; ++cb) {
                     float z[32];
                     tmem_ld32(tmem_me + cb * 32, z);
+#if TC2_BIAS == 2
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) z[i] += bias2;
+#endif
                     store_block<kToBf16Relu>(row_addr, swz, cb, z);
                 }
             } else {                    // last layer feeds only the mean pool
@@ -370,13 +509,19 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
                     tmem_ld32(tmem_me + cb * 32, z);
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
+#if TC2_BIAS == 2
+                        if (cb * 32 + i < kV) pool += fmaxf(z[i] + bias3, 0.f);
+#else
                         if (cb * 32 + i < kV) pool += fmaxf(z[i], 0.f);
+#endif
                 }
             }
         }
         pooled_out[b * kH + tid] = pool / (float)kV;
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-        group_sync(grp);  // the next board overwrites x0 / open_s / the tiles
+        TC2_T(9);
+        // no barrier here: the next board's node threads only write shared memory that the (completed) MMAs of this board
+        // have finished reading, and its first MMA is issued behind a group barrier that every thread reaches after its pool loads
+        TC2_T(10);
     }
     // ---- teardown ---------------------------------------------------------------------------------------------------
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");

@@ -1,0 +1,23 @@
+"""Per-phase cycle accounting of the tc2 trunk (debug variant built with -DTC2_TIMING=1):
+AQ_LIB_PATH=alphaquoridorgnn_b200/variants/libaqgnn_timing.so python scripts/tc2_timing.py"""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from alphaquoridorgnn_b200 import _lib, positions
+from alphaquoridorgnn_b200.pv_network_gnn import GNNNetwork
+B = 16384
+net = GNNNetwork().cuda().eval(); net.precision = "bf16"
+pos = positions.random_positions(B, seed=1, games=8192)
+L = ctypes.CDLL(_lib.LIB_PATH)
+out = (ctypes.c_longlong * 16)()
+net.predict_batch(pos); torch.cuda.synchronize()
+L.aq_debug_tc2_timing(out)
+net.predict_batch(pos); torch.cuda.synchronize()
+L.aq_debug_tc2_timing(out)
+names = {2: "inputs + sync", 3: "node work + sync", 4: "L1 MMA wait", 5: "epilogue X (+sync)", 6: "transform wait", 7: "epilogue Z (+sync)",
+         8: "aggregate wait", 9: "pool / store", 10: "final sync"}
+boards = (B // 148 + 3) // 4
+tot = sum(out[i] for i in range(16))
+for i in range(2, 11):
+    print(f"{names[i]:22s} {out[i]/boards:9.0f} cycles/board  {100*out[i]/tot:5.1f}%")
+print("total per board", tot / boards)
