@@ -82,8 +82,10 @@ struct NodeConst {
 };
 
 struct Tc2Group {
-    unsigned char fm[3 * kFmBlock];          // 24 KB: X^T (B operand, MN-major) / Z^T (A operand, K-major); layer-1 node operand aliases it
-    unsigned char adj[2][kAdjBlock];         // 12 KB: A_hat (fp16) [block 0 | 1]
+    unsigned char fm[3 * kFmBlock];          // 24 KB: X^T (B operand, MN-major) / Z^T (A operand, K-major)
+    unsigned char adj[2][2][kAdjBlock];      // 2 x 12 KB: A_hat (fp16) [board parity][block 0 | 1] -- the next board's tile is built
+                                             //            while the current board's last aggregation is still reading its own
+    unsigned char l1op[kNodesPad * 32];      // 3 KB: layer-1 node operand [96 nodes][16] K-major SWIZZLE_32B
     uint8_t deg[128];                        // degree (1 + open directions) of node v at [16 + v]; neighbours are read at 16 + v +- 1 / 9
     unsigned char pad[1024 - 128];
 };
@@ -91,8 +93,9 @@ static_assert(sizeof(Tc2Group) % 1024 == 0, "group state must keep 1024-byte ali
 
 struct Tc2Smem {
     unsigned char w1[128 * 32];              // layer-1 weight operand [128][16] K-major SWIZZLE_32B: [W1 | W1 | b1_hi | b1_lo | 0 | 0]
-    unsigned char bt[2][128 * 32];           // bias operands of layers 2, 3: fp16 [128][16]: [b_hi | b_lo | 0 ...]
-    unsigned char ones[2048];                // fp16 [48][16]: [1 | 1 | 0 ...]   (1536 B used)
+    unsigned char bt[128 * 32];              // bias operand of layers 2 and 3: fp16 [128][16]: [b2_hi | b2_lo | b3_hi | b3_lo | 0 ...]
+    unsigned char ones[2][48 * 32];          // fp16 [48][16]: [1 | 1 | 0 ...] (layer 2) and [0 | 0 | 1 | 1 | 0 ...] (layer 3)
+    unsigned char pad0[1024];
     Tc2Group g[kG];
     NodeConst nc[kV];                        // loop-invariant per-node constants
     float2 lut[64];                          // [deg_v * 8 + deg_u] -> {dinv_v * dinv_u as float, the same as fp16 bits}; entry 0 = closed edge
@@ -203,8 +206,8 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
 
     // ---- one-time setup ---------------------------------------------------------------------------------------
     {
-        uint4 *adj = reinterpret_cast<uint4 *>(&gs.adj[0][0]);  // adjacency tiles start as zero; only the stencil positions change
-        for (int c = tid; c < (int)(2 * kAdjBlock / 16); c += kGroupThreads) adj[c] = make_uint4(0u, 0u, 0u, 0u);
+        uint4 *adj = reinterpret_cast<uint4 *>(&gs.adj[0][0][0]);  // adjacency tiles start as zero; only the stencil positions change
+        for (int c = tid; c < (int)(4 * kAdjBlock / 16); c += kGroupThreads) adj[c] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (gtid < kV) {
         const int v = gtid, r = v / 9, c = v - 9 * r;
@@ -225,7 +228,7 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         k.adj01 = off(kl0, true) | (off(kl0 - 9, r >= 1) << 16);
         k.adj23 = off(kl0 + 9, r <= 7) | (off(kl0 - 1, c >= 1) << 16);
         k.adj4 = off(kl0 + 1, c <= 7);
-        k.row_off = (uint32_t)v * 128u + (uint32_t)((v & 7) << 4);  // chunk 0 of row v in the K-major SWIZZLE_128B layer-1 operand; chunk 1 = ^ 16
+        k.row_off = sw32_chunk(v, 0);  // chunk 0 of row v in the K-major SWIZZLE_32B layer-1 operand; chunk 1 = ^ 16
         k.pad0 = k.pad1 = 0u;
         sm.nc[v] = k;
     } else if (gtid >= 128 && gtid < 192) {
@@ -252,17 +255,17 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         }
         *reinterpret_cast<uint4 *>(sm.w1 + sw32_chunk(n, 0)) = c0;
         *reinterpret_cast<uint4 *>(sm.w1 + sw32_chunk(n, 1)) = c1;
-    } else if (gtid < 3 * kH) {  // bias operands of layers 2 and 3
-        const int which = gtid / kH - 1, n = gtid % kH;
-        const float bias = __ldg(params + (which ? kOffB3 : kOffB2) + n);
-        const unsigned short hb = f16_bits(bias);
-        *reinterpret_cast<uint4 *>(sm.bt[which] + sw32_chunk(n, 0)) =
-            make_uint4((uint32_t)hb | ((uint32_t)f16_bits(bias - f16_value(hb)) << 16), 0u, 0u, 0u);
-        *reinterpret_cast<uint4 *>(sm.bt[which] + sw32_chunk(n, 1)) = make_uint4(0u, 0u, 0u, 0u);
-    } else if (gtid < 3 * kH + 48) {
-        const int n = gtid - 3 * kH;
-        *reinterpret_cast<uint4 *>(sm.ones + sw32_chunk(n, 0)) = make_uint4(0x3C003C00u, 0u, 0u, 0u);  // fp16 1, 1
-        *reinterpret_cast<uint4 *>(sm.ones + sw32_chunk(n, 1)) = make_uint4(0u, 0u, 0u, 0u);
+    } else if (gtid < 2 * kH) {  // bias operand of layers 2 and 3
+        const int n = gtid - kH;
+        const float b2v = __ldg(params + kOffB2 + n), b3v = __ldg(params + kOffB3 + n);
+        const unsigned short h2 = f16_bits(b2v), h3 = f16_bits(b3v);
+        *reinterpret_cast<uint4 *>(sm.bt + sw32_chunk(n, 0)) =
+            make_uint4((uint32_t)h2 | ((uint32_t)f16_bits(b2v - f16_value(h2)) << 16), (uint32_t)h3 | ((uint32_t)f16_bits(b3v - f16_value(h3)) << 16), 0u, 0u);
+        *reinterpret_cast<uint4 *>(sm.bt + sw32_chunk(n, 1)) = make_uint4(0u, 0u, 0u, 0u);
+    } else if (gtid < 2 * kH + 96) {
+        const int which = (gtid - 2 * kH) / 48, n = (gtid - 2 * kH) % 48;
+        *reinterpret_cast<uint4 *>(sm.ones[which] + sw32_chunk(n, 0)) = which ? make_uint4(0u, 0x3C003C00u, 0u, 0u) : make_uint4(0x3C003C00u, 0u, 0u, 0u);  // fp16 1, 1
+        *reinterpret_cast<uint4 *>(sm.ones[which] + sw32_chunk(n, 1)) = make_uint4(0u, 0u, 0u, 0u);
     }
     if (gtid < kG) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&sm.mbar[gtid])) : "memory");
@@ -309,8 +312,8 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
     const uint32_t tmem_d = tmem_base + (uint32_t)(grp * kNodesPad);   // the group's accumulator columns
     const uint32_t tmem_me = tmem_d + lane_off;
     const uint32_t bar = smem_u32(&sm.mbar[grp]);
-    const uint32_t fm_addr = smem_u32(gs.fm), adj_addr = smem_u32(&gs.adj[0][0]);
-    const uint32_t w1_addr = smem_u32(sm.w1), ones_addr = smem_u32(sm.ones);
+    const uint32_t fm_addr = smem_u32(gs.fm), adj_addr = smem_u32(&gs.adj[0][0][0]), l1_addr = smem_u32(gs.l1op);
+    const uint32_t w1_addr = smem_u32(sm.w1);
     const uint32_t row_addr = fm_addr + (uint32_t)(tid >> 3) * 512u + (uint32_t)(tid & 7) * 64u;  // this thread's feature row
     const int swz = (tid & 7) >> 1;
     uint32_t phase = 0;
@@ -330,7 +333,9 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
 #if TC2_TIMING
     long long t_last = clock64();
 #endif
-    for (int64_t b = (int64_t)blockIdx.x * kG + grp; b < B; b += stride) {
+    // Node phase of board bn: fills the adjacency tile at adj_dst and the layer-1 node operand.  It contains one group barrier
+    // (all 128 threads of the group call it).
+    auto node_phase = [&](int64_t bn, uint32_t adj_dst) {
         // ---- node threads, part 1: open directions of node v from two bitboard windows; degree -> shared memory ----------
         uint32_t wH = 0u, wV = 0u, meta = 0u;
         int m = 0, dv = 1;
@@ -338,13 +343,13 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
 #if TC2_PREFETCH
             const u64 h = ((u64)pre_a.y << 32) | pre_a.x, vw = ((u64)pre_a.w << 32) | pre_a.z;
             meta = pre_b;
-            if (b + stride < B) {
-                pre_a = __ldg(reinterpret_cast<const uint4 *>(states + b + stride));
-                pre_b = __ldg(reinterpret_cast<const uint32_t *>(states + b + stride) + 4);
+            if (bn + stride < B) {
+                pre_a = __ldg(reinterpret_cast<const uint4 *>(states + bn + stride));
+                pre_b = __ldg(reinterpret_cast<const uint32_t *>(states + bn + stride) + 4);
             }
 #else
-            const uint4 sa = __ldg(reinterpret_cast<const uint4 *>(states + b));
-            meta = __ldg(reinterpret_cast<const uint32_t *>(states + b) + 4);
+            const uint4 sa = __ldg(reinterpret_cast<const uint4 *>(states + bn));
+            meta = __ldg(reinterpret_cast<const uint32_t *>(states + bn) + 4);
             const u64 h = ((u64)sa.y << 32) | sa.x, vw = ((u64)sa.w << 32) | sa.z;
 #endif
             const uint4 k0 = *reinterpret_cast<const uint4 *>(&sm.nc[tid].upm);
@@ -371,11 +376,11 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
             const float c0 = e0.x, cu = eu.x, cd = ed.x, cl = el.x, cr = er.x;
             {
                 const uint32_t o0 = k1.z & 0xFFFFu, o1 = k1.z >> 16, o2 = k1.w & 0xFFFFu, o3 = k1.w >> 16, o4 = k2.x;
-                sts16(adj_addr + o0, (unsigned short)__float_as_uint(e0.y));
-                if (o1 != 0xFFFFu) sts16(adj_addr + o1, (unsigned short)__float_as_uint(eu.y));
-                if (o2 != 0xFFFFu) sts16(adj_addr + o2, (unsigned short)__float_as_uint(ed.y));
-                if (o3 != 0xFFFFu) sts16(adj_addr + o3, (unsigned short)__float_as_uint(el.y));
-                if (o4 != 0xFFFFu) sts16(adj_addr + o4, (unsigned short)__float_as_uint(er.y));
+                sts16(adj_dst + o0, (unsigned short)__float_as_uint(e0.y));
+                if (o1 != 0xFFFFu) sts16(adj_dst + o1, (unsigned short)__float_as_uint(eu.y));
+                if (o2 != 0xFFFFu) sts16(adj_dst + o2, (unsigned short)__float_as_uint(ed.y));
+                if (o3 != 0xFFFFu) sts16(adj_dst + o3, (unsigned short)__float_as_uint(el.y));
+                if (o4 != 0xFFFFu) sts16(adj_dst + o4, (unsigned short)__float_as_uint(er.y));
             }
             float s[kF];
             {
@@ -401,9 +406,16 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
             c1v.x = cvt2<false>(s[2] - __uint_as_float(c0v.y << 16), s[3] - __uint_as_float(c0v.y & 0xFFFF0000u));
             c1v.y = cvt2<false>(s[4] - __uint_as_float(c0v.z << 16), s[5] - __uint_as_float(c0v.z & 0xFFFF0000u));
             c1v.z = 0x3F803F80u; c1v.w = 0u;  // 1, 1, 0, 0
-            sts128(fm_addr + k2.y, c0v);          // K-major SWIZZLE_128B rows of 128 B, K = 16 used
-            sts128(fm_addr + (k2.y ^ 16u), c1v);
+            sts128(l1_addr + k2.y, c0v);
+            sts128(l1_addr + (k2.y ^ 16u), c1v);
         }
+    };
+    uint32_t par = 0;  // adjacency buffer of the current board
+    {
+        const int64_t b0 = (int64_t)blockIdx.x * kG + grp;
+        if (b0 < B) node_phase(b0, adj_addr);
+    }
+    for (int64_t b = (int64_t)blockIdx.x * kG + grp; b < B; b += stride) {
         TC2_T(2);
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -411,7 +423,7 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         TC2_T(3);
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            mma_bf16(tmem_d, desc_sw32(w1_addr), desc_sw128(fm_addr), kIdescL1, 0u);  // one K = 16 step
+            mma_bf16(tmem_d, desc_sw32(w1_addr), desc_sw32(l1_addr), kIdescL1, 0u);  // one K = 16 step
             mma_commit(bar);
         }
         mbar_wait2(bar, phase, wait_ns);
@@ -471,14 +483,14 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         TC2_T(7);
             if (tid == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint64_t bias_desc = desc_sw32(smem_u32(sm.bt[layer - 1])), ones_desc = desc_sw32(ones_addr);
+                const uint64_t bias_desc = desc_sw32(smem_u32(sm.bt)), ones_desc = desc_sw32(smem_u32(sm.ones[layer - 1]));
 #pragma unroll
                 for (int blk = 0; blk < 2; ++blk) {
                     const uint32_t d = tmem_d + blk * 48;
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {  // 64 in-nodes = 4 K steps; A: two 32-node blocks, 2 steps of 32 B each
                         const uint64_t a = desc_fm_k(fm_addr + (uint32_t)(blk + (s >> 1)) * kFmBlock + (uint32_t)(s & 1) * 32u);
-                        const uint64_t bd = desc_sw128(adj_addr + (uint32_t)blk * kAdjBlock + (uint32_t)s * 32u);
+                        const uint64_t bd = desc_sw128(adj_addr + (par * 2u + (uint32_t)blk) * kAdjBlock + (uint32_t)s * 32u);
                         mma_bf16(d, a, bd, kIdescA, (s || TC2_BIAS == 1) ? 1u : 0u);
                     }
 #if TC2_BIAS == 0
@@ -487,6 +499,8 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
                 }
                 mma_commit(bar);
             }
+            // while the last aggregation runs: the node phase of this group's next board (other adjacency buffer)
+            if (layer + 1 == kLayers && b + stride < B) node_phase(b + stride, adj_addr + (par ^ 1u) * 2u * kAdjBlock);
             mbar_wait2(bar, phase, wait_ns);
             phase ^= 1u;
         TC2_T(8);
@@ -518,9 +532,9 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
             }
         }
         pooled_out[b * kH + tid] = pool / (float)kV;
+        par ^= 1u;
         TC2_T(9);
-        // no barrier here: the next board's node threads only write shared memory that the (completed) MMAs of this board
-        // have finished reading, and its first MMA is issued behind a group barrier that every thread reaches after its pool loads
+        // no barrier here: the next board's first MMA is issued behind a group barrier that every thread reaches after its pool loads
         TC2_T(10);
     }
     // ---- teardown ---------------------------------------------------------------------------------------------------
