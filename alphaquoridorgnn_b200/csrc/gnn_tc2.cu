@@ -35,9 +35,6 @@ using namespace aqtc;
 #ifndef TC2_PREFETCH
 #define TC2_PREFETCH 1   // 1: fetch the next board's state one board ahead
 #endif
-#ifndef TC2_BIAS
-#define TC2_BIAS 0       // 0: extra MMA step with a ones column, 1: accumulator initialised by tcgen05.st, 2: added in the epilogue
-#endif
 
 #ifndef TC2_TIMING
 #define TC2_TIMING 0     // 1: per-phase clock64 accounting by thread 0 of group 0 of CTA 0 (debug variant)
@@ -194,6 +191,52 @@ __device__ __forceinline__ void store_block(uint32_t row_addr, int swz, int cb, 
     }
 }
 
+#ifndef TC2_LD2
+#define TC2_LD2 0        // 1: epilogues keep two tcgen05.ld in flight (64 accumulator columns) instead of one
+#endif
+#define AQ_R32(o) "%" #o
+// two 32-column loads issued back to back, one wait
+__device__ __forceinline__ void tmem_ld32x2(uint32_t ta, uint32_t tb, float *a, float *b) {
+    uint32_t r[64];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+          "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]),
+          "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]),
+          "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(ta), "r"(tb) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[32 + i]); }
+}
+// the three column blocks of this thread's accumulator lane -> its feature row
+template <int kMode>
+__device__ __forceinline__ void epilogue_store(uint32_t tmem_me, uint32_t row_addr, int swz) {
+#if TC2_LD2
+    float za[32], zb[32];
+    tmem_ld32x2(tmem_me, tmem_me + 32, za, zb);
+    store_block<kMode>(row_addr, swz, 0, za);
+    tmem_ld32(tmem_me + 64, za);
+    store_block<kMode>(row_addr, swz, 1, zb);
+    store_block<kMode>(row_addr, swz, 2, za);
+#else
+#pragma unroll
+    for (int cb = 0; cb < 3; ++cb) {
+        float z[32];
+        tmem_ld32(tmem_me + cb * 32, z);
+        store_block<kMode>(row_addr, swz, cb, z);
+    }
+#endif
+}
+
 __global__ void __launch_bounds__(kG * kGroupThreads, 1)
 gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__restrict__ prepared,
                        const AqState *__restrict__ states, int64_t B, float *__restrict__ pooled_out, uint32_t wait_ns) {
@@ -317,9 +360,6 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
     const uint32_t row_addr = fm_addr + (uint32_t)(tid >> 3) * 512u + (uint32_t)(tid & 7) * 64u;  // this thread's feature row
     const int swz = (tid & 7) >> 1;
     uint32_t phase = 0;
-#if TC2_BIAS != 0
-    const float bias2 = __ldg(params + kOffB2 + tid), bias3 = __ldg(params + kOffB3 + tid);
-#endif
 
     const int64_t stride = (int64_t)gridDim.x * kG;
 #if TC2_PREFETCH
@@ -431,12 +471,7 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         TC2_T(4);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         // ---- layer 1 epilogue: ReLU -> bf16 -> X1^T row ---------------------------------------------------------------
-#pragma unroll
-        for (int cb = 0; cb < 3; ++cb) {
-            float z[32];
-            tmem_ld32(tmem_me + cb * 32, z);
-            store_block<kToBf16Relu>(row_addr, swz, cb, z);
-        }
+        epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz);
         float pool = 0.f;
 #pragma unroll 1
         for (int layer = 1; layer < kLayers; ++layer) {
@@ -457,25 +492,8 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
             phase ^= 1u;
         TC2_T(6);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            // ---- Z^T -> bf16 -> the same tile, now the aggregation's A operand -------------------------------------
-#pragma unroll
-            for (int cb = 0; cb < 3; ++cb) {
-                float z[32];
-                tmem_ld32(tmem_me + cb * 32, z);
-                store_block<kToF16>(row_addr, swz, cb, z);
-#if TC2_BIAS == 1
-                {
-                    const uint32_t bias_bits = __float_as_uint(layer == 1 ? bias2 : bias3);
-                    uint32_t bb[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) bb[i] = bias_bits;
-                    tmem_st32(tmem_me + cb * 32, bb);
-                }
-#endif
-            }
-#if TC2_BIAS == 1
-            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-#endif
+            // ---- Z^T -> fp16 -> the same tile, now the aggregation's A operand -------------------------------------
+            epilogue_store<kToF16>(tmem_me, row_addr, swz);
             // ---- aggregate: Y^T = Z^T A_hat^T + b 1^T --------------------------------------------------------------
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -491,11 +509,9 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
                     for (int s = 0; s < 4; ++s) {  // 64 in-nodes = 4 K steps; A: two 32-node blocks, 2 steps of 32 B each
                         const uint64_t a = desc_fm_k(fm_addr + (uint32_t)(blk + (s >> 1)) * kFmBlock + (uint32_t)(s & 1) * 32u);
                         const uint64_t bd = desc_sw128(adj_addr + (par * 2u + (uint32_t)blk) * kAdjBlock + (uint32_t)s * 32u);
-                        mma_bf16(d, a, bd, kIdescA, (s || TC2_BIAS == 1) ? 1u : 0u);
+                        mma_bf16(d, a, bd, kIdescA, s ? 1u : 0u);
                     }
-#if TC2_BIAS == 0
-                    mma_bf16(d, bias_desc, ones_desc, kIdescA, 1u);
-#endif
+                    mma_bf16(d, bias_desc, ones_desc, kIdescA, 1u);  // + b 1^T
                 }
                 mma_commit(bar);
             }
@@ -506,29 +522,28 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         TC2_T(8);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             if (layer + 1 < kLayers) {  // ReLU -> bf16 -> X^T row of the next layer
-#pragma unroll
-                for (int cb = 0; cb < 3; ++cb) {
-                    float z[32];
-                    tmem_ld32(tmem_me + cb * 32, z);
-#if TC2_BIAS == 2
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) z[i] += bias2;
-#endif
-                    store_block<kToBf16Relu>(row_addr, swz, cb, z);
-                }
+                epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz);
             } else {                    // last layer feeds only the mean pool
+#if TC2_LD2
+                float za[32], zb[32];
+                tmem_ld32x2(tmem_me, tmem_me + 32, za, zb);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pool += fmaxf(za[i], 0.f);
+                tmem_ld32(tmem_me + 64, za);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pool += fmaxf(zb[i], 0.f);
+#pragma unroll
+                for (int i = 0; i < kV - 64; ++i) pool += fmaxf(za[i], 0.f);
+#else
 #pragma unroll
                 for (int cb = 0; cb < 3; ++cb) {
                     float z[32];
                     tmem_ld32(tmem_me + cb * 32, z);
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-#if TC2_BIAS == 2
-                        if (cb * 32 + i < kV) pool += fmaxf(z[i] + bias3, 0.f);
-#else
                         if (cb * 32 + i < kV) pool += fmaxf(z[i], 0.f);
-#endif
                 }
+#endif
             }
         }
         pooled_out[b * kH + tid] = pool / (float)kV;
