@@ -1,12 +1,14 @@
 // Policy / value heads on the tensor cores (bf16 operands, fp32 accumulate in TMEM) -- the
 // inference path that follows gcn_forward_tc_kernel.  pv_network_gnn.py:38-51,62-63:
 //   policy = Softmax(Linear(64->209)(ReLU(Linear(128->64)(g))));  value = Tanh(Linear(64->1)(ReLU(Linear(128->64)(g))))
-// One CTA of 256 threads per tile of 128 boards (thread pair = board = TMEM lane, one thread per column half):
+// One CTA of 512 threads per tile of 128 boards (four threads per board = TMEM lane, one per column quarter):
 //   GEMM 1  [128 boards x 128] x [Wp0 ; Wv0]^T  -> 64 policy-hidden + 64 value-hidden columns
 //   epilogue 1: bias + ReLU; policy hidden -> bf16 A tile of GEMM 2; value head finished in fp32
 //   GEMM 2  [128 boards x 64] x Wp2^T (209 rows padded to 224) -> logits in TMEM
-//   epilogue 2: softmax over the thread's own row straight from TMEM (three passes over 7 column
-//   blocks), optionally restricted to the legal mask and renormalised (BaseNetwork.predict).
+//   epilogue 2: each thread reads its <= 64 logits from TMEM once and keeps them in registers; row max and sums are
+//   exchanged between the four quarters through shared memory; optional restriction to the legal mask and
+//   renormalisation (BaseNetwork.predict); the probabilities leave through a per-warp transposing stage so that every
+//   global store is 32 consecutive floats of one board (the [B, 209] rows are only 4-byte aligned).
 #include <cstddef>
 #include <cuda_bf16.h>
 #include "aq_common.cuh"
@@ -17,7 +19,7 @@ using namespace aq;
 
 namespace {
 
-constexpr int kHtThreads = 256;                // two threads per board row (column halves)
+constexpr int kHtThreads = 512;                // four threads per board row (column quarters)
 constexpr int kTile = 128;                   // boards per CTA
 constexpr int kNPad = 224;                   // 209 logits padded to a multiple of 16
 constexpr uint32_t kKBlock = 128 * 128;      // one 128-row K-block of 64 bf16
@@ -30,7 +32,7 @@ struct HtSmem {
     float bp0[kHH], bv0[kHH], wv2[kHH];
     float bp2[kNPad];
     float bv2;
-    float xch[3][2][kTile];                  // row-wise exchange between the two column halves
+    float xch[4][4][kTile];                  // row-wise exchange between the four column quarters (max, sum, legal sum, value partials)
     unsigned long long mbar;
     uint32_t tmem_base;
 };
@@ -98,7 +100,7 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
     extern __shared__ unsigned char smem_raw[];
     HtSmem &sm = *reinterpret_cast<HtSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int row = tid & (kTile - 1), hf = tid >> 7;  // board of this thread inside the tile / column half it handles
+    const int row = tid & (kTile - 1), q = tid >> 7;  // board of this thread inside the tile / column quarter it handles
     const int64_t b0 = (int64_t)blockIdx.x * kTile;
 
     // ---- operands -> bf16 swizzled tiles ---------------------------------------------------------
@@ -184,27 +186,20 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
     }
     wait(bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    // ---- epilogue 1: half 0 = policy hidden -> bf16 A2; half 1 = value head in fp32 ------------------------
+    // ---- epilogue 1: quarters 0, 1 = policy hidden -> bf16 A2; quarters 2, 3 = value head in fp32 ---------------------
     {
         float v[32];
-        if (hf == 0) {
+        ld32(lane_base + q * 32, v);
+        if (q < 2) {  // bias + ReLU -> bf16 A2 (K-block 0 of the A region; GEMM 1 is done with it)
 #pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {  // bias + ReLU -> bf16 A2 (K-block 0 of the A region; GEMM 1 is done with it)
-                ld32(lane_base + cb * 32, v);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + sm.bp0[q * 32 + i], 0.f);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + sm.bp0[cb * 32 + i], 0.f);
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4 *>(sm.a + sw128(row, q * 4 + i)) = pack8(v + 8 * i);
+        } else {      // Linear(64 -> 1) on relu(hidden) in fp32: each quarter sums its 32 hidden units
+            float u = 0.f;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4 *>(sm.a + sw128(row, cb * 4 + i)) = pack8(v + 8 * i);
-            }
-        } else {
-            float u = sm.bv2;
-#pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {  // Linear(64 -> 1) on relu(hidden) in fp32, then tanh
-                ld32(lane_base + 64 + cb * 32, v);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) u = fmaf(fmaxf(v[i] + sm.bv0[cb * 32 + i], 0.f), sm.wv2[cb * 32 + i], u);
-            }
-            if (valid) value[b0 + row] = tanhf(u);
+            for (int i = 0; i < 32; ++i) u = fmaf(fmaxf(v[i] + sm.bv0[(q - 2) * 32 + i], 0.f), sm.wv2[(q - 2) * 32 + i], u);
+            sm.xch[3][q][row] = u;
         }
     }
     // ---- GEMM 2: logits ------------------------------------------------------------------------------------
@@ -219,70 +214,84 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
             mma(tmem, desc_sw128(a_addr + k * 32u), desc_sw128(b2_addr + k * 32u), idesc, k > 0 ? 1u : 0u);
         commit(bar);
     }
+    if (q == 2 && valid) value[b0 + row] = tanhf(sm.bv2 + sm.xch[3][2][row] + sm.xch[3][3][row]);  // (the barrier before GEMM 2 ordered the partials)
     wait(bar, 1);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    // ---- epilogue 2: softmax of the row (+ legal restriction); the two halves of a row exchange their
-    //      partial max / sums through shared memory; three passes over the thread's TMEM columns ------------
-    const int cb0 = hf == 0 ? 0 : 4, cb1 = hf == 0 ? 4 : 7;  // column blocks of 32: half 0 -> 0..127, half 1 -> 128..223
-    const uint32_t *lmask = mask + (kLegal && valid ? (b0 + row) * 8 : 0);  // 8 words per board, L1-resident
+    // ---- epilogue 2: softmax of the row (+ legal restriction).  Quarter q owns column blocks 2q and 2q + 1 (quarter 3: block 6
+    //      only); its logits are read from TMEM once and stay in registers; the four quarters of a row exchange their partial
+    //      max / sums through shared memory; the probabilities leave through a per-warp transposing stage so that every
+    //      global store writes 32 consecutive floats of one board ---------------------------------------------------------------
+    constexpr int kStagePitch = 33;
+    float *stage = reinterpret_cast<float *>(sm.b1) + warp * (32 * kStagePitch);  // b1 | b2 | a are dead after GEMM 2: 16 x 4.1 KB
+    static_assert(16 * 32 * kStagePitch * 4 <= (int)(2 * kKBlock + kNPad * 128 + 2 * kKBlock), "stage must fit in the dead operand tiles");
+    const int nblk = q == 3 ? 1 : 2;
+    const uint32_t *lmask = mask + (kLegal && valid ? (b0 + row) * 8 : 0);  // 8 words per board
+    float v0[32], v1[32];
+    ld32(lane_base + (2 * q) * 32, v0);
+    if (q < 3) ld32(lane_base + (2 * q + 1) * 32, v1);
+    uint32_t bits0 = 0xFFFFFFFFu, bits1 = 0xFFFFFFFFu;
+    if (kLegal && valid) { bits0 = __ldg(lmask + 2 * q); bits1 = q < 3 ? __ldg(lmask + 2 * q + 1) : 0u; }
     float mx = -INFINITY;
-    {
-        float v[32];
-#pragma unroll 1
-        for (int cb = cb0; cb < cb1; ++cb) {
-            ld32(lane_base + cb * 32, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (cb * 32 + i < kP) mx = fmaxf(mx, v[i] + sm.bp2[cb * 32 + i]);
+    for (int i = 0; i < 32; ++i) {
+        v0[i] += sm.bp2[(2 * q) * 32 + i];
+        if ((2 * q) * 32 + i < kP) mx = fmaxf(mx, v0[i]);
+    }
+    if (q < 3) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            v1[i] += sm.bp2[(2 * q + 1) * 32 + i];
+            mx = fmaxf(mx, v1[i]);  // blocks 1, 3, 5 lie entirely below column 209
         }
     }
-    sm.xch[0][hf][row] = mx;
+    sm.xch[0][q][row] = mx;
     __syncthreads();
-    mx = fmaxf(mx, sm.xch[0][hf ^ 1][row]);
+    mx = fmaxf(fmaxf(sm.xch[0][0][row], sm.xch[0][1][row]), fmaxf(sm.xch[0][2][row], sm.xch[0][3][row]));
     float sum_all = 0.f, sum_legal = 0.f;
-    {
-        float v[32];
-#pragma unroll 1
-        for (int cb = cb0; cb < cb1; ++cb) {
-            ld32(lane_base + cb * 32, v);
-            const uint32_t bits = (kLegal && valid) ? __ldg(lmask + cb) : 0xFFFFFFFFu;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (cb * 32 + i < kP) {
-                    const float e = __expf(v[i] + sm.bp2[cb * 32 + i] - mx);
-                    sum_all += e;
-                    if (kLegal && ((bits >> i) & 1)) sum_legal += e;
-                }
-            }
+    for (int i = 0; i < 32; ++i) {
+        const float e = ((2 * q) * 32 + i < kP) ? __expf(v0[i] - mx) : 0.f;
+        v0[i] = e;
+        sum_all += e;
+        if (kLegal && ((bits0 >> i) & 1)) sum_legal += e;
+    }
+    if (q < 3) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float e = __expf(v1[i] - mx);
+            v1[i] = e;
+            sum_all += e;
+            if (kLegal && ((bits1 >> i) & 1)) sum_legal += e;
         }
     }
-    sm.xch[1][hf][row] = sum_all;
-    sm.xch[2][hf][row] = sum_legal;
+    sm.xch[1][q][row] = sum_all;
+    sm.xch[2][q][row] = sum_legal;
     __syncthreads();
-    sum_all += sm.xch[1][hf ^ 1][row];
-    sum_legal += sm.xch[2][hf ^ 1][row];
+    sum_all = (sm.xch[1][0][row] + sm.xch[1][1][row]) + (sm.xch[1][2][row] + sm.xch[1][3][row]);
+    sum_legal = (sm.xch[2][0][row] + sm.xch[2][1][row]) + (sm.xch[2][2][row] + sm.xch[2][3][row]);
     // softmax then `policy /= sum(policy) if sum(policy) else 1` over the legal entries
     // (pv_network_cnn.py:129-132): p_a / sum_legal p = e_a / sum_legal e
     float inv;
     if (kLegal) inv = sum_legal != 0.f ? 1.f / sum_legal : 1.f / sum_all;
     else inv = 1.f / sum_all;
     {
-        float v[32];
-        float *out = policy + (b0 + row) * kP;
+        const int lane = tid & 31, r0 = row & ~31;  // this warp's 32 boards start at r0
 #pragma unroll 1
-        for (int cb = cb0; cb < cb1; ++cb) {
-            ld32(lane_base + cb * 32, v);  // executed by every lane: tcgen05.ld is warp-convergent
-            if (valid) {
-                const uint32_t bits = kLegal ? __ldg(lmask + cb) : 0xFFFFFFFFu;
+        for (int blk = 0; blk < nblk; ++blk) {
+            const uint32_t bits = blk ? bits1 : bits0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int a = cb * 32 + i;
-                    if (a < kP) {
-                        const float e = __expf(v[i] + sm.bp2[a] - mx) * inv;
-                        out[a] = (!kLegal || ((bits >> i) & 1)) ? e : 0.f;
-                    }
-                }
+            for (int i = 0; i < 32; ++i) {
+                const float e = (blk ? v1[i] : v0[i]) * inv;
+                stage[lane * kStagePitch + i] = (!kLegal || ((bits >> i) & 1)) ? e : 0.f;
             }
+            __syncwarp();
+            const int col = (2 * q + blk) * 32 + lane;
+            if (col < kP) {
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r)
+                    if (b0 + r0 + r < B) policy[(b0 + r0 + r) * kP + col] = stage[r * kStagePitch + lane];
+            }
+            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
