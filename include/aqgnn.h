@@ -159,7 +159,8 @@ int64_t aq_leaf_eval_ws_floats(int64_t B);
  * aq_leaf_eval_host_ws_bytes(B) bytes. */
 int64_t aq_leaf_eval_host_ws_bytes(int64_t B);
 /* host_ctx (optional, may be NULL): context from aq_host_ctx_create; with it, batches >= 4096 are
- * processed in 4 chunks on two worker streams so that the D2H of one chunk overlaps the next chunk. */
+ * processed in 2 chunks on two worker streams so that the D2H of the first overlaps the kernels of the second;
+ * with pinned host buffers the whole pipeline is replayed as one cached CUDA graph per argument tuple. */
 int aq_host_ctx_create(void **ctx);
 int aq_host_ctx_destroy(void *ctx);
 int aq_leaf_eval_host(const float *params, const void *prepared /* or NULL */, const AqState *states_host, int64_t B,
