@@ -340,6 +340,7 @@ static int launch_tc(const float *params, const unsigned char *prepared, const A
 }
 
 int aq_gcn_forward_tc2(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, cudaStream_t st);  // gnn_tc2.cu
+int aq_gcn_forward_tc3(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, cudaStream_t st);  // gnn_tc3.cu
 
 // saved == nullptr: inference.  saved != nullptr: training forward (activations kept for aq_gnn_backward, precision 1).
 int aq_gcn_forward_tc(const float *params, const void *prepared_v, const AqState *states, int64_t B, float *pooled, float *saved,
@@ -347,7 +348,7 @@ int aq_gcn_forward_tc(const float *params, const void *prepared_v, const AqState
     const unsigned char *prepared = reinterpret_cast<const unsigned char *>(prepared_v);
     static int sms = 0, groups = 0, version = 2;
     if (sms == 0) {
-        const char *ver = getenv("AQ_TC_VERSION");  // 1 = CUDA-core stencil aggregation (this file), 2 = tensor-core aggregation (gnn_tc2.cu)
+        const char *ver = getenv("AQ_TC_VERSION");  // 1 = CUDA-core stencil aggregation (this file), 2 = fp16 tensor-core aggregation (gnn_tc2.cu), 3 = tf32 aggregation from the accumulator (gnn_tc3.cu)
         if (ver) version = atoi(ver);
         int dev = 0;
         cudaGetDevice(&dev);
@@ -356,6 +357,7 @@ int aq_gcn_forward_tc(const float *params, const void *prepared_v, const AqState
         const char *env = getenv("AQ_TC_GROUPS");  // tuning knob: boards in flight per SM (3, 4 or 5)
         groups = env ? atoi(env) : 5;
     }
+    if (!saved && version == 3) return aq_gcn_forward_tc3(params, prepared_v, states, B, pooled, st);
     if (!saved && version == 2) return aq_gcn_forward_tc2(params, prepared_v, states, B, pooled, st);
     if (saved || groups == 3) return launch_tc<3>(params, prepared, states, B, pooled, saved, sms, st);  // the save variant needs the registers
     if (groups == 4) return launch_tc<4>(params, prepared, states, B, pooled, saved, sms, st);

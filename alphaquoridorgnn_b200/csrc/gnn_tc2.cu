@@ -149,6 +149,12 @@ __device__ __forceinline__ float dinv_sel(int open_mask) {
     d = deg == 5 ? 0.44721359549995794f : d;
     return d;
 }
+// one lane of a fully converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
 // mbarrier wait: hint_ns == 0 spins on try_wait, otherwise passes the suspend-time hint
 __device__ __forceinline__ void mbar_wait2(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
     uint32_t ok = 0;
@@ -360,6 +366,20 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
     const uint32_t row_addr = fm_addr + (uint32_t)(tid >> 3) * 512u + (uint32_t)(tid & 7) * 64u;  // this thread's feature row
     const int swz = (tid & 7) >> 1;
     uint32_t phase = 0;
+    // The MMAs of a group are issued by its first warp from WARP-UNIFORM values (everything below derives from a shuffled warp
+    // index), so that descriptors live in uniform registers and one tcgen05.mma costs a few instructions instead of a
+    // per-thread register -> uniform register broadcast loop.
+    const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int grp_u = warp_u >> 2;
+    const bool issuer_warp = (warp_u & 3) == 0;
+    const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t tmem_d_u = tmem_base_u + (uint32_t)(grp_u * kNodesPad);
+    const uint32_t smem_u = smem_u32(&sm);
+    const uint32_t fm_u = smem_u + (uint32_t)offsetof(Tc2Smem, g) + (uint32_t)grp_u * (uint32_t)sizeof(Tc2Group);
+    const uint32_t adj_u = fm_u + (uint32_t)offsetof(Tc2Group, adj), l1_u = fm_u + (uint32_t)offsetof(Tc2Group, l1op);
+    const uint32_t w1_u = smem_u + (uint32_t)offsetof(Tc2Smem, w1), bt_u = smem_u + (uint32_t)offsetof(Tc2Smem, bt);
+    const uint32_t ones_u = smem_u + (uint32_t)offsetof(Tc2Smem, ones);
+    const uint32_t bar_u = smem_u + (uint32_t)offsetof(Tc2Smem, mbar) + (uint32_t)grp_u * 8u;
 
     const int64_t stride = (int64_t)gridDim.x * kG;
 #if TC2_PREFETCH
@@ -461,10 +481,13 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         group_sync(grp);
         TC2_T(3);
-        if (tid == 0) {
+        if (issuer_warp) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            mma_bf16(tmem_d, desc_sw32(w1_addr), desc_sw32(l1_addr), kIdescL1, 0u);  // one K = 16 step
-            mma_commit(bar);
+            if (elect_one()) {
+                mma_bf16(tmem_d_u, desc_sw32(w1_u), desc_sw32(l1_u), kIdescL1, 0u);  // one K = 16 step
+                mma_commit(bar_u);
+            }
+            __syncwarp();
         }
         mbar_wait2(bar, phase, wait_ns);
         phase ^= 1u;
@@ -480,13 +503,16 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             group_sync(grp);
         TC2_T(5);
-            if (tid == 0) {
+            if (issuer_warp) {
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint32_t w_tmem = tmem_base + (layer == 1 ? kTmemW2 : kTmemW3);
+                if (elect_one()) {
+                    const uint32_t w_tmem = tmem_base_u + (layer == 1 ? kTmemW2 : kTmemW3);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)  // K = 128 features = 8 x 16: 8 TMEM columns of A, two 8-feature atoms of B per step
-                    mma_ts(tmem_d, w_tmem + k * 8, desc_fm_mn(fm_addr + k * 1024), kIdescT, k > 0 ? 1u : 0u);
-                mma_commit(bar);
+                    for (int k = 0; k < 8; ++k)  // K = 128 features = 8 x 16: 8 TMEM columns of A, two 8-feature atoms of B per step
+                        mma_ts(tmem_d_u, w_tmem + k * 8, desc_fm_mn(fm_u + k * 1024), kIdescT, k > 0 ? 1u : 0u);
+                    mma_commit(bar_u);
+                }
+                __syncwarp();
             }
             mbar_wait2(bar, phase, wait_ns);
             phase ^= 1u;
@@ -499,21 +525,27 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             group_sync(grp);
         TC2_T(7);
-            if (tid == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint64_t bias_desc = desc_sw32(smem_u32(sm.bt)), ones_desc = desc_sw32(smem_u32(sm.ones[layer - 1]));
+            {
+                const uint32_t par_u = __shfl_sync(0xffffffffu, par, 0);
+                if (issuer_warp) {
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    if (elect_one()) {
+                        const uint64_t bias_desc = desc_sw32(bt_u), ones_desc = desc_sw32(ones_u + (uint32_t)(layer - 1) * (48u * 32u));
 #pragma unroll
-                for (int blk = 0; blk < 2; ++blk) {
-                    const uint32_t d = tmem_d + blk * 48;
+                        for (int blk = 0; blk < 2; ++blk) {
+                            const uint32_t d = tmem_d_u + blk * 48;
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) {  // 64 in-nodes = 4 K steps; A: two 32-node blocks, 2 steps of 32 B each
-                        const uint64_t a = desc_fm_k(fm_addr + (uint32_t)(blk + (s >> 1)) * kFmBlock + (uint32_t)(s & 1) * 32u);
-                        const uint64_t bd = desc_sw128(adj_addr + (par * 2u + (uint32_t)blk) * kAdjBlock + (uint32_t)s * 32u);
-                        mma_bf16(d, a, bd, kIdescA, s ? 1u : 0u);
+                            for (int s = 0; s < 4; ++s) {  // 64 in-nodes = 4 K steps; A: two 32-node blocks, 2 steps of 32 B each
+                                const uint64_t a = desc_fm_k(fm_u + (uint32_t)(blk + (s >> 1)) * kFmBlock + (uint32_t)(s & 1) * 32u);
+                                const uint64_t bd = desc_sw128(adj_u + (par_u * 2u + (uint32_t)blk) * kAdjBlock + (uint32_t)s * 32u);
+                                mma_bf16(d, a, bd, kIdescA, s ? 1u : 0u);
+                            }
+                            mma_bf16(d, bias_desc, ones_desc, kIdescA, 1u);  // + b 1^T
+                        }
+                        mma_commit(bar_u);
                     }
-                    mma_bf16(d, bias_desc, ones_desc, kIdescA, 1u);  // + b 1^T
+                    __syncwarp();
                 }
-                mma_commit(bar);
             }
             // while the last aggregation runs: the node phase of this group's next board (other adjacency buffer)
             if (layer + 1 == kLayers && b + stride < B) node_phase(b + stride, adj_addr + (par ^ 1u) * 2u * kAdjBlock);

@@ -14,10 +14,13 @@ net.predict_batch(pos); torch.cuda.synchronize()
 L.aq_debug_tc2_timing(out)
 net.predict_batch(pos); torch.cuda.synchronize()
 L.aq_debug_tc2_timing(out)
+names3 = {3: "epilogue/pool + sync (x3)", 4: "L1 MMA wait", 5: "(unused)", 6: "MMA issue by thread 0 (x2)", 7: "node phase of next board", 8: "transform+aggregate wait (x2)", 9: "pool exchange + store"}
 names = {2: "inputs + sync", 3: "node work + sync", 4: "L1 MMA wait", 5: "epilogue X (+sync)", 6: "transform wait", 7: "epilogue Z (+sync)",
          8: "aggregate wait", 9: "pool / store", 10: "final sync"}
-boards = (B // 148 + 3) // 4
+groups = int(os.environ.get("AQ_TIMING_GROUPS", "4"))
+if groups == 2: names = names3
+boards = (B // 148 + groups - 1) // groups
 tot = sum(out[i] for i in range(16))
-for i in range(2, 11):
-    print(f"{names[i]:22s} {out[i]/boards:9.0f} cycles/board  {100*out[i]/tot:5.1f}%")
+for i in sorted(names):
+    print(f"{names[i]:32s} {out[i]/boards:9.0f} cycles/board  {100*out[i]/tot:5.1f}%")
 print("total per board", tot / boards)
