@@ -15,14 +15,22 @@
 //                                  one extra K = 16 step adds the bias: A = [b_hi b_lo 0..], B = [1 1 0..]
 //                                  D = Y^T [128 lanes][96 columns]
 //
-// A thread owns one feature (TMEM lane) of its board; every epilogue is "tcgen05.ld 32 columns -> cvt.bf16x2 ->
+// A thread owns one feature (TMEM lane) of its board; every epilogue is "tcgen05.ld 32 columns -> cvt.bf16x2 / cvt.f16x2 ->
 // four 16-byte shared stores into the thread's own tile row": no scattered stores, no stencil arithmetic.  Only the 5
 // non-zero positions per adjacency row are rewritten per board (the tiles are zeroed once per kernel).
 //
 // One persistent CTA per SM, 4 independent 4-warp groups (one board each in flight).  TMEM: 4 x 96 accumulator columns +
-// 2 x 64 columns holding W2 and W3 = 512.  Shared memory: 4 x 50 KB group state + 14 KB shared operands.
-// Layer 1 (K = 6) keeps the fp32 aggregation of the 6-wide input by the node threads and one K = 16 MMA
-// (hi/lo split input, bias folded), as in version 1 (gnn_tc.cu).
+// 2 x 64 columns holding W2 and W3 = 512.  Shared memory: 4 x 52 KB group state (tile, double-buffered adjacency,
+// layer-1 operand) + shared operands and tables.
+//   * Node phase (per board, 81 node threads): open directions from two 18-bit windows of the wall bitboards, degrees exchanged
+//     through shared memory, coefficients and their fp16 bits from a 64-entry table, the six input planes from the same windows;
+//     it is software-pipelined: the node phase of a group's NEXT board runs while its last aggregation is in flight.
+//   * MMAs are issued by the first warp of each group from warp-uniform values (elect.sync inside a uniform branch) so that the
+//     descriptors live in uniform registers; issuing from `if (tid == 0)` cost ~80 cycles per MMA (R2UR broadcast loops).
+//   * Layer 1 (K = 6): fp32 aggregation of the 6-wide input by the node threads, one K = 16 MMA (hi/lo split input, bias folded),
+//     as in version 1 (gnn_tc.cu).
+// Measured at B = 16,384 (CUDA events): 251 us (version 1) -> 146 us.  What bounds it now (ncu): the F2FP packs on the XU pipe
+// (16 cycles per warp instruction on this part) and shared-memory bandwidth (SS-mode N = 48 MMAs re-read the 4 KB A slice).
 #include <cstddef>
 #include <cstdlib>
 #include <cuda_bf16.h>
@@ -177,6 +185,8 @@ __device__ __forceinline__ void sts16(uint32_t saddr, unsigned short v) {
 
 // Accumulator columns [32 cb, 32 cb + 32) of this thread's lane -> bf16 -> node block cb of the thread's feature row.
 // Nodes >= 81 are written as zero (they are K padding of the aggregation's A operand: 0 x garbage must not be NaN).
+// (Tried and dropped: converting every other relu -> bf16 pair on the FMA pipe with a Veltkamp split -- 9 full-rate instructions
+// per pair against one F2FP at 16 cycles per warp instruction -- made the kernel 9 % slower: issue slots and registers.)
 enum { kToBf16 = 0, kToBf16Relu = 1, kToF16 = 2 };
 template <int kMode>
 __device__ __forceinline__ uint32_t cvt_pair(float a, float b) {
