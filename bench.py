@@ -32,7 +32,7 @@ FLOP_PER_BOARD_FWDBWD = 16.9e6
 BYTES_PER_POSITION_LEGAL = 72    # 32 B packed state in + 32 B mask + 8 B ordered pawn list out
 BYTES_PER_BOARD_HEADS = 128 * 4 + 209 * 4 + 4 + 32
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu captures (profiles/*.csv)
-NCU_TRAFFIC_BYTES = {("gcn_forward_kernel", 1, 16384): 704768}  # profiles/r1_final_kernels_ncu.csv (outputs stay in L2)
+NCU_TRAFFIC_BYTES = {("gcn_forward_kernel", 1, 16384): 632832}  # profiles/r1_v2_kernels_ncu.csv: dram read + write of gcn_forward_tc2_kernel (outputs stay in L2)
 
 
 def peaks():
@@ -265,7 +265,8 @@ def run_ours(args, rank, world, local_rank):
     traffic = NCU_TRAFFIC_BYTES.get((dom, prec, B))
     roofline = {"kernel": dom, "bound": kinfo[dom]["bound"], "achieved": kinfo[dom]["achieved"], "peak": kinfo[dom]["peak"],
                 "unit": kinfo[dom]["unit"], "frac": kinfo[dom]["frac"], "traffic": traffic, "peak_source": pk["source"],
-                "arith": "fp32 FFMA" if prec == 0 else "bf16 tcgen05, fp32 accumulate"}
+                "arith": "fp32 FFMA" if prec == 0 else "bf16 tcgen05 node transforms + fp16 tcgen05 aggregation, fp32 accumulate in TMEM",
+                "kernel_symbol": "gcn_forward_fp32_kernel" if prec == 0 else "gcn_forward_tc2_kernel"}
 
     # ---- end to end through host buffers (H2D states, D2H priors/value/mask/pawn every step) -----
     hst = [torch.from_numpy(gl.pack_rows_host(*[t.cpu().numpy() for t in gl.unpack_rows(b)])).pin_memory() for b in batches]
@@ -358,10 +359,11 @@ def run_ours(args, rank, world, local_rank):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        v, sec, threads = time_cpu_port(B, 1, 0)
+        cpu_steps = 5
+        v, sec, threads = time_cpu_port(B, cpu_steps, 1)
         cpu_baseline = {"value": v, "unit": "board-evals/s", "cores": threads, "kind": "port",
-                        "sample": f"one step of {B} positions: C oracle legal_actions (OpenMP, {threads} threads) + torch CPU "
-                                  f"GNN forward + legal renorm; {sec:.1f} s"}
+                        "sample": f"{cpu_steps} steps (1 warm-up) of {B} positions: C oracle legal_actions (OpenMP, {threads} threads) + "
+                                  f"torch CPU GNN forward + legal renorm; {sec:.1f} s per step"}
 
     if rank == 0:
         line = {
