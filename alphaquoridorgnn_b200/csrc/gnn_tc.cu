@@ -137,6 +137,17 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const unsigned char *__r
         for (int t = 0; t < 8; ++t) xs[t] = x_addr + (uint32_t)(j >> 3) * kXKBlock + (uint32_t)(((j & 7) ^ t) << 4) + (tid & 7) * 2;
     }
     uint32_t phase = 0;
+    // MMAs are issued by the first warp of a group from warp-uniform values (descriptors in uniform registers; issuing from
+    // `if (tid == 0)` costs a register -> uniform-register broadcast loop of ~80 cycles per MMA)
+    const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int grp_u = warp_u >> 2;
+    const bool issuer_warp = (warp_u & 3) == 0;
+    const uint32_t tmem_grp_u = __shfl_sync(0xffffffffu, sm.tmem_base, 0) + (uint32_t)(grp_u * kNodesPad);
+    const uint32_t smem_u = smem_u32(&sm);
+    const uint32_t x_u = smem_u + (uint32_t)offsetof(TcSmem<kGroups>, g) + (uint32_t)grp_u * (uint32_t)sizeof(TcGroupSmem);
+    const uint32_t w1_u = smem_u + (uint32_t)offsetof(TcSmem<kGroups>, w1), w2_u = smem_u + (uint32_t)offsetof(TcSmem<kGroups>, w2);
+    const uint32_t w3_u = smem_u + (uint32_t)offsetof(TcSmem<kGroups>, w3);
+    const uint32_t bar_u = smem_u + (uint32_t)offsetof(TcSmem<kGroups>, mbar) + (uint32_t)grp_u * 8u;
 
     for (int64_t b = (int64_t)blockIdx.x * kGroups + grp; b < B; b += (int64_t)gridDim.x * kGroups) {
         // ---- inputs: node features + open-direction masks ------------------------------------------
@@ -191,10 +202,13 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const unsigned char *__r
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         group_sync(grp);
-        if (tid == 0) {
+        if (issuer_warp) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            mma_bf16(tmem_grp, desc_sw32(w1_addr), desc_sw128(x_addr), kIdesc, 0u);  // one K = 16 step
-            mma_commit(bar);
+            if (elect_one_lane()) {
+                mma_bf16(tmem_grp_u, desc_sw32(w1_u), desc_sw128(x_u), kIdesc, 0u);  // one K = 16 step
+                mma_commit(bar_u);
+            }
+            __syncwarp();
         }
         mbar_wait(bar, phase);
         phase ^= 1u;
@@ -229,16 +243,19 @@ gcn_forward_tc_kernel(const float *__restrict__ params, const unsigned char *__r
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             group_sync(grp);
-            if (tid == 0) {
+            if (issuer_warp) {
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint32_t w_addr = layer == 1 ? w2_addr : w3_addr;
+                if (elect_one_lane()) {
+                    const uint32_t w_addr = layer == 1 ? w2_u : w3_u;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {  // K = 128 = 8 x UMMA_K(16); 4 steps of 32 B per 128 B swizzle span
-                    const uint32_t woff = (uint32_t)(k >> 2) * kWKBlock + (uint32_t)(k & 3) * 32u;
-                    const uint32_t xoff = (uint32_t)(k >> 2) * kXKBlock + (uint32_t)(k & 3) * 32u;
-                    mma_bf16(tmem_grp, desc_sw128(w_addr + woff), desc_sw128(x_addr + xoff), kIdesc, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < 8; ++k) {  // K = 128 = 8 x UMMA_K(16); 4 steps of 32 B per 128 B swizzle span
+                        const uint32_t woff = (uint32_t)(k >> 2) * kWKBlock + (uint32_t)(k & 3) * 32u;
+                        const uint32_t xoff = (uint32_t)(k >> 2) * kXKBlock + (uint32_t)(k & 3) * 32u;
+                        mma_bf16(tmem_grp_u, desc_sw128(w_addr + woff), desc_sw128(x_u + xoff), kIdesc, k > 0 ? 1u : 0u);
+                    }
+                    mma_commit(bar_u);
                 }
-                mma_commit(bar);
+                __syncwarp();
             }
             mbar_wait(bar, phase);
             phase ^= 1u;
