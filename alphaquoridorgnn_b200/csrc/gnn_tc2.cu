@@ -6,13 +6,13 @@
 //                                  B = X^T [K = 128 feat][N = 96 nodes]  MN-major SWIZZLE_64B in shared memory
 //                                  D = Z^T [128 lanes = features][96 columns = nodes]  fp32 in TMEM
 //   aggregate   Y^T = Z^T A_hat^T  A = Z^T [M = 128 feat][K = 96 nodes]  K-major SWIZZLE_64B -- byte for byte the same
-//               + b 1^T               "feature-major" tile as the transform's B operand, so one 24 KB buffer per board serves both
+//                                     "feature-major" tile as the transform's B operand, so one 24 KB buffer per board serves both
 //                                  B = A_hat, banded: two blocks of [48 out nodes][64 in nodes] K-major SWIZZLE_128B (a 5-point
 //                                      stencil on a 9x9 board reaches at most 9 nodes away: out nodes 0..47 need in nodes 0..63,
 //                                      out nodes 48..80 need 32..95)
 //                                  the aggregation runs in FP16 (A and B must share a format): the coefficients dinv_i dinv_j
 //                                  lie in [0.2, 1] and keep 11 mantissa bits, Z is converted with saturation (|z| <= 65504)
-//                                  one extra K = 16 step adds the bias: A = [b_hi b_lo 0..], B = [1 1 0..]
+//                                  the bias is added in fp32 by the epilogue (an extra "ones column" MMA step costs shared-memory bandwidth)
 //                                  D = Y^T [128 lanes][96 columns]
 //
 // A thread owns one feature (TMEM lane) of its board; every epilogue is "tcgen05.ld 32 columns -> cvt.bf16x2 / cvt.f16x2 ->
@@ -98,9 +98,6 @@ static_assert(sizeof(Tc2Group) % 1024 == 0, "group state must keep 1024-byte ali
 
 struct Tc2Smem {
     unsigned char w1[128 * 32];              // layer-1 weight operand [128][16] K-major SWIZZLE_32B: [W1 | W1 | b1_hi | b1_lo | 0 | 0]
-    unsigned char bt[128 * 32];              // bias operand of layers 2 and 3: fp16 [128][16]: [b2_hi | b2_lo | b3_hi | b3_lo | 0 ...]
-    unsigned char ones[2][48 * 32];          // fp16 [48][16]: [1 | 1 | 0 ...] (layer 2) and [0 | 0 | 1 | 1 | 0 ...] (layer 3)
-    unsigned char pad0[1024];
     Tc2Group g[kG];
     NodeConst nc[kV];                        // loop-invariant per-node constants
     float2 lut[64];                          // [deg_v * 8 + deg_u] -> {dinv_v * dinv_u as float, the same as fp16 bits}; entry 0 = closed edge
@@ -207,50 +204,19 @@ __device__ __forceinline__ void store_block(uint32_t row_addr, int swz, int cb, 
     }
 }
 
-#ifndef TC2_LD2
-#define TC2_LD2 0        // 1: epilogues keep two tcgen05.ld in flight (64 accumulator columns) instead of one
-#endif
-#define AQ_R32(o) "%" #o
-// two 32-column loads issued back to back, one wait
-__device__ __forceinline__ void tmem_ld32x2(uint32_t ta, uint32_t tb, float *a, float *b) {
-    uint32_t r[64];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n"
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n"
-        "tcgen05.wait::ld.sync.aligned;\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
-          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
-          "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
-          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]),
-          "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]),
-          "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
-        : "r"(ta), "r"(tb) : "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[32 + i]); }
-}
-// the three column blocks of this thread's accumulator lane -> its feature row
+// the three column blocks of this thread's accumulator lane (+ bias) -> its feature row
 template <int kMode>
-__device__ __forceinline__ void epilogue_store(uint32_t tmem_me, uint32_t row_addr, int swz) {
-#if TC2_LD2
-    float za[32], zb[32];
-    tmem_ld32x2(tmem_me, tmem_me + 32, za, zb);
-    store_block<kMode>(row_addr, swz, 0, za);
-    tmem_ld32(tmem_me + 64, za);
-    store_block<kMode>(row_addr, swz, 1, zb);
-    store_block<kMode>(row_addr, swz, 2, za);
-#else
+__device__ __forceinline__ void epilogue_store(uint32_t tmem_me, uint32_t row_addr, int swz, float bias) {
 #pragma unroll
     for (int cb = 0; cb < 3; ++cb) {
         float z[32];
         tmem_ld32(tmem_me + cb * 32, z);
+        if (bias != 0.f) {   // (0 where the bias is already inside the MMA or not wanted)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) z[i] += bias;
+        }
         store_block<kMode>(row_addr, swz, cb, z);
     }
-#endif
 }
 
 __global__ void __launch_bounds__(kG * kGroupThreads, 1)
@@ -314,17 +280,6 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         }
         *reinterpret_cast<uint4 *>(sm.w1 + sw32_chunk(n, 0)) = c0;
         *reinterpret_cast<uint4 *>(sm.w1 + sw32_chunk(n, 1)) = c1;
-    } else if (gtid < 2 * kH) {  // bias operand of layers 2 and 3
-        const int n = gtid - kH;
-        const float b2v = __ldg(params + kOffB2 + n), b3v = __ldg(params + kOffB3 + n);
-        const unsigned short h2 = f16_bits(b2v), h3 = f16_bits(b3v);
-        *reinterpret_cast<uint4 *>(sm.bt + sw32_chunk(n, 0)) =
-            make_uint4((uint32_t)h2 | ((uint32_t)f16_bits(b2v - f16_value(h2)) << 16), (uint32_t)h3 | ((uint32_t)f16_bits(b3v - f16_value(h3)) << 16), 0u, 0u);
-        *reinterpret_cast<uint4 *>(sm.bt + sw32_chunk(n, 1)) = make_uint4(0u, 0u, 0u, 0u);
-    } else if (gtid < 2 * kH + 96) {
-        const int which = (gtid - 2 * kH) / 48, n = (gtid - 2 * kH) % 48;
-        *reinterpret_cast<uint4 *>(sm.ones[which] + sw32_chunk(n, 0)) = which ? make_uint4(0u, 0x3C003C00u, 0u, 0u) : make_uint4(0x3C003C00u, 0u, 0u, 0u);  // fp16 1, 1
-        *reinterpret_cast<uint4 *>(sm.ones[which] + sw32_chunk(n, 1)) = make_uint4(0u, 0u, 0u, 0u);
     }
     if (gtid < kG) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&sm.mbar[gtid])) : "memory");
@@ -375,6 +330,7 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
     const uint32_t w1_addr = smem_u32(sm.w1);
     const uint32_t row_addr = fm_addr + (uint32_t)(tid >> 3) * 512u + (uint32_t)(tid & 7) * 64u;  // this thread's feature row
     const int swz = (tid & 7) >> 1;
+    const float bias2 = __ldg(params + kOffB2 + tid), bias3 = __ldg(params + kOffB3 + tid);   // added in the epilogues (fp32)
     uint32_t phase = 0;
     // The MMAs of a group are issued by its first warp from WARP-UNIFORM values (everything below derives from a shuffled warp
     // index), so that descriptors live in uniform registers and one tcgen05.mma costs a few instructions instead of a
@@ -387,8 +343,7 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
     const uint32_t smem_u = smem_u32(&sm);
     const uint32_t fm_u = smem_u + (uint32_t)offsetof(Tc2Smem, g) + (uint32_t)grp_u * (uint32_t)sizeof(Tc2Group);
     const uint32_t adj_u = fm_u + (uint32_t)offsetof(Tc2Group, adj), l1_u = fm_u + (uint32_t)offsetof(Tc2Group, l1op);
-    const uint32_t w1_u = smem_u + (uint32_t)offsetof(Tc2Smem, w1), bt_u = smem_u + (uint32_t)offsetof(Tc2Smem, bt);
-    const uint32_t ones_u = smem_u + (uint32_t)offsetof(Tc2Smem, ones);
+    const uint32_t w1_u = smem_u + (uint32_t)offsetof(Tc2Smem, w1);
     const uint32_t bar_u = smem_u + (uint32_t)offsetof(Tc2Smem, mbar) + (uint32_t)grp_u * 8u;
 
     const int64_t stride = (int64_t)gridDim.x * kG;
@@ -504,7 +459,7 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         TC2_T(4);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         // ---- layer 1 epilogue: ReLU -> bf16 -> X1^T row ---------------------------------------------------------------
-        epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz);
+        epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz, 0.f);   // (b1 is folded into the layer-1 MMA)
         float pool = 0.f;
 #pragma unroll 1
         for (int layer = 1; layer < kLayers; ++layer) {
@@ -529,7 +484,7 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         TC2_T(6);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             // ---- Z^T -> fp16 -> the same tile, now the aggregation's A operand -------------------------------------
-            epilogue_store<kToF16>(tmem_me, row_addr, swz);
+            epilogue_store<kToF16>(tmem_me, row_addr, swz, 0.f);
             // ---- aggregate: Y^T = Z^T A_hat^T + b 1^T --------------------------------------------------------------
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -540,7 +495,6 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
                 if (issuer_warp) {
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     if (elect_one()) {
-                        const uint64_t bias_desc = desc_sw32(bt_u), ones_desc = desc_sw32(ones_u + (uint32_t)(layer - 1) * (48u * 32u));
 #pragma unroll
                         for (int blk = 0; blk < 2; ++blk) {
                             const uint32_t d = tmem_d_u + blk * 48;
@@ -550,7 +504,6 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
                                 const uint64_t bd = desc_sw128(adj_u + (par_u * 2u + (uint32_t)blk) * kAdjBlock + (uint32_t)s * 32u);
                                 mma_bf16(d, a, bd, kIdescA, s ? 1u : 0u);
                             }
-                            mma_bf16(d, bias_desc, ones_desc, kIdescA, 1u);  // + b 1^T
                         }
                         mma_commit(bar_u);
                     }
@@ -563,29 +516,17 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
             phase ^= 1u;
         TC2_T(8);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            if (layer + 1 < kLayers) {  // ReLU -> bf16 -> X^T row of the next layer
-                epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz);
+            if (layer + 1 < kLayers) {  // + bias -> ReLU -> bf16 -> X^T row of the next layer
+                epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz, bias2);
             } else {                    // last layer feeds only the mean pool
-#if TC2_LD2
-                float za[32], zb[32];
-                tmem_ld32x2(tmem_me, tmem_me + 32, za, zb);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) pool += fmaxf(za[i], 0.f);
-                tmem_ld32(tmem_me + 64, za);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) pool += fmaxf(zb[i], 0.f);
-#pragma unroll
-                for (int i = 0; i < kV - 64; ++i) pool += fmaxf(za[i], 0.f);
-#else
 #pragma unroll
                 for (int cb = 0; cb < 3; ++cb) {
                     float z[32];
                     tmem_ld32(tmem_me + cb * 32, z);
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (cb * 32 + i < kV) pool += fmaxf(z[i], 0.f);
+                        if (cb * 32 + i < kV) pool += fmaxf(z[i] + bias3, 0.f);
                 }
-#endif
             }
         }
         pooled_out[b * kH + tid] = pool / (float)kV;
