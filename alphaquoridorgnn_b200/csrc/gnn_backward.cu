@@ -374,7 +374,9 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
 // ------------------------------------------------------------------------------------------
 extern "C" int64_t aq_gnn_backward_ws_floats(int64_t B) { return BwdWs{B}.total(); }
 
-int aq_gcn_backward_tc(const float *params, float *saved, const float *dg, int64_t B, float *partial, cudaStream_t st);  // gnn_tc_bwd.cu
+int aq_gcn_backward_tc(const float *params, float *saved, const float *dg, int64_t B, float *partial, cudaStream_t st);   // gnn_tc_bwd.cu
+int aq_gcn_backward_tc2(const float *params, float *saved, const float *dg, int64_t B, float *partial, cudaStream_t st);  // gnn_tc2_bwd.cu
+int aq_train_tc_version();                                                                                             // gnn_tc.cu
 
 extern "C" int aq_gnn_backward(const float *params, const float *saved, const float *dpolicy, const float *dvalue,
                                int64_t B, float *grads, float *workspace, int precision, void *stream) {
@@ -394,7 +396,11 @@ extern "C" int aq_gnn_backward(const float *params, const float *saved, const fl
     int rc = aq_check_launch("heads_backward_kernel");
     if (rc) return rc;
     if (precision == 1) {  // tensor-core trunk backward: fills the GCN ranges of every partial slot itself
-        if ((rc = aq_gcn_backward_tc(params, const_cast<float *>(saved), workspace + W.dg(), B, workspace + W.partial(), st))) return rc;
+        if (aq_train_tc_version() == 2)
+            rc = aq_gcn_backward_tc2(params, const_cast<float *>(saved), workspace + W.dg(), B, workspace + W.partial(), st);
+        else
+            rc = aq_gcn_backward_tc(params, const_cast<float *>(saved), workspace + W.dg(), B, workspace + W.partial(), st);
+        if (rc) return rc;
     } else {
         gcn_backward_kernel<<<kSlots, kGcnThreads, sizeof(GcnBwdSmem), st>>>(params, saved, B, workspace);
         if ((rc = aq_check_launch("gcn_backward_kernel"))) return rc;

@@ -55,4 +55,25 @@ __host__ __device__ inline unsigned short *tc_a1t(float *saved, int64_t B) {
     return reinterpret_cast<unsigned short *>(saved + SavedLayout{B}.x(0)) + B * kH * 96;
 }
 
+// Version-2 tensor-core training path (gnn_tc2.cu forward with kSave, gnn_tc2_bwd.cu): the x(0) and x(1) regions hold, per board,
+//   x(0): [B][24576 B] X1^T tiles (bf16, feature-major SWIZZLE_64B, exactly the shared-memory bytes), then per board 6144 B:
+//         the layer-1 node operand transposed, bf16 [16][96] as a K-major SWIZZLE_64B tile (3072 B), and the A_hat coefficients
+//         [81][8] floats {self, up, down, left, right, 0, 0, 0} rounded to tf32 (2592 B);
+//   x(1): [B][24576 B] X2^T tiles, then per board the ReLU mask of layer 3: [128 features][4 words] (81 bits used).
+// x(l) has room for B * 41,472 bytes.
+struct Tc2Saved {
+    int64_t B;
+    static constexpr int64_t kTile = 3 * 16 * 512;
+    __host__ __device__ unsigned char *base(float *saved, int l) const { return reinterpret_cast<unsigned char *>(saved + SavedLayout{B}.x(l)); }
+    __host__ __device__ unsigned char *xt(float *saved, int l, int64_t b) const { return base(saved, l) + b * kTile; }
+    __host__ __device__ unsigned char *a1t(float *saved, int64_t b) const { return base(saved, 0) + B * kTile + b * 6144; }
+    __host__ __device__ float *coef(float *saved, int64_t b) const { return reinterpret_cast<float *>(a1t(saved, b) + 3072); }
+    __host__ __device__ unsigned char *mask3(float *saved, int64_t b) const { return base(saved, 1) + B * kTile + b * 2048; }
+    // byte offset of element (row k < 16, node v < 96) in the K-major SWIZZLE_64B [16][96] tile (three 32-node blocks of 1024 B)
+    __host__ __device__ static uint32_t a1t_off(int k, int v) {
+        return (uint32_t)(v >> 5) * 1024u + (uint32_t)(k >> 3) * 512u + (uint32_t)(k & 7) * 64u +
+               (uint32_t)((((v & 31) >> 3) ^ ((k & 7) >> 1)) << 4) + (uint32_t)(v & 7) * 2u;
+    }
+};
+
 }  // namespace aq

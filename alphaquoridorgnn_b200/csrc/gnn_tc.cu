@@ -356,8 +356,20 @@ static int launch_tc(const float *params, const unsigned char *prepared, const A
     return aq_check_launch("gcn_forward_tc_kernel");
 }
 
-int aq_gcn_forward_tc2(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, cudaStream_t st);  // gnn_tc2.cu
+int aq_gcn_forward_tc2(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, float *saved,
+                       cudaStream_t st);  // gnn_tc2.cu
 int aq_gcn_forward_tc3(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, cudaStream_t st);  // gnn_tc3.cu
+
+// Which tensor-core training pair (forward with saved activations + backward) is used at precision 1; both sides read it here.
+int aq_train_tc_version() {
+    static int v = 0;
+    if (v == 0) {
+        const char *env = getenv("AQ_TRAIN_TC_VERSION");  // 1 = gnn_tc.cu + gnn_tc_bwd.cu, 2 = gnn_tc2.cu + gnn_tc2_bwd.cu
+        v = env ? atoi(env) : 2;
+        if (v != 1) v = 2;
+    }
+    return v;
+}
 
 // saved == nullptr: inference.  saved != nullptr: training forward (activations kept for aq_gnn_backward, precision 1).
 int aq_gcn_forward_tc(const float *params, const void *prepared_v, const AqState *states, int64_t B, float *pooled, float *saved,
@@ -375,7 +387,8 @@ int aq_gcn_forward_tc(const float *params, const void *prepared_v, const AqState
         groups = env ? atoi(env) : 5;
     }
     if (!saved && version == 3) return aq_gcn_forward_tc3(params, prepared_v, states, B, pooled, st);
-    if (!saved && version == 2) return aq_gcn_forward_tc2(params, prepared_v, states, B, pooled, st);
+    if (!saved && version == 2) return aq_gcn_forward_tc2(params, prepared_v, states, B, pooled, nullptr, st);
+    if (saved && aq_train_tc_version() == 2) return aq_gcn_forward_tc2(params, prepared_v, states, B, pooled, saved, st);
     if (saved || groups == 3) return launch_tc<3>(params, prepared, states, B, pooled, saved, sms, st);  // the save variant needs the registers
     if (groups == 4) return launch_tc<4>(params, prepared, states, B, pooled, saved, sms, st);
     return launch_tc<5>(params, prepared, states, B, pooled, saved, sms, st);

@@ -189,8 +189,9 @@ template <int kMode>
 __device__ __forceinline__ uint32_t cvt_pair(float a, float b) {
     return kMode == kToF16 ? cvt2_f16(a, b) : cvt2<kMode == kToBf16Relu>(a, b);
 }
+// grow != nullptr (training forward): the same 16-byte chunks also go to the board's saved tile in global memory
 template <int kMode>
-__device__ __forceinline__ void store_block(uint32_t row_addr, int swz, int cb, const float *z) {
+__device__ __forceinline__ void store_block(uint32_t row_addr, int swz, int cb, const float *z, unsigned char *grow = nullptr) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         uint4 v;
@@ -201,12 +202,13 @@ __device__ __forceinline__ void store_block(uint32_t row_addr, int swz, int cb, 
             v.z = cvt_pair<kMode>(z[q * 8 + 4], z[q * 8 + 5]); v.w = cvt_pair<kMode>(z[q * 8 + 6], z[q * 8 + 7]);
         }
         sts128(row_addr + (uint32_t)cb * kFmBlock + (uint32_t)((q ^ swz) << 4), v);
+        if (grow) *reinterpret_cast<uint4 *>(grow + (uint32_t)cb * kFmBlock + (uint32_t)((q ^ swz) << 4)) = v;
     }
 }
 
 // the three column blocks of this thread's accumulator lane (+ bias) -> its feature row
 template <int kMode>
-__device__ __forceinline__ void epilogue_store(uint32_t tmem_me, uint32_t row_addr, int swz, float bias) {
+__device__ __forceinline__ void epilogue_store(uint32_t tmem_me, uint32_t row_addr, int swz, float bias, unsigned char *grow = nullptr) {
 #pragma unroll
     for (int cb = 0; cb < 3; ++cb) {
         float z[32];
@@ -215,13 +217,18 @@ __device__ __forceinline__ void epilogue_store(uint32_t tmem_me, uint32_t row_ad
 #pragma unroll
             for (int i = 0; i < 32; ++i) z[i] += bias;
         }
-        store_block<kMode>(row_addr, swz, cb, z);
+        store_block<kMode>(row_addr, swz, cb, z, grow);
     }
 }
 
+// kSave (training forward, precision 1): additionally writes what gcn_backward_tc2_kernel needs (layout: gnn_layout.cuh, Tc2Saved):
+// the X1^T and X2^T tiles byte for byte as they sit in shared memory, the ReLU mask of layer 3 (81 bits per feature), the
+// layer-1 node operand transposed [16][96] as a K-major SWIZZLE_64B tile, and the A_hat coefficients rounded to tf32.
+template <bool kSave>
 __global__ void __launch_bounds__(kG * kGroupThreads, 1)
 gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__restrict__ prepared,
-                       const AqState *__restrict__ states, int64_t B, float *__restrict__ pooled_out, uint32_t wait_ns) {
+                       const AqState *__restrict__ states, int64_t B, float *__restrict__ pooled_out, float *__restrict__ saved,
+                       uint32_t wait_ns) {
     constexpr int kThreads = kG * kGroupThreads;
     extern __shared__ unsigned char smem_raw[];
     Tc2Smem &sm = *reinterpret_cast<Tc2Smem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -330,6 +337,8 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
     const uint32_t w1_addr = smem_u32(sm.w1);
     const uint32_t row_addr = fm_addr + (uint32_t)(tid >> 3) * 512u + (uint32_t)(tid & 7) * 64u;  // this thread's feature row
     const int swz = (tid & 7) >> 1;
+    const uint32_t row_off = (uint32_t)(tid >> 3) * 512u + (uint32_t)(tid & 7) * 64u;
+    const Tc2Saved SV{B};
     const float bias2 = __ldg(params + kOffB2 + tid), bias3 = __ldg(params + kOffB3 + tid);   // added in the epilogues (fp32)
     uint32_t phase = 0;
     // The MMAs of a group are issued by its first warp from WARP-UNIFORM values (everything below derives from a shuffled warp
@@ -433,6 +442,21 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
             c1v.z = 0x3F803F80u; c1v.w = 0u;  // 1, 1, 0, 0
             sts128(l1_addr + k2.y, c0v);
             sts128(l1_addr + (k2.y ^ 16u), c1v);
+            if (kSave) {
+                auto tf = [](float c) { return __uint_as_float((__float_as_uint(c) + 0x1000u) & 0xFFFFE000u); };
+                float4 *cf = reinterpret_cast<float4 *>(SV.coef(saved, bn) + v * 8);
+                cf[0] = make_float4(tf(c0), tf(cu), tf(cd), tf(cl));
+                cf[1] = make_float4(tf(cr), 0.f, 0.f, 0.f);
+                unsigned char *at = SV.a1t(saved, bn);
+                const uint32_t wds[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    *reinterpret_cast<unsigned short *>(at + Tc2Saved::a1t_off(k, v)) = (unsigned short)(wds[k >> 1] >> (16 * (k & 1)));
+            }
+        } else if (kSave && tid < kNodesPad) {  // node padding of the transposed layer-1 operand must be zero (it is K of dW1)
+            unsigned char *at = SV.a1t(saved, bn);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) *reinterpret_cast<unsigned short *>(at + Tc2Saved::a1t_off(k, tid)) = 0;
         }
     };
     uint32_t par = 0;  // adjacency buffer of the current board
@@ -459,7 +483,7 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         TC2_T(4);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         // ---- layer 1 epilogue: ReLU -> bf16 -> X1^T row ---------------------------------------------------------------
-        epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz, 0.f);   // (b1 is folded into the layer-1 MMA)
+        epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz, 0.f, kSave ? SV.xt(saved, 0, b) + row_off : nullptr);   // (b1 is folded into the layer-1 MMA)
         float pool = 0.f;
 #pragma unroll 1
         for (int layer = 1; layer < kLayers; ++layer) {
@@ -517,16 +541,23 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         TC2_T(8);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             if (layer + 1 < kLayers) {  // + bias -> ReLU -> bf16 -> X^T row of the next layer
-                epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz, bias2);
+                epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz, bias2, kSave ? SV.xt(saved, 1, b) + row_off : nullptr);
             } else {                    // last layer feeds only the mean pool
+#pragma unroll
+                uint32_t m3[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                 for (int cb = 0; cb < 3; ++cb) {
                     float z[32];
                     tmem_ld32(tmem_me + cb * 32, z);
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (cb * 32 + i < kV) pool += fmaxf(z[i] + bias3, 0.f);
+                        if (cb * 32 + i < kV) {
+                            const float y = z[i] + bias3;
+                            pool += fmaxf(y, 0.f);
+                            if (kSave) m3[cb] |= (y > 0.f ? 1u : 0u) << i;
+                        }
                 }
+                if (kSave) *reinterpret_cast<uint4 *>(SV.mask3(saved, b) + tid * 16) = make_uint4(m3[0], m3[1], m3[2], 0u);
             }
         }
         pooled_out[b * kH + tid] = pool / (float)kV;
@@ -545,8 +576,10 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
 
 }  // namespace
 
-// Inference trunk, version 2.  Same contract as aq_gcn_forward_tc(saved == nullptr).
-int aq_gcn_forward_tc2(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, cudaStream_t st) {
+// Trunk, version 2.  saved == nullptr: inference (same contract as aq_gcn_forward_tc); saved != nullptr: training forward, precision 1,
+// activations kept in the Tc2Saved layout for aq_gcn_backward_tc2.
+int aq_gcn_forward_tc2(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, float *saved,
+                       cudaStream_t st) {
     static int sms = 0;
     static uint32_t wait_ns = 0;
     if (sms == 0) {
@@ -560,8 +593,16 @@ int aq_gcn_forward_tc2(const float *params, const void *prepared, const AqState 
     const size_t smem = sizeof(Tc2Smem) + 1024;
     const int64_t want = (B + kG - 1) / kG;
     const unsigned grid = (unsigned)(want < sms ? want : sms);
-    cudaError_t e = cudaFuncSetAttribute(gcn_forward_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return aq_set_error((int)e, "gcn_forward_tc2 smem");
-    gcn_forward_tc2_kernel<<<grid, kG * kGroupThreads, smem, st>>>(params, reinterpret_cast<const unsigned char *>(prepared), states, B, pooled, wait_ns);
+    const unsigned char *prep = reinterpret_cast<const unsigned char *>(prepared);
+    cudaError_t e;
+    if (saved) {
+        e = cudaFuncSetAttribute(gcn_forward_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return aq_set_error((int)e, "gcn_forward_tc2 smem");
+        gcn_forward_tc2_kernel<true><<<grid, kG * kGroupThreads, smem, st>>>(params, prep, states, B, pooled, saved, wait_ns);
+    } else {
+        e = cudaFuncSetAttribute(gcn_forward_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return aq_set_error((int)e, "gcn_forward_tc2 smem");
+        gcn_forward_tc2_kernel<false><<<grid, kG * kGroupThreads, smem, st>>>(params, prep, states, B, pooled, nullptr, wait_ns);
+    }
     return aq_check_launch("gcn_forward_tc2_kernel");
 }

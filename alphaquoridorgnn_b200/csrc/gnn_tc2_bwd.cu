@@ -1,0 +1,357 @@
+// Tensor-core backward of the GCN trunk, version 2 -- the counterpart of gcn_forward_tc2_kernel<kSave = true> (gnn_tc2.cu).
+// As in the forward, every product is feature-major (one FEATURE per TMEM lane, the board's nodes along the columns) and the
+// aggregation of the gradient runs on the tensor cores too; no stencil arithmetic, no node-major scattered stores.
+//
+// One CTA (128 threads = 128 TMEM lanes), persistent over boards.  Per board and layer l = 3, 2:
+//     dY_l = (X_l > 0) * dX_l          thread f masks its lane of the dX accumulator IN PLACE (tcgen05.ld / tcgen05.st)   (dX_3 = dg / 81)
+//     dZ_l^T = dY_l^T A_hat^T          kind::tf32  A = dY_l^T, the fp32 accumulator columns read in place (A_hat is symmetric: the
+//                                                  transposed-CSR scatter of the backward is the same gather), B = A_hat (tf32, banded)
+//     dZ_l^T -> bf16 -> feature-major tile (thread f writes its own row, 16-byte stores)
+//     dX_{l-1}^T = W_l^T dZ_l^T        kind::f16   A = W_l^T [k][n] (shared memory), B = the tile read MN-major [K = n][N = nodes]
+//     dW_l      += dZ_l^T X_{l-1}      kind::f16   A = the same tile read K-major [M = n][K = nodes], B = X_{l-1}^T tile saved by the forward
+// and for layer 1 (forward: Y_1 = (A_hat X0 | 1) W1ext^T):  dW1ext += dY_1^T A1  with A1^T saved as a [16][96] tile.
+// TF32 keeps the gradient's fp32 exponent range (an fp16 aggregation would underflow: dg / 81 / batch is ~1e-7).
+// The weight-gradient accumulators live in TMEM for the whole kernel (accumulate across boards) and are written once per CTA into
+// its slot of the partial-gradient buffer; reduce_partials_kernel sums the slots in a fixed order (deterministic, atomic-free).
+#include <cstddef>
+#include <cuda_bf16.h>
+#include "gnn_fp32.cuh"
+#include "tc_common.cuh"
+
+using namespace aq;
+using namespace aqtc;
+
+namespace {
+
+constexpr int kNodesPad = 96;
+constexpr uint32_t kFmBlock = 16 * 512;     // feature-major tile: [3 node blocks of 32][16 atoms of 8 features][8][64 B]
+constexpr uint32_t kRowBlock = 128 * 128;   // K-block of a 128-row K-major SWIZZLE_128B tile (W^T)
+constexpr uint32_t kAdjKBlock = 48 * 128;   // adjacency block, one K-block: 48 out-node rows x 32 in-nodes (tf32, 128 B)
+constexpr uint32_t kAdjBlock = 2 * kAdjKBlock;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColX = 0, kColZ = 96, kColW3 = 192, kColW2 = 320, kColW1 = 448;  // TMEM column map (464 used)
+
+constexpr uint32_t kIdescBase = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);                  // D = f32, A = B = bf16, M = 128
+constexpr uint32_t kIdescDX = kIdescBase | (1u << 16) | ((uint32_t)(kNodesPad >> 3) << 17);                // B MN-major, N = 96
+constexpr uint32_t kIdescDW = kIdescBase | ((uint32_t)(128 >> 3) << 17);                                   // K-major, N = 128
+constexpr uint32_t kIdescDW1 = kIdescBase | ((uint32_t)(16 >> 3) << 17);                                   // K-major, N = 16
+constexpr uint32_t kIdescAgg = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24) | ((uint32_t)(48 >> 3) << 17);  // tf32, N = 48
+
+struct Bwd2Smem {
+    unsigned char w2t[2 * kRowBlock];   // W2^T: row k, K = n  (K-major SWIZZLE_128B)
+    unsigned char w3t[2 * kRowBlock];
+    unsigned char fm[3 * kFmBlock];     // dZ^T (bf16, feature-major)
+    unsigned char xt[3 * kFmBlock];     // X_{l-1}^T tile of the forward (bf16, feature-major)
+    unsigned char adj[2 * kAdjBlock];   // A_hat (tf32), two blocks of [48 out nodes][64 in nodes]
+    unsigned char a1t[3 * 1024];        // layer-1 node operand transposed [16][96], K-major SWIZZLE_64B
+    unsigned long long mbar;
+    uint32_t tmem_base;
+};
+static_assert(sizeof(Bwd2Smem) + 1024 <= 227 * 1024, "Bwd2Smem exceeds shared memory");
+
+__device__ __forceinline__ uint32_t chunk_off128(int row, int j, uint32_t kblock) {  // 16-byte chunk j of `row`, K-major SWIZZLE_128B
+    return (uint32_t)(j >> 3) * kblock + (uint32_t)row * 128u + (uint32_t)(((j & 7) ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ uint64_t desc_fm_mn_b(uint32_t saddr) {  // MN-major SWIZZLE_64B: LBO = node-block stride, SBO = 8-feature atom stride
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(kFmBlock >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ uint64_t desc_fm_k_b(uint32_t saddr) {   // K-major SWIZZLE_64B: SBO = 512 B (8 rows x 64 B)
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ void mma_ts_tf32_b(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                 ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st32_b(uint32_t taddr, const uint32_t *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                   "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+                   "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+                   "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void mbar_spin_b(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+// bit i of the result = element i of the 8 packed bf16 is > 0 (post-ReLU values are >= 0)
+__device__ __forceinline__ uint32_t positive_bits_b(uint4 c) {
+    const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+    uint32_t m = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m |= ((w[i] & 0x7FFFu) != 0u ? 1u : 0u) << (2 * i);
+        m |= ((w[i] & 0x7FFF0000u) != 0u ? 1u : 0u) << (2 * i + 1);
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(kGroupThreads, 1)
+gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ saved, const float *__restrict__ dg,
+                        int64_t B, float *__restrict__ partial) {
+    extern __shared__ unsigned char smem_raw[];
+    Bwd2Smem &sm = *reinterpret_cast<Bwd2Smem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const int tid = threadIdx.x;  // = feature = TMEM lane
+    float *slot = partial + (int64_t)blockIdx.x * kNumParams;
+
+    if ((int64_t)blockIdx.x >= B) {  // no board for this CTA: its slot contributes zeros to the GCN ranges
+        for (int i = tid; i < kOffWP0; i += kGroupThreads) slot[i] = 0.f;
+        return;
+    }
+    // W_l^T tiles: element (row k, col n) = W_l[n][k]
+    for (int i = tid; i < 2 * kH * kH; i += kGroupThreads) {
+        const int which = i >> 14, e = i & 16383;
+        const int n = e >> 7, k = e & 127;  // coalesced along k
+        const float w = __ldg(params + (which ? kOffW3 : kOffW2) + e);
+        unsigned char *tile = which ? sm.w3t : sm.w2t;
+        *reinterpret_cast<unsigned short *>(tile + chunk_off128(k, n >> 3, kRowBlock) + (n & 7) * 2) = bf16_bits(w);
+    }
+    for (int c = tid; c < (int)(2 * kAdjBlock / 16); c += kGroupThreads)  // adjacency tile starts as zero; only stencil positions change
+        reinterpret_cast<uint4 *>(sm.adj)[c] = make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t bar = smem_u32(&sm.mbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+
+    const uint32_t tmem = sm.tmem_base;
+    const uint32_t lane_base = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+    const uint32_t w2t_addr = smem_u32(sm.w2t), w3t_addr = smem_u32(sm.w3t), fm_addr = smem_u32(sm.fm), xt_addr = smem_u32(sm.xt);
+    const uint32_t adj_addr = smem_u32(sm.adj), a1t_addr = smem_u32(sm.a1t);
+    const uint32_t row_off = (uint32_t)(tid >> 3) * 512u + (uint32_t)(tid & 7) * 64u;   // this thread's feature row inside a feature-major tile
+    const int swz = (tid & 7) >> 1;
+    const bool issuer_warp = __shfl_sync(0xffffffffu, tid >> 5, 0) == 0;
+    // static tile offsets of the 5 stencil positions of node `tid` (self, up, down, left, right); 0xFFFFFFFF = absent
+    uint32_t aoff[5] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    if (tid < kV) {
+        const int v = tid, r = v / 9, c = v - 9 * r;
+        const int blk = v >= 48 ? 1 : 0, row = v - 48 * blk, kl0 = v - 32 * blk;
+        auto off = [&](int kl) -> uint32_t {
+            return (uint32_t)blk * kAdjBlock + (uint32_t)(kl >> 5) * kAdjKBlock + (uint32_t)row * 128u +
+                   (uint32_t)((((kl & 31) >> 2) ^ (row & 7)) << 4) + (uint32_t)(kl & 3) * 4u;
+        };
+        aoff[0] = off(kl0);
+        if (r >= 1) aoff[1] = off(kl0 - 9);
+        if (r <= 7) aoff[2] = off(kl0 + 9);
+        if (c >= 1) aoff[3] = off(kl0 - 1);
+        if (c <= 7) aoff[4] = off(kl0 + 1);
+    }
+    const Tc2Saved SV{B};
+    float db1 = 0.f, db2 = 0.f, db3 = 0.f;
+    uint32_t phase = 0;
+    bool first = true;
+
+    // copies one saved 24 KB feature-major tile into sm.xt (byte for byte)
+    auto load_xt = [&](const unsigned char *g) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g);
+        uint4 *dst = reinterpret_cast<uint4 *>(sm.xt);
+#pragma unroll
+        for (int j = 0; j < 12; ++j) dst[tid + kGroupThreads * j] = __ldg(src + tid + kGroupThreads * j);
+    };
+    // ReLU mask of the layer whose activations are in sm.xt: this thread's feature row -> 96 bits
+    auto mask_from_xt = [&](uint32_t *m) {
+        m[0] = m[1] = m[2] = 0u;
+#pragma unroll
+        for (int c8 = 0; c8 < 12; ++c8) {
+            const uint4 ch = *reinterpret_cast<const uint4 *>(sm.xt + row_off + (uint32_t)(c8 >> 2) * kFmBlock + (uint32_t)(((c8 & 3) ^ swz) << 4));
+            m[c8 >> 2] |= positive_bits_b(ch) << (8 * (c8 & 3));
+        }
+    };
+    // this thread's 32 values -> bf16 -> node block cb of its row of sm.fm (nodes >= 81 written as zero: K padding of the dW MMAs)
+    auto store_block_bf16 = [&](int cb, const float *z) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 v;
+            if (cb == 2 && q == 3) v = make_uint4(0u, 0u, 0u, 0u);
+            else if (cb == 2 && q == 2) v = make_uint4(pack_bf16(z[16], 0.f), 0u, 0u, 0u);
+            else v = pack8_bf16(z + q * 8);
+            *reinterpret_cast<uint4 *>(sm.fm + row_off + (uint32_t)cb * kFmBlock + (uint32_t)((q ^ swz) << 4)) = v;
+        }
+    };
+    auto sync_then_issue_begin = [&]() {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+    };
+    auto wait_mma = [&]() {
+        mbar_spin_b(bar, phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    };
+
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        // ---- per-board inputs: A_hat coefficients -> adjacency tile, X2^T -> xt, A1^T -> a1t, ReLU mask of layer 3 ---------
+        if (tid < kV) {
+            const float4 *cf = reinterpret_cast<const float4 *>(SV.coef(saved, b) + tid * 8);
+            const float4 c0 = cf[0], c1 = cf[1];
+            const float cv[5] = {c0.x, c0.y, c0.z, c0.w, c1.x};
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+                if (aoff[k] != 0xFFFFFFFFu) *reinterpret_cast<float *>(sm.adj + aoff[k]) = cv[k];
+        }
+        load_xt(SV.xt(saved, 1, b));
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(SV.a1t(saved, b));
+            uint4 *dst = reinterpret_cast<uint4 *>(sm.a1t);
+            dst[tid] = __ldg(src + tid);
+            if (tid < 64) dst[128 + tid] = __ldg(src + 128 + tid);
+        }
+        uint32_t m[3];
+        {
+            const uint4 mk = __ldg(reinterpret_cast<const uint4 *>(SV.mask3(saved, b) + tid * 16));
+            m[0] = mk.x; m[1] = mk.y; m[2] = mk.z;
+        }
+        const float dgn = dg[b * kH + tid] / (float)kV;  // d mean / d x_v
+#pragma unroll 1
+        for (int layer = 2; layer >= 1; --layer) {
+            // ---- dY of layer (layer + 1): masked dX, written (back) into this thread's lane of the dX accumulator ----------------
+            {
+                float bsum = 0.f;
+#pragma unroll
+                for (int cb = 0; cb < 3; ++cb) {
+                    uint32_t r[32];
+                    if (layer == 2) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = (m[cb] >> i) & 1u ? __float_as_uint(dgn) : 0u;
+                        bsum += (float)__popc(m[cb]) * dgn;
+                    } else {
+                        float y[32];
+                        tmem_ld32(lane_base + kColX + cb * 32, y);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float t = (m[cb] >> i) & 1u ? y[i] : 0.f;
+                            bsum += t;
+                            r[i] = __float_as_uint(t);
+                        }
+                    }
+                    tmem_st32_b(lane_base + kColX + cb * 32, r);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+                if (layer == 2) db3 += bsum; else db2 += bsum;
+            }
+            // ---- dZ^T = dY^T A_hat^T : tf32, A = the accumulator columns just written -------------------------------------------
+            sync_then_issue_begin();
+            if (issuer_warp) {
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                if (elect_one_lane()) {
+#pragma unroll
+                    for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+                        for (int s = 0; s < 8; ++s)  // 64 in-nodes = 8 K steps of 8 tf32
+                            mma_ts_tf32_b(tmem + kColZ + blk * 48, tmem + kColX + blk * 32 + s * 8,
+                                          desc_sw128(adj_addr + (uint32_t)blk * kAdjBlock + (uint32_t)(s >> 2) * kAdjKBlock + (uint32_t)(s & 3) * 32u),
+                                          kIdescAgg, s ? 1u : 0u);
+                    mma_commit(bar);
+                }
+                __syncwarp();
+            }
+            wait_mma();
+            // ---- dZ^T -> bf16 -> feature-major tile ----------------------------------------------------------------------------
+#pragma unroll
+            for (int cb = 0; cb < 3; ++cb) {
+                float z[32];
+                tmem_ld32(lane_base + kColZ + cb * 32, z);
+                store_block_bf16(cb, z);
+            }
+            // ---- dX_{l}^T = W^T dZ^T (into the dX accumulator) and dW += dZ^T X ------------------------------------------------
+            sync_then_issue_begin();
+            if (issuer_warp) {
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                if (elect_one_lane()) {
+                    const uint32_t wt = layer == 2 ? w3t_addr : w2t_addr;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)  // M = 128 (k_in), N = 96 (nodes), K = 128 (n_out): two 8-feature atoms of the tile per step
+                        mma_bf16(tmem + kColX, desc_sw128(wt + (uint32_t)(k >> 2) * kRowBlock + (uint32_t)(k & 3) * 32u),
+                                 desc_fm_mn_b(fm_addr + k * 1024), kIdescDX, k > 0 ? 1u : 0u);
+                    const uint32_t accw = tmem + (layer == 2 ? kColW3 : kColW2);
+#pragma unroll
+                    for (int s = 0; s < 6; ++s)  // M = 128 (n_out), N = 128 (k_in), K = 96 (nodes): 32 B per step inside a 64 B node block
+                        mma_bf16(accw, desc_fm_k_b(fm_addr + (uint32_t)(s >> 1) * kFmBlock + (uint32_t)(s & 1) * 32u),
+                                 desc_fm_k_b(xt_addr + (uint32_t)(s >> 1) * kFmBlock + (uint32_t)(s & 1) * 32u), kIdescDW, (first && s == 0) ? 0u : 1u);
+                    mma_commit(bar);
+                }
+                __syncwarp();
+            }
+            wait_mma();
+            // ---- mask of the layer below from its activations (this thread's row of xt); then the next operand tile ------------
+            mask_from_xt(m);
+            __syncthreads();  // every thread has read its row before the tile is replaced
+            if (layer == 2) load_xt(SV.xt(saved, 0, b));
+        }
+        // ---- layer 1: dY1 = mask1 * dX1 -> bf16 tile;  dW1ext += dY1^T A1 ------------------------------------------------------------
+        {
+            float bsum = 0.f;
+#pragma unroll
+            for (int cb = 0; cb < 3; ++cb) {
+                float y[32];
+                tmem_ld32(lane_base + kColX + cb * 32, y);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    y[i] = (m[cb] >> i) & 1u ? y[i] : 0.f;
+                    bsum += y[i];
+                }
+                store_block_bf16(cb, y);
+            }
+            db1 += bsum;
+        }
+        sync_then_issue_begin();
+        if (issuer_warp) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (elect_one_lane()) {
+#pragma unroll
+                for (int s = 0; s < 6; ++s)  // M = 128, N = 16, K = 96
+                    mma_bf16(tmem + kColW1, desc_fm_k_b(fm_addr + (uint32_t)(s >> 1) * kFmBlock + (uint32_t)(s & 1) * 32u),
+                             desc_fm_k_b(a1t_addr + (uint32_t)(s >> 1) * 1024u + (uint32_t)(s & 1) * 32u), kIdescDW1, (first && s == 0) ? 0u : 1u);
+                mma_commit(bar);
+            }
+            __syncwarp();
+        }
+        wait_mma();
+        first = false;
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();  // next board overwrites the tiles
+    }
+    // ---- this CTA's partial gradients: accumulator rows -> its slot ---------------------------------------------
+    {
+        float v[32];
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+            tmem_ld32(lane_base + kColW2 + cb * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) slot[kOffW2 + tid * kH + cb * 32 + i] = v[i];
+            tmem_ld32(lane_base + kColW3 + cb * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) slot[kOffW3 + tid * kH + cb * 32 + i] = v[i];
+        }
+        tmem_ld32(lane_base + kColW1, v);  // 16 columns used: [hi part (6) | lo part (6) | bias_hi | bias_lo | 0 | 0]
+#pragma unroll
+        for (int f = 0; f < kF; ++f) slot[kOffW1 + tid * kF + f] = v[f] + v[kF + f];  // both halves multiply W1
+        slot[kOffB1 + tid] = db1;
+        slot[kOffB2 + tid] = db2;
+        slot[kOffB3 + tid] = db3;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+}  // namespace
+
+// partial: [kSlots = 148][64082] floats; this kernel fills the GCN ranges (W1,B1,W2,B2,W3,B3) of every slot
+int aq_gcn_backward_tc2(const float *params, float *saved, const float *dg, int64_t B, float *partial, cudaStream_t st) {
+    const size_t smem = sizeof(Bwd2Smem) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(gcn_backward_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return aq_set_error((int)e, "gcn_backward_tc2 smem");
+    gcn_backward_tc2_kernel<<<148, kGroupThreads, smem, st>>>(params, saved, dg, B, partial);
+    return aq_check_launch("gcn_backward_tc2_kernel");
+}
