@@ -21,6 +21,22 @@
 using namespace aq;
 using namespace aqtc;
 
+#ifndef TC2B_TIMING
+#define TC2B_TIMING 0    // 1: per-phase clock64 accounting by thread 0 of CTA 0 (debug variant, scripts/bwd_timing.py)
+#endif
+#if TC2B_TIMING
+__device__ long long g_tc2b_timing[16];
+#define TC2B_T(slot) do { if (blockIdx.x == 0 && tid == 0) { const long long t_ = clock64(); g_tc2b_timing[slot] += t_ - t_last; t_last = t_; } } while (0)
+extern "C" int aq_debug_bwd_timing(long long *out) {
+    cudaMemcpyFromSymbol(out, g_tc2b_timing, sizeof(long long) * 16);
+    long long z[16] = {0};
+    cudaMemcpyToSymbol(g_tc2b_timing, z, sizeof(z));
+    return 0;
+}
+#else
+#define TC2B_T(slot) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kNodesPad = 96;
@@ -37,13 +53,20 @@ constexpr uint32_t kIdescDW = kIdescBase | ((uint32_t)(128 >> 3) << 17);        
 constexpr uint32_t kIdescDW1 = kIdescBase | ((uint32_t)(16 >> 3) << 17);                                   // K-major, N = 16
 constexpr uint32_t kIdescAgg = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24) | ((uint32_t)(48 >> 3) << 17);  // tf32, N = 48
 
+struct BoardIn {
+    unsigned char xt2[3 * kFmBlock];    // X2^T tile (bf16, feature-major): B operand of dW3, and the ReLU mask of layer 2
+    unsigned char xt1[3 * kFmBlock];    // X1^T tile: B operand of dW2, and the ReLU mask of layer 1
+    unsigned char a1t[3 * 1024];        // layer-1 node operand transposed [16][96], K-major SWIZZLE_64B: B operand of dW1ext
+    float coef[kV * 8 + 120];           // A_hat coefficients [81][8] (tf32): {self, up, down, left, right, 0, 0, 0}
+};
+static_assert(sizeof(BoardIn) % 1024 == 0, "board inputs must keep 1024-byte alignment");
+
 struct Bwd2Smem {
     unsigned char w2t[2 * kRowBlock];   // W2^T: row k, K = n  (K-major SWIZZLE_128B)
     unsigned char w3t[2 * kRowBlock];
     unsigned char fm[3 * kFmBlock];     // dZ^T (bf16, feature-major)
-    unsigned char xt[3 * kFmBlock];     // X_{l-1}^T tile of the forward (bf16, feature-major)
     unsigned char adj[2 * kAdjBlock];   // A_hat (tf32), two blocks of [48 out nodes][64 in nodes]
-    unsigned char a1t[3 * 1024];        // layer-1 node operand transposed [16][96], K-major SWIZZLE_64B
+    BoardIn in[2];                      // what the forward saved for a board, double-buffered: the next board's arrives (cp.async) during this one
     unsigned long long mbar;
     uint32_t tmem_base;
 };
@@ -126,8 +149,8 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
 
     const uint32_t tmem = sm.tmem_base;
     const uint32_t lane_base = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
-    const uint32_t w2t_addr = smem_u32(sm.w2t), w3t_addr = smem_u32(sm.w3t), fm_addr = smem_u32(sm.fm), xt_addr = smem_u32(sm.xt);
-    const uint32_t adj_addr = smem_u32(sm.adj), a1t_addr = smem_u32(sm.a1t);
+    const uint32_t w2t_addr = smem_u32(sm.w2t), w3t_addr = smem_u32(sm.w3t), fm_addr = smem_u32(sm.fm);
+    const uint32_t adj_addr = smem_u32(sm.adj), in_addr = smem_u32(&sm.in[0]);
     const uint32_t row_off = (uint32_t)(tid >> 3) * 512u + (uint32_t)(tid & 7) * 64u;   // this thread's feature row inside a feature-major tile
     const int swz = (tid & 7) >> 1;
     const bool issuer_warp = __shfl_sync(0xffffffffu, tid >> 5, 0) == 0;
@@ -151,19 +174,29 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
     uint32_t phase = 0;
     bool first = true;
 
-    // copies one saved 24 KB feature-major tile into sm.xt (byte for byte)
-    auto load_xt = [&](const unsigned char *g) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(g);
-        uint4 *dst = reinterpret_cast<uint4 *>(sm.xt);
+    // cp.async of everything the forward saved for board bn into buffer `buf` (byte for byte; 16 bytes per copy)
+    auto prefetch_board = [&](int64_t bn, int buf) {
+        const uint32_t dst = in_addr + (uint32_t)buf * (uint32_t)sizeof(BoardIn);
+        auto cp16 = [&](uint32_t d, const unsigned char *g) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(g) : "memory");
+        };
+        const unsigned char *g2 = SV.xt(saved, 1, bn), *g1 = SV.xt(saved, 0, bn), *ga = SV.a1t(saved, bn);
 #pragma unroll
-        for (int j = 0; j < 12; ++j) dst[tid + kGroupThreads * j] = __ldg(src + tid + kGroupThreads * j);
+        for (int j = 0; j < 12; ++j) {
+            cp16(dst + (uint32_t)offsetof(BoardIn, xt2) + (uint32_t)(tid + kGroupThreads * j) * 16u, g2 + (tid + kGroupThreads * j) * 16);
+            cp16(dst + (uint32_t)offsetof(BoardIn, xt1) + (uint32_t)(tid + kGroupThreads * j) * 16u, g1 + (tid + kGroupThreads * j) * 16);
+        }
+        // a1t (3072 B) and the coefficients (2592 B) are contiguous in the saved layout: 354 chunks of 16 B
+        for (int c = tid; c < (3072 + kV * 32) / 16; c += kGroupThreads)
+            cp16(dst + (uint32_t)offsetof(BoardIn, a1t) + (uint32_t)c * 16u, ga + c * 16);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
-    // ReLU mask of the layer whose activations are in sm.xt: this thread's feature row -> 96 bits
-    auto mask_from_xt = [&](uint32_t *m) {
+    // ReLU mask of a layer from its saved activations: this thread's feature row of the tile -> 96 bits
+    auto mask_from_tile = [&](const unsigned char *tile, uint32_t *m) {
         m[0] = m[1] = m[2] = 0u;
 #pragma unroll
         for (int c8 = 0; c8 < 12; ++c8) {
-            const uint4 ch = *reinterpret_cast<const uint4 *>(sm.xt + row_off + (uint32_t)(c8 >> 2) * kFmBlock + (uint32_t)(((c8 & 3) ^ swz) << 4));
+            const uint4 ch = *reinterpret_cast<const uint4 *>(tile + row_off + (uint32_t)(c8 >> 2) * kFmBlock + (uint32_t)(((c8 & 3) ^ swz) << 4));
             m[c8 >> 2] |= positive_bits_b(ch) << (8 * (c8 & 3));
         }
     };
@@ -189,29 +222,37 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     };
 
-    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-        // ---- per-board inputs: A_hat coefficients -> adjacency tile, X2^T -> xt, A1^T -> a1t, ReLU mask of layer 3 ---------
+    int buf = 0;
+    prefetch_board(blockIdx.x, 0);
+#if TC2B_TIMING
+    long long t_last = clock64();
+#endif
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x, buf ^= 1) {
+        // ---- per-board inputs: wait for this board's saved tiles, start the next board's; masks, coefficients -> adjacency tile -------
+        uint32_t m3[3], m2[3], m1[3];
+        {
+            const uint4 mk = __ldg(reinterpret_cast<const uint4 *>(SV.mask3(saved, b) + tid * 16));
+            m3[0] = mk.x; m3[1] = mk.y; m3[2] = mk.z;
+        }
+        const float dgn = dg[b * kH + tid] / (float)kV;  // d mean / d x_v
+        TC2B_T(0);
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();   // the copies of every thread have landed; every thread is done with the other buffer (previous board)
+        if (b + gridDim.x < B) prefetch_board(b + gridDim.x, buf ^ 1);
+        const BoardIn &in = sm.in[buf];
+        const uint32_t xt2_addr = in_addr + (uint32_t)buf * (uint32_t)sizeof(BoardIn), xt1_addr = xt2_addr + (uint32_t)offsetof(BoardIn, xt1);
+        const uint32_t a1t_addr = xt2_addr + (uint32_t)offsetof(BoardIn, a1t);
         if (tid < kV) {
-            const float4 *cf = reinterpret_cast<const float4 *>(SV.coef(saved, b) + tid * 8);
-            const float4 c0 = cf[0], c1 = cf[1];
+            const float4 c0 = *reinterpret_cast<const float4 *>(in.coef + tid * 8), c1 = *reinterpret_cast<const float4 *>(in.coef + tid * 8 + 4);
             const float cv[5] = {c0.x, c0.y, c0.z, c0.w, c1.x};
 #pragma unroll
             for (int k = 0; k < 5; ++k)
                 if (aoff[k] != 0xFFFFFFFFu) *reinterpret_cast<float *>(sm.adj + aoff[k]) = cv[k];
         }
-        load_xt(SV.xt(saved, 1, b));
-        {
-            const uint4 *src = reinterpret_cast<const uint4 *>(SV.a1t(saved, b));
-            uint4 *dst = reinterpret_cast<uint4 *>(sm.a1t);
-            dst[tid] = __ldg(src + tid);
-            if (tid < 64) dst[128 + tid] = __ldg(src + 128 + tid);
-        }
-        uint32_t m[3];
-        {
-            const uint4 mk = __ldg(reinterpret_cast<const uint4 *>(SV.mask3(saved, b) + tid * 16));
-            m[0] = mk.x; m[1] = mk.y; m[2] = mk.z;
-        }
-        const float dgn = dg[b * kH + tid] / (float)kV;  // d mean / d x_v
+        TC2B_T(1);
+        mask_from_tile(in.xt2, m2);
+        mask_from_tile(in.xt1, m1);
+        TC2B_T(2);
 #pragma unroll 1
         for (int layer = 2; layer >= 1; --layer) {
             // ---- dY of layer (layer + 1): masked dX, written (back) into this thread's lane of the dX accumulator ----------------
@@ -222,14 +263,14 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
                     uint32_t r[32];
                     if (layer == 2) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) r[i] = (m[cb] >> i) & 1u ? __float_as_uint(dgn) : 0u;
-                        bsum += (float)__popc(m[cb]) * dgn;
+                        for (int i = 0; i < 32; ++i) r[i] = (m3[cb] >> i) & 1u ? __float_as_uint(dgn) : 0u;
+                        bsum += (float)__popc(m3[cb]) * dgn;
                     } else {
                         float y[32];
                         tmem_ld32(lane_base + kColX + cb * 32, y);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const float t = (m[cb] >> i) & 1u ? y[i] : 0.f;
+                            const float t = (m2[cb] >> i) & 1u ? y[i] : 0.f;
                             bsum += t;
                             r[i] = __float_as_uint(t);
                         }
@@ -239,6 +280,7 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
                 asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
                 if (layer == 2) db3 += bsum; else db2 += bsum;
             }
+            TC2B_T(3);
             // ---- dZ^T = dY^T A_hat^T : tf32, A = the accumulator columns just written -------------------------------------------
             sync_then_issue_begin();
             if (issuer_warp) {
@@ -256,6 +298,7 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
                 __syncwarp();
             }
             wait_mma();
+            TC2B_T(4);
             // ---- dZ^T -> bf16 -> feature-major tile ----------------------------------------------------------------------------
 #pragma unroll
             for (int cb = 0; cb < 3; ++cb) {
@@ -263,6 +306,7 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
                 tmem_ld32(lane_base + kColZ + cb * 32, z);
                 store_block_bf16(cb, z);
             }
+            TC2B_T(5);
             // ---- dX_{l}^T = W^T dZ^T (into the dX accumulator) and dW += dZ^T X ------------------------------------------------
             sync_then_issue_begin();
             if (issuer_warp) {
@@ -277,16 +321,13 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
 #pragma unroll
                     for (int s = 0; s < 6; ++s)  // M = 128 (n_out), N = 128 (k_in), K = 96 (nodes): 32 B per step inside a 64 B node block
                         mma_bf16(accw, desc_fm_k_b(fm_addr + (uint32_t)(s >> 1) * kFmBlock + (uint32_t)(s & 1) * 32u),
-                                 desc_fm_k_b(xt_addr + (uint32_t)(s >> 1) * kFmBlock + (uint32_t)(s & 1) * 32u), kIdescDW, (first && s == 0) ? 0u : 1u);
+                                 desc_fm_k_b((layer == 2 ? xt2_addr : xt1_addr) + (uint32_t)(s >> 1) * kFmBlock + (uint32_t)(s & 1) * 32u), kIdescDW, (first && s == 0) ? 0u : 1u);
                     mma_commit(bar);
                 }
                 __syncwarp();
             }
             wait_mma();
-            // ---- mask of the layer below from its activations (this thread's row of xt); then the next operand tile ------------
-            mask_from_xt(m);
-            __syncthreads();  // every thread has read its row before the tile is replaced
-            if (layer == 2) load_xt(SV.xt(saved, 0, b));
+            TC2B_T(6);
         }
         // ---- layer 1: dY1 = mask1 * dX1 -> bf16 tile;  dW1ext += dY1^T A1 ------------------------------------------------------------
         {
@@ -297,13 +338,14 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
                 tmem_ld32(lane_base + kColX + cb * 32, y);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    y[i] = (m[cb] >> i) & 1u ? y[i] : 0.f;
+                    y[i] = (m1[cb] >> i) & 1u ? y[i] : 0.f;
                     bsum += y[i];
                 }
                 store_block_bf16(cb, y);
             }
             db1 += bsum;
         }
+        TC2B_T(7);
         sync_then_issue_begin();
         if (issuer_warp) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -317,9 +359,9 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
             __syncwarp();
         }
         wait_mma();
+        TC2B_T(8);
         first = false;
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-        __syncthreads();  // next board overwrites the tiles
+        // (no barrier here: the next board starts with one, after its cp.async wait)
     }
     // ---- this CTA's partial gradients: accumulator rows -> its slot ---------------------------------------------
     {
