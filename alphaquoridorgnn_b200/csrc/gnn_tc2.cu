@@ -483,7 +483,7 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         TC2_T(4);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         // ---- layer 1 epilogue: ReLU -> bf16 -> X1^T row ---------------------------------------------------------------
-        epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz, 0.f, kSave ? SV.xt(saved, 0, b) + row_off : nullptr);   // (b1 is folded into the layer-1 MMA)
+        epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz, 0.f);   // (b1 is folded into the layer-1 MMA)
         float pool = 0.f;
 #pragma unroll 1
         for (int layer = 1; layer < kLayers; ++layer) {
@@ -496,9 +496,16 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 if (elect_one()) {
                     const uint32_t w_tmem = tmem_base_u + (layer == 1 ? kTmemW2 : kTmemW3);
+                    if (kSave) {  // training forward: the X^T tile just completed goes to global memory as one bulk copy (TMA), byte for byte
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                                     ::"l"(SV.xt(saved, layer - 1, b)), "r"(fm_u), "r"(3u * kFmBlock) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                    }
 #pragma unroll
                     for (int k = 0; k < 8; ++k)  // K = 128 features = 8 x 16: 8 TMEM columns of A, two 8-feature atoms of B per step
                         mma_ts(tmem_d_u, w_tmem + k * 8, desc_fm_mn(fm_u + k * 1024), kIdescT, k > 0 ? 1u : 0u);
+                    // the tile is overwritten after this phase: the commit is held back until the bulk copy has read it
+                    if (kSave) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
                     mma_commit(bar_u);
                 }
                 __syncwarp();
@@ -541,7 +548,7 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         TC2_T(8);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             if (layer + 1 < kLayers) {  // + bias -> ReLU -> bf16 -> X^T row of the next layer
-                epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz, bias2, kSave ? SV.xt(saved, 1, b) + row_off : nullptr);
+                epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz, bias2);
             } else {                    // last layer feeds only the mean pool
 #pragma unroll
                 uint32_t m3[4] = {0u, 0u, 0u, 0u};
