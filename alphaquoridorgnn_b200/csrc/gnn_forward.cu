@@ -283,7 +283,8 @@ static int set_smem(K kernel, size_t bytes) {
 int aq_gcn_forward_tc(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, float *saved,
                       cudaStream_t st);  // gnn_tc.cu
 int aq_heads_forward_tc(const float *params, const void *prepared, const float *pooled, int64_t B, float *policy, float *value,
-                        const uint32_t *legal_mask, cudaStream_t st);  // heads_tc.cu
+                        const uint32_t *legal_mask, float *saved, cudaStream_t st);  // heads_tc.cu
+int aq_train_tc_version();                                                           // gnn_tc.cu
 
 static int launch_trunk(const float *params, const void *prepared, const AqState *states, const float *x,
                         const uint8_t *open_mask, int64_t B, float *pooled, float *saved, int precision, cudaStream_t st) {
@@ -305,7 +306,9 @@ static int launch_trunk(const float *params, const void *prepared, const AqState
 
 static int launch_heads(const float *params, const void *prepared, const float *pooled, int64_t B, float *policy,
                         float *value, const uint32_t *legal_mask, float *saved, int precision, cudaStream_t st) {
-    if (precision == 1 && !saved) return aq_heads_forward_tc(params, prepared, pooled, B, policy, value, legal_mask, st);
+    // tensor-core heads: inference, and the training forward of the version-2 pair (hidden activations etc. saved by the kernel)
+    if (precision == 1 && (!saved || (aq_train_tc_version() == 2 && !legal_mask)))
+        return aq_heads_forward_tc(params, prepared, pooled, B, policy, value, legal_mask, saved, st);
     const int64_t hb = (B + 7) / 8;
     const unsigned hgrid = (unsigned)(hb < num_sms() ? hb : num_sms());
     int rc;

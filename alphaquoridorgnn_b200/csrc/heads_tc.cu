@@ -96,7 +96,9 @@ template <bool kLegal>
 __global__ void __launch_bounds__(kHtThreads)
 heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *__restrict__ prepared,
                         const float *__restrict__ pooled, int64_t B, float *__restrict__ policy,
-                        float *__restrict__ value, const uint32_t *__restrict__ mask) {
+                        float *__restrict__ value, const uint32_t *__restrict__ mask, float *__restrict__ saved) {
+    // saved != nullptr (training forward, precision 1): the post-ReLU hidden activations (fp32, before the bf16 rounding that feeds
+    // GEMM 2), the probabilities and the value are also written into the SavedLayout regions heads_backward_kernel reads
     extern __shared__ unsigned char smem_raw[];
     HtSmem &sm = *reinterpret_cast<HtSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -190,16 +192,30 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
     {
         float v[32];
         ld32(lane_base + q * 32, v);
+        const SavedLayout SL{B};
         if (q < 2) {  // bias + ReLU -> bf16 A2 (K-block 0 of the A region; GEMM 1 is done with it)
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + sm.bp0[q * 32 + i], 0.f);
+            if (saved && valid) {
+                float4 *dst = reinterpret_cast<float4 *>(saved + SL.hp() + (b0 + row) * kHH + q * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4 *>(sm.a + sw128(row, q * 4 + i)) = pack8(v + 8 * i);
         } else {      // Linear(64 -> 1) on relu(hidden) in fp32: each quarter sums its 32 hidden units
             float u = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) u = fmaf(fmaxf(v[i] + sm.bv0[(q - 2) * 32 + i], 0.f), sm.wv2[(q - 2) * 32 + i], u);
+            for (int i = 0; i < 32; ++i) {
+                v[i] = fmaxf(v[i] + sm.bv0[(q - 2) * 32 + i], 0.f);
+                u = fmaf(v[i], sm.wv2[(q - 2) * 32 + i], u);
+            }
             sm.xch[3][q][row] = u;
+            if (saved && valid) {
+                float4 *dst = reinterpret_cast<float4 *>(saved + SL.hv() + (b0 + row) * kHH + (q - 2) * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
         }
     }
     // ---- GEMM 2: logits ------------------------------------------------------------------------------------
@@ -214,7 +230,11 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
             mma(tmem, desc_sw128(a_addr + k * 32u), desc_sw128(b2_addr + k * 32u), idesc, k > 0 ? 1u : 0u);
         commit(bar);
     }
-    if (q == 2 && valid) value[b0 + row] = tanhf(sm.bv2 + sm.xch[3][2][row] + sm.xch[3][3][row]);  // (the barrier before GEMM 2 ordered the partials)
+    if (q == 2 && valid) {  // (the barrier before GEMM 2 ordered the partials)
+        const float val = tanhf(sm.bv2 + sm.xch[3][2][row] + sm.xch[3][3][row]);
+        value[b0 + row] = val;
+        if (saved) saved[SavedLayout{B}.value() + b0 + row] = val;
+    }
     wait(bar, 1);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     // ---- epilogue 2: softmax of the row (+ legal restriction).  Quarter q owns column blocks 2q and 2q + 1 (quarter 3: block 6
@@ -289,7 +309,11 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
             if (col < kP) {
 #pragma unroll 8
                 for (int r = 0; r < 32; ++r)
-                    if (b0 + r0 + r < B) policy[(b0 + r0 + r) * kP + col] = stage[r * kStagePitch + lane];
+                    if (b0 + r0 + r < B) {
+                        const float pr = stage[r * kStagePitch + lane];
+                        policy[(b0 + r0 + r) * kP + col] = pr;
+                        if (saved) saved[SavedLayout{B}.policy() + (b0 + r0 + r) * kP + col] = pr;
+                    }
             }
             __syncwarp();
         }
@@ -302,7 +326,7 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
 }  // namespace
 
 int aq_heads_forward_tc(const float *params, const void *prepared_v, const float *pooled, int64_t B, float *policy,
-                        float *value, const uint32_t *legal_mask, cudaStream_t st) {
+                        float *value, const uint32_t *legal_mask, float *saved, cudaStream_t st) {
     const unsigned char *prepared = reinterpret_cast<const unsigned char *>(prepared_v);
     const size_t smem = sizeof(HtSmem) + 1024;
     const unsigned grid = (unsigned)((B + kTile - 1) / kTile);
@@ -310,11 +334,11 @@ int aq_heads_forward_tc(const float *params, const void *prepared_v, const float
     if (legal_mask) {
         e = cudaFuncSetAttribute(heads_forward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return aq_set_error((int)e, "heads_forward_tc smem");
-        heads_forward_tc_kernel<true><<<grid, kHtThreads, smem, st>>>(params, prepared, pooled, B, policy, value, legal_mask);
+        heads_forward_tc_kernel<true><<<grid, kHtThreads, smem, st>>>(params, prepared, pooled, B, policy, value, legal_mask, saved);
     } else {
         e = cudaFuncSetAttribute(heads_forward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return aq_set_error((int)e, "heads_forward_tc smem");
-        heads_forward_tc_kernel<false><<<grid, kHtThreads, smem, st>>>(params, prepared, pooled, B, policy, value, nullptr);
+        heads_forward_tc_kernel<false><<<grid, kHtThreads, smem, st>>>(params, prepared, pooled, B, policy, value, nullptr, saved);
     }
     return aq_check_launch("heads_forward_tc_kernel");
 }
