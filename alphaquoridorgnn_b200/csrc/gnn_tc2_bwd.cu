@@ -67,7 +67,8 @@ struct Bwd2Smem {
     unsigned char fm[3 * kFmBlock];     // dZ^T (bf16, feature-major)
     unsigned char adj[2 * kAdjBlock];   // A_hat (tf32), two blocks of [48 out nodes][64 in nodes]
     BoardIn in[2];                      // what the forward saved for a board, double-buffered: the next board's arrives (cp.async) during this one
-    unsigned long long mbar;
+    unsigned long long mbar;            // aggregation / dX MMAs done (the threads need their result)
+    unsigned long long mbar_w;          // weight-gradient MMAs done (only their operand buffers must not be overwritten earlier)
     uint32_t tmem_base;
 };
 static_assert(sizeof(Bwd2Smem) + 1024 <= 227 * 1024, "Bwd2Smem exceeds shared memory");
@@ -136,6 +137,7 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
     const uint32_t bar = smem_u32(&sm.mbar);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&sm.mbar_w)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (tid < 32) {
@@ -216,6 +218,19 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncthreads();
     };
+    // The weight-gradient MMAs (dW3, dW2, dW1ext) produce nothing a thread reads before the end of the kernel: they are committed to
+    // their own mbarrier and only waited for right before one of their operand buffers (the dZ tile, the saved-input buffer) is
+    // overwritten, so they overlap the next phase.
+    const uint32_t bar_w = smem_u32(&sm.mbar_w);
+    uint32_t phase_w = 0;
+    bool w_pending = false;
+    auto wait_dw = [&]() {
+        if (w_pending) {
+            mbar_spin_b(bar_w, phase_w);
+            phase_w ^= 1u;
+            w_pending = false;
+        }
+    };
     auto wait_mma = [&]() {
         mbar_spin_b(bar, phase);
         phase ^= 1u;
@@ -236,6 +251,7 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
         }
         const float dgn = dg[b * kH + tid] / (float)kV;  // d mean / d x_v
         TC2B_T(0);
+        wait_dw();         // dW1ext of the previous board has read its A1^T tile (the buffer the prefetch below overwrites)
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();   // the copies of every thread have landed; every thread is done with the other buffer (previous board)
         if (b + gridDim.x < B) prefetch_board(b + gridDim.x, buf ^ 1);
@@ -300,6 +316,7 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
             wait_mma();
             TC2B_T(4);
             // ---- dZ^T -> bf16 -> feature-major tile ----------------------------------------------------------------------------
+            wait_dw();  // the previous weight-gradient MMA has read the tile
 #pragma unroll
             for (int cb = 0; cb < 3; ++cb) {
                 float z[32];
@@ -317,19 +334,22 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
                     for (int k = 0; k < 8; ++k)  // M = 128 (k_in), N = 96 (nodes), K = 128 (n_out): two 8-feature atoms of the tile per step
                         mma_bf16(tmem + kColX, desc_sw128(wt + (uint32_t)(k >> 2) * kRowBlock + (uint32_t)(k & 3) * 32u),
                                  desc_fm_mn_b(fm_addr + k * 1024), kIdescDX, k > 0 ? 1u : 0u);
+                    mma_commit(bar);
                     const uint32_t accw = tmem + (layer == 2 ? kColW3 : kColW2);
 #pragma unroll
                     for (int s = 0; s < 6; ++s)  // M = 128 (n_out), N = 128 (k_in), K = 96 (nodes): 32 B per step inside a 64 B node block
                         mma_bf16(accw, desc_fm_k_b(fm_addr + (uint32_t)(s >> 1) * kFmBlock + (uint32_t)(s & 1) * 32u),
                                  desc_fm_k_b((layer == 2 ? xt2_addr : xt1_addr) + (uint32_t)(s >> 1) * kFmBlock + (uint32_t)(s & 1) * 32u), kIdescDW, (first && s == 0) ? 0u : 1u);
-                    mma_commit(bar);
+                    mma_commit(bar_w);
                 }
                 __syncwarp();
             }
+            w_pending = true;
             wait_mma();
             TC2B_T(6);
         }
         // ---- layer 1: dY1 = mask1 * dX1 -> bf16 tile;  dW1ext += dY1^T A1 ------------------------------------------------------------
+        wait_dw();  // dW2 has read the tile
         {
             float bsum = 0.f;
 #pragma unroll
@@ -354,16 +374,18 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
                 for (int s = 0; s < 6; ++s)  // M = 128, N = 16, K = 96
                     mma_bf16(tmem + kColW1, desc_fm_k_b(fm_addr + (uint32_t)(s >> 1) * kFmBlock + (uint32_t)(s & 1) * 32u),
                              desc_fm_k_b(a1t_addr + (uint32_t)(s >> 1) * 1024u + (uint32_t)(s & 1) * 32u), kIdescDW1, (first && s == 0) ? 0u : 1u);
-                mma_commit(bar);
+                mma_commit(bar_w);
             }
             __syncwarp();
         }
-        wait_mma();
+        w_pending = true;
         TC2B_T(8);
         first = false;
         // (no barrier here: the next board starts with one, after its cp.async wait)
     }
     // ---- this CTA's partial gradients: accumulator rows -> its slot ---------------------------------------------
+    wait_dw();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     {
         float v[32];
 #pragma unroll 1
