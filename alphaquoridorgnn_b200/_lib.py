@@ -45,6 +45,8 @@ SYMBOLS = {
     "aq_mcts_select": (_i32, [_vp, _i64, _i64, _f32, _vp, _vp, _vp]),
     "aq_mcts_expand_backup": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "aq_mcts_root_counts": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "aq_shortest_paths": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "aq_negamax_backup": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -125,6 +125,32 @@ AQ_DEV bool reaches(const Open &o, int start, int ob, u128 goal) {
     }
 }
 
+// shortest_path_bfs of agents.py:27-41: number of pawn steps (a jump is one step) from `start` to the nearest
+// square of `goal` under the same pawn rules; every iteration of the flood fill is one BFS layer.  -1 if no
+// path exists (agents.py:41).
+AQ_DEV int path_length(const Open &o, int start, int ob, u128 goal) {
+    const u128 srcU = has(o.down, ob) ? bit81(ob + 9) : (u128)0;
+    const u128 srcD = has(o.up, ob) ? bit81(ob - 9) : (u128)0;
+    const u128 srcL = has(o.right, ob) ? bit81(ob + 1) : (u128)0;
+    const u128 srcR = has(o.left, ob) ? bit81(ob - 1) : (u128)0;
+    const u128 jU = jump_targets(o, ob, 0), jD = jump_targets(o, ob, 1);
+    const u128 jL = jump_targets(o, ob, 2), jR = jump_targets(o, ob, 3);
+    const u128 notob = ~bit81(ob);
+    u128 reach = bit81(start);
+    for (int depth = 0;; ++depth) {
+        if (reach & goal) return depth;
+        u128 nb = ((reach & o.up) >> 9) | ((reach & o.down) << 9) | ((reach & o.left) >> 1) | ((reach & o.right) << 1);
+        nb &= notob;
+        if (reach & srcU) nb |= jU;
+        if (reach & srcD) nb |= jD;
+        if (reach & srcL) nb |= jL;
+        if (reach & srcR) nb |= jR;
+        const u128 nxt = reach | nb;
+        if (nxt == reach) return -1;
+        reach = nxt;
+    }
+}
+
 // ---- path witness --------------------------------------------------------------------------------
 // One concrete path start -> goal (with the pawn rules) found by the same flood fill, returned as the
 // set of wall slots whose H / V wall would sever one of the unit edges the path uses.  A candidate

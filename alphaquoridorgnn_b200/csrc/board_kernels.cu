@@ -214,6 +214,67 @@ __global__ void state_next_kernel(const AqState *__restrict__ states, const int1
 }
 
 // ------------------------------------------------------------------------------------------
+// Shortest-path distances and the heuristic evaluation of agents.py:22-54.
+//   dist[b] = {shortest_path_bfs(state), shortest_path_bfs(state seen from the enemy)}; the enemy's search runs
+//   un-rotated (start 80 - epos, obstacle ppos, goal row 8), which is the 180-degree image of agents.py:46-48.
+//   heur[b]  = (dist_enemy - dist_player) / MAX_DIST_FROM_GOAL in float64 (Python's int / int), agents.py:53
+//   leaf48[b] = the depth-0 value of agents.alpha_beta (agents.py:69-75) times 48, as an exact integer:
+//               is_lose -> -48, is_draw -> 0, else dist_enemy - dist_player.
+// One thread per state: two 81-bit flood fills in registers.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxDistFromGoal = AQ_PLIES_FOR_DRAW / 2 - 10;  // agents.py:11 with constants.py:19-20 (NUM_WALLS = 10)
+
+__global__ void __launch_bounds__(128)
+shortest_paths_kernel(const AqState *__restrict__ states, int64_t B, int16_t *__restrict__ dist, double *__restrict__ heur,
+                      int32_t *__restrict__ leaf48) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const AqState s = load_state(states + b);
+    const Open o = open_from_walls(s.hwalls, s.vwalls);
+    const int me = s.ppos, en = 80 - (int)s.epos;
+    const int dp = path_length(o, me, en, kRow0);
+    const int de = path_length(o, en, me, kRow8);
+    if (dist) *reinterpret_cast<short2 *>(dist + 2 * b) = make_short2((short)dp, (short)de);
+    if (heur) heur[b] = (double)(de - dp) / (double)kMaxDistFromGoal;
+    if (leaf48) {
+        const int t = terminal_flags(s);
+        leaf48[b] = (t & 1) ? -kMaxDistFromGoal : (t & 2) ? 0 : de - dp;
+    }
+}
+
+// Negamax backup of one tree level (agents.py:78-86 without the pruning, which does not change the value inside
+// the window nor the action chosen at the root -- see agents.py in this package): for parent p with children
+// [off[p], off[p+1]) in legal_actions() order, value[p] = max_c -child_value[c] and best[p] = the FIRST child
+// attaining it (agents.py:104 uses a strict '>').  Parents with fixed[p] != kNotFixed keep that value (terminal
+// nodes, agents.py:69-73).  One warp per parent.
+constexpr int32_t kNotFixed = INT32_MIN;
+
+__global__ void negamax_backup_kernel(const int32_t *__restrict__ child_value, const int64_t *__restrict__ off, int64_t P,
+                                      const int32_t *__restrict__ fixed, int32_t *__restrict__ value, int32_t *__restrict__ best) {
+    const int lane = threadIdx.x & 31;
+    const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= P) return;
+    if (fixed && fixed[p] != kNotFixed) {
+        if (lane == 0) { value[p] = fixed[p]; if (best) best[p] = -1; }
+        return;
+    }
+    const int64_t lo = off[p], hi = off[p + 1];
+    int bv = -(1 << 20);  // "-inf" (agents.py:99) that survives the parent's negation; only a node without any legal action keeps it
+    int64_t bi = INT64_MAX;
+    for (int64_t c = lo + lane; c < hi; c += 32) {
+        const int v = -child_value[c];
+        if (v > bv) { bv = v; bi = c; }  // ascending c per lane: keeps the first maximum
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const int ov = __shfl_xor_sync(0xffffffffu, bv, d);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, d);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { value[p] = bv; if (best) best[p] = hi > lo ? (int32_t)(bi - lo) : -1; }
+}
+
+// ------------------------------------------------------------------------------------------
 // K2 build_graph: one warp per board
 // ------------------------------------------------------------------------------------------
 __device__ __constant__ float kDinv[6] = {0.f, 1.0f, 0.70710678118654752f, 0.57735026918962576f, 0.5f,
@@ -373,4 +434,20 @@ extern "C" int aq_edges_to_open_mask(const int64_t *src, const int64_t *dst, int
     if (E == 0) return 0;
     edges_to_open_mask_kernel<<<blocks_for(E, 256), 256, 0, S(stream)>>>(src, dst, E, B, reinterpret_cast<unsigned *>(open_mask), bad);
     return aq_check_launch("aq_edges_to_open_mask");
+}
+
+extern "C" int aq_shortest_paths(const AqState *states, int64_t B, int16_t *dist, double *heuristic, int32_t *leaf48,
+                                 void *stream) {
+    if (B < 0 || (B > 0 && (!states || (!dist && !heuristic && !leaf48)))) return aq_set_error(AQ_ERR_ARG, "aq_shortest_paths");
+    if (B == 0) return 0;
+    shortest_paths_kernel<<<blocks_for(B, 128), 128, 0, S(stream)>>>(states, B, dist, heuristic, leaf48);
+    return aq_check_launch("aq_shortest_paths");
+}
+
+extern "C" int aq_negamax_backup(const int32_t *child_value, const int64_t *child_offset, int64_t P, const int32_t *fixed,
+                                 int32_t *value, int32_t *best, void *stream) {
+    if (P < 0 || (P > 0 && (!child_offset || !value))) return aq_set_error(AQ_ERR_ARG, "aq_negamax_backup");
+    if (P == 0) return 0;
+    negamax_backup_kernel<<<blocks_for(P, 8), 256, 0, S(stream)>>>(child_value, child_offset, P, fixed, value, best);
+    return aq_check_launch("aq_negamax_backup");
 }

@@ -412,7 +412,7 @@ struct AqHostKey {
 constexpr int kHostGraphSlots = 8;
 struct AqHostCtx {
     cudaStream_t s[2];
-    cudaEvent_t ready, done[2];
+    cudaEvent_t ready, done[2], chunk_done[8];
     AqHostKey key[kHostGraphSlots];
     cudaGraphExec_t exec[kHostGraphSlots];
     int n_graphs, next_slot;
@@ -428,6 +428,7 @@ extern "C" int aq_host_ctx_create(void **ctx) {
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&c->s[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->chunk_done[i], cudaEventDisableTiming);
     if (e != cudaSuccess) { delete c; return aq_set_error((int)e, "aq_host_ctx_create"); }
     *ctx = c;
     return 0;
@@ -438,6 +439,7 @@ extern "C" int aq_host_ctx_destroy(void *ctx) {
     AqHostCtx *c = reinterpret_cast<AqHostCtx *>(ctx);
     for (int i = 0; i < c->n_graphs; ++i) cudaGraphExecDestroy(c->exec[i]);
     for (int i = 0; i < 2; ++i) { cudaStreamDestroy(c->s[i]); cudaEventDestroy(c->done[i]); }
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(c->chunk_done[i]);
     cudaEventDestroy(c->ready);
     delete c;
     return 0;
@@ -550,5 +552,194 @@ extern "C" int aq_leaf_eval_host(const float *params, const void *prepared, cons
     }
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(sync)");
+    return 0;
+}
+
+// ---- predict()-shaped output: priors of the LEGAL actions only, in legal_actions() order ----------------
+// BaseNetwork.predict (BaseNetwork.py:36-40; pv_network_cnn.py:128-135) returns, per state, the probabilities of the
+// legal actions only, ordered like state.legal_actions().  For a batch that is a ragged array: board b owns
+// compact[offsets[b] .. offsets[b+1]).  Moving this form to the host instead of the dense [B,209] matrix is what the
+// host-buffer path is bound by (PCIe): 4 bytes per legal action instead of 836 per board.
+
+// offsets[b] = number of legal actions of boards < b (exclusive scan of popcount(mask)), offsets[B] = total.
+// One CTA, tiles of 1024 boards with a running carry: B is at most a few 10^4 per call on this path.
+__global__ void __launch_bounds__(1024)
+legal_count_scan_kernel(const uint32_t *__restrict__ mask, int64_t B, int32_t *__restrict__ offsets) {
+    __shared__ int warp_sum[32];
+    __shared__ int carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < B; base += 1024) {
+        const int64_t b = base + tid;
+        int c = 0;
+        if (b < B) {
+            const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(mask + 8 * b));
+            const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(mask + 8 * b) + 1);
+            c = __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w) + __popc(hi.x) + __popc(hi.y) + __popc(hi.z) + __popc(hi.w);
+        }
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += t;
+            }
+            warp_sum[lane] = w;  // inclusive scan of the warp totals
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int excl = carry + (warp ? warp_sum[warp - 1] : 0) + incl - c;
+        if (b < B) offsets[b] = excl;
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + warp_sum[31];
+        __syncthreads();
+    }
+    if (tid == 0) offsets[B] = carry_s;
+}
+
+// One warp per board: every legal action's probability goes to its rank in legal_actions() order
+// (pawn list order, then per wall slot H before V -- game_logic.py:103-117, 350-357).
+__global__ void __launch_bounds__(256)
+compact_priors_kernel(const float *__restrict__ priors, const uint32_t *__restrict__ mask, const uint8_t *__restrict__ pawn,
+                      const int32_t *__restrict__ offsets, int64_t B, float *__restrict__ compact) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const uint32_t *m = mask + 8 * b;
+    const uint32_t mw = lane < 8 ? __ldg(m + lane) : 0u;
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = __shfl_sync(0xffffffffu, mw, k);
+    // wall bits: H = actions 81..144, V = actions 145..208
+    const u64 lo2 = ((u64)w[3] << 32) | w[2], hi2 = ((u64)w[5] << 32) | w[4], top = ((u64)w[7] << 32) | w[6];
+    const u64 legalH = (lo2 >> 17) | (hi2 << 47);            // bit s = action 81 + s
+    const u64 legalV = (hi2 >> 17) | (top << 47);            // bit s = action 145 + s
+    const uint2 pw = __ldg(reinterpret_cast<const uint2 *>(pawn + 8 * b));
+    const int np = pw.x & 0xFF;
+    float *out = compact + offsets[b];
+    const float *p = priors + (int64_t)kP * b;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const int a = lane + 32 * k;
+        if (a >= kP || !((w[a >> 5] >> (a & 31)) & 1)) continue;
+        int rank;
+        if (a < AQ_SQUARES) {
+            const u64 list = ((u64)pw.y << 32 | pw.x) >> 8;  // p0..p4
+            rank = 0;
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+                if (j < np && (int)((list >> (8 * j)) & 0xFF) == a) rank = j;
+        } else {
+            const bool isV = a >= AQ_SQUARES + AQ_SLOTS;
+            const int slot = a - AQ_SQUARES - (isV ? AQ_SLOTS : 0);
+            const u64 below = (1ull << slot) - 1ull;
+            rank = np + __popcll(legalH & below) + __popcll(legalV & below) + (isV ? (int)((legalH >> slot) & 1) : 0);
+        }
+        out[rank] = __ldg(p + a);
+    }
+}
+
+extern "C" int aq_compact_priors(const float *priors, const uint32_t *mask, const uint8_t *pawn, int64_t B, int32_t *offsets,
+                                 float *compact, void *stream) {
+    if (B < 0 || !offsets || (B > 0 && (!priors || !mask || !pawn || !compact))) return aq_set_error(AQ_ERR_ARG, "aq_compact_priors");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    legal_count_scan_kernel<<<1, 1024, 0, st>>>(mask, B, offsets);
+    int rc = aq_check_launch("aq_compact_priors(scan)");
+    if (rc || B == 0) return rc;
+    compact_priors_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(priors, mask, pawn, offsets, B, compact);
+    return aq_check_launch("aq_compact_priors");
+}
+
+// Host-buffer leaf evaluation with predict()-shaped output.  Device workspace: the dense workspace of
+// aq_leaf_eval_host followed by offsets int32[B + chunks] and compact f32[B * 136].
+constexpr int kCompactMaxChunks = 8;
+extern "C" int64_t aq_leaf_eval_host_compact_ws_bytes(int64_t B) {
+    return aq_leaf_eval_host_ws_bytes(B) + (int64_t)align256((size_t)(B + kCompactMaxChunks) * 4) +
+           (int64_t)align256((size_t)B * AQ_MAX_LEGAL * 4);
+}
+
+extern "C" int aq_leaf_eval_host_compact(const float *params, const void *prepared, const AqState *states_host, int64_t B,
+                                         float *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,
+                                         uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision, void *host_ctx,
+                                         void *stream) {
+    if (B < 0 || !params || !offsets_host || (B > 0 && (!states_host || !priors_host || !value_host || !dev_ws || !host_ctx)))
+        return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host_compact");
+    if (B == 0) { offsets_host[0] = 0; return 0; }
+    AqHostCtx *ctx = reinterpret_cast<AqHostCtx *>(host_ctx);
+    cudaStream_t origin = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char *p = reinterpret_cast<unsigned char *>(dev_ws);
+    AqState *d_states = reinterpret_cast<AqState *>(p); p += align256((size_t)B * sizeof(AqState));
+    float *d_priors = reinterpret_cast<float *>(p);     p += align256((size_t)B * kP * 4);
+    float *d_value = reinterpret_cast<float *>(p);      p += align256((size_t)B * 4);
+    uint32_t *d_mask = reinterpret_cast<uint32_t *>(p); p += align256((size_t)B * 32);
+    uint8_t *d_pawn = reinterpret_cast<uint8_t *>(p);   p += align256((size_t)B * 8);
+    float *d_pooled = reinterpret_cast<float *>(p);     p += align256((size_t)B * kH * 4);
+    int32_t *d_offsets = reinterpret_cast<int32_t *>(p); p += align256((size_t)(B + kCompactMaxChunks) * 4);
+    float *d_compact = reinterpret_cast<float *>(p);
+
+    static const int env_chunks = getenv("AQ_HOST_CHUNKS") ? atoi(getenv("AQ_HOST_CHUNKS")) : 0;
+    int nchunk = B >= 4096 ? (env_chunks > 0 ? env_chunks : 2) : 1;
+    if (nchunk > kCompactMaxChunks) nchunk = kCompactMaxChunks;
+    const int64_t per = ((B + nchunk - 1) / nchunk + 127) / 128 * 128;
+    cudaError_t e = cudaEventRecord(ctx->ready, origin);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(ctx->s[i], ctx->ready, 0);
+    if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(fork)");
+    // front half of every chunk: H2D, kernels, the fixed-size results and the chunk's offsets (its last entry = its total)
+    int used = 0;
+    for (int c = 0; c < nchunk; ++c) {
+        const int64_t lo = (int64_t)c * per, n = (lo + per <= B ? per : B - lo);
+        if (n <= 0) break;
+        used = c + 1;
+        cudaStream_t cs = ctx->s[c & 1];
+        int32_t *d_off = d_offsets + lo + c;  // n + 1 entries per chunk
+        e = cudaMemcpyAsync(d_states + lo, states_host + lo, (size_t)n * sizeof(AqState), cudaMemcpyHostToDevice, cs);
+        if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(H2D)");
+        int rc = aq_leaf_eval(params, prepared, d_states + lo, n, d_priors + lo * kP, d_value + lo, d_mask + lo * 8, d_pawn + lo * 8,
+                              d_pooled + lo * kH, precision, cs);
+        if (rc) return rc;
+        rc = aq_compact_priors(d_priors + lo * kP, d_mask + lo * 8, d_pawn + lo * 8, n, d_off, d_compact + lo * AQ_MAX_LEGAL, cs);
+        if (rc) return rc;
+        // offsets land in offsets_host[lo + c ...] for now (chunk-local values); rebased below once the totals are known
+        e = cudaMemcpyAsync(offsets_host + lo, d_off + 1, (size_t)n * 4, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(value_host + lo, d_value + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess && mask_host) e = cudaMemcpyAsync(mask_host + lo * 8, d_mask + lo * 8, (size_t)n * 32, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess && pawn_host) e = cudaMemcpyAsync(pawn_host + lo * 8, d_pawn + lo * 8, (size_t)n * 8, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->chunk_done[c], cs);
+        if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(D2H)");
+    }
+    // back half: as each chunk's total reaches the host, copy exactly that many probabilities behind the previous chunk's
+    int64_t base = 0;
+    for (int c = 0; c < used; ++c) {
+        const int64_t lo = (int64_t)c * per, n = (lo + per <= B ? per : B - lo);
+        e = cudaEventSynchronize(ctx->chunk_done[c]);
+        if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(sync)");
+        // offsets_host[lo + i] currently holds the chunk-local INCLUSIVE end of board lo + i
+        const int64_t total = offsets_host[lo + n - 1];
+        if (base + total > priors_capacity) return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host_compact(priors_capacity too small)");
+        if (total > 0) {
+            e = cudaMemcpyAsync(priors_host + base, d_compact + lo * AQ_MAX_LEGAL, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->s[c & 1]);
+            if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(D2H priors)");
+        }
+        if (base) for (int64_t i = 0; i < n; ++i) offsets_host[lo + i] += (int32_t)base;
+        base += total;
+    }
+    // shift to the exclusive convention: offsets_host[b] = start of board b, offsets_host[B] = total
+    for (int64_t i = B; i > 0; --i) offsets_host[i] = offsets_host[i - 1];
+    offsets_host[0] = 0;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventRecord(ctx->done[i], ctx->s[i]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(origin, ctx->done[i], 0);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(origin);
+    if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(join)");
     return 0;
 }

@@ -182,6 +182,21 @@ int aq_mcts_expand_backup(void *ws, int64_t G, int64_t max_nodes, const float *p
 int aq_mcts_root_counts(void *ws, int64_t G, int64_t max_nodes, int32_t *counts /*[G,136]*/,
                         int16_t *actions /*[G,136]*/, int16_t *n_children /*[G]*/, int32_t *overflow, void *stream);
 
+/* agents.heuristic_eval (agents.py:22-54) for B states: shortest pawn-path lengths to the goal row for the mover
+ * and for the enemy (shortest_path_bfs, agents.py:27-41, with the jump rules of legal_actions_pos; -1 = no path).
+ *   dist      [B,2] int16 : {mover, enemy}                                    (may be NULL)
+ *   heuristic [B] float64 : (dist_enemy - dist_mover) / MAX_DIST_FROM_GOAL (= 116//2 - 10 = 48, agents.py:11)   (may be NULL)
+ *   leaf48    [B] int32   : 48 x the depth-0 value of agents.alpha_beta (agents.py:69-75): is_lose -> -48,
+ *                           is_draw -> 0, else dist_enemy - dist_mover                                          (may be NULL) */
+int aq_shortest_paths(const AqState *states, int64_t B, int16_t *dist, double *heuristic, int32_t *leaf48, void *stream);
+
+/* One level of the negamax recursion of agents.alpha_beta / alpha_beta_action (agents.py:58-107) over a batch of
+ * parents: value[p] = max over children c in [child_offset[p], child_offset[p+1]) of -child_value[c];
+ * best[p] = index (within the parent) of the FIRST child attaining it, -1 if none; parents with
+ * fixed[p] != INT32_MIN keep fixed[p] (terminal nodes).  fixed and best may be NULL. */
+int aq_negamax_backup(const int32_t *child_value, const int64_t *child_offset, int64_t P, const int32_t *fixed,
+                      int32_t *value, int32_t *best, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -342,6 +342,93 @@ void oq_planes_batch(const uint8_t *rows, long long M, int N, float *planes) {
     }
 }
 
+/* ---- agents.py: heuristic evaluation and alpha-beta ---- */
+/* shortest_path_bfs, agents.py:27-41: queue of (position, depth) pairs; -1 if no path. */
+static int oq_shortest_path(const oq_state *s) {
+    int N = s->N;
+    uint8_t seen[OQ_MAXN * OQ_MAXN];
+    int qpos[OQ_MAXN * OQ_MAXN], qdepth[OQ_MAXN * OQ_MAXN];
+    int head = 0, tail = 0, nb[8];
+    memset(seen, 0, sizeof seen);
+    seen[s->ppos] = 1;
+    qpos[tail] = s->ppos; qdepth[tail++] = 0;
+    while (head < tail) {
+        int p = qpos[head], d = qdepth[head++];
+        if (p / N == 0) return d;
+        int k = oq_legal_actions_pos(s, p, nb);
+        for (int i = 0; i < k; ++i)
+            if (!seen[nb[i]]) { seen[nb[i]] = 1; qpos[tail] = nb[i]; qdepth[tail++] = d + 1; }
+    }
+    return -1;
+}
+
+/* shortest_path_diff, agents.py:43-52: the enemy's search runs on the rotated board with the roles swapped. */
+static void oq_shortest_paths(const oq_state *s, int *dp, int *de) {
+    int S = (s->N - 1) * (s->N - 1);
+    *dp = oq_shortest_path(s);
+    oq_state t = *s;
+    for (int i = 0; i < S; ++i) t.walls[i] = s->walls[S - 1 - i]; /* rotate_walls, game_logic.py:359-364 */
+    t.ppos = s->epos; t.pwalls = s->ewalls;
+    t.epos = s->ppos; t.ewalls = s->pwalls;
+    *de = oq_shortest_path(&t);
+}
+
+static double oq_heuristic(const oq_state *s, int plies_for_draw, int num_walls) {
+    int dp, de;
+    oq_shortest_paths(s, &dp, &de);
+    return (double)(de - dp) / (double)(plies_for_draw / 2 - num_walls); /* agents.py:11,52 */
+}
+
+void oq_heuristic_batch(const uint8_t *rows, long long M, int N, int plies_for_draw, int num_walls,
+                        int16_t *dist, double *heur) {
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long long i = 0; i < M; ++i) {
+        oq_state s;
+        int dp, de;
+        oq_load(rows + 68 * i, 0, N, &s);
+        oq_shortest_paths(&s, &dp, &de);
+        if (dist) { dist[2 * i] = (int16_t)dp; dist[2 * i + 1] = (int16_t)de; }
+        if (heur) heur[i] = (double)(de - dp) / (double)(plies_for_draw / 2 - num_walls);
+    }
+}
+
+/* alpha_beta, agents.py:58-86 (fail-hard, returns alpha), kept literal including the pruning. */
+static double oq_alpha_beta(const oq_state *s, double alpha, double beta, int depth, int plies_for_draw, int num_walls) {
+    if (depth == 0 || oq_is_lose(s) || oq_is_draw(s, plies_for_draw)) {
+        if (oq_is_lose(s)) return -1.0;
+        if (oq_is_draw(s, plies_for_draw)) return 0.0;
+        return oq_heuristic(s, plies_for_draw, num_walls);
+    }
+    int acts[OQ_MAXACT];
+    int n = oq_legal_actions(s, acts);
+    for (int i = 0; i < n; ++i) {
+        oq_state t;
+        oq_next(s, acts[i], &t);
+        double score = -oq_alpha_beta(&t, -beta, -alpha, depth - 1, plies_for_draw, num_walls);
+        if (score > alpha) alpha = score;
+        if (alpha >= beta) return alpha;
+    }
+    return alpha;
+}
+
+/* alpha_beta_action, agents.py:90-107. scores (may be NULL): the score the loop saw for every root action. */
+int oq_alpha_beta_action(const uint8_t *row, int plies, int N, int max_depth, int plies_for_draw, int num_walls,
+                         double *scores) {
+    oq_state s;
+    oq_load(row, plies, N, &s);
+    int acts[OQ_MAXACT];
+    int n = oq_legal_actions(&s, acts), best = -1;
+    double alpha = -1.0 / 0.0;
+    for (int i = 0; i < n; ++i) {
+        oq_state t;
+        oq_next(&s, acts[i], &t);
+        double score = -oq_alpha_beta(&t, -1.0 / 0.0, -alpha, max_depth, plies_for_draw, num_walls);
+        if (scores) scores[i] = score;
+        if (score > alpha) { best = acts[i]; alpha = score; }
+    }
+    return best;
+}
+
 int oq_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -59,6 +59,10 @@ def lib():
         L.oq_legal_actions_wall_row.argtypes = [vp, i, i, vp]
         L.oq_legal_actions_wall_row.restype = i
         L.oq_max_threads.restype = i
+        L.oq_heuristic_batch.argtypes = [vp, ll, i, i, i, vp, vp]
+        L.oq_heuristic_batch.restype = None
+        L.oq_alpha_beta_action.argtypes = [vp, i, i, i, i, i, vp]
+        L.oq_alpha_beta_action.restype = i
         _lib = L
     return _lib
 
@@ -127,6 +131,23 @@ def planes_batch(rows, N=9):
     out = np.empty((rows.shape[0], 6, N, N), np.float32)
     lib().oq_planes_batch(_ptr(rows), rows.shape[0], N, _ptr(out))
     return out
+
+
+def heuristic_batch(rows, N=9, plies_for_draw=116, num_walls=10):
+    """agents.heuristic_eval (agents.py:22-54) -> (dist int16[M,2] = {mover, enemy} shortest paths, heur float64[M])."""
+    rows = _rows(rows)
+    dist = np.empty((rows.shape[0], 2), np.int16)
+    heur = np.empty(rows.shape[0], np.float64)
+    lib().oq_heuristic_batch(_ptr(rows), rows.shape[0], N, plies_for_draw, num_walls, _ptr(dist), _ptr(heur))
+    return dist, heur
+
+
+def alpha_beta_action(row, plies=0, max_depth=2, N=9, plies_for_draw=116, num_walls=10):
+    """agents.alpha_beta_action (agents.py:90-107), literal fail-hard alpha-beta -> (action, root scores float64[n])."""
+    row = np.ascontiguousarray(row, dtype=np.uint8)
+    scores = np.full(MAXACT, np.nan, np.float64)
+    a = lib().oq_alpha_beta_action(_ptr(row), int(plies), N, int(max_depth), plies_for_draw, num_walls, _ptr(scores))
+    return a, scores
 
 
 def legal_actions_pos(row, pos, N=9):

@@ -37,3 +37,9 @@ def graph_golden():
 def mcts_golden():
     with open(os.path.join(GOLDEN, "mcts_golden.json")) as f:
         return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def agents_golden():
+    with open(os.path.join(GOLDEN, "agents_golden.json")) as f:
+        return json.load(f)

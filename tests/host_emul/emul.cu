@@ -69,3 +69,14 @@ extern "C" void emul_open_mask(const AqState *states, long long B, uint8_t *open
             open_mask[b * 81 + v] = (uint8_t)((int)has(o.up, v) | ((int)has(o.down, v) << 1) | ((int)has(o.left, v) << 2) | ((int)has(o.right, v) << 3));
     }
 }
+
+// shortest_paths_kernel's per-state computation (agents.heuristic_eval, agents.py:22-54)
+extern "C" void emul_shortest_paths(const AqState *states, long long B, int16_t *dist) {
+    for (long long b = 0; b < B; ++b) {
+        const AqState s = states[b];
+        const Open o = open_from_walls(s.hwalls, s.vwalls);
+        const int me = s.ppos, en = 80 - (int)s.epos;
+        dist[2 * b] = (int16_t)path_length(o, me, en, kRow0);
+        dist[2 * b + 1] = (int16_t)path_length(o, en, me, kRow8);
+    }
+}

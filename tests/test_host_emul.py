@@ -42,3 +42,16 @@ def test_bitboard_algorithm_matches_reference_goldens(emul, traj, graph_golden):
     om = np.zeros((len(idx), 81), np.uint8)
     emul.emul_open_mask(_p(sub), ctypes.c_longlong(len(idx)), _p(om))
     assert np.array_equal(om, graph_golden["open"])
+
+
+def test_path_length_matches_reference_heuristic(emul, traj, agents_golden):
+    """agents.heuristic_eval of the unmodified reference = (dist_enemy - dist_mover) / 48 for the bitboard flood fill."""
+    idx = np.array(agents_golden["heuristic"]["index"])
+    rows, plies = np.ascontiguousarray(traj["rows"][idx]), np.ascontiguousarray(traj["plies"][idx])
+    st = np.zeros((len(idx), 32), np.uint8)
+    emul.emul_pack(_p(rows), _p(plies), ctypes.c_longlong(len(idx)), _p(st))
+    dist = np.zeros((len(idx), 2), np.int16)
+    emul.emul_shortest_paths(_p(st), ctypes.c_longlong(len(idx)), _p(dist))
+    assert (dist >= -1).all() and (dist == -1).sum() >= 1  # -1: the other pawn seals the only corridor (agents.py:41)
+    got = (dist[:, 1].astype(np.int64) - dist[:, 0]) / 48
+    assert np.array_equal(got, np.array(agents_golden["heuristic"]["value"]))
