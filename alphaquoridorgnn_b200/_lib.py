@@ -18,6 +18,8 @@ SYMBOLS = {
     "aq_pack_states": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "aq_unpack_states": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "aq_legal_mask": (_i32, [_vp, _i64, _vp, _vp, _vp]),
+    "aq_legal_mask_ws_bytes": (_i64, [_i64]),
+    "aq_legal_mask_ws": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp]),
     "aq_legal_actions_list": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "aq_state_next": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "aq_build_graph": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
@@ -40,6 +42,9 @@ SYMBOLS = {
     "aq_host_ctx_create": (_i32, [ctypes.POINTER(ctypes.c_void_p)]),
     "aq_host_ctx_destroy": (_i32, [_vp]),
     "aq_leaf_eval_host": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "aq_compact_priors": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "aq_leaf_eval_host_compact_ws_bytes": (_i64, [_i64]),
+    "aq_leaf_eval_host_compact": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "aq_mcts_ws_bytes": (_i64, [_i64, _i64]),
     "aq_mcts_reset": (_i32, [_vp, _vp, _i64, _i64, _vp]),
     "aq_mcts_select": (_i32, [_vp, _i64, _i64, _f32, _vp, _vp, _vp]),

@@ -3,8 +3,10 @@
 //   K2 build_graph     derived from game_logic.py:145-167 (edges) and 56-93 (features)
 //   K9 state_next      game_logic.py:43-54, 359-391
 // plus row68 <-> AqState packing and the ordered action list.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "aq_common.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -76,27 +78,29 @@ __global__ void unpack_states_kernel(const AqState *__restrict__ states, int64_t
 }
 
 // ------------------------------------------------------------------------------------------
-// K1 legal_mask: eight lanes per state (four states per warp).
+// K1 legal_mask: kLanes lanes per state (32 / kLanes states per warp), kLanes in {2, 8, 32} chosen by batch size:
+//   the per-state work is a variable number of flood fills (0 .. ~60), so small batches are bound by the slowest
+//   states of a nearly empty machine and want many lanes per state, while large batches want many states per warp.
 //   every lane: open-direction bitboards, can_place + gate for all 128 candidates (bit-parallel);
 //   sub-lanes 0/1: one witness path for the mover / the opponent on the board WITHOUT a candidate,
 //   as the sets of slots that would cut it (find_path_cuts);
 //   a gated candidate needs a real search only for the player whose witness it cuts: those
 //   (candidate, player) tasks are compacted into a per-state list and dealt round-robin to the
-//   state's eight lanes; each lane runs its flood fills in registers.
+//   state's lanes; each lane runs its flood fills in registers.
 // ------------------------------------------------------------------------------------------
 constexpr int kLegalWarps = 4;
-constexpr int kLanesPerState = 2;
-constexpr int kStatesPerWarp = 32 / kLanesPerState;
 
+template <int kLanesPerState>
 __global__ void __launch_bounds__(kLegalWarps * 32)
 legal_mask_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__restrict__ mask,
                   uint8_t *__restrict__ pawn) {
+    constexpr int kStatesPerWarp = 32 / kLanesPerState;
     __shared__ uint8_t task[kLegalWarps * kStatesPerWarp][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & (kLanesPerState - 1), grp = lane / kLanesPerState;
-    const unsigned gmask = ((1u << kLanesPerState) - 1u) << (grp * kLanesPerState);
+    const unsigned gmask = kLanesPerState == 32 ? 0xffffffffu : ((1u << (kLanesPerState & 31)) - 1u) << (grp * kLanesPerState);
     const int64_t b = ((int64_t)blockIdx.x * kLegalWarps + warp) * kStatesPerWarp + grp;
-    if (b >= B) return;  // whole 8-lane group leaves together
+    if (b >= B) return;  // the whole lane group of a state leaves together
     uint8_t *tl = task[warp * kStatesPerWarp + grp];
     const AqState s = load_state(states + b);
     const Open base = open_from_walls(s.hwalls, s.vwalls);
@@ -171,6 +175,148 @@ legal_mask_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__res
         p.x = pm[0] | (pm[1] << 8) | (pm[2] << 16) | ((unsigned)pm[3] << 24);
         p.y = pm[4] | (pm[5] << 8);
         *reinterpret_cast<uint2 *>(pawn + 8 * b) = p;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1, two-phase form (the default): the searches of ALL states go through one flat task list.
+//   legal_prepare_kernel : two lanes per state; everything of legal_mask_kernel up to the witness paths, then the
+//                          (candidate, player) searches that are still needed are appended to a global task list
+//                          (one warp-aggregated atomicAdd) and the mask is written OPTIMISTICALLY (every gated
+//                          candidate legal);
+//   legal_search_kernel  : one thread per task, grid-stride: rebuild the open-direction boards of the task's state
+//                          (+ the candidate wall), run the flood fill, clear the candidate's mask bit on failure.
+// The per-state number of searches is 0 .. ~60 with a mean of 2-4, so the one-kernel form spends most of its lanes
+// waiting for the slowest state of their warp; the flat list has no such imbalance and the search kernel runs at
+// four times the occupancy.  A state whose tasks do not fit the list (capacity 8 per state on average) runs them
+// itself, as legal_mask_kernel does -- results never depend on the capacity.
+// task word: state index << 8 | slot | (orient - 1) << 6 | opponent << 7;  kNullTask = hole left by an overflow.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kNullTask = 0xFFFFFFFFu;
+constexpr int64_t kLegalChunk = (int64_t)1 << 23;  // states per launch pair (state index field: 24 bits)
+
+__global__ void __launch_bounds__(kLegalWarps * 32)
+legal_prepare_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__restrict__ mask, uint8_t *__restrict__ pawn,
+                     uint32_t *__restrict__ tasks, unsigned cap, unsigned *__restrict__ counter) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane & 1, grp = lane >> 1;
+    const int64_t b0 = ((int64_t)blockIdx.x * kLegalWarps + warp) * 16 + grp;
+    const bool valid = b0 < B;
+    const int64_t b = valid ? b0 : B - 1;  // out-of-range lanes shadow the last state and write nothing
+    const AqState s = load_state(states + b);
+    const Open base = open_from_walls(s.hwalls, s.vwalls);
+    const int me = s.ppos, en = 80 - (int)s.epos;  // enemy square in the mover's frame, game_logic.py:136
+
+    u64 legalH = 0, legalV = 0, needH = 0, needV = 0;
+    u64 set[4] = {0, 0, 0, 0};  // tasks: [mover H, mover V, opponent H, opponent V]
+    if (s.pwalls > 0) {         // game_logic.py:113
+        const WallSets ws = wall_sets(s.hwalls, s.vwalls);
+        legalH = ws.freeH; legalV = ws.freeV; needH = ws.needH; needV = ws.needV;
+    }
+    // witness paths: mover (start me, obstacle en, goal row 0) on sub-lane 0, opponent in the un-rotated frame
+    // (start en, obstacle me, goal row 8) on sub-lane 1  (game_logic.py:332-348)
+    PathCuts pc;
+    pc.cutH = 0; pc.cutV = 0; pc.exists = 1;
+    if (needH | needV) pc = find_path_cuts(base, sub == 0 ? me : en, sub == 0 ? en : me, sub == 0 ? kRow0 : kRow8);
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int src = (lane & ~1) | p;
+        const int ex = __shfl_sync(0xffffffffu, pc.exists, src);
+        const u64 ch = ((u64)__shfl_sync(0xffffffffu, (unsigned)(pc.cutH >> 32), src) << 32) | __shfl_sync(0xffffffffu, (unsigned)pc.cutH, src);
+        const u64 cv = ((u64)__shfl_sync(0xffffffffu, (unsigned)(pc.cutV >> 32), src) << 32) | __shfl_sync(0xffffffffu, (unsigned)pc.cutV, src);
+        set[2 * p + 0] = needH & (ex ? ch : ~0ull);
+        set[2 * p + 1] = needV & (ex ? cv : ~0ull);
+    }
+    int offs[5];
+    offs[0] = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) offs[q + 1] = offs[q] + __popcll(set[q]);
+    const int total = valid ? offs[4] : 0;
+    // list space for the whole warp with one atomic: exclusive scan of the per-state totals (held by both lanes of a pair)
+    int incl = sub == 0 ? total : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned wbase = 0;
+    if (lane == 0 && warp_total) wbase = atomicAdd(counter, (unsigned)warp_total);
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    const unsigned start = wbase + (unsigned)__shfl_sync(0xffffffffu, incl - (sub == 0 ? total : 0), lane & ~1);
+    const bool fits = (u64)start + (unsigned)total <= cap;
+    if (!total || fits) {
+        // optimistic: every gated candidate legal (those whose witnesses survive need no search at all);
+        // legal_search_kernel clears the bits of the candidates whose search fails
+        if (total) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                for (int slot = sub; slot < 64; slot += 2)
+                    if ((set[q] >> slot) & 1)
+                        tasks[start + offs[q] + __popcll(set[q] & ((1ull << slot) - 1))] = ((uint32_t)b << 8) | (uint32_t)(slot | (q << 6));
+        }
+        legalH |= needH;
+        legalV |= needV;
+    } else {
+        // the list is full: mark what is left of it as holes and run this state's searches here
+        for (unsigned t = start + sub; t < cap; t += 2) tasks[t] = kNullTask;
+        u64 failH = 0, failV = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            for (int slot = sub; slot < 64; slot += 2)
+                if ((set[q] >> slot) & 1) {
+                    const int orient = (q & 1) + 1;
+                    Open o = base;
+                    add_wall(o, orient, slot);
+                    const bool ok = (q >> 1) ? reaches(o, en, me, kRow8) : reaches(o, me, en, kRow0);
+                    if (!ok) { if (orient == 1) failH |= 1ull << slot; else failV |= 1ull << slot; }
+                }
+        const unsigned pm2 = 3u << (lane & ~1);
+        failH |= ((u64)__shfl_xor_sync(pm2, (unsigned)(failH >> 32), 1) << 32) | __shfl_xor_sync(pm2, (unsigned)failH, 1);
+        failV |= ((u64)__shfl_xor_sync(pm2, (unsigned)(failV >> 32), 1) << 32) | __shfl_xor_sync(pm2, (unsigned)failV, 1);
+        legalH |= needH & ~failH;
+        legalV |= needV & ~failV;
+    }
+    if (sub == 0 && valid) {
+        uint8_t pm[8] = {0, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0, 0};
+        const int n = pawn_moves(base, me, en, pm + 1);
+        pm[0] = (uint8_t)n;
+        u128 lo = 0;
+        for (int k = 0; k < n; ++k) lo |= bit81(pm[1 + k]);
+        lo |= (u128)legalH << 81;                                  // H wall actions 81..144
+        const u128 hi = (u128)(legalH >> 47) | ((u128)legalV << 17);  // V wall actions 145..208
+        uint4 *m = reinterpret_cast<uint4 *>(mask + 8 * b);
+        uint4 w;
+        w.x = (unsigned)lo; w.y = (unsigned)(lo >> 32); w.z = (unsigned)(lo >> 64); w.w = (unsigned)(lo >> 96);
+        m[0] = w;
+        w.x = (unsigned)hi; w.y = (unsigned)(hi >> 32); w.z = (unsigned)(hi >> 64); w.w = (unsigned)(hi >> 96);
+        m[1] = w;
+        uint2 p;
+        p.x = pm[0] | (pm[1] << 8) | (pm[2] << 16) | ((unsigned)pm[3] << 24);
+        p.y = pm[4] | (pm[5] << 8);
+        *reinterpret_cast<uint2 *>(pawn + 8 * b) = p;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+legal_search_kernel(const AqState *__restrict__ states, const uint32_t *__restrict__ tasks, const unsigned *__restrict__ counter,
+                    unsigned cap, uint32_t *__restrict__ mask) {
+    const unsigned n = min(*counter, cap);
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const uint32_t w = __ldg(tasks + t);
+        if (w == kNullTask) continue;
+        const int64_t b = w >> 8;
+        const int slot = w & 63, orient = ((w >> 6) & 1) + 1, opp = (w >> 7) & 1;
+        const AqState s = load_state(states + b);
+        Open o = open_from_walls(s.hwalls, s.vwalls);
+        add_wall(o, orient, slot);
+        const int me = s.ppos, en = 80 - (int)s.epos;
+        const bool ok = opp ? reaches(o, en, me, kRow8) : reaches(o, me, en, kRow0);
+        if (!ok) {
+            const int a = AQ_SQUARES + (orient == 2 ? AQ_SLOTS : 0) + slot;
+            atomicAnd(mask + 8 * b + (a >> 5), ~(1u << (a & 31)));
+        }
     }
 }
 
@@ -381,11 +527,52 @@ extern "C" int aq_unpack_states(const AqState *states, int64_t B, uint8_t *rows6
     return aq_check_launch("aq_unpack_states");
 }
 
-extern "C" int aq_legal_mask(const AqState *states, int64_t B, uint32_t *mask, uint8_t *pawn, void *stream) {
+static inline size_t legal_task_cap(int64_t B) { const int64_t n = B < kLegalChunk ? B : kLegalChunk; return (size_t)(8 * n + 4096); }
+extern "C" int64_t aq_legal_mask_ws_bytes(int64_t B) { return B <= 0 ? 256 : (int64_t)(256 + 4 * legal_task_cap(B)); }
+
+// ws == NULL: the one-kernel form (lanes per state by batch size); else the two-phase form.
+extern "C" int aq_legal_mask_ws(const AqState *states, int64_t B, uint32_t *mask, uint8_t *pawn, void *ws, int64_t ws_bytes,
+                                void *stream) {
     if (B < 0 || (B > 0 && (!states || !mask || !pawn))) return aq_set_error(AQ_ERR_ARG, "aq_legal_mask");
     if (B == 0) return 0;
-    legal_mask_kernel<<<blocks_for(B, kLegalWarps * kStatesPerWarp), kLegalWarps * 32, 0, S(stream)>>>(states, B, mask, pawn);
-    return aq_check_launch("aq_legal_mask");
+    const char *env = getenv("AQ_LEGAL_LANES");  // experiments only: force the one-kernel form with 2 / 8 / 32 lanes per state
+    const int env_lanes = env ? atoi(env) : 0;
+    // measured on B200 (scripts/legal_lanes.py, gpurun_out/legal_lanes.log): up to 4,096 states one kernel with many lanes per
+    // state has the shorter critical path; above, the two-phase form wins (45 vs 66 us at 16K, 1.22 vs 2.19 ms at 1M)
+    if (!ws || env_lanes || B <= 4096) {
+        const int lanes = env_lanes ? env_lanes : (B <= 1024 ? 32 : B <= 16384 ? 8 : 2);
+        if (lanes == 32)
+            legal_mask_kernel<32><<<blocks_for(B, kLegalWarps * 1), kLegalWarps * 32, 0, S(stream)>>>(states, B, mask, pawn);
+        else if (lanes == 8)
+            legal_mask_kernel<8><<<blocks_for(B, kLegalWarps * 4), kLegalWarps * 32, 0, S(stream)>>>(states, B, mask, pawn);
+        else
+            legal_mask_kernel<2><<<blocks_for(B, kLegalWarps * 16), kLegalWarps * 32, 0, S(stream)>>>(states, B, mask, pawn);
+        return aq_check_launch("aq_legal_mask");
+    }
+    // any workspace >= 4 KB + 256 B works (a state whose searches do not fit the list runs them itself); aq_legal_mask_ws_bytes(B)
+    // is the size at which that practically never happens
+    if (ws_bytes < 256 + 4096 || (reinterpret_cast<uintptr_t>(ws) & 3)) return aq_set_error(AQ_ERR_ARG, "aq_legal_mask(workspace)");
+    unsigned *counter = reinterpret_cast<unsigned *>(ws);
+    uint32_t *tasks = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(ws) + 256);
+    const unsigned cap = (unsigned)std::min<int64_t>((ws_bytes - 256) / 4, (int64_t)legal_task_cap(B));
+    for (int64_t lo = 0; lo < B; lo += kLegalChunk) {
+        const int64_t n = B - lo < kLegalChunk ? B - lo : kLegalChunk;
+        cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), S(stream));
+        if (e != cudaSuccess) return aq_set_error((int)e, "aq_legal_mask(memset)");
+        legal_prepare_kernel<<<blocks_for(n, kLegalWarps * 16), kLegalWarps * 32, 0, S(stream)>>>(states + lo, n, mask + 8 * lo, pawn + 8 * lo,
+                                                                                                     tasks, cap, counter);
+        // enough threads for the expected number of searches (2-4 per state), at most 16 CTAs of 128 per SM; grid-stride beyond
+        const unsigned grid = (unsigned)std::min<int64_t>(148 * 16, std::max<int64_t>(1, (4 * n + 127) / 128));
+        legal_search_kernel<<<grid, 128, 0, S(stream)>>>(states + lo, tasks, counter, cap, mask + 8 * lo);
+        const int rc = aq_check_launch("aq_legal_mask");
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// State.legal_actions() without a workspace: the one-kernel form (no allocation inside the library).
+extern "C" int aq_legal_mask(const AqState *states, int64_t B, uint32_t *mask, uint8_t *pawn, void *stream) {
+    return aq_legal_mask_ws(states, B, mask, pawn, nullptr, 0, stream);
 }
 
 extern "C" int aq_legal_actions_list(const uint32_t *mask, const uint8_t *pawn, int64_t B, int16_t *actions,

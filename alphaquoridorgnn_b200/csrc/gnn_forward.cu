@@ -3,6 +3,8 @@
 //                             iteration, all activations resident in shared memory
 //   heads_forward_kernel    : policy / value MLPs, softmax, tanh, optional legal-action
 //                             renormalisation (BaseNetwork.predict semantics)
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include "gnn_fp32.cuh"
 
@@ -374,14 +376,18 @@ extern "C" int aq_gnn_forward(const float *params, const AqState *states, const 
     return rc;
 }
 
-extern "C" int64_t aq_leaf_eval_ws_floats(int64_t B) { return B * kH; }
+// workspace of one leaf evaluation: pooled [B,128] | the legal-mask task list (aq_legal_mask_ws_bytes)
+extern "C" int64_t aq_legal_mask_ws_bytes(int64_t B);
+extern "C" int aq_legal_mask_ws(const AqState *states, int64_t B, uint32_t *mask, uint8_t *pawn, void *ws, int64_t ws_bytes, void *stream);
+static inline int64_t leaf_pooled_floats(int64_t B) { return (B * kH + 63) / 64 * 64; }
+extern "C" int64_t aq_leaf_eval_ws_floats(int64_t B) { return leaf_pooled_floats(B) + (aq_legal_mask_ws_bytes(B) + 3) / 4; }
 
 extern "C" int aq_leaf_eval(const float *params, const void *prepared, const AqState *states, int64_t B, float *priors,
                             float *value, uint32_t *mask, uint8_t *pawn, float *workspace, int precision, void *stream) {
     if (B < 0 || !params || (B > 0 && (!states || !priors || !value || !mask || !pawn || !workspace)))
         return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval");
     if (B == 0) return 0;
-    int rc = aq_legal_mask(states, B, mask, pawn, stream);
+    int rc = aq_legal_mask_ws(states, B, mask, pawn, workspace + leaf_pooled_floats(B), aq_legal_mask_ws_bytes(B), stream);
     if (rc) return rc;
     return aq_gnn_forward_impl(params, prepared, states, nullptr, nullptr, B, priors, value, nullptr, workspace, mask, precision,
                                reinterpret_cast<cudaStream_t>(stream));
@@ -391,9 +397,18 @@ extern "C" int aq_leaf_eval(const float *params, const void *prepared, const AqS
 // device workspace layout: states | priors | value | mask | pawn | pooled
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// every chunk of the pipelined host path owns a leaf-evaluation workspace for its `per` boards; the workspace size is linear
+// in the board count plus a constant < 32 KB, so all chunks together fit host_ws_region_bytes(B)
+constexpr int kHostMaxChunks = 8;
+static inline size_t host_chunk_ws_bytes(int64_t per) { return align256((size_t)aq_leaf_eval_ws_floats(per) * 4); }
+static inline size_t host_ws_region_bytes(int64_t B) {
+    const size_t saturated = B > ((int64_t)1 << 23) ? kHostMaxChunks * (size_t)aq_legal_mask_ws_bytes(B) : 0;  // the task list stops growing at 2^23 states
+    return host_chunk_ws_bytes(B + 128 * kHostMaxChunks) + kHostMaxChunks * (size_t)32768 + saturated;
+}
+
 extern "C" int64_t aq_leaf_eval_host_ws_bytes(int64_t B) {
     return (int64_t)(align256((size_t)B * sizeof(AqState)) + align256((size_t)B * kP * 4) + align256((size_t)B * 4) +
-                     align256((size_t)B * 32) + align256((size_t)B * 8) + align256((size_t)B * kH * 4));
+                     align256((size_t)B * 32) + align256((size_t)B * 8) + host_ws_region_bytes(B));
 }
 
 // Host-side context for the pipelined host-buffer path: worker streams, their events, and a small cache of
@@ -456,7 +471,7 @@ static int enqueue_host_pipeline(AqHostCtx *ctx, cudaStream_t origin, int nchunk
     float *d_value = reinterpret_cast<float *>(p);      p += align256((size_t)B * 4);
     uint32_t *d_mask = reinterpret_cast<uint32_t *>(p); p += align256((size_t)B * 32);
     uint8_t *d_pawn = reinterpret_cast<uint8_t *>(p);   p += align256((size_t)B * 8);
-    float *d_pooled = reinterpret_cast<float *>(p);
+    unsigned char *d_chunk_ws = p;
     const AqState *states_host = reinterpret_cast<const AqState *>(k.states_host);
     float *priors_host = reinterpret_cast<float *>(const_cast<void *>(k.priors_host));
     float *value_host = reinterpret_cast<float *>(const_cast<void *>(k.value_host));
@@ -477,7 +492,8 @@ static int enqueue_host_pipeline(AqHostCtx *ctx, cudaStream_t origin, int nchunk
         e = cudaMemcpyAsync(d_states + lo, states_host + lo, (size_t)n * sizeof(AqState), cudaMemcpyHostToDevice, cs);
         if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host(H2D)");
         int rc = aq_leaf_eval(reinterpret_cast<const float *>(k.params), k.prepared, d_states + lo, n, d_priors + lo * kP,
-                              d_value + lo, d_mask + lo * 8, d_pawn + lo * 8, d_pooled + lo * kH, k.precision, cs);
+                              d_value + lo, d_mask + lo * 8, d_pawn + lo * 8,
+                              reinterpret_cast<float *>(d_chunk_ws + (size_t)c * host_chunk_ws_bytes(per)), k.precision, cs);
         if (rc) return rc;
         e = cudaMemcpyAsync(priors_host + lo * kP, d_priors + lo * kP, (size_t)n * kP * 4, cudaMemcpyDeviceToHost, cs);
         if (e == cudaSuccess) e = cudaMemcpyAsync(value_host + lo, d_value + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, cs);
@@ -537,7 +553,8 @@ extern "C" int aq_leaf_eval_host(const float *params, const void *prepared, cons
     // with a context, batches >= 4096 are split in two so that the D2H of the first half overlaps the kernels of the second; when all
     // host buffers are pinned the whole pipeline is one CUDA graph per argument tuple (~40 API calls -> one launch)
     static const int env_chunks = getenv("AQ_HOST_CHUNKS") ? atoi(getenv("AQ_HOST_CHUNKS")) : 0;
-    const int nchunk = (ctx && B >= 4096) ? (env_chunks > 0 ? env_chunks : 2) : 1;  // measured: 2 chunks beat 1, 3, 4 and 6 at B = 16384
+    int nchunk = (ctx && B >= 4096) ? (env_chunks > 0 ? env_chunks : 2) : 1;  // measured: 2 chunks beat 1, 3, 4 and 6 at B = 16384
+    if (nchunk > kHostMaxChunks) nchunk = kHostMaxChunks;
     cudaError_t e = cudaSuccess;
     cudaGraphExec_t exec = nullptr;
     if (ctx && ctx->graphs_ok && is_pinned_host(states_host) && is_pinned_host(priors_host) && is_pinned_host(value_host) &&
@@ -661,7 +678,7 @@ extern "C" int aq_compact_priors(const float *priors, const uint32_t *mask, cons
 
 // Host-buffer leaf evaluation with predict()-shaped output.  Device workspace: the dense workspace of
 // aq_leaf_eval_host followed by offsets int32[B + chunks] and compact f32[B * 136].
-constexpr int kCompactMaxChunks = 8;
+constexpr int kCompactMaxChunks = kHostMaxChunks;
 extern "C" int64_t aq_leaf_eval_host_compact_ws_bytes(int64_t B) {
     return aq_leaf_eval_host_ws_bytes(B) + (int64_t)align256((size_t)(B + kCompactMaxChunks) * 4) +
            (int64_t)align256((size_t)B * AQ_MAX_LEGAL * 4);
@@ -682,11 +699,15 @@ extern "C" int aq_leaf_eval_host_compact(const float *params, const void *prepar
     float *d_value = reinterpret_cast<float *>(p);      p += align256((size_t)B * 4);
     uint32_t *d_mask = reinterpret_cast<uint32_t *>(p); p += align256((size_t)B * 32);
     uint8_t *d_pawn = reinterpret_cast<uint8_t *>(p);   p += align256((size_t)B * 8);
-    float *d_pooled = reinterpret_cast<float *>(p);     p += align256((size_t)B * kH * 4);
+    unsigned char *d_chunk_ws = p;                      p += host_ws_region_bytes(B);
     int32_t *d_offsets = reinterpret_cast<int32_t *>(p); p += align256((size_t)(B + kCompactMaxChunks) * 4);
     float *d_compact = reinterpret_cast<float *>(p);
 
     static const int env_chunks = getenv("AQ_HOST_CHUNKS") ? atoi(getenv("AQ_HOST_CHUNKS")) : 0;
+    static const bool trace = getenv("AQ_HOST_TRACE") != nullptr;  // host-side timestamps of the pipeline on stderr (scripts/e2e_probe.py)
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto us_since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
+    double t_front = 0, t_sync[kCompactMaxChunks] = {0}, t_issue[kCompactMaxChunks] = {0};
     int nchunk = B >= 4096 ? (env_chunks > 0 ? env_chunks : 2) : 1;
     if (nchunk > kCompactMaxChunks) nchunk = kCompactMaxChunks;
     const int64_t per = ((B + nchunk - 1) / nchunk + 127) / 128 * 128;
@@ -704,7 +725,7 @@ extern "C" int aq_leaf_eval_host_compact(const float *params, const void *prepar
         e = cudaMemcpyAsync(d_states + lo, states_host + lo, (size_t)n * sizeof(AqState), cudaMemcpyHostToDevice, cs);
         if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(H2D)");
         int rc = aq_leaf_eval(params, prepared, d_states + lo, n, d_priors + lo * kP, d_value + lo, d_mask + lo * 8, d_pawn + lo * 8,
-                              d_pooled + lo * kH, precision, cs);
+                              reinterpret_cast<float *>(d_chunk_ws + (size_t)c * host_chunk_ws_bytes(per)), precision, cs);
         if (rc) return rc;
         rc = aq_compact_priors(d_priors + lo * kP, d_mask + lo * 8, d_pawn + lo * 8, n, d_off, d_compact + lo * AQ_MAX_LEGAL, cs);
         if (rc) return rc;
@@ -716,12 +737,14 @@ extern "C" int aq_leaf_eval_host_compact(const float *params, const void *prepar
         if (e == cudaSuccess) e = cudaEventRecord(ctx->chunk_done[c], cs);
         if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(D2H)");
     }
+    t_front = us_since();
     // back half: as each chunk's total reaches the host, copy exactly that many probabilities behind the previous chunk's
     int64_t base = 0;
     for (int c = 0; c < used; ++c) {
         const int64_t lo = (int64_t)c * per, n = (lo + per <= B ? per : B - lo);
         e = cudaEventSynchronize(ctx->chunk_done[c]);
         if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(sync)");
+        t_sync[c] = us_since();
         // offsets_host[lo + i] currently holds the chunk-local INCLUSIVE end of board lo + i
         const int64_t total = offsets_host[lo + n - 1];
         if (base + total > priors_capacity) return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host_compact(priors_capacity too small)");
@@ -731,6 +754,7 @@ extern "C" int aq_leaf_eval_host_compact(const float *params, const void *prepar
         }
         if (base) for (int64_t i = 0; i < n; ++i) offsets_host[lo + i] += (int32_t)base;
         base += total;
+        t_issue[c] = us_since();
     }
     // shift to the exclusive convention: offsets_host[b] = start of board b, offsets_host[B] = total
     for (int64_t i = B; i > 0; --i) offsets_host[i] = offsets_host[i - 1];
@@ -741,5 +765,10 @@ extern "C" int aq_leaf_eval_host_compact(const float *params, const void *prepar
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(origin);
     if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(join)");
+    if (trace) {
+        fprintf(stderr, "[aq host trace] B=%lld chunks=%d front enqueued %.0f us;", (long long)B, used, t_front);
+        for (int c = 0; c < used; ++c) fprintf(stderr, " chunk %d: results on host %.0f, priors copy issued %.0f;", c, t_sync[c], t_issue[c]);
+        fprintf(stderr, " all done %.0f us\n", us_since());
+    }
     return 0;
 }

@@ -105,9 +105,10 @@ def legal_mask_batch(packed):
     mask = torch.empty((B, 8), dtype=torch.int32, device=packed.device)
     pawn = torch.empty((B, 8), dtype=torch.uint8, device=packed.device)
     L = _lib.load()
+    ws = torch.empty((L.aq_legal_mask_ws_bytes(B),), dtype=torch.uint8, device=packed.device)  # task list of the two-phase form
     with torch.cuda.device(packed.device):
-        _lib.check(L.aq_legal_mask(_lib.ptr(packed), B, _lib.ptr(mask), _lib.ptr(pawn), _lib.stream_ptr(packed.device)),
-                   "aq_legal_mask")
+        _lib.check(L.aq_legal_mask_ws(_lib.ptr(packed), B, _lib.ptr(mask), _lib.ptr(pawn), _lib.ptr(ws), ws.numel(),
+                                      _lib.stream_ptr(packed.device)), "aq_legal_mask_ws")
     return mask, pawn
 
 

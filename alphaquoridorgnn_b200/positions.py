@@ -51,3 +51,15 @@ def random_positions(n, seed=1, games=8192, device=None, max_plies=116):
             nxt, term = gl.next_batch(cur, action)
             packed = nxt[term == 0].contiguous()
     return torch.cat(out, 0)[:n].contiguous()
+
+
+def mixed_batches(nb, B, seed=1, device=None):
+    """nb batches of B positions with the same mix of game phases (plies 0..~31: full wall racks down to endgames):
+    one trajectory harvest of nb*B positions from nb*B/32 lock-step games, shuffled with a fixed permutation.
+    The workload of bench.py and of the committed ncu captures."""
+    dev = gl._dev(device)
+    allpos = random_positions(nb * B, seed=seed, games=max(64, nb * B // 32), device=dev)
+    g = torch.Generator(device="cpu")
+    g.manual_seed(1234 + seed)
+    allpos = allpos[torch.randperm(nb * B, generator=g).to(dev)].contiguous()
+    return allpos, [allpos[i * B:(i + 1) * B].contiguous() for i in range(nb)]

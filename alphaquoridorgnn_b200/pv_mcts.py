@@ -62,7 +62,7 @@ class BatchedMCTS:
                 "value": torch.empty((G,), dtype=torch.float32, device=dev),
                 "mask": torch.empty((G, 8), dtype=torch.int32, device=dev),
                 "pawn": torch.empty((G, 8), dtype=torch.uint8, device=dev),
-                "pooled": torch.empty((G, 128), dtype=torch.float32, device=dev),
+                "pooled": torch.empty((max(1, _lib.load().aq_leaf_eval_ws_floats(G)),), dtype=torch.float32, device=dev),  # leaf-eval workspace
             }
         return self._buf[G]
 
@@ -110,7 +110,9 @@ class BatchedMCTS:
                         if len(self._graphs) >= 16:  # self-play shrinks G as games end: keep the cache bounded
                             self._graphs.clear()
                         self._graphs[key] = graph = g
-                    except Exception:  # capture unsupported: stay eager
+                    except Exception as e:  # capture unsupported: stay eager, but say so
+                        import warnings
+                        warnings.warn(f"CUDA-graph capture of the MCTS simulation step failed ({e!r}); running the step eagerly")
                         self.use_graph, graph, done = False, None, 1
                         torch.cuda.synchronize(dev)
                 else:
@@ -195,23 +197,31 @@ def bench_sims_per_sec(net, dev, world, timed_barrier, games=4096, sims=200, mov
     from . import positions
     import torch.distributed as dist
     mcts = BatchedMCTS(net, sims, device=dev)
-    roots = positions.start_states(games, dev)
     gen = torch.Generator(device=dev)
+
+    def play(n_moves):
+        roots = positions.start_states(games, dev)
+        done = 0
+        for _ in range(n_moves):
+            counts, actions, n = mcts.search(roots)
+            pol = policy_from_counts(counts, 1.0)
+            pick = torch.multinomial(pol.float(), 1, generator=gen)
+            act = torch.gather(actions, 1, pick).squeeze(1)
+            roots, term = gl.next_batch(roots, act)
+            done += roots.shape[0] * sims
+            roots = roots[term == 0].contiguous()
+        return done
+
     gen.manual_seed(5)
-    mcts.search(roots, sims=sims)  # warm-up with the same shape: the simulation-step CUDA graph is captured here
+    play(1)  # warm-up of the whole move cycle with the timed shape: the simulation-step CUDA graph is captured here and every
+    #          torch kernel of the sampling step is loaded (CUDA loads modules lazily, milliseconds each)
+    gen.manual_seed(5)
     timed_barrier()
     t0 = time.perf_counter()
-    done = 0
-    for _ in range(moves):
-        counts, actions, n = mcts.search(roots)
-        pol = policy_from_counts(counts, 1.0)
-        pick = torch.multinomial(pol.float(), 1, generator=gen)
-        act = torch.gather(actions, 1, pick).squeeze(1)
-        roots, term = gl.next_batch(roots, act)
-        done += roots.shape[0] * sims
-        roots = roots[term == 0].contiguous()
+    done = play(moves)
     timed_barrier()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    return {"mcts_sims_per_sec": world * done / float(dt.item()), "mcts_config": f"{games} games x {sims} sims x {moves} moves per GPU"}
+    return {"mcts_sims_per_sec": world * done / float(dt.item()), "mcts_config": f"{games} games x {sims} sims x {moves} moves per GPU",
+            "mcts_cuda_graph": bool(mcts.use_graph)}

@@ -138,8 +138,13 @@ class GraphPolicyValueNetwork(nn.Module):
         self._weights_epoch = 0    # bumped by writers that update the flat buffer through raw pointers (FlatTrainer)
 
     def ordered_parameters(self):
-        named = dict(self.named_parameters())
-        return [named[n] for n in FLAT_PARAM_ORDER]
+        # the Parameter objects keep their identity across .to() / load_state_dict (only .data is replaced), so the module
+        # traversal is done once; this is on the path of every predict / search call
+        cached = self.__dict__.get("_ordered_params")
+        if cached is None:
+            named = dict(self.named_parameters())
+            cached = self.__dict__["_ordered_params"] = [named[n] for n in FLAT_PARAM_ORDER]
+        return cached
 
     # ---- flat parameter buffer: every parameter is a view into one f32[64082] tensor ------------
     def flat_parameters(self):
@@ -325,6 +330,100 @@ class GNNNetwork(GraphPolicyValueNetwork):
                 total += loss.item()
             history.append(total)
         return history
+
+
+class HostLeafEvaluator:
+    """Batched ``predict`` for callers whose states and results live in HOST memory (a Python tree search such as the
+    reference's pv_mcts.py Node tree, many games at once): one call moves B packed states to the GPU, evaluates them and
+    brings back exactly what ``BaseNetwork.predict`` returns per state -- the probabilities of the legal actions only, in
+    ``state.legal_actions()`` order (BaseNetwork.py:36-40) -- as a ragged array, plus value, legal mask and pawn list.
+
+    Pinned host buffers, the device workspace and the worker streams are allocated once for ``max_batch``.
+        ev = HostLeafEvaluator(net, 16384)
+        ev.states[:B] = game_logic.pack_rows_host(rows, plies)      # fill the pinned input
+        out = ev.evaluate(B)   # dict of numpy views: priors [total], offsets [B+1], value [B], mask [B,8], pawn [B,8]
+        p_b = out["priors"][out["offsets"][b]:out["offsets"][b + 1]]   # == predict(state_b)[0]
+    """
+
+    def __init__(self, net, max_batch, dense=False):
+        import ctypes
+        flat = net.flat_parameters()
+        _lib.require_cuda(flat, "model parameters")
+        self.net, self.dev, self.max_batch, self.dense = net, flat.device, int(max_batch), bool(dense)
+        L = self.L = _lib.load()
+        B = self.max_batch
+        self.states = torch.empty((B, gl.STATE_BYTES), dtype=torch.uint8).pin_memory()
+        self.value = torch.empty((B,), dtype=torch.float32).pin_memory()
+        self.mask = torch.empty((B, 8), dtype=torch.int32).pin_memory()
+        self.pawn = torch.empty((B, 8), dtype=torch.uint8).pin_memory()
+        if dense:
+            self.priors = torch.empty((B, POLICY_OUTPUT_SIZE), dtype=torch.float32).pin_memory()
+            self.offsets = None
+            nbytes = L.aq_leaf_eval_host_ws_bytes(B)
+        else:
+            self.priors = torch.empty((B * gl.MAX_LEGAL,), dtype=torch.float32).pin_memory()
+            self.offsets = torch.empty((B + 1,), dtype=torch.int32).pin_memory()
+            nbytes = L.aq_leaf_eval_host_compact_ws_bytes(B)
+        self.ws = torch.empty((max(1, nbytes),), dtype=torch.uint8, device=self.dev)
+        self._ctx = ctypes.c_void_p()
+        _lib.check(L.aq_host_ctx_create(ctypes.byref(self._ctx)), "aq_host_ctx_create")
+        self.refresh_weights()
+
+    def refresh_weights(self):
+        """Re-reads the network's parameters (flat buffer, bf16 operand tiles, precision).  Like the reference's
+        prep_for_inference (BaseNetwork.py:21-32) the evaluator works on the weights as they were at this call; call it again
+        after a training step or load_state_dict."""
+        net = self.net
+        self._flat = net.flat_parameters()
+        self._prec = PRECISIONS[net.precision]
+        self._prep = net.prepared_weights() if self._prec == 1 else None
+        P = _lib.ptr
+        self._fixed = (P(self.priors), P(self.offsets) if self.offsets is not None else None, P(self.value), P(self.mask), P(self.pawn),
+                       P(self.ws), P(self._flat), P(self._prep), P(self.states))
+
+    def close(self):
+        if self._ctx:
+            self.L.aq_host_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def evaluate(self, B=None, states=None):
+        """Evaluates self.states[:B] (or ``states``, the caller's own host uint8[B,32] tensor -- pinned memory makes the copy
+        asynchronous); synchronous.  Returns numpy views into the pinned result buffers."""
+        src = self.states if states is None else states
+        if src.is_cuda or src.dtype != torch.uint8 or not src.is_contiguous():
+            raise ValueError("states must be a contiguous host uint8[B,32] tensor")
+        B = (self.max_batch if states is None else states.shape[0]) if B is None else int(B)
+        if not 0 <= B <= min(self.max_batch, src.shape[0]):
+            raise ValueError("batch larger than max_batch")
+        L = self.L
+        p_pri, p_off, p_val, p_msk, p_pwn, p_ws, p_flat, p_prep, p_states = self._fixed
+        if states is not None:
+            p_states = _lib.ptr(src)
+        with torch.cuda.device(self.dev):
+            st = _lib.stream_ptr(self.dev)
+            if self.dense:
+                _lib.check(L.aq_leaf_eval_host(p_flat, p_prep, p_states, B, p_pri, p_val, p_msk, p_pwn, p_ws, self._prec, self._ctx, st),
+                           "aq_leaf_eval_host")
+                return {"priors": self.priors[:B].numpy(), "value": self.value[:B].numpy(), "mask": self.mask[:B].numpy(),
+                        "pawn": self.pawn[:B].numpy()}
+            _lib.check(L.aq_leaf_eval_host_compact(p_flat, p_prep, p_states, B, p_pri, self.priors.numel(), p_off, p_val, p_msk, p_pwn,
+                                                   p_ws, self._prec, self._ctx, st), "aq_leaf_eval_host_compact")
+        off = self.offsets[:B + 1].numpy()
+        return {"priors": self.priors[:int(off[B])].numpy(), "offsets": off, "value": self.value[:B].numpy(),
+                "mask": self.mask[:B].numpy(), "pawn": self.pawn[:B].numpy()}
+
+    def d2h_bytes(self, out):
+        """Bytes that crossed PCIe device -> host for this result (for bench.py's e2e accounting)."""
+        B = out["value"].shape[0]
+        if self.dense:
+            return B * (POLICY_OUTPUT_SIZE * 4 + 4 + 32 + 8)
+        return int(out["offsets"][B]) * 4 + B * (4 + 4 + 32 + 8)
 
 
 # Function to create the dual network

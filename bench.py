@@ -89,7 +89,7 @@ def oracle_random_positions(n, seed):
     rng = np.random.default_rng(seed)
     out_rows, out_plies, total = [], [], 0
     while total < n:
-        G = 2048
+        G = max(64, n // 32)  # ~32 plies deep, the same mix of game phases as positions.random_positions in run_ours
         rows = np.zeros((G, 68), np.uint8)
         rows[:, [0, 2]] = 76
         rows[:, [1, 3]] = 10
@@ -191,13 +191,13 @@ def run_ours(args, rank, world, local_rank):
     # inference weights prepared once, as prep_for_inference does (the weights do not change between evaluations)
     prep = net.prepared_weights() if prec == 1 else None
     nb = 4
-    allpos = positions.random_positions(nb * B, seed=1 + rank, games=8192, device=dev)
-    batches = [allpos[i * B:(i + 1) * B].contiguous() for i in range(nb)]
+    allpos, batches = positions.mixed_batches(nb, B, seed=1 + rank, device=dev)
     priors = torch.empty((B, 209), dtype=torch.float32, device=dev)
     value = torch.empty((B,), dtype=torch.float32, device=dev)
     mask = torch.empty((B, 8), dtype=torch.int32, device=dev)
     pawn = torch.empty((B, 8), dtype=torch.uint8, device=dev)
-    pooled = torch.empty((B, 128), dtype=torch.float32, device=dev)
+    pooled = torch.empty((L.aq_leaf_eval_ws_floats(B),), dtype=torch.float32, device=dev)  # leaf-eval workspace: pooled [B,128] | legal-mask task list
+    lws = torch.empty((L.aq_legal_mask_ws_bytes(B),), dtype=torch.uint8, device=dev)
     flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
     st = _lib.stream_ptr(dev)
     P = _lib.ptr
@@ -236,7 +236,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- per-kernel durations (same inputs, same stream) for the roofline ------------------------
     def k_legal(i):
-        _lib.check(L.aq_legal_mask(P(batches[i % nb]), B, P(mask), P(pawn), st), "aq_legal_mask")
+        _lib.check(L.aq_legal_mask_ws(P(batches[i % nb]), B, P(mask), P(pawn), P(lws), lws.numel(), st), "aq_legal_mask_ws")
 
     def k_trunk(i):
         _lib.check(L.aq_gcn_trunk_forward(P(flat), P(prep), P(batches[i % nb]), B, P(pooled), prec, st), "aq_gcn_trunk_forward")
@@ -244,11 +244,11 @@ def run_ours(args, rank, world, local_rank):
     def k_heads(i):
         _lib.check(L.aq_heads_forward(P(flat), P(prep), P(pooled), B, P(priors), P(value), P(mask), prec, st), "aq_heads_forward")
 
-    kms = {"legal_mask_kernel": timed(k_legal, K, 2), "gcn_forward_kernel": timed(k_trunk, K, 2),
+    kms = {"legal_mask_kernels": timed(k_legal, K, 2), "gcn_forward_kernel": timed(k_trunk, K, 2),
            "heads_forward_kernel": timed(k_heads, K, 2)}
     ksum = sum(kms.values())
     kinfo = {
-        "legal_mask_kernel": {"bound": "hbm", "achieved": BYTES_PER_POSITION_LEGAL * B / (kms["legal_mask_kernel"] * 1e-3) / 1e9,
+        "legal_mask_kernels": {"bound": "hbm", "achieved": BYTES_PER_POSITION_LEGAL * B / (kms["legal_mask_kernels"] * 1e-3) / 1e9,
                               "peak": pk["hbm"], "unit": "GB/s"},
         "gcn_forward_kernel": {"bound": "tensor", "achieved": FLOP_PER_BOARD_FWD * B / (kms["gcn_forward_kernel"] * 1e-3) / 1e12,
                                "peak": pk["tensor"], "unit": "TFLOP/s"},
@@ -268,49 +268,55 @@ def run_ours(args, rank, world, local_rank):
                 "arith": "fp32 FFMA" if prec == 0 else "bf16 tcgen05 node transforms + fp16 tcgen05 aggregation, fp32 accumulate in TMEM",
                 "kernel_symbol": "gcn_forward_fp32_kernel" if prec == 0 else "gcn_forward_tc2_kernel"}
 
-    # ---- end to end through host buffers (H2D states, D2H priors/value/mask/pawn every step) -----
+    # ---- end to end through host buffers, every step: pinned packed states H2D, kernels, results D2H, stream sync ----
+    # Headline e2e = the repo's public host API (pv_network_gnn.HostLeafEvaluator -> aq_leaf_eval_host_compact): results in
+    # the shape BaseNetwork.predict returns them (probabilities of the LEGAL actions only, legal_actions() order, ragged),
+    # plus value / legal mask / pawn list.  The dense [B,209] flavour (aq_leaf_eval_host) is reported in extra.
+    from alphaquoridorgnn_b200.pv_network_gnn import HostLeafEvaluator
     hst = [torch.from_numpy(gl.pack_rows_host(*[t.cpu().numpy() for t in gl.unpack_rows(b)])).pin_memory() for b in batches]
     for h, b in zip(hst, batches):
         assert torch.equal(h, b.cpu())
-    h_pri = torch.empty((B, 209), dtype=torch.float32).pin_memory()
-    h_val = torch.empty((B,), dtype=torch.float32).pin_memory()
-    h_msk = torch.empty((B, 8), dtype=torch.int32).pin_memory()
-    h_pwn = torch.empty((B, 8), dtype=torch.uint8).pin_memory()
-    ws = torch.empty((L.aq_leaf_eval_host_ws_bytes(B),), dtype=torch.uint8, device=dev)
 
-    import ctypes
-    hctx = ctypes.c_void_p()
-    _lib.check(L.aq_host_ctx_create(ctypes.byref(hctx)), "aq_host_ctx_create")
+    def e2e_run(dense):
+        ev = HostLeafEvaluator(net, B, dense=dense)
+        d2h = []
 
-    def e2e_step(i):
-        _lib.check(L.aq_leaf_eval_host(P(flat), P(prep), P(hst[i % nb]), B, P(h_pri), P(h_val), P(h_msk), P(h_pwn), P(ws), prec, hctx, st),
-                   "aq_leaf_eval_host")
+        def e2e_step(i):
+            d2h.append(ev.d2h_bytes(ev.evaluate(B, states=hst[i % nb])))  # synchronous: results are on the host when it returns
 
-    for i in range(3):
-        e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(K):
-        e2e_step(i)  # synchronises the stream itself: results are on the host when it returns
-    barrier()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e = {"value": world * B * K / float(dt.item()), "unit": "board-evals/s", "h2d_bytes_per_step": B * 32,
-           "d2h_bytes_per_step": B * (209 * 4 + 4 + 32 + 8)}
+        for i in range(3):
+            e2e_step(i)
+        del d2h[:]
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            e2e_step(i)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        ev.close()
+        return world * B * K / float(dt.item()), int(sum(d2h) / len(d2h))
 
-    extra = {}
+    e2e_v, e2e_d2h = e2e_run(dense=False)
+    e2e = {"value": e2e_v, "unit": "board-evals/s", "h2d_bytes_per_step": B * 32, "d2h_bytes_per_step": e2e_d2h,
+           "api": "HostLeafEvaluator.evaluate -> aq_leaf_eval_host_compact: predict()-shaped ragged priors (legal actions only)"}
+    dense_v, dense_d2h = e2e_run(dense=True)
+
+    extra = {"e2e_dense_priors": {"value": dense_v, "unit": "board-evals/s", "d2h_bytes_per_step": dense_d2h,
+                                  "api": "aq_leaf_eval_host: dense priors [B,209]"}}
     if not args.skip_extra:
         # legal mask, BASELINE configs[1]: 1M positions resident in HBM (32 MB in, 40 MB out > L2? no: flushed)
         M = 1_000_000
         big = positions.random_positions(M, seed=101 + rank, games=16384, device=dev)
         bmask = torch.empty((M, 8), dtype=torch.int32, device=dev)
         bpawn = torch.empty((M, 8), dtype=torch.uint8, device=dev)
-        ms = timed(lambda i: _lib.check(L.aq_legal_mask(P(big), M, P(bmask), P(bpawn), st), "aq_legal_mask"), 5, 2)
+        bws = torch.empty((L.aq_legal_mask_ws_bytes(M),), dtype=torch.uint8, device=dev)
+        ms = timed(lambda i: _lib.check(L.aq_legal_mask_ws(P(big), M, P(bmask), P(bpawn), P(bws), bws.numel(), st), "aq_legal_mask_ws"), 5, 2)
         extra["legal_mask_positions_per_sec"] = world * M / (ms * 1e-3)
         extra["legal_mask_ms_per_1M"] = ms
         extra["legal_mask_hbm_frac"] = BYTES_PER_POSITION_LEGAL * M / (ms * 1e-3) / 1e9 / pk["hbm"]
-        del big, bmask, bpawn
+        del big, bmask, bpawn, bws
         # training step (forward + loss + backward + gradient all-reduce + Adam), random targets:
         #   B=256  -- BASELINE configs[0] shape (what one optimizer step of the reference looks like)
         #   B=4096 -- the same step at a throughput-sized per-GPU batch
@@ -375,7 +381,7 @@ def run_ours(args, rank, world, local_rank):
                        "batch_per_gpu": B, "precision": args.precision, "parallelism": f"independent leaf batches x{world}",
                        "l2": "flushed before every timed launch (256 MiB write, outside the per-launch CUDA events)"},
             "roofline": roofline, "kernels": kinfo, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": 3 * K, "clocks": clocks, "extra": extra,
+            "gpu_launches": 4 * K,  # legal_prepare + legal_search + trunk + heads per step (plus one 4-byte memset) "clocks": clocks, "extra": extra,
         }
         print(json.dumps(line), flush=True)
 

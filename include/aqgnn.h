@@ -69,6 +69,13 @@ int aq_unpack_states(const AqState *states, int64_t B, uint8_t *rows68, int16_t 
  * The ordered action list is pawn[1..n] followed by the wall bits of `mask` in ascending
  * slot order, H before V per slot (game_logic.py:352-355); aq_legal_actions_list emits it. */
 int aq_legal_mask(const AqState *states, int64_t B, uint32_t *mask, uint8_t *pawn, void *stream);
+/* Same with a caller-provided workspace (the list of path searches that the second kernel of the two-phase form works
+ * through): the faster form at every batch size.  aq_legal_mask_ws_bytes(B) is the recommended size; any size >= 4352
+ * bytes is valid (states whose searches do not fit the list run them in the first kernel).  ws == NULL selects the
+ * one-kernel form, which is what aq_legal_mask runs (the library never allocates).  Results are identical in every form. */
+int64_t aq_legal_mask_ws_bytes(int64_t B);
+int aq_legal_mask_ws(const AqState *states, int64_t B, uint32_t *mask, uint8_t *pawn, void *ws, int64_t ws_bytes,
+                     void *stream);
 int aq_legal_actions_list(const uint32_t *mask, const uint8_t *pawn, int64_t B, int16_t *actions /*[B,136], -1 pad*/,
                           int16_t *n_actions /*[B]*/, void *stream);
 
@@ -166,6 +173,27 @@ int aq_host_ctx_destroy(void *ctx);
 int aq_leaf_eval_host(const float *params, const void *prepared /* or NULL */, const AqState *states_host, int64_t B,
                       float *priors_host, float *value_host, uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws,
                       int precision, void *host_ctx, void *stream);
+
+/* predict()-shaped output (BaseNetwork.py:36-40, pv_network_cnn.py:128-135: the probabilities of the LEGAL actions
+ * only, in state.legal_actions() order) for a batch, as a ragged array:
+ *   offsets [B+1] int32 : offsets[b] = number of legal actions of boards < b, offsets[B] = total
+ *   compact [total] f32 : board b owns compact[offsets[b] .. offsets[b+1]); capacity B*136 is always enough
+ * priors/mask/pawn are the outputs of aq_leaf_eval (or aq_heads_forward + aq_legal_mask). */
+int aq_compact_priors(const float *priors, const uint32_t *mask, const uint8_t *pawn, int64_t B, int32_t *offsets,
+                      float *compact, void *stream);
+
+/* aq_leaf_eval_host with predict()-shaped output: H2D states, kernels, then only the legal actions' probabilities
+ * travel back (4 bytes per legal action instead of 836 per board; the dense path is PCIe-bound).
+ *   priors_host  [priors_capacity] f32 : ragged priors, board b at [offsets_host[b], offsets_host[b+1]);
+ *                                        B*136 floats always suffice; AQ_ERR_ARG if the capacity is too small
+ *   offsets_host [B+1] int32, value_host [B], mask_host [B,8] / pawn_host [B,8] (may be NULL)
+ * host_ctx is required (worker streams and events).  The call synchronises: results are on the host on return.
+ * dev_ws: aq_leaf_eval_host_compact_ws_bytes(B) bytes. */
+int64_t aq_leaf_eval_host_compact_ws_bytes(int64_t B);
+int aq_leaf_eval_host_compact(const float *params, const void *prepared /* or NULL */, const AqState *states_host, int64_t B,
+                              float *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,
+                              uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision, void *host_ctx,
+                              void *stream);
 
 /* Lock-step PV-MCTS over G independent games (pv_mcts.py:20-95: Node.evaluate / next_child_node).
  * ws: device workspace of aq_mcts_ws_bytes(G, max_nodes); max_nodes >= 1 + sims * 133 never overflows.

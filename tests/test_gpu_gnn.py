@@ -412,3 +412,54 @@ def test_bf16_tensor_core_training_gradients(traj):
         p, v = net(torch.from_numpy(rows[:b]))
         (p.square().sum() + v.sum()).backward()
         assert all(torch.isfinite(q.grad).all() for q in net.parameters())
+
+
+def test_compact_priors_and_host_evaluator_match_predict_order(traj):
+    """predict()-shaped ragged output: board b's slice equals the dense priors gathered in legal_actions() order
+    (bit-exact: it is a permutation of the same floats), through the device API and through HostLeafEvaluator
+    (1 chunk at B < 4096, 2 chunks above), against the reference's ordered action lists in the golden file."""
+    from alphaquoridorgnn_b200.pv_network_gnn import HostLeafEvaluator
+    torch.manual_seed(0)
+    net = GNNNetwork().cuda().eval()
+    L = _lib.load()
+    for B in (0, 1, 777, 9000):
+        sel = np.linspace(0, len(traj["rows"]) - 1, B).astype(int) if B else np.zeros(0, int)
+        rows, plies = traj["rows"][sel], traj["plies"][sel]
+        packed = gl.pack_rows(rows, plies)
+        out = net.predict_batch(packed)
+        offsets = torch.empty((B + 1,), dtype=torch.int32, device="cuda")
+        compact = torch.full((max(B, 1) * 136,), -1.0, dtype=torch.float32, device="cuda")
+        _lib.check(L.aq_compact_priors(_lib.ptr(out["priors"]), _lib.ptr(out["mask"]), _lib.ptr(out["pawn"]), B, _lib.ptr(offsets),
+                                       _lib.ptr(compact), _lib.stream_ptr()), "aq_compact_priors")
+        ref = qo.legal_actions_batch(rows, plies)
+        want_off = np.concatenate([[0], np.cumsum(ref["n"].astype(np.int64))]).astype(np.int32)
+        assert np.array_equal(offsets.cpu().numpy(), want_off)
+        dense = out["priors"].cpu().numpy()
+        want = np.concatenate([dense[b, ref["actions"][b, :ref["n"][b]]] for b in range(B)]) if B else np.zeros(0, np.float32)
+        assert np.array_equal(compact.cpu().numpy()[:len(want)], want)
+        ev = HostLeafEvaluator(net, max(B, 1))
+        ev.states[:B] = torch.from_numpy(gl.pack_rows_host(rows, plies))
+        for _ in range(2):  # second call reuses the buffers
+            ev.priors.fill_(-1.0)
+            res = ev.evaluate(B)
+            assert np.array_equal(res["offsets"], want_off)
+            assert np.array_equal(res["priors"], want)
+            assert np.array_equal(res["value"], out["value"].cpu().numpy())
+            assert np.array_equal(res["mask"], out["mask"].cpu().numpy()) and np.array_equal(res["pawn"], out["pawn"].cpu().numpy())
+        assert ev.d2h_bytes(res) == 4 * len(want) + 48 * B
+        ev.close()
+    # the dense flavour of the same class
+    ev = HostLeafEvaluator(net, 777, dense=True)
+    sel = np.linspace(0, len(traj["rows"]) - 1, 777).astype(int)
+    ev.states[:] = torch.from_numpy(gl.pack_rows_host(traj["rows"][sel], traj["plies"][sel]))
+    res = ev.evaluate()
+    assert np.array_equal(res["priors"], net.predict_batch(gl.pack_rows(traj["rows"][sel], traj["plies"][sel]))["priors"].cpu().numpy())
+    # predict(state) of one State = its slice
+    i = int(sel[300])
+    r = traj["rows"][i]
+    s = gl.State(player=[int(r[0]), int(r[1])], enemy=[int(r[2]), int(r[3])], walls=[int(x) for x in r[4:]], plies_played=int(traj["plies"][i]))
+    p, v = net.predict(s)
+    ev2 = HostLeafEvaluator(net, 4)
+    ev2.states[:1] = torch.from_numpy(gl.pack_rows_host(r[None], traj["plies"][i:i + 1]))
+    res = ev2.evaluate(1)
+    assert np.array_equal(res["priors"], p) and float(res["value"][0]) == v
