@@ -6,6 +6,8 @@
 //   atb_jobs_kernel       : all weight gradients dW = A^T B as split-row partial GEMMs (one launch)
 //   reduce_partials_kernel: grads[i] = sum over slots of partial[slot][i]
 // plus the loss gradient of train_network.py:54-55,85-89 and the Adam step.
+#include <algorithm>
+#include <cstdlib>
 #include "gnn_fp32.cuh"
 
 using namespace aq;
@@ -46,11 +48,16 @@ heads_backward_kernel(const float *__restrict__ params, const float *__restrict_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeadBwdSmem &sm = *reinterpret_cast<HeadBwdSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < kP * kHH; i += kHbThreads) sm.wp2[i] = __ldg(params + kOffWP2 + i);
-    for (int i = tid; i < kHH * kH; i += kHbThreads) {
-        sm.wp0[i] = __ldg(params + kOffWP0 + i);
-        sm.wv0[i] = __ldg(params + kOffWV0 + i);
-    }
+    // 116 KB of head weights per CTA: 16-byte loads where the parameter offset allows it, 8 loads in flight per thread
+    static_assert(kOffWP2 % 4 == 0 && kOffWP0 % 4 == 0 && (kP * kHH) % 4 == 0, "float4 fill");
+#pragma unroll 8
+    for (int i = tid; i < kP * kHH / 4; i += kHbThreads)
+        reinterpret_cast<float4 *>(sm.wp2)[i] = __ldg(reinterpret_cast<const float4 *>(params + kOffWP2) + i);
+#pragma unroll 8
+    for (int i = tid; i < kHH * kH / 4; i += kHbThreads)
+        reinterpret_cast<float4 *>(sm.wp0)[i] = __ldg(reinterpret_cast<const float4 *>(params + kOffWP0) + i);
+#pragma unroll 8
+    for (int i = tid; i < kHH * kH; i += kHbThreads) sm.wv0[i] = __ldg(params + kOffWV0 + i);
     if (tid < kHH) sm.wv2[tid] = __ldg(params + kOffWV2 + tid);
     __syncthreads();
     const SavedLayout L{B};
@@ -217,14 +224,18 @@ gcn_backward_kernel(const float *__restrict__ params, const float *__restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// weight gradients: out[m][n] = sum_r A[r][m] * Bm[r][n], rows split over kSlots chunks.
-// One launch for all jobs: grid = (kSlots, kMaxMTiles, njobs).
+// weight gradients: out[m][n] = sum_r A[r][m] * Bm[r][n], rows split over J.nslots chunks (slot s of the partial buffer).
+// One launch for all jobs: grid = (max nslots, kMaxMTiles, njobs).  The node-level jobs of the fp32 path (R = 81 B rows)
+// use all kSlots chunks; the head jobs (R = B rows) use one chunk per 64 boards -- every chunk writes a full [M][N] tile
+// that reduce_partials_kernel reads back, so chunks that would hold a handful of rows are pure overhead.
 // ------------------------------------------------------------------------------------------
 struct AtbJob {
     const float *A; int lda; int M;
     const float *Bm; int ldb; int N;  // Bm == nullptr: implicit ones, N = 1 (column sums of A)
     int64_t R;
     int out_off;                      // offset inside a partial slot, row-major [M][N]
+    int nslots;                       // row chunks = partial slots this job fills
+    int bias_off;                     // >= 0: also write the column sums of A (the bias gradient of the same layer) there
 };
 constexpr int kMaxJobs = 12;
 struct AtbJobs { AtbJob job[kMaxJobs]; int n; };
@@ -234,33 +245,55 @@ __global__ void __launch_bounds__(256)
 atb_jobs_kernel(const AtbJobs jobs, float *__restrict__ partial) {
     const AtbJob J = jobs.job[blockIdx.z];
     const int m0 = blockIdx.y * kAtbMT;
-    if (m0 >= J.M) return;
+    if (m0 >= J.M || (int)blockIdx.x >= J.nslots) return;
     __shared__ __align__(16) float As[kAtbKT][kAtbMT];
     __shared__ __align__(16) float Bs[kAtbKT][kH];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // tx -> 8 columns, ty -> 4 rows of the tile
-    const int64_t per = (J.R + kSlots - 1) / kSlots;
+    const int64_t per = (J.R + J.nslots - 1) / J.nslots;
     const int64_t r_begin = (int64_t)blockIdx.x * per;
     const int64_t r_end = r_begin + per < J.R ? r_begin + per : J.R;
     float acc[4][8];
+    float bias_acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     for (int64_t r0 = r_begin; r0 < r_end; r0 += kAtbKT) {
-        __syncthreads();
-        for (int i = tid; i < kAtbKT * kAtbMT; i += 256) {
-            const int k = i / kAtbMT, m = i % kAtbMT;
+        // all global loads of the tile are issued before the first use (24 independent loads per thread in flight; a load
+        // per loop iteration with its own bounds test serialised their latencies: 50 us for 0.2 GFLOP)
+        float av_[kAtbKT * kAtbMT / 256], bv_[kAtbKT * kH / 256];
+#pragma unroll
+        for (int j = 0; j < kAtbKT * kAtbMT / 256; ++j) {
+            const int i = tid + 256 * j, k = i / kAtbMT, m = i % kAtbMT;
             const int64_t r = r0 + k;
-            As[k][m] = (r < r_end && m0 + m < J.M) ? __ldg(J.A + r * J.lda + m0 + m) : 0.f;
+            av_[j] = (r < r_end && m0 + m < J.M) ? __ldg(J.A + r * J.lda + m0 + m) : 0.f;
         }
-        for (int i = tid; i < kAtbKT * kH; i += 256) {
-            const int k = i / kH, n = i % kH;
+#pragma unroll
+        for (int j = 0; j < kAtbKT * kH / 256; ++j) {
+            const int i = tid + 256 * j, k = i / kH, n = i % kH;
             const int64_t r = r0 + k;
             float v = 0.f;
             if (r < r_end && n < J.N) v = J.Bm ? __ldg(J.Bm + r * J.ldb + n) : 1.f;
-            Bs[k][n] = v;
+            bv_[j] = v;
         }
         __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kAtbKT * kAtbMT / 256; ++j) {
+            const int i = tid + 256 * j;
+            As[i / kAtbMT][i % kAtbMT] = av_[j];
+        }
+#pragma unroll
+        for (int j = 0; j < kAtbKT * kH / 256; ++j) {
+            const int i = tid + 256 * j;
+            Bs[i / kH][i % kH] = bv_[j];
+        }
+        __syncthreads();
+        if (J.bias_off >= 0 && tid < kAtbMT) {  // bias gradient = column sums of A: two warps, one column each
+            float t = 0.f;
+#pragma unroll
+            for (int k = 0; k < kAtbKT; ++k) t += As[k][tid];
+            bias_acc += t;
+        }
 #pragma unroll 8
         for (int k = 0; k < kAtbKT; ++k) {
             const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
@@ -274,6 +307,7 @@ atb_jobs_kernel(const AtbJobs jobs, float *__restrict__ partial) {
                 for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
     }
+    if (J.bias_off >= 0 && tid < kAtbMT && m0 + tid < J.M) partial[(int64_t)blockIdx.x * kNumParams + J.bias_off + m0 + tid] = bias_acc;
     float *slot = partial + (int64_t)blockIdx.x * kNumParams + J.out_off;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -287,14 +321,35 @@ atb_jobs_kernel(const AtbJobs jobs, float *__restrict__ partial) {
     }
 }
 
-__global__ void reduce_partials_kernel(const float *__restrict__ partial, float *__restrict__ grads) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= kNumParams) return;
-    float s = 0.f;
+// grads[i] = sum over the slots that hold parameter i (GCN ranges: kSlots; head ranges, i >= kOffWP0: head_slots).
+// block = 128 parameter pairs x 4 slot groups: group g adds slots g, g+4, g+8, ... in that order and the four group sums are
+// combined as (g0 + g1) + (g2 + g3) -- a fixed order, so the result is deterministic -- with 4 x 4 independent 8-byte loads
+// in flight per thread (the slot stride, 64082 floats, is 8-byte but not 16-byte aligned).
+constexpr int kRedPairs = 128;
+__global__ void __launch_bounds__(kRedPairs * 4)
+reduce_partials_kernel(const float *__restrict__ partial, float *__restrict__ grads, int head_slots) {
+    __shared__ float2 part[4][kRedPairs];
+    const int tx = threadIdx.x & (kRedPairs - 1), g = threadIdx.x / kRedPairs;
+    const int i = 2 * (blockIdx.x * kRedPairs + tx);  // kNumParams is even
+    float2 s = make_float2(0.f, 0.f);
+    if (i < kNumParams) {
+        // a pair never straddles the GCN / head boundary (kOffWP0 is even)
+        const int n = i >= kOffWP0 ? head_slots : kSlots;
+        const float *src = partial + i;
 #pragma unroll 4
-    for (int k = 0; k < kSlots; ++k) s += partial[(int64_t)k * kNumParams + i];  // fixed order: deterministic
-    grads[i] = s;
+        for (int k = g; k < n; k += 4) {
+            const float2 v = __ldg(reinterpret_cast<const float2 *>(src + (int64_t)k * kNumParams));
+            s.x += v.x; s.y += v.y;
+        }
+    }
+    part[g][tx] = s;
+    __syncthreads();
+    if (g == 0 && i < kNumParams) {
+        const float2 a = part[0][tx], b = part[1][tx], c = part[2][tx], d = part[3][tx];
+        *reinterpret_cast<float2 *>(grads + i) = make_float2((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y));
+    }
 }
+static_assert(kNumParams % 2 == 0 && kOffWP0 % 2 == 0, "reduce_partials_kernel works on parameter pairs");
 
 // ------------------------------------------------------------------------------------------
 // loss gradient (train_network.py:54-55,85-89) and Adam (train_network.py:56,94)
@@ -349,9 +404,22 @@ __global__ void loss_grad_kernel(const float *__restrict__ policy, const float *
             dvalue[b] = 2.f * dv * inv_total;
         }
     }
-    if (lane == 0 && loss) {  // monitoring scalars only; gradients above do not depend on them
-        atomicAdd(loss + 0, lp * inv_total);
-        atomicAdd(loss + 1, lv * inv_total);
+    // monitoring scalars only; gradients above do not depend on them.  One pair of atomics per CTA: a pair per warp
+    // (4,096 warps on two addresses) serialised in L2 and cost 12 of the kernel's 16 us at B = 4096
+    __shared__ float red[2][32];
+    if (lane == 0) { red[0][warp] = lp; red[1][warp] = lv; }
+    __syncthreads();
+    if (warp == 0 && loss) {
+        float a = lane < nwarps ? red[0][lane] : 0.f, c = lane < nwarps ? red[1][lane] : 0.f;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, d);
+            c += __shfl_xor_sync(0xffffffffu, c, d);
+        }
+        if (lane == 0) {
+            atomicAdd(loss + 0, a * inv_total);
+            atomicAdd(loss + 1, c * inv_total);
+        }
     }
 }
 
@@ -408,8 +476,11 @@ extern "C" int aq_gnn_backward(const float *params, const float *saved, const fl
 
     AtbJobs jobs;
     int nj = 0;
-    auto add = [&](const float *A, int lda, int M, const float *Bm, int ldb, int N, int64_t R, int off) {
-        jobs.job[nj++] = AtbJob{A, lda, M, Bm, ldb, N, R, off};
+    // head jobs: one row chunk per 64 boards (at most kSlots); node-level jobs: kSlots chunks
+    static const int chunk_rows = getenv("AQ_HEAD_CHUNK_ROWS") ? atoi(getenv("AQ_HEAD_CHUNK_ROWS")) : 64;  // env: experiments only
+    const int head_slots = (int)std::min<int64_t>(kSlots, (B + chunk_rows - 1) / chunk_rows);
+    auto add = [&](const float *A, int lda, int M, const float *Bm, int ldb, int N, int64_t R, int off, int bias_off = -1) {
+        jobs.job[nj++] = AtbJob{A, lda, M, Bm, ldb, N, R, off, R == B ? head_slots : kSlots, bias_off};
     };
     const int64_t RN = B * kV;
     if (precision != 1) {
@@ -417,18 +488,15 @@ extern "C" int aq_gnn_backward(const float *params, const float *saved, const fl
         add(workspace + W.dz2(), kH, kH, saved + L.x(0), kH, kH, RN, kOffW2);     // dW2 = dZ2^T X1
         add(workspace + W.dz3(), kH, kH, saved + L.x(1), kH, kH, RN, kOffW3);     // dW3 = dZ3^T X2
     }
-    add(workspace + W.dhp(), kHH, kHH, saved + L.pooled(), kH, kH, B, kOffWP0);
-    add(workspace + W.dhp(), kHH, kHH, nullptr, 0, 1, B, kOffBP0);
-    add(workspace + W.dz(), kP, kP, saved + L.hp(), kHH, kHH, B, kOffWP2);
-    add(workspace + W.dz(), kP, kP, nullptr, 0, 1, B, kOffBP2);
-    add(workspace + W.dhv(), kHH, kHH, saved + L.pooled(), kH, kH, B, kOffWV0);
-    add(workspace + W.dhv(), kHH, kHH, nullptr, 0, 1, B, kOffBV0);
-    add(workspace + W.du(), 1, 1, saved + L.hv(), kHH, kHH, B, kOffWV2);
-    add(workspace + W.du(), 1, 1, nullptr, 0, 1, B, kOffBV2);
+    // each head layer's bias gradient (column sums of the same A) rides on its weight job
+    add(workspace + W.dhp(), kHH, kHH, saved + L.pooled(), kH, kH, B, kOffWP0, kOffBP0);
+    add(workspace + W.dz(), kP, kP, saved + L.hp(), kHH, kHH, B, kOffWP2, kOffBP2);
+    add(workspace + W.dhv(), kHH, kHH, saved + L.pooled(), kH, kH, B, kOffWV0, kOffBV0);
+    add(workspace + W.du(), 1, 1, saved + L.hv(), kHH, kHH, B, kOffWV2, kOffBV2);
     jobs.n = nj;
-    atb_jobs_kernel<<<dim3(kSlots, kMaxMTiles, nj), 256, 0, st>>>(jobs, workspace + W.partial());
+    atb_jobs_kernel<<<dim3(precision != 1 ? kSlots : head_slots, kMaxMTiles, nj), 256, 0, st>>>(jobs, workspace + W.partial());
     if ((rc = aq_check_launch("atb_jobs_kernel"))) return rc;
-    reduce_partials_kernel<<<(kNumParams + 255) / 256, 256, 0, st>>>(workspace + W.partial(), grads);
+    reduce_partials_kernel<<<(kNumParams / 2 + kRedPairs - 1) / kRedPairs, kRedPairs * 4, 0, st>>>(workspace + W.partial(), grads, head_slots);
     return aq_check_launch("reduce_partials_kernel");
 }
 
