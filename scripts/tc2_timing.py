@@ -7,7 +7,7 @@ from alphaquoridorgnn_b200 import _lib, positions
 from alphaquoridorgnn_b200.pv_network_gnn import GNNNetwork
 B = 16384
 net = GNNNetwork().cuda().eval(); net.precision = "bf16"
-pos = positions.random_positions(B, seed=1, games=8192)
+_, (pos,) = positions.mixed_batches(1, B, seed=1)
 L = ctypes.CDLL(_lib.LIB_PATH)
 out = (ctypes.c_longlong * 16)()
 net.predict_batch(pos); torch.cuda.synchronize()

@@ -19,3 +19,18 @@ def test_alternate_kernel_versions_within_tolerance(env):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, **env))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert " passed" in out.stdout and "failed" not in out.stdout, out.stdout[-1000:]
+
+
+def test_tmem_resident_aggregation_operand_variant_within_tolerance():
+    """gnn_tc2.cu built with -DTC2_AGG_TMEM=1 (Z^T as a tensor-memory A operand, 3 boards in flight; measured slower, kept as
+    a documented alternative) passes the same bf16 tolerance tests."""
+    lib = os.path.join(ROOT, "alphaquoridorgnn_b200", "variants", "libaqgnn_agg1.so")
+    src = os.path.join(ROOT, "alphaquoridorgnn_b200", "csrc", "gnn_tc2.cu")
+    if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(src):
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "scripts", "build_variant.py"), "agg1", "gnn_tc2.cu", "-DTC2_AGG_TMEM=1"],
+                              cwd=ROOT, timeout=900)
+    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_gnn.py"), "-m", "gpu", "-x", "-q", "-k",
+           "bf16_tensor_core or prepared_inference or empty_and_tiny"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, AQ_LIB_PATH=lib))
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout and "failed" not in out.stdout, out.stdout[-1000:]
