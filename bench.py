@@ -381,7 +381,8 @@ def run_ours(args, rank, world, local_rank):
                        "batch_per_gpu": B, "precision": args.precision, "parallelism": f"independent leaf batches x{world}",
                        "l2": "flushed before every timed launch (256 MiB write, outside the per-launch CUDA events)"},
             "roofline": roofline, "kernels": kinfo, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": 4 * K,  # legal_prepare + legal_search + trunk + heads per step (plus one 4-byte memset) "clocks": clocks, "extra": extra,
+            "gpu_launches": 4 * K,  # legal_prepare + legal_search + trunk + heads per step (plus one 4-byte memset)
+            "clocks": clocks, "extra": extra,
         }
         print(json.dumps(line), flush=True)
 
