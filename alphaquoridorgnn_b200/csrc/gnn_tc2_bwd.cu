@@ -124,13 +124,19 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
         for (int i = tid; i < kOffWP0; i += kGroupThreads) slot[i] = 0.f;
         return;
     }
-    // W_l^T tiles: element (row k, col n) = W_l[n][k]
-    for (int i = tid; i < 2 * kH * kH; i += kGroupThreads) {
-        const int which = i >> 14, e = i & 16383;
-        const int n = e >> 7, k = e & 127;  // coalesced along k
-        const float w = __ldg(params + (which ? kOffW3 : kOffW2) + e);
+    // W_l^T tiles: element (row k, col n) = W_l[n][k].  Thread t converts 8 consecutive k of one row n per step (two 16-byte loads,
+    // 16 steps in flight) and scatters them into 8 tile rows; a scalar load per iteration serialised 256 L2 round trips per thread.
+#pragma unroll 4
+    for (int i = tid; i < 2 * kH * kH / 8; i += kGroupThreads) {
+        const int which = i >> 11, e = i & 2047;
+        const int n = e >> 4, k0 = (e & 15) * 8;  // coalesced along k
+        const float4 lo = __ldg(reinterpret_cast<const float4 *>(params + (which ? kOffW3 : kOffW2) + n * kH + k0));
+        const float4 hi = __ldg(reinterpret_cast<const float4 *>(params + (which ? kOffW3 : kOffW2) + n * kH + k0) + 1);
+        const float w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
         unsigned char *tile = which ? sm.w3t : sm.w2t;
-        *reinterpret_cast<unsigned short *>(tile + chunk_off128(k, n >> 3, kRowBlock) + (n & 7) * 2) = bf16_bits(w);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<unsigned short *>(tile + chunk_off128(k0 + j, n >> 3, kRowBlock) + (n & 7) * 2) = bf16_bits(w[j]);
     }
     for (int c = tid; c < (int)(2 * kAdjBlock / 16); c += kGroupThreads)  // adjacency tile starts as zero; only stencil positions change
         reinterpret_cast<uint4 *>(sm.adj)[c] = make_uint4(0u, 0u, 0u, 0u);
@@ -387,15 +393,25 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
     wait_dw();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     {
+        // dW2 / dW3 rows leave through a per-warp transposing stage (the dZ tile is free now) so that every global store is 32 consecutive
+        // floats of one row; a thread storing its own 32 columns touched 32 sectors per instruction
         float v[32];
+        float *stage = reinterpret_cast<float *>(sm.fm) + (tid >> 5) * (32 * 33);
+        const int lane = tid & 31, wrow = (tid >> 5) * 32;
+        __syncthreads();  // every thread is past its last read of the tile
 #pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
-            tmem_ld32(lane_base + kColW2 + cb * 32, v);
+        for (int m = 0; m < 2; ++m) {
+#pragma unroll 1
+            for (int cb = 0; cb < 4; ++cb) {
+                tmem_ld32(lane_base + (m ? kColW3 : kColW2) + cb * 32, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) slot[kOffW2 + tid * kH + cb * 32 + i] = v[i];
-            tmem_ld32(lane_base + kColW3 + cb * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) slot[kOffW3 + tid * kH + cb * 32 + i] = v[i];
+                for (int i = 0; i < 32; ++i) stage[lane * 33 + i] = v[i];
+                __syncwarp();
+                float *dst = slot + (m ? kOffW3 : kOffW2) + wrow * kH + cb * 32 + lane;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) dst[r * kH] = stage[r * 33 + lane];
+                __syncwarp();
+            }
         }
         tmem_ld32(lane_base + kColW1, v);  // 16 columns used: [hi part (6) | lo part (6) | bias_hi | bias_lo | 0 | 0]
 #pragma unroll

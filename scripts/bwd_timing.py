@@ -9,7 +9,7 @@ from alphaquoridorgnn_b200.pv_network_gnn import GNNNetwork
 TB = 4096
 L = _lib.load(); P = _lib.ptr
 net = GNNNetwork().cuda(); flat = net.flat_parameters().clone()
-tb = positions.random_positions(TB, seed=3, games=512)
+_, (tb,) = positions.mixed_batches(1, TB, seed=3)
 saved = torch.empty((L.aq_gnn_saved_floats(TB),), device="cuda"); bws = torch.empty((L.aq_gnn_backward_ws_floats(TB),), device="cuda")
 tp = torch.empty((TB, 209), device="cuda"); tv = torch.empty((TB,), device="cuda"); dp = torch.randn_like(tp) * 1e-4; dv = torch.randn_like(tv) * 1e-4
 grads = torch.empty_like(flat); st = _lib.stream_ptr()
