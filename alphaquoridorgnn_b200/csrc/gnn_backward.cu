@@ -31,7 +31,7 @@ struct BwdWs {
 // ------------------------------------------------------------------------------------------
 // heads backward: one warp per board
 // ------------------------------------------------------------------------------------------
-constexpr int kHbThreads = 256;
+constexpr int kHbThreads = 512;  // 16 warps = 16 boards in flight per CTA (8 warps left the FMA chains of one board per scheduler exposed: 36 -> see profiles)
 struct HeadBwdSmem {
     float wp2[kP * kHH];  // [a][j]
     float wp0[kHH * kH];  // [j][k]
@@ -458,7 +458,7 @@ extern "C" int aq_gnn_backward(const float *params, const float *saved, const fl
     if (e != cudaSuccess) return aq_set_error((int)e, "heads_backward smem");
     e = cudaFuncSetAttribute(gcn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GcnBwdSmem));
     if (e != cudaSuccess) return aq_set_error((int)e, "gcn_backward smem");
-    const int64_t hb = (B + 7) / 8;
+    const int64_t hb = (B + kHbThreads / 32 - 1) / (kHbThreads / 32);
     heads_backward_kernel<<<(unsigned)(hb < kSlots ? hb : kSlots), kHbThreads, sizeof(HeadBwdSmem), st>>>(
         params, saved, dpolicy, dvalue, B, workspace);
     int rc = aq_check_launch("heads_backward_kernel");

@@ -425,9 +425,20 @@ struct AqHostKey {
     }
 };
 constexpr int kHostGraphSlots = 8;
+struct AqHostPending {  // a batch between aq_leaf_eval_host_compact_submit and _wait
+    bool active = false;
+    int64_t B = 0, per = 0, priors_capacity = 0;
+    int used = 0;
+    float *priors_host = nullptr, *d_compact = nullptr;
+    int32_t *offsets_host = nullptr;
+    cudaStream_t origin = nullptr;
+    std::chrono::steady_clock::time_point t_begin;
+    double t_front = 0;
+};
 struct AqHostCtx {
     cudaStream_t s[2];
     cudaEvent_t ready, done[2], chunk_done[8];
+    AqHostPending pending;
     AqHostKey key[kHostGraphSlots];
     cudaGraphExec_t exec[kHostGraphSlots];
     int n_graphs, next_slot;
@@ -684,15 +695,26 @@ extern "C" int64_t aq_leaf_eval_host_compact_ws_bytes(int64_t B) {
            (int64_t)align256((size_t)B * AQ_MAX_LEGAL * 4);
 }
 
-extern "C" int aq_leaf_eval_host_compact(const float *params, const void *prepared, const AqState *states_host, int64_t B,
-                                         float *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,
-                                         uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision, void *host_ctx,
-                                         void *stream) {
-    if (B < 0 || !params || !offsets_host || (B > 0 && (!states_host || !priors_host || !value_host || !dev_ws || !host_ctx)))
+// The call is split in two so that a caller can keep several batches in flight (one context and one workspace per batch):
+//   submit: fork the worker streams, enqueue every chunk's H2D, kernels and fixed-size results -- returns without waiting;
+//   wait:   as each chunk's offsets reach the host, copy exactly that many probabilities behind the previous chunk's, rebase the
+//           offsets, join and synchronise.
+// aq_leaf_eval_host_compact = submit + wait.
+extern "C" int aq_leaf_eval_host_compact_submit(const float *params, const void *prepared, const AqState *states_host, int64_t B,
+                                                float *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,
+                                                uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision, void *host_ctx,
+                                                void *stream) {
+    if (B < 0 || !params || !offsets_host || !host_ctx || (B > 0 && (!states_host || !priors_host || !value_host || !dev_ws)))
         return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host_compact");
-    if (B == 0) { offsets_host[0] = 0; return 0; }
     AqHostCtx *ctx = reinterpret_cast<AqHostCtx *>(host_ctx);
-    cudaStream_t origin = reinterpret_cast<cudaStream_t>(stream);
+    if (ctx->pending.active) return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host_compact_submit(a batch is already in flight on this context)");
+    AqHostPending &pd = ctx->pending;
+    pd = AqHostPending{};
+    pd.active = true; pd.B = B; pd.priors_host = priors_host; pd.priors_capacity = priors_capacity; pd.offsets_host = offsets_host;
+    pd.origin = reinterpret_cast<cudaStream_t>(stream);
+    pd.t_begin = std::chrono::steady_clock::now();
+    if (B == 0) return 0;
+    cudaStream_t origin = pd.origin;
     unsigned char *p = reinterpret_cast<unsigned char *>(dev_ws);
     AqState *d_states = reinterpret_cast<AqState *>(p); p += align256((size_t)B * sizeof(AqState));
     float *d_priors = reinterpret_cast<float *>(p);     p += align256((size_t)B * kP * 4);
@@ -701,55 +723,66 @@ extern "C" int aq_leaf_eval_host_compact(const float *params, const void *prepar
     uint8_t *d_pawn = reinterpret_cast<uint8_t *>(p);   p += align256((size_t)B * 8);
     unsigned char *d_chunk_ws = p;                      p += host_ws_region_bytes(B);
     int32_t *d_offsets = reinterpret_cast<int32_t *>(p); p += align256((size_t)(B + kCompactMaxChunks) * 4);
-    float *d_compact = reinterpret_cast<float *>(p);
+    pd.d_compact = reinterpret_cast<float *>(p);
 
+    // One chunk per batch by default (measured at B = 16,384: a synchronous caller gets 37.2 M evals/s with one chunk and 36.6 M
+    // with two -- the half-size kernels are less efficient by what the overlap gains -- and two batches in flight get 70.5 M
+    // against 67.4 M); AQ_HOST_CHUNKS = n splits a batch >= 4096 into n pipelined chunks.
     static const int env_chunks = getenv("AQ_HOST_CHUNKS") ? atoi(getenv("AQ_HOST_CHUNKS")) : 0;
-    static const bool trace = getenv("AQ_HOST_TRACE") != nullptr;  // host-side timestamps of the pipeline on stderr (scripts/e2e_probe.py)
-    const auto t_begin = std::chrono::steady_clock::now();
-    auto us_since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
-    double t_front = 0, t_sync[kCompactMaxChunks] = {0}, t_issue[kCompactMaxChunks] = {0};
-    int nchunk = B >= 4096 ? (env_chunks > 0 ? env_chunks : 2) : 1;
+    int nchunk = (B >= 4096 && env_chunks > 0) ? env_chunks : 1;
     if (nchunk > kCompactMaxChunks) nchunk = kCompactMaxChunks;
-    const int64_t per = ((B + nchunk - 1) / nchunk + 127) / 128 * 128;
+    const int64_t per = pd.per = ((B + nchunk - 1) / nchunk + 127) / 128 * 128;
     cudaError_t e = cudaEventRecord(ctx->ready, origin);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(ctx->s[i], ctx->ready, 0);
-    if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(fork)");
+    if (e != cudaSuccess) { pd.active = false; return aq_set_error((int)e, "aq_leaf_eval_host_compact(fork)"); }
     // front half of every chunk: H2D, kernels, the fixed-size results and the chunk's offsets (its last entry = its total)
-    int used = 0;
     for (int c = 0; c < nchunk; ++c) {
         const int64_t lo = (int64_t)c * per, n = (lo + per <= B ? per : B - lo);
         if (n <= 0) break;
-        used = c + 1;
+        pd.used = c + 1;
         cudaStream_t cs = ctx->s[c & 1];
         int32_t *d_off = d_offsets + lo + c;  // n + 1 entries per chunk
         e = cudaMemcpyAsync(d_states + lo, states_host + lo, (size_t)n * sizeof(AqState), cudaMemcpyHostToDevice, cs);
-        if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(H2D)");
-        int rc = aq_leaf_eval(params, prepared, d_states + lo, n, d_priors + lo * kP, d_value + lo, d_mask + lo * 8, d_pawn + lo * 8,
-                              reinterpret_cast<float *>(d_chunk_ws + (size_t)c * host_chunk_ws_bytes(per)), precision, cs);
-        if (rc) return rc;
-        rc = aq_compact_priors(d_priors + lo * kP, d_mask + lo * 8, d_pawn + lo * 8, n, d_off, d_compact + lo * AQ_MAX_LEGAL, cs);
-        if (rc) return rc;
-        // offsets land in offsets_host[lo + c ...] for now (chunk-local values); rebased below once the totals are known
+        int rc = e != cudaSuccess ? aq_set_error((int)e, "aq_leaf_eval_host_compact(H2D)") : 0;
+        if (!rc) rc = aq_leaf_eval(params, prepared, d_states + lo, n, d_priors + lo * kP, d_value + lo, d_mask + lo * 8, d_pawn + lo * 8,
+                                   reinterpret_cast<float *>(d_chunk_ws + (size_t)c * host_chunk_ws_bytes(per)), precision, cs);
+        if (!rc) rc = aq_compact_priors(d_priors + lo * kP, d_mask + lo * 8, d_pawn + lo * 8, n, d_off, pd.d_compact + lo * AQ_MAX_LEGAL, cs);
+        if (rc) { pd.active = false; return rc; }
+        // the chunk-local INCLUSIVE ends land in offsets_host[lo ...]; wait() rebases them once the totals are known
         e = cudaMemcpyAsync(offsets_host + lo, d_off + 1, (size_t)n * 4, cudaMemcpyDeviceToHost, cs);
         if (e == cudaSuccess) e = cudaMemcpyAsync(value_host + lo, d_value + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, cs);
         if (e == cudaSuccess && mask_host) e = cudaMemcpyAsync(mask_host + lo * 8, d_mask + lo * 8, (size_t)n * 32, cudaMemcpyDeviceToHost, cs);
         if (e == cudaSuccess && pawn_host) e = cudaMemcpyAsync(pawn_host + lo * 8, d_pawn + lo * 8, (size_t)n * 8, cudaMemcpyDeviceToHost, cs);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->chunk_done[c], cs);
-        if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(D2H)");
+        if (e != cudaSuccess) { pd.active = false; return aq_set_error((int)e, "aq_leaf_eval_host_compact(D2H)"); }
     }
-    t_front = us_since();
-    // back half: as each chunk's total reaches the host, copy exactly that many probabilities behind the previous chunk's
+    pd.t_front = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - pd.t_begin).count();
+    return 0;
+}
+
+extern "C" int aq_leaf_eval_host_compact_wait(void *host_ctx) {
+    if (!host_ctx) return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host_compact_wait");
+    AqHostCtx *ctx = reinterpret_cast<AqHostCtx *>(host_ctx);
+    AqHostPending &pd = ctx->pending;
+    if (!pd.active) return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host_compact_wait(nothing in flight)");
+    pd.active = false;
+    const int64_t B = pd.B, per = pd.per;
+    int32_t *offsets_host = pd.offsets_host;
+    if (B == 0) { offsets_host[0] = 0; return 0; }
+    static const bool trace = getenv("AQ_HOST_TRACE") != nullptr;  // host-side timestamps of the pipeline on stderr (scripts/e2e_trace.py)
+    auto us_since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - pd.t_begin).count(); };
+    double t_sync[kCompactMaxChunks] = {0}, t_issue[kCompactMaxChunks] = {0};
+    cudaError_t e = cudaSuccess;
     int64_t base = 0;
-    for (int c = 0; c < used; ++c) {
+    for (int c = 0; c < pd.used; ++c) {
         const int64_t lo = (int64_t)c * per, n = (lo + per <= B ? per : B - lo);
         e = cudaEventSynchronize(ctx->chunk_done[c]);
         if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(sync)");
         t_sync[c] = us_since();
-        // offsets_host[lo + i] currently holds the chunk-local INCLUSIVE end of board lo + i
         const int64_t total = offsets_host[lo + n - 1];
-        if (base + total > priors_capacity) return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host_compact(priors_capacity too small)");
+        if (base + total > pd.priors_capacity) return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host_compact(priors_capacity too small)");
         if (total > 0) {
-            e = cudaMemcpyAsync(priors_host + base, d_compact + lo * AQ_MAX_LEGAL, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->s[c & 1]);
+            e = cudaMemcpyAsync(pd.priors_host + base, pd.d_compact + lo * AQ_MAX_LEGAL, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->s[c & 1]);
             if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(D2H priors)");
         }
         if (base) for (int64_t i = 0; i < n; ++i) offsets_host[lo + i] += (int32_t)base;
@@ -761,14 +794,24 @@ extern "C" int aq_leaf_eval_host_compact(const float *params, const void *prepar
     offsets_host[0] = 0;
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventRecord(ctx->done[i], ctx->s[i]);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(origin, ctx->done[i], 0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(pd.origin, ctx->done[i], 0);
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(origin);
+    // only this batch's own work is waited for (the worker streams), not whatever else the caller queued on `stream`
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamSynchronize(ctx->s[i]);
     if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(join)");
     if (trace) {
-        fprintf(stderr, "[aq host trace] B=%lld chunks=%d front enqueued %.0f us;", (long long)B, used, t_front);
-        for (int c = 0; c < used; ++c) fprintf(stderr, " chunk %d: results on host %.0f, priors copy issued %.0f;", c, t_sync[c], t_issue[c]);
+        fprintf(stderr, "[aq host trace] B=%lld chunks=%d front enqueued %.0f us;", (long long)B, pd.used, pd.t_front);
+        for (int c = 0; c < pd.used; ++c) fprintf(stderr, " chunk %d: results on host %.0f, priors copy issued %.0f;", c, t_sync[c], t_issue[c]);
         fprintf(stderr, " all done %.0f us\n", us_since());
     }
     return 0;
+}
+
+extern "C" int aq_leaf_eval_host_compact(const float *params, const void *prepared, const AqState *states_host, int64_t B,
+                                         float *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,
+                                         uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision, void *host_ctx,
+                                         void *stream) {
+    const int rc = aq_leaf_eval_host_compact_submit(params, prepared, states_host, B, priors_host, priors_capacity, offsets_host, value_host,
+                                                    mask_host, pawn_host, dev_ws, precision, host_ctx, stream);
+    return rc ? rc : aq_leaf_eval_host_compact_wait(host_ctx);
 }

@@ -366,6 +366,7 @@ class HostLeafEvaluator:
             nbytes = L.aq_leaf_eval_host_compact_ws_bytes(B)
         self.ws = torch.empty((max(1, nbytes),), dtype=torch.uint8, device=self.dev)
         self._ctx = ctypes.c_void_p()
+        self._inflight = None
         _lib.check(L.aq_host_ctx_create(ctypes.byref(self._ctx)), "aq_host_ctx_create")
         self.refresh_weights()
 
@@ -392,28 +393,51 @@ class HostLeafEvaluator:
         except Exception:
             pass
 
-    def evaluate(self, B=None, states=None):
-        """Evaluates self.states[:B] (or ``states``, the caller's own host uint8[B,32] tensor -- pinned memory makes the copy
-        asynchronous); synchronous.  Returns numpy views into the pinned result buffers."""
+    def _args(self, B, states):
         src = self.states if states is None else states
         if src.is_cuda or src.dtype != torch.uint8 or not src.is_contiguous():
             raise ValueError("states must be a contiguous host uint8[B,32] tensor")
         B = (self.max_batch if states is None else states.shape[0]) if B is None else int(B)
         if not 0 <= B <= min(self.max_batch, src.shape[0]):
             raise ValueError("batch larger than max_batch")
-        L = self.L
-        p_pri, p_off, p_val, p_msk, p_pwn, p_ws, p_flat, p_prep, p_states = self._fixed
-        if states is not None:
-            p_states = _lib.ptr(src)
+        return B, (self._fixed[8] if states is None else _lib.ptr(src))
+
+    def evaluate(self, B=None, states=None):
+        """Evaluates self.states[:B] (or ``states``, the caller's own host uint8[B,32] tensor -- pinned memory makes the copy
+        asynchronous); synchronous.  Returns numpy views into the pinned result buffers."""
+        if self.dense:
+            B, p_states = self._args(B, states)
+            p_pri, _, p_val, p_msk, p_pwn, p_ws, p_flat, p_prep, _ = self._fixed
+            with torch.cuda.device(self.dev):
+                _lib.check(self.L.aq_leaf_eval_host(p_flat, p_prep, p_states, B, p_pri, p_val, p_msk, p_pwn, p_ws, self._prec, self._ctx,
+                                                    _lib.stream_ptr(self.dev)), "aq_leaf_eval_host")
+            return {"priors": self.priors[:B].numpy(), "value": self.value[:B].numpy(), "mask": self.mask[:B].numpy(),
+                    "pawn": self.pawn[:B].numpy()}
+        self.submit(B, states)
+        return self.wait()
+
+    def submit(self, B=None, states=None):
+        """First half of ``evaluate`` (ragged flavour only): enqueue the copies and kernels of this batch and return at once.
+        A host that keeps two evaluators busy alternately -- ``a.submit(); b.submit(); a.wait(); a.submit(); b.wait(); ...`` --
+        hides each batch's transfers behind the other's kernels."""
+        if self.dense:
+            raise ValueError("submit/wait exist for the ragged (predict-shaped) flavour")
+        B, p_states = self._args(B, states)
+        p_pri, p_off, p_val, p_msk, p_pwn, p_ws, p_flat, p_prep, _ = self._fixed
         with torch.cuda.device(self.dev):
-            st = _lib.stream_ptr(self.dev)
-            if self.dense:
-                _lib.check(L.aq_leaf_eval_host(p_flat, p_prep, p_states, B, p_pri, p_val, p_msk, p_pwn, p_ws, self._prec, self._ctx, st),
-                           "aq_leaf_eval_host")
-                return {"priors": self.priors[:B].numpy(), "value": self.value[:B].numpy(), "mask": self.mask[:B].numpy(),
-                        "pawn": self.pawn[:B].numpy()}
-            _lib.check(L.aq_leaf_eval_host_compact(p_flat, p_prep, p_states, B, p_pri, self.priors.numel(), p_off, p_val, p_msk, p_pwn,
-                                                   p_ws, self._prec, self._ctx, st), "aq_leaf_eval_host_compact")
+            _lib.check(self.L.aq_leaf_eval_host_compact_submit(p_flat, p_prep, p_states, B, p_pri, self.priors.numel(), p_off, p_val, p_msk,
+                                                               p_pwn, p_ws, self._prec, self._ctx, _lib.stream_ptr(self.dev)),
+                       "aq_leaf_eval_host_compact_submit")
+        self._inflight = B
+
+    def wait(self):
+        """Second half: returns when the results of the submitted batch are on the host (numpy views into the pinned buffers)."""
+        B = self._inflight
+        if B is None:
+            raise ValueError("wait() without submit()")
+        self._inflight = None
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.aq_leaf_eval_host_compact_wait(self._ctx), "aq_leaf_eval_host_compact_wait")
         off = self.offsets[:B + 1].numpy()
         return {"priors": self.priors[:int(off[B])].numpy(), "offsets": off, "value": self.value[:B].numpy(),
                 "mask": self.mask[:B].numpy(), "pawn": self.pawn[:B].numpy()}

@@ -298,13 +298,44 @@ def run_ours(args, rank, world, local_rank):
         ev.close()
         return world * B * K / float(dt.item()), int(sum(d2h) / len(d2h))
 
-    e2e_v, e2e_d2h = e2e_run(dense=False)
+    def e2e_pipelined():
+        """Two evaluators (two pools of games) alternate: while the host waits for one batch, the other batch's kernels run and
+        the first one's results cross PCIe.  Every step still moves its own states H2D and its own results D2H."""
+        evs = [HostLeafEvaluator(net, B), HostLeafEvaluator(net, B)]
+        d2h = []
+
+        def run(n):
+            evs[0].submit(B, states=hst[0])
+            for i in range(n):
+                if i + 1 < n:
+                    evs[(i + 1) & 1].submit(B, states=hst[(i + 1) % nb])
+                out = evs[i & 1].wait()
+                d2h.append(evs[i & 1].d2h_bytes(out))
+
+        run(4)
+        del d2h[:]
+        barrier()
+        t0 = time.perf_counter()
+        run(K)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        for ev in evs:
+            ev.close()
+        return world * B * K / float(dt.item()), int(sum(d2h) / len(d2h))
+
+    e2e_v, e2e_d2h = e2e_pipelined()
     e2e = {"value": e2e_v, "unit": "board-evals/s", "h2d_bytes_per_step": B * 32, "d2h_bytes_per_step": e2e_d2h,
-           "api": "HostLeafEvaluator.evaluate -> aq_leaf_eval_host_compact: predict()-shaped ragged priors (legal actions only)"}
+           "api": "HostLeafEvaluator.submit / wait -> aq_leaf_eval_host_compact_submit / _wait: predict()-shaped ragged priors (legal "
+                  "actions only) + value + legal mask + pawn list; two batches in flight (two evaluators used alternately)"}
+    sync_v, sync_d2h = e2e_run(dense=False)
     dense_v, dense_d2h = e2e_run(dense=True)
 
-    extra = {"e2e_dense_priors": {"value": dense_v, "unit": "board-evals/s", "d2h_bytes_per_step": dense_d2h,
-                                  "api": "aq_leaf_eval_host: dense priors [B,209]"}}
+    extra = {"e2e_one_batch_in_flight": {"value": sync_v, "unit": "board-evals/s", "d2h_bytes_per_step": sync_d2h,
+                                         "api": "HostLeafEvaluator.evaluate (synchronous, one caller): aq_leaf_eval_host_compact"},
+             "e2e_dense_priors": {"value": dense_v, "unit": "board-evals/s", "d2h_bytes_per_step": dense_d2h,
+                                  "api": "aq_leaf_eval_host (synchronous): dense priors [B,209]"}}
     if not args.skip_extra:
         # legal mask, BASELINE configs[1]: 1M positions resident in HBM (32 MB in, 40 MB out > L2? no: flushed)
         M = 1_000_000

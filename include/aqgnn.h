@@ -187,8 +187,17 @@ int aq_compact_priors(const float *priors, const uint32_t *mask, const uint8_t *
  *   priors_host  [priors_capacity] f32 : ragged priors, board b at [offsets_host[b], offsets_host[b+1]);
  *                                        B*136 floats always suffice; AQ_ERR_ARG if the capacity is too small
  *   offsets_host [B+1] int32, value_host [B], mask_host [B,8] / pawn_host [B,8] (may be NULL)
- * host_ctx is required (worker streams and events).  The call synchronises: results are on the host on return.
+ * host_ctx is required (worker streams and events).  The call synchronises: results are on the host on return
+ * (only this batch's own work is waited for, not other work queued on `stream`).
  * dev_ws: aq_leaf_eval_host_compact_ws_bytes(B) bytes. */
+/* The same call in two halves, so that a host can keep several batches in flight (one host_ctx + dev_ws + set of host buffers per
+ * batch, e.g. two pools of games evaluated alternately): _submit enqueues the copies and kernels and returns immediately; _wait
+ * finishes the transfer of that context's batch and returns when its results are on the host.  One batch per context at a time. */
+int aq_leaf_eval_host_compact_submit(const float *params, const void *prepared, const AqState *states_host, int64_t B,
+                                     float *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,
+                                     uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision, void *host_ctx,
+                                     void *stream);
+int aq_leaf_eval_host_compact_wait(void *host_ctx);
 int64_t aq_leaf_eval_host_compact_ws_bytes(int64_t B);
 int aq_leaf_eval_host_compact(const float *params, const void *prepared /* or NULL */, const AqState *states_host, int64_t B,
                               float *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,

@@ -463,3 +463,31 @@ def test_compact_priors_and_host_evaluator_match_predict_order(traj):
     ev2.states[:1] = torch.from_numpy(gl.pack_rows_host(r[None], traj["plies"][i:i + 1]))
     res = ev2.evaluate(1)
     assert np.array_equal(res["priors"], p) and float(res["value"][0]) == v
+
+
+def test_two_host_evaluators_in_flight_give_the_same_results(traj):
+    """submit / wait: two batches in flight on two evaluators return exactly what the synchronous call returns."""
+    from alphaquoridorgnn_b200.pv_network_gnn import HostLeafEvaluator
+    torch.manual_seed(0)
+    net = GNNNetwork().cuda().eval()
+    net.precision = "bf16"
+    B = 6000
+    sels = [np.linspace(k, len(traj["rows"]) - 1 - k, B).astype(int) for k in (0, 5)]
+    hosts = [torch.from_numpy(gl.pack_rows_host(traj["rows"][s], traj["plies"][s])).pin_memory() for s in sels]
+    a, b, ref = HostLeafEvaluator(net, B), HostLeafEvaluator(net, B), HostLeafEvaluator(net, B)
+    want = []
+    for h in hosts:
+        out = ref.evaluate(B, states=h)
+        want.append({k: v.copy() for k, v in out.items()})
+    with pytest.raises(ValueError):
+        a.wait()
+    for _ in range(3):
+        a.submit(B, states=hosts[0])
+        b.submit(B, states=hosts[1])
+        with pytest.raises(Exception):
+            a.submit(B, states=hosts[0])  # one batch per evaluator at a time
+        ra = a.wait()
+        rb = b.wait()
+        for got, w in ((ra, want[0]), (rb, want[1])):
+            for k in ("offsets", "priors", "value", "mask", "pawn"):
+                assert np.array_equal(got[k], w[k]), k
