@@ -70,12 +70,13 @@ mcts_select_kernel(MctsGame *games, const MctsNode *__restrict__ nodes_all, int6
     while (true) {
         const int tf = terminal_flags(s);  // pv_mcts.py:35-42: terminal test comes first
         if (tf) { kind = (tf & 1) ? 1 : 2; break; }
-        const int first = nodes[node].first_child, nc = nodes[node].n_children;
+        const MctsNode nd = nodes[node];
+        const int first = nd.first_child, nc = nd.n_children;
         if (first < 0 || nc <= 0) { kind = 0; break; }  // `not self.child_nodes` (None or empty)
-        // t = sum(child.n)
-        int t = 0;
-        for (int c = lane; c < nc; c += 32) t += nodes[first + c].n;
-        t = __reduce_add_sync(0xffffffffu, t);
+        // t = sum(child.n) (pv_mcts.py:70-72) = n - 1: the visit that expanded this node went to no child, every later
+        // visit went to exactly one (terminal children count their visits too), so the extra pass over the children and its
+        // dependent round trip to memory are not needed
+        const int t = nd.n - 1;
         const float sq = (float)sqrt((double)t);
         float best = -INFINITY;
         int best_c = 0x7fffffff;
