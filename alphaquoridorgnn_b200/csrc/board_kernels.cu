@@ -134,10 +134,14 @@ legal_mask_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__res
 #pragma unroll
             for (int q = 0; q < 4; ++q) offs[q + 1] = offs[q] + __popcll(set[q]);
             const int total = offs[4];
+            // every lane walks the (few) set bits and writes those whose rank is its own modulo the lane count; a loop over all
+            // 64 slots per set cost 128 iterations per lane at two lanes per state
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                for (int slot = sub; slot < 64; slot += kLanesPerState)
-                    if ((set[q] >> slot) & 1) tl[offs[q] + __popcll(set[q] & ((1ull << slot) - 1))] = (uint8_t)(slot | (q << 6));
+            for (int q = 0; q < 4; ++q) {
+                u64 mm = set[q];
+                for (int r = 0; mm; ++r, mm &= mm - 1)
+                    if ((r & (kLanesPerState - 1)) == sub) tl[offs[q] + r] = (uint8_t)((__ffsll((long long)mm) - 1) | (q << 6));
+            }
             __syncwarp(gmask);
             u64 failH = 0, failV = 0;
             for (int j = sub; j < total; j += kLanesPerState) {
@@ -251,10 +255,11 @@ legal_prepare_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__
         // legal_search_kernel clears the bits of the candidates whose search fails
         if (total) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                for (int slot = sub; slot < 64; slot += 2)
-                    if ((set[q] >> slot) & 1)
-                        tasks[start + offs[q] + __popcll(set[q] & ((1ull << slot) - 1))] = ((uint32_t)b << 8) | (uint32_t)(slot | (q << 6));
+            for (int q = 0; q < 4; ++q) {  // both lanes walk the (few) set bits; lane `sub` writes the tasks of its rank parity
+                u64 mm = set[q];
+                for (int r = 0; mm; ++r, mm &= mm - 1)
+                    if ((r & 1) == sub) tasks[start + offs[q] + r] = ((uint32_t)b << 8) | (uint32_t)((__ffsll((long long)mm) - 1) | (q << 6));
+            }
         }
         legalH |= needH;
         legalV |= needV;

@@ -44,6 +44,33 @@ def peaks():
     return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI device) BEFORE any pinned host buffer is
+    allocated, so that the buffers of the host-buffer path live on the GPU's NUMA node.  Best effort: returns a description."""
+    if os.environ.get("AQ_BENCH_NUMA", "1") == "0":
+        return "off"
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bdf = out[-12:] if len(out) >= 12 else out  # nvidia-smi prints an 8-digit domain; sysfs uses 4
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"gpu {index} at {bdf}: no usable local cpus ({cpulist})"
+        os.sched_setaffinity(0, cpus)
+        return f"gpu {index} at {bdf}: bound to {len(cpus)} local cpus ({cpulist})"
+    except Exception as e:  # sysfs not visible in this container, single-socket host, ...
+        return f"unavailable ({type(e).__name__}: {e})"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -177,6 +204,7 @@ def run_ours(args, rank, world, local_rank):
     from alphaquoridorgnn_b200 import game_logic as gl
     from alphaquoridorgnn_b200.pv_network_gnn import GNNNetwork, PRECISIONS
 
+    numa = bind_to_gpu_numa(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     L = _lib.load()
@@ -410,7 +438,8 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": "leaf_eval: BASELINE configs[2], batched predict (legal mask + graph + GNN forward + legal "
                                    "renorm) on random legal 9x9 positions, random-init weights",
                        "batch_per_gpu": B, "precision": args.precision, "parallelism": f"independent leaf batches x{world}",
-                       "l2": "flushed before every timed launch (256 MiB write, outside the per-launch CUDA events)"},
+                       "l2": "flushed before every timed launch (256 MiB write, outside the per-launch CUDA events)",
+                       "host_numa": numa},
             "roofline": roofline, "kernels": kinfo, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": 4 * K,  # legal_prepare + legal_search + trunk + heads per step (plus one 4-byte memset)
             "clocks": clocks, "extra": extra,
