@@ -16,7 +16,7 @@ mask = torch.empty((1 << 20, 8), dtype=torch.int32, device="cuda")
 pawn = torch.empty((1 << 20, 8), dtype=torch.uint8, device="cuda")
 st = _lib.stream_ptr()
 lws = torch.empty((L.aq_legal_mask_ws_bytes(1 << 20),), dtype=torch.uint8, device="cuda")
-print("B, " + ", ".join(f"one-kernel lanes={l} us" for l in (2, 8, 32)) + ", two-phase (pool ws) us, two-phase (caller ws) us")
+print("B, " + ", ".join(f"one-kernel lanes={l} us" for l in (2, 8, 32)) + ", aq_legal_mask (one kernel, lanes by batch size) us, aq_legal_mask_ws (two-phase above 4096 states) us")
 for B in (256, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072, 262144, 1 << 20):
     row = []
     for lanes in (2, 8, 32, 0, -1):
