@@ -32,7 +32,7 @@ FLOP_PER_BOARD_FWDBWD = 16.9e6
 BYTES_PER_POSITION_LEGAL = 72    # 32 B packed state in + 32 B mask + 8 B ordered pawn list out
 BYTES_PER_BOARD_HEADS = 128 * 4 + 209 * 4 + 4 + 32
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu captures (profiles/*.csv)
-NCU_TRAFFIC_BYTES = {("gcn_forward_kernel", 1, 16384): 632832}  # profiles/r1_v2_kernels_ncu.csv: dram read + write of gcn_forward_tc2_kernel (outputs stay in L2)
+NCU_TRAFFIC_BYTES = {("gcn_forward_kernel", 1, 16384): 632064}  # profiles/r1_v3_kernels_ncu.csv: dram read 0.632064 MB + write 0 of gcn_forward_tc2_kernel (outputs stay in L2)
 
 
 def peaks():

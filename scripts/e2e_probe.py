@@ -61,7 +61,7 @@ def main():
         pos = positions.random_positions(B, seed=1, games=8192, device=dev)
         pri = torch.empty((B, 209), device=dev); val = torch.empty((B,), device=dev)
         msk = torch.empty((B, 8), dtype=torch.int32, device=dev); pwn = torch.empty((B, 8), dtype=torch.uint8, device=dev)
-        pooled = torch.empty((B, 128), device=dev)
+        pooled = torch.empty((L.aq_leaf_eval_ws_floats(B),), device=dev)  # leaf-eval workspace (pooled | legal-mask task list)
         for _ in range(3):
             L.aq_leaf_eval(P(flat), P(prep), P(pos), B, P(pri), P(val), P(msk), P(pwn), P(pooled), 1, st)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
