@@ -16,17 +16,22 @@
 
 using namespace aq;
 
-struct __align__(16) MctsNode {
+// A node is split into the 16 bytes the PUCT scan of a parent reads for EVERY child (w, prior, n) and the 16 bytes only the chosen
+// child needs (links, action): the selection kernel is bound by the bytes of the children it scans (133 children per level).
+struct __align__(16) MctsHot {
     double w;           // cumulative value
     float prior;        // p
     int n;              // visit count
+};
+struct __align__(16) MctsCold {
     int first_child;    // -1 = not expanded
     int parent;         // -1 = root
     short n_children;
     short action;       // action that leads here from the parent
     int pad;
 };
-static_assert(sizeof(MctsNode) == 32, "MctsNode must be 32 bytes");
+static_assert(sizeof(MctsHot) == 16 && sizeof(MctsCold) == 16, "node halves must be 16 bytes");
+constexpr size_t kNodeBytes = sizeof(MctsHot) + sizeof(MctsCold);
 
 struct __align__(16) MctsGame {
     AqState root;
@@ -40,7 +45,7 @@ static_assert(sizeof(MctsGame) == 64, "MctsGame must be 64 bytes");
 
 static inline size_t mcts_nodes_offset(int64_t G) { return ((size_t)G * sizeof(MctsGame) + 255) & ~(size_t)255; }
 
-__global__ void mcts_reset_kernel(MctsGame *games, MctsNode *nodes, const AqState *__restrict__ roots, int64_t G,
+__global__ void mcts_reset_kernel(MctsGame *games, MctsHot *hot, MctsCold *cold, const AqState *__restrict__ roots, int64_t G,
                                   int64_t max_nodes) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
@@ -52,40 +57,47 @@ __global__ void mcts_reset_kernel(MctsGame *games, MctsNode *nodes, const AqStat
     gm.overflow = 0;
     gm.pad[0] = gm.pad[1] = gm.pad[2] = gm.pad[3] = 0;
     games[g] = gm;
-    MctsNode r;
-    r.w = 0.0; r.prior = 0.f; r.n = 0; r.first_child = -1; r.parent = -1; r.n_children = 0; r.action = -1; r.pad = 0;
-    nodes[g * max_nodes] = r;  // root node: Node(state, 0), pv_mcts.py:81
+    MctsHot rh;
+    rh.w = 0.0; rh.prior = 0.f; rh.n = 0;
+    MctsCold rc;
+    rc.first_child = -1; rc.parent = -1; rc.n_children = 0; rc.action = -1; rc.pad = 0;
+    hot[g * max_nodes] = rh;  // root node: Node(state, 0), pv_mcts.py:81
+    cold[g * max_nodes] = rc;
 }
 
 // one warp per game
 __global__ void __launch_bounds__(128)
-mcts_select_kernel(MctsGame *games, const MctsNode *__restrict__ nodes_all, int64_t G, int64_t max_nodes, float c_puct,
-                   AqState *__restrict__ leaf_states, int32_t *__restrict__ leaf_kind) {
+mcts_select_kernel(MctsGame *games, const MctsHot *__restrict__ hot_all, const MctsCold *__restrict__ cold_all, int64_t G,
+                   int64_t max_nodes, float c_puct, AqState *__restrict__ leaf_states, int32_t *__restrict__ leaf_kind) {
     const int lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= G) return;
-    const MctsNode *nodes = nodes_all + g * max_nodes;
+    const MctsHot *hot = hot_all + g * max_nodes;
+    const MctsCold *cold = cold_all + g * max_nodes;
     AqState s = games[g].root;
     int node = 0, kind = 0;
+    // what the descent needs from a node: first_child, n_children (cold half) and n (hot half, known from the scan of its parent)
+    int first = cold[0].first_child, nc = cold[0].n_children, nn = hot[0].n;
     while (true) {
         const int tf = terminal_flags(s);  // pv_mcts.py:35-42: terminal test comes first
         if (tf) { kind = (tf & 1) ? 1 : 2; break; }
-        const MctsNode nd = nodes[node];
-        const int first = nd.first_child, nc = nd.n_children;
         if (first < 0 || nc <= 0) { kind = 0; break; }  // `not self.child_nodes` (None or empty)
         // t = sum(child.n) (pv_mcts.py:70-72) = n - 1: the visit that expanded this node went to no child, every later
-        // visit went to exactly one (terminal children count their visits too), so the extra pass over the children and its
-        // dependent round trip to memory are not needed
-        const int t = nd.n - 1;
+        // visit went to exactly one (terminal children count their visits too)
+        const int t = nn - 1;
         const float sq = (float)sqrt((double)t);
         float best = -INFINITY;
         int best_c = 0x7fffffff;
+        int b_n = 0;  // visit count of this lane's best child
         for (int c = lane; c < nc; c += 32) {
-            const MctsNode ch = nodes[first + c];
+            const MctsHot ch = hot[first + c];
             const float q = ch.n ? (float)(-ch.w / (double)ch.n) : 0.0f;
             const float u = __fdiv_rn(__fmul_rn(__fmul_rn(c_puct, ch.prior), sq), (float)(1 + ch.n));
             const float sc = __fadd_rn(q, u);
-            if (sc > best || (sc == best && c < best_c) || best_c == 0x7fffffff) { best = sc; best_c = c; }
+            if (sc > best || (sc == best && c < best_c) || best_c == 0x7fffffff) {
+                best = sc; best_c = c;
+                b_n = ch.n;
+            }
         }
         // warp arg-max, lowest index among equal maxima (np.argmax)
 #pragma unroll
@@ -95,8 +107,13 @@ mcts_select_kernel(MctsGame *games, const MctsNode *__restrict__ nodes_all, int6
             const bool take = (oc != 0x7fffffff) && (best_c == 0x7fffffff || ob > best || (ob == best && oc < best_c));
             if (take) { best = ob; best_c = oc; }
         }
+        const int owner = best_c & 31;  // child c is examined by lane c % 32, whose own best is then the global best
         node = first + best_c;
-        s = state_after(s, nodes[node].action);  // lazy State.next along the path
+        nn = __shfl_sync(0xffffffffu, b_n, owner);
+        const MctsCold cc = cold[node];  // one 16-byte record of the chosen child
+        first = cc.first_child;
+        nc = cc.n_children;
+        s = state_after(s, cc.action);  // lazy State.next along the path
     }
     if (lane == 0) {
         games[g].leaf = node;
@@ -107,13 +124,14 @@ mcts_select_kernel(MctsGame *games, const MctsNode *__restrict__ nodes_all, int6
 }
 
 __global__ void __launch_bounds__(128)
-mcts_expand_backup_kernel(MctsGame *games, MctsNode *nodes_all, int64_t G, int64_t max_nodes,
+mcts_expand_backup_kernel(MctsGame *games, MctsHot *hot_all, MctsCold *cold_all, int64_t G, int64_t max_nodes,
                           const float *__restrict__ priors, const float *__restrict__ values,
                           const uint32_t *__restrict__ mask, const uint8_t *__restrict__ pawn) {
     const int lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= G) return;
-    MctsNode *nodes = nodes_all + g * max_nodes;
+    MctsHot *hot = hot_all + g * max_nodes;
+    MctsCold *cold = cold_all + g * max_nodes;
     const int leaf = games[g].leaf, kind = games[g].leaf_kind;
     double value;
     if (kind == 0) {
@@ -139,13 +157,16 @@ mcts_expand_backup_kernel(MctsGame *games, MctsNode *nodes_all, int64_t G, int64
             total = 0;
         }
         if (fits) {
-            MctsNode ch;
-            ch.w = 0.0; ch.n = 0; ch.first_child = -1; ch.parent = leaf; ch.n_children = 0; ch.pad = 0;
+            MctsHot ch;
+            ch.w = 0.0; ch.n = 0;
+            MctsCold cc;
+            cc.first_child = -1; cc.parent = leaf; cc.n_children = 0; cc.pad = 0;
             if (lane < np) {
                 const int a = pawn[8 * g + 1 + lane];
-                ch.action = (short)a;
+                cc.action = (short)a;
                 ch.prior = pr[a];
-                nodes[first + lane] = ch;
+                hot[first + lane] = ch;
+                cold[first + lane] = cc;
             }
             int base = first + np;
             for (int k = 0; k < 4; ++k) {
@@ -155,16 +176,18 @@ mcts_expand_backup_kernel(MctsGame *games, MctsNode *nodes_all, int64_t G, int64
                 const bool on = (m[a >> 5] >> (a & 31)) & 1;
                 const unsigned bal = __ballot_sync(0xffffffffu, on);
                 if (on) {
-                    ch.action = (short)a;
+                    const int at = base + __popc(bal & ((1u << lane) - 1));
+                    cc.action = (short)a;
                     ch.prior = pr[a];
-                    nodes[base + __popc(bal & ((1u << lane) - 1))] = ch;
+                    hot[at] = ch;
+                    cold[at] = cc;
                 }
                 base += __popc(bal);
             }
         }
         if (lane == 0) {
-            nodes[leaf].first_child = first;
-            nodes[leaf].n_children = (short)total;
+            cold[leaf].first_child = first;
+            cold[leaf].n_children = (short)total;
             games[g].node_count = first + total;
         }
     } else {
@@ -174,27 +197,28 @@ mcts_expand_backup_kernel(MctsGame *games, MctsNode *nodes_all, int64_t G, int64
     if (lane == 0) {
         int node = leaf;
         while (node >= 0) {  // pv_mcts.py:50-51, 63-65: w += value; n += 1; parent gets -value
-            nodes[node].w += value;
-            nodes[node].n += 1;
+            hot[node].w += value;
+            hot[node].n += 1;
             value = -value;
-            node = nodes[node].parent;
+            node = cold[node].parent;
         }
     }
 }
 
-__global__ void mcts_root_counts_kernel(const MctsGame *__restrict__ games, const MctsNode *__restrict__ nodes_all,
-                                        int64_t G, int64_t max_nodes, int32_t *__restrict__ counts,
+__global__ void mcts_root_counts_kernel(const MctsGame *__restrict__ games, const MctsHot *__restrict__ hot_all,
+                                        const MctsCold *__restrict__ cold_all, int64_t G, int64_t max_nodes, int32_t *__restrict__ counts,
                                         int16_t *__restrict__ actions, int16_t *__restrict__ n_out,
                                         int32_t *__restrict__ overflow) {
     const int lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= G) return;
-    const MctsNode *nodes = nodes_all + g * max_nodes;
-    const int first = nodes[0].first_child;
-    const int nc = first < 0 ? 0 : nodes[0].n_children;
+    const MctsHot *hot = hot_all + g * max_nodes;
+    const MctsCold *cold = cold_all + g * max_nodes;
+    const int first = cold[0].first_child;
+    const int nc = first < 0 ? 0 : cold[0].n_children;
     for (int c = lane; c < AQ_MAX_LEGAL; c += 32) {
-        counts[g * AQ_MAX_LEGAL + c] = c < nc ? nodes[first + c].n : 0;
-        actions[g * AQ_MAX_LEGAL + c] = c < nc ? nodes[first + c].action : (int16_t)-1;
+        counts[g * AQ_MAX_LEGAL + c] = c < nc ? hot[first + c].n : 0;
+        actions[g * AQ_MAX_LEGAL + c] = c < nc ? cold[first + c].action : (int16_t)-1;
     }
     if (lane == 0) {
         n_out[g] = (int16_t)nc;
@@ -204,18 +228,22 @@ __global__ void mcts_root_counts_kernel(const MctsGame *__restrict__ games, cons
 
 // ------------------------------------------------------------------------------------------
 extern "C" int64_t aq_mcts_ws_bytes(int64_t G, int64_t max_nodes) {
-    return (int64_t)(mcts_nodes_offset(G) + (size_t)G * (size_t)max_nodes * sizeof(MctsNode));
+    return (int64_t)(mcts_nodes_offset(G) + (size_t)G * (size_t)max_nodes * kNodeBytes);
 }
 
 static inline MctsGame *games_of(void *ws) { return reinterpret_cast<MctsGame *>(ws); }
-static inline MctsNode *nodes_of(void *ws, int64_t G) {
-    return reinterpret_cast<MctsNode *>(reinterpret_cast<unsigned char *>(ws) + mcts_nodes_offset(G));
+// workspace: games | hot halves [G][max_nodes] | cold halves [G][max_nodes]
+static inline MctsHot *hot_of(void *ws, int64_t G) {
+    return reinterpret_cast<MctsHot *>(reinterpret_cast<unsigned char *>(ws) + mcts_nodes_offset(G));
+}
+static inline MctsCold *cold_of(void *ws, int64_t G, int64_t max_nodes) {
+    return reinterpret_cast<MctsCold *>(reinterpret_cast<unsigned char *>(ws) + mcts_nodes_offset(G) + (size_t)G * (size_t)max_nodes * sizeof(MctsHot));
 }
 
 extern "C" int aq_mcts_reset(void *ws, const AqState *roots, int64_t G, int64_t max_nodes, void *stream) {
     if (G <= 0 || max_nodes < 1 || !ws || !roots) return aq_set_error(AQ_ERR_ARG, "aq_mcts_reset");
     mcts_reset_kernel<<<(unsigned)((G + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        games_of(ws), nodes_of(ws, G), roots, G, max_nodes);
+        games_of(ws), hot_of(ws, G), cold_of(ws, G, max_nodes), roots, G, max_nodes);
     return aq_check_launch("aq_mcts_reset");
 }
 
@@ -223,7 +251,7 @@ extern "C" int aq_mcts_select(void *ws, int64_t G, int64_t max_nodes, float c_pu
                               int32_t *leaf_kind, void *stream) {
     if (G <= 0 || !ws || !leaf_states || !leaf_kind) return aq_set_error(AQ_ERR_ARG, "aq_mcts_select");
     mcts_select_kernel<<<(unsigned)((G + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        games_of(ws), nodes_of(ws, G), G, max_nodes, c_puct, leaf_states, leaf_kind);
+        games_of(ws), hot_of(ws, G), cold_of(ws, G, max_nodes), G, max_nodes, c_puct, leaf_states, leaf_kind);
     return aq_check_launch("aq_mcts_select");
 }
 
@@ -231,7 +259,7 @@ extern "C" int aq_mcts_expand_backup(void *ws, int64_t G, int64_t max_nodes, con
                                      const uint32_t *mask, const uint8_t *pawn, void *stream) {
     if (G <= 0 || !ws || !priors || !values || !mask || !pawn) return aq_set_error(AQ_ERR_ARG, "aq_mcts_expand_backup");
     mcts_expand_backup_kernel<<<(unsigned)((G + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        games_of(ws), nodes_of(ws, G), G, max_nodes, priors, values, mask, pawn);
+        games_of(ws), hot_of(ws, G), cold_of(ws, G, max_nodes), G, max_nodes, priors, values, mask, pawn);
     return aq_check_launch("aq_mcts_expand_backup");
 }
 
@@ -243,7 +271,7 @@ extern "C" int aq_mcts_root_counts(void *ws, int64_t G, int64_t max_nodes, int32
         cudaError_t e = cudaMemsetAsync(overflow, 0, sizeof(int32_t), st);
         if (e != cudaSuccess) return aq_set_error((int)e, "aq_mcts_root_counts");
     }
-    mcts_root_counts_kernel<<<(unsigned)((G + 3) / 4), 128, 0, st>>>(games_of(ws), nodes_of(ws, G), G, max_nodes, counts,
+    mcts_root_counts_kernel<<<(unsigned)((G + 3) / 4), 128, 0, st>>>(games_of(ws), hot_of(ws, G), cold_of(ws, G, max_nodes), G, max_nodes, counts,
                                                                      actions, n_children, overflow);
     return aq_check_launch("aq_mcts_root_counts");
 }
