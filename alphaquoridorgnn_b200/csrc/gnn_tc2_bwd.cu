@@ -2,7 +2,9 @@
 // As in the forward, every product is feature-major (one FEATURE per TMEM lane, the board's nodes along the columns) and the
 // aggregation of the gradient runs on the tensor cores too; no stencil arithmetic, no node-major scattered stores.
 //
-// One CTA (128 threads = 128 TMEM lanes), persistent over boards.  Per board and layer l = 3, 2:
+// One CTA per SM, persistent over boards: 256 threads = two threads per TMEM lane (feature); the thread with half index h owns node
+// columns [48 h, 48 h + 48) of every accumulator row it touches, so each epilogue phase of the (single) dependency chain is split
+// in two.  Per board and layer l = 3, 2:
 //     dY_l = (X_l > 0) * dX_l          thread f masks its lane of the dX accumulator IN PLACE (tcgen05.ld / tcgen05.st)   (dX_3 = dg / 81)
 //     dZ_l^T = dY_l^T A_hat^T          kind::tf32  A = dY_l^T, the fp32 accumulator columns read in place (A_hat is symmetric: the
 //                                                  transposed-CSR scatter of the backward is the same gather), B = A_hat (tf32, banded)
@@ -26,7 +28,7 @@ using namespace aqtc;
 #endif
 #if TC2B_TIMING
 __device__ long long g_tc2b_timing[16];
-#define TC2B_T(slot) do { if (blockIdx.x == 0 && tid == 0) { const long long t_ = clock64(); g_tc2b_timing[slot] += t_ - t_last; t_last = t_; } } while (0)
+#define TC2B_T(slot) do { if (blockIdx.x == 0 && gtid == 0) { const long long t_ = clock64(); g_tc2b_timing[slot] += t_ - t_last; t_last = t_; } } while (0)
 extern "C" int aq_debug_bwd_timing(long long *out) {
     cudaMemcpyFromSymbol(out, g_tc2b_timing, sizeof(long long) * 16);
     long long z[16] = {0};
@@ -94,6 +96,37 @@ __device__ __forceinline__ void tmem_st32_b(uint32_t taddr, const uint32_t *r) {
                    "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
                    "r"(r[30]), "r"(r[31]) : "memory");
 }
+__device__ __forceinline__ void tmem_st16_b(uint32_t taddr, const uint32_t *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                   "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+// 48 accumulator columns of this thread's lane starting at taddr: one x32 and one x16 load, one wait
+__device__ __forceinline__ void tmem_ld48_b(uint32_t taddr, float *v) {
+    uint32_t r[48];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47])
+        : "r"(taddr + 32) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 48; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st48_b(uint32_t taddr, const uint32_t *r) {
+    tmem_st32_b(taddr, r);
+    tmem_st16_b(taddr + 32, r + 32);
+}
 __device__ __forceinline__ void mbar_spin_b(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
     while (!ok)
@@ -112,22 +145,26 @@ __device__ __forceinline__ uint32_t positive_bits_b(uint4 c) {
     return m;
 }
 
-__global__ void __launch_bounds__(kGroupThreads, 1)
+constexpr int kBwdThreads = 256;
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
 gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ saved, const float *__restrict__ dg,
                         int64_t B, float *__restrict__ partial) {
     extern __shared__ unsigned char smem_raw[];
     Bwd2Smem &sm = *reinterpret_cast<Bwd2Smem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-    const int tid = threadIdx.x;  // = feature = TMEM lane
+    const int gtid = threadIdx.x;
+    const int tid = gtid & 127;   // = feature = TMEM lane
+    const int half = gtid >> 7;   // this thread's node columns: [48 half, 48 half + 48)
     float *slot = partial + (int64_t)blockIdx.x * kNumParams;
 
     if ((int64_t)blockIdx.x >= B) {  // no board for this CTA: its slot contributes zeros to the GCN ranges
-        for (int i = tid; i < kOffWP0; i += kGroupThreads) slot[i] = 0.f;
+        for (int i = gtid; i < kOffWP0; i += kBwdThreads) slot[i] = 0.f;
         return;
     }
     // W_l^T tiles: element (row k, col n) = W_l[n][k].  Thread t converts 8 consecutive k of one row n per step (two 16-byte loads,
     // 16 steps in flight) and scatters them into 8 tile rows; a scalar load per iteration serialised 256 L2 round trips per thread.
 #pragma unroll 4
-    for (int i = tid; i < 2 * kH * kH / 8; i += kGroupThreads) {
+    for (int i = gtid; i < 2 * kH * kH / 8; i += kBwdThreads) {
         const int which = i >> 11, e = i & 2047;
         const int n = e >> 4, k0 = (e & 15) * 8;  // coalesced along k
         const float4 lo = __ldg(reinterpret_cast<const float4 *>(params + (which ? kOffW3 : kOffW2) + n * kH + k0));
@@ -138,15 +175,15 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
         for (int j = 0; j < 8; ++j)
             *reinterpret_cast<unsigned short *>(tile + chunk_off128(k0 + j, n >> 3, kRowBlock) + (n & 7) * 2) = bf16_bits(w[j]);
     }
-    for (int c = tid; c < (int)(2 * kAdjBlock / 16); c += kGroupThreads)  // adjacency tile starts as zero; only stencil positions change
+    for (int c = gtid; c < (int)(2 * kAdjBlock / 16); c += kBwdThreads)  // adjacency tile starts as zero; only stencil positions change
         reinterpret_cast<uint4 *>(sm.adj)[c] = make_uint4(0u, 0u, 0u, 0u);
     const uint32_t bar = smem_u32(&sm.mbar);
-    if (tid == 0) {
+    if (gtid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&sm.mbar_w)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (tid < 32) {
+    if (gtid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
@@ -156,16 +193,17 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 
     const uint32_t tmem = sm.tmem_base;
-    const uint32_t lane_base = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+    const uint32_t lane_base = tmem + ((uint32_t)((tid >> 5) * 32) << 16);   // lane quadrant of this warp (warps w and w + 4 share one)
+    const uint32_t col0 = (uint32_t)half * 48u;                              // first of this thread's 48 columns
     const uint32_t w2t_addr = smem_u32(sm.w2t), w3t_addr = smem_u32(sm.w3t), fm_addr = smem_u32(sm.fm);
     const uint32_t adj_addr = smem_u32(sm.adj), in_addr = smem_u32(&sm.in[0]);
     const uint32_t row_off = (uint32_t)(tid >> 3) * 512u + (uint32_t)(tid & 7) * 64u;   // this thread's feature row inside a feature-major tile
     const int swz = (tid & 7) >> 1;
-    const bool issuer_warp = __shfl_sync(0xffffffffu, tid >> 5, 0) == 0;
+    const bool issuer_warp = __shfl_sync(0xffffffffu, gtid >> 5, 0) == 0;
     // static tile offsets of the 5 stencil positions of node `tid` (self, up, down, left, right); 0xFFFFFFFF = absent
     uint32_t aoff[5] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-    if (tid < kV) {
-        const int v = tid, r = v / 9, c = v - 9 * r;
+    if (gtid < kV) {
+        const int v = gtid, r = v / 9, c = v - 9 * r;
         const int blk = v >= 48 ? 1 : 0, row = v - 48 * blk, kl0 = v - 32 * blk;
         auto off = [&](int kl) -> uint32_t {
             return (uint32_t)blk * kAdjBlock + (uint32_t)(kl >> 5) * kAdjKBlock + (uint32_t)row * 128u +
@@ -190,33 +228,36 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
         };
         const unsigned char *g2 = SV.xt(saved, 1, bn), *g1 = SV.xt(saved, 0, bn), *ga = SV.a1t(saved, bn);
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
-            cp16(dst + (uint32_t)offsetof(BoardIn, xt2) + (uint32_t)(tid + kGroupThreads * j) * 16u, g2 + (tid + kGroupThreads * j) * 16);
-            cp16(dst + (uint32_t)offsetof(BoardIn, xt1) + (uint32_t)(tid + kGroupThreads * j) * 16u, g1 + (tid + kGroupThreads * j) * 16);
+        for (int j = 0; j < 6; ++j) {
+            cp16(dst + (uint32_t)offsetof(BoardIn, xt2) + (uint32_t)(gtid + kBwdThreads * j) * 16u, g2 + (gtid + kBwdThreads * j) * 16);
+            cp16(dst + (uint32_t)offsetof(BoardIn, xt1) + (uint32_t)(gtid + kBwdThreads * j) * 16u, g1 + (gtid + kBwdThreads * j) * 16);
         }
         // a1t (3072 B) and the coefficients (2592 B) are contiguous in the saved layout: 354 chunks of 16 B
-        for (int c = tid; c < (3072 + kV * 32) / 16; c += kGroupThreads)
+        for (int c = gtid; c < (3072 + kV * 32) / 16; c += kBwdThreads)
             cp16(dst + (uint32_t)offsetof(BoardIn, a1t) + (uint32_t)c * 16u, ga + c * 16);
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
-    // ReLU mask of a layer from its saved activations: this thread's feature row of the tile -> 96 bits
-    auto mask_from_tile = [&](const unsigned char *tile, uint32_t *m) {
-        m[0] = m[1] = m[2] = 0u;
+    // ReLU mask of a layer from its saved activations: this thread's 48 nodes of its feature row of the tile -> 48 bits
+    auto mask_from_tile = [&](const unsigned char *tile) -> u64 {
+        u64 m = 0ull;
 #pragma unroll
-        for (int c8 = 0; c8 < 12; ++c8) {
+        for (int j = 0; j < 6; ++j) {
+            const int c8 = 6 * half + j;
             const uint4 ch = *reinterpret_cast<const uint4 *>(tile + row_off + (uint32_t)(c8 >> 2) * kFmBlock + (uint32_t)(((c8 & 3) ^ swz) << 4));
-            m[c8 >> 2] |= positive_bits_b(ch) << (8 * (c8 & 3));
+            m |= (u64)positive_bits_b(ch) << (8 * j);
         }
+        return m;
     };
-    // this thread's 32 values -> bf16 -> node block cb of its row of sm.fm (nodes >= 81 written as zero: K padding of the dW MMAs)
-    auto store_block_bf16 = [&](int cb, const float *z) {
+    // this thread's 48 values -> bf16 -> chunks 6 half .. 6 half + 5 of its row of sm.fm (nodes >= 81 written as zero: K padding of the dW MMAs)
+    auto store_half_bf16 = [&](const float *z) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int j = 0; j < 6; ++j) {
+            const int c8 = 6 * half + j;
             uint4 v;
-            if (cb == 2 && q == 3) v = make_uint4(0u, 0u, 0u, 0u);
-            else if (cb == 2 && q == 2) v = make_uint4(pack_bf16(z[16], 0.f), 0u, 0u, 0u);
-            else v = pack8_bf16(z + q * 8);
-            *reinterpret_cast<uint4 *>(sm.fm + row_off + (uint32_t)cb * kFmBlock + (uint32_t)((q ^ swz) << 4)) = v;
+            if (c8 == 11) v = make_uint4(0u, 0u, 0u, 0u);                                  // nodes 88..95
+            else if (c8 == 10) v = make_uint4(pack_bf16(z[8 * j], 0.f), 0u, 0u, 0u);       // node 80, then padding
+            else v = pack8_bf16(z + 8 * j);
+            *reinterpret_cast<uint4 *>(sm.fm + row_off + (uint32_t)(c8 >> 2) * kFmBlock + (uint32_t)(((c8 & 3) ^ swz) << 4)) = v;
         }
     };
     auto sync_then_issue_begin = [&]() {
@@ -250,10 +291,10 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
 #endif
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x, buf ^= 1) {
         // ---- per-board inputs: wait for this board's saved tiles, start the next board's; masks, coefficients -> adjacency tile -------
-        uint32_t m3[3], m2[3], m1[3];
+        u64 m3, m2, m1;  // ReLU masks of this thread's 48 nodes
         {
             const uint4 mk = __ldg(reinterpret_cast<const uint4 *>(SV.mask3(saved, b) + tid * 16));
-            m3[0] = mk.x; m3[1] = mk.y; m3[2] = mk.z;
+            m3 = half ? ((u64)(mk.y >> 16) | ((u64)mk.z << 16)) : ((u64)mk.x | ((u64)(mk.y & 0xFFFFu) << 32));
         }
         const float dgn = dg[b * kH + tid] / (float)kV;  // d mean / d x_v
         TC2B_T(0);
@@ -264,41 +305,38 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
         const BoardIn &in = sm.in[buf];
         const uint32_t xt2_addr = in_addr + (uint32_t)buf * (uint32_t)sizeof(BoardIn), xt1_addr = xt2_addr + (uint32_t)offsetof(BoardIn, xt1);
         const uint32_t a1t_addr = xt2_addr + (uint32_t)offsetof(BoardIn, a1t);
-        if (tid < kV) {
-            const float4 c0 = *reinterpret_cast<const float4 *>(in.coef + tid * 8), c1 = *reinterpret_cast<const float4 *>(in.coef + tid * 8 + 4);
+        if (gtid < kV) {
+            const float4 c0 = *reinterpret_cast<const float4 *>(in.coef + gtid * 8), c1 = *reinterpret_cast<const float4 *>(in.coef + gtid * 8 + 4);
             const float cv[5] = {c0.x, c0.y, c0.z, c0.w, c1.x};
 #pragma unroll
             for (int k = 0; k < 5; ++k)
                 if (aoff[k] != 0xFFFFFFFFu) *reinterpret_cast<float *>(sm.adj + aoff[k]) = cv[k];
         }
         TC2B_T(1);
-        mask_from_tile(in.xt2, m2);
-        mask_from_tile(in.xt1, m1);
+        m2 = mask_from_tile(in.xt2);
+        m1 = mask_from_tile(in.xt1);
         TC2B_T(2);
 #pragma unroll 1
         for (int layer = 2; layer >= 1; --layer) {
             // ---- dY of layer (layer + 1): masked dX, written (back) into this thread's lane of the dX accumulator ----------------
             {
                 float bsum = 0.f;
+                uint32_t r[48];
+                if (layer == 2) {
 #pragma unroll
-                for (int cb = 0; cb < 3; ++cb) {
-                    uint32_t r[32];
-                    if (layer == 2) {
+                    for (int i = 0; i < 48; ++i) r[i] = (m3 >> i) & 1ull ? __float_as_uint(dgn) : 0u;
+                    bsum = (float)__popcll(m3) * dgn;
+                } else {
+                    float y[48];
+                    tmem_ld48_b(lane_base + kColX + col0, y);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) r[i] = (m3[cb] >> i) & 1u ? __float_as_uint(dgn) : 0u;
-                        bsum += (float)__popc(m3[cb]) * dgn;
-                    } else {
-                        float y[32];
-                        tmem_ld32(lane_base + kColX + cb * 32, y);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float t = (m2[cb] >> i) & 1u ? y[i] : 0.f;
-                            bsum += t;
-                            r[i] = __float_as_uint(t);
-                        }
+                    for (int i = 0; i < 48; ++i) {
+                        const float t = (m2 >> i) & 1ull ? y[i] : 0.f;
+                        bsum += t;
+                        r[i] = __float_as_uint(t);
                     }
-                    tmem_st32_b(lane_base + kColX + cb * 32, r);
                 }
+                tmem_st48_b(lane_base + kColX + col0, r);
                 asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
                 if (layer == 2) db3 += bsum; else db2 += bsum;
             }
@@ -323,11 +361,10 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
             TC2B_T(4);
             // ---- dZ^T -> bf16 -> feature-major tile ----------------------------------------------------------------------------
             wait_dw();  // the previous weight-gradient MMA has read the tile
-#pragma unroll
-            for (int cb = 0; cb < 3; ++cb) {
-                float z[32];
-                tmem_ld32(lane_base + kColZ + cb * 32, z);
-                store_block_bf16(cb, z);
+            {
+                float z[48];
+                tmem_ld48_b(lane_base + kColZ + col0, z);
+                store_half_bf16(z);
             }
             TC2B_T(5);
             // ---- dX_{l}^T = W^T dZ^T (into the dX accumulator) and dW += dZ^T X ------------------------------------------------
@@ -358,17 +395,14 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
         wait_dw();  // dW2 has read the tile
         {
             float bsum = 0.f;
+            float y[48];
+            tmem_ld48_b(lane_base + kColX + col0, y);
 #pragma unroll
-            for (int cb = 0; cb < 3; ++cb) {
-                float y[32];
-                tmem_ld32(lane_base + kColX + cb * 32, y);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    y[i] = (m1[cb] >> i) & 1u ? y[i] : 0.f;
-                    bsum += y[i];
-                }
-                store_block_bf16(cb, y);
+            for (int i = 0; i < 48; ++i) {
+                y[i] = (m1 >> i) & 1ull ? y[i] : 0.f;
+                bsum += y[i];
             }
+            store_half_bf16(y);
             db1 += bsum;
         }
         TC2B_T(7);
@@ -393,36 +427,40 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
     wait_dw();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     {
-        // dW2 / dW3 rows leave through a per-warp transposing stage (the dZ tile is free now) so that every global store is 32 consecutive
-        // floats of one row; a thread storing its own 32 columns touched 32 sectors per instruction
+        // dW2 (threads of half 0) / dW3 (half 1) rows leave through a per-warp transposing stage (the saved-input buffers are free now) so
+        // that every global store is 32 consecutive floats of one row; a thread storing its own 32 columns touched 32 sectors per instruction
         float v[32];
-        float *stage = reinterpret_cast<float *>(sm.fm) + (tid >> 5) * (32 * 33);
-        const int lane = tid & 31, wrow = (tid >> 5) * 32;
-        __syncthreads();  // every thread is past its last read of the tile
+        float *stage = reinterpret_cast<float *>(&sm.in[0]) + (gtid >> 5) * (32 * 33);
+        float *bred = reinterpret_cast<float *>(sm.fm);  // [3][2][128]: the two halves' bias sums
+        const int lane = gtid & 31, wrow = (tid >> 5) * 32;
+        __syncthreads();  // every thread is past its last read of the tile and of the saved inputs
+        bred[(0 * 2 + half) * 128 + tid] = db1;
+        bred[(1 * 2 + half) * 128 + tid] = db2;
+        bred[(2 * 2 + half) * 128 + tid] = db3;
 #pragma unroll 1
-        for (int m = 0; m < 2; ++m) {
-#pragma unroll 1
-            for (int cb = 0; cb < 4; ++cb) {
-                tmem_ld32(lane_base + (m ? kColW3 : kColW2) + cb * 32, v);
+        for (int cb = 0; cb < 4; ++cb) {
+            tmem_ld32(lane_base + (half ? kColW3 : kColW2) + cb * 32, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) stage[lane * 33 + i] = v[i];
-                __syncwarp();
-                float *dst = slot + (m ? kOffW3 : kOffW2) + wrow * kH + cb * 32 + lane;
+            for (int i = 0; i < 32; ++i) stage[lane * 33 + i] = v[i];
+            __syncwarp();
+            float *dst = slot + (half ? kOffW3 : kOffW2) + wrow * kH + cb * 32 + lane;
 #pragma unroll 8
-                for (int r = 0; r < 32; ++r) dst[r * kH] = stage[r * 33 + lane];
-                __syncwarp();
-            }
+            for (int r = 0; r < 32; ++r) dst[r * kH] = stage[r * 33 + lane];
+            __syncwarp();
         }
-        tmem_ld32(lane_base + kColW1, v);  // 16 columns used: [hi part (6) | lo part (6) | bias_hi | bias_lo | 0 | 0]
+        __syncthreads();
+        if (half == 0) {
+            tmem_ld32(lane_base + kColW1, v);  // 16 columns used: [hi part (6) | lo part (6) | bias_hi | bias_lo | 0 | 0]
 #pragma unroll
-        for (int f = 0; f < kF; ++f) slot[kOffW1 + tid * kF + f] = v[f] + v[kF + f];  // both halves multiply W1
-        slot[kOffB1 + tid] = db1;
-        slot[kOffB2 + tid] = db2;
-        slot[kOffB3 + tid] = db3;
+            for (int f = 0; f < kF; ++f) slot[kOffW1 + tid * kF + f] = v[f] + v[kF + f];  // both halves multiply W1
+            slot[kOffB1 + tid] = bred[0 * 128 + tid] + bred[1 * 128 + tid];
+            slot[kOffB2 + tid] = bred[2 * 128 + tid] + bred[3 * 128 + tid];
+            slot[kOffB3 + tid] = bred[4 * 128 + tid] + bred[5 * 128 + tid];
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    if (gtid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(kTmemCols) : "memory");
 }
 
 }  // namespace
@@ -432,6 +470,6 @@ int aq_gcn_backward_tc2(const float *params, float *saved, const float *dg, int6
     const size_t smem = sizeof(Bwd2Smem) + 1024;
     cudaError_t e = cudaFuncSetAttribute(gcn_backward_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return aq_set_error((int)e, "gcn_backward_tc2 smem");
-    gcn_backward_tc2_kernel<<<148, kGroupThreads, smem, st>>>(params, saved, dg, B, partial);
+    gcn_backward_tc2_kernel<<<148, kBwdThreads, smem, st>>>(params, saved, dg, B, partial);
     return aq_check_launch("gcn_backward_tc2_kernel");
 }
