@@ -286,17 +286,23 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
 
     int buf = 0;
     prefetch_board(blockIdx.x, 0);
+    uint4 mk_next = __ldg(reinterpret_cast<const uint4 *>(SV.mask3(saved, blockIdx.x) + tid * 16));
+    float dg_next = __ldg(dg + (int64_t)blockIdx.x * kH + tid);
 #if TC2B_TIMING
     long long t_last = clock64();
 #endif
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x, buf ^= 1) {
         // ---- per-board inputs: wait for this board's saved tiles, start the next board's; masks, coefficients -> adjacency tile -------
         u64 m3, m2, m1;  // ReLU masks of this thread's 48 nodes
-        {
-            const uint4 mk = __ldg(reinterpret_cast<const uint4 *>(SV.mask3(saved, b) + tid * 16));
-            m3 = half ? ((u64)(mk.y >> 16) | ((u64)mk.z << 16)) : ((u64)mk.x | ((u64)(mk.y & 0xFFFFu) << 32));
+        // mask3 and dg of this board were requested one board ahead (two dependent-free global loads whose latency, ~900 cycles, sat
+        // at the top of every board); the next board's are requested here
+        const uint4 mk = mk_next;
+        const float dgn = dg_next / (float)kV;  // d mean / d x_v
+        if (b + gridDim.x < B) {
+            mk_next = __ldg(reinterpret_cast<const uint4 *>(SV.mask3(saved, b + gridDim.x) + tid * 16));
+            dg_next = __ldg(dg + (b + gridDim.x) * kH + tid);
         }
-        const float dgn = dg[b * kH + tid] / (float)kV;  // d mean / d x_v
+        m3 = half ? ((u64)(mk.y >> 16) | ((u64)mk.z << 16)) : ((u64)mk.x | ((u64)(mk.y & 0xFFFFu) << 32));
         TC2B_T(0);
         wait_dw();         // dW1ext of the previous board has read its A1^T tile (the buffer the prefetch below overwrites)
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
