@@ -31,7 +31,7 @@ struct BwdWs {
 // ------------------------------------------------------------------------------------------
 // heads backward: one warp per board
 // ------------------------------------------------------------------------------------------
-constexpr int kHbThreads = 512;  // 16 warps = 16 boards in flight per CTA (8 warps left the FMA chains of one board per scheduler exposed: 36 -> see profiles)
+constexpr int kHbThreads = 512;  // at most 16 warps = 16 boards in flight per CTA (launched with 8 warps for small batches, where the weight fill dominates)
 struct HeadBwdSmem {
     float wp2[kP * kHH];  // [a][j]
     float wp0[kHH * kH];  // [j][k]
@@ -51,18 +51,18 @@ heads_backward_kernel(const float *__restrict__ params, const float *__restrict_
     // 116 KB of head weights per CTA: 16-byte loads where the parameter offset allows it, 8 loads in flight per thread
     static_assert(kOffWP2 % 4 == 0 && kOffWP0 % 4 == 0 && (kP * kHH) % 4 == 0, "float4 fill");
 #pragma unroll 8
-    for (int i = tid; i < kP * kHH / 4; i += kHbThreads)
+    for (int i = tid; i < kP * kHH / 4; i += (int)blockDim.x)
         reinterpret_cast<float4 *>(sm.wp2)[i] = __ldg(reinterpret_cast<const float4 *>(params + kOffWP2) + i);
 #pragma unroll 8
-    for (int i = tid; i < kHH * kH / 4; i += kHbThreads)
+    for (int i = tid; i < kHH * kH / 4; i += (int)blockDim.x)
         reinterpret_cast<float4 *>(sm.wp0)[i] = __ldg(reinterpret_cast<const float4 *>(params + kOffWP0) + i);
 #pragma unroll 8
-    for (int i = tid; i < kHH * kH; i += kHbThreads) sm.wv0[i] = __ldg(params + kOffWV0 + i);
+    for (int i = tid; i < kHH * kH; i += (int)blockDim.x) sm.wv0[i] = __ldg(params + kOffWV0 + i);
     if (tid < kHH) sm.wv2[tid] = __ldg(params + kOffWV2 + tid);
     __syncthreads();
     const SavedLayout L{B};
     const BwdWs W{B};
-    const int nwarps = kHbThreads / 32;
+    const int nwarps = (int)blockDim.x >> 5;
     for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
         __syncwarp();
         // softmax backward: dz = p * (dp - sum_j dp_j p_j)
@@ -458,8 +458,9 @@ extern "C" int aq_gnn_backward(const float *params, const float *saved, const fl
     if (e != cudaSuccess) return aq_set_error((int)e, "heads_backward smem");
     e = cudaFuncSetAttribute(gcn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GcnBwdSmem));
     if (e != cudaSuccess) return aq_set_error((int)e, "gcn_backward smem");
-    const int64_t hb = (B + kHbThreads / 32 - 1) / (kHbThreads / 32);
-    heads_backward_kernel<<<(unsigned)(hb < kSlots ? hb : kSlots), kHbThreads, sizeof(HeadBwdSmem), st>>>(
+    const int hb_threads = B <= 1184 ? 256 : kHbThreads;  // 148 CTAs x 8 boards cover 1,184 boards in one pass
+    const int64_t hb = (B + hb_threads / 32 - 1) / (hb_threads / 32);
+    heads_backward_kernel<<<(unsigned)(hb < kSlots ? hb : kSlots), hb_threads, sizeof(HeadBwdSmem), st>>>(
         params, saved, dpolicy, dvalue, B, workspace);
     int rc = aq_check_launch("heads_backward_kernel");
     if (rc) return rc;
