@@ -87,3 +87,20 @@ def test_negamax_empty_and_terminal_children():
     for depth in (0, 1, 2):
         out = agents.negamax_batch(packed, max_depth=depth)
         assert int(out["action"][0]) == 4 and int(out["value48"][0]) == 48
+
+
+def test_shortest_paths_200k_generated_positions_against_oracle():
+    """Row f4 at scale: 200,000 GPU-generated reachable positions (plies 0..~24 of 8,192 lock-step random games), both distances
+    and the float64 heuristic against the CPU oracle's queue BFS on the rotated board -- bit-exact."""
+    packed = positions.random_positions(200_000, seed=21, games=8192)
+    rows, _ = [t.cpu().numpy() for t in gl.unpack_rows(packed)]
+    out = agents.shortest_paths_batch(packed)
+    dist, heur = qo.heuristic_batch(rows)
+    assert np.array_equal(out["dist"].cpu().numpy(), dist)
+    assert np.array_equal(out["heuristic"].cpu().numpy(), heur)
+    # linearity property that needs no oracle: swapping the players' roles negates the heuristic (agents.py:43-52)
+    r2 = rows.copy()
+    r2[:, 0:2], r2[:, 2:4] = rows[:, 2:4], rows[:, 0:2]
+    r2[:, 4:] = rows[:, 4:][:, ::-1]
+    swapped = agents.heuristic_eval_batch(gl.pack_rows(r2, np.zeros(len(r2), np.int16)))
+    assert np.array_equal(swapped.cpu().numpy(), -out["heuristic"].cpu().numpy())
