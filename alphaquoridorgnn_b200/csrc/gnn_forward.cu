@@ -285,7 +285,7 @@ static int set_smem(K kernel, size_t bytes) {
 int aq_gcn_forward_tc(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, float *saved,
                       cudaStream_t st);  // gnn_tc.cu
 int aq_heads_forward_tc(const float *params, const void *prepared, const float *pooled, int64_t B, float *policy, float *value,
-                        const uint32_t *legal_mask, float *saved, cudaStream_t st);  // heads_tc.cu
+                        const uint32_t *legal_mask, float *saved, bool pdl, cudaStream_t st);  // heads_tc.cu
 int aq_train_tc_version();                                                           // gnn_tc.cu
 
 static int launch_trunk(const float *params, const void *prepared, const AqState *states, const float *x,
@@ -307,10 +307,10 @@ static int launch_trunk(const float *params, const void *prepared, const AqState
 }
 
 static int launch_heads(const float *params, const void *prepared, const float *pooled, int64_t B, float *policy,
-                        float *value, const uint32_t *legal_mask, float *saved, int precision, cudaStream_t st) {
+                        float *value, const uint32_t *legal_mask, float *saved, int precision, cudaStream_t st, bool after_trunk = false) {
     // tensor-core heads: inference, and the training forward of the version-2 pair (hidden activations etc. saved by the kernel)
     if (precision == 1 && (!saved || (aq_train_tc_version() == 2 && !legal_mask)))
-        return aq_heads_forward_tc(params, prepared, pooled, B, policy, value, legal_mask, saved, st);
+        return aq_heads_forward_tc(params, prepared, pooled, B, policy, value, legal_mask, saved, after_trunk, st);
     const int64_t hb = (B + 7) / 8;
     const unsigned hgrid = (unsigned)(hb < num_sms() ? hb : num_sms());
     int rc;
@@ -352,7 +352,7 @@ int aq_gnn_forward_impl(const float *params, const void *prepared, const AqState
     if (!pooled) return aq_set_error(AQ_ERR_ARG, "aq_gnn_forward(pooled scratch)");
     int rc = launch_trunk(params, prepared, states, x, open_mask, B, pooled, saved, precision, st);
     if (rc) return rc;
-    return launch_heads(params, prepared, pooled, B, policy, value, legal_mask, saved, precision, st);
+    return launch_heads(params, prepared, pooled, B, policy, value, legal_mask, saved, precision, st, /*after_trunk=*/true);
 }
 
 extern "C" int64_t aq_param_count(void) { return kNumParams; }

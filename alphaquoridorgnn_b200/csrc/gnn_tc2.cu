@@ -262,6 +262,9 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
     const int grp = gtid / kGroupThreads, tid = gtid % kGroupThreads;  // tid = feature = TMEM lane
     Tc2Group &gs = sm.g[grp];
 
+    // the next kernel in the stream (the heads) may be launched now: it loads its weight tiles while this grid drains and waits for
+    // this grid's completion (griddepcontrol.wait) before it reads the pooled activations
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     // ---- one-time setup ---------------------------------------------------------------------------------------
     {
         uint4 *adj = reinterpret_cast<uint4 *>(&gs.adj[0][0][0]);  // adjacency tiles start as zero; only the stencil positions change

@@ -138,19 +138,6 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
             *reinterpret_cast<uint4 *>(sm.b2 + sw128(n, j)) = pack8(f);
         }
     }
-    for (int c = tid; c < kTile * 16; c += kHtThreads) {  // A1 = pooled rows of this tile (zeros past B)
-        const int r = c >> 4, j = c & 15;
-        float f[8];
-        if (b0 + r < B) {
-            const float4 lo = __ldg(reinterpret_cast<const float4 *>(pooled + (b0 + r) * kH + j * 8));
-            const float4 hi = __ldg(reinterpret_cast<const float4 *>(pooled + (b0 + r) * kH + j * 8) + 1);
-            f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = 0.f;
-        }
-        *reinterpret_cast<uint4 *>(sm.a + sw128(r, j)) = pack8(f);
-    }
     if (tid < kHH) {
         sm.bp0[tid] = __ldg(params + kOffBP0 + tid);
         sm.bv0[tid] = __ldg(params + kOffBV0 + tid);
@@ -166,6 +153,23 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    // Programmatic dependent launch: everything above (weight tiles, biases, barrier, tensor-memory allocation) depends only on the
+    // parameters and overlaps the tail of the kernel that produces `pooled` (the trunk triggers its dependents at its start); the
+    // activations and the legal mask are read after the wait.  Without a programmatic predecessor the wait returns at once.
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    for (int c = tid; c < kTile * 16; c += kHtThreads) {  // A1 = pooled rows of this tile (zeros past B)
+        const int r = c >> 4, j = c & 15;
+        float f[8];
+        if (b0 + r < B) {
+            const float4 lo = __ldg(reinterpret_cast<const float4 *>(pooled + (b0 + r) * kH + j * 8));
+            const float4 hi = __ldg(reinterpret_cast<const float4 *>(pooled + (b0 + r) * kH + j * 8) + 1);
+            f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        }
+        *reinterpret_cast<uint4 *>(sm.a + sw128(r, j)) = pack8(f);
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -325,20 +329,40 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
 
 }  // namespace
 
+// launch with the programmatic-stream-serialization attribute: the grid may start while its predecessor in the stream is still
+// draining; the kernel orders itself behind the predecessor's results with griddepcontrol.wait
+template <typename Kernel, typename... Args>
+static cudaError_t launch_pdl(bool pdl, Kernel kernel, unsigned grid, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(kHtThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+// pdl: the predecessor in the stream is the trunk kernel of the same forward pass (it triggers its dependents early and does not write the
+// parameters this kernel reads before its griddepcontrol.wait); standalone calls launch normally
 int aq_heads_forward_tc(const float *params, const void *prepared_v, const float *pooled, int64_t B, float *policy,
-                        float *value, const uint32_t *legal_mask, float *saved, cudaStream_t st) {
+                        float *value, const uint32_t *legal_mask, float *saved, bool pdl, cudaStream_t st) {
     const unsigned char *prepared = reinterpret_cast<const unsigned char *>(prepared_v);
     const size_t smem = sizeof(HtSmem) + 1024;
     const unsigned grid = (unsigned)((B + kTile - 1) / kTile);
-    cudaError_t e;
+    cudaError_t e, rc_launch = cudaSuccess;
     if (legal_mask) {
         e = cudaFuncSetAttribute(heads_forward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return aq_set_error((int)e, "heads_forward_tc smem");
-        heads_forward_tc_kernel<true><<<grid, kHtThreads, smem, st>>>(params, prepared, pooled, B, policy, value, legal_mask, saved);
+        rc_launch = launch_pdl(pdl, heads_forward_tc_kernel<true>, grid, smem, st, params, prepared, pooled, B, policy, value, legal_mask, saved);
     } else {
         e = cudaFuncSetAttribute(heads_forward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return aq_set_error((int)e, "heads_forward_tc smem");
-        heads_forward_tc_kernel<false><<<grid, kHtThreads, smem, st>>>(params, prepared, pooled, B, policy, value, nullptr, saved);
+        rc_launch = launch_pdl(pdl, heads_forward_tc_kernel<false>, grid, smem, st, params, prepared, pooled, B, policy, value, (const uint32_t *)nullptr, saved);
     }
+    if (rc_launch != cudaSuccess) return aq_set_error((int)rc_launch, "heads_forward_tc_kernel(launch)");
     return aq_check_launch("heads_forward_tc_kernel");
 }
