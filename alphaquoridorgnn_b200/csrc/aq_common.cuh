@@ -14,6 +14,30 @@ typedef unsigned long long u64;
 int aq_set_error(int code, const char *what);
 int aq_check_launch(const char *what);
 
+// Programmatic dependent launch (PDL).  A kernel launched with aq_launch_pdl may start while its predecessor in the stream is still
+// draining; it must call aq_pdl_wait() before it touches anything the predecessor (or anything earlier in the stream) writes, and may
+// run a prologue that reads only long-lived inputs (parameters) before that.  A predecessor that calls aq_pdl_trigger() at its start
+// lets the dependent grid be scheduled as soon as SM resources free up; without the trigger the dependent starts when the
+// predecessor's blocks have exited, as with a normal launch.  Both device calls are no-ops for normally launched kernels.
+#ifdef __CUDACC__
+__device__ __forceinline__ void aq_pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void aq_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t aq_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#endif
+
 namespace aq {
 
 AQ_DEV u128 bit81(int sq) { return (u128)1 << sq; }

@@ -48,6 +48,7 @@ heads_backward_kernel(const float *__restrict__ params, const float *__restrict_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeadBwdSmem &sm = *reinterpret_cast<HeadBwdSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    aq_pdl_trigger();  // the trunk backward may be scheduled as SMs free up; it waits for this grid before it reads dg
     // 116 KB of head weights per CTA: 16-byte loads where the parameter offset allows it, 8 loads in flight per thread
     static_assert(kOffWP2 % 4 == 0 && kOffWP0 % 4 == 0 && (kP * kHH) % 4 == 0, "float4 fill");
 #pragma unroll 8
@@ -59,6 +60,7 @@ heads_backward_kernel(const float *__restrict__ params, const float *__restrict_
 #pragma unroll 8
     for (int i = tid; i < kHH * kH; i += (int)blockDim.x) sm.wv0[i] = __ldg(params + kOffWV0 + i);
     if (tid < kHH) sm.wv2[tid] = __ldg(params + kOffWV2 + tid);
+    aq_pdl_wait();     // launched with aq_launch_pdl: the weight fill above overlaps the tail of the loss kernel; dpolicy / dvalue are read below
     __syncthreads();
     const SavedLayout L{B};
     const BwdWs W{B};
@@ -243,6 +245,8 @@ constexpr int kAtbMT = 64, kAtbKT = 32, kMaxMTiles = 4;
 
 __global__ void __launch_bounds__(256)
 atb_jobs_kernel(const AtbJobs jobs, float *__restrict__ partial) {
+    aq_pdl_trigger();
+    aq_pdl_wait();  // everything this kernel reads was written by the backward kernels before it
     const AtbJob J = jobs.job[blockIdx.z];
     const int m0 = blockIdx.y * kAtbMT;
     if (m0 >= J.M || (int)blockIdx.x >= J.nslots) return;
@@ -329,6 +333,7 @@ constexpr int kRedPairs = 128;
 __global__ void __launch_bounds__(kRedPairs * 4)
 reduce_partials_kernel(const float *__restrict__ partial, float *__restrict__ grads, int head_slots) {
     __shared__ float2 part[4][kRedPairs];
+    aq_pdl_wait();
     const int tx = threadIdx.x & (kRedPairs - 1), g = threadIdx.x / kRedPairs;
     const int i = 2 * (blockIdx.x * kRedPairs + tx);  // kNumParams is even
     float2 s = make_float2(0.f, 0.f);
@@ -359,6 +364,7 @@ __global__ void loss_grad_kernel(const float *__restrict__ policy, const float *
                                  float inv_total, float *__restrict__ loss, float *__restrict__ dpolicy,
                                  float *__restrict__ dvalue) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    aq_pdl_trigger();  // the heads backward that usually follows can load its weights while this grid drains
     float lp = 0.f, lv = 0.f;
     for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
         // CrossEntropyLoss(input = softmax probabilities, target = probabilities):
@@ -460,8 +466,10 @@ extern "C" int aq_gnn_backward(const float *params, const float *saved, const fl
     if (e != cudaSuccess) return aq_set_error((int)e, "gcn_backward smem");
     const int hb_threads = B <= 1184 ? 256 : kHbThreads;  // 148 CTAs x 8 boards cover 1,184 boards in one pass
     const int64_t hb = (B + hb_threads / 32 - 1) / (hb_threads / 32);
-    heads_backward_kernel<<<(unsigned)(hb < kSlots ? hb : kSlots), hb_threads, sizeof(HeadBwdSmem), st>>>(
-        params, saved, dpolicy, dvalue, B, workspace);
+    // the backward kernels are chained by programmatic dependent launches: each reads only the parameters before its aq_pdl_wait()
+    e = aq_launch_pdl(heads_backward_kernel, dim3((unsigned)(hb < kSlots ? hb : kSlots)), dim3(hb_threads), sizeof(HeadBwdSmem), st,
+                      params, saved, dpolicy, dvalue, B, workspace);
+    if (e != cudaSuccess) return aq_set_error((int)e, "heads_backward_kernel(launch)");
     int rc = aq_check_launch("heads_backward_kernel");
     if (rc) return rc;
     if (precision == 1) {  // tensor-core trunk backward: fills the GCN ranges of every partial slot itself
@@ -495,9 +503,12 @@ extern "C" int aq_gnn_backward(const float *params, const float *saved, const fl
     add(workspace + W.dhv(), kHH, kHH, saved + L.pooled(), kH, kH, B, kOffWV0, kOffBV0);
     add(workspace + W.du(), 1, 1, saved + L.hv(), kHH, kHH, B, kOffWV2, kOffBV2);
     jobs.n = nj;
-    atb_jobs_kernel<<<dim3(precision != 1 ? kSlots : head_slots, kMaxMTiles, nj), 256, 0, st>>>(jobs, workspace + W.partial());
+    e = aq_launch_pdl(atb_jobs_kernel, dim3(precision != 1 ? kSlots : head_slots, kMaxMTiles, nj), dim3(256), 0, st, jobs, workspace + W.partial());
+    if (e != cudaSuccess) return aq_set_error((int)e, "atb_jobs_kernel(launch)");
     if ((rc = aq_check_launch("atb_jobs_kernel"))) return rc;
-    reduce_partials_kernel<<<(kNumParams / 2 + kRedPairs - 1) / kRedPairs, kRedPairs * 4, 0, st>>>(workspace + W.partial(), grads, head_slots);
+    e = aq_launch_pdl(reduce_partials_kernel, dim3((kNumParams / 2 + kRedPairs - 1) / kRedPairs), dim3(kRedPairs * 4), 0, st,
+                      (const float *)(workspace + W.partial()), grads, head_slots);
+    if (e != cudaSuccess) return aq_set_error((int)e, "reduce_partials_kernel(launch)");
     return aq_check_launch("reduce_partials_kernel");
 }
 

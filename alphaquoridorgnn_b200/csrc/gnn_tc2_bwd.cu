@@ -153,11 +153,13 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
     extern __shared__ unsigned char smem_raw[];
     Bwd2Smem &sm = *reinterpret_cast<Bwd2Smem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int gtid = threadIdx.x;
+    aq_pdl_trigger();             // the weight-gradient kernel behind this one may be scheduled as SMs free up
     const int tid = gtid & 127;   // = feature = TMEM lane
     const int half = gtid >> 7;   // this thread's node columns: [48 half, 48 half + 48)
     float *slot = partial + (int64_t)blockIdx.x * kNumParams;
 
     if ((int64_t)blockIdx.x >= B) {  // no board for this CTA: its slot contributes zeros to the GCN ranges
+        aq_pdl_wait();               // (the slot may still be read by work queued earlier in the stream)
         for (int i = gtid; i < kOffWP0; i += kBwdThreads) slot[i] = 0.f;
         return;
     }
@@ -285,6 +287,9 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
     };
 
     int buf = 0;
+    // launched with aq_launch_pdl: everything above (W^T tiles, zeroed adjacency, barriers, tensor-memory allocation) read only the parameters
+    // and overlapped the tail of the heads backward; the saved activations and dg are read from here on
+    aq_pdl_wait();
     prefetch_board(blockIdx.x, 0);
     uint4 mk_next = __ldg(reinterpret_cast<const uint4 *>(SV.mask3(saved, blockIdx.x) + tid * 16));
     float dg_next = __ldg(dg + (int64_t)blockIdx.x * kH + tid);
@@ -476,6 +481,7 @@ int aq_gcn_backward_tc2(const float *params, float *saved, const float *dg, int6
     const size_t smem = sizeof(Bwd2Smem) + 1024;
     cudaError_t e = cudaFuncSetAttribute(gcn_backward_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return aq_set_error((int)e, "gcn_backward_tc2 smem");
-    gcn_backward_tc2_kernel<<<148, kBwdThreads, smem, st>>>(params, saved, dg, B, partial);
+    e = aq_launch_pdl(gcn_backward_tc2_kernel, dim3(148), dim3(kBwdThreads), smem, st, params, saved, dg, B, partial);
+    if (e != cudaSuccess) return aq_set_error((int)e, "gcn_backward_tc2_kernel(launch)");
     return aq_check_launch("gcn_backward_tc2_kernel");
 }
