@@ -19,6 +19,9 @@ int aq_check_launch(const char *what);
 // run a prologue that reads only long-lived inputs (parameters) before that.  A predecessor that calls aq_pdl_trigger() at its start
 // lets the dependent grid be scheduled as soon as SM resources free up; without the trigger the dependent starts when the
 // predecessor's blocks have exited, as with a normal launch.  Both device calls are no-ops for normally launched kernels.
+// RULE: what the predecessor wrote must be read with coherent loads (__ldcg / plain loads through a non-restrict pointer) after
+// aq_pdl_wait().  A load through a `const __restrict__` pointer or __ldg() is an invariant (LDG.CONSTANT) load to the compiler and
+// gets hoisted ABOVE the wait -- seen in the SASS of legal_search_kernel, which then read the previous call's task count.
 #ifdef __CUDACC__
 __device__ __forceinline__ void aq_pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 __device__ __forceinline__ void aq_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }

@@ -96,6 +96,7 @@ legal_mask_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__res
                   uint8_t *__restrict__ pawn) {
     constexpr int kStatesPerWarp = 32 / kLanesPerState;
     __shared__ uint8_t task[kLegalWarps * kStatesPerWarp][256];
+    aq_pdl_trigger();  // a kernel launched programmatically behind this one (the GNN trunk of a leaf evaluation) may start as SMs free up
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & (kLanesPerState - 1), grp = lane / kLanesPerState;
     const unsigned gmask = kLanesPerState == 32 ? 0xffffffffu : ((1u << (kLanesPerState & 31)) - 1u) << (grp * kLanesPerState);
@@ -204,6 +205,7 @@ legal_prepare_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__
                      uint32_t *__restrict__ tasks, unsigned cap, unsigned *__restrict__ counter) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & 1, grp = lane >> 1;
+    aq_pdl_trigger();  // legal_search_kernel may be scheduled; it waits for this grid's completion before it reads the task list
     const int64_t b0 = ((int64_t)blockIdx.x * kLegalWarps + warp) * 16 + grp;
     const bool valid = b0 < B;
     const int64_t b = valid ? b0 : B - 1;  // out-of-range lanes shadow the last state and write nothing
@@ -305,11 +307,13 @@ legal_prepare_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__
 }
 
 __global__ void __launch_bounds__(128)
-legal_search_kernel(const AqState *__restrict__ states, const uint32_t *__restrict__ tasks, const unsigned *__restrict__ counter,
+legal_search_kernel(const AqState *__restrict__ states, const uint32_t *tasks, const unsigned *counter,
                     unsigned cap, uint32_t *__restrict__ mask) {
-    const unsigned n = min(*counter, cap);
+    aq_pdl_trigger();
+    aq_pdl_wait();  // launched programmatically behind legal_prepare_kernel: its task list and counter are complete from here on
+    const unsigned n = min(__ldcg(counter), cap);  // coherent loads: see the PDL rule in aq_common.cuh
     for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-        const uint32_t w = __ldg(tasks + t);
+        const uint32_t w = __ldcg(tasks + t);
         if (w == kNullTask) continue;
         const int64_t b = w >> 8;
         const int slot = w & 63, orient = ((w >> 6) & 1) + 1, opp = (w >> 7) & 1;
@@ -568,7 +572,9 @@ extern "C" int aq_legal_mask_ws(const AqState *states, int64_t B, uint32_t *mask
                                                                                                      tasks, cap, counter);
         // enough threads for the expected number of searches (2-4 per state), at most 16 CTAs of 128 per SM; grid-stride beyond
         const unsigned grid = (unsigned)std::min<int64_t>(148 * 16, std::max<int64_t>(1, (4 * n + 127) / 128));
-        legal_search_kernel<<<grid, 128, 0, S(stream)>>>(states + lo, tasks, counter, cap, mask + 8 * lo);
+        e = aq_launch_pdl(legal_search_kernel, dim3(grid), dim3(128), 0, S(stream), states + lo, (const uint32_t *)tasks, (const unsigned *)counter, cap,
+                          mask + 8 * lo);
+        if (e != cudaSuccess) return aq_set_error((int)e, "aq_legal_mask(search launch)");
         const int rc = aq_check_launch("aq_legal_mask");
         if (rc) return rc;
     }

@@ -43,7 +43,7 @@ struct HeadBwdSmem {
 
 __global__ void __launch_bounds__(kHbThreads, 1)
 heads_backward_kernel(const float *__restrict__ params, const float *__restrict__ saved,
-                      const float *__restrict__ dpolicy, const float *__restrict__ dvalue, int64_t B,
+                      const float *dpolicy, const float *dvalue, int64_t B,
                       float *__restrict__ ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeadBwdSmem &sm = *reinterpret_cast<HeadBwdSmem *>(smem_raw);
@@ -73,7 +73,7 @@ heads_backward_kernel(const float *__restrict__ params, const float *__restrict_
         for (int t = 0; t < 7; ++t) {
             const int a = lane + 32 * t;
             p[t] = a < kP ? saved[L.policy() + b * kP + a] : 0.f;
-            dp[t] = a < kP ? __ldg(dpolicy + b * kP + a) : 0.f;
+            dp[t] = a < kP ? __ldcg(dpolicy + b * kP + a) : 0.f;  // written by the loss kernel this grid may overlap: coherent load (PDL rule, aq_common.cuh)
             s = fmaf(dp[t], p[t], s);
         }
 #pragma unroll
@@ -99,7 +99,7 @@ heads_backward_kernel(const float *__restrict__ params, const float *__restrict_
         h1 = hp1 > 0.f ? h1 : 0.f;
         // value head: v = tanh(u); du = dv * (1 - v^2); dhv = du * wv2 * (hv > 0)
         const float v = saved[L.value() + b];
-        const float du = __ldg(dvalue + b) * (1.f - v * v);
+        const float du = __ldcg(dvalue + b) * (1.f - v * v);
         const float hv0 = saved[L.hv() + b * kHH + lane], hv1 = saved[L.hv() + b * kHH + lane + 32];
         const float g0 = hv0 > 0.f ? du * sm.wv2[lane] : 0.f;
         const float g1 = hv1 > 0.f ? du * sm.wv2[lane + 32] : 0.f;
@@ -270,14 +270,14 @@ atb_jobs_kernel(const AtbJobs jobs, float *__restrict__ partial) {
         for (int j = 0; j < kAtbKT * kAtbMT / 256; ++j) {
             const int i = tid + 256 * j, k = i / kAtbMT, m = i % kAtbMT;
             const int64_t r = r0 + k;
-            av_[j] = (r < r_end && m0 + m < J.M) ? __ldg(J.A + r * J.lda + m0 + m) : 0.f;
+            av_[j] = (r < r_end && m0 + m < J.M) ? __ldcg(J.A + r * J.lda + m0 + m) : 0.f;  // coherent loads: PDL rule (aq_common.cuh)
         }
 #pragma unroll
         for (int j = 0; j < kAtbKT * kH / 256; ++j) {
             const int i = tid + 256 * j, k = i / kH, n = i % kH;
             const int64_t r = r0 + k;
             float v = 0.f;
-            if (r < r_end && n < J.N) v = J.Bm ? __ldg(J.Bm + r * J.ldb + n) : 1.f;
+            if (r < r_end && n < J.N) v = J.Bm ? __ldcg(J.Bm + r * J.ldb + n) : 1.f;
             bv_[j] = v;
         }
         __syncthreads();
@@ -331,7 +331,7 @@ atb_jobs_kernel(const AtbJobs jobs, float *__restrict__ partial) {
 // in flight per thread (the slot stride, 64082 floats, is 8-byte but not 16-byte aligned).
 constexpr int kRedPairs = 128;
 __global__ void __launch_bounds__(kRedPairs * 4)
-reduce_partials_kernel(const float *__restrict__ partial, float *__restrict__ grads, int head_slots) {
+reduce_partials_kernel(const float *partial, float *__restrict__ grads, int head_slots) {
     __shared__ float2 part[4][kRedPairs];
     aq_pdl_wait();
     const int tx = threadIdx.x & (kRedPairs - 1), g = threadIdx.x / kRedPairs;
@@ -343,7 +343,7 @@ reduce_partials_kernel(const float *__restrict__ partial, float *__restrict__ gr
         const float *src = partial + i;
 #pragma unroll 4
         for (int k = g; k < n; k += 4) {
-            const float2 v = __ldg(reinterpret_cast<const float2 *>(src + (int64_t)k * kNumParams));
+            const float2 v = __ldcg(reinterpret_cast<const float2 *>(src + (int64_t)k * kNumParams));  // coherent: PDL rule
             s.x += v.x; s.y += v.y;
         }
     }

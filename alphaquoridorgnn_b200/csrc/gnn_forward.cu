@@ -283,16 +283,17 @@ static int set_smem(K kernel, size_t bytes) {
 }
 
 int aq_gcn_forward_tc(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, float *saved,
-                      cudaStream_t st);  // gnn_tc.cu
+                      cudaStream_t st, bool after_legal);  // gnn_tc.cu
 int aq_heads_forward_tc(const float *params, const void *prepared, const float *pooled, int64_t B, float *policy, float *value,
                         const uint32_t *legal_mask, float *saved, bool pdl, cudaStream_t st);  // heads_tc.cu
 int aq_train_tc_version();                                                           // gnn_tc.cu
 
 static int launch_trunk(const float *params, const void *prepared, const AqState *states, const float *x,
-                        const uint8_t *open_mask, int64_t B, float *pooled, float *saved, int precision, cudaStream_t st) {
+                        const uint8_t *open_mask, int64_t B, float *pooled, float *saved, int precision, cudaStream_t st,
+                        bool after_legal = false) {
     if (precision == 1) {
         if (!states) return aq_set_error(AQ_ERR_UNSUPPORTED, "aq_gnn_forward(bf16 path needs packed states)");
-        return aq_gcn_forward_tc(params, prepared, states, B, pooled, saved, st);
+        return aq_gcn_forward_tc(params, prepared, states, B, pooled, saved, st, after_legal);
     }
     const unsigned grid = (unsigned)(B < num_sms() ? B : num_sms());
     int rc;
@@ -345,12 +346,12 @@ extern "C" int aq_heads_forward(const float *params, const void *prepared, const
 // saved workspace the pooled section of `saved` is used.
 int aq_gnn_forward_impl(const float *params, const void *prepared, const AqState *states, const float *x,
                         const uint8_t *open_mask, int64_t B, float *policy, float *value, float *saved, float *pooled_scratch,
-                        const uint32_t *legal_mask, int precision, cudaStream_t st) {
+                        const uint32_t *legal_mask, int precision, cudaStream_t st, bool after_legal = false) {
     if (B == 0) return 0;
     const SavedLayout L{B};
     float *pooled = saved ? saved + L.pooled() : pooled_scratch;
     if (!pooled) return aq_set_error(AQ_ERR_ARG, "aq_gnn_forward(pooled scratch)");
-    int rc = launch_trunk(params, prepared, states, x, open_mask, B, pooled, saved, precision, st);
+    int rc = launch_trunk(params, prepared, states, x, open_mask, B, pooled, saved, precision, st, after_legal);
     if (rc) return rc;
     return launch_heads(params, prepared, pooled, B, policy, value, legal_mask, saved, precision, st, /*after_trunk=*/true);
 }
@@ -389,8 +390,9 @@ extern "C" int aq_leaf_eval(const float *params, const void *prepared, const AqS
     if (B == 0) return 0;
     int rc = aq_legal_mask_ws(states, B, mask, pawn, workspace + leaf_pooled_floats(B), aq_legal_mask_ws_bytes(B), stream);
     if (rc) return rc;
+    // the trunk does not read the legal mask: it is launched programmatically behind the legal-mask kernel (see aq_gcn_forward_tc2)
     return aq_gnn_forward_impl(params, prepared, states, nullptr, nullptr, B, priors, value, nullptr, workspace, mask, precision,
-                               reinterpret_cast<cudaStream_t>(stream));
+                               reinterpret_cast<cudaStream_t>(stream), /*after_legal=*/true);
 }
 
 // ---- host-buffer variant ----------------------------------------------------------------------

@@ -357,7 +357,7 @@ static int launch_tc(const float *params, const unsigned char *prepared, const A
 }
 
 int aq_gcn_forward_tc2(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, float *saved,
-                       cudaStream_t st);  // gnn_tc2.cu
+                       cudaStream_t st, bool after_legal);  // gnn_tc2.cu
 int aq_gcn_forward_tc3(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, cudaStream_t st);  // gnn_tc3.cu
 
 // Which tensor-core training pair (forward with saved activations + backward) is used at precision 1; both sides read it here.
@@ -373,7 +373,7 @@ int aq_train_tc_version() {
 
 // saved == nullptr: inference.  saved != nullptr: training forward (activations kept for aq_gnn_backward, precision 1).
 int aq_gcn_forward_tc(const float *params, const void *prepared_v, const AqState *states, int64_t B, float *pooled, float *saved,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool after_legal) {
     const unsigned char *prepared = reinterpret_cast<const unsigned char *>(prepared_v);
     static int sms = 0, groups = 0, version = 2;
     if (sms == 0) {
@@ -387,8 +387,8 @@ int aq_gcn_forward_tc(const float *params, const void *prepared_v, const AqState
         groups = env ? atoi(env) : 5;
     }
     if (!saved && version == 3) return aq_gcn_forward_tc3(params, prepared_v, states, B, pooled, st);
-    if (!saved && version == 2) return aq_gcn_forward_tc2(params, prepared_v, states, B, pooled, nullptr, st);
-    if (saved && aq_train_tc_version() == 2) return aq_gcn_forward_tc2(params, prepared_v, states, B, pooled, saved, st);
+    if (!saved && version == 2) return aq_gcn_forward_tc2(params, prepared_v, states, B, pooled, nullptr, st, after_legal);
+    if (saved && aq_train_tc_version() == 2) return aq_gcn_forward_tc2(params, prepared_v, states, B, pooled, saved, st, false);
     if (saved || groups == 3) return launch_tc<3>(params, prepared, states, B, pooled, saved, sms, st);  // the save variant needs the registers
     if (groups == 4) return launch_tc<4>(params, prepared, states, B, pooled, saved, sms, st);
     return launch_tc<5>(params, prepared, states, B, pooled, saved, sms, st);

@@ -658,6 +658,7 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         TC2_T(10);
     }
     // ---- teardown ---------------------------------------------------------------------------------------------------
+    aq_pdl_wait();  // programmatic launch behind the legal-mask kernel: this grid is complete only once that one is (no-op otherwise)
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (gtid < 32) {
@@ -669,8 +670,11 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
 
 // Trunk, version 2.  saved == nullptr: inference (same contract as aq_gcn_forward_tc); saved != nullptr: training forward, precision 1,
 // activations kept in the Tc2Saved layout for aq_gcn_backward_tc2.
+// after_legal: the predecessor in the stream is the legal-mask kernel of the same leaf evaluation, whose output this kernel does not read:
+// the grid is launched programmatically (it starts on SMs as the legal-mask grid drains from them) and orders itself behind that grid
+// only at its very end (aq_pdl_wait before the teardown), so that the heads kernel behind it sees the mask.
 int aq_gcn_forward_tc2(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, float *saved,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool after_legal) {
     static int sms = 0;
     static uint32_t wait_ns = 0;
     if (sms == 0) {
@@ -693,7 +697,13 @@ int aq_gcn_forward_tc2(const float *params, const void *prepared, const AqState 
     } else {
         e = cudaFuncSetAttribute(gcn_forward_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return aq_set_error((int)e, "gcn_forward_tc2 smem");
-        gcn_forward_tc2_kernel<false><<<grid, kG * kGroupThreads, smem, st>>>(params, prep, states, B, pooled, nullptr, wait_ns);
+        if (after_legal) {
+            e = aq_launch_pdl(gcn_forward_tc2_kernel<false>, dim3(grid), dim3(kG * kGroupThreads), smem, st, params, prep, states, B, pooled,
+                              (float *)nullptr, wait_ns);
+            if (e != cudaSuccess) return aq_set_error((int)e, "gcn_forward_tc2_kernel(launch)");
+        } else {
+            gcn_forward_tc2_kernel<false><<<grid, kG * kGroupThreads, smem, st>>>(params, prep, states, B, pooled, nullptr, wait_ns);
+        }
     }
     return aq_check_launch("gcn_forward_tc2_kernel");
 }

@@ -148,7 +148,7 @@ __device__ __forceinline__ uint32_t positive_bits_b(uint4 c) {
 constexpr int kBwdThreads = 256;
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
-gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ saved, const float *__restrict__ dg,
+gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ saved, const float *dg,
                         int64_t B, float *__restrict__ partial) {
     extern __shared__ unsigned char smem_raw[];
     Bwd2Smem &sm = *reinterpret_cast<Bwd2Smem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -291,8 +291,8 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
     // and overlapped the tail of the heads backward; the saved activations and dg are read from here on
     aq_pdl_wait();
     prefetch_board(blockIdx.x, 0);
-    uint4 mk_next = __ldg(reinterpret_cast<const uint4 *>(SV.mask3(saved, blockIdx.x) + tid * 16));
-    float dg_next = __ldg(dg + (int64_t)blockIdx.x * kH + tid);
+    uint4 mk_next = __ldcg(reinterpret_cast<const uint4 *>(SV.mask3(saved, blockIdx.x) + tid * 16));  // coherent: PDL rule (aq_common.cuh)
+    float dg_next = __ldcg(dg + (int64_t)blockIdx.x * kH + tid);
 #if TC2B_TIMING
     long long t_last = clock64();
 #endif
@@ -304,8 +304,8 @@ gcn_backward_tc2_kernel(const float *__restrict__ params, float *__restrict__ sa
         const uint4 mk = mk_next;
         const float dgn = dg_next / (float)kV;  // d mean / d x_v
         if (b + gridDim.x < B) {
-            mk_next = __ldg(reinterpret_cast<const uint4 *>(SV.mask3(saved, b + gridDim.x) + tid * 16));
-            dg_next = __ldg(dg + (b + gridDim.x) * kH + tid);
+            mk_next = __ldcg(reinterpret_cast<const uint4 *>(SV.mask3(saved, b + gridDim.x) + tid * 16));
+            dg_next = __ldcg(dg + (b + gridDim.x) * kH + tid);
         }
         m3 = half ? ((u64)(mk.y >> 16) | ((u64)mk.z << 16)) : ((u64)mk.x | ((u64)(mk.y & 0xFFFFu) << 32));
         TC2B_T(0);

@@ -95,8 +95,8 @@ __device__ __forceinline__ uint4 pack8(const float *f) {
 template <bool kLegal>
 __global__ void __launch_bounds__(kHtThreads)
 heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *__restrict__ prepared,
-                        const float *__restrict__ pooled, int64_t B, float *__restrict__ policy,
-                        float *__restrict__ value, const uint32_t *__restrict__ mask, float *__restrict__ saved) {
+                        const float *pooled, int64_t B, float *__restrict__ policy,
+                        float *__restrict__ value, const uint32_t *mask, float *__restrict__ saved) {
     // saved != nullptr (training forward, precision 1): the post-ReLU hidden activations (fp32, before the bf16 rounding that feeds
     // GEMM 2), the probabilities and the value are also written into the SavedLayout regions heads_backward_kernel reads
     extern __shared__ unsigned char smem_raw[];
@@ -162,8 +162,8 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
         const int r = c >> 4, j = c & 15;
         float f[8];
         if (b0 + r < B) {
-            const float4 lo = __ldg(reinterpret_cast<const float4 *>(pooled + (b0 + r) * kH + j * 8));
-            const float4 hi = __ldg(reinterpret_cast<const float4 *>(pooled + (b0 + r) * kH + j * 8) + 1);
+            const float4 lo = __ldcg(reinterpret_cast<const float4 *>(pooled + (b0 + r) * kH + j * 8));  // coherent: PDL rule (aq_common.cuh)
+            const float4 hi = __ldcg(reinterpret_cast<const float4 *>(pooled + (b0 + r) * kH + j * 8) + 1);
             f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
         } else {
 #pragma unroll
@@ -254,7 +254,7 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
     ld32(lane_base + (2 * q) * 32, v0);
     if (q < 3) ld32(lane_base + (2 * q + 1) * 32, v1);
     uint32_t bits0 = 0xFFFFFFFFu, bits1 = 0xFFFFFFFFu;
-    if (kLegal && valid) { bits0 = __ldg(lmask + 2 * q); bits1 = q < 3 ? __ldg(lmask + 2 * q + 1) : 0u; }
+    if (kLegal && valid) { bits0 = __ldcg(lmask + 2 * q); bits1 = q < 3 ? __ldcg(lmask + 2 * q + 1) : 0u; }
     float mx = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {

@@ -161,3 +161,30 @@ def test_legal_mask_every_form_agrees_with_reference(traj, monkeypatch):
     pawn = torch.zeros((B, 8), dtype=torch.uint8, device="cuda")
     _lib.check(L.aq_legal_mask(_lib.ptr(packed), B, _lib.ptr(mask), _lib.ptr(pawn), _lib.stream_ptr()), "aq_legal_mask")
     assert np.array_equal(_np(mask).view(np.uint32), want_mask) and np.array_equal(_np(pawn), want_pawn)
+
+
+def test_two_phase_legal_mask_back_to_back_calls_with_different_task_counts(traj):
+    """Regression: the search kernel is launched programmatically behind the prepare kernel; its loads of the task count and the
+    task list must come after its grid-dependency wait (a `const __restrict__` load was hoisted above it and read the PREVIOUS
+    call's count).  Alternating batches with many / no / few path searches through the same workspace must all be exact."""
+    from alphaquoridorgnn_b200 import _lib
+    L = _lib.load()
+    rows, plies = traj["rows"], traj["plies"]
+    nwalls = (rows[:, 4:] != 0).sum(1)
+    hard = np.argsort(-nwalls)[:6000]          # many walls on the board: many gated candidates
+    easy = np.nonzero(nwalls == 0)[0][:6000]   # no walls: no path search at all
+    mid = np.arange(5000, 11000)
+    ws = torch.empty((L.aq_legal_mask_ws_bytes(6000),), dtype=torch.uint8, device="cuda")
+    packed = {k: gl.pack_rows(rows[idx], plies[idx]) for k, idx in (("hard", hard), ("easy", easy), ("mid", mid))}
+    want = {k: (traj["mask"][idx], traj["pawn"][idx]) for k, idx in (("hard", hard), ("easy", easy), ("mid", mid))}
+    outs = []
+    for k in ("hard", "easy", "hard", "mid", "easy", "mid", "hard"):
+        mask = torch.zeros((6000, 8), dtype=torch.int32, device="cuda")
+        pawn = torch.zeros((6000, 8), dtype=torch.uint8, device="cuda")
+        _lib.check(L.aq_legal_mask_ws(_lib.ptr(packed[k]), 6000, _lib.ptr(mask), _lib.ptr(pawn), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   "aq_legal_mask_ws")
+        outs.append((k, mask, pawn))  # no synchronisation between the calls
+    torch.cuda.synchronize()
+    for k, mask, pawn in outs:
+        assert np.array_equal(_np(mask).view(np.uint32), want[k][0]), k
+        assert np.array_equal(_np(pawn), want[k][1]), k
