@@ -440,7 +440,11 @@ def run_ours(args, rank, world, local_rank):
                        "batch_per_gpu": B, "precision": args.precision, "parallelism": f"independent leaf batches x{world}",
                        "l2": "flushed before every timed launch (256 MiB write, outside the per-launch CUDA events)",
                        "host_numa": numa},
-            "roofline": roofline, "kernels": kinfo, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "roofline": roofline, "kernels": kinfo,
+            # the kernels of a step are chained by programmatic dependent launches (prologues overlap the predecessor's tail), so the
+            # step is shorter than the sum of its kernels timed alone
+            "sum_of_kernels_timed_alone_ms": ksum,
+            "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": 4 * K,  # legal_prepare + legal_search + trunk + heads per step (plus one 4-byte memset)
             "clocks": clocks, "extra": extra,
         }
