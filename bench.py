@@ -98,7 +98,7 @@ class ClockSampler:
     def stop(self):
         self.stop_flag = True
         if self.t:
-            self.t.join(timeout=6)
+            self.t.join(timeout=15)  # a query in flight (nvidia-smi takes seconds on a fresh box) still belongs to the timed region
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
