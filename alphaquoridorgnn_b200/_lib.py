@@ -8,7 +8,8 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("AQ_LIB_PATH") or os.path.join(_PKG, "libaqgnn.so")  # AQ_LIB_PATH: kernel-variant builds (scripts/build_variant.py)
+LIB_PATH = os.path.join(_PKG, "libaqgnn.so")
+ABI_VERSION = 200  # AQ_VERSION of include/aqgnn.h this table of signatures was written for
 
 # name -> (restype, argtypes); must list every symbol declared in include/aqgnn.h
 _vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
@@ -44,9 +45,10 @@ SYMBOLS = {
     "aq_leaf_eval_host": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "aq_compact_priors": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "aq_leaf_eval_host_compact_ws_bytes": (_i64, [_i64]),
-    "aq_leaf_eval_host_compact": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
-    "aq_leaf_eval_host_compact_submit": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "aq_leaf_eval_host_compact": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "aq_leaf_eval_host_compact_submit": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "aq_leaf_eval_host_compact_wait": (_i32, [_vp]),
+    "aq_host_ctx_stats": (_i32, [_vp, _vp]),
     "aq_mcts_ws_bytes": (_i64, [_i64, _i64]),
     "aq_mcts_reset": (_i32, [_vp, _vp, _i64, _i64, _vp]),
     "aq_mcts_select": (_i32, [_vp, _i64, _i64, _f32, _vp, _vp, _vp]),
@@ -64,20 +66,25 @@ class AqError(RuntimeError):
 
 
 def load(build_if_missing=True):
-    """Load libaqgnn.so, building it with nvcc if it is absent. Raises if that is impossible."""
+    """Load libaqgnn.so, (re)building it with nvcc if it is absent or older than its sources.  Raises if that is
+    impossible, or if the library's ABI version is not the one this table of signatures was written for."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise AqError(f"{LIB_PATH} is missing; run `python -m alphaquoridorgnn_b200.build`")
-        from . import build as _build
+    from . import build as _build
+    stale = _build.needs_build()
+    if stale:
+        if not build_if_missing or _build.find_nvcc() is None:
+            raise AqError(f"{LIB_PATH} is {'missing' if not os.path.exists(LIB_PATH) else 'older than csrc/ or include/aqgnn.h'}; "
+                          "run `python -m alphaquoridorgnn_b200.build`")
         _build.build()
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
+    if lib.aq_version() != ABI_VERSION:
+        raise AqError(f"{LIB_PATH} has ABI version {lib.aq_version()}, the loader expects {ABI_VERSION}: rebuild the library")
     _lib = lib
     return lib
 

@@ -20,23 +20,47 @@ NVCC_FLAGS = [
 ]
 
 
-def nvcc_path():
+def find_nvcc():
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
             return cand
-    raise RuntimeError("nvcc not found")
+    return None
+
+
+def nvcc_path():
+    p = find_nvcc()
+    if p is None:
+        raise RuntimeError("nvcc not found")
+    return p
 
 
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+STAMP_PATH = LIB_PATH + ".stamp"
+
+
+def source_digest():
+    """sha256 over every file the library is built from (content, not mtime: the snapshot that carries the repo to the
+    GPU box does not keep modification times)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(PKG_DIR, "..", "include", "aqgnn.h")]
+    for p in deps:
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB_PATH):
+    """True if libaqgnn.so is missing or was built from other sources than the ones in the tree."""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(STAMP_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(PKG_DIR, "..", "include", "aqgnn.h")]
-    return any(os.path.getmtime(p) > t for p in deps)
+    with open(STAMP_PATH) as f:
+        return f.read().strip() != source_digest()
 
 
 def build(force=False, verbose=False):
@@ -67,6 +91,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed; see " + os.path.join(obj_dir, "nvcc.log"))
     link = [nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs + ["-lcuda"]
     subprocess.check_call(link)
+    with open(STAMP_PATH, "w") as f:
+        f.write(source_digest() + "\n")
     return LIB_PATH
 
 

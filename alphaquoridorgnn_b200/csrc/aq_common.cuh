@@ -43,17 +43,54 @@ static inline cudaError_t aq_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim
 
 namespace aq {
 
-AQ_DEV u128 bit81(int sq) { return (u128)1 << sq; }
-AQ_DEV constexpr u128 make128(u64 hi, u64 lo) { return ((u128)hi << 64) | lo; }
+// ---- 81-square bitboards: three 27-bit words, word w = rows 3w .. 3w+2, bit 9 (r % 3) + c -------------------------------------
+// (An `unsigned __int128` board costs 4 ALU instructions per AND/OR and 6-8 per shift on a 32-bit machine; three words that hold
+// whole rows need 3, and a row shift by +-1 is one shift per word because the open-direction boards never let a bit leave its row.)
+struct B81 {
+    uint32_t w0, w1, w2;
+};
+constexpr uint32_t kM27 = 0x7FFFFFFu;
+constexpr uint32_t kRowLo = 0x1FFu;            // first row of a word
+constexpr uint32_t kCol0W = 1u | (1u << 9) | (1u << 18);
+constexpr uint32_t kCol8W = kCol0W << 8;
 
-// rows r has bits 9r..9r+8
-constexpr u128 kFull = (((u128)1) << 81) - 1;
-constexpr u128 kRow0 = (u128)0x1FF;
-constexpr u128 kRow8 = (u128)0x1FF << 72;
-// column 0: bits 0,9,18,...,72
-constexpr u128 kCol0 = ((u128)1) | ((u128)1 << 9) | ((u128)1 << 18) | ((u128)1 << 27) | ((u128)1 << 36) |
-                       ((u128)1 << 45) | ((u128)1 << 54) | ((u128)1 << 63) | ((u128)1 << 72);
-constexpr u128 kCol8 = kCol0 << 8;
+AQ_DEV B81 b81(uint32_t a, uint32_t b, uint32_t c) { B81 r; r.w0 = a; r.w1 = b; r.w2 = c; return r; }
+AQ_DEV B81 operator&(B81 a, B81 b) { return b81(a.w0 & b.w0, a.w1 & b.w1, a.w2 & b.w2); }
+AQ_DEV B81 operator|(B81 a, B81 b) { return b81(a.w0 | b.w0, a.w1 | b.w1, a.w2 | b.w2); }
+AQ_DEV B81 andn(B81 a, B81 b) { return b81(a.w0 & ~b.w0, a.w1 & ~b.w1, a.w2 & ~b.w2); }  // a & ~b
+AQ_DEV bool any(B81 a) { return (a.w0 | a.w1 | a.w2) != 0u; }
+AQ_DEV bool meets(B81 a, B81 b) { return ((a.w0 & b.w0) | (a.w1 & b.w1) | (a.w2 & b.w2)) != 0u; }
+AQ_DEV bool same(B81 a, B81 b) { return ((a.w0 ^ b.w0) | (a.w1 ^ b.w1) | (a.w2 ^ b.w2)) == 0u; }
+AQ_DEV B81 bit81(int sq) {
+    const int w = sq >= 54 ? 2 : sq >= 27 ? 1 : 0;
+    const uint32_t m = 1u << (sq - 27 * w);
+    return b81(w == 0 ? m : 0u, w == 1 ? m : 0u, w == 2 ? m : 0u);
+}
+AQ_DEV bool has(B81 b, int sq) {
+    const int w = sq >= 54 ? 2 : sq >= 27 ? 1 : 0;
+    const uint32_t x = w == 0 ? b.w0 : w == 1 ? b.w1 : b.w2;
+    return ((x >> (sq - 27 * w)) & 1u) != 0u;
+}
+// every square one row down (sq + 9) / up (sq - 9); bits that leave the board are dropped
+AQ_DEV B81 down9(B81 b) { return b81((b.w0 << 9) & kM27, ((b.w1 << 9) | (b.w0 >> 18)) & kM27, ((b.w2 << 9) | (b.w1 >> 18)) & kM27); }
+AQ_DEV B81 up9(B81 b) { return b81((b.w0 >> 9) | ((b.w1 << 18) & kM27), (b.w1 >> 9) | ((b.w2 << 18) & kM27), b.w2 >> 9); }
+// sq + 1 / sq - 1 inside the words (callers mask the source so that no bit crosses a row end)
+AQ_DEV B81 right1(B81 b) { return b81((b.w0 << 1) & kM27, (b.w1 << 1) & kM27, (b.w2 << 1) & kM27); }
+AQ_DEV B81 left1(B81 b) { return b81(b.w0 >> 1, b.w1 >> 1, b.w2 >> 1); }
+AQ_DEV int lowest_square(B81 b) {
+#ifdef __CUDA_ARCH__
+    return b.w0 ? __ffs((int)b.w0) - 1 : b.w1 ? 27 + __ffs((int)b.w1) - 1 : 54 + __ffs((int)b.w2) - 1;
+#else
+    return b.w0 ? __builtin_ctz(b.w0) : b.w1 ? 27 + __builtin_ctz(b.w1) : 54 + __builtin_ctz(b.w2);
+#endif
+}
+AQ_DEV int count81(B81 b) {
+#ifdef __CUDA_ARCH__
+    return __popc(b.w0) + __popc(b.w1) + __popc(b.w2);
+#else
+    return __builtin_popcount(b.w0) + __builtin_popcount(b.w1) + __builtin_popcount(b.w2);
+#endif
+}
 
 constexpr u64 kC0 = 0x0101010101010101ull;  // wall-slot column 0
 constexpr u64 kC7 = 0x8080808080808080ull;  // wall-slot column 7
@@ -61,28 +98,35 @@ constexpr u64 kR0 = 0x00000000000000FFull;  // wall-slot row 0
 constexpr u64 kR7 = 0xFF00000000000000ull;  // wall-slot row 7
 
 // 8x8 slot board -> 9x9 square board, slot (x,y) -> square (x,y) (its top-left tile)
-AQ_DEV u128 expand8to9(u64 b) {
-    u128 r = 0;
-#pragma unroll
-    for (int x = 0; x < 8; ++x) r |= (u128)((b >> (8 * x)) & 0xFFull) << (9 * x);
-    return r;
+AQ_DEV B81 expand8to9(u64 b) {
+    const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+    return b81((lo & 0xFFu) | ((lo & 0xFF00u) << 1) | ((lo & 0xFF0000u) << 2),
+               (lo >> 24) | ((hi & 0xFFu) << 9) | ((hi & 0xFF00u) << 10),
+               ((hi >> 16) & 0xFFu) | ((hi >> 24) << 9));
+}
+// 9x9 square board -> 8x8 slot board: slot (x,y) <- square (x,y); column 8 and row 8 are dropped
+AQ_DEV u64 compress9to8(B81 b) {
+    const uint32_t lo = (b.w0 & 0xFFu) | ((b.w0 >> 1) & 0xFF00u) | ((b.w0 >> 2) & 0xFF0000u) | (b.w1 << 24);
+    const uint32_t hi = ((b.w1 >> 9) & 0xFFu) | ((b.w1 >> 10) & 0xFF00u) | ((b.w2 & 0xFFu) << 16) | (((b.w2 >> 9) & 0xFFu) << 24);
+    return ((u64)hi << 32) | lo;
 }
 
 // Open-direction bitboards: bit sq of up/down/left/right set iff the pawn move from sq in that
 // direction stays on the board and is not wall-blocked (is_wall_blocking, game_logic.py:145-167).
 struct Open {
-    u128 up, down, left, right;
+    B81 up, down, left, right;
 };
 
 AQ_DEV Open open_from_walls(u64 h, u64 v) {
-    const u128 eh = expand8to9(h), ev = expand8to9(v);
-    const u128 bdown = eh | (eh << 1);   // H wall in slot (x,y) blocks squares (x,y),(x,y+1) downward
-    const u128 bright = ev | (ev << 9);  // V wall in slot (x,y) blocks squares (x,y),(x+1,y) rightward
+    const B81 eh = expand8to9(h), ev = expand8to9(v);
+    const B81 bdown = eh | right1(eh);    // H wall in slot (x,y) blocks squares (x,y),(x,y+1) downward
+    const B81 bright = ev | down9(ev);    // V wall in slot (x,y) blocks squares (x,y),(x+1,y) rightward
+    const B81 bup = down9(bdown), bleft = right1(bright);
     Open o;
-    o.down = ~bdown & ~kRow8 & kFull;
-    o.up = ~(bdown << 9) & ~kRow0 & kFull;
-    o.right = ~bright & ~kCol8 & kFull;
-    o.left = ~(bright << 1) & ~kCol0 & kFull;
+    o.down = b81(~bdown.w0 & kM27, ~bdown.w1 & kM27, ~bdown.w2 & (kM27 >> 9));        // no move down from row 8
+    o.up = b81(~bup.w0 & (kM27 & ~kRowLo), ~bup.w1 & kM27, ~bup.w2 & kM27);           // none up from row 0
+    o.right = b81(~bright.w0 & (kM27 & ~kCol8W), ~bright.w1 & (kM27 & ~kCol8W), ~bright.w2 & (kM27 & ~kCol8W));
+    o.left = b81(~bleft.w0 & (kM27 & ~kCol0W), ~bleft.w1 & (kM27 & ~kCol0W), ~bleft.w2 & (kM27 & ~kCol0W));
     return o;
 }
 
@@ -91,92 +135,82 @@ AQ_DEV void add_wall(Open &o, int orient, int slot) {
     const int x = slot >> 3, y = slot & 7;
     const int sq = 9 * x + y;
     if (orient == 1) {
-        const u128 m = (u128)3 << sq;
-        o.down &= ~m;
-        o.up &= ~(m << 9);
+        const B81 m = bit81(sq) | bit81(sq + 1);
+        o.down = andn(o.down, m);
+        o.up = andn(o.up, down9(m));
     } else {
-        const u128 m = ((u128)1 | ((u128)1 << 9)) << sq;
-        o.right &= ~m;
-        o.left &= ~(m << 1);
+        const B81 m = bit81(sq) | bit81(sq + 9);
+        o.right = andn(o.right, m);
+        o.left = andn(o.left, right1(m));
     }
 }
-
-AQ_DEV bool has(u128 b, int sq) { return (unsigned)((b >> sq) & 1) != 0u; }
 
 // Targets of a jump over the pawn on `ob` when it is approached moving in direction d
 // (0=U,1=D,2=L,3=R): straight if open, else the two perpendicular squares that are open
 // (game_logic.py:174-188).  Returned as a bitboard (order is irrelevant for reachability).
-AQ_DEV u128 jump_targets(const Open &o, int ob, int d) {
-    u128 t = 0;
-    if (d == 0) {
-        if (has(o.up, ob)) t = bit81(ob - 9);
-        else { if (has(o.left, ob)) t |= bit81(ob - 1); if (has(o.right, ob)) t |= bit81(ob + 1); }
-    } else if (d == 1) {
-        if (has(o.down, ob)) t = bit81(ob + 9);
-        else { if (has(o.left, ob)) t |= bit81(ob - 1); if (has(o.right, ob)) t |= bit81(ob + 1); }
-    } else if (d == 2) {
-        if (has(o.left, ob)) t = bit81(ob - 1);
-        else { if (has(o.up, ob)) t |= bit81(ob - 9); if (has(o.down, ob)) t |= bit81(ob + 9); }
-    } else {
-        if (has(o.right, ob)) t = bit81(ob + 1);
-        else { if (has(o.up, ob)) t |= bit81(ob - 9); if (has(o.down, ob)) t |= bit81(ob + 9); }
+AQ_DEV B81 jump_targets(const Open &o, int ob, int d) {
+    const bool u = has(o.up, ob), dn = has(o.down, ob), l = has(o.left, ob), r = has(o.right, ob);
+    const B81 none = b81(0u, 0u, 0u);
+    if (d == 0) return u ? bit81(ob - 9) : ((l ? bit81(ob - 1) : none) | (r ? bit81(ob + 1) : none));
+    if (d == 1) return dn ? bit81(ob + 9) : ((l ? bit81(ob - 1) : none) | (r ? bit81(ob + 1) : none));
+    if (d == 2) return l ? bit81(ob - 1) : ((u ? bit81(ob - 9) : none) | (dn ? bit81(ob + 9) : none));
+    return r ? bit81(ob + 1) : ((u ? bit81(ob - 9) : none) | (dn ? bit81(ob + 9) : none));
+}
+
+// The pawn rules around the obstacle square `ob` (the other pawn) for a flood fill: src[d] = the square from which a move in
+// direction d lands on ob (only if that edge is open), jump[d] = where that move ends up instead.
+struct Jumps {
+    B81 pending;   // union of the source squares whose jump has not been applied yet
+    B81 jump[4];
+    int src[4];    // -1: no such source
+};
+AQ_DEV Jumps jumps_around(const Open &o, int ob) {
+    Jumps j;
+    j.src[0] = has(o.down, ob) ? ob + 9 : -1;   // below ob, moving up
+    j.src[1] = has(o.up, ob) ? ob - 9 : -1;
+    j.src[2] = has(o.right, ob) ? ob + 1 : -1;  // right of ob, moving left
+    j.src[3] = has(o.left, ob) ? ob - 1 : -1;
+    j.pending = b81(0u, 0u, 0u);
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        j.jump[d] = jump_targets(o, ob, d);
+        if (j.src[d] >= 0) j.pending = j.pending | bit81(j.src[d]);
     }
-    return t;
+    return j;
+}
+
+// one flood-fill step: the squares reachable by one plain move from `reach` (the obstacle square excluded by `notob`)
+AQ_DEV B81 step81(const Open &o, B81 reach) {
+    return up9(reach & o.up) | down9(reach & o.down) | left1(reach & o.left) | right1(reach & o.right);
 }
 
 // bfs() of game_logic.py:309-324 as a bitboard flood fill with the pawn rules of
 // legal_actions_pos applied at every visited square: the obstacle square `ob` is never entered;
-// a square adjacent to it (edge open) reaches the jump targets instead.  Returns true iff a
-// square of `goal` is reachable from `start`.
-AQ_DEV bool reaches(const Open &o, int start, int ob, u128 goal) {
-    // source squares from which a move in direction d lands on the obstacle
-    const u128 srcU = has(o.down, ob) ? bit81(ob + 9) : (u128)0;  // below, moving up
-    const u128 srcD = has(o.up, ob) ? bit81(ob - 9) : (u128)0;
-    const u128 srcL = has(o.right, ob) ? bit81(ob + 1) : (u128)0;  // right of it, moving left
-    const u128 srcR = has(o.left, ob) ? bit81(ob - 1) : (u128)0;
-    const u128 jU = jump_targets(o, ob, 0), jD = jump_targets(o, ob, 1);
-    const u128 jL = jump_targets(o, ob, 2), jR = jump_targets(o, ob, 3);
-    const u128 notob = ~bit81(ob);
-    u128 reach = bit81(start);
-    while (true) {
-        if (reach & goal) return true;
-        u128 nb = ((reach & o.up) >> 9) | ((reach & o.down) << 9) | ((reach & o.left) >> 1) | ((reach & o.right) << 1);
-        nb &= notob;
-        if (reach & srcU) nb |= jU;
-        if (reach & srcD) nb |= jD;
-        if (reach & srcL) nb |= jL;
-        if (reach & srcR) nb |= jR;
-        const u128 nxt = reach | nb;
-        if (nxt == reach) return false;
-        reach = nxt;
-    }
-}
-
-// shortest_path_bfs of agents.py:27-41: number of pawn steps (a jump is one step) from `start` to the nearest
-// square of `goal` under the same pawn rules; every iteration of the flood fill is one BFS layer.  -1 if no
-// path exists (agents.py:41).
-AQ_DEV int path_length(const Open &o, int start, int ob, u128 goal) {
-    const u128 srcU = has(o.down, ob) ? bit81(ob + 9) : (u128)0;
-    const u128 srcD = has(o.up, ob) ? bit81(ob - 9) : (u128)0;
-    const u128 srcL = has(o.right, ob) ? bit81(ob + 1) : (u128)0;
-    const u128 srcR = has(o.left, ob) ? bit81(ob - 1) : (u128)0;
-    const u128 jU = jump_targets(o, ob, 0), jD = jump_targets(o, ob, 1);
-    const u128 jL = jump_targets(o, ob, 2), jR = jump_targets(o, ob, 3);
-    const u128 notob = ~bit81(ob);
-    u128 reach = bit81(start);
+// a square adjacent to it (edge open) reaches the jump targets instead.  Returns the number of fill
+// iterations (= BFS depth, a jump is one step) after which a square of `goal` is reached, -1 if none is.
+AQ_DEV int flood_depth(const Open &o, int start, int ob, B81 goal) {
+    Jumps j = jumps_around(o, ob);
+    const B81 ob_b = bit81(ob);
+    B81 reach = bit81(start);
     for (int depth = 0;; ++depth) {
-        if (reach & goal) return depth;
-        u128 nb = ((reach & o.up) >> 9) | ((reach & o.down) << 9) | ((reach & o.left) >> 1) | ((reach & o.right) << 1);
-        nb &= notob;
-        if (reach & srcU) nb |= jU;
-        if (reach & srcD) nb |= jD;
-        if (reach & srcL) nb |= jL;
-        if (reach & srcR) nb |= jR;
-        const u128 nxt = reach | nb;
-        if (nxt == reach) return -1;
+        if (meets(reach, goal)) return depth;
+        B81 nxt = reach | andn(step81(o, reach), ob_b);
+        if (meets(reach, j.pending)) {  // at most four times per fill: a source square was reached, its jump targets join
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+                if (j.src[d] >= 0 && has(reach, j.src[d])) nxt = nxt | j.jump[d];
+            j.pending = andn(j.pending, reach);
+        }
+        if (same(nxt, reach)) return -1;
         reach = nxt;
     }
 }
+AQ_DEV bool reaches(const Open &o, int start, int ob, B81 goal) { return flood_depth(o, start, ob, goal) >= 0; }
+// shortest_path_bfs of agents.py:27-41: number of pawn steps from `start` to the nearest square of `goal`; -1 if no path (agents.py:41)
+AQ_DEV int path_length(const Open &o, int start, int ob, B81 goal) { return flood_depth(o, start, ob, goal); }
+
+AQ_DEV B81 goal_row0() { return b81(kRowLo, 0u, 0u); }
+AQ_DEV B81 goal_row8() { return b81(0u, 0u, kRowLo << 18); }
 
 // ---- path witness --------------------------------------------------------------------------------
 // One concrete path start -> goal (with the pawn rules) found by the same flood fill, returned as the
@@ -186,77 +220,69 @@ AQ_DEV int path_length(const Open &o, int start, int ob, u128 goal) {
 // severed, and every "straight jump blocked" condition stays true.  (The converse is not used: a
 // candidate that cuts the witness gets a real search.  If no path exists without the candidate, all
 // candidates are searched -- a wall behind the other pawn can create diagonal jumps.)
+// The fill records for every square the move that reached it first as two direction-code planes (0 = up, 1 = down, 2 = left,
+// 3 = right) plus a "by a jump" plane; the path is read back from the goal with one-square lookups.
 struct PathCuts {
     u64 cutH, cutV;
     int exists;
 };
 
-AQ_DEV int lowest_bit(u128 b) {
-    const u64 lo = (u64)b, hi = (u64)(b >> 64);
-#ifdef __CUDA_ARCH__
-    return lo ? __ffsll((long long)lo) - 1 : 64 + __ffsll((long long)hi) - 1;
-#else
-    return lo ? __builtin_ctzll(lo) : 64 + __builtin_ctzll(hi);
-#endif
+AQ_DEV void mark(B81 &b, int sq) {
+    const int w = sq >= 54 ? 2 : sq >= 27 ? 1 : 0;
+    const uint32_t m = 1u << (sq - 27 * w);
+    b.w0 |= w == 0 ? m : 0u; b.w1 |= w == 1 ? m : 0u; b.w2 |= w == 2 ? m : 0u;
 }
 
-// unit edge between adjacent squares a and b -> slots whose wall severs it
-AQ_DEV void add_edge_cut(PathCuts &pc, int a, int b) {
-    const int lo = a < b ? a : b, hi = a < b ? b : a;
-    const int r = lo / 9, c = lo % 9;
-    if (hi - lo == 9) {  // vertical edge (r,c)-(r+1,c): H walls in slots (r,c) and (r,c-1)
-        if (c < 8) pc.cutH |= 1ull << (8 * r + c);
-        if (c > 0) pc.cutH |= 1ull << (8 * r + c - 1);
-    } else {             // horizontal edge (r,c)-(r,c+1): V walls in slots (r,c) and (r-1,c)
-        if (r < 8) pc.cutV |= 1ull << (8 * r + c);
-        if (r > 0) pc.cutV |= 1ull << (8 * (r - 1) + c);
-    }
-}
-
-AQ_DEV PathCuts find_path_cuts(const Open &o, int start, int ob, u128 goal) {
-    const u128 srcU = has(o.down, ob) ? bit81(ob + 9) : (u128)0;
-    const u128 srcD = has(o.up, ob) ? bit81(ob - 9) : (u128)0;
-    const u128 srcL = has(o.right, ob) ? bit81(ob + 1) : (u128)0;
-    const u128 srcR = has(o.left, ob) ? bit81(ob - 1) : (u128)0;
-    const u128 jU = jump_targets(o, ob, 0), jD = jump_targets(o, ob, 1);
-    const u128 jL = jump_targets(o, ob, 2), jR = jump_targets(o, ob, 3);
-    const u128 notob = ~bit81(ob);
-    u128 reach = bit81(start);
-    // squares first reached by a plain move in direction U/D/L/R, or by a jump approached in that direction
-    u128 byU = 0, byD = 0, byL = 0, byR = 0, jbU = 0, jbD = 0, jbL = 0, jbR = 0;
+AQ_DEV PathCuts find_path_cuts(const Open &o, int start, int ob, B81 goal) {
+    Jumps j = jumps_around(o, ob);
+    const B81 ob_b = bit81(ob);
+    B81 reach = bit81(start);
+    B81 c0 = b81(0u, 0u, 0u), c1 = c0, byj = c0;
     PathCuts pc;
     pc.cutH = 0; pc.cutV = 0; pc.exists = 0;
-    while (!(reach & goal)) {
-        u128 acc = reach, n;
-        n = ((reach & o.up) >> 9) & notob & ~acc;    byU |= n; acc |= n;
-        n = ((reach & o.down) << 9) & notob & ~acc;  byD |= n; acc |= n;
-        n = ((reach & o.left) >> 1) & notob & ~acc;  byL |= n; acc |= n;
-        n = ((reach & o.right) << 1) & notob & ~acc; byR |= n; acc |= n;
-        if (reach & srcU) { n = jU & ~acc; jbU |= n; acc |= n; }
-        if (reach & srcD) { n = jD & ~acc; jbD |= n; acc |= n; }
-        if (reach & srcL) { n = jL & ~acc; jbL |= n; acc |= n; }
-        if (reach & srcR) { n = jR & ~acc; jbR |= n; acc |= n; }
-        if (acc == reach) return pc;  // goal unreachable even without a candidate
+    while (!meets(reach, goal)) {
+        B81 acc = reach, n;
+        n = andn(andn(up9(reach & o.up), ob_b), acc);      acc = acc | n;                              // code 0
+        n = andn(andn(down9(reach & o.down), ob_b), acc);  acc = acc | n; c0 = c0 | n;                 // code 1
+        n = andn(andn(left1(reach & o.left), ob_b), acc);  acc = acc | n; c1 = c1 | n;                 // code 2
+        n = andn(andn(right1(reach & o.right), ob_b), acc); acc = acc | n; c0 = c0 | n; c1 = c1 | n;   // code 3
+        if (meets(reach, j.pending)) {
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+                if (j.src[d] >= 0 && has(reach, j.src[d])) {
+                    n = andn(j.jump[d], acc);
+                    acc = acc | n; byj = byj | n;
+                    if (d & 1) c0 = c0 | n;
+                    if (d & 2) c1 = c1 | n;
+                }
+            j.pending = andn(j.pending, reach);
+        }
+        if (same(acc, reach)) return pc;  // goal unreachable even without a candidate
         reach = acc;
     }
     pc.exists = 1;
-    int cur = lowest_bit(reach & goal);
+    // unit edges of the path: vertical edge (r,c)-(r+1,c) marked at square (r,c) in ve, horizontal edge (r,c)-(r,c+1) at (r,c) in he
+    B81 ve = b81(0u, 0u, 0u), he = ve;
+    int cur = lowest_square(reach & goal);
     while (cur != start) {
-        int prev;
-        if (has(byU, cur)) prev = cur + 9;
-        else if (has(byD, cur)) prev = cur - 9;
-        else if (has(byL, cur)) prev = cur + 1;
-        else if (has(byR, cur)) prev = cur - 1;
-        else {  // jump over the pawn on ob: two unit edges, src-ob and ob-cur
-            prev = has(jbU, cur) ? ob + 9 : has(jbD, cur) ? ob - 9 : has(jbL, cur) ? ob + 1 : ob - 1;
-            add_edge_cut(pc, prev, ob);
-            add_edge_cut(pc, ob, cur);
+        const int code = (int)has(c0, cur) | ((int)has(c1, cur) << 1);
+        const int back = code == 0 ? 9 : code == 1 ? -9 : code == 2 ? 1 : -1;  // from the square back to where the move came from
+        if (has(byj, cur)) {  // jump over the pawn on ob, approached in direction `code`: unit edges src-ob and ob-cur
+            const int src = ob + back;
+            if (back == 9 || back == -9) mark(ve, src < ob ? src : ob); else mark(he, src < ob ? src : ob);
+            const int lo = cur < ob ? cur : ob, df = cur < ob ? ob - cur : cur - ob;
+            if (df == 9) mark(ve, lo); else mark(he, lo);
+            cur = src;
+        } else {
+            const int prev = cur + back;
+            if (back == 9 || back == -9) mark(ve, prev < cur ? prev : cur); else mark(he, prev < cur ? prev : cur);
             cur = prev;
-            continue;
         }
-        add_edge_cut(pc, prev, cur);
-        cur = prev;
     }
+    // vertical edge at (r,c): H walls in slots (r,c) [c < 8] and (r,c-1) [c > 0]; horizontal edge at (r,c): V walls in slots
+    // (r,c) [r < 8] and (r-1,c) [r > 0].  compress9to8 drops column 8 / row 8, the shifts drop column 0 / row 0.
+    pc.cutH = compress9to8(ve) | compress9to8(left1(andn(ve, b81(kCol0W, kCol0W, kCol0W))));
+    pc.cutV = compress9to8(he) | compress9to8(up9(he));
     return pc;
 }
 
@@ -267,7 +293,7 @@ AQ_DEV int pawn_moves(const Open &o, int p, int e, uint8_t *out) {
     const int delta[4] = {-9, 9, -1, 1};
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
-        const u128 od = d == 0 ? o.up : d == 1 ? o.down : d == 2 ? o.left : o.right;
+        const B81 od = d == 0 ? o.up : d == 1 ? o.down : d == 2 ? o.left : o.right;
         if (!has(od, p)) continue;
         const int q = p + delta[d];
         if (q != e) { out[n++] = (uint8_t)q; continue; }

@@ -28,7 +28,7 @@ int aq_check_launch(const char *what) {
     return 0;
 }
 
-extern "C" int aq_version(void) { return 100; }
+extern "C" int aq_version(void) { return AQ_VERSION; }
 extern "C" const char *aq_last_error_string(void) { return g_err; }
 
 using namespace aq;
@@ -117,7 +117,7 @@ legal_mask_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__res
             // un-rotated frame (start en, obstacle me, goal row 8) on sub-lane 1  (game_logic.py:332-348)
             PathCuts pc;
             pc.cutH = 0; pc.cutV = 0; pc.exists = 0;
-            if (sub < 2) pc = find_path_cuts(base, sub == 0 ? me : en, sub == 0 ? en : me, sub == 0 ? kRow0 : kRow8);
+            if (sub < 2) pc = find_path_cuts(base, sub == 0 ? me : en, sub == 0 ? en : me, sub == 0 ? goal_row0() : goal_row8());
             __syncwarp(gmask);
             u64 set[4];  // tasks: [mover H, mover V, opponent H, opponent V]
 #pragma unroll
@@ -150,7 +150,7 @@ legal_mask_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__res
                 const int slot = code & 63, orient = ((code >> 6) & 1) + 1, opp = code >> 7;
                 Open o = base;
                 add_wall(o, orient, slot);
-                const bool ok = opp ? reaches(o, en, me, kRow8) : reaches(o, me, en, kRow0);
+                const bool ok = opp ? reaches(o, en, me, goal_row8()) : reaches(o, me, en, goal_row0());
                 if (!ok) {
                     if (orient == 1) failH |= 1ull << slot; else failV |= 1ull << slot;
                 }
@@ -167,7 +167,7 @@ legal_mask_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__res
         const int n = pawn_moves(base, me, en, pm + 1);
         pm[0] = (uint8_t)n;
         u128 lo = 0;
-        for (int k = 0; k < n; ++k) lo |= bit81(pm[1 + k]);
+        for (int k = 0; k < n; ++k) lo |= (u128)1 << pm[1 + k];
         lo |= (u128)legalH << 81;                                  // H wall actions 81..144
         const u128 hi = (u128)(legalH >> 47) | ((u128)legalV << 17);  // V wall actions 145..208
         uint4 *m = reinterpret_cast<uint4 *>(mask + 8 * b);
@@ -223,7 +223,7 @@ legal_prepare_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__
     // (start en, obstacle me, goal row 8) on sub-lane 1  (game_logic.py:332-348)
     PathCuts pc;
     pc.cutH = 0; pc.cutV = 0; pc.exists = 1;
-    if (needH | needV) pc = find_path_cuts(base, sub == 0 ? me : en, sub == 0 ? en : me, sub == 0 ? kRow0 : kRow8);
+    if (needH | needV) pc = find_path_cuts(base, sub == 0 ? me : en, sub == 0 ? en : me, sub == 0 ? goal_row0() : goal_row8());
     __syncwarp();
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
@@ -276,7 +276,7 @@ legal_prepare_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__
                     const int orient = (q & 1) + 1;
                     Open o = base;
                     add_wall(o, orient, slot);
-                    const bool ok = (q >> 1) ? reaches(o, en, me, kRow8) : reaches(o, me, en, kRow0);
+                    const bool ok = (q >> 1) ? reaches(o, en, me, goal_row8()) : reaches(o, me, en, goal_row0());
                     if (!ok) { if (orient == 1) failH |= 1ull << slot; else failV |= 1ull << slot; }
                 }
         const unsigned pm2 = 3u << (lane & ~1);
@@ -290,7 +290,7 @@ legal_prepare_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__
         const int n = pawn_moves(base, me, en, pm + 1);
         pm[0] = (uint8_t)n;
         u128 lo = 0;
-        for (int k = 0; k < n; ++k) lo |= bit81(pm[1 + k]);
+        for (int k = 0; k < n; ++k) lo |= (u128)1 << pm[1 + k];
         lo |= (u128)legalH << 81;                                  // H wall actions 81..144
         const u128 hi = (u128)(legalH >> 47) | ((u128)legalV << 17);  // V wall actions 145..208
         uint4 *m = reinterpret_cast<uint4 *>(mask + 8 * b);
@@ -321,7 +321,7 @@ legal_search_kernel(const AqState *__restrict__ states, const uint32_t *tasks, c
         Open o = open_from_walls(s.hwalls, s.vwalls);
         add_wall(o, orient, slot);
         const int me = s.ppos, en = 80 - (int)s.epos;
-        const bool ok = opp ? reaches(o, en, me, kRow8) : reaches(o, me, en, kRow0);
+        const bool ok = opp ? reaches(o, en, me, goal_row8()) : reaches(o, me, en, goal_row0());
         if (!ok) {
             const int a = AQ_SQUARES + (orient == 2 ? AQ_SLOTS : 0) + slot;
             atomicAnd(mask + 8 * b + (a >> 5), ~(1u << (a & 31)));
@@ -387,8 +387,8 @@ shortest_paths_kernel(const AqState *__restrict__ states, int64_t B, int16_t *__
     const AqState s = load_state(states + b);
     const Open o = open_from_walls(s.hwalls, s.vwalls);
     const int me = s.ppos, en = 80 - (int)s.epos;
-    const int dp = path_length(o, me, en, kRow0);
-    const int de = path_length(o, en, me, kRow8);
+    const int dp = path_length(o, me, en, goal_row0());
+    const int de = path_length(o, en, me, goal_row8());
     if (dist) *reinterpret_cast<short2 *>(dist + 2 * b) = make_short2((short)dp, (short)de);
     if (heur) heur[b] = (double)(de - dp) / (double)kMaxDistFromGoal;
     if (leaf48) {
@@ -442,7 +442,7 @@ __global__ void build_graph_kernel(const AqState *__restrict__ states, int64_t B
     if (b >= B) return;
     const AqState s = load_state(states + b);
     const Open o = open_from_walls(s.hwalls, s.vwalls);
-    const u128 eh = expand8to9(s.hwalls), ev = expand8to9(s.vwalls);
+    const B81 eh = expand8to9(s.hwalls), ev = expand8to9(s.vwalls);
     int edges = 0;
     for (int v = lane; v < AQ_SQUARES; v += 32) {
         const int m = (int)has(o.up, v) | ((int)has(o.down, v) << 1) | ((int)has(o.left, v) << 2) | ((int)has(o.right, v) << 3);
@@ -510,10 +510,24 @@ __global__ void edges_to_open_mask_kernel(const int64_t *__restrict__ src, const
         else if (diff == -1 && v % AQ_N != 0) d = 2;
         else if (diff == 1 && v % AQ_N != AQ_N - 1) d = 3;
     }
-    if (d < 0) { atomicExch(bad, 1); return; }
+    if (d < 0) { atomicMax(bad, 1); return; }
     // byte v of board b inside a word array (4 bytes per word)
     const int64_t byte = b * AQ_SQUARES + v;
     atomicOr(open_words + (byte >> 2), (1u << d) << (8 * (int)(byte & 3)));
+}
+
+// GCNConv normalises with the in-degree at the TARGET node (gcn_norm, flow = source_to_target); the kernels use the degree
+// 1 + popcount(open directions) of the node itself.  The two agree exactly when every edge has its reverse, which holds for every
+// board graph (is_wall_blocking is symmetric, game_logic.py:145-167).  A caller-supplied edge_index that is not symmetric would be
+// evaluated differently from GCNConv, so it is rejected: bad[0] = 2.
+__global__ void open_mask_symmetry_kernel(const uint8_t *__restrict__ open_mask, int64_t B, int32_t *__restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * AQ_SQUARES) return;
+    const int m = open_mask[i];
+    const int delta[4] = {-9, 9, -1, 1};
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+        if (((m >> d) & 1) && !((open_mask[i + delta[d]] >> (d ^ 1)) & 1)) atomicMax(bad, 2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -544,12 +558,10 @@ extern "C" int aq_legal_mask_ws(const AqState *states, int64_t B, uint32_t *mask
                                 void *stream) {
     if (B < 0 || (B > 0 && (!states || !mask || !pawn))) return aq_set_error(AQ_ERR_ARG, "aq_legal_mask");
     if (B == 0) return 0;
-    const char *env = getenv("AQ_LEGAL_LANES");  // experiments only: force the one-kernel form with 2 / 8 / 32 lanes per state
-    const int env_lanes = env ? atoi(env) : 0;
-    // measured on B200 (scripts/legal_lanes.py, gpurun_out/legal_lanes.log): up to 4,096 states one kernel with many lanes per
-    // state has the shorter critical path; above, the two-phase form wins (45 vs 66 us at 16K, 1.22 vs 2.19 ms at 1M)
-    if (!ws || env_lanes || B <= 4096) {
-        const int lanes = env_lanes ? env_lanes : (B <= 1024 ? 32 : B <= 16384 ? 8 : 2);
+    // measured on B200 (scripts/legal_lanes.py, profiles/): up to 4,096 states one kernel with many lanes per state has the
+    // shorter critical path; above, the two-phase form wins
+    if (!ws || B <= 4096) {
+        const int lanes = B <= 1024 ? 32 : B <= 16384 ? 8 : 2;
         if (lanes == 32)
             legal_mask_kernel<32><<<blocks_for(B, kLegalWarps * 1), kLegalWarps * 32, 0, S(stream)>>>(states, B, mask, pawn);
         else if (lanes == 8)
@@ -631,7 +643,10 @@ extern "C" int aq_edges_to_open_mask(const int64_t *src, const int64_t *dst, int
     if (e != cudaSuccess) return aq_set_error((int)e, "aq_edges_to_open_mask");
     if (E == 0) return 0;
     edges_to_open_mask_kernel<<<blocks_for(E, 256), 256, 0, S(stream)>>>(src, dst, E, B, reinterpret_cast<unsigned *>(open_mask), bad);
-    return aq_check_launch("aq_edges_to_open_mask");
+    const int rc = aq_check_launch("aq_edges_to_open_mask");
+    if (rc) return rc;
+    open_mask_symmetry_kernel<<<blocks_for(B * AQ_SQUARES, 256), 256, 0, S(stream)>>>(open_mask, B, bad);
+    return aq_check_launch("aq_edges_to_open_mask(symmetry)");
 }
 
 extern "C" int aq_shortest_paths(const AqState *states, int64_t B, int16_t *dist, double *heuristic, int32_t *leaf48,

@@ -448,9 +448,7 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
 // ------------------------------------------------------------------------------------------
 extern "C" int64_t aq_gnn_backward_ws_floats(int64_t B) { return BwdWs{B}.total(); }
 
-int aq_gcn_backward_tc(const float *params, float *saved, const float *dg, int64_t B, float *partial, cudaStream_t st);   // gnn_tc_bwd.cu
 int aq_gcn_backward_tc2(const float *params, float *saved, const float *dg, int64_t B, float *partial, cudaStream_t st);  // gnn_tc2_bwd.cu
-int aq_train_tc_version();                                                                                             // gnn_tc.cu
 
 extern "C" int aq_gnn_backward(const float *params, const float *saved, const float *dpolicy, const float *dvalue,
                                int64_t B, float *grads, float *workspace, int precision, void *stream) {
@@ -473,10 +471,7 @@ extern "C" int aq_gnn_backward(const float *params, const float *saved, const fl
     int rc = aq_check_launch("heads_backward_kernel");
     if (rc) return rc;
     if (precision == 1) {  // tensor-core trunk backward: fills the GCN ranges of every partial slot itself
-        if (aq_train_tc_version() == 2)
-            rc = aq_gcn_backward_tc2(params, const_cast<float *>(saved), workspace + W.dg(), B, workspace + W.partial(), st);
-        else
-            rc = aq_gcn_backward_tc(params, const_cast<float *>(saved), workspace + W.dg(), B, workspace + W.partial(), st);
+        rc = aq_gcn_backward_tc2(params, const_cast<float *>(saved), workspace + W.dg(), B, workspace + W.partial(), st);
         if (rc) return rc;
     } else {
         gcn_backward_kernel<<<kSlots, kGcnThreads, sizeof(GcnBwdSmem), st>>>(params, saved, B, workspace);
@@ -486,7 +481,7 @@ extern "C" int aq_gnn_backward(const float *params, const float *saved, const fl
     AtbJobs jobs;
     int nj = 0;
     // head jobs: one row chunk per 64 boards (at most kSlots); node-level jobs: kSlots chunks
-    static const int chunk_rows = getenv("AQ_HEAD_CHUNK_ROWS") ? atoi(getenv("AQ_HEAD_CHUNK_ROWS")) : 64;  // env: experiments only
+    constexpr int chunk_rows = 64;
     const int head_slots = (int)std::min<int64_t>(kSlots, (B + chunk_rows - 1) / chunk_rows);
     auto add = [&](const float *A, int lda, int M, const float *Bm, int ldb, int N, int64_t R, int off, int bias_off = -1) {
         jobs.job[nj++] = AtbJob{A, lda, M, Bm, ldb, N, R, off, R == B ? head_slots : kSlots, bias_off};

@@ -3,9 +3,9 @@
 //                             iteration, all activations resident in shared memory
 //   heads_forward_kernel    : policy / value MLPs, softmax, tanh, optional legal-action
 //                             renormalisation (BaseNetwork.predict semantics)
-#include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include "gnn_fp32.cuh"
 
 using namespace aq;
@@ -282,18 +282,17 @@ static int set_smem(K kernel, size_t bytes) {
     return e == cudaSuccess ? 0 : (int)e;
 }
 
-int aq_gcn_forward_tc(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, float *saved,
-                      cudaStream_t st, bool after_legal);  // gnn_tc.cu
+int aq_gcn_forward_tc2(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, float *saved,
+                       cudaStream_t st, bool after_legal);  // gnn_tc2.cu
 int aq_heads_forward_tc(const float *params, const void *prepared, const float *pooled, int64_t B, float *policy, float *value,
                         const uint32_t *legal_mask, float *saved, bool pdl, cudaStream_t st);  // heads_tc.cu
-int aq_train_tc_version();                                                           // gnn_tc.cu
 
 static int launch_trunk(const float *params, const void *prepared, const AqState *states, const float *x,
                         const uint8_t *open_mask, int64_t B, float *pooled, float *saved, int precision, cudaStream_t st,
                         bool after_legal = false) {
     if (precision == 1) {
         if (!states) return aq_set_error(AQ_ERR_UNSUPPORTED, "aq_gnn_forward(bf16 path needs packed states)");
-        return aq_gcn_forward_tc(params, prepared, states, B, pooled, saved, st, after_legal);
+        return aq_gcn_forward_tc2(params, prepared, states, B, pooled, saved, st, saved ? false : after_legal);
     }
     const unsigned grid = (unsigned)(B < num_sms() ? B : num_sms());
     int rc;
@@ -310,7 +309,7 @@ static int launch_trunk(const float *params, const void *prepared, const AqState
 static int launch_heads(const float *params, const void *prepared, const float *pooled, int64_t B, float *policy,
                         float *value, const uint32_t *legal_mask, float *saved, int precision, cudaStream_t st, bool after_trunk = false) {
     // tensor-core heads: inference, and the training forward of the version-2 pair (hidden activations etc. saved by the kernel)
-    if (precision == 1 && (!saved || (aq_train_tc_version() == 2 && !legal_mask)))
+    if (precision == 1 && (!saved || !legal_mask))
         return aq_heads_forward_tc(params, prepared, pooled, B, policy, value, legal_mask, saved, after_trunk, st);
     const int64_t hb = (B + 7) / 8;
     const unsigned hgrid = (unsigned)(hb < num_sms() ? hb : num_sms());
@@ -429,13 +428,12 @@ struct AqHostKey {
 constexpr int kHostGraphSlots = 8;
 struct AqHostPending {  // a batch between aq_leaf_eval_host_compact_submit and _wait
     bool active = false;
-    int64_t B = 0, per = 0, priors_capacity = 0;
-    int used = 0;
-    float *priors_host = nullptr, *d_compact = nullptr;
+    int64_t B = 0, priors_capacity = 0, copied = 0;
+    int elem = 4;  // bytes per ragged prior on the wire
+    void *priors_host = nullptr;
+    unsigned char *d_compact = nullptr;
     int32_t *offsets_host = nullptr;
     cudaStream_t origin = nullptr;
-    std::chrono::steady_clock::time_point t_begin;
-    double t_front = 0;
 };
 struct AqHostCtx {
     cudaStream_t s[2];
@@ -444,14 +442,14 @@ struct AqHostCtx {
     AqHostKey key[kHostGraphSlots];
     cudaGraphExec_t exec[kHostGraphSlots];
     int n_graphs, next_slot;
-    bool graphs_ok;
+    int64_t est_per_board_x1024 = 0;  // running estimate of legal actions per board (x1024) that sizes the ragged priors copy; 0 = none yet
+    int64_t short_copies = 0;         // batches that needed a second copy
 };
 
 extern "C" int aq_host_ctx_create(void **ctx) {
     if (!ctx) return aq_set_error(AQ_ERR_ARG, "aq_host_ctx_create");
     AqHostCtx *c = new AqHostCtx();
     c->n_graphs = c->next_slot = 0;
-    c->graphs_ok = getenv("AQ_HOST_GRAPH") ? atoi(getenv("AQ_HOST_GRAPH")) != 0 : true;
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&c->s[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);
@@ -565,12 +563,10 @@ extern "C" int aq_leaf_eval_host(const float *params, const void *prepared, cons
     const AqHostKey k{params, prepared, states_host, priors_host, value_host, mask_host, pawn_host, dev_ws, B, precision};
     // with a context, batches >= 4096 are split in two so that the D2H of the first half overlaps the kernels of the second; when all
     // host buffers are pinned the whole pipeline is one CUDA graph per argument tuple (~40 API calls -> one launch)
-    static const int env_chunks = getenv("AQ_HOST_CHUNKS") ? atoi(getenv("AQ_HOST_CHUNKS")) : 0;
-    int nchunk = (ctx && B >= 4096) ? (env_chunks > 0 ? env_chunks : 2) : 1;  // measured: 2 chunks beat 1, 3, 4 and 6 at B = 16384
-    if (nchunk > kHostMaxChunks) nchunk = kHostMaxChunks;
+    const int nchunk = (ctx && B >= 4096) ? 2 : 1;  // measured: 2 chunks beat 1, 3, 4 and 6 at B = 16384
     cudaError_t e = cudaSuccess;
     cudaGraphExec_t exec = nullptr;
-    if (ctx && ctx->graphs_ok && is_pinned_host(states_host) && is_pinned_host(priors_host) && is_pinned_host(value_host) &&
+    if (ctx && is_pinned_host(states_host) && is_pinned_host(priors_host) && is_pinned_host(value_host) &&
         is_pinned_host(mask_host) && is_pinned_host(pawn_host))
         exec = host_graph_for(ctx, nchunk, k);
     if (exec) {
@@ -638,9 +634,11 @@ legal_count_scan_kernel(const uint32_t *__restrict__ mask, int64_t B, int32_t *_
 
 // One warp per board: every legal action's probability goes to its rank in legal_actions() order
 // (pawn list order, then per wall slot H before V -- game_logic.py:103-117, 350-357).
+// T = float (the bits of the dense priors) or __half (16-bit wire format of the host path, round to nearest even).
+template <typename T>
 __global__ void __launch_bounds__(256)
 compact_priors_kernel(const float *__restrict__ priors, const uint32_t *__restrict__ mask, const uint8_t *__restrict__ pawn,
-                      const int32_t *__restrict__ offsets, int64_t B, float *__restrict__ compact) {
+                      const int32_t *__restrict__ offsets, int64_t B, T *__restrict__ compact) {
     const int lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (b >= B) return;
@@ -655,7 +653,7 @@ compact_priors_kernel(const float *__restrict__ priors, const uint32_t *__restri
     const u64 legalV = (hi2 >> 17) | (top << 47);            // bit s = action 145 + s
     const uint2 pw = __ldg(reinterpret_cast<const uint2 *>(pawn + 8 * b));
     const int np = pw.x & 0xFF;
-    float *out = compact + offsets[b];
+    T *out = compact + offsets[b];
     const float *p = priors + (int64_t)kP * b;
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
@@ -674,91 +672,92 @@ compact_priors_kernel(const float *__restrict__ priors, const uint32_t *__restri
             const u64 below = (1ull << slot) - 1ull;
             rank = np + __popcll(legalH & below) + __popcll(legalV & below) + (isV ? (int)((legalH >> slot) & 1) : 0);
         }
-        out[rank] = __ldg(p + a);
+        if constexpr (sizeof(T) == 4) out[rank] = __ldg(p + a);
+        else out[rank] = __float2half_rn(__ldg(p + a));
     }
+}
+
+static int compact_priors_impl(const float *priors, const uint32_t *mask, const uint8_t *pawn, int64_t B, int32_t *offsets, void *compact,
+                               int wire, cudaStream_t st) {
+    legal_count_scan_kernel<<<1, 1024, 0, st>>>(mask, B, offsets);
+    int rc = aq_check_launch("aq_compact_priors(scan)");
+    if (rc || B == 0) return rc;
+    if (wire == AQ_WIRE_F16)
+        compact_priors_kernel<__half><<<(unsigned)((B + 7) / 8), 256, 0, st>>>(priors, mask, pawn, offsets, B, reinterpret_cast<__half *>(compact));
+    else
+        compact_priors_kernel<float><<<(unsigned)((B + 7) / 8), 256, 0, st>>>(priors, mask, pawn, offsets, B, reinterpret_cast<float *>(compact));
+    return aq_check_launch("aq_compact_priors");
 }
 
 extern "C" int aq_compact_priors(const float *priors, const uint32_t *mask, const uint8_t *pawn, int64_t B, int32_t *offsets,
                                  float *compact, void *stream) {
     if (B < 0 || !offsets || (B > 0 && (!priors || !mask || !pawn || !compact))) return aq_set_error(AQ_ERR_ARG, "aq_compact_priors");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    legal_count_scan_kernel<<<1, 1024, 0, st>>>(mask, B, offsets);
-    int rc = aq_check_launch("aq_compact_priors(scan)");
-    if (rc || B == 0) return rc;
-    compact_priors_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(priors, mask, pawn, offsets, B, compact);
-    return aq_check_launch("aq_compact_priors");
+    return compact_priors_impl(priors, mask, pawn, B, offsets, compact, AQ_WIRE_F32, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // Host-buffer leaf evaluation with predict()-shaped output.  Device workspace: the dense workspace of
-// aq_leaf_eval_host followed by offsets int32[B + chunks] and compact f32[B * 136].
-constexpr int kCompactMaxChunks = kHostMaxChunks;
+// aq_leaf_eval_host followed by offsets int32[B + 1] and compact [B * 136] (4 bytes per entry reserved).
 extern "C" int64_t aq_leaf_eval_host_compact_ws_bytes(int64_t B) {
-    return aq_leaf_eval_host_ws_bytes(B) + (int64_t)align256((size_t)(B + kCompactMaxChunks) * 4) +
-           (int64_t)align256((size_t)B * AQ_MAX_LEGAL * 4);
+    return aq_leaf_eval_host_ws_bytes(B) + (int64_t)align256((size_t)(B + 8) * 4) + (int64_t)align256((size_t)B * AQ_MAX_LEGAL * 4);
 }
 
-// The call is split in two so that a caller can keep several batches in flight (one context and one workspace per batch):
-//   submit: fork the worker streams, enqueue every chunk's H2D, kernels and fixed-size results -- returns without waiting;
-//   wait:   as each chunk's offsets reach the host, copy exactly that many probabilities behind the previous chunk's, rebase the
-//           offsets, join and synchronise.
+// The call is split in two so that a caller can keep several batches in flight (one context, workspace and set of host buffers per
+// batch):
+//   submit: H2D of the packed states, legal mask + trunk + heads, the scan of the legal counts and the compaction, then EVERY
+//           result copy of the batch -- offsets, value, optionally mask / pawn, and the ragged priors -- behind the kernels on one
+//           worker stream.  The ragged array's length is only known on the device, so the priors copy is sized by a running estimate
+//           the context keeps (the largest recent total plus a margin, the full capacity on the first call): no host round trip in
+//           the middle of a batch;
+//   wait:   one event synchronisation; in the rare case that the batch held more legal actions than the estimate, the remainder is
+//           copied and waited for here.
 // aq_leaf_eval_host_compact = submit + wait.
 extern "C" int aq_leaf_eval_host_compact_submit(const float *params, const void *prepared, const AqState *states_host, int64_t B,
-                                                float *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,
-                                                uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision, void *host_ctx,
-                                                void *stream) {
-    if (B < 0 || !params || !offsets_host || !host_ctx || (B > 0 && (!states_host || !priors_host || !value_host || !dev_ws)))
+                                                void *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,
+                                                uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision, int wire,
+                                                void *host_ctx, void *stream) {
+    if (B < 0 || !params || !offsets_host || !host_ctx || (B > 0 && (!states_host || !priors_host || !value_host || !dev_ws)) ||
+        (wire != AQ_WIRE_F32 && wire != AQ_WIRE_F16))
         return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host_compact");
     AqHostCtx *ctx = reinterpret_cast<AqHostCtx *>(host_ctx);
     if (ctx->pending.active) return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host_compact_submit(a batch is already in flight on this context)");
     AqHostPending &pd = ctx->pending;
     pd = AqHostPending{};
     pd.active = true; pd.B = B; pd.priors_host = priors_host; pd.priors_capacity = priors_capacity; pd.offsets_host = offsets_host;
+    pd.elem = wire == AQ_WIRE_F16 ? 2 : 4;
     pd.origin = reinterpret_cast<cudaStream_t>(stream);
-    pd.t_begin = std::chrono::steady_clock::now();
     if (B == 0) return 0;
-    cudaStream_t origin = pd.origin;
     unsigned char *p = reinterpret_cast<unsigned char *>(dev_ws);
     AqState *d_states = reinterpret_cast<AqState *>(p); p += align256((size_t)B * sizeof(AqState));
     float *d_priors = reinterpret_cast<float *>(p);     p += align256((size_t)B * kP * 4);
     float *d_value = reinterpret_cast<float *>(p);      p += align256((size_t)B * 4);
     uint32_t *d_mask = reinterpret_cast<uint32_t *>(p); p += align256((size_t)B * 32);
     uint8_t *d_pawn = reinterpret_cast<uint8_t *>(p);   p += align256((size_t)B * 8);
-    unsigned char *d_chunk_ws = p;                      p += host_ws_region_bytes(B);
-    int32_t *d_offsets = reinterpret_cast<int32_t *>(p); p += align256((size_t)(B + kCompactMaxChunks) * 4);
-    pd.d_compact = reinterpret_cast<float *>(p);
+    unsigned char *d_leaf_ws = p;                       p += host_ws_region_bytes(B);
+    int32_t *d_offsets = reinterpret_cast<int32_t *>(p); p += align256((size_t)(B + 8) * 4);
+    pd.d_compact = p;
 
-    // One chunk per batch by default (measured at B = 16,384: a synchronous caller gets 37.2 M evals/s with one chunk and 36.6 M
-    // with two -- the half-size kernels are less efficient by what the overlap gains -- and two batches in flight get 70.5 M
-    // against 67.4 M); AQ_HOST_CHUNKS = n splits a batch >= 4096 into n pipelined chunks.
-    static const int env_chunks = getenv("AQ_HOST_CHUNKS") ? atoi(getenv("AQ_HOST_CHUNKS")) : 0;
-    int nchunk = (B >= 4096 && env_chunks > 0) ? env_chunks : 1;
-    if (nchunk > kCompactMaxChunks) nchunk = kCompactMaxChunks;
-    const int64_t per = pd.per = ((B + nchunk - 1) / nchunk + 127) / 128 * 128;
-    cudaError_t e = cudaEventRecord(ctx->ready, origin);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(ctx->s[i], ctx->ready, 0);
-    if (e != cudaSuccess) { pd.active = false; return aq_set_error((int)e, "aq_leaf_eval_host_compact(fork)"); }
-    // front half of every chunk: H2D, kernels, the fixed-size results and the chunk's offsets (its last entry = its total)
-    for (int c = 0; c < nchunk; ++c) {
-        const int64_t lo = (int64_t)c * per, n = (lo + per <= B ? per : B - lo);
-        if (n <= 0) break;
-        pd.used = c + 1;
-        cudaStream_t cs = ctx->s[c & 1];
-        int32_t *d_off = d_offsets + lo + c;  // n + 1 entries per chunk
-        e = cudaMemcpyAsync(d_states + lo, states_host + lo, (size_t)n * sizeof(AqState), cudaMemcpyHostToDevice, cs);
-        int rc = e != cudaSuccess ? aq_set_error((int)e, "aq_leaf_eval_host_compact(H2D)") : 0;
-        if (!rc) rc = aq_leaf_eval(params, prepared, d_states + lo, n, d_priors + lo * kP, d_value + lo, d_mask + lo * 8, d_pawn + lo * 8,
-                                   reinterpret_cast<float *>(d_chunk_ws + (size_t)c * host_chunk_ws_bytes(per)), precision, cs);
-        if (!rc) rc = aq_compact_priors(d_priors + lo * kP, d_mask + lo * 8, d_pawn + lo * 8, n, d_off, pd.d_compact + lo * AQ_MAX_LEGAL, cs);
-        if (rc) { pd.active = false; return rc; }
-        // the chunk-local INCLUSIVE ends land in offsets_host[lo ...]; wait() rebases them once the totals are known
-        e = cudaMemcpyAsync(offsets_host + lo, d_off + 1, (size_t)n * 4, cudaMemcpyDeviceToHost, cs);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(value_host + lo, d_value + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, cs);
-        if (e == cudaSuccess && mask_host) e = cudaMemcpyAsync(mask_host + lo * 8, d_mask + lo * 8, (size_t)n * 32, cudaMemcpyDeviceToHost, cs);
-        if (e == cudaSuccess && pawn_host) e = cudaMemcpyAsync(pawn_host + lo * 8, d_pawn + lo * 8, (size_t)n * 8, cudaMemcpyDeviceToHost, cs);
-        if (e == cudaSuccess) e = cudaEventRecord(ctx->chunk_done[c], cs);
-        if (e != cudaSuccess) { pd.active = false; return aq_set_error((int)e, "aq_leaf_eval_host_compact(D2H)"); }
-    }
-    pd.t_front = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - pd.t_begin).count();
+    cudaStream_t cs = ctx->s[0];
+    cudaError_t e = cudaEventRecord(ctx->ready, pd.origin);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ctx->ready, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_states, states_host, (size_t)B * sizeof(AqState), cudaMemcpyHostToDevice, cs);
+    int rc = e != cudaSuccess ? aq_set_error((int)e, "aq_leaf_eval_host_compact(H2D)") : 0;
+    if (!rc) rc = aq_leaf_eval(params, prepared, d_states, B, d_priors, d_value, d_mask, d_pawn, reinterpret_cast<float *>(d_leaf_ws), precision, cs);
+    if (!rc) rc = compact_priors_impl(d_priors, d_mask, d_pawn, B, d_offsets, pd.d_compact, wire, cs);
+    if (rc) { pd.active = false; return rc; }
+    // how many ragged entries to copy without knowing the total: the context's running estimate, capped by what can exist and by
+    // the caller's buffer (a too-small buffer is reported by wait(), which knows the total)
+    const int64_t most = B * AQ_MAX_LEGAL;
+    int64_t est = ctx->est_per_board_x1024 > 0 ? (B * ctx->est_per_board_x1024 + 1023) / 1024 + 2048 : most;
+    if (est > most) est = most;
+    if (est > priors_capacity) est = priors_capacity;
+    pd.copied = est;
+    e = cudaMemcpyAsync(offsets_host, d_offsets, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(value_host, d_value, (size_t)B * 4, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess && mask_host) e = cudaMemcpyAsync(mask_host, d_mask, (size_t)B * 32, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess && pawn_host) e = cudaMemcpyAsync(pawn_host, d_pawn, (size_t)B * 8, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess && est > 0) e = cudaMemcpyAsync(priors_host, pd.d_compact, (size_t)est * pd.elem, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->chunk_done[0], cs);
+    if (e != cudaSuccess) { pd.active = false; return aq_set_error((int)e, "aq_leaf_eval_host_compact(D2H)"); }
     return 0;
 }
 
@@ -768,52 +767,46 @@ extern "C" int aq_leaf_eval_host_compact_wait(void *host_ctx) {
     AqHostPending &pd = ctx->pending;
     if (!pd.active) return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host_compact_wait(nothing in flight)");
     pd.active = false;
-    const int64_t B = pd.B, per = pd.per;
-    int32_t *offsets_host = pd.offsets_host;
-    if (B == 0) { offsets_host[0] = 0; return 0; }
-    static const bool trace = getenv("AQ_HOST_TRACE") != nullptr;  // host-side timestamps of the pipeline on stderr (scripts/e2e_trace.py)
-    auto us_since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - pd.t_begin).count(); };
-    double t_sync[kCompactMaxChunks] = {0}, t_issue[kCompactMaxChunks] = {0};
-    cudaError_t e = cudaSuccess;
-    int64_t base = 0;
-    for (int c = 0; c < pd.used; ++c) {
-        const int64_t lo = (int64_t)c * per, n = (lo + per <= B ? per : B - lo);
-        e = cudaEventSynchronize(ctx->chunk_done[c]);
-        if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(sync)");
-        t_sync[c] = us_since();
-        const int64_t total = offsets_host[lo + n - 1];
-        if (base + total > pd.priors_capacity) return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host_compact(priors_capacity too small)");
-        if (total > 0) {
-            e = cudaMemcpyAsync(pd.priors_host + base, pd.d_compact + lo * AQ_MAX_LEGAL, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->s[c & 1]);
-            if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(D2H priors)");
-        }
-        if (base) for (int64_t i = 0; i < n; ++i) offsets_host[lo + i] += (int32_t)base;
-        base += total;
-        t_issue[c] = us_since();
+    const int64_t B = pd.B;
+    if (B == 0) { pd.offsets_host[0] = 0; return 0; }
+    cudaStream_t cs = ctx->s[0];
+    // only this batch's own work is waited for (the worker stream), not whatever else the caller queued on `stream`
+    cudaError_t e = cudaEventSynchronize(ctx->chunk_done[0]);
+    if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(sync)");
+    const int64_t total = pd.offsets_host[B];
+    if (total > pd.priors_capacity) return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host_compact(priors_capacity too small)");
+    if (total > pd.copied) {  // more legal actions than estimated: fetch the rest now
+        e = cudaMemcpyAsync(reinterpret_cast<unsigned char *>(pd.priors_host) + (size_t)pd.copied * pd.elem,
+                            pd.d_compact + (size_t)pd.copied * pd.elem, (size_t)(total - pd.copied) * pd.elem, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+        if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(D2H remainder)");
+        ctx->short_copies++;
     }
-    // shift to the exclusive convention: offsets_host[b] = start of board b, offsets_host[B] = total
-    for (int64_t i = B; i > 0; --i) offsets_host[i] = offsets_host[i - 1];
-    offsets_host[0] = 0;
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-        e = cudaEventRecord(ctx->done[i], ctx->s[i]);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(pd.origin, ctx->done[i], 0);
-    }
-    // only this batch's own work is waited for (the worker streams), not whatever else the caller queued on `stream`
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamSynchronize(ctx->s[i]);
+    // running estimate of legal actions per board (x1024): jumps up to this batch's density + 3 %, decays by 1/64 per batch
+    const int64_t now = (total * 1024 + B - 1) / B;
+    const int64_t want = now + now / 32, decayed = ctx->est_per_board_x1024 - ctx->est_per_board_x1024 / 64;
+    ctx->est_per_board_x1024 = want > decayed ? want : decayed;
+    // later work on the caller's stream is ordered behind this batch
+    e = cudaStreamWaitEvent(pd.origin, ctx->chunk_done[0], 0);
     if (e != cudaSuccess) return aq_set_error((int)e, "aq_leaf_eval_host_compact(join)");
-    if (trace) {
-        fprintf(stderr, "[aq host trace] B=%lld chunks=%d front enqueued %.0f us;", (long long)B, pd.used, pd.t_front);
-        for (int c = 0; c < pd.used; ++c) fprintf(stderr, " chunk %d: results on host %.0f, priors copy issued %.0f;", c, t_sync[c], t_issue[c]);
-        fprintf(stderr, " all done %.0f us\n", us_since());
-    }
     return 0;
 }
 
-extern "C" int aq_leaf_eval_host_compact(const float *params, const void *prepared, const AqState *states_host, int64_t B,
-                                         float *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,
-                                         uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision, void *host_ctx,
+extern "C" int aq_leaf_eval_host_compact(const float *params, const void *prepared /* or NULL */, const AqState *states_host, int64_t B,
+                                         void *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,
+                                         uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision, int wire, void *host_ctx,
                                          void *stream) {
     const int rc = aq_leaf_eval_host_compact_submit(params, prepared, states_host, B, priors_host, priors_capacity, offsets_host, value_host,
-                                                    mask_host, pawn_host, dev_ws, precision, host_ctx, stream);
+                                                    mask_host, pawn_host, dev_ws, precision, wire, host_ctx, stream);
     return rc ? rc : aq_leaf_eval_host_compact_wait(host_ctx);
+}
+
+// Diagnostics of a host context: [0] = batches whose ragged priors needed a second copy (estimate too small), [1] = the current
+// estimate of legal actions per board x 1024.
+extern "C" int aq_host_ctx_stats(void *host_ctx, int64_t *out2) {
+    if (!host_ctx || !out2) return aq_set_error(AQ_ERR_ARG, "aq_host_ctx_stats");
+    AqHostCtx *ctx = reinterpret_cast<AqHostCtx *>(host_ctx);
+    out2[0] = ctx->short_copies;
+    out2[1] = ctx->est_per_board_x1024;
+    return 0;
 }

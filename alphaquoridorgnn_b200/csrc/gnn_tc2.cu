@@ -676,10 +676,8 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
 int aq_gcn_forward_tc2(const float *params, const void *prepared, const AqState *states, int64_t B, float *pooled, float *saved,
                        cudaStream_t st, bool after_legal) {
     static int sms = 0;
-    static uint32_t wait_ns = 0;
+    const uint32_t wait_ns = 0;  // suspend-time hint of the mbarrier waits (0 = spin; measured best)
     if (sms == 0) {
-        const char *env = getenv("AQ_TC_WAIT_NS");  // tuning knob: suspend-time hint of the mbarrier waits (0 = spin)
-        if (env) wait_ns = (uint32_t)atoi(env);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -188,7 +188,11 @@ def open_mask_from_edge_index(edge_index, num_graphs):
     with torch.cuda.device(dev):
         _lib.check(L.aq_edges_to_open_mask(_lib.ptr(ei[0]), _lib.ptr(ei[1]), ei.shape[1], num_graphs, _lib.ptr(buf),
                                            _lib.ptr(bad), _lib.stream_ptr(dev)), "aq_edges_to_open_mask")
-    if int(bad.item()) != 0:
+    code = int(bad.item())
+    if code == 2:
+        raise ValueError("edge_index is not symmetric: every edge of a board graph has its reverse (GCNConv's target-degree "
+                         "normalisation and the kernels' node-degree normalisation agree only then)")
+    if code != 0:
         raise ValueError("edge_index is not a 9x9 Quoridor board graph (edges must join 4-neighbours of one board)")
     return buf[: num_graphs * NUM_SQUARES].view(num_graphs, NUM_SQUARES)
 

@@ -55,6 +55,9 @@ class BatchedMCTS:
     def _buffers(self, G):
         if G not in self._buf:
             dev = self.device
+            if len(self._buf) >= 16:  # self-play shrinks G almost every ply: bound the cache; the captured graphs hold raw
+                self._buf.clear()     # pointers into these buffers, so both caches are dropped together
+                self._graphs.clear()
             self._buf[G] = {
                 "leaf": torch.empty((G, gl.STATE_BYTES), dtype=torch.uint8, device=dev),
                 "kind": torch.empty((G,), dtype=torch.int32, device=dev),
@@ -99,24 +102,26 @@ class BatchedMCTS:
                 prep = self.model.prepared_weights() if prec == 1 else None
                 key = (G, max_nodes, flat.data_ptr(), prep.data_ptr() if prep is not None else 0, prec)
                 graph = self._graphs.get(key) if self.use_graph else None
+                done = 0
                 if self.use_graph and graph is None:
+                    # warm-up outside capture (= simulation 1); a failure here is a real error and propagates
+                    self._step_network(ws, G, max_nodes, buf, flat, prep, prec, st)
+                    done = 1
+                    torch.cuda.synchronize(dev)
                     try:
-                        self._step_network(ws, G, max_nodes, buf, flat, prep, prec, st)  # warm-up outside capture (= simulation 1)
-                        done = 1
-                        torch.cuda.synchronize(dev)
                         g = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g):
                             self._step_network(ws, G, max_nodes, buf, flat, prep, prec, _lib.stream_ptr(dev))
-                        if len(self._graphs) >= 16:  # self-play shrinks G as games end: keep the cache bounded
+                        if len(self._graphs) >= 32:
                             self._graphs.clear()
                         self._graphs[key] = graph = g
+                    except _lib.AqError:
+                        raise
                     except Exception as e:  # capture unsupported: stay eager, but say so
                         import warnings
                         warnings.warn(f"CUDA-graph capture of the MCTS simulation step failed ({e!r}); running the step eagerly")
-                        self.use_graph, graph, done = False, None, 1
+                        self.use_graph, graph = False, None
                         torch.cuda.synchronize(dev)
-                else:
-                    done = 0
                 for _ in range(sims - done):
                     if graph is not None:
                         graph.replay()
@@ -151,14 +156,9 @@ def policy_from_counts(counts, temperature):
     return x / x.sum(dim=1, keepdim=True)
 
 
-def _as_evaluator(model):
-    """BatchedMCTS accepts a network or an evaluator callable directly."""
-    return model
-
-
 def pv_mcts_policy_batch(model, packed_roots, temperature, sims=None, device=None):
     """Batched pv_mcts_policy: -> (policy float64[G,136], actions int16[G,136], n_children int16[G])."""
-    mcts = BatchedMCTS(_as_evaluator(model), sims or PV_EVALUATE_COUNT, device=device)
+    mcts = BatchedMCTS(model, sims or PV_EVALUATE_COUNT, device=device)
     counts, actions, n = mcts.search(packed_roots)
     return policy_from_counts(counts, temperature), actions, n
 

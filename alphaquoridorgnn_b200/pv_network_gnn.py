@@ -336,32 +336,42 @@ class HostLeafEvaluator:
     """Batched ``predict`` for callers whose states and results live in HOST memory (a Python tree search such as the
     reference's pv_mcts.py Node tree, many games at once): one call moves B packed states to the GPU, evaluates them and
     brings back exactly what ``BaseNetwork.predict`` returns per state -- the probabilities of the legal actions only, in
-    ``state.legal_actions()`` order (BaseNetwork.py:36-40) -- as a ragged array, plus value, legal mask and pawn list.
+    ``state.legal_actions()`` order (BaseNetwork.py:36-40) -- as a ragged array, plus the values.
 
     Pinned host buffers, the device workspace and the worker streams are allocated once for ``max_batch``.
         ev = HostLeafEvaluator(net, 16384)
         ev.states[:B] = game_logic.pack_rows_host(rows, plies)      # fill the pinned input
-        out = ev.evaluate(B)   # dict of numpy views: priors [total], offsets [B+1], value [B], mask [B,8], pawn [B,8]
+        out = ev.evaluate(B)   # dict of numpy views: priors [total], offsets [B+1], value [B] (+ mask [B,8], pawn [B,8])
         p_b = out["priors"][out["offsets"][b]:out["offsets"][b + 1]]   # == predict(state_b)[0]
+
+    wire:      "f32" -- the ragged priors are the float32 bits of the dense priors (exact);
+               "f16" -- IEEE half on the wire and in the returned array (relative error <= 2^-12, well inside the stated
+                        bf16-path tolerance; halves the device -> host bytes, which bound the multi-GPU host path).
+    with_mask: also return the 256-bit legal masks and ordered pawn lists (the action ids of the ragged entries without a host
+               ``legal_actions()`` call); predict() itself returns only (policy, value).
+    dense:     the [B,209] matrix instead of the ragged array (aq_leaf_eval_host).
     """
 
-    def __init__(self, net, max_batch, dense=False):
+    def __init__(self, net, max_batch, dense=False, wire="f32", with_mask=True):
         import ctypes
         flat = net.flat_parameters()
         _lib.require_cuda(flat, "model parameters")
+        if wire not in ("f32", "f16") or (dense and wire != "f32"):
+            raise ValueError("wire must be 'f32' or 'f16' (ragged flavour only)")
         self.net, self.dev, self.max_batch, self.dense = net, flat.device, int(max_batch), bool(dense)
+        self.wire, self.with_mask = wire, bool(with_mask) or bool(dense)
         L = self.L = _lib.load()
         B = self.max_batch
         self.states = torch.empty((B, gl.STATE_BYTES), dtype=torch.uint8).pin_memory()
         self.value = torch.empty((B,), dtype=torch.float32).pin_memory()
-        self.mask = torch.empty((B, 8), dtype=torch.int32).pin_memory()
-        self.pawn = torch.empty((B, 8), dtype=torch.uint8).pin_memory()
+        self.mask = torch.empty((B, 8), dtype=torch.int32).pin_memory() if self.with_mask else None
+        self.pawn = torch.empty((B, 8), dtype=torch.uint8).pin_memory() if self.with_mask else None
         if dense:
             self.priors = torch.empty((B, POLICY_OUTPUT_SIZE), dtype=torch.float32).pin_memory()
             self.offsets = None
             nbytes = L.aq_leaf_eval_host_ws_bytes(B)
         else:
-            self.priors = torch.empty((B * gl.MAX_LEGAL,), dtype=torch.float32).pin_memory()
+            self.priors = torch.empty((B * gl.MAX_LEGAL,), dtype=torch.float16 if wire == "f16" else torch.float32).pin_memory()
             self.offsets = torch.empty((B + 1,), dtype=torch.int32).pin_memory()
             nbytes = L.aq_leaf_eval_host_compact_ws_bytes(B)
         self.ws = torch.empty((max(1, nbytes),), dtype=torch.uint8, device=self.dev)
@@ -418,15 +428,16 @@ class HostLeafEvaluator:
 
     def submit(self, B=None, states=None):
         """First half of ``evaluate`` (ragged flavour only): enqueue the copies and kernels of this batch and return at once.
-        A host that keeps two evaluators busy alternately -- ``a.submit(); b.submit(); a.wait(); a.submit(); b.wait(); ...`` --
-        hides each batch's transfers behind the other's kernels."""
+        A host that keeps several evaluators busy round-robin -- ``a.submit(); b.submit(); c.submit(); a.wait(); a.submit();
+        b.wait(); ...`` -- hides each batch's transfers and wake-up latency behind the others' kernels."""
         if self.dense:
             raise ValueError("submit/wait exist for the ragged (predict-shaped) flavour")
         B, p_states = self._args(B, states)
         p_pri, p_off, p_val, p_msk, p_pwn, p_ws, p_flat, p_prep, _ = self._fixed
         with torch.cuda.device(self.dev):
             _lib.check(self.L.aq_leaf_eval_host_compact_submit(p_flat, p_prep, p_states, B, p_pri, self.priors.numel(), p_off, p_val, p_msk,
-                                                               p_pwn, p_ws, self._prec, self._ctx, _lib.stream_ptr(self.dev)),
+                                                               p_pwn, p_ws, self._prec, 1 if self.wire == "f16" else 0, self._ctx,
+                                                               _lib.stream_ptr(self.dev)),
                        "aq_leaf_eval_host_compact_submit")
         self._inflight = B
 
@@ -439,15 +450,26 @@ class HostLeafEvaluator:
         with torch.cuda.device(self.dev):
             _lib.check(self.L.aq_leaf_eval_host_compact_wait(self._ctx), "aq_leaf_eval_host_compact_wait")
         off = self.offsets[:B + 1].numpy()
-        return {"priors": self.priors[:int(off[B])].numpy(), "offsets": off, "value": self.value[:B].numpy(),
-                "mask": self.mask[:B].numpy(), "pawn": self.pawn[:B].numpy()}
+        out = {"priors": self.priors[:int(off[B])].numpy(), "offsets": off, "value": self.value[:B].numpy()}
+        if self.with_mask:
+            out["mask"], out["pawn"] = self.mask[:B].numpy(), self.pawn[:B].numpy()
+        return out
+
+    def stats(self):
+        """(batches whose ragged copy had to be completed by a second copy, current estimate of legal actions per board)."""
+        import ctypes
+        out = (ctypes.c_int64 * 2)()
+        _lib.check(self.L.aq_host_ctx_stats(self._ctx, out), "aq_host_ctx_stats")
+        return int(out[0]), out[1] / 1024.0
 
     def d2h_bytes(self, out):
-        """Bytes that crossed PCIe device -> host for this result (for bench.py's e2e accounting)."""
+        """Bytes of RESULTS that crossed PCIe device -> host for this batch (for bench.py's e2e accounting; the ragged copy is sized
+        by an estimate, so up to ~3 % more than this may actually have moved)."""
         B = out["value"].shape[0]
+        extra = (32 + 8) if self.with_mask else 0
         if self.dense:
-            return B * (POLICY_OUTPUT_SIZE * 4 + 4 + 32 + 8)
-        return int(out["offsets"][B]) * 4 + B * (4 + 4 + 32 + 8)
+            return B * (POLICY_OUTPUT_SIZE * 4 + 4 + extra)
+        return int(out["offsets"][B]) * (2 if self.wire == "f16" else 4) + (B + 1) * 4 + B * (4 + extra)
 
 
 # Function to create the dual network

@@ -46,7 +46,7 @@ def play_batch(model, num_games, device=None, sims=None, temperature=SP_TEMPERAT
     dev = gl._dev(device)
     gen = torch.Generator(device=dev)
     gen.manual_seed(int(seed) if seed is not None else int(torch.seed() % (2 ** 31)))
-    mcts = pv_mcts.BatchedMCTS(pv_mcts._as_evaluator(model), sims or pv_mcts.PV_EVALUATE_COUNT, device=dev)
+    mcts = pv_mcts.BatchedMCTS(model, sims or pv_mcts.PV_EVALUATE_COUNT, device=dev)
     states = start_states(num_games, dev)
     game_id = torch.arange(num_games, device=dev)
     rec_state, rec_policy, rec_game = [], [], []

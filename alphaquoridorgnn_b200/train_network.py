@@ -66,6 +66,13 @@ class FlatTrainer:
         global batch of `global_batch` samples (b may be 0).  Returns the loss tensor [policy, value]
         contribution of this rank (already divided by the global batch size)."""
         L, P = _lib.load(), _lib.ptr
+        flat = self.model.flat_parameters()
+        if flat.data_ptr() != self.flat.data_ptr() or flat.device != self.flat.device:
+            # the module was moved (.to) or its storage replaced (load_state_dict(assign=True)) since the last step: follow it, keep
+            # the Adam moments (on the new device), so that the update does not go into an orphaned buffer
+            self.flat = flat
+            self.exp_avg, self.exp_avg_sq = self.exp_avg.to(flat.device), self.exp_avg_sq.to(flat.device)
+            self.grads, self.loss = torch.zeros_like(flat), torch.zeros(2, device=flat.device)
         dev = self.flat.device
         b = packed.shape[0]
         with torch.cuda.device(dev):

@@ -53,6 +53,7 @@ typedef struct AqState {
     uint64_t reserved; /* reserved, 0 */
 } AqState;
 
+#define AQ_VERSION 200 /* bumped with every change of a signature below; the ctypes loader refuses a library of another version */
 int aq_version(void);
 const char *aq_last_error_string(void);
 
@@ -96,8 +97,9 @@ int aq_build_graph(const AqState *states, int64_t B, uint8_t *open_mask, float *
  * (pv_network_gnn.py:53): edge_offset[B] = exclusive scan of edge_count; src/dst int64[E]. */
 int aq_build_edge_index(const uint8_t *open_mask, const int64_t *edge_offset, int64_t B, int64_t *src, int64_t *dst,
                         void *stream);
-/* Inverse, for callers that hand us (x, edge_index, batch): rebuild open masks; bad[0] is set
- * non-zero if an edge does not join 4-neighbours of one 9x9 board. */
+/* Inverse, for callers that hand us (x, edge_index, batch): rebuild open masks; bad[0] is set to 1 if an edge does not join
+ * 4-neighbours of one 9x9 board and to 2 if an edge lacks its reverse (the kernels take a node's own degree where GCNConv's
+ * gcn_norm takes the in-degree at the target; the two agree only on symmetric edge lists, which every board graph is). */
 int aq_edges_to_open_mask(const int64_t *src, const int64_t *dst, int64_t E, int64_t B, uint8_t *open_mask,
                           int32_t *bad, void *stream);
 
@@ -182,27 +184,37 @@ int aq_leaf_eval_host(const float *params, const void *prepared /* or NULL */, c
 int aq_compact_priors(const float *priors, const uint32_t *mask, const uint8_t *pawn, int64_t B, int32_t *offsets,
                       float *compact, void *stream);
 
-/* aq_leaf_eval_host with predict()-shaped output: H2D states, kernels, then only the legal actions' probabilities
- * travel back (4 bytes per legal action instead of 836 per board; the dense path is PCIe-bound).
- *   priors_host  [priors_capacity] f32 : ragged priors, board b at [offsets_host[b], offsets_host[b+1]);
- *                                        B*136 floats always suffice; AQ_ERR_ARG if the capacity is too small
- *   offsets_host [B+1] int32, value_host [B], mask_host [B,8] / pawn_host [B,8] (may be NULL)
- * host_ctx is required (worker streams and events).  The call synchronises: results are on the host on return
- * (only this batch's own work is waited for, not other work queued on `stream`).
- * dev_ws: aq_leaf_eval_host_compact_ws_bytes(B) bytes. */
-/* The same call in two halves, so that a host can keep several batches in flight (one host_ctx + dev_ws + set of host buffers per
- * batch, e.g. two pools of games evaluated alternately): _submit enqueues the copies and kernels and returns immediately; _wait
- * finishes the transfer of that context's batch and returns when its results are on the host.  One batch per context at a time. */
+/* aq_leaf_eval_host with predict()-shaped output (BaseNetwork.py:36-40, pv_network_cnn.py:128-135): H2D states, kernels, then
+ * only the legal actions' probabilities travel back (4 or 2 bytes per legal action instead of 836 per board; the dense path is
+ * PCIe-bound).
+ *   priors_host  [priors_capacity] : ragged priors, board b at [offsets_host[b], offsets_host[b+1]); f32 (wire = AQ_WIRE_F32: the
+ *                                    bits of the dense priors) or IEEE half (AQ_WIRE_F16: the same values rounded to nearest even,
+ *                                    |error| <= 2^-12 relative; halves the device -> host bytes).  B*136 entries always suffice;
+ *                                    AQ_ERR_ARG from _wait if the capacity is too small
+ *   offsets_host [B+1] int32, value_host [B]; mask_host [B,8] / pawn_host [B,8] are optional (NULL: not copied -- predict() itself
+ *                                    returns only (policy, value); callers that want the action ids without running
+ *                                    legal_actions() on the host ask for them)
+ * host_ctx is required (worker stream, events, and the running estimate that sizes the ragged copy -- see gnn_forward.cu).
+ * dev_ws: aq_leaf_eval_host_compact_ws_bytes(B) bytes.
+ * The call comes in two halves so that a host can keep several batches in flight (one host_ctx + dev_ws + set of host buffers per
+ * batch, e.g. three pools of games evaluated round-robin): _submit enqueues the copies and kernels and returns immediately; _wait
+ * returns when that context's results are on the host (one event wait; only this batch's own work is waited for, not other work
+ * queued on `stream`).  One batch per context at a time.  aq_leaf_eval_host_compact = _submit + _wait. */
+#define AQ_WIRE_F32 0
+#define AQ_WIRE_F16 1
 int aq_leaf_eval_host_compact_submit(const float *params, const void *prepared, const AqState *states_host, int64_t B,
-                                     float *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,
-                                     uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision, void *host_ctx,
-                                     void *stream);
+                                     void *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,
+                                     uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision, int wire,
+                                     void *host_ctx, void *stream);
 int aq_leaf_eval_host_compact_wait(void *host_ctx);
 int64_t aq_leaf_eval_host_compact_ws_bytes(int64_t B);
 int aq_leaf_eval_host_compact(const float *params, const void *prepared /* or NULL */, const AqState *states_host, int64_t B,
-                              float *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,
-                              uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision, void *host_ctx,
+                              void *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,
+                              uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision, int wire, void *host_ctx,
                               void *stream);
+/* Diagnostics of a host context: out2[0] = batches whose ragged priors needed a second copy (estimate too small),
+ * out2[1] = current estimate of legal actions per board x 1024. */
+int aq_host_ctx_stats(void *host_ctx, int64_t *out2);
 
 /* Lock-step PV-MCTS over G independent games (pv_mcts.py:20-95: Node.evaluate / next_child_node).
  * ws: device workspace of aq_mcts_ws_bytes(G, max_nodes); max_nodes >= 1 + sims * 133 never overflows.

@@ -32,8 +32,8 @@ extern "C" void emul_legal_mask(const AqState *states, long long B, uint32_t *ma
             legalV = ws.freeV;
             // same decision structure as legal_mask_kernel: witness paths first, a real search only for the
             // player whose witness the candidate cuts
-            const PathCuts pm_ = find_path_cuts(base, me, en, kRow0);
-            const PathCuts pe_ = find_path_cuts(base, en, me, kRow8);
+            const PathCuts pm_ = find_path_cuts(base, me, en, goal_row0());
+            const PathCuts pe_ = find_path_cuts(base, en, me, goal_row8());
             for (int slot = 0; slot < 64; ++slot)
                 for (int orient = 1; orient <= 2; ++orient) {
                     const u64 need = orient == 1 ? ws.needH : ws.needV;
@@ -42,8 +42,8 @@ extern "C" void emul_legal_mask(const AqState *states, long long B, uint32_t *ma
                     Open o = base;
                     add_wall(o, orient, slot);
                     bool ok = true;
-                    if (!pm_.exists || ((cm >> slot) & 1)) ok = ok && reaches(o, me, en, kRow0);
-                    if (!pe_.exists || ((ce >> slot) & 1)) ok = ok && reaches(o, en, me, kRow8);
+                    if (!pm_.exists || ((cm >> slot) & 1)) ok = ok && reaches(o, me, en, goal_row0());
+                    if (!pe_.exists || ((ce >> slot) & 1)) ok = ok && reaches(o, en, me, goal_row8());
                     if (ok) {
                         if (orient == 1) legalH |= 1ull << slot; else legalV |= 1ull << slot;
                     }
@@ -53,7 +53,7 @@ extern "C" void emul_legal_mask(const AqState *states, long long B, uint32_t *ma
         const int n = pawn_moves(base, me, en, pm + 1);
         pm[0] = (uint8_t)n;
         u128 lo = 0;
-        for (int k = 0; k < n; ++k) lo |= bit81(pm[1 + k]);
+        for (int k = 0; k < n; ++k) lo |= (u128)1 << pm[1 + k];
         lo |= (u128)legalH << 81;
         const u128 hi = (u128)(legalH >> 47) | ((u128)legalV << 17);
         uint32_t *m = mask + 8 * b;
@@ -76,7 +76,7 @@ extern "C" void emul_shortest_paths(const AqState *states, long long B, int16_t 
         const AqState s = states[b];
         const Open o = open_from_walls(s.hwalls, s.vwalls);
         const int me = s.ppos, en = 80 - (int)s.epos;
-        dist[2 * b] = (int16_t)path_length(o, me, en, kRow0);
-        dist[2 * b + 1] = (int16_t)path_length(o, en, me, kRow8);
+        dist[2 * b] = (int16_t)path_length(o, me, en, goal_row0());
+        dist[2 * b + 1] = (int16_t)path_length(o, en, me, goal_row8());
     }
 }

@@ -132,28 +132,31 @@ def test_gpu_generated_positions_match_oracle_at_scale():
     assert np.array_equal(_np(term), ref_flags)
 
 
-def test_legal_mask_every_form_agrees_with_reference(traj, monkeypatch):
-    """The one-kernel form at 2 / 8 / 32 lanes per state, the two-phase form with its recommended workspace and with a
-    workspace so small that most states overflow the task list and search in the first kernel: all bit-exact."""
+def test_legal_mask_every_form_agrees_with_reference(traj):
+    """The one-kernel form at 2 / 8 / 32 lanes per state (chosen by the batch size: <= 1,024 states 32 lanes, <= 16,384 eight,
+    above two), the two-phase form with its recommended workspace and with a workspace so small that most states overflow the
+    task list and search in the first kernel: all bit-exact."""
     from alphaquoridorgnn_b200 import _lib
     L = _lib.load()
     packed = gl.pack_rows(traj["rows"], traj["plies"])
     B = packed.shape[0]
     want_mask, want_pawn = traj["mask"], traj["pawn"]
 
-    def run(ws_bytes):
-        mask = torch.zeros((B, 8), dtype=torch.int32, device="cuda")
-        pawn = torch.zeros((B, 8), dtype=torch.uint8, device="cuda")
+    def run(ws_bytes, lo=0, hi=B):
+        n = hi - lo
+        mask = torch.zeros((n, 8), dtype=torch.int32, device="cuda")
+        pawn = torch.zeros((n, 8), dtype=torch.uint8, device="cuda")
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device="cuda") if ws_bytes else None
-        _lib.check(L.aq_legal_mask_ws(_lib.ptr(packed), B, _lib.ptr(mask), _lib.ptr(pawn), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
+        _lib.check(L.aq_legal_mask_ws(_lib.ptr(packed[lo:hi]), n, _lib.ptr(mask), _lib.ptr(pawn), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
                    "aq_legal_mask_ws")
-        assert np.array_equal(_np(mask).view(np.uint32), want_mask) and np.array_equal(_np(pawn), want_pawn)
+        assert np.array_equal(_np(mask).view(np.uint32), want_mask[lo:hi]) and np.array_equal(_np(pawn), want_pawn[lo:hi])
 
-    for lanes in ("2", "8", "32"):
-        monkeypatch.setenv("AQ_LEGAL_LANES", lanes)
-        run(0)
-    monkeypatch.delenv("AQ_LEGAL_LANES")
-    run(0)                                  # aq_legal_mask's form
+    run(0)                                  # one kernel, 2 lanes per state (54 k states)
+    for lo in range(0, B, 9000):
+        run(0, lo, min(B, lo + 9000))       # one kernel, 8 lanes per state
+    for lo in range(0, B, 7001):
+        run(0, lo, min(B, lo + 1000))       # one kernel, 32 lanes per state
+    run(L.aq_legal_mask_ws_bytes(3000), 100, 3100)   # small batches with a workspace still take the one-kernel form
     run(L.aq_legal_mask_ws_bytes(B))        # two-phase, everything through the list
     run(256 + 4096)                         # 1,024 list entries for 54k states: overflow path
     run(256 + 4 * 30000)
