@@ -44,14 +44,6 @@ using namespace aqtc;
 #define TC2_PREFETCH 1   // 1: fetch the next board's state one board ahead
 #endif
 
-#ifndef TC2_AGG_TMEM
-#define TC2_AGG_TMEM 0   // 0 (default): Z^T goes back into the shared-memory tile (SS-form aggregation); 4 groups of 96 columns, W2 and W3 in TMEM
-                         // 1 (measured alternative, 156 us against 143 us at B = 16,384): the aggregation's A operand (Z^T, fp16) lives in
-                         //    TENSOR MEMORY (TS form) -- the Z epilogue is a tcgen05.st, the aggregation MMAs read no A bytes from shared
-                         //    memory (1,000 instead of 1,300 cycles per aggregation) -- but 144 columns per board leave room for 3 boards in
-                         //    flight instead of 4 (W3 in TMEM, W2 as a shared-memory operand) and the per-board chain (7,800 cycles, 40 %
-                         //    of them epilogue instructions) is not hidden any more.  scripts/tc2_timing.py has the per-phase cycles.
-#endif
 
 #ifndef TC2_TIMING
 #define TC2_TIMING 0     // 1: per-phase clock64 accounting by thread 0 of group 0 of CTA 0 (debug variant)
@@ -71,19 +63,14 @@ extern "C" int aq_debug_tc2_timing(long long *out) {
 
 namespace {
 
-constexpr int kG = TC2_AGG_TMEM ? 3 : 4;             // groups (boards in flight) per CTA
-constexpr uint32_t kGroupCols = TC2_AGG_TMEM ? 144 : 96;  // TMEM columns per group: accumulator [128 x 96] fp32 (+ Z^T [128 x 96] fp16 = 48 columns)
-constexpr uint32_t kColZA = 96;                      // offset of the fp16 Z^T operand inside a group's columns
+constexpr int kG = 4;             // groups (boards in flight) per CTA
+constexpr uint32_t kGroupCols = 96;                  // TMEM columns per group: accumulator [128 x 96] fp32
 constexpr int kNodesPad = 96;
 constexpr uint32_t kFmBlock = 16 * 512;              // feature-major tile: [3 node blocks of 32][16 atoms of 8 features][8][64 B]
 constexpr uint32_t kAdjBlock = 48 * 128;             // adjacency block: 48 out-node rows x 64 in-nodes (128 B)
 constexpr uint32_t kWKBlock = 128 * 128;
 constexpr uint32_t kTmemCols = 512;
-#if TC2_AGG_TMEM
-constexpr uint32_t kTmemW3 = kG * kGroupCols, kTmemW2 = 0xFFFFFFFFu;  // W2 is a shared-memory operand in this mode
-#else
 constexpr uint32_t kTmemW2 = kG * kGroupCols, kTmemW3 = kTmemW2 + 64;
-#endif
 static_assert(kTmemW3 + 64 <= kTmemCols, "TMEM columns");
 
 // instruction descriptors (kind::f16): D = f32, A = B = bf16, M = 128
@@ -114,18 +101,12 @@ static_assert(sizeof(Tc2Group) % 1024 == 0, "group state must keep 1024-byte ali
 struct Tc2Smem {
     unsigned char w1[128 * 32];              // layer-1 weight operand [128][16] K-major SWIZZLE_32B: [W1 | W1 | b1_hi | b1_lo | 0 | 0]
     Tc2Group g[kG];
-#if TC2_AGG_TMEM
-    unsigned char w2s[2 * kWKBlock];         // 32 KB: W2 [128 out][128 in] K-major SWIZZLE_128B (SS-form A operand of the layer-2 transform)
-#endif
     NodeConst nc[kV];                        // loop-invariant per-node constants
     float2 lut[64];                          // [deg_v * 8 + deg_u] -> {dinv_v * dinv_u as float, the same as fp16 bits}; entry 0 = closed edge
     unsigned long long mbar[kG];
     uint32_t tmem_base;
 };
 static_assert(offsetof(Tc2Smem, g) % 1024 == 0, "group state must be 1024-byte aligned");
-#if TC2_AGG_TMEM
-static_assert(offsetof(Tc2Smem, w2s) % 1024 == 0, "SWIZZLE_128B tiles must be 1024-byte aligned");
-#endif
 static_assert(sizeof(Tc2Smem) + 1024 <= 227 * 1024, "Tc2Smem exceeds shared memory");
 
 __device__ __forceinline__ uint64_t desc_fm_mn(uint32_t saddr) {  // MN-major SWIZZLE_64B: LBO = node-block stride, SBO = 8-feature atom stride
@@ -146,11 +127,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *r) {
                    "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
                    "r"(r[30]), "r"(r[31]) : "memory");
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-                   "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
-}
 // two floats -> packed bf16x2 (a in the low half), optionally through ReLU
 template <bool kRelu>
 __device__ __forceinline__ uint32_t cvt2(float a, float b) {
@@ -162,6 +138,13 @@ __device__ __forceinline__ uint32_t cvt2(float a, float b) {
 __device__ __forceinline__ uint32_t cvt2_f16(float a, float b) {  // packed f16x2 (a in the low half), saturating
     uint32_t d;
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+// running maximum of |x| over packed f16 pairs (both halves at once): what the fp16 aggregation operand saturates at is detected here
+__device__ __forceinline__ uint32_t hmax2_abs(uint32_t acc, uint32_t v) {
+    uint32_t a, d;
+    asm("abs.f16x2 %0, %1;\n" : "=r"(a) : "r"(v));
+    asm("max.f16x2 %0, %1, %2;\n" : "=r"(d) : "r"(acc), "r"(a));
     return d;
 }
 __device__ __forceinline__ unsigned short f16_bits(float x) { return (unsigned short)(cvt2_f16(x, 0.f) & 0xFFFFu); }
@@ -215,9 +198,10 @@ template <int kMode>
 __device__ __forceinline__ uint32_t cvt_pair(float a, float b) {
     return kMode == kToF16 ? cvt2_f16(a, b) : cvt2<kMode == kToBf16Relu>(a, b);
 }
-// grow != nullptr (training forward): the same 16-byte chunks also go to the board's saved tile in global memory
+// grow != nullptr (training forward): the same 16-byte chunks also go to the board's saved tile in global memory.
+// kToF16: `amax` (packed f16x2) collects the largest |z| of the thread's row, so that a saturated conversion is noticed.
 template <int kMode>
-__device__ __forceinline__ void store_block(uint32_t row_addr, int swz, int cb, const float *z, unsigned char *grow = nullptr) {
+__device__ __forceinline__ void store_block(uint32_t row_addr, int swz, int cb, const float *z, unsigned char *grow, uint32_t &amax) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         uint4 v;
@@ -227,6 +211,10 @@ __device__ __forceinline__ void store_block(uint32_t row_addr, int swz, int cb, 
             v.x = cvt_pair<kMode>(z[q * 8 + 0], z[q * 8 + 1]); v.y = cvt_pair<kMode>(z[q * 8 + 2], z[q * 8 + 3]);
             v.z = cvt_pair<kMode>(z[q * 8 + 4], z[q * 8 + 5]); v.w = cvt_pair<kMode>(z[q * 8 + 6], z[q * 8 + 7]);
         }
+        if (kMode == kToF16) {
+            amax = hmax2_abs(amax, v.x);
+            if (!(cb == 2 && q == 2)) amax = hmax2_abs(hmax2_abs(hmax2_abs(amax, v.y), v.z), v.w);
+        }
         sts128(row_addr + (uint32_t)cb * kFmBlock + (uint32_t)((q ^ swz) << 4), v);
         if (grow) *reinterpret_cast<uint4 *>(grow + (uint32_t)cb * kFmBlock + (uint32_t)((q ^ swz) << 4)) = v;
     }
@@ -234,7 +222,7 @@ __device__ __forceinline__ void store_block(uint32_t row_addr, int swz, int cb, 
 
 // the three column blocks of this thread's accumulator lane (+ bias) -> its feature row
 template <int kMode>
-__device__ __forceinline__ void epilogue_store(uint32_t tmem_me, uint32_t row_addr, int swz, float bias, unsigned char *grow = nullptr) {
+__device__ __forceinline__ void epilogue_store(uint32_t tmem_me, uint32_t row_addr, int swz, float bias, uint32_t &amax, unsigned char *grow = nullptr) {
 #pragma unroll
     for (int cb = 0; cb < 3; ++cb) {
         float z[32];
@@ -243,7 +231,7 @@ __device__ __forceinline__ void epilogue_store(uint32_t tmem_me, uint32_t row_ad
 #pragma unroll
             for (int i = 0; i < 32; ++i) z[i] += bias;
         }
-        store_block<kMode>(row_addr, swz, cb, z, grow);
+        store_block<kMode>(row_addr, swz, cb, z, grow, amax);
     }
 }
 
@@ -330,29 +318,9 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = sm.tmem_base;
     const uint32_t lane_off = (uint32_t)((tid >> 5) * 32) << 16;  // this warp's TMEM lane quadrant
-#if TC2_AGG_TMEM
-    {   // W2 -> shared memory, the tile aq_prepare_inference builds (or the same layout converted here)
-        if (prepared) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(prepared + kPrepW2);
-            uint4 *dst = reinterpret_cast<uint4 *>(sm.w2s);
-            for (int c = gtid; c < (int)(2 * kWKBlock / 16); c += kThreads) dst[c] = __ldg(src + c);
-        } else {
-            for (int c = gtid; c < 128 * 16; c += kThreads) {
-                const int n = c >> 4, j = c & 15;
-                const float4 lo = __ldg(reinterpret_cast<const float4 *>(params + kOffW2 + n * kH + j * 8));
-                const float4 hi = __ldg(reinterpret_cast<const float4 *>(params + kOffW2 + n * kH + j * 8) + 1);
-                uint4 v;
-                v.x = pack_bf16(lo.x, lo.y); v.y = pack_bf16(lo.z, lo.w); v.z = pack_bf16(hi.x, hi.y); v.w = pack_bf16(hi.z, hi.w);
-                *reinterpret_cast<uint4 *>(sm.w2s + sw128_chunk(n, j, kWKBlock)) = v;
-            }
-        }
-    }
-    constexpr int kWeightGroups = 1;   // group 0 stores W3
-#else
     constexpr int kWeightGroups = 2;   // W2 (group 0) / W3 (group 1)
-#endif
     if (grp < kWeightGroups) {  // row `tid` -> 64 TMEM columns, two bf16 per column (k = 2c, 2c + 1)
-        const bool w3 = TC2_AGG_TMEM ? true : grp != 0;
+        const bool w3 = grp != 0;
         const uint32_t dst = tmem_base + lane_off + (w3 ? kTmemW3 : kTmemW2);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -404,9 +372,6 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
     const uint32_t fm_u = smem_u + (uint32_t)offsetof(Tc2Smem, g) + (uint32_t)grp_u * (uint32_t)sizeof(Tc2Group);
     const uint32_t adj_u = fm_u + (uint32_t)offsetof(Tc2Group, adj), l1_u = fm_u + (uint32_t)offsetof(Tc2Group, l1op);
     const uint32_t w1_u = smem_u + (uint32_t)offsetof(Tc2Smem, w1);
-#if TC2_AGG_TMEM
-    const uint32_t w2s_u = smem_u + (uint32_t)offsetof(Tc2Smem, w2s);
-#endif
     const uint32_t bar_u = smem_u + (uint32_t)offsetof(Tc2Smem, mbar) + (uint32_t)grp_u * 8u;
 
     const int64_t stride = (int64_t)gridDim.x * kG;
@@ -537,7 +502,8 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         TC2_T(4);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         // ---- layer 1 epilogue: ReLU -> bf16 -> X1^T row ---------------------------------------------------------------
-        epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz, 0.f);   // (b1 is folded into the layer-1 MMA)
+        uint32_t amax = 0u;  // largest |Z| (packed f16x2) this thread converted for this board
+        epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz, 0.f, amax);   // (b1 is folded into the layer-1 MMA)
         float pool = 0.f;
 #pragma unroll 1
         for (int layer = 1; layer < kLayers; ++layer) {
@@ -555,14 +521,6 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
                                      ::"l"(SV.xt(saved, layer - 1, b)), "r"(fm_u), "r"(3u * kFmBlock) : "memory");
                         asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
                     }
-#if TC2_AGG_TMEM
-                    if (layer == 1) {  // W2 from shared memory (SS form): 4 steps of 32 B per 128-byte swizzle span, two K blocks
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            mma_bf16(tmem_d_u, desc_sw128(w2s_u + (uint32_t)(k >> 2) * kWKBlock + (uint32_t)(k & 3) * 32u),
-                                     desc_fm_mn(fm_u + k * 1024), kIdescT, k > 0 ? 1u : 0u);
-                    } else
-#endif
                     {
 #pragma unroll
                         for (int k = 0; k < 8; ++k)  // K = 128 features = 8 x 16: 8 TMEM columns of A, two 8-feature atoms of B per step
@@ -578,23 +536,8 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
             phase ^= 1u;
         TC2_T(6);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-#if TC2_AGG_TMEM
-            // ---- Z^T -> fp16 -> 48 columns of tensor memory next to the accumulator: the aggregation's A operand (TS form).
-            //      Nodes 81..95 of Z are exact zeros (the X^T tile is zero there), so the K padding needs no special case ----
-#pragma unroll
-            for (int cb = 0; cb < 3; ++cb) {
-                float z[32];
-                tmem_ld32(tmem_me + cb * 32, z);
-                uint32_t h[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) h[i] = cvt2_f16(z[2 * i], z[2 * i + 1]);
-                tmem_st16(tmem_me + kColZA + cb * 16, h);
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-#else
             // ---- Z^T -> fp16 -> the same tile, now the aggregation's A operand -------------------------------------
-            epilogue_store<kToF16>(tmem_me, row_addr, swz, 0.f);
-#endif
+            epilogue_store<kToF16>(tmem_me, row_addr, swz, 0.f, amax);
             // ---- aggregate: Y^T = Z^T A_hat^T + b 1^T --------------------------------------------------------------
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -611,13 +554,8 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
 #pragma unroll
                             for (int s = 0; s < 4; ++s) {  // 64 in-nodes = 4 K steps; A: two 32-node blocks, 2 steps of 32 B each
                                 const uint64_t bd = desc_sw128(adj_u + (par_u * 2u + (uint32_t)blk) * kAdjBlock + (uint32_t)s * 32u);
-#if TC2_AGG_TMEM
-                                // A: in-nodes 32 blk + 16 s .. + 15 = 8 columns of the fp16 Z^T operand (two nodes per column)
-                                mma_ts(d, tmem_d_u + kColZA + (uint32_t)(16 * blk + 8 * s), bd, kIdescA, s ? 1u : 0u);
-#else
                                 const uint64_t a = desc_fm_k(fm_u + (uint32_t)(blk + (s >> 1)) * kFmBlock + (uint32_t)(s & 1) * 32u);
                                 mma_bf16(d, a, bd, kIdescA, s ? 1u : 0u);
-#endif
                             }
                         }
                         mma_commit(bar_u);
@@ -632,7 +570,7 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
         TC2_T(8);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             if (layer + 1 < kLayers) {  // + bias -> ReLU -> bf16 -> X^T row of the next layer
-                epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz, bias2);
+                epilogue_store<kToBf16Relu>(tmem_me, row_addr, swz, bias2, amax);
             } else {                    // last layer feeds only the mean pool
 #pragma unroll
                 uint32_t m3[4] = {0u, 0u, 0u, 0u};
@@ -651,7 +589,11 @@ gcn_forward_tc2_kernel(const float *__restrict__ params, const unsigned char *__
                 if (kSave) *reinterpret_cast<uint4 *>(SV.mask3(saved, b) + tid * 16) = make_uint4(m3[0], m3[1], m3[2], 0u);
             }
         }
-        pooled_out[b * kH + tid] = pool / (float)kV;
+        // The aggregation operand is fp16: a transform output beyond +-65504 would be clamped by the saturating conversion.  That is
+        // never passed on silently: the feature's pooled value becomes NaN, so the board's policy and value come out as NaN
+        // (fp32 precision has no such limit).
+        const bool clamped = (amax & 0x7FFFu) >= 0x7BFFu || (amax >> 16) >= 0x7BFFu;
+        pooled_out[b * kH + tid] = clamped ? __int_as_float(0x7FC00000) : pool / (float)kV;
         par ^= 1u;
         TC2_T(9);
         // no barrier here: the next board's first MMA is issued behind a group barrier that every thread reaches after its pool loads

@@ -33,6 +33,7 @@ struct HtSmem {
     float bp2[kNPad];
     float bv2;
     float xch[4][4][kTile];                  // row-wise exchange between the four column quarters (max, sum, legal sum, value partials)
+    uint8_t poisoned[kTile];                 // board's pooled vector holds a NaN: the trunk's fp16 aggregation operand overflowed (gnn_tc2.cu)
     unsigned long long mbar;
     uint32_t tmem_base;
 };
@@ -170,6 +171,11 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
             for (int e = 0; e < 8; ++e) f[e] = 0.f;
         }
         *reinterpret_cast<uint4 *>(sm.a + sw128(r, j)) = pack8(f);
+        // a NaN marks a board whose activations did not fit the trunk's fp16 aggregation: fmaxf() in the ReLUs below would swallow
+        // it, so the row is remembered and its outputs are written as NaN.  The 16 chunks of a row sit in one half-warp.
+        const float sum8 = ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));   // pooled >= 0: NaN iff an element is NaN
+        const unsigned nan_lanes = __ballot_sync(0xffffffffu, sum8 != sum8);
+        if ((tid & 15) == 0) sm.poisoned[r] = ((nan_lanes >> (tid & 16)) & 0xFFFFu) != 0u;
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -235,7 +241,7 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
         commit(bar);
     }
     if (q == 2 && valid) {  // (the barrier before GEMM 2 ordered the partials)
-        const float val = tanhf(sm.bv2 + sm.xch[3][2][row] + sm.xch[3][3][row]);
+        const float val = sm.poisoned[row] ? __int_as_float(0x7FC00000) : tanhf(sm.bv2 + sm.xch[3][2][row] + sm.xch[3][3][row]);
         value[b0 + row] = val;
         if (saved) saved[SavedLayout{B}.value() + b0 + row] = val;
     }
@@ -298,6 +304,7 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
     float inv;
     if (kLegal) inv = sum_legal != 0.f ? 1.f / sum_legal : 1.f / sum_all;
     else inv = 1.f / sum_all;
+    if (sm.poisoned[row]) inv = __int_as_float(0x7FC00000);  // every probability this board writes becomes NaN
     {
         const int lane = tid & 31, r0 = row & ~31;  // this warp's 32 boards start at r0
 #pragma unroll 1

@@ -30,9 +30,10 @@ def update_best_player(model_dir=PV_NETWORK_PATH):
 
 
 @torch.no_grad()
-def play_matches(model0, model1, num_games=EN_GAME_COUNT, temperature=EN_TEMPERATURE, sims=None, seed=0, device=None):
+def play_matches(model0, model1, num_games=EN_GAME_COUNT, temperature=EN_TEMPERATURE, sims=None, seed=0, device=None,
+                 details=False):
     """-> total points of model0 over num_games (game i: model0 moves first iff i is even,
-    evaluate_network.py:69-73)."""
+    evaluate_network.py:69-73).  details=True: -> (total, per-game first_player_point list, per-game action lists)."""
     dev = gl._dev(device)
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
@@ -41,6 +42,7 @@ def play_matches(model0, model1, num_games=EN_GAME_COUNT, temperature=EN_TEMPERA
     states = start_states(num_games, dev)
     gid = torch.arange(num_games, device=dev)
     points = torch.zeros(num_games, dtype=torch.float64, device=dev)  # points of the FIRST player of each game
+    log = [[] for _ in range(num_games)] if details else None
     ply = 0
     while states.shape[0] > 0:
         # first player moves on even plies; game i's first player is model (i % 2)
@@ -53,6 +55,9 @@ def play_matches(model0, model1, num_games=EN_GAME_COUNT, temperature=EN_TEMPERA
                 pol = pv_mcts.policy_from_counts(counts, temperature)
                 pick = torch.multinomial(pol.float(), 1, generator=gen)
                 act[sel] = torch.gather(actions, 1, pick).squeeze(1)
+        if details:
+            for g, a in zip(gid.tolist(), act.tolist()):
+                log[g].append(int(a))
         states, term = gl.next_batch(states, act)
         ply += 1
         done = term != 0
@@ -65,7 +70,8 @@ def play_matches(model0, model1, num_games=EN_GAME_COUNT, temperature=EN_TEMPERA
         states, gid = states[~done].contiguous(), gid[~done]
     g = torch.arange(num_games, device=dev)
     model0_points = torch.where(g % 2 == 0, points, 1.0 - points)
-    return float(model0_points.sum().item())
+    total = float(model0_points.sum().item())
+    return (total, points.tolist(), log) if details else total
 
 
 def evaluate_network(model_dir=PV_NETWORK_PATH, num_games=EN_GAME_COUNT, sims=None):

@@ -125,3 +125,51 @@ def test_arena_and_tiny_train_cycle(tmp_path, monkeypatch):
     assert promoted in (True, False)
     pts = evaluate_network.play_matches(_net(0), _net(0), num_games=4, sims=6, seed=1)
     assert 0.0 <= pts <= 4.0
+
+
+def _arena_evaluator(kind, salt):
+    """The evaluators of tests/golden/make_arena_golden.py in torch integer ops (bit-identical priors and values)."""
+    def ev(packed):
+        rows, plies = gl.unpack_rows(packed)
+        w = (torch.arange(68, device=rows.device, dtype=torch.int64) + 1) * 7919
+        key = ((rows.to(torch.int64) * w).sum(1) + plies.to(torch.int64) * 104729) % (2 ** 31)
+        mask, pawn = gl.legal_mask_batch(packed)
+        dense = gl.mask_to_dense(mask)
+        a = torch.arange(209, device=rows.device, dtype=torch.int64)
+        if kind == "runner":
+            prow, arow = (rows[:, 0].to(torch.int64) // 9)[:, None], (a // 9)[None, :]
+            base = torch.where(arow < prow, 60, torch.where(arow == prow, 6, 2))
+            base = torch.where(a[None, :] < 81, base, torch.ones_like(base))
+            raw = base * 8 + (key[:, None] + a[None, :] * 40503 + salt) % 7
+            val = torch.zeros(packed.shape[0], dtype=torch.float32, device=rows.device)
+        else:
+            raw = (key[:, None] + a[None, :] * 40503 + salt) % 1009 + 1
+            val = (((key + salt) % 2001) - 1000).to(torch.float32) / torch.tensor(1000.0, dtype=torch.float32, device=rows.device)
+        raw = torch.where(dense, raw, torch.zeros_like(raw))
+        pri = raw.to(torch.float32) / raw.sum(1).to(torch.float32)[:, None]
+        return {"priors": pri.contiguous(), "value": val.contiguous(), "mask": mask, "pawn": pawn}
+    return ev
+
+
+def test_arena_matches_reference_play_and_scoring():
+    """evaluate_network.play / first_player_point / the colour alternation of the match loop (evaluate_network.py:18-45, 66-73):
+    the UNMODIFIED reference played these pairings with deterministic evaluators at temperature 0
+    (tests/golden/make_arena_golden.py); play_matches must reproduce every game move for move, every first-player point
+    and the total."""
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "arena_golden.json")) as f:
+        golden = json.load(f)
+    for pairing in golden["pairings"]:
+        m0, m1 = _arena_evaluator(*pairing["model0"]), _arena_evaluator(*pairing["model1"])
+        n = len(pairing["games"])
+        total, points, log = evaluate_network.play_matches(m0, m1, num_games=n, temperature=golden["temperature"],
+                                                           sims=golden["sims"], seed=0, details=True)
+        for i, g in enumerate(pairing["games"]):
+            assert log[i] == g["actions"], (pairing["name"], i)
+            assert points[i] == g["first_player_point"], (pairing["name"], i)
+        assert total == pairing["total_point_model0"], pairing["name"]
+    # the fixture exercises what it should: both colours win somewhere, a draw occurs, and alternation changes the total
+    pts = [g["first_player_point"] for p in golden["pairings"] for g in p["games"]]
+    assert {0, 1, 0.5} <= set(pts)
+    rr = [p for p in golden["pairings"] if p["name"] == "runner_vs_runner"][0]
+    assert rr["total_point_model0"] == 2.0 and len(rr["games"]) == 5   # second mover always wins: model0 scores on odd games only

@@ -446,8 +446,36 @@ def test_compact_priors_and_host_evaluator_match_predict_order(traj):
             assert np.array_equal(res["priors"], want)
             assert np.array_equal(res["value"], out["value"].cpu().numpy())
             assert np.array_equal(res["mask"], out["mask"].cpu().numpy()) and np.array_equal(res["pawn"], out["pawn"].cpu().numpy())
-        assert ev.d2h_bytes(res) == 4 * len(want) + 48 * B
+        assert ev.d2h_bytes(res) == 4 * len(want) + 48 * B + 4
         ev.close()
+        # 16-bit wire format without mask / pawn: the same values rounded to IEEE half (round to nearest even), offsets and values exact;
+        # the context's running estimate of the ragged length makes the second and third call copy less than the capacity
+        ev16 = HostLeafEvaluator(net, max(B, 1), wire="f16", with_mask=False)
+        ev16.states[:B] = torch.from_numpy(gl.pack_rows_host(rows, plies))
+        for _ in range(3):
+            ev16.priors.fill_(-1.0)
+            r16 = ev16.evaluate(B)
+            assert set(r16) == {"priors", "offsets", "value"} and r16["priors"].dtype == np.float16
+            assert np.array_equal(r16["offsets"], want_off) and np.array_equal(r16["value"], out["value"].cpu().numpy())
+            assert np.array_equal(r16["priors"], want.astype(np.float16))
+        assert ev16.d2h_bytes(r16) == 2 * len(want) + 8 * B + 4
+        assert ev16.stats()[0] == 0 and (B == 0 or abs(ev16.stats()[1] - 1.03 * len(want) / B) < 1.0)
+        ev16.close()
+    # a batch with more legal actions per board than the running estimate: the remainder arrives by a second copy, same bytes
+    order = np.argsort(traj["nact"].astype(np.int64), kind="stable")
+    few, many = order[:3000], order[-3000:]
+    ev = HostLeafEvaluator(net, 3000)
+    for idx in (few, many, few):
+        rows, plies = traj["rows"][idx], traj["plies"][idx]
+        ev.states[:] = torch.from_numpy(gl.pack_rows_host(rows, plies))
+        ev.priors.fill_(-1.0)
+        res = ev.evaluate(3000)
+        dense = net.predict_batch(gl.pack_rows(rows, plies))["priors"].cpu().numpy()
+        ref = qo.legal_actions_batch(rows, plies)
+        want = np.concatenate([dense[b, ref["actions"][b, :ref["n"][b]]] for b in range(3000)])
+        assert int(res["offsets"][-1]) == len(want) and np.array_equal(res["priors"], want)
+    assert ev.stats()[0] == 1   # exactly the switch from few to many needed the second copy
+    ev.close()
     # the dense flavour of the same class
     ev = HostLeafEvaluator(net, 777, dense=True)
     sel = np.linspace(0, len(traj["rows"]) - 1, 777).astype(int)
@@ -475,6 +503,7 @@ def test_two_host_evaluators_in_flight_give_the_same_results(traj):
     sels = [np.linspace(k, len(traj["rows"]) - 1 - k, B).astype(int) for k in (0, 5)]
     hosts = [torch.from_numpy(gl.pack_rows_host(traj["rows"][s], traj["plies"][s])).pin_memory() for s in sels]
     a, b, ref = HostLeafEvaluator(net, B), HostLeafEvaluator(net, B), HostLeafEvaluator(net, B)
+    c = HostLeafEvaluator(net, B)
     want = []
     for h in hosts:
         out = ref.evaluate(B, states=h)
@@ -486,8 +515,192 @@ def test_two_host_evaluators_in_flight_give_the_same_results(traj):
         b.submit(B, states=hosts[1])
         with pytest.raises(Exception):
             a.submit(B, states=hosts[0])  # one batch per evaluator at a time
+        c.submit(B, states=hosts[0])   # three batches in flight
         ra = a.wait()
         rb = b.wait()
-        for got, w in ((ra, want[0]), (rb, want[1])):
+        rc = c.wait()
+        for got, w in ((ra, want[0]), (rb, want[1]), (rc, want[0])):
             for k in ("offsets", "priors", "value", "mask", "pawn"):
                 assert np.array_equal(got[k], w[k]), k
+
+
+# ---- the benchmarked configurations themselves (parity of what bench.py times) ---------------------------------
+def _oracle_predict(ref, rows, plies):
+    """predict() semantics for a batch on the CPU: oracle legal actions + oracle fp32 forward + restriction to the legal actions +
+    renormalisation (pv_network_cnn.py:128-135)."""
+    legal = qo.legal_actions_batch(rows, plies)
+    x, ei, batch = gnn_oracle.graph_inputs_from_rows(rows)
+    with torch.no_grad():
+        p_ref, v_ref = ref(x, ei, batch)
+    dense = torch.from_numpy(np.unpackbits(legal["mask"].view(np.uint8), axis=1, bitorder="little")[:, :209].astype(bool))
+    want = torch.where(dense, p_ref, torch.zeros_like(p_ref))
+    ssum = want.sum(1, keepdim=True)
+    want = want / torch.where(ssum == 0, torch.ones_like(ssum), ssum)
+    return legal, want, v_ref.squeeze(1)
+
+
+def test_bf16_leaf_eval_at_the_benchmarked_batch_matches_oracle():
+    """bench.py's headline step: B = 16,384 positions of positions.mixed_batches (the bench workload), bf16 tensor-core path with
+    prepared weights -- 148 CTAs x 4 groups, ~28 boards per group, i.e. the software-pipelined next-board path the small-batch
+    tests barely touch -- against the fp32 CPU oracle.  Stated tolerance: policy abs <= 2e-3, value abs <= 5e-3; legal mask exact.
+    The same batch through the host API (ragged priors, f32 and f16 wire) must agree with the device path."""
+    from alphaquoridorgnn_b200 import positions
+    from alphaquoridorgnn_b200.pv_network_gnn import HostLeafEvaluator
+    B = 16384
+    _, batches = positions.mixed_batches(1, B, seed=1, device="cuda")
+    packed = batches[0]
+    rows, plies = [t.cpu().numpy() for t in gl.unpack_rows(packed)]
+    ref, net = _models(21)
+    net.eval()
+    legal, want, v_ref = _oracle_predict(ref, rows, plies)
+    net.precision = "bf16"
+    out = net.predict_batch(packed)
+    assert np.array_equal(out["mask"].cpu().numpy().view(np.uint32), legal["mask"])
+    assert np.array_equal(out["pawn"].cpu().numpy(), legal["pawn"])
+    ep = (out["priors"].cpu() - want).abs().max().item()
+    ev = (out["value"].cpu() - v_ref).abs().max().item()
+    print(f"bf16 leaf eval at B={B}: max |dp| = {ep:.3e}, max |dv| = {ev:.3e}")
+    assert ep <= 2e-3 and ev <= 5e-3, (ep, ev)
+    assert torch.isfinite(out["priors"]).all() and torch.isfinite(out["value"]).all()
+    # fp32 path on the same batch: tight tolerance
+    net.precision = "fp32"
+    out32 = net.predict_batch(packed)
+    assert (out32["priors"].cpu() - want).abs().max().item() <= 5e-5 and (out32["value"].cpu() - v_ref).abs().max().item() <= TOL_OUT
+    # host API, the call bench.py's e2e makes: ragged priors in legal_actions() order
+    net.precision = "bf16"
+    host = torch.from_numpy(gl.pack_rows_host(rows, plies)).pin_memory()
+    dense = out["priors"].cpu().numpy()
+    gathered = np.concatenate([dense[b, legal["actions"][b, :legal["n"][b]]] for b in range(B)])
+    want_ragged = np.concatenate([want[b, legal["actions"][b, :legal["n"][b]].astype(np.int64)].numpy() for b in range(B)])
+    for wire in ("f32", "f16"):
+        evl = HostLeafEvaluator(net, B, wire=wire, with_mask=False)
+        for _ in range(2):
+            res = evl.evaluate(B, states=host)
+        assert int(res["offsets"][B]) == len(gathered)
+        assert np.array_equal(res["priors"], gathered.astype(np.float16) if wire == "f16" else gathered)
+        assert np.array_equal(res["value"], out["value"].cpu().numpy())
+        assert np.abs(res["priors"].astype(np.float32) - want_ragged).max() <= 2e-3   # vs the oracle, wire rounding included
+        evl.close()
+
+
+def _oracle_grads_fp64(ref, rows, pt, vt, chunk=512):
+    """fp64 oracle autograd of the reference loss (train_network.py:54-55,85-89: both 'mean' over the batch), accumulated over chunks
+    of boards so that the edge-list formulation fits in memory: mean over B = sum over chunks of (chunk mean x n_chunk / B)."""
+    ref64 = copy.deepcopy(ref).double()
+    B = len(rows)
+    total = 0.0
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        x, ei, batch = gnn_oracle.graph_inputs_from_rows(rows[lo:hi], dtype=torch.float64)
+        p64, v64 = ref64(x, ei, batch)
+        loss, _, _ = gnn_oracle.training_loss(p64, v64, pt[lo:hi].double(), vt[lo:hi].double())
+        (loss * ((hi - lo) / B)).backward()
+        total += loss.item() * (hi - lo) / B
+    return total, {n: p.grad for n, p in ref64.named_parameters()}
+
+
+@pytest.mark.parametrize("B", [256, 4096])
+def test_bf16_training_gradients_at_the_benchmarked_batches(B):
+    """The training step bench.py times (B = 256: BASELINE configs[0]; B = 4096: 28 boards per CTA through the double-buffered
+    cp.async path of the tensor-core backward) against fp64 oracle autograd.  Stated tolerance: flat gradient rel-L2 <= 1e-2, every
+    tensor <= 2e-2 (<= 1e-1 for tensors whose norm is below 1e-3 of the largest, see test_bf16_tensor_core_training_gradients)."""
+    from alphaquoridorgnn_b200 import positions
+    from alphaquoridorgnn_b200.train_network import FlatTrainer
+    packed = positions.mixed_batches(1, B, seed=2, device="cuda")[1][0]
+    rows = gl.unpack_rows(packed)[0].cpu().numpy()
+    ref, net = _models(22)
+    torch.manual_seed(5)
+    pt = torch.softmax(2 * torch.randn(B, 209), dim=1)
+    vt = torch.randint(-1, 2, (B,)).float()
+    loss64, g_ref = _oracle_grads_fp64(ref, rows, pt, vt)
+    net.train()
+    net.train_precision = "bf16"
+    tr = FlatTrainer(net, lr=0.0)                      # lr 0: the step leaves the weights alone, tr.grads holds the gradient
+    loss = tr.step(packed, pt.cuda(), vt.cuda(), B).sum().item()
+    assert abs(loss - loss64) <= 2e-3
+    flat = tr.grads.cpu().double()
+    assert torch.isfinite(flat).all()
+    from alphaquoridorgnn_b200.pv_network_gnn import FLAT_PARAM_ORDER
+    flat_ref = torch.cat([g_ref[n].reshape(-1) for n in FLAT_PARAM_ORDER])
+    err = ((flat - flat_ref).norm() / flat_ref.norm()).item()
+    off, worst, norms = 0, {}, {}
+    for n in FLAT_PARAM_ORDER:
+        k = g_ref[n].numel()
+        worst[n] = _rel_l2(flat[off:off + k], g_ref[n].reshape(-1))
+        norms[n] = g_ref[n].norm().item()
+        off += k
+    print(f"bf16 training step at B={B}: flat rel-L2 {err:.2e}; per tensor", {k: f"{e:.1e}" for k, e in worst.items()})
+    assert err <= 1e-2, err
+    big = max(norms.values())
+    for n, e in worst.items():
+        assert e <= (2e-2 if norms[n] >= 1e-3 * big else 1e-1), (n, e, norms[n])
+    # the fp32 path at the same batch: tight
+    net.train_precision = "fp32"
+    tr32 = FlatTrainer(net, lr=0.0)
+    tr32.step(packed, pt.cuda(), vt.cuda(), B)
+    assert ((tr32.grads.cpu().double() - flat_ref).norm() / flat_ref.norm()).item() <= 1e-4
+
+
+def net_forward_bf16(net, packed):
+    old = net.precision
+    net.precision = "bf16"
+    try:
+        return net(packed)
+    finally:
+        net.precision = old
+
+
+def test_fp16_aggregation_overflow_is_never_silent(traj):
+    """The tensor-core trunk aggregates in fp16 (gnn_tc2.cu): a node-transform output beyond +-65504 cannot be represented.  The
+    stated behaviour: such a board's policy and value are NaN -- never a silently clamped number -- while
+    boards whose activations fit are unaffected, and the fp32 path evaluates every board."""
+    rows, plies = _sample_rows(traj, 500, seed=41)
+    ref, net = _models(23)
+    net.eval()
+    packed = gl.pack_rows(rows, plies)
+    # layer-2 weights scaled up: Z2 = X1 W2^T grows linearly with the scale
+    base = net.gcn_layers[1].lin.weight.detach().clone()
+
+    def zmax(scale):  # per board max |Z2|, |Z3| (the two fp16 aggregation operands) in fp32 from the oracle
+        x, ei, batch = gnn_oracle.graph_inputs_from_rows(rows)
+        with torch.no_grad():
+            x1 = torch.relu(ref.gcn_layers[0](x, ei))
+            w2 = base.cpu() * scale
+            z2 = x1 @ w2.t()
+            src, dst, w = gnn_oracle.gcn_norm(ei, x.shape[0], x.dtype)
+            x2 = torch.relu(torch.zeros_like(z2).index_add_(0, dst, w.unsqueeze(1) * z2[src]) + ref.gcn_layers[1].bias)
+            z3 = x2 @ ref.gcn_layers[2].lin.weight.t()
+        return torch.maximum(z2.abs().reshape(len(rows), -1).max(1).values, z3.abs().reshape(len(rows), -1).max(1).values)
+
+    m1 = zmax(1.0)
+    assert float(m1.max()) < 3.0e4            # the random-init network itself is far from the limit
+    s_ok = float(3.0e4 / m1.max())            # every board stays below 3e4 < 65504 (Z2 and Z3 scale linearly with the factor)
+    s_bad = float(4.0 * 65504 / m1.min())     # every board exceeds 65504 by a factor 4
+    with torch.no_grad():
+        for scale, overflow in ((s_ok, False), (s_bad, True)):
+            net.gcn_layers[1].lin.weight.copy_(base * scale)
+            ref.gcn_layers[1].lin.weight.copy_(base.cpu() * scale)
+            net.precision = "bf16"
+            out = net.predict_batch(packed)
+            net.precision = "fp32"
+            out32 = net.predict_batch(packed)
+            assert torch.isfinite(out32["priors"]).all() and torch.isfinite(out32["value"]).all()
+            if overflow:   # value NaN, and NaN exactly on the legal actions (illegal ones stay 0)
+                assert torch.isnan(out["value"]).all()
+                assert torch.equal(torch.isnan(out["priors"]), gl.mask_to_dense(out["mask"]))
+                with torch.no_grad():
+                    pfw, vfw = net_forward_bf16(net, packed)
+                assert torch.isnan(pfw).all() and torch.isnan(vfw).all()   # forward() (no legal restriction): the whole row
+            else:
+                assert torch.isfinite(out["priors"]).all() and torch.isfinite(out["value"]).all()
+                _, want, v_ref = _oracle_predict(ref, rows, plies)
+                assert (out["priors"].cpu() - want).abs().max().item() <= 2e-2   # large activations: bf16 relative error on big logits
+        # mixed batch: only the boards that overflow are poisoned
+        s_mid = float(65504 / m1.median())
+        net.gcn_layers[1].lin.weight.copy_(base * s_mid)
+        net.precision = "bf16"
+        out = net.predict_batch(packed)
+        zm = zmax(s_mid)
+        bad = torch.isnan(out["value"]).cpu()
+        assert bad[zm > 1.1 * 65504].all() and not bad[zm < 0.9 * 65504].any()   # (bf16 operands move |Z| by < 1 %)
+        assert 0 < int(bad.sum()) < len(rows)

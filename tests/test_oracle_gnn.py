@@ -50,3 +50,46 @@ def test_loss_restates_double_softmax():
     want_p = -(t * torch.log_softmax(p, 1)).sum(1).mean()
     want_v = ((v.squeeze() - vt) ** 2).mean()
     assert torch.allclose(lp, want_p) and torch.allclose(lv, want_v) and torch.allclose(loss, want_p + want_v)
+
+
+def test_matches_torch_geometric(traj):
+    """The day torch_geometric is importable, this pins the restatement against the real GCNConv / global_mean_pool the reference
+    calls (pv_network_gnn.py:13,33,35,56,59).  It is not vendored in the reference, not pinned by its requirements.txt and not
+    installed in this image (no index access), so the test skips here -- the oracle stays "parity unpinned" until it runs."""
+    import pytest
+    pyg = pytest.importorskip("torch_geometric.nn")
+    rows = traj["rows"][::900][:48]
+    torch.manual_seed(0)
+    ours = gnn_oracle.GraphPolicyValueNetworkOracle()
+    with torch.no_grad():
+        for layer in ours.gcn_layers:
+            layer.bias.uniform_(-0.1, 0.1)
+
+    class Real(torch.nn.Module):  # pv_network_gnn.py:24-64, literally
+        def __init__(self):
+            super().__init__()
+            self.gcn_layers = torch.nn.ModuleList([pyg.GCNConv(6, 128), pyg.GCNConv(128, 128), pyg.GCNConv(128, 128)])
+            self.policy_head = torch.nn.Sequential(torch.nn.Linear(128, 64), torch.nn.ReLU(), torch.nn.Linear(64, 209), torch.nn.Softmax(dim=1))
+            self.value_head = torch.nn.Sequential(torch.nn.Linear(128, 64), torch.nn.ReLU(), torch.nn.Linear(64, 1), torch.nn.Tanh())
+
+        def forward(self, x, edge_index, batch):
+            for layer in self.gcn_layers:
+                x = torch.nn.functional.relu(layer(x, edge_index))
+            x = pyg.global_mean_pool(x, batch)
+            return self.policy_head(x), self.value_head(x)
+
+    real = Real()
+    real.load_state_dict(ours.state_dict())   # same key names: gcn_layers.{i}.lin.weight / .bias
+    x, ei, batch = gnn_oracle.graph_inputs_from_rows(rows)
+    with torch.no_grad():
+        p, v = ours(x, ei, batch)
+        p2, v2 = real(x, ei, batch)
+    assert (p - p2).abs().max().item() <= 1e-6 and (v - v2).abs().max().item() <= 1e-6
+    # gradients of the reference loss too
+    pt = torch.softmax(torch.randn(len(rows), 209), 1)
+    vt = torch.randint(-1, 2, (len(rows),)).float()
+    for net in (ours, real):
+        pp, vv = net(x, ei, batch)
+        gnn_oracle.training_loss(pp, vv, pt, vt)[0].backward()
+    for (n, a), (_, b) in zip(ours.named_parameters(), real.named_parameters()):
+        assert (a.grad - b.grad).abs().max().item() <= 1e-6 * max(1.0, b.grad.abs().max().item()), n
