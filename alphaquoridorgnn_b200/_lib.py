@@ -16,6 +16,7 @@ _vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_
 SYMBOLS = {
     "aq_version": (_i32, []),
     "aq_last_error_string": (ctypes.c_char_p, []),
+    "aq_launch_count": (_i64, []),
     "aq_pack_states": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "aq_unpack_states": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "aq_legal_mask": (_i32, [_vp, _i64, _vp, _vp, _vp]),

@@ -4,6 +4,7 @@
 //   K9 state_next      game_logic.py:43-54, 359-391
 // plus row68 <-> AqState packing and the ordered action list.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -22,11 +23,18 @@ int aq_set_error(int code, const char *what) {
     return code;
 }
 
+// every kernel launch of the library is followed by aq_check_launch: the successful ones are counted (aq_launch_count), so
+// that a caller can state how many of this library's kernels ran in a region instead of assuming it (bench.py: gpu_launches)
+static std::atomic<long long> g_launches{0};
+
 int aq_check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return aq_set_error((int)e, what);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
+
+extern "C" int64_t aq_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int aq_version(void) { return AQ_VERSION; }
 extern "C" const char *aq_last_error_string(void) { return g_err; }

@@ -87,6 +87,17 @@ class BatchedMCTS:
         L, P = _lib.load(), _lib.ptr
         dev = self.device
         roots = roots.to(dev).contiguous()
+        G_real = roots.shape[0]
+        if G_real == 0:
+            return (torch.empty((0, gl.MAX_LEGAL), dtype=torch.int32, device=dev), torch.empty((0, gl.MAX_LEGAL), dtype=torch.int16, device=dev),
+                    torch.empty((0,), dtype=torch.int16, device=dev))
+        # Self-play and the arena drop finished games, so the number of roots shrinks by a few almost every ply.  Batches above 256
+        # are padded to the next multiple of 256 with copies of the last root (searched and discarded; games are independent, so the
+        # real ones are unaffected): workspaces, buffers and the captured CUDA graph of the simulation step are then reused across
+        # plies instead of being rebuilt for every distinct size.
+        if self.model is not None and self.use_graph and G_real > 256 and G_real % 256:
+            pad = 256 - G_real % 256
+            roots = torch.cat([roots, roots[-1:].expand(pad, -1)]).contiguous()
         G = roots.shape[0]
         max_nodes = 1 + sims * MAX_CHILDREN
         ws = self._workspace(G, max_nodes)
@@ -139,9 +150,14 @@ class BatchedMCTS:
             ovf = torch.zeros((1,), dtype=torch.int32, device=dev)
             _lib.check(L.aq_mcts_root_counts(P(ws), G, max_nodes, P(counts), P(actions), P(n), P(ovf), st),
                        "aq_mcts_root_counts")
-        if int(ovf.item()):
+            bad = torch.isnan(buf["value"]).any().to(torch.int32).reshape(1) if self.model is not None else torch.zeros_like(ovf)
+        status = torch.cat([ovf, bad]).tolist()   # one synchronisation for both flags
+        if status[0]:
             raise _lib.AqError("MCTS node arena overflow")
-        return counts, actions, n
+        if status[1]:
+            raise _lib.AqError("the network returned NaN for a leaf: with precision 'bf16' that is how an activation beyond the fp16 range of the "
+                               "aggregation operand is reported (gnn_tc2.cu); evaluate this network with precision 'fp32'")
+        return counts[:G_real], actions[:G_real], n[:G_real]
 
 
 def policy_from_counts(counts, temperature):

@@ -40,28 +40,34 @@ def write_data(history, directory='./data/'):
 
 
 @torch.no_grad()
-def play_batch(model, num_games, device=None, sims=None, temperature=SP_TEMPERATURE, seed=None, max_plies=None):
-    """Execute `num_games` self-play games in lock-step (self_play.py:40-68 per game).
-    Returns (history in the reference format, dict with per-game results)."""
+def play_batch_device(model, num_games, device=None, sims=None, temperature=SP_TEMPERATURE, seed=None, max_plies=None,
+                      policy_dtype=torch.float64):
+    """Execute `num_games` self-play games in lock-step (self_play.py:40-68 per game) and keep the record on the device:
+    dict(states uint8[T,32] packed, policy [T,209] search policies over all actions (self_play.py:51-54), value f32[T]
+    back-filled game results seen from the player to move (self_play.py:63-66), game int64[T], ply int64[T],
+    flags uint8[G] (bit 0 = the player to move at the end has lost, bit 1 = draw), plies int64[G], sims int = simulations run)."""
     dev = gl._dev(device)
     gen = torch.Generator(device=dev)
     gen.manual_seed(int(seed) if seed is not None else int(torch.seed() % (2 ** 31)))
-    mcts = pv_mcts.BatchedMCTS(model, sims or pv_mcts.PV_EVALUATE_COUNT, device=dev)
+    sims = sims or pv_mcts.PV_EVALUATE_COUNT
+    mcts = pv_mcts.BatchedMCTS(model, sims, device=dev)
     states = start_states(num_games, dev)
     game_id = torch.arange(num_games, device=dev)
-    rec_state, rec_policy, rec_game = [], [], []
+    rec_state, rec_policy, rec_game, rec_ply = [], [], [], []
     final_flags = torch.zeros(num_games, dtype=torch.uint8, device=dev)
     final_plies = torch.zeros(num_games, dtype=torch.int64, device=dev)
-    ply = 0
+    ply, sims_run = 0, 0
     while states.shape[0] > 0 and (max_plies is None or ply < max_plies):
         counts, actions, n = mcts.search(states)
+        sims_run += states.shape[0] * sims
         pol = pv_mcts.policy_from_counts(counts, temperature)            # [G,136] over legal actions
-        dense = torch.zeros((states.shape[0], POLICY_OUTPUT_SIZE), dtype=torch.float64, device=dev)
+        dense = torch.zeros((states.shape[0], POLICY_OUTPUT_SIZE), dtype=policy_dtype, device=dev)
         valid = actions >= 0
-        dense.scatter_(1, actions.clamp(min=0).to(torch.int64), torch.where(valid, pol, torch.zeros_like(pol)))
+        dense.scatter_(1, actions.clamp(min=0).to(torch.int64), torch.where(valid, pol, torch.zeros_like(pol)).to(policy_dtype))
         rec_state.append(states)
         rec_policy.append(dense)
         rec_game.append(game_id)
+        rec_ply.append(torch.full_like(game_id, ply))
         pick = torch.multinomial(pol.float(), 1, generator=gen)          # np.random.choice(legal, p=scores)
         act = torch.gather(actions, 1, pick).squeeze(1)
         states, term = gl.next_batch(states, act)
@@ -70,25 +76,31 @@ def play_batch(model, num_games, device=None, sims=None, temperature=SP_TEMPERAT
         final_flags[game_id[done]] = term[done]
         final_plies[game_id[done]] = ply
         states, game_id = states[~done].contiguous(), game_id[~done]
-    # ---- host side: the reference's list-of-lists with back-filled values (self_play.py:63-66) ----
-    all_states = torch.cat(rec_state)
-    rows, _ = gl.unpack_rows(all_states)
+    game, plyv = torch.cat(rec_game), torch.cat(rec_ply)
+    # first_player_value of the ended state (self_play.py:22-27): the player to move there has lost; the value target of a
+    # position alternates in sign with the ply (self_play.py:63-66); unfinished games (max_plies) count as draws
+    lost = (final_flags[game] & 1) != 0
+    fpv = torch.where(lost, torch.where(final_plies[game] % 2 == 0, -1.0, 1.0), 0.0)
+    value = torch.where(plyv % 2 == 0, fpv, -fpv).to(torch.float32)
+    return {"states": torch.cat(rec_state), "policy": torch.cat(rec_policy), "value": value, "game": game, "ply": plyv,
+            "flags": final_flags, "plies": final_plies, "sims": sims_run}
+
+
+def play_batch(model, num_games, device=None, sims=None, temperature=SP_TEMPERATURE, seed=None, max_plies=None):
+    """play_batch_device + conversion to the reference's history: a list of [[player, enemy, walls], policy (209 floats), value]
+    (self_play.py:51-54, 63-66), games in order, plies in order within a game.  Returns (history, dict with per-game results)."""
+    rec = play_batch_device(model, num_games, device, sims, temperature, seed, max_plies)
+    rows, _ = gl.unpack_rows(rec["states"])
     rows = rows.cpu().numpy()
-    pols = torch.cat(rec_policy).cpu().numpy()
-    gids = torch.cat(rec_game).cpu().numpy()
-    flags, plies = final_flags.cpu().numpy(), final_plies.cpu().numpy()
+    pols = rec["policy"].cpu().numpy()
+    vals = rec["value"].cpu().numpy()
+    gids = rec["game"].cpu().numpy()
     order = np.argsort(gids, kind='stable')                              # plies stay in order within a game
-    history, seen = [], {}
+    history = []
     for i in order:
-        g = int(gids[i])
-        k = seen.get(g, 0)                                               # ply index inside game g
-        seen[g] = k + 1
-        # first_player_value of the ended state (self_play.py:22-27): the player to move there has lost
-        fpv = (-1 if plies[g] % 2 == 0 else 1) if (flags[g] & 1) else 0
-        value = fpv if k % 2 == 0 else -fpv                              # alternating sign, self_play.py:63-66
         r = rows[i]
-        history.append([[r[0:2].tolist(), r[2:4].tolist(), r[4:].tolist()], pols[i].tolist(), value])
-    return history, {"flags": flags, "plies": plies}
+        history.append([[r[0:2].tolist(), r[2:4].tolist(), r[4:].tolist()], pols[i].tolist(), int(vals[i])])
+    return history, {"flags": rec["flags"].cpu().numpy(), "plies": rec["plies"].cpu().numpy()}
 
 
 def play(model, device=None):

@@ -111,6 +111,14 @@ def train_on_history(model, history, num_epochs=NUM_EPOCH, batch_size=BATCH_SIZE
     packed = gl.pack_rows(rows, None, dev)
     p = torch.tensor(np.array(p), dtype=torch.float32, device=dev)     # policy targets
     v = torch.tensor(np.array(v), dtype=torch.float32, device=dev)     # value targets
+    return train_on_buffer(model, packed, p, v, num_epochs, batch_size, rank, world_size, seed, verbose)
+
+
+def train_on_buffer(model, packed, p, v, num_epochs=NUM_EPOCH, batch_size=BATCH_SIZE, rank=0, world_size=1, seed=0, verbose=True):
+    """The same loop on a self-play record that is already on the device (self_play.play_batch_device): packed states
+    uint8[M,32], policy targets f32[M,209], value targets f32[M]."""
+    dev = model.flat_parameters().device
+    packed, p, v = packed.to(dev), p.to(device=dev, dtype=torch.float32), v.to(device=dev, dtype=torch.float32)
     M = packed.shape[0]
     trainer = FlatTrainer(model, lr=0.001, rank=rank, world_size=world_size)
     gen = torch.Generator(device='cpu')

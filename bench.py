@@ -1,17 +1,21 @@
 #!/usr/bin/env python
-"""Benchmark of the AlphaQuoridorGNN hot path on B200 (contract: see the task statement / DESIGN.md).
+"""Benchmark of the AlphaQuoridorGNN hot path on B200 (contract: see the task statement / DESIGN.md section 7).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one batched leaf evaluation (BaseNetwork.predict semantics for B states: legal-move
-mask + graph build + GNN forward + restriction to legal actions) over one batch of B=16384
-synthetic legal positions per GPU  -- BASELINE.json configs[2].  Headline metric: GNN board-evals/s.
-The other two BASELINE metrics (legal-mask positions/s for 1M positions, train samples/s at B=256)
-and, when available, MCTS sims/s are measured after the headline and reported under "extra".
+One "step" = one batched leaf evaluation (BaseNetwork.predict semantics for B states: legal-move mask + graph build +
+GNN forward + restriction to legal actions) over one batch of B = 16,384 synthetic legal positions per GPU --
+BASELINE.json configs[2].  Headline metric: GNN board-evals/s.  The other BASELINE metrics are measured after the
+headline and reported under "extra", each with its own roofline block and the CPU port of the same work timed in the
+same run (rank 0, N = 1 only):
+    extra.legal_mask     configs[1]: legal-move + wall-legality masks of 1,000,000 positions
+    extra.train          configs[0]: forward + loss + backward + (all-reduce) + Adam at B = 256, and at B = 4096
+    extra.mcts           configs[3]: 4,096 lock-step self-play games x 200 simulations per move, WHOLE games
+    extra.train_cycle    configs[4]: the self-play record of extra.mcts -> data-parallel training (one epoch)
 
-`--impl reference` times the CPU port of the reference path (oracle/: C restatement of game_logic
-+ torch restatement of pv_network_gnn) on the host cores; the reference itself is pure Python with
-un-vendored dependencies and cannot travel to the GPU box.
+`--impl reference` times the CPU port of the reference path (oracle/: C restatement of game_logic + torch restatement of
+pv_network_gnn) on the host cores; the reference itself is pure Python with un-vendored dependencies and cannot travel to
+the GPU box.
 """
 import argparse
 import json
@@ -29,10 +33,12 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_BOARD_FWD = 5.79e6
 FLOP_PER_BOARD_FWDBWD = 16.9e6
-BYTES_PER_POSITION_LEGAL = 72    # 32 B packed state in + 32 B mask + 8 B ordered pawn list out (DESIGN.md)
+BYTES_PER_POSITION_LEGAL = 72    # 32 B packed state in + 32 B mask + 8 B ordered pawn list out (DESIGN.md section 4)
 BYTES_PER_BOARD_HEADS = 128 * 4 + 209 * 4 + 4 + 32
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu captures (profiles/*.csv)
-NCU_TRAFFIC_BYTES = {("gcn_forward_kernel", 1, 16384): 632064}  # profiles/r1_v3_kernels_ncu.csv: dram read 0.632064 MB + write 0 of gcn_forward_tc2_kernel (outputs stay in L2)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture
+# named here (a profiler cannot run inside the timed bench; the capture is of the same command line)
+NCU_TRAFFIC = {("gcn_forward_kernel", 1, 16384): (632064, "profiles/r1_v3_kernels_ncu.csv: gcn_forward_tc2_kernel, dram read 0.632 MB + write 0 "
+                                                  "(the 8 MB of pooled output is still in L2 when the kernel ends)")}
 
 
 def peaks():
@@ -72,43 +78,69 @@ def bind_to_gpu_numa(index):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clocks and throttle reasons sampled DURING the timed regions, through NVML in this process (what nvidia-smi itself reads;
+    a process per sample -- round 1 -- costs seconds on a fresh box and takes driver locks that the host path's CUDA calls contend
+    for at N = 8).  Falls back to one long-running `nvidia-smi -lms` child if the NVML bindings are unavailable."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
-        self.index, self.rows, self.stop_flag, self.t = index, [], False, None
+    def __init__(self, index, period=0.1):
+        self.index, self.period, self.rows, self.stop_flag, self.t, self.child, self.source = index, period, [], False, None, None, None
 
-    def _run(self):
+    def _run_nvml(self):
+        import pynvml
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), float(mx), int(rs)))
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(self.period)
+
+    def _run_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.child = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms",
+                                       str(int(self.period * 1000))], stdout=subprocess.PIPE, text=True)
+        for line in self.child.stdout:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) >= 6 and c[0].replace(".", "").isdigit():
+                bits = sum(bit for (_, bit), v in zip(self.REASONS, c[2:6]) if v.lower().startswith("active"))
+                self.rows.append((float(c[0]), float(c[1]), bits))
+            if self.stop_flag:
+                break
 
     def start(self):
-        self.t = threading.Thread(target=self._run, daemon=True)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.source, target = "nvml", self._run_nvml
+        except Exception:
+            self.source, target = "nvidia-smi -lms", self._run_smi
+        self.t = threading.Thread(target=target, daemon=True)
         self.t.start()
 
     def stop(self):
         self.stop_flag = True
+        if self.child is not None:
+            self.child.terminate()
         if self.t:
-            self.t.join(timeout=15)  # a query in flight (nvidia-smi takes seconds on a fresh box) still belongs to the timed region
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+            self.t.join(timeout=10)
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        bits = 0
+        for r in self.rows:
+            bits |= r[2]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": sorted(n for n, b in self.REASONS if bits & b), "samples": len(self.rows), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: CPU port (oracle/) of the same step
+# CPU ports (oracle/) of the same work: the reference arm and every cpu_baseline block
 # ------------------------------------------------------------------------------------------------
 def oracle_random_positions(n, seed):
     """Lock-step random games on the CPU with the C oracle (same move mix as positions.py)."""
@@ -116,7 +148,7 @@ def oracle_random_positions(n, seed):
     rng = np.random.default_rng(seed)
     out_rows, out_plies, total = [], [], 0
     while total < n:
-        G = max(64, n // 32)  # ~32 plies deep, the same mix of game phases as positions.random_positions in run_ours
+        G = max(64, n // 32)  # ~32 plies deep, the same mix of game phases as positions.mixed_batches in run_ours
         rows = np.zeros((G, 68), np.uint8)
         rows[:, [0, 2]] = 76
         rows[:, [1, 3]] = 10
@@ -158,7 +190,7 @@ def oracle_leaf_eval(model, rows, plies, threads):
     return p, v
 
 
-def time_cpu_port(sample, steps, warmup, seed=1):
+def time_cpu_leaf_eval(sample, steps, warmup, seed=1):
     from oracle import gnn_oracle, quoridor_oracle as qo
     qo.build()
     threads = os.cpu_count() or 1
@@ -175,11 +207,94 @@ def time_cpu_port(sample, steps, warmup, seed=1):
     return sample * steps / dt, dt / steps, threads
 
 
+def time_cpu_legal_mask(sample=200_000, seed=3):
+    """BASELINE configs[1] on the host: the C oracle's State.legal_actions() port over `sample` positions, all threads (OpenMP)."""
+    from oracle import quoridor_oracle as qo
+    threads = os.cpu_count() or 1
+    rows, _ = oracle_random_positions(sample, seed)
+    rows = rows[np.random.default_rng(seed).permutation(len(rows))]  # the generator emits plies in order: mix the game phases
+    qo.legal_mask_only(rows[:2000], nthreads=threads)
+    t0 = time.perf_counter()
+    qo.legal_mask_only(rows, nthreads=threads)
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    qo.legal_mask_only(rows[:sample // 8], nthreads=1)
+    dt1 = time.perf_counter() - t1
+    return {"value": sample / dt, "unit": "positions/s", "cores": threads, "kind": "port",
+            "one_thread_positions_per_sec": (sample // 8) / dt1,
+            "sample": f"{sample} synthetic positions (same move mix), C restatement of game_logic.legal_actions (oracle/quoridor_oracle.c, "
+                      f"OpenMP, {threads} threads): {dt:.2f} s; one thread on {sample // 8}: {dt1:.2f} s"}
+
+
+def time_cpu_train(B=256, steps=10, warmup=2, seed=5):
+    """BASELINE configs[0] -- IS the CPU reference path: forward + loss + backward of the oracle network at B = 256 (plus Adam),
+    all host threads and one thread."""
+    from oracle import gnn_oracle
+    rows, _ = oracle_random_positions(B, seed)
+    x, ei, batch = gnn_oracle.graph_inputs_from_rows(rows)
+    torch.manual_seed(1)
+    pt = torch.softmax(torch.randn(B, 209), 1)
+    vt = torch.randint(-1, 2, (B,)).float()
+    out = {}
+    for label, threads, n in (("all", os.cpu_count() or 1, steps), ("one", 1, max(2, steps // 3))):
+        torch.set_num_threads(threads)
+        torch.manual_seed(0)
+        model = gnn_oracle.GraphPolicyValueNetworkOracle().train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+        def one_step():
+            p, v = model(x, ei, batch)
+            loss, _, _ = gnn_oracle.training_loss(p, v, pt, vt)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+
+        for _ in range(warmup):
+            one_step()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            one_step()
+        out[label] = (B * n / (time.perf_counter() - t0), threads, n)
+    torch.set_num_threads(os.cpu_count() or 1)
+    v, threads, n = out["all"]
+    return {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "one_thread_samples_per_sec": out["one"][0],
+            "sample": f"{n} steps (after {warmup} warm-up) of B = {B}: torch-CPU restatement of pv_network_gnn forward + the reference loss + "
+                      f"autograd backward + torch.optim.Adam, {threads} threads; one thread: {out['one'][2]} steps"}
+
+
+def time_cpu_mcts(sims=200, roots=4, seed=7):
+    """BASELINE configs[3] on the host: the port of pv_mcts_policy (oracle/mcts_oracle.py) at `sims` simulations with the torch-CPU
+    GNN oracle as model.predict (batch of one per leaf, as the reference does), on a few mid-game roots, one process."""
+    from oracle import gnn_oracle, mcts_oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model = gnn_oracle.GraphPolicyValueNetworkOracle().eval()
+    rows, plies = oracle_random_positions(2048, seed)
+
+    def predict(state):  # BaseNetwork.predict semantics (pv_network_cnn.py:117-137) for one state
+        x, ei, batch = gnn_oracle.graph_inputs_from_rows(state.row[None, :])
+        with torch.inference_mode():
+            p, v = model(x, ei, batch)
+        pol = p[0][state.legal_actions()]
+        s = pol.sum()
+        return (pol / (s if s else 1)).numpy(), float(v.item())
+
+    pick = np.linspace(0, len(rows) - 1, roots).astype(int)
+    mcts_oracle.pv_mcts_scores(predict, mcts_oracle.COracleState(rows[pick[0]], plies[pick[0]]), 8)  # warm-up
+    t0 = time.perf_counter()
+    for i in pick:
+        mcts_oracle.pv_mcts_scores(predict, mcts_oracle.COracleState(rows[i], plies[i]), sims)
+    dt = time.perf_counter() - t0
+    return {"value": roots * sims / dt, "unit": "simulations/s", "cores": 1, "kind": "port",
+            "sample": f"{roots} roots x {sims} simulations: port of pv_mcts_policy (pv_mcts.py:20-95) over the C game-logic oracle with the "
+                      f"torch-CPU GNN oracle as model.predict (one leaf per call, torch using {os.cpu_count()} threads): {dt:.1f} s"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     sample = 2048
-    value, sec_per_step, threads = time_cpu_port(sample, args.steps, args.warmup)
+    value, sec_per_step, threads = time_cpu_leaf_eval(sample, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "gnn_board_evals_per_sec", "value": value, "unit": "board-evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3,
@@ -198,11 +313,54 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def dp_check(dev, rank, world):
+    """NCCL data-parallel PARITY inside the multi-GPU bench run (scripts/dp_check.py's assertions): three FlatTrainer steps with the
+    batch sharded over the ranks and one all-reduce of the flat gradient per step give the gradients and losses of the
+    single-GPU step on the whole batch, and every rank ends with bit-identical parameters."""
+    import torch.distributed as dist
+    from alphaquoridorgnn_b200 import positions, train_network
+    from alphaquoridorgnn_b200.pv_network_gnn import GNNNetwork
+    B = 250  # not divisible by 4 or 8: the shards differ in size
+    packed = positions.random_positions(B, seed=7, games=64, device=dev)
+    torch.manual_seed(1)
+    pt = torch.softmax(torch.randn(B, 209), 1).to(dev)
+    vt = torch.randint(-1, 2, (B,)).float().to(dev)
+    report = {}
+    for prec in ("fp32", "bf16"):
+        torch.manual_seed(2)
+        dp_net = GNNNetwork().to(dev).train()
+        ref_net = GNNNetwork().to(dev).train()
+        ref_net.load_state_dict(dp_net.state_dict())
+        dp = train_network.FlatTrainer(dp_net, rank=rank, world_size=world, precision=prec)
+        one = train_network.FlatTrainer(ref_net, precision=prec)
+        lo, hi = train_network.shard_bounds(B, rank, world)
+        worst = 0.0
+        for _ in range(3):
+            l_dp = dp.step(packed[lo:hi].contiguous(), pt[lo:hi].contiguous(), vt[lo:hi].contiguous(), B).clone()
+            dist.all_reduce(l_dp)
+            l_one = one.step(packed, pt, vt, B)
+            gerr = ((dp.grads - one.grads).norm() / one.grads.norm()).item()
+            worst = max(worst, gerr)
+            # fp32: summation order only.  bf16: the shard boundaries change which boards share a CTA, not the arithmetic per board, so
+            # the sharded gradient differs from the single-GPU one by the fp32 summation order of the accumulators as well
+            assert abs(l_dp.sum().item() - l_one.sum().item()) < 1e-5 and gerr < (1e-5 if prec == "fp32" else 1e-4), (prec, gerr)
+        mine = dp.flat.clone()
+        ref0 = mine.clone()
+        dist.broadcast(ref0, 0)
+        same = torch.tensor([1 if torch.equal(mine, ref0) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        assert int(same.item()) == 1, "ranks diverged"
+        report[prec] = {"grad_rel_l2_vs_single_gpu": worst, "ranks_bit_identical": True}
+    if rank == 0:
+        print(f"dp_check ok (world {world}): {json.dumps(report)}", file=sys.stderr, flush=True)
+    return report
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
-    from alphaquoridorgnn_b200 import _lib, positions
+    from alphaquoridorgnn_b200 import _lib, positions, self_play, train_network
     from alphaquoridorgnn_b200 import game_logic as gl
-    from alphaquoridorgnn_b200.pv_network_gnn import GNNNetwork, PRECISIONS
+    from alphaquoridorgnn_b200.pv_network_gnn import GNNNetwork, HostLeafEvaluator, PRECISIONS
 
     numa = bind_to_gpu_numa(local_rank)
     torch.cuda.set_device(local_rank)
@@ -235,31 +393,36 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def step(i):
-        _lib.check(L.aq_leaf_eval(P(flat), P(prep), P(batches[i % nb]), B, P(priors), P(value), P(mask), P(pawn), P(pooled), prec, st),
-                   "aq_leaf_eval")
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     def timed(fn, n, warm):
-        """n launches of fn(i), L2 flushed before each, per-launch CUDA events on the launch stream."""
+        """n launches of fn(i), L2 flushed before each, per-launch CUDA events on the launch stream -> (max over ranks of the
+        mean ms per launch, this library's kernel launches per call, counted)."""
         for i in range(warm):
             fn(i)
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         barrier()
+        c0 = L.aq_launch_count()
         for i in range(n):
             flush.fill_(i & 0xFF)
             evs[i][0].record()
             fn(i)
             evs[i][1].record()
+        launches = L.aq_launch_count() - c0
         barrier()
-        ms = [a.elapsed_time(b) for a, b in evs]
-        tot = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-        return float(tot.item()) / n  # max over ranks of the mean ms per launch
+        return reduce_max(sum(a.elapsed_time(b) for a, b in evs) / n), launches
+
+    def step(i, precision=prec, prepared=prep):
+        _lib.check(L.aq_leaf_eval(P(flat), P(prepared), P(batches[i % nb]), B, P(priors), P(value), P(mask), P(pawn), P(pooled), precision, st),
+                   "aq_leaf_eval")
 
     sampler = ClockSampler(local_rank)  # samples clocks / throttle reasons during ALL timed regions below
     sampler.start()
-    ms_step = timed(step, K, Wm)
+    ms_step, gpu_launches = timed(step, K, Wm)
     value_main = world * B / (ms_step * 1e-3)
 
     # ---- per-kernel durations (same inputs, same stream) for the roofline ------------------------
@@ -272,8 +435,8 @@ def run_ours(args, rank, world, local_rank):
     def k_heads(i):
         _lib.check(L.aq_heads_forward(P(flat), P(prep), P(pooled), B, P(priors), P(value), P(mask), prec, st), "aq_heads_forward")
 
-    kms = {"legal_mask_kernels": timed(k_legal, K, 2), "gcn_forward_kernel": timed(k_trunk, K, 2),
-           "heads_forward_kernel": timed(k_heads, K, 2)}
+    kms = {"legal_mask_kernels": timed(k_legal, K, 2)[0], "gcn_forward_kernel": timed(k_trunk, K, 2)[0],
+           "heads_forward_kernel": timed(k_heads, K, 2)[0]}
     ksum = sum(kms.values())
     kinfo = {
         "legal_mask_kernels": {"bound": "hbm", "achieved": BYTES_PER_POSITION_LEGAL * B / (kms["legal_mask_kernels"] * 1e-3) / 1e9,
@@ -288,144 +451,203 @@ def run_ours(args, rank, world, local_rank):
         v["share_of_step"] = kms[k] / ksum
         v["frac"] = v["achieved"] / v["peak"]
     dom = max(kms, key=kms.get)
-    # DRAM traffic per launch of the dominant kernel from `ncu --set full` (profiles/): the trunk reads the packed
-    # states and 256 KB of weights and writes pooled [B,128]; everything else stays in shared memory / TMEM.
-    traffic = NCU_TRAFFIC_BYTES.get((dom, prec, B))
+    traffic = NCU_TRAFFIC.get((dom, prec, B), (None, "no ncu capture for this configuration"))
     roofline = {"kernel": dom, "bound": kinfo[dom]["bound"], "achieved": kinfo[dom]["achieved"], "peak": kinfo[dom]["peak"],
-                "unit": kinfo[dom]["unit"], "frac": kinfo[dom]["frac"], "traffic": traffic, "peak_source": pk["source"],
+                "unit": kinfo[dom]["unit"], "frac": kinfo[dom]["frac"], "traffic": traffic[0], "traffic_source": traffic[1],
+                "peak_source": pk["source"],
                 "arith": "fp32 FFMA" if prec == 0 else "bf16 tcgen05 node transforms + fp16 tcgen05 aggregation, fp32 accumulate in TMEM",
                 "kernel_symbol": "gcn_forward_fp32_kernel" if prec == 0 else "gcn_forward_tc2_kernel"}
 
-    # ---- end to end through host buffers, every step: pinned packed states H2D, kernels, results D2H, stream sync ----
-    # Headline e2e = the repo's public host API (pv_network_gnn.HostLeafEvaluator -> aq_leaf_eval_host_compact): results in
-    # the shape BaseNetwork.predict returns them (probabilities of the LEGAL actions only, legal_actions() order, ragged),
-    # plus value / legal mask / pawn list.  The dense [B,209] flavour (aq_leaf_eval_host) is reported in extra.
-    from alphaquoridorgnn_b200.pv_network_gnn import HostLeafEvaluator
+    # ---- end to end through host buffers, every step: pinned packed states H2D, kernels, results D2H, one event wait ----
     hst = [torch.from_numpy(gl.pack_rows_host(*[t.cpu().numpy() for t in gl.unpack_rows(b)])).pin_memory() for b in batches]
     for h, b in zip(hst, batches):
         assert torch.equal(h, b.cpu())
 
-    def e2e_run(dense):
-        ev = HostLeafEvaluator(net, B, dense=dense)
-        d2h = []
-
-        def e2e_step(i):
-            d2h.append(ev.d2h_bytes(ev.evaluate(B, states=hst[i % nb])))  # synchronous: results are on the host when it returns
-
-        for i in range(3):
-            e2e_step(i)
-        del d2h[:]
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(K):
-            e2e_step(i)
-        barrier()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        ev.close()
-        return world * B * K / float(dt.item()), int(sum(d2h) / len(d2h))
-
-    def e2e_pipelined():
-        """Two evaluators (two pools of games) alternate: while the host waits for one batch, the other batch's kernels run and
-        the first one's results cross PCIe.  Every step still moves its own states H2D and its own results D2H."""
-        evs = [HostLeafEvaluator(net, B), HostLeafEvaluator(net, B)]
+    def e2e_pipelined(inflight, **kw):
+        """`inflight` evaluators (pools of games) used round-robin: while the host waits for one batch, the others' kernels run and
+        their results cross PCIe.  Every step still moves its own states H2D and its own results D2H inside the timed region."""
+        evs = [HostLeafEvaluator(net, B, **kw) for _ in range(inflight)]
         d2h = []
 
         def run(n):
-            evs[0].submit(B, states=hst[0])
+            for j in range(min(inflight - 1, n)):
+                evs[j].submit(B, states=hst[j % nb])
             for i in range(n):
-                if i + 1 < n:
-                    evs[(i + 1) & 1].submit(B, states=hst[(i + 1) % nb])
-                out = evs[i & 1].wait()
-                d2h.append(evs[i & 1].d2h_bytes(out))
+                j = i + inflight - 1
+                if j < n:
+                    evs[j % inflight].submit(B, states=hst[j % nb])
+                out = evs[i % inflight].wait()
+                d2h.append(evs[i % inflight].d2h_bytes(out))
 
-        run(4)
+        run(2 * inflight + 2)
         del d2h[:]
         barrier()
         t0 = time.perf_counter()
         run(K)
         barrier()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = reduce_max(time.perf_counter() - t0)
+        short = sum(ev.stats()[0] for ev in evs)
         for ev in evs:
             ev.close()
-        return world * B * K / float(dt.item()), int(sum(d2h) / len(d2h))
+        return world * B * K / dt, int(sum(d2h) / len(d2h)), short
 
-    e2e_v, e2e_d2h = e2e_pipelined()
+    def e2e_sync(dense):
+        ev = HostLeafEvaluator(net, B, dense=dense)
+        d2h = []
+        for i in range(3):
+            ev.evaluate(B, states=hst[i % nb])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            d2h.append(ev.d2h_bytes(ev.evaluate(B, states=hst[i % nb])))  # synchronous: results are on the host when it returns
+        barrier()
+        dt = reduce_max(time.perf_counter() - t0)
+        ev.close()
+        return world * B * K / dt, int(sum(d2h) / len(d2h))
+
+    def d2h_ceiling(nbytes, reps=40):
+        """What this box's device -> host path gives one plain pinned cudaMemcpyAsync loop per rank, all ranks at once."""
+        src = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        dst = torch.empty((nbytes,), dtype=torch.uint8).pin_memory()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        barrier()
+        return nbytes * reps / reduce_max(time.perf_counter() - t0) / 1e9
+
+    wire = "f16" if prec == 1 else "f32"
+    e2e_v, e2e_d2h, e2e_short = e2e_pipelined(3, wire=wire, with_mask=False)
     e2e = {"value": e2e_v, "unit": "board-evals/s", "h2d_bytes_per_step": B * 32, "d2h_bytes_per_step": e2e_d2h,
-           "api": "HostLeafEvaluator.submit / wait -> aq_leaf_eval_host_compact_submit / _wait: predict()-shaped ragged priors (legal "
-                  "actions only) + value + legal mask + pawn list; two batches in flight (two evaluators used alternately)"}
-    sync_v, sync_d2h = e2e_run(dense=False)
-    dense_v, dense_d2h = e2e_run(dense=True)
+           "api": f"HostLeafEvaluator(wire='{wire}', with_mask=False).submit / wait -> aq_leaf_eval_host_compact_submit / _wait: what "
+                  "BaseNetwork.predict returns for a batch (ragged priors of the legal actions in legal_actions() order + value); three "
+                  "batches in flight (three evaluators used round-robin); one event wait per batch",
+           "ragged_copies_completed_by_a_second_copy": e2e_short}
+    ceil_gbs = d2h_ceiling(max(1 << 20, e2e_d2h))
+    e2e["d2h_ceiling_gbs_per_gpu"] = ceil_gbs
+    e2e["d2h_achieved_gbs_per_gpu"] = e2e_d2h * (e2e_v / world / B) / 1e9
+    extra = {}
+    v32, d32, _ = e2e_pipelined(3, wire="f32", with_mask=True)
+    extra["e2e_f32_wire_with_mask_and_pawn"] = {"value": v32, "unit": "board-evals/s", "d2h_bytes_per_step": d32,
+                                                "api": "the round-1 result set (f32 ragged priors + value + legal mask + pawn list), three in flight"}
+    sync_v, sync_d2h = e2e_sync(dense=False)
+    dense_v, dense_d2h = e2e_sync(dense=True)
+    extra["e2e_one_batch_in_flight"] = {"value": sync_v, "unit": "board-evals/s", "d2h_bytes_per_step": sync_d2h,
+                                        "api": "HostLeafEvaluator.evaluate (synchronous, one caller): aq_leaf_eval_host_compact"}
+    extra["e2e_dense_priors"] = {"value": dense_v, "unit": "board-evals/s", "d2h_bytes_per_step": dense_d2h,
+                                 "api": "aq_leaf_eval_host (synchronous): dense priors [B,209]"}
+    cpu_ok = rank == 0 and world == 1 and not args.skip_cpu
 
-    extra = {"e2e_one_batch_in_flight": {"value": sync_v, "unit": "board-evals/s", "d2h_bytes_per_step": sync_d2h,
-                                         "api": "HostLeafEvaluator.evaluate (synchronous, one caller): aq_leaf_eval_host_compact"},
-             "e2e_dense_priors": {"value": dense_v, "unit": "board-evals/s", "d2h_bytes_per_step": dense_d2h,
-                                  "api": "aq_leaf_eval_host (synchronous): dense priors [B,209]"}}
     if not args.skip_extra:
-        # legal mask, BASELINE configs[1]: 1M positions resident in HBM (32 MB in, 40 MB out > L2? no: flushed)
+        # ---- the fp32 (FFMA) leaf evaluation beside the bf16 headline --------------------------------------------------------
+        if prec == 1:
+            ms32, _ = timed(lambda i: step(i, 0, None), max(3, K // 4), 2)
+            extra["leaf_eval_fp32"] = {"value": world * B / (ms32 * 1e-3), "unit": "board-evals/s", "ms_per_step": ms32,
+                                       "note": "the same step with precision fp32 (FFMA trunk and heads): the arithmetic of the reference"}
+        # ---- legal mask, BASELINE configs[1]: 1M positions resident in HBM ----------------------------------------------------
         M = 1_000_000
         big = positions.random_positions(M, seed=101 + rank, games=16384, device=dev)
         bmask = torch.empty((M, 8), dtype=torch.int32, device=dev)
         bpawn = torch.empty((M, 8), dtype=torch.uint8, device=dev)
         bws = torch.empty((L.aq_legal_mask_ws_bytes(M),), dtype=torch.uint8, device=dev)
-        ms = timed(lambda i: _lib.check(L.aq_legal_mask_ws(P(big), M, P(bmask), P(bpawn), P(bws), bws.numel(), st), "aq_legal_mask_ws"), 5, 2)
-        extra["legal_mask_positions_per_sec"] = world * M / (ms * 1e-3)
-        extra["legal_mask_ms_per_1M"] = ms
-        extra["legal_mask_hbm_frac"] = BYTES_PER_POSITION_LEGAL * M / (ms * 1e-3) / 1e9 / pk["hbm"]
+        ms, _ = timed(lambda i: _lib.check(L.aq_legal_mask_ws(P(big), M, P(bmask), P(bpawn), P(bws), bws.numel(), st), "aq_legal_mask_ws"), 5, 2)
+        gbs = BYTES_PER_POSITION_LEGAL * M / (ms * 1e-3) / 1e9
+        extra["legal_mask"] = {"value": world * M / (ms * 1e-3), "unit": "positions/s", "ms_per_1M": ms,
+                               "config": "BASELINE configs[1]: 1,000,000 random legal positions per GPU (plies 0..61), two-phase kernel pair",
+                               "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                                            "note": "HBM by rule (72 B per position); the kernels are integer-issue bound (DESIGN.md section 4)"},
+                               "cpu_baseline": time_cpu_legal_mask() if cpu_ok else None}
         del big, bmask, bpawn, bws
-        # training step (forward + loss + backward + gradient all-reduce + Adam), random targets:
-        #   B=256  -- BASELINE configs[0] shape (what one optimizer step of the reference looks like)
-        #   B=4096 -- the same step at a throughput-sized per-GPU batch
-        def train_bench(TB):
+
+        # ---- training step through the public trainer (forward + loss + backward + gradient all-reduce + Adam), random targets ----
+        def train_bench(TB, precision):
+            torch.manual_seed(0)
+            tnet = GNNNetwork().to(dev).train()
+            trainer = train_network.FlatTrainer(tnet, rank=rank, world_size=world, precision=precision)
             tb = allpos[:TB].contiguous()
             torch.manual_seed(1)
             pt = torch.softmax(torch.randn(TB, 209, device=dev), 1)
             vt = torch.randint(-1, 2, (TB,), device=dev).float()
-            tflat = flat.clone()
-            saved = torch.empty((L.aq_gnn_saved_floats(TB),), dtype=torch.float32, device=dev)
-            bws = torch.empty((L.aq_gnn_backward_ws_floats(TB),), dtype=torch.float32, device=dev)
-            tp = torch.empty((TB, 209), dtype=torch.float32, device=dev)
-            tv = torch.empty((TB,), dtype=torch.float32, device=dev)
-            dp, dv = torch.empty_like(tp), torch.empty_like(tv)
-            grads, m1, m2 = torch.empty_like(tflat), torch.zeros_like(tflat), torch.zeros_like(tflat)
-            loss = torch.zeros(2, device=dev)
-            stepno = [0]
-            tprec = prec  # training arithmetic follows --precision (bf16 = tcgen05 trunk forward/backward, fp32 accumulate)
+            return timed(lambda i: trainer.step(tb, pt, vt, TB * world), 20, 5)
 
-            def train_step(i):
-                stepno[0] += 1
-                _lib.check(L.aq_gnn_forward(P(tflat), P(tb), None, None, TB, P(tp), P(tv), P(saved), tprec, st), "fwd")
-                _lib.check(L.aq_loss_grad(P(tp), P(tv), P(pt), P(vt), TB, TB * world, P(loss), P(dp), P(dv), st), "loss")
-                _lib.check(L.aq_gnn_backward(P(tflat), P(saved), P(dp), P(dv), TB, P(grads), P(bws), tprec, st), "bwd")
-                if world > 1:
-                    dist.all_reduce(grads)
-                _lib.check(L.aq_adam_step(P(tflat), P(grads), P(m1), P(m2), tflat.numel(), stepno[0], 1e-3, 0.9, 0.999, 1e-8,
-                                          1.0, st), "adam")
+        tr = {}
+        for TB in (256, 4096):
+            ms, launches = train_bench(TB, args.precision)
+            tf = FLOP_PER_BOARD_FWDBWD * TB / (ms * 1e-3) / 1e12
+            tr[f"B{TB}"] = {"value": world * TB / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "kernel_launches_per_step": launches / 20,
+                            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tf / pk["tensor"]}}
+        if prec == 1:
+            ms, _ = train_bench(256, "fp32")
+            tr["B256_fp32"] = {"value": world * 256 / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms}
+        tr["config"] = ("BASELINE configs[0] shape (B = 256 per GPU) and a throughput-sized batch (B = 4096 per GPU): FlatTrainer.step = "
+                        "aq_gnn_forward(saved) + aq_loss_grad + aq_gnn_backward + all-reduce of the flat gradient + aq_adam_step")
+        tr["cpu_baseline"] = time_cpu_train() if cpu_ok else None
+        extra["train"] = tr
 
-            return timed(train_step, 20, 5)
-
-        ms = train_bench(256)
-        extra["train_samples_per_sec"] = world * 256 / (ms * 1e-3)
-        extra["train_ms_per_step_B256"] = ms
-        ms = train_bench(4096)
-        extra["train_samples_per_sec_B4096"] = world * 4096 / (ms * 1e-3)
-        extra["train_ms_per_step_B4096"] = ms
-        extra["train_tensor_frac_B4096"] = FLOP_PER_BOARD_FWDBWD * 4096 / (ms * 1e-3) / 1e12 / pk["tensor"]
+        # ---- lock-step PV-MCTS self-play, WHOLE games (BASELINE configs[3]) and training on that record (configs[4]) ----------
         try:
-            from alphaquoridorgnn_b200 import pv_mcts
-            extra.update(pv_mcts.bench_sims_per_sec(net, dev, world, timed_barrier=barrier))
-        except Exception as e:  # MCTS is a "next" row; absence must not break the headline
+            G, SIMS = args.mcts_games, args.mcts_sims
+            self_play.play_batch_device(net, G, dev, sims=SIMS, seed=4, max_plies=1)  # warm-up: module loads, first graph capture
+            barrier()
+            t0 = time.perf_counter()
+            rec = self_play.play_batch_device(net, G, dev, sims=SIMS, seed=5 + rank, policy_dtype=torch.float32)
+            barrier()
+            dt = reduce_max(time.perf_counter() - t0)
+            tot = torch.tensor([rec["sims"], rec["states"].shape[0], int((rec["flags"] & 1).sum()), int(rec["plies"].sum())],
+                               dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tot)
+            sims_s = float(tot[0]) / dt
+            tf = sims_s * FLOP_PER_BOARD_FWD / 1e12
+            extra["mcts"] = {"value": sims_s, "unit": "simulations/s", "seconds": dt, "games": G * world, "sims_per_move": SIMS,
+                             "positions": int(tot[1]), "decided_games": int(tot[2]), "mean_plies_per_game": float(tot[3]) / (G * world),
+                             "config": f"BASELINE configs[3]: {G} concurrent self-play games per GPU x {SIMS} simulations per move, whole games "
+                                       "(start position to win / 116-ply draw), T = 1 sampling; every simulation = select + leaf evaluation "
+                                       "(legal mask + GNN) + expand/backup, replayed as one CUDA graph",
+                             "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tf / pk["tensor"],
+                                          "note": "one leaf evaluation (5.79 MFLOP) per simulation; the tree kernels are HBM/latency work"},
+                             "cpu_baseline": time_cpu_mcts(SIMS) if cpu_ok else None}
+            # configs[4]: the buffer just produced -> one epoch of data-parallel training at the reference's batch size per GPU
+            torch.manual_seed(0)
+            tnet = GNNNetwork().to(dev).train()
+            tnet.train_precision = args.precision
+            Mrec = int(rec["states"].shape[0])
+            Muse = Mrec // (128 * 1) * 128   # whole batches; every rank trains on its own record, gradients all-reduced (global batch 128 x world)
+            if world > 1:
+                mm = torch.tensor([Muse], device=dev)
+                dist.all_reduce(mm, op=dist.ReduceOp.MIN)
+                Muse = int(mm.item())
+            trainer = train_network.FlatTrainer(tnet, rank=rank, world_size=world)
+            perm = torch.randperm(Muse, device=dev)
+            sp, pp, vv = rec["states"][:Muse][perm].contiguous(), rec["policy"][:Muse][perm].contiguous(), rec["value"][:Muse][perm].contiguous()
+            nsteps = min(Muse // 128, 400)
+            for i in range(5):
+                trainer.step(sp[i * 128:(i + 1) * 128], pp[i * 128:(i + 1) * 128], vv[i * 128:(i + 1) * 128], 128 * world)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(nsteps):
+                trainer.step(sp[i * 128:(i + 1) * 128], pp[i * 128:(i + 1) * 128], vv[i * 128:(i + 1) * 128], 128 * world)
+            barrier()
+            dt = reduce_max(time.perf_counter() - t0)
+            extra["train_cycle"] = {"value": world * 128 * nsteps / dt, "unit": "samples/s", "steps": nsteps, "ms_per_step": dt / nsteps * 1e3,
+                                    "config": "BASELINE configs[4]: the self-play record above (device-resident) -> data-parallel training, "
+                                              "batch 128 per GPU (train_network.py:15), one all-reduce of the flat gradient per step, wall clock "
+                                              "including the host loop"}
+            del rec, sp, pp, vv
+        except Exception as e:  # the callers of the hot path must not take the headline down with them
             extra["mcts"] = f"unavailable: {type(e).__name__}: {e}"
+
+    if world > 1:
+        extra["dp_check"] = dp_check(dev, rank, world)
 
     clocks = sampler.stop()
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.skip_cpu:
-        cpu_steps = 5
-        v, sec, threads = time_cpu_port(B, cpu_steps, 1)
+    if cpu_ok:
+        cpu_steps = 3
+        v, sec, threads = time_cpu_leaf_eval(B, cpu_steps, 1)
         cpu_baseline = {"value": v, "unit": "board-evals/s", "cores": threads, "kind": "port",
                         "sample": f"{cpu_steps} steps (1 warm-up) of {B} positions: C oracle legal_actions (OpenMP, {threads} threads) + "
                                   f"torch CPU GNN forward + legal renorm; {sec:.1f} s per step"}
@@ -445,7 +667,7 @@ def run_ours(args, rank, world, local_rank):
             # step is shorter than the sum of its kernels timed alone
             "sum_of_kernels_timed_alone_ms": ksum,
             "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": 4 * K,  # legal_prepare + legal_search + trunk + heads per step (plus one 4-byte memset)
+            "gpu_launches": int(gpu_launches),  # counted by the library (aq_launch_count) over the K timed steps
             "clocks": clocks, "extra": extra,
         }
         print(json.dumps(line), flush=True)
@@ -460,6 +682,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16384)
     ap.add_argument("--precision", default=os.environ.get("AQ_PRECISION", "bf16"), choices=["fp32", "bf16"],
                     help="GNN inference arithmetic: bf16 = tcgen05 tensor cores (default), fp32 = FFMA")
+    ap.add_argument("--mcts-games", type=int, default=4096)
+    ap.add_argument("--mcts-sims", type=int, default=200)
     ap.add_argument("--skip-extra", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()

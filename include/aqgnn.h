@@ -56,6 +56,9 @@ typedef struct AqState {
 #define AQ_VERSION 200 /* bumped with every change of a signature below; the ctypes loader refuses a library of another version */
 int aq_version(void);
 const char *aq_last_error_string(void);
+/* Number of kernels this library has launched in the process so far (monotonic; kernels replayed through a CUDA graph the caller
+ * captured are counted once, at capture).  Lets a benchmark report measured launch counts. */
+int64_t aq_launch_count(void);
 
 /* State.to_array() rows ("row68": uint8[68] = player[2], enemy[2], walls[64]) <-> AqState.
  * Replaces the python list handling of game_logic.py:96-100. */

@@ -112,3 +112,31 @@ def test_open_mask_symmetric_and_edge_count(traj):
     nwalls = (rows[:, 4:] != 0).sum(axis=1)
     edges = np.unpackbits(opn.reshape(len(rows), -1), axis=1).sum(axis=1)
     assert np.array_equal(edges, 288 - 4 * nwalls)  # legal positions: every wall severs 4 directed edges
+
+
+def test_mcts_port_matches_reference_visit_counts(mcts_golden):
+    """oracle/mcts_oracle.py (the CPU baseline of the MCTS metric) against the visit counts of the UNMODIFIED reference
+    pv_mcts_policy (tests/golden/make_golden.py: deterministic hash / uniform evaluators)."""
+    from oracle import mcts_oracle
+
+    def hash_predict(state):
+        r = [int(v) for v in state.row]
+        key = (sum(v * (i + 1) * 7919 for i, v in enumerate(r)) + state.plies_played * 104729) % (2 ** 31)
+        la = state.legal_actions()
+        raw = np.array([(key + a * 40503) % 1009 + 1 for a in la], dtype=np.int64)
+        return raw.astype(np.float32) / np.float32(raw.sum()), float(np.float32((key % 2001) - 1000) / np.float32(1000))
+
+    def uniform_predict(state):
+        la = state.legal_actions()
+        return np.full(len(la), 1.0 / len(la), dtype=np.float32), 0.0
+
+    checked = 0
+    for case in mcts_golden["roots"]:
+        if case["sims"] != 50 and checked >= 20:   # the 200-simulation cases: a few are enough for the CPU suite's time budget
+            continue
+        st = mcts_oracle.COracleState(np.array(case["row"], np.uint8), case["plies"])
+        assert st.legal_actions() == case["legal_actions"]
+        counts = mcts_oracle.pv_mcts_scores(hash_predict if case["evaluator"] == "hash" else uniform_predict, st, case["sims"])
+        assert counts == case["visit_counts"], (case["evaluator"], case["sims"])
+        checked += 1
+    assert checked >= 16
