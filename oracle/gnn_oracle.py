@@ -173,3 +173,49 @@ def dense_forward_fp64(state_dict, rows):
         h = np.maximum(sd["value_head.0.weight"] @ g + sd["value_head.0.bias"], 0.0)
         val[b] = np.tanh(sd["value_head.2.weight"] @ h + sd["value_head.2.bias"])
     return pol, val
+
+
+# ---- the tensor-core path's rounding points, emulated (test infrastructure) -----------------------------------------------
+class _Round(torch.autograd.Function):
+    """x -> x rounded to bfloat16 / float16 and back, gradient passed straight through: what storing an operand in a 16-bit tile
+    does to the forward pass, with the backward pass seeing the rounded operand (as the kernels' saved tiles do)."""
+
+    @staticmethod
+    def forward(ctx, t, dtype):
+        return t.to(torch.float32).to(dtype).to(t.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def forward_tc_emulation(model, x, edge_index, batch):
+    """GraphPolicyValueNetworkOracle.forward with the rounding points of the bf16 tensor-core path and exact
+    (caller's dtype, normally float64) accumulation everywhere else:
+      trunk  W1, W2, W3 -> bf16; X1, X2 -> bf16 (the feature-major tiles); Z2, Z3 -> fp16 and the A_hat coefficients -> fp16 (the
+             aggregation MMA's operands); layer 1's 6-wide input is carried as a bf16 hi/lo pair (~16 mantissa bits: left exact here);
+             the last layer feeds the mean pool from the fp32 accumulator (no rounding);
+      heads  pooled -> bf16, Wp0, Wv0, Wp2 -> bf16, policy hidden -> bf16; the value head's second layer, biases, softmax and tanh in
+             full precision.
+    Comparing the CUDA path with THIS isolates kernel errors from the error bf16 operands imply (the difference between this and the
+    exact forward is what the stated bf16 tolerances cover)."""
+    bf, hf = torch.bfloat16, torch.float16
+    src, dst, w = gcn_norm(edge_index, x.shape[0], x.dtype)
+    h = x
+    n_layers = len(model.gcn_layers)
+    for i, layer in enumerate(model.gcn_layers):
+        z = h @ _Round.apply(layer.lin.weight, bf).t()
+        we = w
+        if i > 0:
+            z, we = _Round.apply(z, hf), _Round.apply(w, hf)
+        out = torch.zeros_like(z).index_add_(0, dst, we.unsqueeze(1) * z[src]) + layer.bias
+        h = F.relu(out)
+        if i + 1 < n_layers:
+            h = _Round.apply(h, bf)
+    g = _Round.apply(global_mean_pool(h, batch), bf)
+    ph, vh = model.policy_head, model.value_head
+    hp = _Round.apply(F.relu(g @ _Round.apply(ph[0].weight, bf).t() + ph[0].bias), bf)
+    policy = torch.softmax(hp @ _Round.apply(ph[2].weight, bf).t() + ph[2].bias, dim=1)
+    hv = F.relu(g @ _Round.apply(vh[0].weight, bf).t() + vh[0].bias)
+    value = torch.tanh(hv @ vh[2].weight.t() + vh[2].bias)
+    return policy, value

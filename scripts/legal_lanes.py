@@ -1,4 +1,5 @@
-"""Legal-mask kernel time by batch size and lanes per state (AQ_LEGAL_LANES = 2 / 8 / 32), mixed game phases.
+"""Legal-mask time by batch size, mixed game phases: the one-kernel form (aq_legal_mask: 32 / 8 / 2 lanes per state by batch size)
+against the two-phase form with a workspace (aq_legal_mask_ws, which itself takes the one-kernel form up to 4,096 states).
    python scripts/legal_lanes.py"""
 import os
 import sys
@@ -16,21 +17,17 @@ mask = torch.empty((1 << 20, 8), dtype=torch.int32, device="cuda")
 pawn = torch.empty((1 << 20, 8), dtype=torch.uint8, device="cuda")
 st = _lib.stream_ptr()
 lws = torch.empty((L.aq_legal_mask_ws_bytes(1 << 20),), dtype=torch.uint8, device="cuda")
-print("B, " + ", ".join(f"one-kernel lanes={l} us" for l in (2, 8, 32)) + ", aq_legal_mask (one kernel, lanes by batch size) us, aq_legal_mask_ws (two-phase above 4096 states) us")
-for B in (256, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072, 262144, 1 << 20):
+print("B, aq_legal_mask (one kernel, lanes by batch size) us, aq_legal_mask_ws (two-phase above 4096 states) us")
+for B in (256, 1024, 2048, 4096, 4097, 8192, 16384, 32768, 65536, 131072, 262144, 1 << 20):
     row = []
-    for lanes in (2, 8, 32, 0, -1):
-        if lanes > 0:
-            os.environ["AQ_LEGAL_LANES"] = str(lanes)
-        else:
-            os.environ.pop("AQ_LEGAL_LANES", None)
+    for two_phase in (False, True):
         ts = []
         for it in range(8):
             x = allpos[(it * B) % ((1 << 20) - B + 1):][:B]
             flush.fill_(it)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            if lanes == -1:
+            if two_phase:
                 _lib.check(L.aq_legal_mask_ws(P(x), B, P(mask), P(pawn), P(lws), lws.numel(), st), "aq_legal_mask_ws")
             else:
                 _lib.check(L.aq_legal_mask(P(x), B, P(mask), P(pawn), st), "aq_legal_mask")
