@@ -41,10 +41,14 @@ struct HeadBwdSmem {
     float dh[kHbThreads / 32][2 * kHH];  // dhp | dhv
 };
 
+// kLoss: the loss gradient of train_network.py:54-55,85-89 (loss_grad_kernel below, same expressions in the same order) is computed
+// here from the saved network outputs and the targets instead of being read from dpolicy / dvalue: one launch and one
+// [B,209] round trip less per training step.
+template <bool kLoss>
 __global__ void __launch_bounds__(kHbThreads, 1)
-heads_backward_kernel(const float *__restrict__ params, const float *__restrict__ saved,
-                      const float *dpolicy, const float *dvalue, int64_t B,
-                      float *__restrict__ ws) {
+heads_backward_kernel(const float *__restrict__ params, const float *saved,   // saved: written by the kernel this one may overlap -- no __restrict__ (PDL rule)
+                      const float *dpolicy, const float *dvalue, const float *__restrict__ ptarget, const float *__restrict__ vtarget,
+                      float inv_total, float *__restrict__ loss, int64_t B, float *__restrict__ ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeadBwdSmem &sm = *reinterpret_cast<HeadBwdSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -65,16 +69,65 @@ heads_backward_kernel(const float *__restrict__ params, const float *__restrict_
     const SavedLayout L{B};
     const BwdWs W{B};
     const int nwarps = (int)blockDim.x >> 5;
+    float loss_p = 0.f, loss_v = 0.f;
     for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
         __syncwarp();
         // softmax backward: dz = p * (dp - sum_j dp_j p_j)
         float p[7], dp[7], s = 0.f;
+        float dval;
+        if (kLoss) {
+            // CrossEntropyLoss(input = softmax probabilities, target = probabilities): -sum_a t_a log_softmax(p)_a -- the second
+            // softmax is the reference's behaviour -- and MSELoss, both 'mean' over the global batch
+            float tg[7], mx = -INFINITY;
 #pragma unroll
-        for (int t = 0; t < 7; ++t) {
-            const int a = lane + 32 * t;
-            p[t] = a < kP ? saved[L.policy() + b * kP + a] : 0.f;
-            dp[t] = a < kP ? __ldcg(dpolicy + b * kP + a) : 0.f;  // written by the loss kernel this grid may overlap: coherent load (PDL rule, aq_common.cuh)
-            s = fmaf(dp[t], p[t], s);
+            for (int t = 0; t < 7; ++t) {
+                const int a = lane + 32 * t;
+                p[t] = a < kP ? __ldcg(saved + L.policy() + b * kP + a) : -INFINITY;
+                tg[t] = a < kP ? __ldg(ptarget + b * kP + a) : 0.f;
+                mx = fmaxf(mx, p[t]);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            float se = 0.f, tsum = 0.f;
+#pragma unroll
+            for (int t = 0; t < 7; ++t) {
+                if (lane + 32 * t < kP) se += expf(p[t] - mx);
+                tsum += tg[t];
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                se += __shfl_xor_sync(0xffffffffu, se, d);
+                tsum += __shfl_xor_sync(0xffffffffu, tsum, d);
+            }
+            const float lse = mx + logf(se);
+            float l = 0.f;
+#pragma unroll
+            for (int t = 0; t < 7; ++t) {
+                if (lane + 32 * t < kP) {
+                    const float ls = p[t] - lse;
+                    l -= tg[t] * ls;
+                    dp[t] = (expf(ls) * tsum - tg[t]) * inv_total;
+                } else {
+                    p[t] = 0.f;
+                    dp[t] = 0.f;
+                }
+                s = fmaf(dp[t], p[t], s);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) l += __shfl_xor_sync(0xffffffffu, l, d);
+            const float dv0 = __ldcg(saved + L.value() + b) - __ldg(vtarget + b);
+            dval = 2.f * dv0 * inv_total;
+            loss_p += l;
+            loss_v += dv0 * dv0;
+        } else {
+#pragma unroll
+            for (int t = 0; t < 7; ++t) {
+                const int a = lane + 32 * t;
+                p[t] = a < kP ? saved[L.policy() + b * kP + a] : 0.f;
+                dp[t] = a < kP ? __ldcg(dpolicy + b * kP + a) : 0.f;  // written by the loss kernel this grid may overlap: coherent load (PDL rule, aq_common.cuh)
+                s = fmaf(dp[t], p[t], s);
+            }
+            dval = __ldcg(dvalue + b);
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
@@ -99,7 +152,7 @@ heads_backward_kernel(const float *__restrict__ params, const float *__restrict_
         h1 = hp1 > 0.f ? h1 : 0.f;
         // value head: v = tanh(u); du = dv * (1 - v^2); dhv = du * wv2 * (hv > 0)
         const float v = saved[L.value() + b];
-        const float du = __ldcg(dvalue + b) * (1.f - v * v);
+        const float du = dval * (1.f - v * v);
         const float hv0 = saved[L.hv() + b * kHH + lane], hv1 = saved[L.hv() + b * kHH + lane + 32];
         const float g0 = hv0 > 0.f ? du * sm.wv2[lane] : 0.f;
         const float g1 = hv1 > 0.f ? du * sm.wv2[lane + 32] : 0.f;
@@ -122,6 +175,23 @@ heads_backward_kernel(const float *__restrict__ params, const float *__restrict_
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) ws[W.dg() + b * kH + lane + 32 * t] = dg[t];
+    }
+    if (kLoss && loss) {  // monitoring scalars: one pair of atomics per CTA
+        __shared__ float red[2][kHbThreads / 32];
+        if (lane == 0) { red[0][warp] = loss_p; red[1][warp] = loss_v; }
+        __syncthreads();
+        if (warp == 0) {
+            float a = lane < nwarps ? red[0][lane] : 0.f, c = lane < nwarps ? red[1][lane] : 0.f;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, d);
+                c += __shfl_xor_sync(0xffffffffu, c, d);
+            }
+            if (lane == 0) {
+                atomicAdd(loss + 0, a * inv_total);
+                atomicAdd(loss + 1, c * inv_total);
+            }
+        }
     }
 }
 
@@ -450,23 +520,40 @@ extern "C" int64_t aq_gnn_backward_ws_floats(int64_t B) { return BwdWs{B}.total(
 
 int aq_gcn_backward_tc2(const float *params, float *saved, const float *dg, int64_t B, float *partial, cudaStream_t st);  // gnn_tc2_bwd.cu
 
-extern "C" int aq_gnn_backward(const float *params, const float *saved, const float *dpolicy, const float *dvalue,
-                               int64_t B, float *grads, float *workspace, int precision, void *stream) {
-    if (B <= 0 || !params || !saved || !dpolicy || !dvalue || !grads || !workspace)
-        return aq_set_error(AQ_ERR_ARG, "aq_gnn_backward");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+int aq_dp_adam_launch(void *comm, const float *grads_in, const float *partial, int gcn_slots, int head_slots, float *params, float *exp_avg,
+                      float *exp_avg_sq, float *grads_out, float lr, float beta1, float beta2, float eps, bool pdl, cudaStream_t st);  // dp_comm.cu
+
+static inline int head_slot_count(int64_t B) { return (int)std::min<int64_t>(kSlots, (B + 63) / 64); }  // one row chunk per 64 boards
+
+// The backward kernels up to the partial-gradient slots.  Loss gradient either given (dpolicy, dvalue) or computed in the heads
+// backward from the targets (ptarget, vtarget, B_total, loss).
+static int backward_to_partials(const float *params, const float *saved, const float *dpolicy, const float *dvalue, const float *ptarget,
+                                const float *vtarget, int64_t B, int64_t B_total, float *loss, float *workspace, int precision,
+                                cudaStream_t st) {
     const SavedLayout L{B};
     const BwdWs W{B};
+    const bool fused_loss = ptarget != nullptr;
     cudaError_t e;
-    e = cudaFuncSetAttribute(heads_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadBwdSmem));
+    e = cudaFuncSetAttribute(heads_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadBwdSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(heads_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadBwdSmem));
     if (e != cudaSuccess) return aq_set_error((int)e, "heads_backward smem");
     e = cudaFuncSetAttribute(gcn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GcnBwdSmem));
     if (e != cudaSuccess) return aq_set_error((int)e, "gcn_backward smem");
+    if (fused_loss && loss) {
+        e = cudaMemsetAsync(loss, 0, 2 * sizeof(float), st);
+        if (e != cudaSuccess) return aq_set_error((int)e, "aq_loss_backward(memset)");
+    }
     const int hb_threads = B <= 1184 ? 256 : kHbThreads;  // 148 CTAs x 8 boards cover 1,184 boards in one pass
     const int64_t hb = (B + hb_threads / 32 - 1) / (hb_threads / 32);
+    const dim3 hgrid((unsigned)(hb < kSlots ? hb : kSlots));
+    const float inv_total = 1.0f / (float)(B_total > 0 ? B_total : B);
     // the backward kernels are chained by programmatic dependent launches: each reads only the parameters before its aq_pdl_wait()
-    e = aq_launch_pdl(heads_backward_kernel, dim3((unsigned)(hb < kSlots ? hb : kSlots)), dim3(hb_threads), sizeof(HeadBwdSmem), st,
-                      params, saved, dpolicy, dvalue, B, workspace);
+    if (fused_loss)
+        e = aq_launch_pdl(heads_backward_kernel<true>, hgrid, dim3(hb_threads), sizeof(HeadBwdSmem), st, params, saved, dpolicy, dvalue, ptarget,
+                          vtarget, inv_total, loss, B, workspace);
+    else
+        e = aq_launch_pdl(heads_backward_kernel<false>, hgrid, dim3(hb_threads), sizeof(HeadBwdSmem), st, params, saved, dpolicy, dvalue, ptarget,
+                          vtarget, inv_total, loss, B, workspace);
     if (e != cudaSuccess) return aq_set_error((int)e, "heads_backward_kernel(launch)");
     int rc = aq_check_launch("heads_backward_kernel");
     if (rc) return rc;
@@ -481,8 +568,7 @@ extern "C" int aq_gnn_backward(const float *params, const float *saved, const fl
     AtbJobs jobs;
     int nj = 0;
     // head jobs: one row chunk per 64 boards (at most kSlots); node-level jobs: kSlots chunks
-    constexpr int chunk_rows = 64;
-    const int head_slots = (int)std::min<int64_t>(kSlots, (B + chunk_rows - 1) / chunk_rows);
+    const int head_slots = head_slot_count(B);
     auto add = [&](const float *A, int lda, int M, const float *Bm, int ldb, int N, int64_t R, int off, int bias_off = -1) {
         jobs.job[nj++] = AtbJob{A, lda, M, Bm, ldb, N, R, off, R == B ? head_slots : kSlots, bias_off};
     };
@@ -500,11 +586,36 @@ extern "C" int aq_gnn_backward(const float *params, const float *saved, const fl
     jobs.n = nj;
     e = aq_launch_pdl(atb_jobs_kernel, dim3(precision != 1 ? kSlots : head_slots, kMaxMTiles, nj), dim3(256), 0, st, jobs, workspace + W.partial());
     if (e != cudaSuccess) return aq_set_error((int)e, "atb_jobs_kernel(launch)");
-    if ((rc = aq_check_launch("atb_jobs_kernel"))) return rc;
-    e = aq_launch_pdl(reduce_partials_kernel, dim3((kNumParams / 2 + kRedPairs - 1) / kRedPairs), dim3(kRedPairs * 4), 0, st,
-                      (const float *)(workspace + W.partial()), grads, head_slots);
+    return aq_check_launch("atb_jobs_kernel");
+}
+
+extern "C" int aq_gnn_backward(const float *params, const float *saved, const float *dpolicy, const float *dvalue,
+                               int64_t B, float *grads, float *workspace, int precision, void *stream) {
+    if (B <= 0 || !params || !saved || !dpolicy || !dvalue || !grads || !workspace)
+        return aq_set_error(AQ_ERR_ARG, "aq_gnn_backward");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = backward_to_partials(params, saved, dpolicy, dvalue, nullptr, nullptr, B, B, nullptr, workspace, precision, st);
+    if (rc) return rc;
+    cudaError_t e = aq_launch_pdl(reduce_partials_kernel, dim3((kNumParams / 2 + kRedPairs - 1) / kRedPairs), dim3(kRedPairs * 4), 0, st,
+                                  (const float *)(workspace + BwdWs{B}.partial()), grads, head_slot_count(B));
     if (e != cudaSuccess) return aq_set_error((int)e, "reduce_partials_kernel(launch)");
     return aq_check_launch("reduce_partials_kernel");
+}
+
+// One training step behind the forward pass, as the reference's `loss = ...; optimizer.zero_grad(); loss.backward(); optimizer.step()`
+// (train_network.py:85-94) under data parallelism: loss gradient + heads backward (one kernel), trunk backward, head weight
+// gradients, then ONE kernel that reduces the partial slots, all-reduces the flat gradient over the ranks of `comm` (NVLink peer
+// memory, dp_comm.cu) and applies Adam.  grads (may be NULL) receives the reduced gradient (sum over the ranks).
+extern "C" int aq_train_backward_step(void *comm, float *params, const float *saved, const float *policy_target, const float *value_target,
+                                      int64_t B, int64_t B_total, float *loss, float *grads, float *exp_avg, float *exp_avg_sq,
+                                      float *workspace, int precision, float lr, float beta1, float beta2, float eps, void *stream) {
+    if (B <= 0 || B_total < B || !comm || !params || !saved || !policy_target || !value_target || !exp_avg || !exp_avg_sq || !workspace)
+        return aq_set_error(AQ_ERR_ARG, "aq_train_backward_step");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = backward_to_partials(params, saved, nullptr, nullptr, policy_target, value_target, B, B_total, loss, workspace, precision, st);
+    if (rc) return rc;
+    return aq_dp_adam_launch(comm, nullptr, workspace + BwdWs{B}.partial(), kSlots, head_slot_count(B), params, exp_avg, exp_avg_sq, grads, lr,
+                             beta1, beta2, eps, /*pdl=*/true, st);
 }
 
 extern "C" int aq_loss_grad(const float *policy, const float *value, const float *policy_target,

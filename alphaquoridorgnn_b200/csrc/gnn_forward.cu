@@ -588,23 +588,38 @@ extern "C" int aq_leaf_eval_host(const float *params, const void *prepared, cons
 // host-buffer path is bound by (PCIe): 4 bytes per legal action instead of 836 per board.
 
 // offsets[b] = number of legal actions of boards < b (exclusive scan of popcount(mask)), offsets[B] = total.
-// One CTA, tiles of 1024 boards with a running carry: B is at most a few 10^4 per call on this path.
+// One CTA; thread t owns the contiguous run of ceil(B / 1024) boards starting at t * run: all of a thread's mask loads are issued
+// before the first use (a tile-by-tile scan with two block barriers per 1,024 boards paid the load latency 16 times at B = 16,384),
+// one block-wide scan of the 1,024 run totals, then every thread writes its run.  B is at most a few 10^4 per call on this path;
+// runs longer than kScanRun are walked in pieces with a running carry.
+constexpr int kScanRun = 16;
 __global__ void __launch_bounds__(1024)
-legal_count_scan_kernel(const uint32_t *__restrict__ mask, int64_t B, int32_t *__restrict__ offsets) {
+legal_count_scan_kernel(const uint32_t *mask, int64_t B, int32_t *__restrict__ offsets) {
     __shared__ int warp_sum[32];
     __shared__ int carry_s;
+    aq_pdl_trigger();  // the compaction kernel behind this one may be scheduled; it waits for this grid before it reads the offsets
+    aq_pdl_wait();  // launched programmatically behind the kernels that finalise the mask (coherent loads below: PDL rule, aq_common.cuh)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (int64_t base = 0; base < B; base += 1024) {
-        const int64_t b = base + tid;
-        int c = 0;
-        if (b < B) {
-            const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(mask + 8 * b));
-            const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(mask + 8 * b) + 1);
-            c = __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w) + __popc(hi.x) + __popc(hi.y) + __popc(hi.z) + __popc(hi.w);
+    for (int64_t base = 0; base < B; base += 1024 * kScanRun) {
+        const int64_t left = B - base;
+        const int run = (int)((left < 1024 * kScanRun ? left : 1024 * kScanRun) + 1023) / 1024;  // boards per thread in this piece
+        const int64_t b0 = base + (int64_t)tid * run;
+        int c[kScanRun];
+#pragma unroll
+        for (int k = 0; k < kScanRun; ++k) {
+            c[k] = 0;
+            if (k < run && b0 + k < B) {
+                const uint4 lo = __ldcg(reinterpret_cast<const uint4 *>(mask + 8 * (b0 + k)));
+                const uint4 hi = __ldcg(reinterpret_cast<const uint4 *>(mask + 8 * (b0 + k)) + 1);
+                c[k] = __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w) + __popc(hi.x) + __popc(hi.y) + __popc(hi.z) + __popc(hi.w);
+            }
         }
-        int incl = c;
+        int mine = 0;
+#pragma unroll
+        for (int k = 0; k < kScanRun; ++k) mine += c[k];
+        int incl = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, d);
@@ -623,8 +638,10 @@ legal_count_scan_kernel(const uint32_t *__restrict__ mask, int64_t B, int32_t *_
         }
         __syncthreads();
         const int carry = carry_s;
-        const int excl = carry + (warp ? warp_sum[warp - 1] : 0) + incl - c;
-        if (b < B) offsets[b] = excl;
+        int at = carry + (warp ? warp_sum[warp - 1] : 0) + incl - mine;
+#pragma unroll
+        for (int k = 0; k < kScanRun; ++k)
+            if (k < run && b0 + k < B) { offsets[b0 + k] = at; at += c[k]; }
         __syncthreads();
         if (tid == 1023) carry_s = carry + warp_sum[31];
         __syncthreads();
@@ -637,13 +654,14 @@ legal_count_scan_kernel(const uint32_t *__restrict__ mask, int64_t B, int32_t *_
 // T = float (the bits of the dense priors) or __half (16-bit wire format of the host path, round to nearest even).
 template <typename T>
 __global__ void __launch_bounds__(256)
-compact_priors_kernel(const float *__restrict__ priors, const uint32_t *__restrict__ mask, const uint8_t *__restrict__ pawn,
-                      const int32_t *__restrict__ offsets, int64_t B, T *__restrict__ compact) {
+compact_priors_kernel(const float *priors, const uint32_t *mask, const uint8_t *pawn, const int32_t *offsets, int64_t B,
+                      T *__restrict__ compact) {
     const int lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    aq_pdl_wait();  // launched programmatically behind the scan (and, through it, the heads kernel): coherent loads below
     if (b >= B) return;
     const uint32_t *m = mask + 8 * b;
-    const uint32_t mw = lane < 8 ? __ldg(m + lane) : 0u;
+    const uint32_t mw = lane < 8 ? __ldcg(m + lane) : 0u;
     uint32_t w[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) w[k] = __shfl_sync(0xffffffffu, mw, k);
@@ -651,9 +669,9 @@ compact_priors_kernel(const float *__restrict__ priors, const uint32_t *__restri
     const u64 lo2 = ((u64)w[3] << 32) | w[2], hi2 = ((u64)w[5] << 32) | w[4], top = ((u64)w[7] << 32) | w[6];
     const u64 legalH = (lo2 >> 17) | (hi2 << 47);            // bit s = action 81 + s
     const u64 legalV = (hi2 >> 17) | (top << 47);            // bit s = action 145 + s
-    const uint2 pw = __ldg(reinterpret_cast<const uint2 *>(pawn + 8 * b));
+    const uint2 pw = __ldcg(reinterpret_cast<const uint2 *>(pawn + 8 * b));
     const int np = pw.x & 0xFF;
-    T *out = compact + offsets[b];
+    T *out = compact + __ldcg(offsets + b);
     const float *p = priors + (int64_t)kP * b;
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
@@ -672,20 +690,23 @@ compact_priors_kernel(const float *__restrict__ priors, const uint32_t *__restri
             const u64 below = (1ull << slot) - 1ull;
             rank = np + __popcll(legalH & below) + __popcll(legalV & below) + (isV ? (int)((legalH >> slot) & 1) : 0);
         }
-        if constexpr (sizeof(T) == 4) out[rank] = __ldg(p + a);
-        else out[rank] = __float2half_rn(__ldg(p + a));
+        if constexpr (sizeof(T) == 4) out[rank] = __ldcg(p + a);
+        else out[rank] = __float2half_rn(__ldcg(p + a));
     }
 }
 
 static int compact_priors_impl(const float *priors, const uint32_t *mask, const uint8_t *pawn, int64_t B, int32_t *offsets, void *compact,
                                int wire, cudaStream_t st) {
-    legal_count_scan_kernel<<<1, 1024, 0, st>>>(mask, B, offsets);
+    cudaError_t e = aq_launch_pdl(legal_count_scan_kernel, dim3(1), dim3(1024), 0, st, mask, B, offsets);
+    if (e != cudaSuccess) return aq_set_error((int)e, "aq_compact_priors(scan launch)");
     int rc = aq_check_launch("aq_compact_priors(scan)");
     if (rc || B == 0) return rc;
+    const dim3 grid((unsigned)((B + 7) / 8));
     if (wire == AQ_WIRE_F16)
-        compact_priors_kernel<__half><<<(unsigned)((B + 7) / 8), 256, 0, st>>>(priors, mask, pawn, offsets, B, reinterpret_cast<__half *>(compact));
+        e = aq_launch_pdl(compact_priors_kernel<__half>, grid, dim3(256), 0, st, priors, mask, pawn, (const int32_t *)offsets, B, reinterpret_cast<__half *>(compact));
     else
-        compact_priors_kernel<float><<<(unsigned)((B + 7) / 8), 256, 0, st>>>(priors, mask, pawn, offsets, B, reinterpret_cast<float *>(compact));
+        e = aq_launch_pdl(compact_priors_kernel<float>, grid, dim3(256), 0, st, priors, mask, pawn, (const int32_t *)offsets, B, reinterpret_cast<float *>(compact));
+    if (e != cudaSuccess) return aq_set_error((int)e, "aq_compact_priors(launch)");
     return aq_check_launch("aq_compact_priors");
 }
 

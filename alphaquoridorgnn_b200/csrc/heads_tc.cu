@@ -105,6 +105,8 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & (kTile - 1), q = tid >> 7;  // board of this thread inside the tile / column quarter it handles
     const int64_t b0 = (int64_t)blockIdx.x * kTile;
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");  // a kernel launched programmatically behind this one (the scan of the
+                                                                        // host path) may be scheduled; it waits for this grid's completion
 
     // ---- operands -> bf16 swizzled tiles ---------------------------------------------------------
     if (prepared) {  // b1 | b2 are contiguous here and in the prepared buffer (aq_prepare_inference)

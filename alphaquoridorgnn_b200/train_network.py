@@ -45,11 +45,86 @@ def shard_bounds(n, rank, world_size):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-class FlatTrainer:
-    """One model replica + Adam state on flat buffers; step() = forward/loss/backward/all-reduce/Adam."""
+class PeerAccessUnavailable(_lib.AqError):
+    """The ranks cannot map each other's memory (no CUDA IPC / no peer access between the GPUs)."""
 
-    def __init__(self, model, lr=0.001, betas=(0.9, 0.999), eps=1e-8, rank=0, world_size=1, precision=None):
+
+class PeerCommunicator:
+    """The ranks of one box mapped into each other's address space (CUDA IPC over NVLink; csrc/dp_comm.cu), for the fused
+    all-reduce + Adam kernel.  Handles are exchanged through torch.distributed (any backend)."""
+
+    def __init__(self, rank, world_size, device):
+        import ctypes
+        self.L = _lib.load()
+        self.rank, self.world, self.device = rank, world_size, device
+        self._h = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            rc = self.L.aq_comm_create(rank, world_size, ctypes.byref(self._h), handle)
+            err = self.L.aq_last_error_string().decode() if rc else ""
+            if world_size == 1:
+                _lib.check(rc, "aq_comm_create")
+                return
+            # every rank must take the same decision: exchange (ok, handle), map the peers, exchange ok again
+            import torch.distributed as dist
+            gathered = [None] * world_size
+            dist.all_gather_object(gathered, (rc == 0, bytes(handle), err))
+            if all(g[0] for g in gathered):
+                blob = (ctypes.c_ubyte * (64 * world_size)).from_buffer_copy(b"".join(g[1] for g in gathered))
+                rc = self.L.aq_comm_open(self._h, blob)
+                err = self.L.aq_last_error_string().decode() if rc else ""
+                opened = [None] * world_size
+                dist.all_gather_object(opened, (rc == 0, err))
+                bad = [f"rank {r}: {e}" for r, (ok, e) in enumerate(opened) if not ok]
+            else:
+                bad = [f"rank {r}: {g[2]}" for r, g in enumerate(gathered) if not g[0]]
+            if bad:
+                self.close()
+                raise PeerAccessUnavailable("; ".join(bad))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def status(self):
+        """-> (optimiser steps completed on the device, status: 0 ok, 1 = a peer did not arrive in time).  Synchronises."""
+        import ctypes
+        out = (ctypes.c_int64 * 2)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.aq_comm_status(self._h, out, _lib.stream_ptr(self.device)), "aq_comm_status")
+        return int(out[0]), int(out[1])
+
+    def set_step(self, step):
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.aq_comm_set_step(self._h, int(step), _lib.stream_ptr(self.device)), "aq_comm_set_step")
+
+    def close(self):
+        if self._h:
+            with torch.cuda.device(self.device):
+                self.L.aq_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FlatTrainer:
+    """One model replica + Adam state on flat buffers; step() = forward / loss / backward / gradient all-reduce / Adam.
+
+    collective: "p2p"  -- the default: the optimiser step is ONE kernel that reduces the partial gradients, all-reduces them over
+                          NVLink peer memory and applies Adam (aq_train_backward_step; csrc/dp_comm.cu); the whole step is 6 kernels
+                          and is replayed as a CUDA graph per batch shape (use_graph);
+                "nccl" -- the checked alternative: the same backward kernels, torch.distributed.all_reduce of the flat gradient,
+                          aq_adam_step.  Also what a world spanning several boxes needs."""
+
+    def __init__(self, model, lr=0.001, betas=(0.9, 0.999), eps=1e-8, rank=0, world_size=1, precision=None, collective="p2p",
+                 use_graph=True):
         from .pv_network_gnn import PRECISIONS
+        if collective not in ("p2p", "nccl"):
+            raise ValueError("collective must be 'p2p' or 'nccl'")
         self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
         self.prec = PRECISIONS[precision if precision is not None else model.train_precision]
         self.rank, self.world = rank, world_size
@@ -60,6 +135,47 @@ class FlatTrainer:
         self.grads = torch.zeros_like(self.flat)
         self.step_count = 0
         self.loss = torch.zeros(2, device=self.flat.device)
+        self.collective, self.use_graph = collective, use_graph
+        self.comm = None
+        if collective == "p2p":
+            try:
+                self.comm = PeerCommunicator(rank, world_size, self.flat.device)
+            except PeerAccessUnavailable as e:  # raised on every rank alike (the ranks exchange their outcome)
+                import warnings
+                warnings.warn(f"peer memory is not available ({e}); the gradient all-reduce falls back to torch.distributed")
+                self.collective = "nccl"
+        self._bufs, self._graphs = {}, {}
+
+    def _buffers(self, b):
+        buf = self._bufs.get(b)
+        if buf is None:
+            L, dev = _lib.load(), self.flat.device
+            if len(self._bufs) >= 4:  # a training loop has one full batch size and one tail
+                self._bufs.clear()
+                self._graphs.clear()
+            buf = self._bufs[b] = {
+                "packed": torch.empty((b, gl.STATE_BYTES), dtype=torch.uint8, device=dev),
+                "pt": torch.empty((b, POLICY_OUTPUT_SIZE), dtype=torch.float32, device=dev),
+                "vt": torch.empty((b,), dtype=torch.float32, device=dev),
+                "policy": torch.empty((b, POLICY_OUTPUT_SIZE), dtype=torch.float32, device=dev),
+                "value": torch.empty((b,), dtype=torch.float32, device=dev),
+                "saved": torch.empty((L.aq_gnn_saved_floats(b),), dtype=torch.float32, device=dev),
+                "ws": torch.empty((L.aq_gnn_backward_ws_floats(b),), dtype=torch.float32, device=dev),
+                "dp": torch.empty((b, POLICY_OUTPUT_SIZE), dtype=torch.float32, device=dev) if self.collective == "nccl" else None,
+                "dv": torch.empty((b,), dtype=torch.float32, device=dev) if self.collective == "nccl" else None,
+            }
+        return buf
+
+    def _enqueue(self, buf, b, global_batch, lr):
+        """The library calls of one step on the static buffers (eagerly, or under CUDA-graph capture)."""
+        L, P = _lib.load(), _lib.ptr
+        st = _lib.stream_ptr(self.flat.device)
+        _lib.check(L.aq_gnn_forward(P(self.flat), P(buf["packed"]), None, None, b, P(buf["policy"]), P(buf["value"]), P(buf["saved"]), self.prec, st),
+                   "aq_gnn_forward")
+        if self.collective == "p2p":
+            _lib.check(L.aq_train_backward_step(self.comm.handle, P(self.flat), P(buf["saved"]), P(buf["pt"]), P(buf["vt"]), b, global_batch,
+                                                P(self.loss), P(self.grads), P(self.exp_avg), P(self.exp_avg_sq), P(buf["ws"]), self.prec, lr,
+                                                self.betas[0], self.betas[1], self.eps, st), "aq_train_backward_step")
 
     def step(self, packed, policy_target, value_target, global_batch, lr_scale=1.0):
         """packed uint8[b,32], policy_target f32[b,209], value_target f32[b]: this rank's slice of a
@@ -70,36 +186,88 @@ class FlatTrainer:
         if flat.data_ptr() != self.flat.data_ptr() or flat.device != self.flat.device:
             # the module was moved (.to) or its storage replaced (load_state_dict(assign=True)) since the last step: follow it, keep
             # the Adam moments (on the new device), so that the update does not go into an orphaned buffer
+            if self.comm is not None and flat.device != self.flat.device:
+                raise _lib.AqError("the model moved to another device: create a new FlatTrainer (its peer communicator is bound to the old one)")
             self.flat = flat
             self.exp_avg, self.exp_avg_sq = self.exp_avg.to(flat.device), self.exp_avg_sq.to(flat.device)
             self.grads, self.loss = torch.zeros_like(flat), torch.zeros(2, device=flat.device)
+            self._bufs.clear()
+            self._graphs.clear()
         dev = self.flat.device
         b = packed.shape[0]
+        lr = float(self.lr * lr_scale)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
-            if b > 0:
-                policy = torch.empty((b, POLICY_OUTPUT_SIZE), dtype=torch.float32, device=dev)
-                value = torch.empty((b,), dtype=torch.float32, device=dev)
-                saved = torch.empty((L.aq_gnn_saved_floats(b),), dtype=torch.float32, device=dev)
-                ws = torch.empty((L.aq_gnn_backward_ws_floats(b),), dtype=torch.float32, device=dev)
-                dp, dv = torch.empty_like(policy), torch.empty_like(value)
-                _lib.check(L.aq_gnn_forward(P(self.flat), P(packed), None, None, b, P(policy), P(value), P(saved), self.prec, st), "aq_gnn_forward")
-                _lib.check(L.aq_loss_grad(P(policy), P(value), P(policy_target), P(value_target), b, global_batch, P(self.loss),
-                                          P(dp), P(dv), st), "aq_loss_grad")
-                _lib.check(L.aq_gnn_backward(P(self.flat), P(saved), P(dp), P(dv), b, P(self.grads), P(ws), self.prec, st), "aq_gnn_backward")
+            if self.collective == "p2p":
+                if b == 0:  # an empty shard still takes part in the exchange: zero gradient through the plain entry point
+                    self.grads.zero_()
+                    self.loss.zero_()
+                    _lib.check(L.aq_dp_adam_step(self.comm.handle, P(self.flat), P(self.grads), P(self.exp_avg), P(self.exp_avg_sq), lr,
+                                                 self.betas[0], self.betas[1], self.eps, st), "aq_dp_adam_step")
+                else:
+                    buf = self._buffers(b)
+                    buf["packed"].copy_(packed, non_blocking=True)
+                    buf["pt"].copy_(policy_target, non_blocking=True)
+                    buf["vt"].copy_(value_target, non_blocking=True)
+                    key = (b, int(global_batch), lr)
+                    graph = self._graphs.get(key) if self.use_graph else None
+                    if self.use_graph and graph is None and key not in self._graphs:
+                        # first step of this shape runs eagerly (it IS a step: the optimiser state advances exactly once per call);
+                        # the capture happens on the second, when every lazily loaded module is resident
+                        self._graphs[key] = None
+                        self._enqueue(buf, b, int(global_batch), lr)
+                    elif self.use_graph and graph is None:
+                        try:
+                            torch.cuda.synchronize(dev)
+                            g = torch.cuda.CUDAGraph()
+                            with torch.cuda.graph(g):
+                                self._enqueue(buf, b, int(global_batch), lr)
+                            self._graphs[key] = g
+                            g.replay()   # capture records, it does not execute
+                        except _lib.AqError:
+                            raise
+                        except Exception as e:  # capture unsupported: stay eager, but say so
+                            import warnings
+                            warnings.warn(f"CUDA-graph capture of the training step failed ({e!r}); running eagerly")
+                            self.use_graph = False
+                            torch.cuda.synchronize(dev)
+                            self._enqueue(buf, b, int(global_batch), lr)
+                    elif graph is not None:
+                        graph.replay()
+                    else:
+                        self._enqueue(buf, b, int(global_batch), lr)
+                self.step_count += 1
             else:
-                self.grads.zero_()
-                self.loss.zero_()
-            if self.world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(self.grads)  # one 256 KB all-reduce per step; losses divide by the global batch already
-            self.step_count += 1
-            _lib.check(L.aq_adam_step(P(self.flat), P(self.grads), P(self.exp_avg), P(self.exp_avg_sq), self.flat.numel(),
-                                      self.step_count, self.lr * lr_scale, self.betas[0], self.betas[1], self.eps, 1.0, st),
-                       "aq_adam_step")
+                if b > 0:
+                    buf = self._buffers(b)
+                    _lib.check(L.aq_gnn_forward(P(self.flat), P(packed), None, None, b, P(buf["policy"]), P(buf["value"]), P(buf["saved"]), self.prec, st),
+                               "aq_gnn_forward")
+                    _lib.check(L.aq_loss_grad(P(buf["policy"]), P(buf["value"]), P(policy_target), P(value_target), b, global_batch, P(self.loss),
+                                              P(buf["dp"]), P(buf["dv"]), st), "aq_loss_grad")
+                    _lib.check(L.aq_gnn_backward(P(self.flat), P(buf["saved"]), P(buf["dp"]), P(buf["dv"]), b, P(self.grads), P(buf["ws"]), self.prec, st),
+                               "aq_gnn_backward")
+                else:
+                    self.grads.zero_()
+                    self.loss.zero_()
+                if self.world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(self.grads)  # one 256 KB all-reduce per step; losses divide by the global batch already
+                self.step_count += 1
+                _lib.check(L.aq_adam_step(P(self.flat), P(self.grads), P(self.exp_avg), P(self.exp_avg_sq), self.flat.numel(),
+                                          self.step_count, lr, self.betas[0], self.betas[1], self.eps, 1.0, st),
+                           "aq_adam_step")
         if hasattr(self.model, "mark_weights_changed"):
             self.model.mark_weights_changed()  # the flat buffer was written through a raw pointer
         return self.loss
+
+    def check(self):
+        """Synchronises and raises if the peer exchange timed out or the device step counter disagrees with the host's."""
+        if self.comm is not None:
+            steps, status = self.comm.status()
+            if status:
+                raise _lib.AqError("data-parallel step: a peer rank did not arrive within the kernel's time-out")
+            if steps != self.step_count:
+                raise _lib.AqError(f"device step counter {steps} != host step count {self.step_count}")
 
 
 def train_on_history(model, history, num_epochs=NUM_EPOCH, batch_size=BATCH_SIZE, rank=0, world_size=1, seed=0,
@@ -142,6 +310,7 @@ def train_on_buffer(model, packed, p, v, num_epochs=NUM_EPOCH, batch_size=BATCH_
             print(f"\rEpoch {epoch + 1}/{num_epochs} | Policy Loss: {losses[-1][0]:.4f} | Value Loss: {losses[-1][1]:.4f}", end='')
     if verbose and rank == 0:
         print('')
+    trainer.check()
     return losses
 
 

@@ -335,7 +335,7 @@ def dp_check(dev, rank, world):
         one = train_network.FlatTrainer(ref_net, precision=prec)
         lo, hi = train_network.shard_bounds(B, rank, world)
         worst = 0.0
-        for _ in range(3):
+        for _ in range(4):   # the first step of a shape runs eagerly, the second captures the CUDA graph, the others replay it
             l_dp = dp.step(packed[lo:hi].contiguous(), pt[lo:hi].contiguous(), vt[lo:hi].contiguous(), B).clone()
             dist.all_reduce(l_dp)
             l_one = one.step(packed, pt, vt, B)
@@ -350,7 +350,20 @@ def dp_check(dev, rank, world):
         same = torch.tensor([1 if torch.equal(mine, ref0) else 0], device=dev)
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         assert int(same.item()) == 1, "ranks diverged"
-        report[prec] = {"grad_rel_l2_vs_single_gpu": worst, "ranks_bit_identical": True}
+        dp.check()
+        # the NCCL alternative gives the same gradient sum up to fp32 summation order
+        torch.manual_seed(2)
+        nc_net = GNNNetwork().to(dev).train()
+        nc = train_network.FlatTrainer(nc_net, rank=rank, world_size=world, precision=prec, collective="nccl")
+        torch.manual_seed(2)
+        p2_net = GNNNetwork().to(dev).train()
+        p2 = train_network.FlatTrainer(p2_net, rank=rank, world_size=world, precision=prec, use_graph=False)
+        nc.step(packed[lo:hi].contiguous(), pt[lo:hi].contiguous(), vt[lo:hi].contiguous(), B)
+        p2.step(packed[lo:hi].contiguous(), pt[lo:hi].contiguous(), vt[lo:hi].contiguous(), B)
+        nerr = ((nc.grads - p2.grads).norm() / p2.grads.norm()).item()
+        assert nerr < 1e-6, (prec, nerr)
+        report[prec] = {"grad_rel_l2_vs_single_gpu": worst, "ranks_bit_identical": True, "collective": dp.collective,
+                        "grad_rel_l2_peer_memory_vs_nccl": nerr}
     if rank == 0:
         print(f"dp_check ok (world {world}): {json.dumps(report)}", file=sys.stderr, flush=True)
     return report
@@ -562,10 +575,10 @@ def run_ours(args, rank, world, local_rank):
         del big, bmask, bpawn, bws
 
         # ---- training step through the public trainer (forward + loss + backward + gradient all-reduce + Adam), random targets ----
-        def train_bench(TB, precision):
+        def train_bench(TB, precision, collective="p2p"):
             torch.manual_seed(0)
             tnet = GNNNetwork().to(dev).train()
-            trainer = train_network.FlatTrainer(tnet, rank=rank, world_size=world, precision=precision)
+            trainer = train_network.FlatTrainer(tnet, rank=rank, world_size=world, precision=precision, collective=collective)
             tb = allpos[:TB].contiguous()
             torch.manual_seed(1)
             pt = torch.softmax(torch.randn(TB, 209, device=dev), 1)
@@ -581,8 +594,15 @@ def run_ours(args, rank, world, local_rank):
         if prec == 1:
             ms, _ = train_bench(256, "fp32")
             tr["B256_fp32"] = {"value": world * 256 / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms}
+        if world > 1:  # the checked alternative: same backward kernels, torch.distributed (NCCL) all-reduce + aq_adam_step
+            for TB in (256, 4096):
+                ms, launches = train_bench(TB, args.precision, "nccl")
+                tr[f"B{TB}_nccl_allreduce"] = {"value": world * TB / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+                                               "kernel_launches_per_step": launches / 20}
+            tr["nvlink_bytes_per_step_per_gpu"] = (world - 1) * 64082 * 4 + 2 * (world - 1) * 251 * 4
         tr["config"] = ("BASELINE configs[0] shape (B = 256 per GPU) and a throughput-sized batch (B = 4096 per GPU): FlatTrainer.step = "
-                        "aq_gnn_forward(saved) + aq_loss_grad + aq_gnn_backward + all-reduce of the flat gradient + aq_adam_step")
+                        "aq_gnn_forward(saved) + aq_train_backward_step (loss gradient + heads backward | trunk backward | head weight gradients "
+                        "| slot reduction + peer-memory all-reduce + Adam), replayed as one CUDA graph")
         tr["cpu_baseline"] = time_cpu_train() if cpu_ok else None
         extra["train"] = tr
 

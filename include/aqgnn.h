@@ -53,7 +53,7 @@ typedef struct AqState {
     uint64_t reserved; /* reserved, 0 */
 } AqState;
 
-#define AQ_VERSION 200 /* bumped with every change of a signature below; the ctypes loader refuses a library of another version */
+#define AQ_VERSION 201 /* bumped with every change of a signature below; the ctypes loader refuses a library of another version */
 int aq_version(void);
 const char *aq_last_error_string(void);
 /* Number of kernels this library has launched in the process so far (monotonic; kernels replayed through a CUDA graph the caller
@@ -155,6 +155,32 @@ int aq_loss_grad(const float *policy, const float *value, const float *policy_ta
  * buffers. step is the 1-based step count; lr already includes the LambdaLR factor. */
 int aq_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, int64_t step,
                  float lr, float beta1, float beta2, float eps, float grad_scale, void *stream);
+
+/* Data-parallel optimiser step without NCCL on the path (csrc/dp_comm.cu): one communicator per rank (process) of ONE box.
+ *   aq_comm_create  allocates the rank's communication block and returns its 64-byte CUDA IPC handle in handle_out64;
+ *   aq_comm_open    maps the other ranks' blocks: handles = world x 64 bytes, entry r from rank r (exchanged by the caller over any
+ *                   host channel, e.g. torch.distributed.all_gather_object); not needed when world == 1;
+ *   aq_comm_status  out2[0] = optimiser steps completed (device counter), out2[1] = 0 ok / 1 a peer did not arrive within the
+ *                   kernel's time-out (the kernel gives up instead of hanging); synchronises `stream`;
+ *   aq_comm_set_step sets the device step counter (0 for a fresh optimiser; every rank at the same point).
+ * aq_dp_adam_step: all-reduce (sum over the ranks) of the flat gradient `grads` + torch.optim.Adam step (train_network.py:56,94) in
+ * ONE kernel over NVLink peer memory; `grads` holds the sum afterwards; every rank ends with bit-identical parameters.  The step
+ * number of the bias corrections is the device counter + 1.  The replacement for torch.distributed.all_reduce + aq_adam_step. */
+int aq_comm_create(int rank, int world, void **comm, void *handle_out64);
+int aq_comm_open(void *comm, const void *handles);
+int aq_comm_destroy(void *comm);
+int aq_comm_status(void *comm, int64_t *out2, void *stream);
+int aq_comm_set_step(void *comm, int64_t step, void *stream);
+int aq_dp_adam_step(void *comm, float *params, float *grads, float *exp_avg, float *exp_avg_sq, float lr, float beta1, float beta2,
+                    float eps, void *stream);
+/* Everything of a training step behind the forward pass -- the reference's `loss = CE + MSE; zero_grad(); loss.backward();
+ * optimizer.step()` (train_network.py:85-94) with the gradient all-reduce of data parallelism in between -- in four kernels:
+ * loss gradient + heads backward, trunk backward, head weight gradients, and slot reduction + all-reduce + Adam (above).
+ * saved / workspace / precision as in aq_gnn_forward / aq_gnn_backward; B_total = the global batch the 'mean' losses divide by;
+ * loss (may be NULL) receives this rank's {policy, value} loss contributions; grads (may be NULL) the reduced gradient. */
+int aq_train_backward_step(void *comm, float *params, const float *saved, const float *policy_target, const float *value_target,
+                           int64_t B, int64_t B_total, float *loss, float *grads, float *exp_avg, float *exp_avg_sq, float *workspace,
+                           int precision, float lr, float beta1, float beta2, float eps, void *stream);
 
 /* Batched BaseNetwork.predict (BaseNetwork.py:36-40; behaviour pv_network_cnn.py:117-137):
  * legal mask + graph + forward + restriction to legal actions + renormalisation, for B leaves.

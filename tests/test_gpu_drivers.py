@@ -173,3 +173,40 @@ def test_arena_matches_reference_play_and_scoring():
     assert {0, 1, 0.5} <= set(pts)
     rr = [p for p in golden["pairings"] if p["name"] == "runner_vs_runner"][0]
     assert rr["total_point_model0"] == 2.0 and len(rr["games"]) == 5   # second mover always wins: model0 scores on odd games only
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_fused_training_step_equals_the_unfused_kernels(traj, prec):
+    """FlatTrainer's default step (loss gradient inside the heads backward; slot reduction + all-reduce + Adam in one kernel with the
+    bias corrections from the device step counter; the step replayed as a CUDA graph from the third call on) against the same step
+    made of the separate entry points (aq_loss_grad, aq_gnn_backward, aq_adam_step): same losses and gradients bit for bit, same
+    parameters up to the rounding of the bias-correction scalars."""
+    rng = np.random.default_rng(2)
+    idx = rng.choice(len(traj["rows"]), 200, replace=False)
+    packed = gl.pack_rows(traj["rows"][idx])
+    torch.manual_seed(4)
+    pt = torch.softmax(2 * torch.randn(200, 209), 1).cuda()
+    vt = torch.randint(-1, 2, (200,)).float().cuda()
+    a, b, c = _net(7).train(), _net(7).train(), _net(7).train()
+    fused = train_network.FlatTrainer(a, lr=1e-3, precision=prec)
+    eager = train_network.FlatTrainer(c, lr=1e-3, precision=prec, use_graph=False)
+    plain = train_network.FlatTrainer(b, lr=1e-3, precision=prec, collective="nccl")
+    assert fused.collective == "p2p"
+    for step in range(6):
+        sl = slice(0, 200) if step != 3 else slice(0, 77)   # a second batch shape in between
+        n = sl.stop
+        lf = fused.step(packed[sl], pt[sl], vt[sl], n).clone()
+        le = eager.step(packed[sl], pt[sl], vt[sl], n).clone()
+        lp = plain.step(packed[sl], pt[sl], vt[sl], n).clone()
+        assert torch.equal(lf, le)
+        assert (lf - lp).abs().max().item() <= 1e-6      # the loss scalars are atomically accumulated per CTA: summation order
+        assert torch.equal(fused.grads, eager.grads)
+        assert (fused.grads - plain.grads).abs().max().item() <= 1e-6 * max(1.0, plain.grads.abs().max().item())
+        assert (fused.flat - plain.flat).abs().max().item() <= 2e-6
+        assert torch.equal(fused.flat, eager.flat)
+    fused.check()
+    assert fused.comm.status() == (6, 0)
+    # an empty shard takes part in the step with a zero gradient
+    fused.step(packed[:0], pt[:0], vt[:0], 64)
+    plain.step(packed[:0], pt[:0], vt[:0], 64)
+    assert (fused.flat - plain.flat).abs().max().item() <= 4e-6
