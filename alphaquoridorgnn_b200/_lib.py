@@ -9,7 +9,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libaqgnn.so")
-ABI_VERSION = 201  # AQ_VERSION of include/aqgnn.h this table of signatures was written for
+ABI_VERSION = 202  # AQ_VERSION of include/aqgnn.h this table of signatures was written for
 
 # name -> (restype, argtypes); must list every symbol declared in include/aqgnn.h
 _vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
@@ -42,7 +42,7 @@ SYMBOLS = {
     "aq_comm_open": (_i32, [_vp, _vp]),
     "aq_comm_destroy": (_i32, [_vp]),
     "aq_comm_status": (_i32, [_vp, _vp, _vp]),
-    "aq_comm_set_step": (_i32, [_vp, _i64, _vp]),
+    "aq_comm_set_step": (_i32, [_vp, _i64, _f32, _f32, _vp]),
     "aq_dp_adam_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp]),
     "aq_train_backward_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _vp]),
     "aq_leaf_eval": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),

@@ -23,6 +23,7 @@
 // A rank that does not show up within kTimeoutNs (a crashed peer) makes the waiting CTAs give up and raise the status word, which
 // aq_comm_status returns: the kernel never hangs the GPU.
 // No host value changes between steps except the learning rate, so the whole training step can be captured in a CUDA graph.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include "gnn_fp32.cuh"
@@ -47,6 +48,8 @@ struct CommBlock {                       // layout of the exported device block
     uint32_t ticket;                     // CTAs finished in the current launch
     uint32_t status;                     // != 0: a wait timed out
     uint32_t pad;
+    double beta_pow[2];                  // beta1^step, beta2^step (running products: a double-precision pow() per CTA at the top of
+                                         // every launch sat on the kernel's critical path)
 };
 
 struct CommPtrs {                        // passed to the kernel by value
@@ -93,10 +96,11 @@ dp_adam_kernel(CommPtrs c, const float *grads_in, const float *partial, int gcn_
     CommBlock *me = c.peer[c.rank];
     const uint32_t e = *reinterpret_cast<volatile uint32_t *>(&me->step) + 1u;  // the same value in every CTA of this launch
     const int par = (int)(e & 1u);
+    const double b1p = *reinterpret_cast<volatile double *>(&me->beta_pow[0]) * (double)beta1;   // beta1^e
+    const double b2p = *reinterpret_cast<volatile double *>(&me->beta_pow[1]) * (double)beta2;
     if (tid == 0) {
-        const double bc1 = 1.0 - pow((double)beta1, (double)e), bc2 = 1.0 - pow((double)beta2, (double)e);
-        hyper[0] = (float)((double)lr / bc1);   // step_size
-        hyper[1] = (float)sqrt(bc2);            // bias_correction2_sqrt
+        hyper[0] = (float)((double)lr / (1.0 - b1p));   // step_size = lr / bias_correction1
+        hyper[1] = (float)sqrt(1.0 - b2p);              // bias_correction2_sqrt
         timed_out = 0;
     }
     const int i = cta * kChunkFloats + 2 * tx;  // this thread's parameter pair (pairs beyond kNumParams are padding)
@@ -170,6 +174,8 @@ dp_adam_kernel(CommPtrs c, const float *grads_in, const float *partial, int gcn_
         __threadfence();
         if (atomicAdd(&me->ticket, 1u) == gridDim.x - 1) {
             me->ticket = 0u;
+            *reinterpret_cast<volatile double *>(&me->beta_pow[0]) = b1p;
+            *reinterpret_cast<volatile double *>(&me->beta_pow[1]) = b2p;
             __threadfence();
             *reinterpret_cast<volatile uint32_t *>(&me->step) = e;
         }
@@ -188,6 +194,8 @@ extern "C" int aq_comm_create(int rank, int world, void **comm, void *handle_out
     c->p.world = world;
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&c->local), sizeof(CommBlock));
     if (e == cudaSuccess) e = cudaMemset(c->local, 0, sizeof(CommBlock));
+    const double ones[2] = {1.0, 1.0};
+    if (e == cudaSuccess) e = cudaMemcpy(&c->local->beta_pow[0], ones, sizeof ones, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess && world > 1) e = cudaIpcGetMemHandle(&c->handle, c->local);
     if (e != cudaSuccess) { if (c->local) cudaFree(c->local); delete c; return aq_set_error((int)e, "aq_comm_create"); }
@@ -239,13 +247,17 @@ extern "C" int aq_comm_status(void *comm, int64_t *out2, void *stream) {
     return 0;
 }
 
-// Sets the device step counter (a fresh optimiser: 0).  Every rank must call it at the same point of its stream.
-extern "C" int aq_comm_set_step(void *comm, int64_t step, void *stream) {
+// Sets the device step counter (a fresh optimiser: 0) and the running powers beta1^step, beta2^step of the bias corrections.
+// Every rank must call it at the same point of its stream.
+extern "C" int aq_comm_set_step(void *comm, int64_t step, float beta1, float beta2, void *stream) {
     if (!comm || step < 0) return aq_set_error(AQ_ERR_ARG, "aq_comm_set_step");
     AqComm *c = reinterpret_cast<AqComm *>(comm);
     const uint32_t v = (uint32_t)step;
-    cudaError_t e = cudaMemcpyAsync(&c->local->step, &v, 4, cudaMemcpyHostToDevice, reinterpret_cast<cudaStream_t>(stream));
-    if (e == cudaSuccess) e = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+    const double pw[2] = {pow((double)beta1, (double)step), pow((double)beta2, (double)step)};
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemcpyAsync(&c->local->step, &v, 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&c->local->beta_pow[0], pw, sizeof pw, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     return e == cudaSuccess ? 0 : aq_set_error((int)e, "aq_comm_set_step");
 }
 

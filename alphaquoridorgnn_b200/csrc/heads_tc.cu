@@ -303,9 +303,11 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
     sum_legal = (sm.xch[2][0][row] + sm.xch[2][1][row]) + (sm.xch[2][2][row] + sm.xch[2][3][row]);
     // softmax then `policy /= sum(policy) if sum(policy) else 1` over the legal entries
     // (pv_network_cnn.py:129-132): p_a / sum_legal p = e_a / sum_legal e
-    float inv;
-    if (kLegal) inv = sum_legal != 0.f ? 1.f / sum_legal : 1.f / sum_all;
-    else inv = 1.f / sum_all;
+    // (the denominator can be subnormal when the logits of the legal actions lie hundreds below the maximum: its reciprocal would
+    // overflow to infinity, so such rows divide -- the reference's own arithmetic -- instead of multiplying by the reciprocal)
+    const float denom = (kLegal && sum_legal != 0.f) ? sum_legal : sum_all;
+    const bool tiny = denom < 1e-30f;
+    float inv = 1.f / (tiny ? 1.f : denom);
     if (sm.poisoned[row]) inv = __int_as_float(0x7FC00000);  // every probability this board writes becomes NaN
     {
         const int lane = tid & 31, r0 = row & ~31;  // this warp's 32 boards start at r0
@@ -314,7 +316,8 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
             const uint32_t bits = blk ? bits1 : bits0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const float e = (blk ? v1[i] : v0[i]) * inv;
+                const float ev = blk ? v1[i] : v0[i];
+                const float e = tiny ? (ev / denom) * inv : ev * inv;   // tiny: inv is 1 (or the NaN of a poisoned row)
                 stage[lane * kStagePitch + i] = (!kLegal || ((bits >> i) & 1)) ? e : 0.f;
             }
             __syncwarp();

@@ -94,9 +94,9 @@ class PeerCommunicator:
             _lib.check(self.L.aq_comm_status(self._h, out, _lib.stream_ptr(self.device)), "aq_comm_status")
         return int(out[0]), int(out[1])
 
-    def set_step(self, step):
+    def set_step(self, step, betas=(0.9, 0.999)):
         with torch.cuda.device(self.device):
-            _lib.check(self.L.aq_comm_set_step(self._h, int(step), _lib.stream_ptr(self.device)), "aq_comm_set_step")
+            _lib.check(self.L.aq_comm_set_step(self._h, int(step), betas[0], betas[1], _lib.stream_ptr(self.device)), "aq_comm_set_step")
 
     def close(self):
         if self._h:
@@ -145,18 +145,16 @@ class FlatTrainer:
                 warnings.warn(f"peer memory is not available ({e}); the gradient all-reduce falls back to torch.distributed")
                 self.collective = "nccl"
         self._bufs, self._graphs = {}, {}
+        self.kernels_per_step = None   # this library's kernel launches in one step, counted on the last eagerly run step
 
     def _buffers(self, b):
         buf = self._bufs.get(b)
         if buf is None:
             L, dev = _lib.load(), self.flat.device
-            if len(self._bufs) >= 4:  # a training loop has one full batch size and one tail
+            if len(self._bufs) >= 8:  # a training loop has one full batch size and one tail (each with workspace + inputs)
                 self._bufs.clear()
                 self._graphs.clear()
             buf = self._bufs[b] = {
-                "packed": torch.empty((b, gl.STATE_BYTES), dtype=torch.uint8, device=dev),
-                "pt": torch.empty((b, POLICY_OUTPUT_SIZE), dtype=torch.float32, device=dev),
-                "vt": torch.empty((b,), dtype=torch.float32, device=dev),
                 "policy": torch.empty((b, POLICY_OUTPUT_SIZE), dtype=torch.float32, device=dev),
                 "value": torch.empty((b,), dtype=torch.float32, device=dev),
                 "saved": torch.empty((L.aq_gnn_saved_floats(b),), dtype=torch.float32, device=dev),
@@ -166,16 +164,29 @@ class FlatTrainer:
             }
         return buf
 
-    def _enqueue(self, buf, b, global_batch, lr):
-        """The library calls of one step on the static buffers (eagerly, or under CUDA-graph capture)."""
+    def inputs(self, b):
+        """Persistent input tensors (packed uint8[b,32], policy_target f32[b,209], value_target f32[b]) a data loader can fill in
+        place (e.g. torch.index_select(..., out=...)): a step on tensors whose addresses repeat is replayed as one CUDA graph."""
+        key = ("in", b)
+        buf = self._bufs.get(key)
+        if buf is None:
+            dev = self.flat.device
+            buf = self._bufs[key] = (torch.empty((b, gl.STATE_BYTES), dtype=torch.uint8, device=dev),
+                                     torch.empty((b, POLICY_OUTPUT_SIZE), dtype=torch.float32, device=dev),
+                                     torch.empty((b,), dtype=torch.float32, device=dev))
+        return buf
+
+    def _enqueue(self, buf, packed, policy_target, value_target, b, global_batch, lr):
+        """The library calls of one step (eagerly, or under CUDA-graph capture)."""
         L, P = _lib.load(), _lib.ptr
         st = _lib.stream_ptr(self.flat.device)
-        _lib.check(L.aq_gnn_forward(P(self.flat), P(buf["packed"]), None, None, b, P(buf["policy"]), P(buf["value"]), P(buf["saved"]), self.prec, st),
+        c0 = L.aq_launch_count()
+        _lib.check(L.aq_gnn_forward(P(self.flat), P(packed), None, None, b, P(buf["policy"]), P(buf["value"]), P(buf["saved"]), self.prec, st),
                    "aq_gnn_forward")
-        if self.collective == "p2p":
-            _lib.check(L.aq_train_backward_step(self.comm.handle, P(self.flat), P(buf["saved"]), P(buf["pt"]), P(buf["vt"]), b, global_batch,
-                                                P(self.loss), P(self.grads), P(self.exp_avg), P(self.exp_avg_sq), P(buf["ws"]), self.prec, lr,
-                                                self.betas[0], self.betas[1], self.eps, st), "aq_train_backward_step")
+        _lib.check(L.aq_train_backward_step(self.comm.handle, P(self.flat), P(buf["saved"]), P(policy_target), P(value_target), b, global_batch,
+                                            P(self.loss), P(self.grads), P(self.exp_avg), P(self.exp_avg_sq), P(buf["ws"]), self.prec, lr,
+                                            self.betas[0], self.betas[1], self.eps, st), "aq_train_backward_step")
+        self.kernels_per_step = L.aq_launch_count() - c0
 
     def step(self, packed, policy_target, value_target, global_batch, lr_scale=1.0):
         """packed uint8[b,32], policy_target f32[b,209], value_target f32[b]: this rank's slice of a
@@ -205,23 +216,27 @@ class FlatTrainer:
                     _lib.check(L.aq_dp_adam_step(self.comm.handle, P(self.flat), P(self.grads), P(self.exp_avg), P(self.exp_avg_sq), lr,
                                                  self.betas[0], self.betas[1], self.eps, st), "aq_dp_adam_step")
                 else:
+                    for t, name in ((packed, "packed"), (policy_target, "policy_target"), (value_target, "value_target")):
+                        if not (t.is_cuda and t.is_contiguous()):
+                            raise ValueError(f"{name} must be a contiguous CUDA tensor")
                     buf = self._buffers(b)
-                    buf["packed"].copy_(packed, non_blocking=True)
-                    buf["pt"].copy_(policy_target, non_blocking=True)
-                    buf["vt"].copy_(value_target, non_blocking=True)
-                    key = (b, int(global_batch), lr)
+                    args = (buf, packed, policy_target, value_target, b, int(global_batch), lr)
+                    # a step whose input addresses repeat (FlatTrainer.inputs(), or a loader that reuses its batch tensors) is
+                    # replayed as one CUDA graph; the first step with a key runs eagerly, the second is captured
+                    key = (b, int(global_batch), lr, packed.data_ptr(), policy_target.data_ptr(), value_target.data_ptr())
                     graph = self._graphs.get(key) if self.use_graph else None
-                    if self.use_graph and graph is None and key not in self._graphs:
-                        # first step of this shape runs eagerly (it IS a step: the optimiser state advances exactly once per call);
-                        # the capture happens on the second, when every lazily loaded module is resident
-                        self._graphs[key] = None
-                        self._enqueue(buf, b, int(global_batch), lr)
-                    elif self.use_graph and graph is None:
+                    if not self.use_graph or (graph is None and key not in self._graphs):
+                        if self.use_graph:
+                            if len(self._graphs) >= 16:
+                                self._graphs.clear()
+                            self._graphs[key] = None
+                        self._enqueue(*args)
+                    elif graph is None:
                         try:
                             torch.cuda.synchronize(dev)
                             g = torch.cuda.CUDAGraph()
                             with torch.cuda.graph(g):
-                                self._enqueue(buf, b, int(global_batch), lr)
+                                self._enqueue(*args)
                             self._graphs[key] = g
                             g.replay()   # capture records, it does not execute
                         except _lib.AqError:
@@ -231,11 +246,9 @@ class FlatTrainer:
                             warnings.warn(f"CUDA-graph capture of the training step failed ({e!r}); running eagerly")
                             self.use_graph = False
                             torch.cuda.synchronize(dev)
-                            self._enqueue(buf, b, int(global_batch), lr)
-                    elif graph is not None:
-                        graph.replay()
+                            self._enqueue(*args)
                     else:
-                        self._enqueue(buf, b, int(global_batch), lr)
+                        graph.replay()
                 self.step_count += 1
             else:
                 if b > 0:
@@ -300,8 +313,12 @@ def train_on_buffer(model, packed, p, v, num_epochs=NUM_EPOCH, batch_size=BATCH_
             idx = perm[start:start + batch_size]
             lo, hi = shard_bounds(idx.numel(), rank, world_size)
             mine = idx[lo:hi]
-            ep += trainer.step(packed[mine].contiguous(), p[mine].contiguous(), v[mine].contiguous(), idx.numel(),
-                               lr_lambda(epoch))
+            bp, bt, bv = trainer.inputs(mine.numel())   # gathered in place: the step's addresses repeat, so it replays as a CUDA graph
+            if mine.numel():
+                torch.index_select(packed, 0, mine, out=bp)
+                torch.index_select(p, 0, mine, out=bt)
+                torch.index_select(v, 0, mine, out=bv)
+            ep += trainer.step(bp, bt, bv, idx.numel(), lr_lambda(epoch))
         if world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(ep)

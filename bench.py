@@ -583,13 +583,16 @@ def run_ours(args, rank, world, local_rank):
             torch.manual_seed(1)
             pt = torch.softmax(torch.randn(TB, 209, device=dev), 1)
             vt = torch.randint(-1, 2, (TB,), device=dev).float()
-            return timed(lambda i: trainer.step(tb, pt, vt, TB * world), 20, 5)
+            ms, launches = timed(lambda i: trainer.step(tb, pt, vt, TB * world), 20, 5)
+            trainer.check()
+            # graph replays do not pass through the library's launch counter: the count of the last eagerly run step stands for them
+            return ms, (trainer.kernels_per_step if trainer.kernels_per_step is not None else launches / 20)
 
         tr = {}
         for TB in (256, 4096):
             ms, launches = train_bench(TB, args.precision)
             tf = FLOP_PER_BOARD_FWDBWD * TB / (ms * 1e-3) / 1e12
-            tr[f"B{TB}"] = {"value": world * TB / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "kernel_launches_per_step": launches / 20,
+            tr[f"B{TB}"] = {"value": world * TB / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "kernel_launches_per_step": launches,
                             "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tf / pk["tensor"]}}
         if prec == 1:
             ms, _ = train_bench(256, "fp32")
@@ -598,7 +601,7 @@ def run_ours(args, rank, world, local_rank):
             for TB in (256, 4096):
                 ms, launches = train_bench(TB, args.precision, "nccl")
                 tr[f"B{TB}_nccl_allreduce"] = {"value": world * TB / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
-                                               "kernel_launches_per_step": launches / 20}
+                                               "kernel_launches_per_step": launches}
             tr["nvlink_bytes_per_step_per_gpu"] = (world - 1) * 64082 * 4 + 2 * (world - 1) * 251 * 4
         tr["config"] = ("BASELINE configs[0] shape (B = 256 per GPU) and a throughput-sized batch (B = 4096 per GPU): FlatTrainer.step = "
                         "aq_gnn_forward(saved) + aq_train_backward_step (loss gradient + heads backward | trunk backward | head weight gradients "
@@ -640,17 +643,27 @@ def run_ours(args, rank, world, local_rank):
                 dist.all_reduce(mm, op=dist.ReduceOp.MIN)
                 Muse = int(mm.item())
             trainer = train_network.FlatTrainer(tnet, rank=rank, world_size=world)
-            perm = torch.randperm(Muse, device=dev)
-            sp, pp, vv = rec["states"][:Muse][perm].contiguous(), rec["policy"][:Muse][perm].contiguous(), rec["value"][:Muse][perm].contiguous()
+            perm = torch.randperm(Muse, device=dev)       # DataLoader(shuffle=True), train_network.py:49
+            sp, pp, vv = rec["states"][:Muse], rec["policy"][:Muse], rec["value"][:Muse]
+            bp, bt, bv = trainer.inputs(128)
             nsteps = min(Muse // 128, 400)
+
+            def cycle_step(i):  # what train_network.train_on_buffer does per batch: gather into the persistent inputs, one step
+                idx = perm[i * 128:(i + 1) * 128]
+                torch.index_select(sp, 0, idx, out=bp)
+                torch.index_select(pp, 0, idx, out=bt)
+                torch.index_select(vv, 0, idx, out=bv)
+                trainer.step(bp, bt, bv, 128 * world)
+
             for i in range(5):
-                trainer.step(sp[i * 128:(i + 1) * 128], pp[i * 128:(i + 1) * 128], vv[i * 128:(i + 1) * 128], 128 * world)
+                cycle_step(i)
             barrier()
             t0 = time.perf_counter()
             for i in range(nsteps):
-                trainer.step(sp[i * 128:(i + 1) * 128], pp[i * 128:(i + 1) * 128], vv[i * 128:(i + 1) * 128], 128 * world)
+                cycle_step(i)
             barrier()
             dt = reduce_max(time.perf_counter() - t0)
+            trainer.check()
             extra["train_cycle"] = {"value": world * 128 * nsteps / dt, "unit": "samples/s", "steps": nsteps, "ms_per_step": dt / nsteps * 1e3,
                                     "config": "BASELINE configs[4]: the self-play record above (device-resident) -> data-parallel training, "
                                               "batch 128 per GPU (train_network.py:15), one all-reduce of the flat gradient per step, wall clock "

@@ -53,7 +53,7 @@ typedef struct AqState {
     uint64_t reserved; /* reserved, 0 */
 } AqState;
 
-#define AQ_VERSION 201 /* bumped with every change of a signature below; the ctypes loader refuses a library of another version */
+#define AQ_VERSION 202 /* bumped with every change of a signature below; the ctypes loader refuses a library of another version */
 int aq_version(void);
 const char *aq_last_error_string(void);
 /* Number of kernels this library has launched in the process so far (monotonic; kernels replayed through a CUDA graph the caller
@@ -162,7 +162,8 @@ int aq_adam_step(float *params, const float *grads, float *exp_avg, float *exp_a
  *                   host channel, e.g. torch.distributed.all_gather_object); not needed when world == 1;
  *   aq_comm_status  out2[0] = optimiser steps completed (device counter), out2[1] = 0 ok / 1 a peer did not arrive within the
  *                   kernel's time-out (the kernel gives up instead of hanging); synchronises `stream`;
- *   aq_comm_set_step sets the device step counter (0 for a fresh optimiser; every rank at the same point).
+ *   aq_comm_set_step sets the device step counter (0 for a fresh optimiser; every rank at the same point) and the running powers
+ *                   beta^step the bias corrections are computed from.
  * aq_dp_adam_step: all-reduce (sum over the ranks) of the flat gradient `grads` + torch.optim.Adam step (train_network.py:56,94) in
  * ONE kernel over NVLink peer memory; `grads` holds the sum afterwards; every rank ends with bit-identical parameters.  The step
  * number of the bias corrections is the device counter + 1.  The replacement for torch.distributed.all_reduce + aq_adam_step. */
@@ -170,7 +171,7 @@ int aq_comm_create(int rank, int world, void **comm, void *handle_out64);
 int aq_comm_open(void *comm, const void *handles);
 int aq_comm_destroy(void *comm);
 int aq_comm_status(void *comm, int64_t *out2, void *stream);
-int aq_comm_set_step(void *comm, int64_t step, void *stream);
+int aq_comm_set_step(void *comm, int64_t step, float beta1, float beta2, void *stream);
 int aq_dp_adam_step(void *comm, float *params, float *grads, float *exp_avg, float *exp_avg_sq, float lr, float beta1, float beta2,
                     float eps, void *stream);
 /* Everything of a training step behind the forward pass -- the reference's `loss = CE + MSE; zero_grad(); loss.backward();

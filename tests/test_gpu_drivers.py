@@ -198,7 +198,7 @@ def test_fused_training_step_equals_the_unfused_kernels(traj, prec):
         lf = fused.step(packed[sl], pt[sl], vt[sl], n).clone()
         le = eager.step(packed[sl], pt[sl], vt[sl], n).clone()
         lp = plain.step(packed[sl], pt[sl], vt[sl], n).clone()
-        assert torch.equal(lf, le)
+        assert (lf - le).abs().max().item() <= 1e-6
         assert (lf - lp).abs().max().item() <= 1e-6      # the loss scalars are atomically accumulated per CTA: summation order
         assert torch.equal(fused.grads, eager.grads)
         assert (fused.grads - plain.grads).abs().max().item() <= 1e-6 * max(1.0, plain.grads.abs().max().item())
