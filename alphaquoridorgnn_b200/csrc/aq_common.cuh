@@ -157,52 +157,81 @@ AQ_DEV B81 jump_targets(const Open &o, int ob, int d) {
     return r ? bit81(ob + 1) : ((u ? bit81(ob - 9) : none) | (dn ? bit81(ob + 9) : none));
 }
 
-// The pawn rules around the obstacle square `ob` (the other pawn) for a flood fill: src[d] = the square from which a move in
-// direction d lands on ob (only if that edge is open), jump[d] = where that move ends up instead.
-struct Jumps {
-    B81 pending;   // union of the source squares whose jump has not been applied yet
-    B81 jump[4];
-    int src[4];    // -1: no such source
-};
-AQ_DEV Jumps jumps_around(const Open &o, int ob) {
-    Jumps j;
-    j.src[0] = has(o.down, ob) ? ob + 9 : -1;   // below ob, moving up
-    j.src[1] = has(o.up, ob) ? ob - 9 : -1;
-    j.src[2] = has(o.right, ob) ? ob + 1 : -1;  // right of ob, moving left
-    j.src[3] = has(o.left, ob) ? ob - 1 : -1;
-    j.pending = b81(0u, 0u, 0u);
+// The pawn rules around the obstacle square `ob` (the other pawn) for a flood fill: a square from which a move in direction d lands
+// on ob (only if that edge is open) is a jump SOURCE; reaching it adds jump_targets(o, ob, d) instead of ob.  The fills keep the
+// union of the sources whose jump has not been applied yet (`pending`); a source is reached at most once, so the per-direction
+// work below runs at most four times per fill and is recomputed there instead of being carried in registers.
+AQ_DEV int jump_source(const Open &o, int ob, int d) {   // -1: no such source
+    if (d == 0) return has(o.down, ob) ? ob + 9 : -1;    // below ob, moving up
+    if (d == 1) return has(o.up, ob) ? ob - 9 : -1;
+    if (d == 2) return has(o.right, ob) ? ob + 1 : -1;   // right of ob, moving left
+    return has(o.left, ob) ? ob - 1 : -1;
+}
+AQ_DEV B81 jump_sources(const Open &o, int ob) {
+    B81 p = b81(0u, 0u, 0u);
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
-        j.jump[d] = jump_targets(o, ob, d);
-        if (j.src[d] >= 0) j.pending = j.pending | bit81(j.src[d]);
+        const int s = jump_source(o, ob, d);
+        if (s >= 0) p = p | bit81(s);
     }
-    return j;
+    return p;
 }
 
-// one flood-fill step: the squares reachable by one plain move from `reach` (the obstacle square excluded by `notob`)
+// one flood-fill step: the squares reachable by one plain move from `reach`
 AQ_DEV B81 step81(const Open &o, B81 reach) {
     return up9(reach & o.up) | down9(reach & o.down) | left1(reach & o.left) | right1(reach & o.right);
 }
 
-// bfs() of game_logic.py:309-324 as a bitboard flood fill with the pawn rules of
-// legal_actions_pos applied at every visited square: the obstacle square `ob` is never entered;
-// a square adjacent to it (edge open) reaches the jump targets instead.  Returns the number of fill
-// iterations (= BFS depth, a jump is one step) after which a square of `goal` is reached, -1 if none is.
-AQ_DEV int flood_depth(const Open &o, int start, int ob, B81 goal) {
-    Jumps j = jumps_around(o, ob);
-    const B81 ob_b = bit81(ob);
-    B81 reach = bit81(start);
-    for (int depth = 0;; ++depth) {
-        if (meets(reach, goal)) return depth;
-        B81 nxt = reach | andn(step81(o, reach), ob_b);
-        if (meets(reach, j.pending)) {  // at most four times per fill: a source square was reached, its jump targets join
+// bfs() of game_logic.py:309-324 as a bitboard flood fill with the pawn rules of legal_actions_pos applied at every visited
+// square: the obstacle square `ob` is never entered; a square adjacent to it (edge open) reaches the jump targets instead.
+// The jump rules of one fill, computed once when the fill starts: in a warp that runs 32 fills as per-lane state machines the
+// branch that applies a jump is taken by one or two lanes at a time, so it has to be a handful of instructions, not the
+// derivation of the targets (measured: deriving them inside the branch halved the lanes active per instruction).
+struct Jumps {
+    B81 src[4];    // one-hot source square per approach direction (empty: no such source)
+    B81 jump[4];   // where a move from that source ends up
+};
+AQ_DEV Jumps jumps_around(const Open &o, int ob) {
+    Jumps j;
 #pragma unroll
-            for (int d = 0; d < 4; ++d)
-                if (j.src[d] >= 0 && has(reach, j.src[d])) nxt = nxt | j.jump[d];
-            j.pending = andn(j.pending, reach);
-        }
-        if (same(nxt, reach)) return -1;
-        reach = nxt;
+    for (int d = 0; d < 4; ++d) {
+        const int s = jump_source(o, ob, d);
+        j.src[d] = s >= 0 ? bit81(s) : b81(0u, 0u, 0u);
+        j.jump[d] = jump_targets(o, ob, d);
+    }
+    return j;
+}
+struct Fill {
+    B81 reach, pending;
+    Jumps j;
+};
+AQ_DEV Fill fill_begin(const Open &o, int start, int ob) {
+    Fill f;
+    f.reach = bit81(start);
+    f.j = jumps_around(o, ob);
+    f.pending = (f.j.src[0] | f.j.src[1]) | (f.j.src[2] | f.j.src[3]);
+    return f;
+}
+// One BFS layer.  Returns false when nothing new was reached (the fill is complete).
+AQ_DEV bool fill_step(const Open &o, int ob, B81 ob_b, Fill &f) {
+    B81 nxt = f.reach | andn(step81(o, f.reach), ob_b);
+    if (meets(f.reach, f.pending)) {  // at most four times per fill: a source square was reached, its jump targets join
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            if (meets(f.reach, f.j.src[d])) nxt = nxt | f.j.jump[d];
+        f.pending = andn(f.pending, f.reach);
+    }
+    const bool grew = !same(nxt, f.reach);
+    f.reach = nxt;
+    return grew;
+}
+// Number of fill iterations (= BFS depth, a jump is one step) after which a square of `goal` is reached, -1 if none is.
+AQ_DEV int flood_depth(const Open &o, int start, int ob, B81 goal) {
+    Fill f = fill_begin(o, start, ob);
+    const B81 ob_b = bit81(ob);
+    for (int depth = 0;; ++depth) {
+        if (meets(f.reach, goal)) return depth;
+        if (!fill_step(o, ob, ob_b, f)) return -1;
     }
 }
 AQ_DEV bool reaches(const Open &o, int start, int ob, B81 goal) { return flood_depth(o, start, ob, goal) >= 0; }
@@ -222,6 +251,8 @@ AQ_DEV B81 goal_row8() { return b81(0u, 0u, kRowLo << 18); }
 // candidates are searched -- a wall behind the other pawn can create diagonal jumps.)
 // The fill records for every square the move that reached it first as two direction-code planes (0 = up, 1 = down, 2 = left,
 // 3 = right) plus a "by a jump" plane; the path is read back from the goal with one-square lookups.
+// The pieces are step functions so that the kernels can run many witnesses per warp as per-lane state machines
+// (board_kernels.cu); find_path_cuts() below is the plain loop over the same steps.
 struct PathCuts {
     u64 cutH, cutV;
     int exists;
@@ -233,57 +264,83 @@ AQ_DEV void mark(B81 &b, int sq) {
     b.w0 |= w == 0 ? m : 0u; b.w1 |= w == 1 ? m : 0u; b.w2 |= w == 2 ? m : 0u;
 }
 
-AQ_DEV PathCuts find_path_cuts(const Open &o, int start, int ob, B81 goal) {
-    Jumps j = jumps_around(o, ob);
-    const B81 ob_b = bit81(ob);
-    B81 reach = bit81(start);
-    B81 c0 = b81(0u, 0u, 0u), c1 = c0, byj = c0;
-    PathCuts pc;
-    pc.cutH = 0; pc.cutV = 0; pc.exists = 0;
-    while (!meets(reach, goal)) {
-        B81 acc = reach, n;
-        n = andn(andn(up9(reach & o.up), ob_b), acc);      acc = acc | n;                              // code 0
-        n = andn(andn(down9(reach & o.down), ob_b), acc);  acc = acc | n; c0 = c0 | n;                 // code 1
-        n = andn(andn(left1(reach & o.left), ob_b), acc);  acc = acc | n; c1 = c1 | n;                 // code 2
-        n = andn(andn(right1(reach & o.right), ob_b), acc); acc = acc | n; c0 = c0 | n; c1 = c1 | n;   // code 3
-        if (meets(reach, j.pending)) {
+struct Witness {
+    B81 reach, pending;   // the fill
+    Jumps j;
+    B81 c0, c1, byj;      // first-reached-by planes
+    B81 ve, he;           // unit edges of the path read back so far: vertical edge (r,c)-(r+1,c) marked at (r,c) in ve,
+                          // horizontal edge (r,c)-(r,c+1) at (r,c) in he
+    int cur;              // read-back cursor
+};
+AQ_DEV Witness witness_begin(const Open &o, int start, int ob) {
+    Witness w;
+    w.reach = bit81(start);
+    w.j = jumps_around(o, ob);
+    w.pending = (w.j.src[0] | w.j.src[1]) | (w.j.src[2] | w.j.src[3]);
+    w.c0 = w.c1 = w.byj = w.ve = w.he = b81(0u, 0u, 0u);
+    w.cur = -1;
+    return w;
+}
+// One BFS layer with the first-reached-by planes.  Returns false when nothing new was reached.
+AQ_DEV bool witness_fill_step(const Open &o, int ob, B81 ob_b, Witness &w) {
+    const B81 reach = w.reach;
+    B81 acc = reach, n;
+    n = andn(andn(up9(reach & o.up), ob_b), acc);       acc = acc | n;                                       // code 0
+    n = andn(andn(down9(reach & o.down), ob_b), acc);   acc = acc | n; w.c0 = w.c0 | n;                      // code 1
+    n = andn(andn(left1(reach & o.left), ob_b), acc);   acc = acc | n; w.c1 = w.c1 | n;                      // code 2
+    n = andn(andn(right1(reach & o.right), ob_b), acc); acc = acc | n; w.c0 = w.c0 | n; w.c1 = w.c1 | n;     // code 3
+    if (meets(reach, w.pending)) {
 #pragma unroll
-            for (int d = 0; d < 4; ++d)
-                if (j.src[d] >= 0 && has(reach, j.src[d])) {
-                    n = andn(j.jump[d], acc);
-                    acc = acc | n; byj = byj | n;
-                    if (d & 1) c0 = c0 | n;
-                    if (d & 2) c1 = c1 | n;
-                }
-            j.pending = andn(j.pending, reach);
-        }
-        if (same(acc, reach)) return pc;  // goal unreachable even without a candidate
-        reach = acc;
+        for (int d = 0; d < 4; ++d)
+            if (meets(reach, w.j.src[d])) {
+                n = andn(w.j.jump[d], acc);
+                acc = acc | n; w.byj = w.byj | n;
+                if (d & 1) w.c0 = w.c0 | n;
+                if (d & 2) w.c1 = w.c1 | n;
+            }
+        w.pending = andn(w.pending, reach);
     }
+    const bool grew = !same(acc, reach);
+    w.reach = acc;
+    return grew;
+}
+// One step of the read-back from w.cur towards `start`; marks the unit edge(s) of the move that reached w.cur.
+AQ_DEV void witness_back_step(int ob, Witness &w) {
+    const int cur = w.cur;
+    const int code = (int)has(w.c0, cur) | ((int)has(w.c1, cur) << 1);
+    const int back = code == 0 ? 9 : code == 1 ? -9 : code == 2 ? 1 : -1;  // from the square back to where the move came from
+    if (has(w.byj, cur)) {  // jump over the pawn on ob, approached in direction `code`: unit edges src-ob and ob-cur
+        const int src = ob + back;
+        if (back == 9 || back == -9) mark(w.ve, src < ob ? src : ob); else mark(w.he, src < ob ? src : ob);
+        const int lo = cur < ob ? cur : ob, df = cur < ob ? ob - cur : cur - ob;
+        if (df == 9) mark(w.ve, lo); else mark(w.he, lo);
+        w.cur = src;
+    } else {
+        const int prev = cur + back;
+        if (back == 9 || back == -9) mark(w.ve, prev < cur ? prev : cur); else mark(w.he, prev < cur ? prev : cur);
+        w.cur = prev;
+    }
+}
+// vertical edge at (r,c): H walls in slots (r,c) [c < 8] and (r,c-1) [c > 0]; horizontal edge at (r,c): V walls in slots
+// (r,c) [r < 8] and (r-1,c) [r > 0].  compress9to8 drops column 8 / row 8, the shifts drop column 0 / row 0.
+AQ_DEV PathCuts witness_cuts(const Witness &w) {
+    PathCuts pc;
     pc.exists = 1;
-    // unit edges of the path: vertical edge (r,c)-(r+1,c) marked at square (r,c) in ve, horizontal edge (r,c)-(r,c+1) at (r,c) in he
-    B81 ve = b81(0u, 0u, 0u), he = ve;
-    int cur = lowest_square(reach & goal);
-    while (cur != start) {
-        const int code = (int)has(c0, cur) | ((int)has(c1, cur) << 1);
-        const int back = code == 0 ? 9 : code == 1 ? -9 : code == 2 ? 1 : -1;  // from the square back to where the move came from
-        if (has(byj, cur)) {  // jump over the pawn on ob, approached in direction `code`: unit edges src-ob and ob-cur
-            const int src = ob + back;
-            if (back == 9 || back == -9) mark(ve, src < ob ? src : ob); else mark(he, src < ob ? src : ob);
-            const int lo = cur < ob ? cur : ob, df = cur < ob ? ob - cur : cur - ob;
-            if (df == 9) mark(ve, lo); else mark(he, lo);
-            cur = src;
-        } else {
-            const int prev = cur + back;
-            if (back == 9 || back == -9) mark(ve, prev < cur ? prev : cur); else mark(he, prev < cur ? prev : cur);
-            cur = prev;
-        }
-    }
-    // vertical edge at (r,c): H walls in slots (r,c) [c < 8] and (r,c-1) [c > 0]; horizontal edge at (r,c): V walls in slots
-    // (r,c) [r < 8] and (r-1,c) [r > 0].  compress9to8 drops column 8 / row 8, the shifts drop column 0 / row 0.
-    pc.cutH = compress9to8(ve) | compress9to8(left1(andn(ve, b81(kCol0W, kCol0W, kCol0W))));
-    pc.cutV = compress9to8(he) | compress9to8(up9(he));
+    pc.cutH = compress9to8(w.ve) | compress9to8(left1(andn(w.ve, b81(kCol0W, kCol0W, kCol0W))));
+    pc.cutV = compress9to8(w.he) | compress9to8(up9(w.he));
     return pc;
+}
+
+AQ_DEV PathCuts find_path_cuts(const Open &o, int start, int ob, B81 goal) {
+    Witness w = witness_begin(o, start, ob);
+    const B81 ob_b = bit81(ob);
+    PathCuts none;
+    none.cutH = 0; none.cutV = 0; none.exists = 0;
+    while (!meets(w.reach, goal))
+        if (!witness_fill_step(o, ob, ob_b, w)) return none;  // goal unreachable even without a candidate
+    w.cur = lowest_square(w.reach & goal);
+    while (w.cur != start) witness_back_step(ob, w);
+    return witness_cuts(w);
 }
 
 // legal_actions_pos (game_logic.py:120-192) from square p with the enemy pawn on e (mover's

@@ -192,21 +192,28 @@ legal_mask_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__res
 }
 
 // ------------------------------------------------------------------------------------------
-// K1, two-phase form (the default): the searches of ALL states go through one flat task list.
-//   legal_prepare_kernel : two lanes per state; everything of legal_mask_kernel up to the witness paths, then the
-//                          (candidate, player) searches that are still needed are appended to a global task list
-//                          (one warp-aggregated atomicAdd) and the mask is written OPTIMISTICALLY (every gated
+// K1, two-phase form (the default above 4,096 states): the searches of ALL states go through one flat task list.
+//   legal_prepare_kernel : two lanes per state; everything of legal_mask_kernel up to the witness paths (lane 0: the mover's,
+//                          lane 1: the opponent's), then the (candidate, player) searches that are still needed are appended to a
+//                          global task list (one warp-aggregated atomicAdd) and the mask is written OPTIMISTICALLY (every gated
 //                          candidate legal);
-//   legal_search_kernel  : one thread per task, grid-stride: rebuild the open-direction boards of the task's state
-//                          (+ the candidate wall), run the flood fill, clear the candidate's mask bit on failure.
-// The per-state number of searches is 0 .. ~60 with a mean of 2-4, so the one-kernel form spends most of its lanes
-// waiting for the slowest state of their warp; the flat list has no such imbalance and the search kernel runs at
-// four times the occupancy.  A state whose tasks do not fit the list (capacity 8 per state on average) runs them
-// itself, as legal_mask_kernel does -- results never depend on the capacity.
+//   legal_search_kernel  : persistent warps of 32 search state machines fed from the global list through a cursor: a lane whose
+//                          flood fill has finished (goal reached, or nothing new: clear the candidate's mask bit) takes the next
+//                          task while the others continue.  Fills that fail explore their whole region and take several times
+//                          longer than the ones that succeed; one task per thread left 21 of 32 lanes idle on average (ncu,
+//                          profiles/): 408 -> 352 us per 1 M positions.
+//                          (The same per-lane state machines for the WITNESS paths of the first kernel -- CTA-local task list,
+//                          fill and read-back as stages -- were built and measured: 13 instead of 11 active lanes per instruction, no
+//                          gain in time, because lanes in different stages split every round; dropped.)
+// The per-state number of searches is 0 .. ~60 with a mean of 2-4, so the one-kernel form spends most of its lanes waiting for the
+// slowest state of their warp.  A state whose tasks do not fit the list (capacity 8 per state on average) runs them itself, as
+// legal_mask_kernel does -- results never depend on the capacity.
 // task word: state index << 8 | slot | (orient - 1) << 6 | opponent << 7;  kNullTask = hole left by an overflow.
+// workspace: [0] number of tasks, [1] the search kernel's cursor, tasks from byte 256.
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kNullTask = 0xFFFFFFFFu;
 constexpr int64_t kLegalChunk = (int64_t)1 << 23;  // states per launch pair (state index field: 24 bits)
+constexpr int kRefillIdle = 8;                     // a warp fetches new tasks when at least this many of its lanes are idle
 
 __global__ void __launch_bounds__(kLegalWarps * 32)
 legal_prepare_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__restrict__ mask, uint8_t *__restrict__ pawn,
@@ -315,24 +322,64 @@ legal_prepare_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__
 }
 
 __global__ void __launch_bounds__(128)
-legal_search_kernel(const AqState *__restrict__ states, const uint32_t *tasks, const unsigned *counter,
+legal_search_kernel(const AqState *__restrict__ states, const uint32_t *tasks, const unsigned *counter, unsigned *cursor,
                     unsigned cap, uint32_t *__restrict__ mask) {
     aq_pdl_trigger();
     aq_pdl_wait();  // launched programmatically behind legal_prepare_kernel: its task list and counter are complete from here on
+    const int lane = threadIdx.x & 31;
     const unsigned n = min(__ldcg(counter), cap);  // coherent loads: see the PDL rule in aq_common.cuh
-    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-        const uint32_t w = __ldcg(tasks + t);
-        if (w == kNullTask) continue;
-        const int64_t b = w >> 8;
-        const int slot = w & 63, orient = ((w >> 6) & 1) + 1, opp = (w >> 7) & 1;
-        const AqState s = load_state(states + b);
-        Open o = open_from_walls(s.hwalls, s.vwalls);
-        add_wall(o, orient, slot);
-        const int me = s.ppos, en = 80 - (int)s.epos;
-        const bool ok = opp ? reaches(o, en, me, goal_row8()) : reaches(o, me, en, goal_row0());
-        if (!ok) {
-            const int a = AQ_SQUARES + (orient == 2 ? AQ_SLOTS : 0) + slot;
-            atomicAnd(mask + 8 * b + (a >> 5), ~(1u << (a & 31)));
+    bool active = false, exhausted = n == 0u;
+    Open o;
+    Fill f;
+    B81 ob_b = b81(0u, 0u, 0u), goal = ob_b;
+    o.up = o.down = o.left = o.right = ob_b;
+    f.reach = f.pending = ob_b;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) f.j.src[d] = f.j.jump[d] = ob_b;
+    int ob = 0, action = 0;
+    int64_t b = 0;
+    while (true) {
+        unsigned act = __ballot_sync(0xffffffffu, active);
+        const int n_idle = 32 - __popc(act);
+        if (!exhausted && (n_idle >= kRefillIdle || act == 0u)) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (unsigned)n_idle);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            exhausted = base + (unsigned)n_idle >= n;
+            if (!active) {
+                const unsigned t = base + (unsigned)__popc(~act & ((1u << lane) - 1u));
+                const uint32_t w = t < n ? __ldcg(tasks + t) : kNullTask;
+                if (w != kNullTask) {
+                    b = w >> 8;
+                    const int slot = w & 63, orient = ((w >> 6) & 1) + 1, opp = (w >> 7) & 1;
+                    const AqState s = load_state(states + b);
+                    o = open_from_walls(s.hwalls, s.vwalls);
+                    add_wall(o, orient, slot);
+                    const int me = s.ppos, en = 80 - (int)s.epos;
+                    ob = opp ? me : en;
+                    goal = opp ? goal_row8() : goal_row0();
+                    ob_b = bit81(ob);
+                    f = fill_begin(o, opp ? en : me, ob);
+                    action = AQ_SQUARES + (orient == 2 ? AQ_SLOTS : 0) + slot;
+                    active = true;
+                }
+            }
+            act = __ballot_sync(0xffffffffu, active);
+        }
+        if (act == 0u) {
+            if (exhausted) break;
+            continue;   // every fetched word was a hole: fetch again
+        }
+        if (active) {
+            // two BFS layers per round (one exit test per two layers: the fill is monotone, a layer too many changes nothing)
+            bool grew = fill_step(o, ob, ob_b, f);
+            if (grew && !meets(f.reach, goal)) grew = fill_step(o, ob, ob_b, f);
+            if (meets(f.reach, goal)) {
+                active = false;
+            } else if (!grew) {
+                atomicAnd(mask + 8 * b + (action >> 5), ~(1u << (action & 31)));
+                active = false;
+            }
         }
     }
 }
@@ -581,19 +628,20 @@ extern "C" int aq_legal_mask_ws(const AqState *states, int64_t B, uint32_t *mask
     // any workspace >= 4 KB + 256 B works (a state whose searches do not fit the list runs them itself); aq_legal_mask_ws_bytes(B)
     // is the size at which that practically never happens
     if (ws_bytes < 256 + 4096 || (reinterpret_cast<uintptr_t>(ws) & 3)) return aq_set_error(AQ_ERR_ARG, "aq_legal_mask(workspace)");
-    unsigned *counter = reinterpret_cast<unsigned *>(ws);
+    unsigned *counter = reinterpret_cast<unsigned *>(ws);   // [0] task count, [1] the search kernel's cursor
     uint32_t *tasks = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(ws) + 256);
     const unsigned cap = (unsigned)std::min<int64_t>((ws_bytes - 256) / 4, (int64_t)legal_task_cap(B));
     for (int64_t lo = 0; lo < B; lo += kLegalChunk) {
         const int64_t n = B - lo < kLegalChunk ? B - lo : kLegalChunk;
-        cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), S(stream));
+        cudaError_t e = cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned), S(stream));
         if (e != cudaSuccess) return aq_set_error((int)e, "aq_legal_mask(memset)");
         legal_prepare_kernel<<<blocks_for(n, kLegalWarps * 16), kLegalWarps * 32, 0, S(stream)>>>(states + lo, n, mask + 8 * lo, pawn + 8 * lo,
                                                                                                      tasks, cap, counter);
-        // enough threads for the expected number of searches (2-4 per state), at most 16 CTAs of 128 per SM; grid-stride beyond
-        const unsigned grid = (unsigned)std::min<int64_t>(148 * 16, std::max<int64_t>(1, (4 * n + 127) / 128));
-        e = aq_launch_pdl(legal_search_kernel, dim3(grid), dim3(128), 0, S(stream), states + lo, (const uint32_t *)tasks, (const unsigned *)counter, cap,
-                          mask + 8 * lo);
+        // persistent warps fed through the cursor: enough of them for the expected number of searches (2-4 per state), at most 8 CTAs
+        // of 128 threads per SM
+        const unsigned grid = (unsigned)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (3 * n + 127) / 128));
+        e = aq_launch_pdl(legal_search_kernel, dim3(grid), dim3(128), 0, S(stream), states + lo, (const uint32_t *)tasks, (const unsigned *)counter,
+                          counter + 1, cap, mask + 8 * lo);
         if (e != cudaSuccess) return aq_set_error((int)e, "aq_legal_mask(search launch)");
         const int rc = aq_check_launch("aq_legal_mask");
         if (rc) return rc;
