@@ -7,20 +7,21 @@
 // all_gather_object in train_network.py) and map each other's block with cudaIpcOpenMemHandle -- from then on a kernel on GPU r
 // loads and stores GPU q's block directly (NVLink 5 through NVSwitch on a B200 box).
 //
-// dp_adam_kernel, CTA c of rank r, step e (= the device-side step counter + 1, parity p = e & 1):
-//   1. local gradient of parameter chunk c (256 parameters): the fixed-order slot sum of reduce_partials_kernel (deterministic), or a
-//      given flat gradient;
-//   2. world > 1: store the chunk into the own slot p, __syncthreads, then thread t < world publishes it to rank t: fence.sc.sys
-//      and a release store of e into flag[r][c] of rank t's block (peer store); the same threads spin (ld.acquire.sys) until
-//      the own flag[t][c] reaches e -- CTA c only ever waits for the CTA c of the other ranks, which wait for nothing of this rank
-//      before they publish, so there is no cyclic wait whatever the order in which CTAs are scheduled; then every thread adds the
-//      chunk of ranks 0 .. world-1 IN THAT ORDER (own value included, coherent loads from peer memory): every rank computes the
-//      same sum bit for bit, so the replicas never diverge.  The two slots alternate by step: a rank can only be one step ahead of
-//      a peer (it needs the peer's flag of step e to finish step e), so slot p is never overwritten while a peer still reads it;
-//   3. Adam on the summed gradient (torch's lerp / addcmul / addcdiv sequence, bias corrections from the device step counter in
-//      double precision);
+// dp_adam_kernel, thread of parameter pair i on rank r, step e (= the device-side step counter + 1, parity p = e & 1):
+//   1. local gradient of the pair: the fixed-order slot sum of reduce_partials_kernel (deterministic), or a given flat gradient;
+//   2. world > 1: PUSH the pair into the inbox every other rank keeps for rank r -- two 8-byte peer stores {value, e}: the step
+//      number travels in the same 8-byte word as the value, so a word whose tag reads e carries this step's value (8-byte stores are
+//      single transactions; the low-latency scheme of NCCL's LL protocol).  No fence, no block barrier, no flag round trip: measured
+//      against a first version that stored into an own slot, published a flag with a system-scope release and let the peers pull
+//      (15-20 us per step at two GPUs: fence + flag + pull round trip), this costs one NVLink store latency;
+//      then poll the own inboxes (local memory) until the words of ranks 0 .. world-1 carry tag e and add them IN RANK ORDER (own
+//      value included): every rank computes the same sum bit for bit, so the replicas never diverge.  Inboxes alternate by step
+//      parity: a rank can only be one step ahead of a peer (it needs the peer's words of step e to finish step e), so a word is
+//      never overwritten before it has been read;
+//   3. Adam on the summed gradient (torch's lerp / addcmul / addcdiv sequence, bias corrections from the device step counter and
+//      running powers of the betas in double precision);
 //   4. the last CTA to finish advances the step counter.
-// A rank that does not show up within kTimeoutNs (a crashed peer) makes the waiting CTAs give up and raise the status word, which
+// A rank that does not show up within kTimeoutNs (a crashed peer) makes the waiting threads give up and raise the status word, which
 // aq_comm_status returns: the kernel never hangs the GPU.
 // No host value changes between steps except the learning rate, so the whole training step can be captured in a CUDA graph.
 #include <cmath>
@@ -42,8 +43,7 @@ constexpr unsigned long long kTimeoutNs = 5ull * 1000 * 1000 * 1000;
 static_assert(kNumParams % 2 == 0 && kOffWP0 % 2 == 0, "parameter pairs must not straddle the GCN / head boundary");
 
 struct CommBlock {                       // layout of the exported device block
-    float slot[2][kPadFloats];
-    uint32_t flag[kMaxWorld][kChunks + 1];
+    uint2 inbox[2][kMaxWorld][kPadFloats];   // [step parity][sender][parameter] = {value bits, step tag}
     uint32_t step;                       // completed optimiser steps
     uint32_t ticket;                     // CTAs finished in the current launch
     uint32_t status;                     // != 0: a wait timed out
@@ -69,13 +69,14 @@ __device__ __forceinline__ unsigned long long now_ns() {
     asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+// one 8-byte transaction each: {value, tag} never tears
+__device__ __forceinline__ uint2 ld_word(const uint2 *p) {
+    uint2 v;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_word(uint2 *p, uint32_t value, uint32_t tag) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};\n" ::"l"(p), "r"(value), "r"(tag) : "memory");
 }
 
 // block = 128 parameter pairs x 4 slot groups.  kFromSlots: the local gradient is the fixed-order sum of the partial slots
@@ -89,7 +90,6 @@ dp_adam_kernel(CommPtrs c, const float *grads_in, const float *partial, int gcn_
                float beta2, float eps) {
     __shared__ float2 part[4][kPairs];
     __shared__ float hyper[2];
-    __shared__ int timed_out;
     aq_pdl_wait();  // launched programmatically behind the backward kernels: everything read below was written before it
     const int tid = threadIdx.x, cta = blockIdx.x;
     const int tx = tid & (kPairs - 1), grp = tid / kPairs;
@@ -101,9 +101,15 @@ dp_adam_kernel(CommPtrs c, const float *grads_in, const float *partial, int gcn_
     if (tid == 0) {
         hyper[0] = (float)((double)lr / (1.0 - b1p));   // step_size = lr / bias_correction1
         hyper[1] = (float)sqrt(1.0 - b2p);              // bias_correction2_sqrt
-        timed_out = 0;
     }
     const int i = cta * kChunkFloats + 2 * tx;  // this thread's parameter pair (pairs beyond kNumParams are padding)
+    // the optimiser state of the pair is requested now, under the slot loads, not behind the reduction's barrier
+    float2 m0 = make_float2(0.f, 0.f), v0 = m0, p0 = m0;
+    if (grp == 0 && i < kNumParams) {
+        m0 = *reinterpret_cast<const float2 *>(exp_avg + i);
+        v0 = *reinterpret_cast<const float2 *>(exp_avg_sq + i);
+        p0 = *reinterpret_cast<const float2 *>(params + i);
+    }
     float2 g = make_float2(0.f, 0.f);
     if (kFromSlots) {
         if (i < kNumParams) {
@@ -124,38 +130,35 @@ dp_adam_kernel(CommPtrs c, const float *grads_in, const float *partial, int gcn_
     } else if (grp == 0 && i < kNumParams) {
         g = __ldcg(reinterpret_cast<const float2 *>(grads_in + i));
     }
-    if (c.world > 1) {
-        if (grp == 0) *reinterpret_cast<float2 *>(&me->slot[par][i]) = g;
-        __syncthreads();
-        // publish chunk `cta` of this rank to every rank (release: ordered behind the chunk's stores, which the barrier made
-        // happen-before this thread), then wait for chunk `cta` of every rank
-        if (tid < c.world) {
-            __threadfence_system();
-            st_release_sys(&c.peer[tid]->flag[c.rank][cta], e);
-            const unsigned long long t0 = now_ns();
-            while (ld_acquire_sys(&me->flag[tid][cta]) < e) {
-                if (now_ns() - t0 > kTimeoutNs) { timed_out = 1; break; }
+    __syncthreads();   // hyper[]
+    if (c.world > 1 && grp == 0) {
+        // push this rank's pair into its inbox on every other rank
+        for (int r = 0; r < c.world; ++r)
+            if (r != c.rank) {
+                uint2 *dst = &c.peer[r]->inbox[par][c.rank][i];
+                st_word(dst, __float_as_uint(g.x), e);
+                st_word(dst + 1, __float_as_uint(g.y), e);
             }
-        }
-        __syncthreads();
-        if (timed_out) {
-            if (tid == 0) atomicExch(&me->status, 1u);
-        } else if (grp == 0) {
-            float2 a = make_float2(0.f, 0.f);
-#pragma unroll 8
-            for (int r = 0; r < c.world; ++r) {   // fixed order, the own contribution included: bit-identical on every rank
-                const float2 v = __ldcg(reinterpret_cast<const float2 *>(&c.peer[r]->slot[par][i]));
-                a.x += v.x; a.y += v.y;
+        // collect: ranks in fixed order, the own contribution in its place: bit-identical sums on every rank
+        float2 a = make_float2(0.f, 0.f);
+        const unsigned long long t0 = now_ns();
+        bool ok = true;
+        for (int r = 0; r < c.world && ok; ++r) {
+            if (r == c.rank) { a.x += g.x; a.y += g.y; continue; }
+            const uint2 *src = &me->inbox[par][r][i];
+            uint2 w0 = ld_word(src), w1 = ld_word(src + 1);
+            unsigned polls = 0;
+            while (w0.y != e || w1.y != e) {
+                if ((++polls & 255u) == 0u && now_ns() - t0 > kTimeoutNs) { ok = false; break; }
+                w0 = ld_word(src); w1 = ld_word(src + 1);
             }
-            g = a;
+            a.x += __uint_as_float(w0.x); a.y += __uint_as_float(w1.x);
         }
-    } else {
-        __syncthreads();
+        if (!ok) atomicExch(&me->status, 1u);
+        g = a;
     }
     if (grp == 0 && i < kNumParams) {
         const float step_size = hyper[0], bc2_sqrt = hyper[1];
-        const float2 m0 = *reinterpret_cast<const float2 *>(exp_avg + i), v0 = *reinterpret_cast<const float2 *>(exp_avg_sq + i);
-        const float2 p0 = *reinterpret_cast<const float2 *>(params + i);
         float2 m1, v1, p1;
         m1.x = m0.x + (1.f - beta1) * (g.x - m0.x);            // exp_avg.lerp_(grad, 1 - beta1)
         m1.y = m0.y + (1.f - beta1) * (g.y - m0.y);
@@ -248,14 +251,16 @@ extern "C" int aq_comm_status(void *comm, int64_t *out2, void *stream) {
 }
 
 // Sets the device step counter (a fresh optimiser: 0) and the running powers beta1^step, beta2^step of the bias corrections.
-// Every rank must call it at the same point of its stream.
+// Every rank must call it at the same point, with no step in flight on any rank (a host barrier before and after).
 extern "C" int aq_comm_set_step(void *comm, int64_t step, float beta1, float beta2, void *stream) {
     if (!comm || step < 0) return aq_set_error(AQ_ERR_ARG, "aq_comm_set_step");
     AqComm *c = reinterpret_cast<AqComm *>(comm);
     const uint32_t v = (uint32_t)step;
     const double pw[2] = {pow((double)beta1, (double)step), pow((double)beta2, (double)step)};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemcpyAsync(&c->local->step, &v, 4, cudaMemcpyHostToDevice, st);
+    // the inboxes are cleared too: their words carry step tags, and tags of an earlier run must not be mistaken for this one's
+    cudaError_t e = cudaMemsetAsync(c->local->inbox, 0, sizeof(c->local->inbox), st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&c->local->step, &v, 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&c->local->beta_pow[0], pw, sizeof pw, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     return e == cudaSuccess ? 0 : aq_set_error((int)e, "aq_comm_set_step");

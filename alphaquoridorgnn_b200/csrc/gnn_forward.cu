@@ -308,10 +308,9 @@ static int launch_trunk(const float *params, const void *prepared, const AqState
 
 static int launch_heads(const float *params, const void *prepared, const float *pooled, int64_t B, float *policy,
                         float *value, const uint32_t *legal_mask, float *saved, int precision, cudaStream_t st, bool after_trunk = false) {
-    // tensor-core heads: inference, and the training forward (hidden activations etc. saved by the kernel).  A training batch of up
-    // to one wave of the warp-per-board kernel (148 CTAs x 8 boards) takes that kernel instead: the tensor-core kernel is a serial
-    // chain of ~20 us per 128-board tile whatever the batch, the warp-per-board kernel needs ~9 us for one wave (B = 256: 23 -> 9 us)
-    if (precision == 1 && (!saved || !legal_mask) && !(saved && B <= 1184))
+    // tensor-core heads: inference, and the training forward (hidden activations etc. saved by the kernel).  (Measured at B = 256: the
+    // warp-per-board kernel is no faster there -- 26 us against 23 us: its 116 KB weight fill per CTA costs what the tile chain costs.)
+    if (precision == 1 && (!saved || !legal_mask))
         return aq_heads_forward_tc(params, prepared, pooled, B, policy, value, legal_mask, saved, after_trunk, st);
     const int64_t hb = (B + 7) / 8;
     const unsigned hgrid = (unsigned)(hb < num_sms() ? hb : num_sms());

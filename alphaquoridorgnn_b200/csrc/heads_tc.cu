@@ -9,7 +9,6 @@
 //   exchanged between the four quarters through shared memory; optional restriction to the legal mask and
 //   renormalisation (BaseNetwork.predict); the probabilities leave through a per-warp transposing stage so that every
 //   global store is 32 consecutive floats of one board (the [B, 209] rows are only 4-byte aligned).
-#include <algorithm>
 #include <cstddef>
 #include <cuda_bf16.h>
 #include "aq_common.cuh"
@@ -98,16 +97,14 @@ template <bool kLegal>
 __global__ void __launch_bounds__(kHtThreads)
 heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *__restrict__ prepared,
                         const float *pooled, int64_t B, float *__restrict__ policy,
-                        float *__restrict__ value, const uint32_t *mask, float *__restrict__ saved, int rows) {
-    // rows (a multiple of 16, <= 128): boards per CTA.  The MMAs always work on M = 128 (rows beyond `rows` hold stale bytes whose
-    // results are never read); what shrinks with `rows` is what bounds the kernel -- the pooled loads and the output stores of a CTA
+                        float *__restrict__ value, const uint32_t *mask, float *__restrict__ saved) {
     // saved != nullptr (training forward, precision 1): the post-ReLU hidden activations (fp32, before the bf16 rounding that feeds
     // GEMM 2), the probabilities and the value are also written into the SavedLayout regions heads_backward_kernel reads
     extern __shared__ unsigned char smem_raw[];
     HtSmem &sm = *reinterpret_cast<HtSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & (kTile - 1), q = tid >> 7;  // board of this thread inside the tile / column quarter it handles
-    const int64_t b0 = (int64_t)blockIdx.x * rows;
+    const int64_t b0 = (int64_t)blockIdx.x * kTile;
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");  // a kernel launched programmatically behind this one (the scan of the
                                                                         // host path) may be scheduled; it waits for this grid's completion
 
@@ -164,31 +161,17 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
     // parameters and overlaps the tail of the kernel that produces `pooled` (the trunk triggers its dependents at its start); the
     // activations and the legal mask are read after the wait.  Without a programmatic predecessor the wait returns at once.
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
-    // A1 = pooled rows of this tile (zeros past B)
-#ifndef HT_BATCHED
-#define HT_BATCHED 1
-#endif
-    float4 pl[4][2];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int c = tid + k * kHtThreads, r = c >> 4, j = c & 15;
-        pl[k][0] = pl[k][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (HT_BATCHED && r < rows && b0 + r < B) {   // all of a thread's loads are issued before the first use
-            pl[k][0] = __ldcg(reinterpret_cast<const float4 *>(pooled + (b0 + r) * kH + j * 8));  // coherent: PDL rule (aq_common.cuh)
-            pl[k][1] = __ldcg(reinterpret_cast<const float4 *>(pooled + (b0 + r) * kH + j * 8) + 1);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int c = tid + k * kHtThreads, r = c >> 4, j = c & 15;
-        if (r >= rows) break;   // warp-uniform: a warp covers two consecutive rows, `rows` is even
-        if (!HT_BATCHED && b0 + r < B) {
-            pl[k][0] = __ldcg(reinterpret_cast<const float4 *>(pooled + (b0 + r) * kH + j * 8));
-            pl[k][1] = __ldcg(reinterpret_cast<const float4 *>(pooled + (b0 + r) * kH + j * 8) + 1);
-        }
-        const float4 lo = pl[k][0], hi = pl[k][1];
+    for (int c = tid; c < kTile * 16; c += kHtThreads) {  // A1 = pooled rows of this tile (zeros past B)
+        const int r = c >> 4, j = c & 15;
         float f[8];
-        f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+        if (b0 + r < B) {
+            const float4 lo = __ldcg(reinterpret_cast<const float4 *>(pooled + (b0 + r) * kH + j * 8));  // coherent: PDL rule (aq_common.cuh)
+            const float4 hi = __ldcg(reinterpret_cast<const float4 *>(pooled + (b0 + r) * kH + j * 8) + 1);
+            f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        }
         *reinterpret_cast<uint4 *>(sm.a + sw128(r, j)) = pack8(f);
         // a NaN marks a board whose activations did not fit the trunk's fp16 aggregation: fmaxf() in the ReLUs below would swallow
         // it, so the row is remembered and its outputs are written as NaN.  The 16 chunks of a row sit in one half-warp.
@@ -203,7 +186,7 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
     const uint32_t tmem = sm.tmem_base;
     const uint32_t a_addr = smem_u32(sm.a), b1_addr = smem_u32(sm.b1), b2_addr = smem_u32(sm.b2);
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's TMEM lane quadrant
-    const bool valid = row < rows && b0 + row < B;
+    const bool valid = b0 + row < B;
 
     // ---- GEMM 1: hidden layers of both heads -------------------------------------------------------
     if (tid == 0) {
@@ -341,7 +324,7 @@ heads_forward_tc_kernel(const float *__restrict__ params, const unsigned char *_
             if (col < kP) {
 #pragma unroll 8
                 for (int r = 0; r < 32; ++r)
-                    if (r0 + r < rows && b0 + r0 + r < B) {
+                    if (b0 + r0 + r < B) {
                         const float pr = stage[r * kStagePitch + lane];
                         policy[(b0 + r0 + r) * kP + col] = pr;
                         if (saved) saved[SavedLayout{B}.policy() + (b0 + r0 + r) * kP + col] = pr;
@@ -380,31 +363,16 @@ int aq_heads_forward_tc(const float *params, const void *prepared_v, const float
                         float *value, const uint32_t *legal_mask, float *saved, bool pdl, cudaStream_t st) {
     const unsigned char *prepared = reinterpret_cast<const unsigned char *>(prepared_v);
     const size_t smem = sizeof(HtSmem) + 1024;
-    // boards per CTA: as few as fill the machine once (148 SMs), in steps of 16, at most 128 (16,384 boards: 112 per CTA on 147 SMs
-    // instead of 128 on 128; 4,096 boards: 32 per CTA)
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-#ifdef HT_FIXED_ROWS
-    int rows = HT_FIXED_ROWS;
-#else
-    int rows = (int)std::min<int64_t>(kTile, ((B + sms - 1) / sms + 15) / 16 * 16);
-    if (rows < 32) rows = 32;
-#endif
-    const unsigned grid = (unsigned)((B + rows - 1) / rows);
+    const unsigned grid = (unsigned)((B + kTile - 1) / kTile);
     cudaError_t e, rc_launch = cudaSuccess;
     if (legal_mask) {
         e = cudaFuncSetAttribute(heads_forward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return aq_set_error((int)e, "heads_forward_tc smem");
-        rc_launch = launch_pdl(pdl, heads_forward_tc_kernel<true>, grid, smem, st, params, prepared, pooled, B, policy, value, legal_mask, saved, rows);
+        rc_launch = launch_pdl(pdl, heads_forward_tc_kernel<true>, grid, smem, st, params, prepared, pooled, B, policy, value, legal_mask, saved);
     } else {
         e = cudaFuncSetAttribute(heads_forward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return aq_set_error((int)e, "heads_forward_tc smem");
-        rc_launch = launch_pdl(pdl, heads_forward_tc_kernel<false>, grid, smem, st, params, prepared, pooled, B, policy, value, (const uint32_t *)nullptr, saved, rows);
+        rc_launch = launch_pdl(pdl, heads_forward_tc_kernel<false>, grid, smem, st, params, prepared, pooled, B, policy, value, (const uint32_t *)nullptr, saved);
     }
     if (rc_launch != cudaSuccess) return aq_set_error((int)rc_launch, "heads_forward_tc_kernel(launch)");
     return aq_check_launch("heads_forward_tc_kernel");
