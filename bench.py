@@ -602,7 +602,8 @@ def run_ours(args, rank, world, local_rank):
                 ms, launches = train_bench(TB, args.precision, "nccl")
                 tr[f"B{TB}_nccl_allreduce"] = {"value": world * TB / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
                                                "kernel_launches_per_step": launches}
-            tr["nvlink_bytes_per_step_per_gpu"] = (world - 1) * 64082 * 4 + 2 * (world - 1) * 251 * 4
+            # every rank pushes its flat gradient as {value, step tag} words of 8 bytes into its inbox on each of the other ranks
+            tr["nvlink_bytes_per_step_per_gpu"] = {"sent": (world - 1) * 251 * 256 * 8, "received": (world - 1) * 251 * 256 * 8}
         tr["config"] = ("BASELINE configs[0] shape (B = 256 per GPU) and a throughput-sized batch (B = 4096 per GPU): FlatTrainer.step = "
                         "aq_gnn_forward(saved) + aq_train_backward_step (loss gradient + heads backward | trunk backward | head weight gradients "
                         "| slot reduction + peer-memory all-reduce + Adam), replayed as one CUDA graph")
