@@ -9,7 +9,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libaqgnn.so")
-ABI_VERSION = 202  # AQ_VERSION of include/aqgnn.h this table of signatures was written for
+ABI_VERSION = 203  # AQ_VERSION of include/aqgnn.h this table of signatures was written for
 
 # name -> (restype, argtypes); must list every symbol declared in include/aqgnn.h
 _vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
@@ -56,6 +56,7 @@ SYMBOLS = {
     "aq_leaf_eval_host_compact": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "aq_leaf_eval_host_compact_submit": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "aq_leaf_eval_host_compact_wait": (_i32, [_vp]),
+    "aq_leaf_eval_host_compact_layout": (_i32, [_i64, _vp]),
     "aq_host_ctx_stats": (_i32, [_vp, _vp]),
     "aq_mcts_ws_bytes": (_i64, [_i64, _i64]),
     "aq_mcts_reset": (_i32, [_vp, _vp, _i64, _i64, _vp]),

@@ -719,8 +719,18 @@ extern "C" int aq_compact_priors(const float *priors, const uint32_t *mask, cons
 
 // Host-buffer leaf evaluation with predict()-shaped output.  Device workspace: the dense workspace of
 // aq_leaf_eval_host followed by offsets int32[B + 1] and compact [B * 136] (4 bytes per entry reserved).
+static inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 extern "C" int64_t aq_leaf_eval_host_compact_ws_bytes(int64_t B) {
-    return aq_leaf_eval_host_ws_bytes(B) + (int64_t)align256((size_t)(B + 8) * 4) + (int64_t)align256((size_t)B * AQ_MAX_LEGAL * 4);
+    return aq_leaf_eval_host_ws_bytes(B) + (int64_t)align256(align16((size_t)(B + 1) * 4) + align16((size_t)B * 4) + (size_t)B * AQ_MAX_LEGAL * 4);
+}
+// The results of a batch form ONE block on the device: offsets int32[B+1] | value f32[B] | ragged priors, each part starting on a
+// 16-byte boundary.  A caller whose host buffers have the same layout -- value_host = offsets_host + out2[0] bytes, priors_host =
+// offsets_host + out2[1] bytes -- gets them with a single device -> host copy per batch instead of three.
+extern "C" int aq_leaf_eval_host_compact_layout(int64_t B, int64_t *out2) {
+    if (B < 0 || !out2) return aq_set_error(AQ_ERR_ARG, "aq_leaf_eval_host_compact_layout");
+    out2[0] = (int64_t)align16((size_t)(B + 1) * 4);
+    out2[1] = out2[0] + (int64_t)align16((size_t)B * 4);
+    return 0;
 }
 
 // The call is split in two so that a caller can keep several batches in flight (one context, workspace and set of host buffers per
@@ -751,12 +761,16 @@ extern "C" int aq_leaf_eval_host_compact_submit(const float *params, const void 
     unsigned char *p = reinterpret_cast<unsigned char *>(dev_ws);
     AqState *d_states = reinterpret_cast<AqState *>(p); p += align256((size_t)B * sizeof(AqState));
     float *d_priors = reinterpret_cast<float *>(p);     p += align256((size_t)B * kP * 4);
-    float *d_value = reinterpret_cast<float *>(p);      p += align256((size_t)B * 4);
+    p += align256((size_t)B * 4);                       // (the dense path's value array; unused here)
     uint32_t *d_mask = reinterpret_cast<uint32_t *>(p); p += align256((size_t)B * 32);
     uint8_t *d_pawn = reinterpret_cast<uint8_t *>(p);   p += align256((size_t)B * 8);
     unsigned char *d_leaf_ws = p;                       p += host_ws_region_bytes(B);
-    int32_t *d_offsets = reinterpret_cast<int32_t *>(p); p += align256((size_t)(B + 8) * 4);
-    pd.d_compact = p;
+    // the result block: offsets | value | ragged priors (aq_leaf_eval_host_compact_layout)
+    const size_t value_off = align16((size_t)(B + 1) * 4), priors_off = value_off + align16((size_t)B * 4);
+    unsigned char *d_block = p;
+    int32_t *d_offsets = reinterpret_cast<int32_t *>(d_block);
+    float *d_value = reinterpret_cast<float *>(d_block + value_off);
+    pd.d_compact = d_block + priors_off;
 
     cudaStream_t cs = ctx->s[0];
     cudaError_t e = cudaEventRecord(ctx->ready, pd.origin);
@@ -773,11 +787,17 @@ extern "C" int aq_leaf_eval_host_compact_submit(const float *params, const void 
     if (est > most) est = most;
     if (est > priors_capacity) est = priors_capacity;
     pd.copied = est;
-    e = cudaMemcpyAsync(offsets_host, d_offsets, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost, cs);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(value_host, d_value, (size_t)B * 4, cudaMemcpyDeviceToHost, cs);
+    const unsigned char *h0 = reinterpret_cast<const unsigned char *>(offsets_host);
+    if (reinterpret_cast<const unsigned char *>(value_host) == h0 + value_off && reinterpret_cast<const unsigned char *>(priors_host) == h0 + priors_off) {
+        // the host buffers mirror the device block: one copy for offsets, values and the estimated part of the priors
+        e = cudaMemcpyAsync(offsets_host, d_block, priors_off + (size_t)est * pd.elem, cudaMemcpyDeviceToHost, cs);
+    } else {
+        e = cudaMemcpyAsync(offsets_host, d_offsets, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(value_host, d_value, (size_t)B * 4, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess && est > 0) e = cudaMemcpyAsync(priors_host, pd.d_compact, (size_t)est * pd.elem, cudaMemcpyDeviceToHost, cs);
+    }
     if (e == cudaSuccess && mask_host) e = cudaMemcpyAsync(mask_host, d_mask, (size_t)B * 32, cudaMemcpyDeviceToHost, cs);
     if (e == cudaSuccess && pawn_host) e = cudaMemcpyAsync(pawn_host, d_pawn, (size_t)B * 8, cudaMemcpyDeviceToHost, cs);
-    if (e == cudaSuccess && est > 0) e = cudaMemcpyAsync(priors_host, pd.d_compact, (size_t)est * pd.elem, cudaMemcpyDeviceToHost, cs);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->chunk_done[0], cs);
     if (e != cudaSuccess) { pd.active = false; return aq_set_error((int)e, "aq_leaf_eval_host_compact(D2H)"); }
     return 0;

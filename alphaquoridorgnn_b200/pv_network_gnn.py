@@ -371,8 +371,14 @@ class HostLeafEvaluator:
             self.offsets = None
             nbytes = L.aq_leaf_eval_host_ws_bytes(B)
         else:
-            self.priors = torch.empty((B * gl.MAX_LEGAL,), dtype=torch.float16 if wire == "f16" else torch.float32).pin_memory()
-            self.offsets = torch.empty((B + 1,), dtype=torch.int32).pin_memory()
+            # one pinned block laid out like the device's result block (offsets | value | ragged priors): one D2H copy per batch
+            lay = (ctypes.c_int64 * 2)()
+            _lib.check(L.aq_leaf_eval_host_compact_layout(B, lay), "aq_leaf_eval_host_compact_layout")
+            elem = 2 if wire == "f16" else 4
+            self._block = torch.empty((lay[1] + B * gl.MAX_LEGAL * elem,), dtype=torch.uint8).pin_memory()
+            self.offsets = self._block[: (B + 1) * 4].view(torch.int32)
+            self.value = self._block[lay[0]: lay[0] + B * 4].view(torch.float32)
+            self.priors = self._block[lay[1]:].view(torch.float16 if wire == "f16" else torch.float32)
             nbytes = L.aq_leaf_eval_host_compact_ws_bytes(B)
         self.ws = torch.empty((max(1, nbytes),), dtype=torch.uint8, device=self.dev)
         self._ctx = ctypes.c_void_p()

@@ -53,7 +53,7 @@ typedef struct AqState {
     uint64_t reserved; /* reserved, 0 */
 } AqState;
 
-#define AQ_VERSION 202 /* bumped with every change of a signature below; the ctypes loader refuses a library of another version */
+#define AQ_VERSION 203 /* bumped with every change of a signature below; the ctypes loader refuses a library of another version */
 int aq_version(void);
 const char *aq_last_error_string(void);
 /* Number of kernels this library has launched in the process so far (monotonic; kernels replayed through a CUDA graph the caller
@@ -238,6 +238,9 @@ int aq_leaf_eval_host_compact_submit(const float *params, const void *prepared, 
                                      void *host_ctx, void *stream);
 int aq_leaf_eval_host_compact_wait(void *host_ctx);
 int64_t aq_leaf_eval_host_compact_ws_bytes(int64_t B);
+/* Optional: host buffers laid out as ONE block -- value_host = (char *)offsets_host + out2[0], priors_host = (char *)offsets_host +
+ * out2[1] -- are filled by a single device -> host copy per batch (the device keeps its results in the same layout). */
+int aq_leaf_eval_host_compact_layout(int64_t B, int64_t *out2);
 int aq_leaf_eval_host_compact(const float *params, const void *prepared /* or NULL */, const AqState *states_host, int64_t B,
                               void *priors_host, int64_t priors_capacity, int32_t *offsets_host, float *value_host,
                               uint32_t *mask_host, uint8_t *pawn_host, void *dev_ws, int precision, int wire, void *host_ctx,

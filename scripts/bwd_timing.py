@@ -1,10 +1,12 @@
 """Per-phase cycle accounting of gcn_backward_tc2_kernel (debug variant built with -DTC2B_TIMING=1):
-python scripts/build_variant.py bwdt gnn_tc2_bwd.cu -DTC2B_TIMING=1
-AQ_LIB_PATH=alphaquoridorgnn_b200/variants/libaqgnn_bwdt.so python scripts/bwd_timing.py"""
+python scripts/build_debug_lib.py timing <source>.cu -D...=1;  python scripts/bwd_timing.py alphaquoridorgnn_b200/debug/libaqgnn_timing.so"""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from alphaquoridorgnn_b200 import _lib, positions
+import alphaquoridorgnn_b200.build as _b
+_lib.LIB_PATH = os.path.abspath(sys.argv[1])   # the debug copy, loaded explicitly
+_b.needs_build = lambda: False
 from alphaquoridorgnn_b200.pv_network_gnn import GNNNetwork
 TB = 4096
 L = _lib.load(); P = _lib.ptr
