@@ -32,25 +32,30 @@ struct BwdWs {
 // heads backward: one warp per board
 // ------------------------------------------------------------------------------------------
 constexpr int kHbThreads = 512;  // at most 16 warps = 16 boards in flight per CTA (launched with 8 warps for small batches, where the weight fill dominates)
+// kNB boards per warp at a time: the three contractions of a board are bound by shared-memory reads of the weights (one LDS per
+// FMA when a warp owns one board); with kNB boards every weight value read feeds kNB FMAs.  kNB is chosen by the batch size so that
+// the warps of the machine still get one group each (1 up to 2,367 boards, 2 up to 8,191, 4 above).
+template <int kNB>
 struct HeadBwdSmem {
     float wp2[kP * kHH];  // [a][j]
     float wp0[kHH * kH];  // [j][k]
     float wv0[kHH * kH];
     float wv2[kHH];
-    float dz[kHbThreads / 32][224];
-    float dh[kHbThreads / 32][2 * kHH];  // dhp | dhv
+    float dz[kHbThreads / 32][kNB][224];
+    float dh[kHbThreads / 32][kNB][2 * kHH];  // dhp | dhv
 };
+static_assert(sizeof(HeadBwdSmem<4>) <= 227 * 1024, "HeadBwdSmem too large");
 
 // kLoss: the loss gradient of train_network.py:54-55,85-89 (loss_grad_kernel below, same expressions in the same order) is computed
 // here from the saved network outputs and the targets instead of being read from dpolicy / dvalue: one launch and one
 // [B,209] round trip less per training step.
-template <bool kLoss>
+template <bool kLoss, int kNB>
 __global__ void __launch_bounds__(kHbThreads, 1)
 heads_backward_kernel(const float *__restrict__ params, const float *saved,   // saved: written by the kernel this one may overlap -- no __restrict__ (PDL rule)
                       const float *dpolicy, const float *dvalue, const float *__restrict__ ptarget, const float *__restrict__ vtarget,
                       float inv_total, float *__restrict__ loss, int64_t B, float *__restrict__ ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    HeadBwdSmem &sm = *reinterpret_cast<HeadBwdSmem *>(smem_raw);
+    HeadBwdSmem<kNB> &sm = *reinterpret_cast<HeadBwdSmem<kNB> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     aq_pdl_trigger();  // the trunk backward may be scheduled as SMs free up; it waits for this grid before it reads dg
     // 116 KB of head weights per CTA: 16-byte loads where the parameter offset allows it, 8 loads in flight per thread
@@ -70,111 +75,150 @@ heads_backward_kernel(const float *__restrict__ params, const float *saved,   //
     const BwdWs W{B};
     const int nwarps = (int)blockDim.x >> 5;
     float loss_p = 0.f, loss_v = 0.f;
-    for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
+    for (int64_t b0 = ((int64_t)blockIdx.x * nwarps + warp) * kNB; b0 < B; b0 += (int64_t)gridDim.x * nwarps * kNB) {
         __syncwarp();
-        // softmax backward: dz = p * (dp - sum_j dp_j p_j)
-        float p[7], dp[7], s = 0.f;
-        float dval;
-        if (kLoss) {
-            // CrossEntropyLoss(input = softmax probabilities, target = probabilities): -sum_a t_a log_softmax(p)_a -- the second
-            // softmax is the reference's behaviour -- and MSELoss, both 'mean' over the global batch
-            float tg[7], mx = -INFINITY;
+        float du_[kNB];
+        // ---- per board: loss gradient (or the given one), softmax backward dz = p * (dp - sum_j dp_j p_j) -> shared memory ----
 #pragma unroll
-            for (int t = 0; t < 7; ++t) {
-                const int a = lane + 32 * t;
-                p[t] = a < kP ? __ldcg(saved + L.policy() + b * kP + a) : -INFINITY;
-                tg[t] = a < kP ? __ldg(ptarget + b * kP + a) : 0.f;
-                mx = fmaxf(mx, p[t]);
+        for (int nb = 0; nb < kNB; ++nb) {
+            const int64_t b = b0 + nb;
+            du_[nb] = 0.f;
+            if (b >= B) {   // a group's tail: zero rows contribute nothing to the blocked contractions below
+#pragma unroll
+                for (int t = 0; t < 7; ++t) sm.dz[warp][nb][lane + 32 * t] = 0.f;
+                continue;
             }
+            float p[7], dp[7], s = 0.f;
+            float dval;
+            if (kLoss) {
+                // CrossEntropyLoss(input = softmax probabilities, target = probabilities): -sum_a t_a log_softmax(p)_a -- the second
+                // softmax is the reference's behaviour -- and MSELoss, both 'mean' over the global batch
+                float tg[7], mx = -INFINITY;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-            float se = 0.f, tsum = 0.f;
-#pragma unroll
-            for (int t = 0; t < 7; ++t) {
-                if (lane + 32 * t < kP) se += expf(p[t] - mx);
-                tsum += tg[t];
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                se += __shfl_xor_sync(0xffffffffu, se, d);
-                tsum += __shfl_xor_sync(0xffffffffu, tsum, d);
-            }
-            const float lse = mx + logf(se);
-            float l = 0.f;
-#pragma unroll
-            for (int t = 0; t < 7; ++t) {
-                if (lane + 32 * t < kP) {
-                    const float ls = p[t] - lse;
-                    l -= tg[t] * ls;
-                    dp[t] = (expf(ls) * tsum - tg[t]) * inv_total;
-                } else {
-                    p[t] = 0.f;
-                    dp[t] = 0.f;
+                for (int t = 0; t < 7; ++t) {
+                    const int a = lane + 32 * t;
+                    p[t] = a < kP ? __ldcg(saved + L.policy() + b * kP + a) : -INFINITY;
+                    tg[t] = a < kP ? __ldg(ptarget + b * kP + a) : 0.f;
+                    mx = fmaxf(mx, p[t]);
                 }
-                s = fmaf(dp[t], p[t], s);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+                float se = 0.f, tsum = 0.f;
+#pragma unroll
+                for (int t = 0; t < 7; ++t) {
+                    if (lane + 32 * t < kP) se += expf(p[t] - mx);
+                    tsum += tg[t];
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    se += __shfl_xor_sync(0xffffffffu, se, d);
+                    tsum += __shfl_xor_sync(0xffffffffu, tsum, d);
+                }
+                const float lse = mx + logf(se);
+                float l = 0.f;
+#pragma unroll
+                for (int t = 0; t < 7; ++t) {
+                    if (lane + 32 * t < kP) {
+                        const float ls = p[t] - lse;
+                        l -= tg[t] * ls;
+                        dp[t] = (expf(ls) * tsum - tg[t]) * inv_total;
+                    } else {
+                        p[t] = 0.f;
+                        dp[t] = 0.f;
+                    }
+                    s = fmaf(dp[t], p[t], s);
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) l += __shfl_xor_sync(0xffffffffu, l, d);
+                const float dv0 = __ldcg(saved + L.value() + b) - __ldg(vtarget + b);
+                dval = 2.f * dv0 * inv_total;
+                loss_p += l;
+                loss_v += dv0 * dv0;
+            } else {
+#pragma unroll
+                for (int t = 0; t < 7; ++t) {
+                    const int a = lane + 32 * t;
+                    p[t] = a < kP ? saved[L.policy() + b * kP + a] : 0.f;
+                    dp[t] = a < kP ? __ldcg(dpolicy + b * kP + a) : 0.f;  // written by the loss kernel this grid may overlap: coherent load (PDL rule, aq_common.cuh)
+                    s = fmaf(dp[t], p[t], s);
+                }
+                dval = __ldcg(dvalue + b);
             }
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) l += __shfl_xor_sync(0xffffffffu, l, d);
-            const float dv0 = __ldcg(saved + L.value() + b) - __ldg(vtarget + b);
-            dval = 2.f * dv0 * inv_total;
-            loss_p += l;
-            loss_v += dv0 * dv0;
-        } else {
+            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
 #pragma unroll
             for (int t = 0; t < 7; ++t) {
                 const int a = lane + 32 * t;
-                p[t] = a < kP ? saved[L.policy() + b * kP + a] : 0.f;
-                dp[t] = a < kP ? __ldcg(dpolicy + b * kP + a) : 0.f;  // written by the loss kernel this grid may overlap: coherent load (PDL rule, aq_common.cuh)
-                s = fmaf(dp[t], p[t], s);
+                const float dz = p[t] * (dp[t] - s);
+                sm.dz[warp][nb][a] = dz;
+                if (a < kP) ws[W.dz() + b * kP + a] = dz;
             }
-            dval = __ldcg(dvalue + b);
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-#pragma unroll
-        for (int t = 0; t < 7; ++t) {
-            const int a = lane + 32 * t;
-            const float dz = p[t] * (dp[t] - s);
-            sm.dz[warp][a] = dz;
-            if (a < kP) ws[W.dz() + b * kP + a] = dz;
+            // value head: v = tanh(u); du = dv * (1 - v^2)
+            const float v = saved[L.value() + b];
+            du_[nb] = dval * (1.f - v * v);
         }
         __syncwarp();
-        // dhp = (Wp2^T dz) * (hp > 0); outputs j = lane, lane+32
-        float h0 = 0.f, h1 = 0.f;
+        // ---- dhp = (Wp2^T dz) * (hp > 0) for the kNB boards at once; outputs j = lane, lane+32 ----
+        float h0[kNB], h1[kNB];
+#pragma unroll
+        for (int nb = 0; nb < kNB; ++nb) h0[nb] = h1[nb] = 0.f;
 #pragma unroll 4
         for (int a = 0; a < kP; ++a) {
-            const float dz = sm.dz[warp][a];
-            h0 = fmaf(dz, sm.wp2[a * kHH + lane], h0);
-            h1 = fmaf(dz, sm.wp2[a * kHH + lane + 32], h1);
-        }
-        const float hp0 = saved[L.hp() + b * kHH + lane], hp1 = saved[L.hp() + b * kHH + lane + 32];
-        h0 = hp0 > 0.f ? h0 : 0.f;
-        h1 = hp1 > 0.f ? h1 : 0.f;
-        // value head: v = tanh(u); du = dv * (1 - v^2); dhv = du * wv2 * (hv > 0)
-        const float v = saved[L.value() + b];
-        const float du = dval * (1.f - v * v);
-        const float hv0 = saved[L.hv() + b * kHH + lane], hv1 = saved[L.hv() + b * kHH + lane + 32];
-        const float g0 = hv0 > 0.f ? du * sm.wv2[lane] : 0.f;
-        const float g1 = hv1 > 0.f ? du * sm.wv2[lane + 32] : 0.f;
-        sm.dh[warp][lane] = h0; sm.dh[warp][lane + 32] = h1;
-        sm.dh[warp][kHH + lane] = g0; sm.dh[warp][kHH + lane + 32] = g1;
-        ws[W.dhp() + b * kHH + lane] = h0; ws[W.dhp() + b * kHH + lane + 32] = h1;
-        ws[W.dhv() + b * kHH + lane] = g0; ws[W.dhv() + b * kHH + lane + 32] = g1;
-        if (lane == 0) ws[W.du() + b] = du;
-        __syncwarp();
-        // dg = Wp0^T dhp + Wv0^T dhv ; outputs k = lane + 32 t
-        float dg[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-        for (int j = 0; j < kHH; ++j) {
-            const float a = sm.dh[warp][j], c = sm.dh[warp][kHH + j];
+            const float w0 = sm.wp2[a * kHH + lane], w1 = sm.wp2[a * kHH + lane + 32];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                dg[t] = fmaf(a, sm.wp0[j * kH + lane + 32 * t], dg[t]);
-                dg[t] = fmaf(c, sm.wv0[j * kH + lane + 32 * t], dg[t]);
+            for (int nb = 0; nb < kNB; ++nb) {
+                const float dz = sm.dz[warp][nb][a];
+                h0[nb] = fmaf(dz, w0, h0[nb]);
+                h1[nb] = fmaf(dz, w1, h1[nb]);
             }
         }
 #pragma unroll
-        for (int t = 0; t < 4; ++t) ws[W.dg() + b * kH + lane + 32 * t] = dg[t];
+        for (int nb = 0; nb < kNB; ++nb) {
+            const int64_t b = b0 + nb;
+            float a0 = 0.f, a1 = 0.f, g0 = 0.f, g1 = 0.f;
+            if (b < B) {
+                const float hp0 = saved[L.hp() + b * kHH + lane], hp1 = saved[L.hp() + b * kHH + lane + 32];
+                a0 = hp0 > 0.f ? h0[nb] : 0.f;
+                a1 = hp1 > 0.f ? h1[nb] : 0.f;
+                // dhv = du * wv2 * (hv > 0)
+                const float hv0 = saved[L.hv() + b * kHH + lane], hv1 = saved[L.hv() + b * kHH + lane + 32];
+                g0 = hv0 > 0.f ? du_[nb] * sm.wv2[lane] : 0.f;
+                g1 = hv1 > 0.f ? du_[nb] * sm.wv2[lane + 32] : 0.f;
+                ws[W.dhp() + b * kHH + lane] = a0; ws[W.dhp() + b * kHH + lane + 32] = a1;
+                ws[W.dhv() + b * kHH + lane] = g0; ws[W.dhv() + b * kHH + lane + 32] = g1;
+                if (lane == 0) ws[W.du() + b] = du_[nb];
+            }
+            sm.dh[warp][nb][lane] = a0; sm.dh[warp][nb][lane + 32] = a1;
+            sm.dh[warp][nb][kHH + lane] = g0; sm.dh[warp][nb][kHH + lane + 32] = g1;
+        }
+        __syncwarp();
+        // ---- dg = Wp0^T dhp + Wv0^T dhv for the kNB boards at once; outputs k = lane + 32 t ----
+        float dg[kNB][4];
+#pragma unroll
+        for (int nb = 0; nb < kNB; ++nb)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) dg[nb][t] = 0.f;
+#pragma unroll 2
+        for (int j = 0; j < kHH; ++j) {
+            float wa[4], wc[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { wa[t] = sm.wp0[j * kH + lane + 32 * t]; wc[t] = sm.wv0[j * kH + lane + 32 * t]; }
+#pragma unroll
+            for (int nb = 0; nb < kNB; ++nb) {
+                const float a = sm.dh[warp][nb][j], c = sm.dh[warp][nb][kHH + j];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    dg[nb][t] = fmaf(a, wa[t], dg[nb][t]);
+                    dg[nb][t] = fmaf(c, wc[t], dg[nb][t]);
+                }
+            }
+        }
+#pragma unroll
+        for (int nb = 0; nb < kNB; ++nb)
+            if (b0 + nb < B) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) ws[W.dg() + (b0 + nb) * kH + lane + 32 * t] = dg[nb][t];
+            }
     }
     if (kLoss && loss) {  // monitoring scalars: one pair of atomics per CTA
         __shared__ float red[2][kHbThreads / 32];
@@ -523,7 +567,10 @@ int aq_gcn_backward_tc2(const float *params, float *saved, const float *dg, int6
 int aq_dp_adam_launch(void *comm, const float *grads_in, const float *partial, int gcn_slots, int head_slots, float *params, float *exp_avg,
                       float *exp_avg_sq, float *grads_out, float lr, float beta1, float beta2, float eps, bool pdl, cudaStream_t st);  // dp_comm.cu
 
-static inline int head_slot_count(int64_t B) { return (int)std::min<int64_t>(kSlots, (B + 63) / 64); }  // one row chunk per 64 boards
+#ifndef AQ_HEAD_CHUNK_ROWS
+#define AQ_HEAD_CHUNK_ROWS 64
+#endif
+static inline int head_slot_count(int64_t B) { return (int)std::min<int64_t>(kSlots, (B + AQ_HEAD_CHUNK_ROWS - 1) / AQ_HEAD_CHUNK_ROWS); }  // one row chunk per 64 boards
 
 // The backward kernels up to the partial-gradient slots.  Loss gradient either given (dpolicy, dvalue) or computed in the heads
 // backward from the targets (ptarget, vtarget, B_total, loss).
@@ -534,9 +581,6 @@ static int backward_to_partials(const float *params, const float *saved, const f
     const BwdWs W{B};
     const bool fused_loss = ptarget != nullptr;
     cudaError_t e;
-    e = cudaFuncSetAttribute(heads_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadBwdSmem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(heads_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadBwdSmem));
-    if (e != cudaSuccess) return aq_set_error((int)e, "heads_backward smem");
     e = cudaFuncSetAttribute(gcn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GcnBwdSmem));
     if (e != cudaSuccess) return aq_set_error((int)e, "gcn_backward smem");
     if (fused_loss && loss) {
@@ -544,16 +588,27 @@ static int backward_to_partials(const float *params, const float *saved, const f
         if (e != cudaSuccess) return aq_set_error((int)e, "aq_loss_backward(memset)");
     }
     const int hb_threads = B <= 1184 ? 256 : kHbThreads;  // 148 CTAs x 8 boards cover 1,184 boards in one pass
-    const int64_t hb = (B + hb_threads / 32 - 1) / (hb_threads / 32);
+    const int nb = B >= 8192 ? 4 : B >= kSlots * (kHbThreads / 32) ? 2 : 1;   // boards per warp at a time (HeadBwdSmem)
+    const int64_t per_cta = (int64_t)(hb_threads / 32) * nb;
+    const int64_t hb = (B + per_cta - 1) / per_cta;
     const dim3 hgrid((unsigned)(hb < kSlots ? hb : kSlots));
     const float inv_total = 1.0f / (float)(B_total > 0 ? B_total : B);
     // the backward kernels are chained by programmatic dependent launches: each reads only the parameters before its aq_pdl_wait()
-    if (fused_loss)
-        e = aq_launch_pdl(heads_backward_kernel<true>, hgrid, dim3(hb_threads), sizeof(HeadBwdSmem), st, params, saved, dpolicy, dvalue, ptarget,
-                          vtarget, inv_total, loss, B, workspace);
-    else
-        e = aq_launch_pdl(heads_backward_kernel<false>, hgrid, dim3(hb_threads), sizeof(HeadBwdSmem), st, params, saved, dpolicy, dvalue, ptarget,
-                          vtarget, inv_total, loss, B, workspace);
+    auto launch_hb = [&](auto kernel, size_t smem) -> cudaError_t {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        return aq_launch_pdl(kernel, hgrid, dim3(hb_threads), smem, st, params, saved, dpolicy, dvalue, ptarget, vtarget, inv_total, loss, B,
+                             workspace);
+    };
+    if (fused_loss) {
+        if (nb == 4) e = launch_hb(heads_backward_kernel<true, 4>, sizeof(HeadBwdSmem<4>));
+        else if (nb == 2) e = launch_hb(heads_backward_kernel<true, 2>, sizeof(HeadBwdSmem<2>));
+        else e = launch_hb(heads_backward_kernel<true, 1>, sizeof(HeadBwdSmem<1>));
+    } else {
+        if (nb == 4) e = launch_hb(heads_backward_kernel<false, 4>, sizeof(HeadBwdSmem<4>));
+        else if (nb == 2) e = launch_hb(heads_backward_kernel<false, 2>, sizeof(HeadBwdSmem<2>));
+        else e = launch_hb(heads_backward_kernel<false, 1>, sizeof(HeadBwdSmem<1>));
+    }
     if (e != cudaSuccess) return aq_set_error((int)e, "heads_backward_kernel(launch)");
     int rc = aq_check_launch("heads_backward_kernel");
     if (rc) return rc;
