@@ -227,6 +227,145 @@ __global__ void mcts_root_counts_kernel(const MctsGame *__restrict__ games, cons
 }
 
 // ------------------------------------------------------------------------------------------
+// One ply of G lock-step self-play games after their searches (reference self_play.py:47-60): for every game
+//   scores = counts ** (1 / temperature) / sum  (pv_mcts.py:88-95; temperature 0 = one-hot on the FIRST maximum, np.argmax)
+//   policy[action] = score for the legal actions, 0 elsewhere, over all 209 actions  (self_play.py:51-54)
+//   action = one draw from `scores` (self_play.py:57, np.random.choice(legal_actions, p=scores)): inverse CDF in
+//            legal_actions() order of a counter-based uniform -- a hash of (seed, game id, ply), so a game's moves do not
+//            depend on which other games are still running
+//   state  = state.next(action) (self_play.py:60), with its terminal flags.
+// One warp per game; child c of the root lives in lane c % 32, slot c / 32.
+// ------------------------------------------------------------------------------------------
+constexpr int kChildSlots = (AQ_MAX_LEGAL + 31) / 32;
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+selfplay_move_kernel(const AqState *__restrict__ states, const int32_t *__restrict__ counts, const int16_t *__restrict__ actions,
+                     const int16_t *__restrict__ n_children, const int64_t *__restrict__ game_id, int64_t G, double inv_t, int greedy,
+                     uint64_t seed, int ply, T *__restrict__ policy, int16_t *__restrict__ chosen, AqState *__restrict__ moved,
+                     uint8_t *__restrict__ term) {
+    __shared__ T rows[4][AQ_ACTIONS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t g = (int64_t)blockIdx.x * 4 + w;
+    if (g >= G) return;
+    const int n = n_children[g];
+    double x[kChildSlots];
+    int act[kChildSlots];
+    long long best = -1;
+#pragma unroll
+    for (int k = 0; k < kChildSlots; ++k) {
+        const int c = lane + 32 * k;
+        const int cnt = c < n ? counts[g * AQ_MAX_LEGAL + c] : 0;
+        act[k] = c < n ? (int)actions[g * AQ_MAX_LEGAL + c] : -1;
+        x[k] = inv_t == 1.0 ? (double)cnt : (cnt > 0 ? pow((double)cnt, inv_t) : 0.0);
+        if (c < n) best = max(best, ((long long)cnt << 8) | (long long)(255 - c));   // largest count, then smallest index
+    }
+    if (greedy) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
+        const int arg = 255 - (int)(best & 255);
+#pragma unroll
+        for (int k = 0; k < kChildSlots; ++k) x[k] = (lane + 32 * k == arg && n > 0) ? 1.0 : 0.0;
+    }
+    // running sums in child order: a warp scan per slot on top of the slots before it (fixed order: deterministic)
+    double cum[kChildSlots], base = 0.0;
+#pragma unroll
+    for (int k = 0; k < kChildSlots; ++k) {
+        double v = x[k];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += up;
+        }
+        cum[k] = base + v;
+        base = __shfl_sync(0xffffffffu, cum[k], 31);
+    }
+    const double total = base;
+    const uint64_t bits = mix64(mix64(seed + 0x9E3779B97F4A7C15ull * (uint64_t)(game_id[g] + 1)) + 0xD1B54A32D192ED03ull * (uint64_t)(ply + 1));
+    const double target = (double)(bits >> 11) * (1.0 / 9007199254740992.0) * total;   // u in [0, 1) times the sum
+    int pick = -1, last = -1;
+#pragma unroll
+    for (int k = 0; k < kChildSlots; ++k) {
+        const unsigned over = __ballot_sync(0xffffffffu, x[k] > 0.0 && target < cum[k]);
+        const unsigned any = __ballot_sync(0xffffffffu, x[k] > 0.0);
+        if (pick < 0 && over) pick = 32 * k + __ffs(over) - 1;
+        if (any) last = 32 * k + 31 - __clz(any);
+    }
+    if (pick < 0) pick = last;   // target == total after rounding: the last child with a positive score
+    int a = -1;
+#pragma unroll
+    for (int k = 0; k < kChildSlots; ++k) {
+        const int v = __shfl_sync(0xffffffffu, act[k], pick & 31);
+        if ((pick >> 5) == k) a = v;
+    }
+    // dense policy row, staged so that the global stores are consecutive
+    T *row = rows[w];
+    for (int i = lane; i < AQ_ACTIONS; i += 32) row[i] = (T)0;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kChildSlots; ++k)
+        if (act[k] >= 0) row[act[k]] = (T)(total > 0.0 ? x[k] / total : 0.0);   // x / sum(xs), pv_mcts.py:94
+    __syncwarp();
+    for (int i = lane; i < AQ_ACTIONS; i += 32) policy[g * AQ_ACTIONS + i] = row[i];
+    if (lane == 0) {
+        AqState t = load_state(states + g);
+        int flags = 2;   // a root without children cannot move: reported as a draw (does not happen for non-terminal roots)
+        if (pick >= 0) {
+            t = state_after(t, a);
+            flags = terminal_flags(t);
+        }
+        store_state(moved + g, t);
+        term[g] = (uint8_t)flags;
+        if (chosen) chosen[g] = (int16_t)a;
+    }
+}
+
+// Survivors keep their order (games that ended leave; self_play.py:45 `while not state.is_done()`); one CTA, a block scan per
+// 1,024 games.  For a game that ended: final_flags[game] = terminal flags of its last state, final_plies[game] = its length.
+__global__ void __launch_bounds__(1024)
+selfplay_compact_kernel(const AqState *__restrict__ moved, const uint8_t *__restrict__ term, const int64_t *__restrict__ game_id,
+                        int64_t G, int ply, AqState *__restrict__ next_states, int64_t *__restrict__ next_game_id,
+                        uint8_t *__restrict__ final_flags, int64_t *__restrict__ final_plies, int32_t *__restrict__ alive_count) {
+    __shared__ int warp_total[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int base = 0;
+    for (int64_t start = 0; start < G; start += 1024) {
+        const int64_t i = start + threadIdx.x;
+        const int flags = i < G ? (int)term[i] : 1;
+        const bool alive = i < G && flags == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) warp_total[w] = __popc(m);
+        __syncthreads();
+        int before = 0, all = 0;
+        for (int v = 0; v < 32; ++v) {
+            const int t = warp_total[v];
+            before += v < w ? t : 0;
+            all += t;
+        }
+        if (i < G) {
+            const int64_t id = game_id[i];
+            if (alive) {
+                const int64_t o = base + before + __popc(m & ((1u << lane) - 1u));
+                store_state(next_states + o, load_state(moved + i));
+                next_game_id[o] = id;
+            } else {
+                final_flags[id] = (uint8_t)flags;
+                final_plies[id] = ply + 1;
+            }
+        }
+        base += all;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *alive_count = base;
+}
+
+// ------------------------------------------------------------------------------------------
 extern "C" int64_t aq_mcts_ws_bytes(int64_t G, int64_t max_nodes) {
     return (int64_t)(mcts_nodes_offset(G) + (size_t)G * (size_t)max_nodes * kNodeBytes);
 }
@@ -274,4 +413,33 @@ extern "C" int aq_mcts_root_counts(void *ws, int64_t G, int64_t max_nodes, int32
     mcts_root_counts_kernel<<<(unsigned)((G + 3) / 4), 128, 0, st>>>(games_of(ws), hot_of(ws, G), cold_of(ws, G, max_nodes), G, max_nodes, counts,
                                                                      actions, n_children, overflow);
     return aq_check_launch("aq_mcts_root_counts");
+}
+
+extern "C" int64_t aq_selfplay_ws_bytes(int64_t G) {
+    return (int64_t)(((size_t)(G > 0 ? G : 0) * sizeof(AqState) + 255) & ~(size_t)255) + (G > 0 ? G : 0);
+}
+
+extern "C" int aq_selfplay_advance(const AqState *states, const int32_t *counts, const int16_t *actions, const int16_t *n_children,
+                                   const int64_t *game_id, int64_t G, double temperature, uint64_t seed, int32_t ply, void *policy,
+                                   int policy_f64, int16_t *chosen, AqState *next_states, int64_t *next_game_id, uint8_t *final_flags,
+                                   int64_t *final_plies, int32_t *alive_count, void *workspace, void *stream) {
+    if (G <= 0 || !states || !counts || !actions || !n_children || !game_id || !policy || !next_states || !next_game_id || !final_flags ||
+        !final_plies || !alive_count || !workspace || !(temperature >= 0.0))
+        return aq_set_error(AQ_ERR_ARG, "aq_selfplay_advance");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    AqState *moved = reinterpret_cast<AqState *>(workspace);
+    uint8_t *term = reinterpret_cast<uint8_t *>(workspace) + (((size_t)G * sizeof(AqState) + 255) & ~(size_t)255);
+    const int greedy = temperature == 0.0;
+    const double inv_t = greedy ? 1.0 : 1.0 / temperature;
+    const unsigned grid = (unsigned)((G + 3) / 4);
+    if (policy_f64)
+        selfplay_move_kernel<double><<<grid, 128, 0, st>>>(states, counts, actions, n_children, game_id, G, inv_t, greedy, seed, ply,
+                                                          reinterpret_cast<double *>(policy), chosen, moved, term);
+    else
+        selfplay_move_kernel<float><<<grid, 128, 0, st>>>(states, counts, actions, n_children, game_id, G, inv_t, greedy, seed, ply,
+                                                         reinterpret_cast<float *>(policy), chosen, moved, term);
+    int rc = aq_check_launch("aq_selfplay_advance(move)");
+    if (rc) return rc;
+    selfplay_compact_kernel<<<1, 1024, 0, st>>>(moved, term, game_id, G, ply, next_states, next_game_id, final_flags, final_plies, alive_count);
+    return aq_check_launch("aq_selfplay_advance(compact)");
 }

@@ -38,7 +38,7 @@ def play_matches(model0, model1, num_games=EN_GAME_COUNT, temperature=EN_TEMPERA
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
     sims = sims or pv_mcts.PV_EVALUATE_COUNT
-    searchers = [pv_mcts.BatchedMCTS(m, sims, device=dev) for m in (model0, model1)]
+    searchers = [pv_mcts.searcher_for(m, sims, dev) for m in (model0, model1)]
     states = start_states(num_games, dev)
     gid = torch.arange(num_games, device=dev)
     points = torch.zeros(num_games, dtype=torch.float64, device=dev)  # points of the FIRST player of each game

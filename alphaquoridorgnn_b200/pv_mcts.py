@@ -18,6 +18,7 @@ from . import game_logic as gl
 PV_EVALUATE_COUNT = 50  # Number of simulations per inference (pv_mcts.py:18)
 C_PUCT = 1.25           # pv_mcts.py:71
 MAX_CHILDREN = 133      # 5 pawn moves + 128 wall placements
+GRAPH_CHUNK = 25        # simulations per launch of the chunk graph (BatchedMCTS.search)
 
 
 def network_evaluator(model):
@@ -78,11 +79,27 @@ class BatchedMCTS:
         _lib.check(L.aq_mcts_expand_backup(P(ws), G, max_nodes, P(buf["priors"]), P(buf["value"]), P(buf["mask"]),
                                            P(buf["pawn"]), st), "aq_mcts_expand_backup")
 
+    def _capture(self, enqueue):
+        """Capture enqueue(stream pointer) into a CUDA graph.  `torch.cuda.graph` is not used on purpose: on entry it empties the
+        caching allocator (the 3.5 GB workspace of a finished searcher goes back to the driver and the next one pays cudaMalloc
+        again) -- 50-350 ms per capture on the boxes measured, and self-play captures once per batch size."""
+        dev = self.device
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            g.capture_begin(capture_error_mode="thread_local")
+            try:
+                enqueue(_lib.stream_ptr(dev))
+            finally:
+                g.capture_end()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        return g
+
     @torch.no_grad()
-    def search(self, roots, sims=None):
-        """roots: packed uint8[G,32] (non-terminal states).  Runs `sims` simulations per game
-        (pv_mcts.py:84) and returns (counts int32[G,136], actions int16[G,136], n_children int16[G]):
-        visit counts of the root's children in State.legal_actions() order (pv_mcts.py:88)."""
+    def search_async(self, roots, sims=None):
+        """search() without the synchronisation: returns (counts, actions, n_children, status int32[2] on the device); the caller
+        passes status.tolist() to check_status() when it synchronises anyway."""
         sims = sims or self.sims or PV_EVALUATE_COUNT
         L, P = _lib.load(), _lib.ptr
         dev = self.device
@@ -90,7 +107,7 @@ class BatchedMCTS:
         G_real = roots.shape[0]
         if G_real == 0:
             return (torch.empty((0, gl.MAX_LEGAL), dtype=torch.int32, device=dev), torch.empty((0, gl.MAX_LEGAL), dtype=torch.int16, device=dev),
-                    torch.empty((0,), dtype=torch.int16, device=dev))
+                    torch.empty((0,), dtype=torch.int16, device=dev), torch.zeros((2,), dtype=torch.int32, device=dev))
         # Self-play and the arena drop finished games, so the number of roots shrinks by a few almost every ply.  Batches above 256
         # are padded to the next multiple of 256 with copies of the last root (searched and discarded; games are independent, so the
         # real ones are unaffected): workspaces, buffers and the captured CUDA graph of the simulation step are then reused across
@@ -112,31 +129,37 @@ class BatchedMCTS:
                 # bf16 operand tiles, refreshed in place if the parameters changed since the last search
                 prep = self.model.prepared_weights() if prec == 1 else None
                 key = (G, max_nodes, flat.data_ptr(), prep.data_ptr() if prep is not None else 0, prec)
-                graph = self._graphs.get(key) if self.use_graph else None
+                graphs = self._graphs.get(key) if self.use_graph else None
                 done = 0
-                if self.use_graph and graph is None:
+                if self.use_graph and graphs is None:
                     # warm-up outside capture (= simulation 1); a failure here is a real error and propagates
                     self._step_network(ws, G, max_nodes, buf, flat, prep, prec, st)
                     done = 1
                     torch.cuda.synchronize(dev)
                     try:
-                        g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g):
-                            self._step_network(ws, G, max_nodes, buf, flat, prep, prec, _lib.stream_ptr(dev))
+                        # two graphs: one simulation, and GRAPH_CHUNK simulations back to back -- a search is then a handful of
+                        # graph launches instead of one per simulation (a launch costs the host 10-100 us depending on the box,
+                        # the step 80 us of GPU time at 4,096 games)
+                        graphs = tuple(self._capture(lambda cst, k=steps: [self._step_network(ws, G, max_nodes, buf, flat, prep, prec, cst)
+                                                                           for _ in range(k)]) for steps in (1, GRAPH_CHUNK))
                         if len(self._graphs) >= 32:
                             self._graphs.clear()
-                        self._graphs[key] = graph = g
+                        self._graphs[key] = graphs
                     except _lib.AqError:
                         raise
                     except Exception as e:  # capture unsupported: stay eager, but say so
                         import warnings
                         warnings.warn(f"CUDA-graph capture of the MCTS simulation step failed ({e!r}); running the step eagerly")
-                        self.use_graph, graph = False, None
+                        self.use_graph, graphs = False, None
                         torch.cuda.synchronize(dev)
-                for _ in range(sims - done):
-                    if graph is not None:
-                        graph.replay()
-                    else:
+                left = sims - done
+                if graphs is not None:
+                    for _ in range(left // GRAPH_CHUNK):
+                        graphs[1].replay()
+                    for _ in range(left % GRAPH_CHUNK):
+                        graphs[0].replay()
+                else:
+                    for _ in range(left):
                         self._step_network(ws, G, max_nodes, buf, flat, prep, prec, st)
             else:
                 for _ in range(sims):
@@ -151,13 +174,40 @@ class BatchedMCTS:
             _lib.check(L.aq_mcts_root_counts(P(ws), G, max_nodes, P(counts), P(actions), P(n), P(ovf), st),
                        "aq_mcts_root_counts")
             bad = torch.isnan(buf["value"]).any().to(torch.int32).reshape(1) if self.model is not None else torch.zeros_like(ovf)
-        status = torch.cat([ovf, bad]).tolist()   # one synchronisation for both flags
+        return counts[:G_real], actions[:G_real], n[:G_real], torch.cat([ovf, bad])
+
+    @staticmethod
+    def check_status(status):
+        """status: the two flags search_async returns, as host integers."""
         if status[0]:
             raise _lib.AqError("MCTS node arena overflow")
         if status[1]:
             raise _lib.AqError("the network returned NaN for a leaf: with precision 'bf16' that is how an activation beyond the fp16 range of the "
                                "aggregation operand is reported (gnn_tc2.cu); evaluate this network with precision 'fp32'")
-        return counts[:G_real], actions[:G_real], n[:G_real]
+
+    def search(self, roots, sims=None):
+        """roots: packed uint8[G,32] (non-terminal states).  Runs `sims` simulations per game
+        (pv_mcts.py:84) and returns (counts int32[G,136], actions int16[G,136], n_children int16[G]):
+        visit counts of the root's children in State.legal_actions() order (pv_mcts.py:88)."""
+        counts, actions, n, status = self.search_async(roots, sims)
+        self.check_status(status.tolist())   # one synchronisation for both flags
+        return counts, actions, n
+
+
+def searcher_for(evaluator, sims, device=None):
+    """The BatchedMCTS of a network for `sims` simulations, kept on the network object: its node arenas (3.5 GB at 4,096 games x
+    200 simulations), leaf buffers and captured graphs are reused by every later self-play / arena / policy call on that network
+    instead of being allocated and captured again.  Evaluators that are plain callables get a fresh searcher."""
+    dev = gl._dev(device)
+    if not hasattr(evaluator, "flat_parameters"):
+        return BatchedMCTS(evaluator, sims, device=dev)
+    cache = evaluator.__dict__.setdefault("_searchers", {})
+    key = (int(sims), str(dev))
+    if key not in cache:
+        if len(cache) >= 4:
+            cache.clear()
+        cache[key] = BatchedMCTS(evaluator, sims, device=dev)
+    return cache[key]
 
 
 def policy_from_counts(counts, temperature):
@@ -174,7 +224,7 @@ def policy_from_counts(counts, temperature):
 
 def pv_mcts_policy_batch(model, packed_roots, temperature, sims=None, device=None):
     """Batched pv_mcts_policy: -> (policy float64[G,136], actions int16[G,136], n_children int16[G])."""
-    mcts = BatchedMCTS(model, sims or PV_EVALUATE_COUNT, device=device)
+    mcts = searcher_for(model, sims or PV_EVALUATE_COUNT, device)
     counts, actions, n = mcts.search(packed_roots)
     return policy_from_counts(counts, temperature), actions, n
 

@@ -10,6 +10,7 @@ from datetime import datetime
 import numpy as np
 import torch
 
+from . import _lib
 from . import game_logic as gl
 from . import pv_mcts
 from .constants import PV_NETWORK_PATH
@@ -45,38 +46,54 @@ def play_batch_device(model, num_games, device=None, sims=None, temperature=SP_T
     """Execute `num_games` self-play games in lock-step (self_play.py:40-68 per game) and keep the record on the device:
     dict(states uint8[T,32] packed, policy [T,209] search policies over all actions (self_play.py:51-54), value f32[T]
     back-filled game results seen from the player to move (self_play.py:63-66), game int64[T], ply int64[T],
-    flags uint8[G] (bit 0 = the player to move at the end has lost, bit 1 = draw), plies int64[G], sims int = simulations run)."""
+    flags uint8[G] (bit 0 = the player to move at the end has lost, bit 1 = draw), plies int64[G], sims int = simulations run).
+
+    Per ply: one search (200 graph-replayed simulation steps in a handful of launches) and ONE library call,
+    aq_selfplay_advance -- search policy, its dense 209-wide record, the sampled move, the next states and the compaction of the
+    games still running -- then one synchronisation that reads the search's status flags and the number of survivors together.
+    A game's moves are drawn from a hash of (seed, game, ply): they do not depend on the other games of the batch."""
+    if policy_dtype not in (torch.float64, torch.float32):
+        raise ValueError("policy_dtype must be torch.float64 or torch.float32")
     dev = gl._dev(device)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(int(seed) if seed is not None else int(torch.seed() % (2 ** 31)))
+    L, P = _lib.load(), _lib.ptr
+    seed = (int(seed) if seed is not None else int(torch.seed())) & (2 ** 64 - 1)
     sims = sims or pv_mcts.PV_EVALUATE_COUNT
-    mcts = pv_mcts.BatchedMCTS(model, sims, device=dev)
+    mcts = pv_mcts.searcher_for(model, sims, dev)
     states = start_states(num_games, dev)
     game_id = torch.arange(num_games, device=dev)
-    rec_state, rec_policy, rec_game, rec_ply = [], [], [], []
-    final_flags = torch.zeros(num_games, dtype=torch.uint8, device=dev)
-    final_plies = torch.zeros(num_games, dtype=torch.int64, device=dev)
+    rec_state, rec_policy, rec_game, sizes = [], [], [], []
+    final_flags = torch.zeros(max(num_games, 1), dtype=torch.uint8, device=dev)
+    final_plies = torch.zeros(max(num_games, 1), dtype=torch.int64, device=dev)
+    ws = torch.empty((max(1, L.aq_selfplay_ws_bytes(num_games)),), dtype=torch.uint8, device=dev)
+    alive = torch.zeros((1,), dtype=torch.int32, device=dev)
     ply, sims_run = 0, 0
-    while states.shape[0] > 0 and (max_plies is None or ply < max_plies):
-        counts, actions, n = mcts.search(states)
-        sims_run += states.shape[0] * sims
-        pol = pv_mcts.policy_from_counts(counts, temperature)            # [G,136] over legal actions
-        dense = torch.zeros((states.shape[0], POLICY_OUTPUT_SIZE), dtype=policy_dtype, device=dev)
-        valid = actions >= 0
-        dense.scatter_(1, actions.clamp(min=0).to(torch.int64), torch.where(valid, pol, torch.zeros_like(pol)).to(policy_dtype))
-        rec_state.append(states)
-        rec_policy.append(dense)
-        rec_game.append(game_id)
-        rec_ply.append(torch.full_like(game_id, ply))
-        pick = torch.multinomial(pol.float(), 1, generator=gen)          # np.random.choice(legal, p=scores)
-        act = torch.gather(actions, 1, pick).squeeze(1)
-        states, term = gl.next_batch(states, act)
-        ply += 1
-        done = term != 0
-        final_flags[game_id[done]] = term[done]
-        final_plies[game_id[done]] = ply
-        states, game_id = states[~done].contiguous(), game_id[~done]
-    game, plyv = torch.cat(rec_game), torch.cat(rec_ply)
+    with torch.cuda.device(dev):
+        while states.shape[0] > 0 and (max_plies is None or ply < max_plies):
+            G = states.shape[0]
+            counts, actions, n, status = mcts.search_async(states)
+            sims_run += G * sims
+            dense = torch.empty((G, POLICY_OUTPUT_SIZE), dtype=policy_dtype, device=dev)
+            nxt = torch.empty_like(states)
+            nxt_id = torch.empty_like(game_id)
+            _lib.check(L.aq_selfplay_advance(P(states), P(counts), P(actions), P(n), P(game_id), G, float(temperature), seed, ply,
+                                             P(dense), int(policy_dtype == torch.float64), None, P(nxt), P(nxt_id), P(final_flags),
+                                             P(final_plies), P(alive), P(ws), _lib.stream_ptr(dev)), "aq_selfplay_advance")
+            flags = torch.cat([status, alive]).tolist()      # the ply's only synchronisation
+            mcts.check_status(flags)
+            rec_state.append(states)
+            rec_policy.append(dense)
+            rec_game.append(game_id)
+            sizes.append(G)
+            ply += 1
+            states, game_id = nxt[:flags[2]], nxt_id[:flags[2]]
+    if not sizes:
+        z = torch.zeros((0,), dtype=torch.int64, device=dev)
+        return {"states": states, "policy": torch.zeros((0, POLICY_OUTPUT_SIZE), dtype=policy_dtype, device=dev),
+                "value": torch.zeros((0,), dtype=torch.float32, device=dev), "game": z, "ply": z, "flags": final_flags[:num_games],
+                "plies": final_plies[:num_games], "sims": 0}
+    game = torch.cat(rec_game)
+    plyv = torch.repeat_interleave(torch.arange(len(sizes), device=dev), torch.tensor(sizes, device=dev))
+    final_flags, final_plies = final_flags[:num_games], final_plies[:num_games]
     # first_player_value of the ended state (self_play.py:22-27): the player to move there has lost; the value target of a
     # position alternates in sign with the ply (self_play.py:63-66); unfinished games (max_plies) count as draws
     lost = (final_flags[game] & 1) != 0

@@ -53,7 +53,7 @@ typedef struct AqState {
     uint64_t reserved; /* reserved, 0 */
 } AqState;
 
-#define AQ_VERSION 203 /* bumped with every change of a signature below; the ctypes loader refuses a library of another version */
+#define AQ_VERSION 204 /* bumped with every change of a signature below; the ctypes loader refuses a library of another version */
 int aq_version(void);
 const char *aq_last_error_string(void);
 /* Number of kernels this library has launched in the process so far (monotonic; kernels replayed through a CUDA graph the caller
@@ -263,6 +263,22 @@ int aq_mcts_expand_backup(void *ws, int64_t G, int64_t max_nodes, const float *p
                           const uint32_t *mask, const uint8_t *pawn, void *stream);
 int aq_mcts_root_counts(void *ws, int64_t G, int64_t max_nodes, int32_t *counts /*[G,136]*/,
                         int16_t *actions /*[G,136]*/, int16_t *n_children /*[G]*/, int32_t *overflow, void *stream);
+
+/* One ply of G lock-step self-play games after their searches (self_play.py:47-60), two launches:
+ *   scores = counts ** (1 / temperature) / sum over the root's children (pv_mcts.py:88-95; temperature 0 = one-hot on
+ *            the first maximum, np.argmax); policy[g, action] = score, 0 for the other of the 209 actions (self_play.py:51-54),
+ *            float64 if policy_f64 else float32;
+ *   action = one draw from scores (self_play.py:57, np.random.choice(legal_actions, p=scores)): inverse CDF in
+ *            legal_actions() order of a uniform hashed from (seed, game_id[g], ply); chosen[g] (may be NULL);
+ *   the games whose next state (self_play.py:60) is not terminal are written, in order, to next_states / next_game_id
+ *   and counted in alive_count[0]; for the others final_flags[game_id] = is_lose | is_draw << 1 of the last state
+ *   (game_logic.py:43-50) and final_plies[game_id] = ply + 1.
+ * counts / actions / n_children as aq_mcts_root_counts returns them; workspace: aq_selfplay_ws_bytes(G) device bytes. */
+int64_t aq_selfplay_ws_bytes(int64_t G);
+int aq_selfplay_advance(const AqState *states, const int32_t *counts, const int16_t *actions, const int16_t *n_children,
+                        const int64_t *game_id, int64_t G, double temperature, uint64_t seed, int32_t ply, void *policy,
+                        int policy_f64, int16_t *chosen, AqState *next_states, int64_t *next_game_id, uint8_t *final_flags,
+                        int64_t *final_plies, int32_t *alive_count, void *workspace, void *stream);
 
 /* agents.heuristic_eval (agents.py:22-54) for B states: shortest pawn-path lengths to the goal row for the mover
  * and for the enemy (shortest_path_bfs, agents.py:27-41, with the jump rules of legal_actions_pos; -1 = no path).

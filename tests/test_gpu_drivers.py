@@ -54,6 +54,135 @@ def test_self_play_history_format_and_semantics():
             assert game[0][2] == 0 and n == 116
 
 
+_M64 = (1 << 64) - 1
+
+
+def _mix64(z):
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def _uniform(seed, game, ply):
+    """The counter-based uniform aq_selfplay_advance documents: a hash of (seed, game id, ply) -> [0, 1)."""
+    z = _mix64((seed + 0x9E3779B97F4A7C15 * (game + 1)) & _M64)
+    z = _mix64((z + 0xD1B54A32D192ED03 * (ply + 1)) & _M64)
+    return (z >> 11) / 9007199254740992.0
+
+
+def _advance(states, counts, actions, n, game_id, temperature, seed, ply, num_games, dtype=torch.float64):
+    from alphaquoridorgnn_b200 import _lib
+    L, P = _lib.load(), _lib.ptr
+    G = states.shape[0]
+    dev = states.device
+    out = dict(policy=torch.full((G, 209), -1, dtype=dtype, device=dev), chosen=torch.full((G,), -7, dtype=torch.int16, device=dev),
+               nxt=torch.zeros_like(states), nxt_id=torch.full_like(game_id, -1), flags=torch.zeros(num_games, dtype=torch.uint8, device=dev),
+               plies=torch.zeros(num_games, dtype=torch.int64, device=dev), alive=torch.zeros(1, dtype=torch.int32, device=dev))
+    ws = torch.empty(L.aq_selfplay_ws_bytes(G), dtype=torch.uint8, device=dev)
+    _lib.check(L.aq_selfplay_advance(P(states), P(counts), P(actions), P(n), P(game_id), G, float(temperature), seed, ply, P(out["policy"]),
+                                     int(dtype == torch.float64), P(out["chosen"]), P(out["nxt"]), P(out["nxt_id"]), P(out["flags"]),
+                                     P(out["plies"]), P(out["alive"]), P(ws), _lib.stream_ptr()), "aq_selfplay_advance")
+    torch.cuda.synchronize()
+    return out
+
+
+def test_selfplay_advance_policy_move_and_compaction(traj):
+    """aq_selfplay_advance against the reference's expressions evaluated on the host (self_play.py:47-60, pv_mcts.py:88-95):
+    scores = counts / sum exactly, dense 209-wide record, the drawn action = inverse CDF of the documented uniform in
+    legal_actions() order, next state = State.next, survivors in order, final flags / lengths of the games that ended."""
+    rng = np.random.default_rng(3)
+    # 1,500 > 1,024 exercises the second block of the compaction scan; 300 positions one ply before the draw so that games end
+    live = np.nonzero((traj["plies"] < 116) & (traj["rows"][:, 2] // 9 != 0))[0]
+    late = live[np.argsort(-traj["plies"][live], kind="stable")[:300]]
+    pick = np.concatenate([late, rng.choice(np.setdiff1d(live, late), 1200, replace=False)])
+    rng.shuffle(pick)
+    rows, plies = traj["rows"][pick], traj["plies"][pick]
+    G = len(rows)
+    packed = gl.pack_rows(rows, plies, "cuda")
+    legal = qo.legal_actions_batch(rows, plies)
+    actions, nch = legal["actions"], legal["n"]
+    counts = np.zeros((G, 136), dtype=np.int32)
+    for g in range(G):
+        k = int(nch[g])
+        c = rng.integers(0, 40, k) * (rng.random(k) < 0.5)                 # many zero counts, as after a search
+        if c.sum() == 0:
+            c[rng.integers(k)] = 1
+        counts[g, :k] = c
+    game_id = torch.from_numpy(rng.permutation(5000)[:G].astype(np.int64)).cuda()
+    seed, ply = 0xDEADBEEF12345, 57
+    dev = lambda a: torch.from_numpy(a).cuda()
+    out = _advance(packed, dev(counts), dev(actions), dev(nch), game_id, 1.0, seed, ply, 5000)
+    pol = out["policy"].cpu().numpy()
+    chosen = out["chosen"].cpu().numpy()
+    gid = game_id.cpu().numpy()
+    for g in range(G):
+        k = int(nch[g])
+        scores = counts[g, :k] / counts[g, :k].sum()                       # float64, exact for integer counts
+        dense = np.zeros(209)
+        dense[actions[g, :k]] = scores
+        assert np.array_equal(pol[g], dense), g
+        target = _uniform(seed, int(gid[g]), ply) * float(counts[g, :k].sum())
+        cum = np.cumsum(counts[g, :k].astype(np.float64))
+        hit = np.nonzero((counts[g, :k] > 0) & (target < cum))[0]
+        assert chosen[g] == actions[g, hit[0]], g
+    nrows_exp, nplies_exp, flags = qo.next_batch(rows, plies, chosen)
+    live = flags == 0
+    alive_rows, alive_ids = nrows_exp[live], gid[live]
+    exp_flags, exp_plies = np.zeros(5000, np.uint8), np.zeros(5000, np.int64)
+    exp_flags[gid[~live]], exp_plies[gid[~live]] = flags[~live], ply + 1
+    k = int(out["alive"].item())
+    assert 0 < k == len(alive_rows) < G                                    # the case has both survivors and finished games
+    nrows, nplies = gl.unpack_rows(out["nxt"][:k].contiguous())
+    assert np.array_equal(nrows.cpu().numpy(), alive_rows) and np.array_equal(nplies.cpu().numpy(), nplies_exp[live])
+    assert np.array_equal(out["nxt_id"][:k].cpu().numpy(), alive_ids)
+    assert np.array_equal(out["flags"].cpu().numpy(), exp_flags) and np.array_equal(out["plies"].cpu().numpy(), exp_plies)
+    # float32 record: the same scores rounded once
+    out32 = _advance(packed, dev(counts), dev(actions), dev(nch), game_id, 1.0, seed, ply, 5000, torch.float32)
+    assert np.array_equal(out32["policy"].cpu().numpy(), pol.astype(np.float32)) and torch.equal(out32["chosen"], out["chosen"])
+    # temperature 0: one-hot on the first maximum (np.argmax, pv_mcts.py:90-93)
+    out0 = _advance(packed, dev(counts), dev(actions), dev(nch), game_id, 0.0, seed, ply, 5000)
+    first_max = actions[np.arange(G), counts.argmax(axis=1)]
+    assert np.array_equal(out0["chosen"].cpu().numpy(), first_max)
+    p0 = out0["policy"].cpu().numpy()
+    assert np.array_equal(p0.sum(axis=1), np.ones(G)) and np.array_equal(p0[np.arange(G), first_max], np.ones(G))
+    # a game's draw depends on (seed, game, ply) only -- not on its row or on the other games of the batch
+    sub = torch.arange(G - 1, -1, -3).cuda()
+    outs = _advance(packed[sub].contiguous(), dev(counts)[sub].contiguous(), dev(actions)[sub].contiguous(), dev(nch)[sub].contiguous(),
+                    game_id[sub].contiguous(), 1.0, seed, ply, 5000)
+    assert torch.equal(outs["chosen"], out["chosen"][sub])
+    # temperature 2: counts ** 0.5 normalised
+    out2 = _advance(packed, dev(counts), dev(actions), dev(nch), game_id, 2.0, seed, ply, 5000)
+    x = np.sqrt(counts.astype(np.float64))
+    exp = np.zeros((G, 209))
+    for g in range(G):
+        exp[g, actions[g, :nch[g]]] = x[g, :nch[g]] / x[g, :nch[g]].sum()
+    assert np.abs(out2["policy"].cpu().numpy() - exp).max() < 1e-14
+
+
+def test_selfplay_advance_draws_follow_the_search_policy():
+    """20,000 games with the same root and the same visit counts: the empirical frequencies of the drawn actions match
+    counts / sum (np.random.choice(legal_actions, p=scores), self_play.py:57)."""
+    G = 20000
+    st = qo.PyOracleState()
+    la = st.legal_actions()
+    rows, plies = gl.rows_from_states([st])
+    packed = gl.pack_rows(rows, plies, "cuda").expand(G, -1).contiguous()
+    c = np.zeros(136, dtype=np.int32)
+    c[:len(la)] = np.random.default_rng(1).integers(0, 30, len(la))
+    a = np.full(136, -1, dtype=np.int16)
+    a[:len(la)] = la
+    rep = lambda v: torch.from_numpy(np.broadcast_to(v, (G,) + v.shape).copy()).cuda()
+    out = _advance(packed, rep(c), rep(a), torch.full((G,), len(la), dtype=torch.int16).cuda(), torch.arange(G).cuda(), 1.0, 99, 0, G)
+    freq = np.bincount(out["chosen"].cpu().numpy().astype(np.int64), minlength=209) / G
+    p = np.zeros(209)
+    p[la] = c[:len(la)] / c.sum()
+    assert np.abs(freq - p).max() < 4 * np.sqrt(0.25 / G) and freq[p == 0].sum() == 0
+    # other seeds / plies give other draws
+    out_b = _advance(packed, rep(c), rep(a), torch.full((G,), len(la), dtype=torch.int16).cuda(), torch.arange(G).cuda(), 1.0, 100, 0, G)
+    out_c = _advance(packed, rep(c), rep(a), torch.full((G,), len(la), dtype=torch.int16).cuda(), torch.arange(G).cuda(), 1.0, 99, 1, G)
+    assert 0.5 < (out_b["chosen"] != out["chosen"]).float().mean() and 0.5 < (out_c["chosen"] != out["chosen"]).float().mean()
+
+
 def test_flat_trainer_matches_torch_autograd_and_adam(traj):
     rng = np.random.default_rng(0)
     idx = rng.choice(len(traj["rows"]), 96, replace=False)
