@@ -213,9 +213,15 @@ legal_mask_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__res
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kNullTask = 0xFFFFFFFFu;
 constexpr int64_t kLegalChunk = (int64_t)1 << 23;  // states per launch pair (state index field: 24 bits)
-constexpr int kRefillIdle = 8;                     // a warp fetches new tasks when at least this many of its lanes are idle
+#ifndef AQ_REFILL_IDLE
+#define AQ_REFILL_IDLE 28
+#endif
+constexpr int kRefillIdle = AQ_REFILL_IDLE;                     // a warp fetches new tasks when at least this many of its lanes are idle
 
-__global__ void __launch_bounds__(kLegalWarps * 32)
+#ifndef AQ_PREP_MIN_CTAS
+#define AQ_PREP_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(kLegalWarps * 32, AQ_PREP_MIN_CTAS)
 legal_prepare_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__restrict__ mask, uint8_t *__restrict__ pawn,
                      uint32_t *__restrict__ tasks, unsigned cap, unsigned *__restrict__ counter) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -321,7 +327,13 @@ legal_prepare_kernel(const AqState *__restrict__ states, int64_t B, uint32_t *__
     }
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef AQ_FILL_STEPS
+#define AQ_FILL_STEPS 2
+#endif
+#ifndef AQ_SEARCH_MIN_CTAS
+#define AQ_SEARCH_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(128, AQ_SEARCH_MIN_CTAS)
 legal_search_kernel(const AqState *__restrict__ states, const uint32_t *tasks, const unsigned *counter, unsigned *cursor,
                     unsigned cap, uint32_t *__restrict__ mask) {
     aq_pdl_trigger();
@@ -373,7 +385,9 @@ legal_search_kernel(const AqState *__restrict__ states, const uint32_t *tasks, c
         if (active) {
             // two BFS layers per round (one exit test per two layers: the fill is monotone, a layer too many changes nothing)
             bool grew = fill_step(o, ob, ob_b, f);
-            if (grew && !meets(f.reach, goal)) grew = fill_step(o, ob, ob_b, f);
+#pragma unroll
+            for (int k = 1; k < AQ_FILL_STEPS; ++k)
+                if (grew && !meets(f.reach, goal)) grew = fill_step(o, ob, ob_b, f);
             if (meets(f.reach, goal)) {
                 active = false;
             } else if (!grew) {
