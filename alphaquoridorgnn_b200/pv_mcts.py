@@ -44,6 +44,7 @@ class BatchedMCTS:
         self._ws = None
         self._buf = {}
         self._graphs = {}
+        self._warm = False   # one eager simulation step has run (lazy initialisation is done)
 
     def _workspace(self, G, max_nodes):
         L = _lib.load()
@@ -131,33 +132,40 @@ class BatchedMCTS:
                 key = (G, max_nodes, flat.data_ptr(), prep.data_ptr() if prep is not None else 0, prec)
                 graphs = self._graphs.get(key) if self.use_graph else None
                 done = 0
-                if self.use_graph and graphs is None:
-                    # warm-up outside capture (= simulation 1); a failure here is a real error and propagates
-                    self._step_network(ws, G, max_nodes, buf, flat, prep, prec, st)
-                    done = 1
-                    torch.cuda.synchronize(dev)
-                    try:
-                        # two graphs: one simulation, and GRAPH_CHUNK simulations back to back -- a search is then a handful of
-                        # graph launches instead of one per simulation (a launch costs the host 10-100 us depending on the box,
-                        # the step 80 us of GPU time at 4,096 games)
-                        graphs = tuple(self._capture(lambda cst, k=steps: [self._step_network(ws, G, max_nodes, buf, flat, prep, prec, cst)
-                                                                           for _ in range(k)]) for steps in (1, GRAPH_CHUNK))
+                if self.use_graph:
+                    if graphs is None:
+                        if not self._warm:
+                            # the searcher's first step runs outside capture (= simulation 1): lazy initialisation (module load,
+                            # function attributes) must not happen inside one; a failure here is a real error and propagates
+                            self._step_network(ws, G, max_nodes, buf, flat, prep, prec, st)
+                            done, self._warm = 1, True
+                            torch.cuda.synchronize(dev)
                         if len(self._graphs) >= 32:
                             self._graphs.clear()
-                        self._graphs[key] = graphs
+                        self._graphs[key] = graphs = {}
+                    left = sims - done
+                    try:
+                        # GRAPH_CHUNK simulations back to back in one graph (+ a one-step graph for the remainder, captured only when
+                        # there is one): a search is a handful of graph launches instead of one per simulation -- a launch costs the
+                        # host 10-100 us depending on the box, the step 75 us of GPU time at 4,096 games
+                        for steps in ((GRAPH_CHUNK,) if left >= GRAPH_CHUNK else ()) + ((1,) if left % GRAPH_CHUNK else ()):
+                            if steps not in graphs:
+                                graphs[steps] = self._capture(lambda cst, k=steps: [self._step_network(ws, G, max_nodes, buf, flat, prep, prec, cst)
+                                                                                    for _ in range(k)])
                     except _lib.AqError:
                         raise
                     except Exception as e:  # capture unsupported: stay eager, but say so
                         import warnings
                         warnings.warn(f"CUDA-graph capture of the MCTS simulation step failed ({e!r}); running the step eagerly")
                         self.use_graph, graphs = False, None
+                        self._graphs.clear()
                         torch.cuda.synchronize(dev)
                 left = sims - done
                 if graphs is not None:
                     for _ in range(left // GRAPH_CHUNK):
-                        graphs[1].replay()
+                        graphs[GRAPH_CHUNK].replay()
                     for _ in range(left % GRAPH_CHUNK):
-                        graphs[0].replay()
+                        graphs[1].replay()
                 else:
                     for _ in range(left):
                         self._step_network(ws, G, max_nodes, buf, flat, prep, prec, st)

@@ -613,7 +613,8 @@ def run_ours(args, rank, world, local_rank):
         # ---- lock-step PV-MCTS self-play, WHOLE games (BASELINE configs[3]) and training on that record (configs[4]) ----------
         try:
             G, SIMS = args.mcts_games, args.mcts_sims
-            self_play.play_batch_device(net, G, dev, sims=SIMS, seed=4, max_plies=1)  # warm-up: module loads, first graph capture
+            # warm-up = one untimed pass of the same work: module loads and the graph captures for the batch sizes a game passes through
+            self_play.play_batch_device(net, G, dev, sims=SIMS, seed=4, policy_dtype=torch.float32)
             barrier()
             t0 = time.perf_counter()
             rec = self_play.play_batch_device(net, G, dev, sims=SIMS, seed=5 + rank, policy_dtype=torch.float32)
