@@ -532,13 +532,22 @@ def run_ours(args, rank, world, local_rank):
         return nbytes * reps / reduce_max(time.perf_counter() - t0) / 1e9
 
     wire = "f16" if prec == 1 else "f32"
-    e2e_v, e2e_d2h, e2e_short = e2e_pipelined(3, wire=wire, with_mask=False)
+    # How many batches to keep in flight is the caller's choice (one HostLeafEvaluator per pool of games).  More of them let the
+    # legal-mask / heads / compaction kernels of neighbouring batches fill the ends of each other's trunk (6 in flight: +10 % on one
+    # GPU); where the box's device -> host link is the limit (eight GPUs at once) more outstanding copies only contend (-6 %).  The
+    # link is measured first, with copies of the step's size, and the pool sized by the headroom it shows.
+    est_d2h = B * (4 + 4 + 102 * (2 if wire == "f16" else 4))          # offsets + value + ~102 legal actions per board
+    ceil_gbs = d2h_ceiling(max(1 << 20, est_d2h))
+    need_gbs = est_d2h / (ms_step * 1e-3) / 1e9                          # at the device-resident rate of this run
+    inflight = 6 if ceil_gbs >= 2.0 * need_gbs else 3
+    e2e_v, e2e_d2h, e2e_short = e2e_pipelined(inflight, wire=wire, with_mask=False)
     e2e = {"value": e2e_v, "unit": "board-evals/s", "h2d_bytes_per_step": B * 32, "d2h_bytes_per_step": e2e_d2h,
            "api": f"HostLeafEvaluator(wire='{wire}', with_mask=False).submit / wait -> aq_leaf_eval_host_compact_submit / _wait: what "
-                  "BaseNetwork.predict returns for a batch (ragged priors of the legal actions in legal_actions() order + value); three "
-                  "batches in flight (three evaluators used round-robin); one event wait per batch",
+                  f"BaseNetwork.predict returns for a batch (ragged priors of the legal actions in legal_actions() order + value); "
+                  f"{inflight} batches in flight ({inflight} evaluators used round-robin; 6 where the measured device -> host ceiling "
+                  f"is at least twice what the step needs, else 3); one event wait per batch",
+           "batches_in_flight": inflight,
            "ragged_copies_completed_by_a_second_copy": e2e_short}
-    ceil_gbs = d2h_ceiling(max(1 << 20, e2e_d2h))
     e2e["d2h_ceiling_gbs_per_gpu"] = ceil_gbs
     e2e["d2h_achieved_gbs_per_gpu"] = e2e_d2h * (e2e_v / world / B) / 1e9
     extra = {}

@@ -57,6 +57,16 @@ def run(inflight, **kw):
 
 
 out = {}
+if os.environ.get("TRUNK_CTAS"):
+    import ctypes
+    from alphaquoridorgnn_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for cap in [int(c) for c in os.environ["TRUNK_CTAS"].split(",")]:
+        lib.aq_debug_trunk_ctas(cap)
+        for inflight in (3, 4):
+            out[f"f16 x{inflight} trunk {cap} CTAs"] = round(run(inflight, wire="f16", with_mask=False), 1)
+    print(json.dumps(out))
+    sys.exit(0)
 for inflight in (2, 3, 4, 6, 8):
     out[f"f16 x{inflight}"] = round(run(inflight, wire="f16", with_mask=False), 1)
 out["f32+mask x3"] = round(run(3, wire="f32", with_mask=True), 1)
