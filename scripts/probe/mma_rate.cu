@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128, 1) k(int mode, int N, int iters, long lon
         const uint32_t t32 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24) | ((uint32_t)(N >> 3) << 17);
         const long long t0 = clock64();
         for (int i = 0; i < iters; ++i) {
-            const uint32_t dd = tb + (uint32_t)(i % nchains) * 48u;
+            const uint32_t dd = tb + (uint32_t)(i % nchains) * (uint32_t)(N <= 48 ? 48 : 96);
             if (mode == 0) mma_bf16(dd, desc_sw128(a_s + (i & 3) * 32), desc_sw128(b_s + (i & 3) * 32), f16, 1u);      // SS f16
             else if (mode == 1) mma_ts(dd, tb + 448 + (i & 7) * 8, desc_sw128(b_s + (i & 3) * 32), f16, 0);            // TS f16
             else mma_ts(dd, tb + 448 + (i & 7) * 8, desc_sw128(b_s + (i & 3) * 32), t32, 1);                            // TS tf32
@@ -50,7 +50,7 @@ int main() {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 70 * 1024);
     const char *names[3] = {"SS f16 (A, B smem)", "TS f16 (A TMEM)", "TS tf32 (A TMEM)"};
     for (int mode = 0; mode < 3; ++mode)
-        for (int nch : {1, 2, 4, 8}) for (int N : {48}) {
+        for (int nch : {1, 4}) for (int N : {16, 32, 48, 64, 96}) {
             const int iters = 2000;
             k<<<148, 128, 70 * 1024>>>(mode, N, iters, d, nch);
             if (cudaDeviceSynchronize() != cudaSuccess) { printf("error mode %d N %d\n", mode, N); return 1; }
