@@ -518,11 +518,12 @@ def run_ours(args, rank, world, local_rank):
         ev.close()
         return world * B * K / dt, int(sum(d2h) / len(d2h))
 
-    def d2h_ceiling(nbytes, reps=40):
-        """What this box's device -> host path gives one plain pinned cudaMemcpyAsync loop per rank, all ranks at once."""
+    def d2h_ceiling(nbytes, reps=300):
+        """What this box's device -> host path gives one plain pinned cudaMemcpyAsync loop per rank, all ranks at once.  Long enough
+        (about 1 GB per rank) that the ranks' loops really overlap: with 40 copies the eight-GPU figure came out a third too high."""
         src = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         dst = torch.empty((nbytes,), dtype=torch.uint8).pin_memory()
-        for _ in range(3):
+        for _ in range(10):
             dst.copy_(src, non_blocking=True)
         barrier()
         t0 = time.perf_counter()
