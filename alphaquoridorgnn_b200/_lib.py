@@ -9,7 +9,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libaqgnn.so")
-ABI_VERSION = 204  # AQ_VERSION of include/aqgnn.h this table of signatures was written for
+ABI_VERSION = 205  # AQ_VERSION of include/aqgnn.h this table of signatures was written for
 
 # name -> (restype, argtypes); must list every symbol declared in include/aqgnn.h
 _vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
@@ -63,6 +63,7 @@ SYMBOLS = {
     "aq_mcts_reset": (_i32, [_vp, _vp, _i64, _i64, _vp]),
     "aq_mcts_select": (_i32, [_vp, _i64, _i64, _f32, _vp, _vp, _vp]),
     "aq_mcts_expand_backup": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "aq_mcts_expand_select": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp]),
     "aq_mcts_root_counts": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "aq_selfplay_ws_bytes": (_i64, [_i64]),
     "aq_selfplay_advance": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _f64, _u64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -65,15 +65,10 @@ __global__ void mcts_reset_kernel(MctsGame *games, MctsHot *hot, MctsCold *cold,
     cold[g * max_nodes] = rc;
 }
 
-// one warp per game
-__global__ void __launch_bounds__(128)
-mcts_select_kernel(MctsGame *games, const MctsHot *__restrict__ hot_all, const MctsCold *__restrict__ cold_all, int64_t G,
-                   int64_t max_nodes, float c_puct, AqState *__restrict__ leaf_states, int32_t *__restrict__ leaf_kind) {
-    const int lane = threadIdx.x & 31;
-    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (g >= G) return;
-    const MctsHot *hot = hot_all + g * max_nodes;
-    const MctsCold *cold = cold_all + g * max_nodes;
+// Descent of game g by its warp (pv_mcts.py:69-78).  The node arrays are read through plain pointers: in the fused kernel the same
+// warp has just written them (expansion + backup), so the loads must be coherent ones.
+__device__ __forceinline__ void select_game(MctsGame *games, const MctsHot *hot, const MctsCold *cold, int64_t g, int lane, float c_puct,
+                                            AqState *leaf_states, int32_t *leaf_kind) {
     AqState s = games[g].root;
     int node = 0, kind = 0;
     // what the descent needs from a node: first_child, n_children (cold half) and n (hot half, known from the scan of its parent)
@@ -123,15 +118,19 @@ mcts_select_kernel(MctsGame *games, const MctsHot *__restrict__ hot_all, const M
     }
 }
 
+// one warp per game
 __global__ void __launch_bounds__(128)
-mcts_expand_backup_kernel(MctsGame *games, MctsHot *hot_all, MctsCold *cold_all, int64_t G, int64_t max_nodes,
-                          const float *__restrict__ priors, const float *__restrict__ values,
-                          const uint32_t *__restrict__ mask, const uint8_t *__restrict__ pawn) {
+mcts_select_kernel(MctsGame *games, const MctsHot *hot_all, const MctsCold *cold_all, int64_t G, int64_t max_nodes, float c_puct,
+                   AqState *leaf_states, int32_t *leaf_kind) {
     const int lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= G) return;
-    MctsHot *hot = hot_all + g * max_nodes;
-    MctsCold *cold = cold_all + g * max_nodes;
+    select_game(games, hot_all + g * max_nodes, cold_all + g * max_nodes, g, lane, c_puct, leaf_states, leaf_kind);
+}
+
+// Expansion of the selected leaf of game g with the evaluated priors (pv_mcts.py:47-56) and the backup of its value (:60-66).
+__device__ __forceinline__ void expand_backup_game(MctsGame *games, MctsHot *hot, MctsCold *cold, int64_t g, int lane, int64_t max_nodes,
+                                                   const float *priors, const float *values, const uint32_t *mask, const uint8_t *pawn) {
     const int leaf = games[g].leaf, kind = games[g].leaf_kind;
     double value;
     if (kind == 0) {
@@ -203,6 +202,32 @@ mcts_expand_backup_kernel(MctsGame *games, MctsHot *hot_all, MctsCold *cold_all,
             node = cold[node].parent;
         }
     }
+}
+
+__global__ void __launch_bounds__(128)
+mcts_expand_backup_kernel(MctsGame *games, MctsHot *hot_all, MctsCold *cold_all, int64_t G, int64_t max_nodes,
+                          const float *__restrict__ priors, const float *__restrict__ values,
+                          const uint32_t *__restrict__ mask, const uint8_t *__restrict__ pawn) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= G) return;
+    expand_backup_game(games, hot_all + g * max_nodes, cold_all + g * max_nodes, g, lane, max_nodes, priors, values, mask, pawn);
+}
+
+// Expansion + backup of simulation i and the descent of simulation i + 1 in one launch: a game's next descent only needs that game's
+// own backup, so there is no reason to wait for the other 4,095 games and for a kernel boundary in between.
+__global__ void __launch_bounds__(128)
+mcts_expand_select_kernel(MctsGame *games, MctsHot *hot_all, MctsCold *cold_all, int64_t G, int64_t max_nodes,
+                          const float *__restrict__ priors, const float *__restrict__ values, const uint32_t *__restrict__ mask,
+                          const uint8_t *__restrict__ pawn, float c_puct, AqState *leaf_states, int32_t *leaf_kind) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= G) return;
+    MctsHot *hot = hot_all + g * max_nodes;
+    MctsCold *cold = cold_all + g * max_nodes;
+    expand_backup_game(games, hot, cold, g, lane, max_nodes, priors, values, mask, pawn);
+    __syncwarp();   // orders the warp's node writes (children by all lanes, the backup by lane 0) before the descent's reads
+    select_game(games, hot, cold, g, lane, c_puct, leaf_states, leaf_kind);
 }
 
 __global__ void mcts_root_counts_kernel(const MctsGame *__restrict__ games, const MctsHot *__restrict__ hot_all,
@@ -400,6 +425,14 @@ extern "C" int aq_mcts_expand_backup(void *ws, int64_t G, int64_t max_nodes, con
     mcts_expand_backup_kernel<<<(unsigned)((G + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         games_of(ws), hot_of(ws, G), cold_of(ws, G, max_nodes), G, max_nodes, priors, values, mask, pawn);
     return aq_check_launch("aq_mcts_expand_backup");
+}
+
+extern "C" int aq_mcts_expand_select(void *ws, int64_t G, int64_t max_nodes, const float *priors, const float *values, const uint32_t *mask,
+                                     const uint8_t *pawn, float c_puct, AqState *leaf_states, int32_t *leaf_kind, void *stream) {
+    if (G <= 0 || !ws || !priors || !values || !mask || !pawn || !leaf_states || !leaf_kind) return aq_set_error(AQ_ERR_ARG, "aq_mcts_expand_select");
+    mcts_expand_select_kernel<<<(unsigned)((G + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        games_of(ws), hot_of(ws, G), cold_of(ws, G, max_nodes), G, max_nodes, priors, values, mask, pawn, c_puct, leaf_states, leaf_kind);
+    return aq_check_launch("aq_mcts_expand_select");
 }
 
 extern "C" int aq_mcts_root_counts(void *ws, int64_t G, int64_t max_nodes, int32_t *counts, int16_t *actions,

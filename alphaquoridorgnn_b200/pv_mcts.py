@@ -71,14 +71,20 @@ class BatchedMCTS:
             }
         return self._buf[G]
 
-    def _step_network(self, ws, G, max_nodes, buf, flat, prep, prec, st):
-        """One simulation for all games with the network evaluator: three library calls, five kernels."""
+    def _step_network(self, ws, G, max_nodes, buf, flat, prep, prec, st, steps=1):
+        """`steps` simulations for all games with the network evaluator: select, then `steps` leaf evaluations (three kernels each)
+        joined by the fused expand + backup + next select, then the last expand + backup."""
         L, P = _lib.load(), _lib.ptr
         _lib.check(L.aq_mcts_select(P(ws), G, max_nodes, self.c_puct, P(buf["leaf"]), P(buf["kind"]), st), "aq_mcts_select")
-        _lib.check(L.aq_leaf_eval(P(flat), P(prep), P(buf["leaf"]), G, P(buf["priors"]), P(buf["value"]), P(buf["mask"]), P(buf["pawn"]),
-                                  P(buf["pooled"]), prec, st), "aq_leaf_eval")
-        _lib.check(L.aq_mcts_expand_backup(P(ws), G, max_nodes, P(buf["priors"]), P(buf["value"]), P(buf["mask"]),
-                                           P(buf["pawn"]), st), "aq_mcts_expand_backup")
+        for i in range(steps):
+            _lib.check(L.aq_leaf_eval(P(flat), P(prep), P(buf["leaf"]), G, P(buf["priors"]), P(buf["value"]), P(buf["mask"]), P(buf["pawn"]),
+                                      P(buf["pooled"]), prec, st), "aq_leaf_eval")
+            if i + 1 < steps:
+                _lib.check(L.aq_mcts_expand_select(P(ws), G, max_nodes, P(buf["priors"]), P(buf["value"]), P(buf["mask"]), P(buf["pawn"]),
+                                                   self.c_puct, P(buf["leaf"]), P(buf["kind"]), st), "aq_mcts_expand_select")
+            else:
+                _lib.check(L.aq_mcts_expand_backup(P(ws), G, max_nodes, P(buf["priors"]), P(buf["value"]), P(buf["mask"]),
+                                                   P(buf["pawn"]), st), "aq_mcts_expand_backup")
 
     def _capture(self, enqueue):
         """Capture enqueue(stream pointer) into a CUDA graph.  `torch.cuda.graph` is not used on purpose: on entry it empties the
@@ -150,8 +156,7 @@ class BatchedMCTS:
                         # host 10-100 us depending on the box, the step 75 us of GPU time at 4,096 games
                         for steps in ((GRAPH_CHUNK,) if left >= GRAPH_CHUNK else ()) + ((1,) if left % GRAPH_CHUNK else ()):
                             if steps not in graphs:
-                                graphs[steps] = self._capture(lambda cst, k=steps: [self._step_network(ws, G, max_nodes, buf, flat, prep, prec, cst)
-                                                                                    for _ in range(k)])
+                                graphs[steps] = self._capture(lambda cst, k=steps: self._step_network(ws, G, max_nodes, buf, flat, prep, prec, cst, k))
                     except _lib.AqError:
                         raise
                     except Exception as e:  # capture unsupported: stay eager, but say so

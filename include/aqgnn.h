@@ -53,7 +53,7 @@ typedef struct AqState {
     uint64_t reserved; /* reserved, 0 */
 } AqState;
 
-#define AQ_VERSION 204 /* bumped with every change of a signature below; the ctypes loader refuses a library of another version */
+#define AQ_VERSION 205 /* bumped with every change of a signature below; the ctypes loader refuses a library of another version */
 int aq_version(void);
 const char *aq_last_error_string(void);
 /* Number of kernels this library has launched in the process so far (monotonic; kernels replayed through a CUDA graph the caller
@@ -261,6 +261,10 @@ int aq_mcts_select(void *ws, int64_t G, int64_t max_nodes, float c_puct, AqState
                    void *stream);
 int aq_mcts_expand_backup(void *ws, int64_t G, int64_t max_nodes, const float *priors, const float *values,
                           const uint32_t *mask, const uint8_t *pawn, void *stream);
+/* aq_mcts_expand_backup of one simulation followed by aq_mcts_select of the next in one launch (same results: a game's next
+ * descent depends only on that game's own backup). */
+int aq_mcts_expand_select(void *ws, int64_t G, int64_t max_nodes, const float *priors, const float *values, const uint32_t *mask,
+                          const uint8_t *pawn, float c_puct, AqState *leaf_states, int32_t *leaf_kind, void *stream);
 int aq_mcts_root_counts(void *ws, int64_t G, int64_t max_nodes, int32_t *counts /*[G,136]*/,
                         int16_t *actions /*[G,136]*/, int16_t *n_children /*[G]*/, int32_t *overflow, void *stream);
 

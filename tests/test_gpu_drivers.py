@@ -327,8 +327,10 @@ def test_fused_training_step_equals_the_unfused_kernels(traj, prec):
         lf = fused.step(packed[sl], pt[sl], vt[sl], n).clone()
         le = eager.step(packed[sl], pt[sl], vt[sl], n).clone()
         lp = plain.step(packed[sl], pt[sl], vt[sl], n).clone()
-        assert (lf - le).abs().max().item() <= 1e-6
-        assert (lf - lp).abs().max().item() <= 5e-6      # the loss scalars are atomically accumulated per CTA: summation order
+        # the loss scalars (policy loss ~ 5.3) are accumulated with float atomics, one per CTA: the summation order, hence the last
+        # few ulps (4.8e-7 each at that magnitude), differs from launch to launch
+        assert (lf - le).abs().max().item() <= 1e-5
+        assert (lf - lp).abs().max().item() <= 1e-5
         assert torch.equal(fused.grads, eager.grads)
         assert (fused.grads - plain.grads).abs().max().item() <= 1e-6 * max(1.0, plain.grads.abs().max().item())
         assert (fused.flat - plain.flat).abs().max().item() <= 2e-6
