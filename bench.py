@@ -476,7 +476,7 @@ def run_ours(args, rank, world, local_rank):
     for h, b in zip(hst, batches):
         assert torch.equal(h, b.cpu())
 
-    def e2e_pipelined(inflight, **kw):
+    def e2e_pipelined(inflight, steps=None, **kw):
         """`inflight` evaluators (pools of games) used round-robin: while the host waits for one batch, the others' kernels run and
         their results cross PCIe.  Every step still moves its own states H2D and its own results D2H inside the timed region."""
         evs = [HostLeafEvaluator(net, B, **kw) for _ in range(inflight)]
@@ -492,17 +492,18 @@ def run_ours(args, rank, world, local_rank):
                 out = evs[i % inflight].wait()
                 d2h.append(evs[i % inflight].d2h_bytes(out))
 
+        n_timed = steps or K
         run(2 * inflight + 2)
         del d2h[:]
         barrier()
         t0 = time.perf_counter()
-        run(K)
+        run(n_timed)
         barrier()
         dt = reduce_max(time.perf_counter() - t0)
         short = sum(ev.stats()[0] for ev in evs)
         for ev in evs:
             ev.close()
-        return world * B * K / dt, int(sum(d2h) / len(d2h)), short
+        return world * B * n_timed / dt, int(sum(d2h) / len(d2h)), short
 
     def e2e_sync(dense):
         ev = HostLeafEvaluator(net, B, dense=dense)
@@ -535,19 +536,20 @@ def run_ours(args, rank, world, local_rank):
     wire = "f16" if prec == 1 else "f32"
     # How many batches to keep in flight is the caller's choice (one HostLeafEvaluator per pool of games).  More of them let the
     # legal-mask / heads / compaction kernels of neighbouring batches fill the ends of each other's trunk (6 in flight: +10 % on one
-    # GPU); where the box's device -> host link is the limit (eight GPUs at once) more outstanding copies only contend (-6 %).  The
-    # link is measured first, with copies of the step's size, and the pool sized by the headroom it shows.
+    # GPU); where the box's device -> host link is the limit (eight GPUs at once) more outstanding copies only contend (-6 %).  A
+    # host would try both once; so does this: an untimed trial of each, then the K timed steps with the better one (the decision is
+    # taken on the maximum over ranks, so every rank takes the same).
     est_d2h = B * (4 + 4 + 102 * (2 if wire == "f16" else 4))          # offsets + value + ~102 legal actions per board
     ceil_gbs = d2h_ceiling(max(1 << 20, est_d2h))
-    need_gbs = est_d2h / (ms_step * 1e-3) / 1e9                          # at the device-resident rate of this run
-    inflight = 6 if ceil_gbs >= 2.0 * need_gbs else 3
+    trial = {n: e2e_pipelined(n, steps=max(12, K // 2), wire=wire, with_mask=False)[0] for n in (3, 6)}
+    inflight = max(trial, key=trial.get)
     e2e_v, e2e_d2h, e2e_short = e2e_pipelined(inflight, wire=wire, with_mask=False)
     e2e = {"value": e2e_v, "unit": "board-evals/s", "h2d_bytes_per_step": B * 32, "d2h_bytes_per_step": e2e_d2h,
            "api": f"HostLeafEvaluator(wire='{wire}', with_mask=False).submit / wait -> aq_leaf_eval_host_compact_submit / _wait: what "
                   f"BaseNetwork.predict returns for a batch (ragged priors of the legal actions in legal_actions() order + value); "
-                  f"{inflight} batches in flight ({inflight} evaluators used round-robin; 6 where the measured device -> host ceiling "
-                  f"is at least twice what the step needs, else 3); one event wait per batch",
-           "batches_in_flight": inflight,
+                  f"{inflight} batches in flight ({inflight} evaluators used round-robin; the better of 3 and 6 in an untimed trial "
+                  f"before the timed steps); one event wait per batch",
+           "batches_in_flight": inflight, "trial_board_evals_per_sec": {str(n): v for n, v in trial.items()},
            "ragged_copies_completed_by_a_second_copy": e2e_short}
     e2e["d2h_ceiling_gbs_per_gpu"] = ceil_gbs
     e2e["d2h_achieved_gbs_per_gpu"] = e2e_d2h * (e2e_v / world / B) / 1e9
