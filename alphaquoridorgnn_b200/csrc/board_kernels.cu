@@ -651,6 +651,8 @@ extern "C" int aq_legal_mask_ws(const AqState *states, int64_t B, uint32_t *mask
         if (e != cudaSuccess) return aq_set_error((int)e, "aq_legal_mask(memset)");
         legal_prepare_kernel<<<blocks_for(n, kLegalWarps * 16), kLegalWarps * 32, 0, S(stream)>>>(states + lo, n, mask + 8 * lo, pawn + 8 * lo,
                                                                                                      tasks, cap, counter);
+        const int rc0 = aq_check_launch("aq_legal_mask(prepare)");
+        if (rc0) return rc0;
         // persistent warps fed through the cursor: enough of them for the expected number of searches (2-4 per state), at most 8 CTAs
         // of 128 threads per SM
         const unsigned grid = (unsigned)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (3 * n + 127) / 128));
