@@ -570,7 +570,14 @@ int aq_dp_adam_launch(void *comm, const float *grads_in, const float *partial, i
 #ifndef AQ_HEAD_CHUNK_ROWS
 #define AQ_HEAD_CHUNK_ROWS 64
 #endif
-static inline int head_slot_count(int64_t B) { return (int)std::min<int64_t>(kSlots, (B + AQ_HEAD_CHUNK_ROWS - 1) / AQ_HEAD_CHUNK_ROWS); }  // one row chunk per 64 boards
+int aq_heads_wgrad_tc_slots(int64_t B);  // heads_wgrad_tc.cu
+int aq_heads_wgrad_tc(const float *dhp, const float *dhv, const float *dz, const float *du, const float *pooled, const float *hp,
+                      const float *hv, int64_t B, float *partial, cudaStream_t st);
+// partial slots that hold head gradients: fp32 path (atb_jobs_kernel) one row chunk per 64 boards; tensor-core path one per 128-board tile
+static inline int head_slot_count(int64_t B, int precision) {
+    if (precision == 1) return aq_heads_wgrad_tc_slots(B);
+    return (int)std::min<int64_t>(kSlots, (B + AQ_HEAD_CHUNK_ROWS - 1) / AQ_HEAD_CHUNK_ROWS);
+}
 
 // The backward kernels up to the partial-gradient slots.  Loss gradient either given (dpolicy, dvalue) or computed in the heads
 // backward from the targets (ptarget, vtarget, B_total, loss).
@@ -620,10 +627,13 @@ static int backward_to_partials(const float *params, const float *saved, const f
         if ((rc = aq_check_launch("gcn_backward_kernel"))) return rc;
     }
 
+    if (precision == 1)   // head weight gradients on the tensor cores (the trunk backward above filled the GCN ranges of the slots)
+        return aq_heads_wgrad_tc(workspace + W.dhp(), workspace + W.dhv(), workspace + W.dz(), workspace + W.du(), saved + L.pooled(),
+                                 saved + L.hp(), saved + L.hv(), B, workspace + W.partial(), st);
     AtbJobs jobs;
     int nj = 0;
     // head jobs: one row chunk per 64 boards (at most kSlots); node-level jobs: kSlots chunks
-    const int head_slots = head_slot_count(B);
+    const int head_slots = head_slot_count(B, precision);
     auto add = [&](const float *A, int lda, int M, const float *Bm, int ldb, int N, int64_t R, int off, int bias_off = -1) {
         jobs.job[nj++] = AtbJob{A, lda, M, Bm, ldb, N, R, off, R == B ? head_slots : kSlots, bias_off};
     };
@@ -652,7 +662,7 @@ extern "C" int aq_gnn_backward(const float *params, const float *saved, const fl
     int rc = backward_to_partials(params, saved, dpolicy, dvalue, nullptr, nullptr, B, B, nullptr, workspace, precision, st);
     if (rc) return rc;
     cudaError_t e = aq_launch_pdl(reduce_partials_kernel, dim3((kNumParams / 2 + kRedPairs - 1) / kRedPairs), dim3(kRedPairs * 4), 0, st,
-                                  (const float *)(workspace + BwdWs{B}.partial()), grads, head_slot_count(B));
+                                  (const float *)(workspace + BwdWs{B}.partial()), grads, head_slot_count(B, precision));
     if (e != cudaSuccess) return aq_set_error((int)e, "reduce_partials_kernel(launch)");
     return aq_check_launch("reduce_partials_kernel");
 }
@@ -669,7 +679,7 @@ extern "C" int aq_train_backward_step(void *comm, float *params, const float *sa
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc = backward_to_partials(params, saved, nullptr, nullptr, policy_target, value_target, B, B_total, loss, workspace, precision, st);
     if (rc) return rc;
-    return aq_dp_adam_launch(comm, nullptr, workspace + BwdWs{B}.partial(), kSlots, head_slot_count(B), params, exp_avg, exp_avg_sq, grads, lr,
+    return aq_dp_adam_launch(comm, nullptr, workspace + BwdWs{B}.partial(), kSlots, head_slot_count(B, precision), params, exp_avg, exp_avg_sq, grads, lr,
                              beta1, beta2, eps, /*pdl=*/true, st);
 }
 
