@@ -267,40 +267,3 @@ def boltzman(xs, temperature):
     """Boltzmann distribution (pv_mcts.py:106-109)"""
     xs = [x ** (1 / temperature) for x in xs]
     return [x / sum(xs) for x in xs]
-
-
-def bench_sims_per_sec(net, dev, world, timed_barrier, games=4096, sims=200, moves=2):
-    """MCTS simulations/s for bench.py (BASELINE configs[3] shape: `games` concurrent games x `sims`
-    simulations per move, `moves` moves from the start position, T=1 sampling)."""
-    import time
-    from . import positions
-    import torch.distributed as dist
-    mcts = BatchedMCTS(net, sims, device=dev)
-    gen = torch.Generator(device=dev)
-
-    def play(n_moves):
-        roots = positions.start_states(games, dev)
-        done = 0
-        for _ in range(n_moves):
-            counts, actions, n = mcts.search(roots)
-            pol = policy_from_counts(counts, 1.0)
-            pick = torch.multinomial(pol.float(), 1, generator=gen)
-            act = torch.gather(actions, 1, pick).squeeze(1)
-            roots, term = gl.next_batch(roots, act)
-            done += roots.shape[0] * sims
-            roots = roots[term == 0].contiguous()
-        return done
-
-    gen.manual_seed(5)
-    play(1)  # warm-up of the whole move cycle with the timed shape: the simulation-step CUDA graph is captured here and every
-    #          torch kernel of the sampling step is loaded (CUDA loads modules lazily, milliseconds each)
-    gen.manual_seed(5)
-    timed_barrier()
-    t0 = time.perf_counter()
-    done = play(moves)
-    timed_barrier()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    return {"mcts_sims_per_sec": world * done / float(dt.item()), "mcts_config": f"{games} games x {sims} sims x {moves} moves per GPU",
-            "mcts_cuda_graph": bool(mcts.use_graph)}
