@@ -207,6 +207,17 @@ class BatchedMCTS:
         return counts, actions, n
 
 
+class _SearcherCache(dict):
+    """The searchers kept on a network object.  A copy or a pickle of the network starts with none: node arenas, captured graphs and
+    raw pointers belong to the object they were made for."""
+
+    def __deepcopy__(self, memo):
+        return _SearcherCache()
+
+    def __reduce__(self):
+        return (_SearcherCache, ())
+
+
 def searcher_for(evaluator, sims, device=None):
     """The BatchedMCTS of a network for `sims` simulations, kept on the network object: its node arenas (3.5 GB at 4,096 games x
     200 simulations), leaf buffers and captured graphs are reused by every later self-play / arena / policy call on that network
@@ -214,7 +225,7 @@ def searcher_for(evaluator, sims, device=None):
     dev = gl._dev(device)
     if not hasattr(evaluator, "flat_parameters"):
         return BatchedMCTS(evaluator, sims, device=dev)
-    cache = evaluator.__dict__.setdefault("_searchers", {})
+    cache = evaluator.__dict__.setdefault("_searchers", _SearcherCache())
     key = (int(sims), str(dev))
     if key not in cache:
         if len(cache) >= 4:
